@@ -1,0 +1,200 @@
+/*
+ * vqa.h -- C ABI of the B200-native dense-retrieval engine (libvqa_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * vTuanpham/Vietnamese_QA_System that this repository accelerates: scoring
+ * query embeddings against the document-embedding index and returning the top-k
+ * passages (reference call sites: inference_pipeline/db_utils/heavy_ranker.py:78-101).
+ *
+ * The reference is 100 % Python and has NO native interface of its own; the
+ * arithmetic it calls lives in third-party txtai -> faiss-cpu.  Each entry point
+ * below therefore cites the reference line (or the txtai backend method called
+ * from that line) whose work it replaces.  A Python maintainer binds these with
+ * ctypes (INTEGRATION.md shows the stub); nothing in the signatures is a torch
+ * type -- plain pointers, sizes and a CUDA stream handle passed as void*.
+ *
+ * Conventions
+ *   - every function returns a vqa_status (0 = OK, negative = error) and never
+ *     throws or aborts; vqa_last_error() returns a thread-local message.
+ *   - all *_dev pointers are device pointers on the index's device; the engine
+ *     BORROWS them (the caller -- PyTorch in the shipped host layer -- owns all
+ *     device memory).  All device work is stream-ordered on `stream`.
+ *   - vqa_search performs no allocation and no host synchronisation: the caller
+ *     passes a workspace of vqa_workspace_bytes() bytes, so a search is CUDA-graph
+ *     capturable.
+ *   - ordering everywhere: score descending, ties -> lower doc id
+ *     (BASELINE.json north_star; txtai NumPy backend's stable sort).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns VQA_E_CUDA.
+ */
+#ifndef VQA_H_
+#define VQA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VQA_API __declspec(dllexport)
+#else
+#define VQA_API __attribute__((visibility("default")))
+#endif
+
+#define VQA_VERSION 100 /* 0.1.0 */
+
+typedef enum vqa_status {
+    VQA_OK = 0,
+    VQA_E_INVALID = -1,     /* bad argument (shape, dtype, alignment, k)        */
+    VQA_E_CUDA = -2,        /* CUDA runtime / driver error, or no device        */
+    VQA_E_UNSUPPORTED = -3, /* valid request the engine does not implement yet  */
+    VQA_E_NOMEM = -4        /* workspace too small / host allocation failure    */
+} vqa_status;
+
+typedef enum vqa_dtype {
+    VQA_F32 = 0,
+    VQA_BF16 = 1,
+    VQA_F16 = 2,
+    VQA_I64 = 3, /* masks only */
+    VQA_I32 = 4, /* masks only */
+    VQA_U8 = 5   /* masks only (bool) */
+} vqa_dtype;
+
+typedef enum vqa_mode {
+    /* fp32 arithmetic in the canonical FMA / butterfly order:
+     * ids bit-identical to the CPU oracle, works for fp32 / bf16 / fp16 rows. */
+    VQA_MODE_VERIFY = 0,
+    /* free summation order; engine picks the HBM-streaming CUDA-core kernel
+     * (small batches) or the tcgen05/TMEM tensor-core kernel (large batches). */
+    VQA_MODE_FAST = 1,
+    /* FAST, but force one kernel family (benchmarks / tests). */
+    VQA_MODE_FAST_STREAM = 2,
+    VQA_MODE_FAST_TENSOR = 3
+} vqa_mode;
+
+typedef struct vqa_index vqa_index_t; /* opaque */
+
+/* Library version (VQA_VERSION). */
+VQA_API int vqa_version(void);
+
+/* Thread-local message for the last non-OK status returned on this thread. */
+VQA_API const char *vqa_last_error(void);
+
+/* Number of visible CUDA devices (0 when there is no driver / GPU).  Never fails. */
+VQA_API int vqa_device_count(void);
+
+/*
+ * Create an index descriptor for one row shard.
+ * Replaces: txtai ANN backend construction under Embeddings.index()/load()
+ *           (heavy_ranker.py:86,88,91-94).
+ *   n_rows           rows (documents) in THIS shard
+ *   dim              embedding dimension; dim * sizeof(dtype) must be a multiple of 16
+ *   dtype            storage type of the rows: VQA_F32 | VQA_BF16 | VQA_F16
+ *   device           CUDA device ordinal holding the rows
+ *   first_global_id  position of this shard's row 0 in the whole index
+ *                    (rank r of G holds rows [r*ceil(N/G), ...))
+ */
+VQA_API int vqa_index_create(vqa_index_t **out, int64_t n_rows, int32_t dim, int32_t dtype,
+                             int32_t device, int64_t first_global_id);
+
+/*
+ * Bind (borrow) the caller's device buffer holding the shard, row-major,
+ * `row_stride_bytes` between rows (>= dim*sizeof(dtype), multiple of 16, base
+ * 16-byte aligned).  Builds the TMA tensor map used by the tensor-core kernel.
+ * Replaces: faiss add_with_ids under Embeddings.index() (heavy_ranker.py:86,88).
+ */
+VQA_API int vqa_index_bind(vqa_index_t *h, const void *rows_dev, int64_t n_rows,
+                           int64_t row_stride_bytes);
+
+VQA_API int vqa_index_destroy(vqa_index_t *h);
+
+/* Bytes of device workspace vqa_search needs for a batch of `n_queries`, top `k`. */
+VQA_API int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode,
+                                size_t *bytes);
+
+/*
+ * Score `n_queries` query embeddings against the shard and select the top k.
+ * Replaces: txtai ann.search(queries, limit) -> faiss index.search under
+ *           Embeddings.search()/batchsearch() (heavy_ranker.py:98,100).
+ *   queries_dev   float32 [n_queries, dim] row-major, already L2-normalised
+ *                 (stride q_stride elements between rows)
+ *   k             1..128
+ *   out_scores_dev float32 [n_queries, k]  descending
+ *   out_ids_dev    int64   [n_queries, k]  first_global_id + row position;
+ *                  slots beyond the shard's row count: score -inf, id -1
+ * The [n_queries, n_rows] score matrix is never written to memory.
+ */
+VQA_API int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
+                       int32_t n_queries, int32_t k, int32_t mode, float *out_scores_dev,
+                       int64_t *out_ids_dev, void *workspace_dev, size_t workspace_bytes,
+                       void *stream);
+
+/*
+ * Same search with HOST buffers: H2D copy of the queries, search, D2H copy of
+ * the results, stream-synchronised before returning.  `staging_dev` must hold
+ * vqa_search_host_staging_bytes() bytes.  This is the call the reference-facing
+ * plugin makes for numpy inputs (heavy_ranker.py:98-101 receives host lists).
+ */
+VQA_API int vqa_search_host_staging_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k,
+                                          int32_t mode, size_t *bytes);
+VQA_API int vqa_search_host(const vqa_index_t *h, const float *queries_host, int32_t n_queries,
+                            int32_t k, int32_t mode, float *out_scores_host,
+                            int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
+                            void *stream);
+
+/*
+ * Merge `n_lists` candidate lists per query (the row shards' results after the
+ * all-gather) into the global top k_out.  Padding entries have id < 0.
+ * Replaces: nothing in the reference (single process); it is the exchange step
+ *           of the row-sharded engine.
+ *   cand_*_dev layout [n_lists, n_queries, k_in]
+ */
+VQA_API int vqa_merge_topk(const float *cand_scores_dev, const int64_t *cand_ids_dev,
+                           int32_t n_lists, int32_t n_queries, int32_t k_in, int32_t k_out,
+                           float *out_scores_dev, int64_t *out_ids_dev, int32_t device,
+                           void *stream);
+
+/*
+ * Fused masked mean-pool (+ optional L2 normalise) over encoder hidden states:
+ *   e[b,:] = sum_s h[b,s,:]*m[b,s] / max(sum_s m[b,s], 1e-9);  e /= ||e||_2
+ * Replaces: txtai MeanPooling.forward + normalize under Embeddings.search()/
+ *           index() (heavy_ranker.py:86,88,98,100; in-tree twin src/test.py:97-99).
+ *   hidden_dev [B,S,D] h_dtype (F32|BF16|F16), contiguous;  mask_dev [B,S]
+ *   m_dtype (I64|I32|U8|F32);  out_dev [B,D] float32.
+ */
+VQA_API int vqa_pool_normalize(const void *hidden_dev, int32_t h_dtype, const void *mask_dev,
+                               int32_t m_dtype, int32_t batch, int32_t seq, int32_t dim,
+                               int32_t normalize, float *out_dev, int32_t device, void *stream);
+
+/*
+ * Row-wise L2 normalise float32 [n,dim] (in place allowed) and optionally cast
+ * into a second buffer of `cast_dtype` (the index storage type).  Zero rows stay 0.
+ * Replaces: txtai normalize (numpy, in place) under Embeddings.index()/search().
+ *   cast_out_dev may be NULL; row strides in elements.
+ */
+VQA_API int vqa_normalize_rows(const float *in_dev, int64_t in_stride, int64_t n_rows, int32_t dim,
+                               float *out_dev, int64_t out_stride, void *cast_out_dev,
+                               int32_t cast_dtype, int64_t cast_stride, int32_t device,
+                               void *stream);
+
+/*
+ * Two-index agreement rule, batched (heavy_ranker.py:110):
+ *   accept[i] = ids_a[i] == ids_b[i] && scores_a[i] + scores_b[i] > threshold
+ * combined[i] = scores_a[i] + scores_b[i].  All device pointers, length n.
+ */
+VQA_API int vqa_agree(const int64_t *ids_a_dev, const float *scores_a_dev,
+                      const int64_t *ids_b_dev, const float *scores_b_dev, int64_t n,
+                      double threshold, uint8_t *accept_dev, float *combined_dev, int32_t device,
+                      void *stream);
+
+/* Introspection used by bench/tests: which kernel family a FAST search would use
+ * (VQA_MODE_FAST_STREAM or VQA_MODE_FAST_TENSOR), how many kernels one search launches. */
+VQA_API int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode,
+                            int32_t *family, int32_t *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_H_ */

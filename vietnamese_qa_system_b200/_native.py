@@ -1,0 +1,124 @@
+"""ctypes binding of libvqa_b200.so (include/vqa.h).
+
+The library is the product's only compute path.  There is NO CPU fallback: if the
+shared object is missing and cannot be built, or a compute entry point is called
+without a CUDA device, this module raises -- it never routes anywhere else.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvqa_b200.so")
+
+# vqa_status
+OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
+# vqa_dtype
+F32, BF16, F16, I64, I32, U8 = 0, 1, 2, 3, 4, 5
+# vqa_mode
+MODE_VERIFY, MODE_FAST, MODE_FAST_STREAM, MODE_FAST_TENSOR = 0, 1, 2, 3
+
+MODES = {"verify": MODE_VERIFY, "fp32": MODE_VERIFY, "fast": MODE_FAST, "stream": MODE_FAST_STREAM,
+         "tensor": MODE_FAST_TENSOR}
+
+EXPORTS = [
+    "vqa_version", "vqa_last_error", "vqa_device_count", "vqa_index_create", "vqa_index_bind",
+    "vqa_index_destroy", "vqa_workspace_bytes", "vqa_search", "vqa_search_host_staging_bytes",
+    "vqa_search_host", "vqa_merge_topk", "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
+    "vqa_search_plan",
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class VqaError(RuntimeError):
+    """CUDA / driver failure reported by the native library."""
+
+
+def _bind(L: ctypes.CDLL) -> None:
+    c = ctypes
+    vp, i32, i64, sz = c.c_void_p, c.c_int32, c.c_int64, c.c_size_t
+    L.vqa_version.restype = c.c_int
+    L.vqa_version.argtypes = []
+    L.vqa_last_error.restype = c.c_char_p
+    L.vqa_last_error.argtypes = []
+    L.vqa_device_count.restype = c.c_int
+    L.vqa_device_count.argtypes = []
+    L.vqa_index_create.restype = c.c_int
+    L.vqa_index_create.argtypes = [c.POINTER(vp), i64, i32, i32, i32, i64]
+    L.vqa_index_bind.restype = c.c_int
+    L.vqa_index_bind.argtypes = [vp, vp, i64, i64]
+    L.vqa_index_destroy.restype = c.c_int
+    L.vqa_index_destroy.argtypes = [vp]
+    L.vqa_workspace_bytes.restype = c.c_int
+    L.vqa_workspace_bytes.argtypes = [vp, i32, i32, i32, c.POINTER(sz)]
+    L.vqa_search.restype = c.c_int
+    L.vqa_search.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp, vp, sz, vp]
+    L.vqa_search_host_staging_bytes.restype = c.c_int
+    L.vqa_search_host_staging_bytes.argtypes = [vp, i32, i32, i32, c.POINTER(sz)]
+    L.vqa_search_host.restype = c.c_int
+    L.vqa_search_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
+    L.vqa_merge_topk.restype = c.c_int
+    L.vqa_merge_topk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.vqa_pool_normalize.restype = c.c_int
+    L.vqa_pool_normalize.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]
+    L.vqa_normalize_rows.restype = c.c_int
+    L.vqa_normalize_rows.argtypes = [vp, i64, i64, i32, vp, i64, vp, i32, i64, i32, vp]
+    L.vqa_agree.restype = c.c_int
+    L.vqa_agree.argtypes = [vp, vp, vp, vp, i64, c.c_double, vp, vp, i32, vp]
+    L.vqa_search_plan.restype = c.c_int
+    L.vqa_search_plan.argtypes = [vp, i32, i32, i32, c.POINTER(i32), c.POINTER(i32)]
+
+
+def lib() -> ctypes.CDLL:
+    """Load (building first if the .so is absent) the native library.  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                from . import build as _build  # needs nvcc; raises if it cannot build
+
+                _build.build()
+            try:
+                L = ctypes.CDLL(LIB_PATH)
+            except OSError as exc:  # pragma: no cover - depends on the box
+                raise RuntimeError(
+                    f"cannot load {LIB_PATH}: {exc}. The CUDA extension is the only compute path of this "
+                    "package (no CPU fallback); build it with `python -m vietnamese_qa_system_b200.build`."
+                ) from exc
+            _bind(L)
+            _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().vqa_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int) -> None:
+    """Map a vqa_status to the Python exception the reference-facing API documents."""
+    if status == OK:
+        return
+    msg = last_error()
+    if status == E_INVALID:
+        raise ValueError(msg)
+    if status == E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if status == E_NOMEM:
+        raise MemoryError(msg)
+    raise VqaError(msg)
+
+
+def device_count() -> int:
+    return int(lib().vqa_device_count())
+
+
+def require_cuda() -> None:
+    if device_count() == 0:
+        raise VqaError("no CUDA device available: vietnamese_qa_system_b200 has no CPU fallback")

@@ -1,0 +1,61 @@
+"""Build libvqa_b200.so in-tree with nvcc for sm_100a (no GPU needed to compile)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libvqa_b200.so")
+SOURCES = ["api.cu", "misc_launch.cu", "scan_f32.cu", "scan_bf16.cu", "scan_f16.cu", "mma_launch.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libvqa_b200.so cannot be built")
+
+
+def _deps_mtime() -> float:
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    paths.append(os.path.join(HERE, "..", "include", "vqa.h"))
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source with -gencode arch=compute_100a,code=sm_100a -lineinfo."""
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(BUILD, exist_ok=True)
+    flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
+             "-Xptxas", "-v" if verbose else "-warn-spills"] + ARCH
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj] + flags
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

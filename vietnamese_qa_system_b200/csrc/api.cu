@@ -1,0 +1,500 @@
+// api.cu -- the C ABI of libvqa_b200.so (include/vqa.h): argument validation,
+// kernel-family dispatch, launches.  No torch types, no hidden allocations in
+// the search path, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/vqa.h"
+#include "launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(VQA_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),     \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+int elem_size(int dtype) {
+    switch (dtype) {
+        case VQA_F32: return 4;
+        case VQA_BF16: return 2;
+        case VQA_F16: return 2;
+        default: return 0;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+}  // namespace
+
+struct vqa_index {
+    int64_t n_rows = 0;
+    int dim = 0;
+    int dtype = 0;
+    int device = 0;
+    int64_t first_id = 0;
+    const void *rows = nullptr;
+    int64_t stride = 0;
+    int sm_count = 0;
+    int max_smem = 0;
+    bool tmap_ok = false;
+    alignas(64) CUtensorMap tmap;
+};
+
+namespace {
+
+// ---- planning -----------------------------------------------------------------
+struct Plan {
+    int family;   // VQA_MODE_FAST_STREAM (also verify) or VQA_MODE_FAST_TENSOR
+    int pass_nq;  // queries per pass
+    int ncol;     // tensor: MMA N
+    int stages;   // tensor: smem ring depth
+    int passes;
+    int grid;
+};
+
+bool tensor_eligible(const vqa_index *h) {
+    return h->tmap_ok && (h->dtype == VQA_BF16 || h->dtype == VQA_F16) && h->dim % 64 == 0 && h->dim >= 64;
+}
+
+// pick the widest MMA N (<= what the batch needs) whose smem ring still has >= 4 stages
+bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
+    const int cands[3] = {64, 32, 16};
+    int want = nq * 2;  // hi + lo columns
+    for (int ci = 0; ci < 3; ++ci) {
+        int ncol = cands[ci];
+        if (ci < 2 && cands[ci + 1] >= want) continue;  // a narrower tile still covers the batch
+        size_t fixed = vqa::mma_smem_bytes_rt(ncol, h->dim, k, 0);
+        if (fixed >= (size_t)h->max_smem) continue;
+        int stages = (int)(((size_t)h->max_smem - fixed) / vqa::kStageBytes);
+        if (stages > vqa::kMaxStages) stages = vqa::kMaxStages;
+        if (stages < 4) continue;
+        pl->family = VQA_MODE_FAST_TENSOR;
+        pl->ncol = ncol;
+        pl->pass_nq = ncol / 2;
+        pl->stages = stages;
+        pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
+        long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
+        pl->grid = (int)(tiles < h->sm_count ? (tiles > 0 ? tiles : 1) : h->sm_count);
+        return true;
+    }
+    return false;
+}
+
+void plan_stream(const vqa_index *h, int nq, Plan *pl) {
+    pl->family = VQA_MODE_FAST_STREAM;
+    pl->pass_nq = nq >= 5 ? 8 : (nq >= 3 ? 4 : (nq == 2 ? 2 : 1));
+    pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
+    pl->ncol = 0;
+    pl->stages = 0;
+    pl->grid = h->sm_count;
+}
+
+int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
+    if (mode == VQA_MODE_VERIFY || mode == VQA_MODE_FAST_STREAM) {
+        plan_stream(h, nq, pl);
+        return VQA_OK;
+    }
+    if (mode == VQA_MODE_FAST_TENSOR) {
+        if (!tensor_eligible(h) || !plan_tensor(h, nq, k, pl))
+            return fail(VQA_E_UNSUPPORTED,
+                        "tensor-core path needs bf16/fp16 rows, dim %% 64 == 0 and a bound index (dim=%d dtype=%d)",
+                        h->dim, h->dtype);
+        return VQA_OK;
+    }
+    if (mode == VQA_MODE_FAST) {
+        // CUDA-core FMA keeps up with HBM only for a handful of queries per streamed
+        // element; beyond that the contraction goes to the tensor cores.
+        if (nq > 4 && tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
+        plan_stream(h, nq, pl);
+        return VQA_OK;
+    }
+    return fail(VQA_E_INVALID, "unknown mode %d", mode);
+}
+
+int check_search_args(const vqa_index *h, int nq, int k) {
+    if (!h) return fail(VQA_E_INVALID, "null index handle");
+    if (nq < 1) return fail(VQA_E_INVALID, "n_queries must be >= 1 (got %d)", nq);
+    if (k < 1 || k > vqa::kMaxK) return fail(VQA_E_INVALID, "k must be in [1, %d] (got %d)", vqa::kMaxK, k);
+    return VQA_OK;
+}
+
+size_t cand_elems(const vqa_index *h, int nq, int k) { return (size_t)h->sm_count * nq * k; }
+
+}  // namespace
+
+// =================================================================================
+extern "C" {
+
+int vqa_version(void) { return VQA_VERSION; }
+
+const char *vqa_last_error(void) { return g_err.c_str(); }
+
+int vqa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int vqa_index_create(vqa_index_t **out, int64_t n_rows, int32_t dim, int32_t dtype, int32_t device,
+                     int64_t first_global_id) {
+    if (!out) return fail(VQA_E_INVALID, "out is null");
+    *out = nullptr;
+    const int es = elem_size(dtype);
+    if (!es) return fail(VQA_E_INVALID, "row dtype must be F32, BF16 or F16 (got %d)", dtype);
+    if (n_rows < 0 || n_rows > 0x7fffffffLL)
+        return fail(VQA_E_INVALID, "n_rows per shard must be in [0, 2^31) (got %lld)", (long long)n_rows);
+    if (dim < 1 || ((int64_t)dim * es) % 16 != 0)
+        return fail(VQA_E_INVALID, "dim*sizeof(dtype) must be a positive multiple of 16 bytes (dim=%d)", dim);
+    if (dim > 8192) return fail(VQA_E_UNSUPPORTED, "dim > 8192 not supported (dim=%d)", dim);
+    int ndev = vqa_device_count();
+    if (ndev == 0) return fail(VQA_E_CUDA, "no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(VQA_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+    vqa_index *h = new (std::nothrow) vqa_index();
+    if (!h) return fail(VQA_E_NOMEM, "host allocation failed");
+    h->n_rows = n_rows;
+    h->dim = dim;
+    h->dtype = dtype;
+    h->device = device;
+    h->first_id = first_global_id;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(VQA_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        delete h;
+        return fail(VQA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    *out = h;
+    return VQA_OK;
+}
+
+int vqa_index_bind(vqa_index_t *h, const void *rows_dev, int64_t n_rows, int64_t row_stride_bytes) {
+    if (!h) return fail(VQA_E_INVALID, "null index handle");
+    const int es = elem_size(h->dtype);
+    if (n_rows != h->n_rows)
+        return fail(VQA_E_INVALID, "n_rows mismatch: created with %lld, bound %lld", (long long)h->n_rows,
+                    (long long)n_rows);
+    if (n_rows > 0 && !rows_dev) return fail(VQA_E_INVALID, "rows_dev is null");
+    if (row_stride_bytes < (int64_t)h->dim * es || row_stride_bytes % 16 != 0)
+        return fail(VQA_E_INVALID, "row_stride_bytes must be >= dim*sizeof and a multiple of 16 (got %lld)",
+                    (long long)row_stride_bytes);
+    if (reinterpret_cast<uintptr_t>(rows_dev) % 16 != 0) return fail(VQA_E_INVALID, "rows_dev must be 16-byte aligned");
+    h->rows = rows_dev;
+    h->stride = row_stride_bytes;
+    h->tmap_ok = false;
+    if (n_rows > 0 && es == 2 && h->dim % 64 == 0) {
+        EncodeTiledFn enc = get_encode_fn();
+        if (enc) {
+            cuuint64_t gdim[2] = {(cuuint64_t)h->dim, (cuuint64_t)n_rows};
+            cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
+            cuuint32_t box[2] = {(cuuint32_t)vqa::kBlockK, (cuuint32_t)vqa::kTileRows};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&h->tmap, h->dtype == VQA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                            : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                             2, const_cast<void *>(rows_dev), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            h->tmap_ok = (r == CUDA_SUCCESS);
+        }
+    }
+    return VQA_OK;
+}
+
+int vqa_index_destroy(vqa_index_t *h) {
+    delete h;
+    return VQA_OK;
+}
+
+int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode, int32_t *family,
+                    int32_t *n_launches) {
+    int rc = check_search_args(h, n_queries, k);
+    if (rc) return rc;
+    Plan pl;
+    rc = make_plan(h, n_queries, k, mode, &pl);
+    if (rc) return rc;
+    if (family) *family = pl.family;
+    if (n_launches) *n_launches = pl.passes + 1;
+    return VQA_OK;
+}
+
+int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode, size_t *bytes) {
+    int rc = check_search_args(h, n_queries, k);
+    if (rc) return rc;
+    if (!bytes) return fail(VQA_E_INVALID, "bytes is null");
+    (void)mode;
+    // candidates: per CTA, per query, k entries of (float score, u32 row)
+    *bytes = cand_elems(h, n_queries, k) * 8 + 256;
+    return VQA_OK;
+}
+
+int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride, int32_t n_queries, int32_t k,
+               int32_t mode, float *out_scores_dev, int64_t *out_ids_dev, void *workspace_dev,
+               size_t workspace_bytes, void *stream) {
+    int rc = check_search_args(h, n_queries, k);
+    if (rc) return rc;
+    if (!queries_dev || !out_scores_dev || !out_ids_dev || !workspace_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (h->n_rows > 0 && !h->rows) return fail(VQA_E_INVALID, "index has no bound rows (call vqa_index_bind)");
+    if (q_stride < h->dim || q_stride % 4 != 0 || reinterpret_cast<uintptr_t>(queries_dev) % 16 != 0)
+        return fail(VQA_E_INVALID, "queries must be 16-byte aligned with q_stride >= dim and q_stride %% 4 == 0");
+    size_t need = 0;
+    vqa_workspace_bytes(h, n_queries, k, mode, &need);
+    if (workspace_bytes < need)
+        return fail(VQA_E_NOMEM, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    Plan pl;
+    rc = make_plan(h, n_queries, k, mode, &pl);
+    if (rc) return rc;
+
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    uintptr_t ws = (reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~(uintptr_t)255;
+    float *cand_s = reinterpret_cast<float *>(ws);
+    uint32_t *cand_i = reinterpret_cast<uint32_t *>(cand_s + cand_elems(h, n_queries, k));
+    const long long cand_stride = (long long)n_queries * k;
+
+    int n_lists = 0;
+    if (h->n_rows > 0) {
+        n_lists = pl.grid;
+        for (int p0 = 0; p0 < n_queries; p0 += pl.pass_nq) {
+            const int nq = n_queries - p0 < pl.pass_nq ? n_queries - p0 : pl.pass_nq;
+            cudaError_t e;
+            if (pl.family == VQA_MODE_FAST_TENSOR) {
+                vqa::MmaLaunch a;
+                a.tmap = &h->tmap;
+                a.bf16 = h->dtype == VQA_BF16;
+                a.ncol = pl.ncol;
+                a.stages = pl.stages;
+                a.grid = pl.grid;
+                a.q = queries_dev + (long long)p0 * q_stride;
+                a.q_stride = q_stride;
+                a.nq = nq;
+                a.k = k;
+                a.n_rows = h->n_rows;
+                a.dim = h->dim;
+                a.cand_s = cand_s + (long long)p0 * k;
+                a.cand_i = cand_i + (long long)p0 * k;
+                a.cand_stride = cand_stride;
+                e = vqa::launch_mma(a, st);
+            } else {
+                vqa::ScanLaunch a;
+                a.dtype = h->dtype;
+                a.bt = pl.pass_nq;
+                a.grid = pl.grid;
+                a.rows = h->rows;
+                a.n_rows = h->n_rows;
+                a.row_stride_bytes = h->stride;
+                a.dim = h->dim;
+                a.q = queries_dev + (long long)p0 * q_stride;
+                a.q_stride = q_stride;
+                a.nq = nq;
+                a.k = k;
+                a.cand_s = cand_s + (long long)p0 * k;
+                a.cand_i = cand_i + (long long)p0 * k;
+                a.cand_stride = cand_stride;
+                e = vqa::launch_scan(a, st);
+            }
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaError_t e = vqa::launch_reduce_u32(cand_s, cand_i, cand_stride, k, n_lists, k, k, h->first_id,
+                                           out_scores_dev, (long long *)out_ids_dev, n_queries, st);
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_search_host_staging_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode,
+                                  size_t *bytes) {
+    size_t ws = 0;
+    int rc = vqa_workspace_bytes(h, n_queries, k, mode, &ws);
+    if (rc) return rc;
+    size_t q = ((size_t)n_queries * h->dim * 4 + 255) & ~(size_t)255;
+    size_t os = ((size_t)n_queries * k * 4 + 255) & ~(size_t)255;
+    size_t oi = ((size_t)n_queries * k * 8 + 255) & ~(size_t)255;
+    *bytes = q + os + oi + ws + 256;
+    return VQA_OK;
+}
+
+int vqa_search_host(const vqa_index_t *h, const float *queries_host, int32_t n_queries, int32_t k, int32_t mode,
+                    float *out_scores_host, int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
+                    void *stream) {
+    size_t need = 0;
+    int rc = vqa_search_host_staging_bytes(h, n_queries, k, mode, &need);
+    if (rc) return rc;
+    if (!queries_host || !out_scores_host || !out_ids_host || !staging_dev)
+        return fail(VQA_E_INVALID, "null pointer argument");
+    if (staging_bytes < need)
+        return fail(VQA_E_NOMEM, "staging too small: need %zu bytes, got %zu", need, staging_bytes);
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uintptr_t base = (reinterpret_cast<uintptr_t>(staging_dev) + 255) & ~(uintptr_t)255;
+    size_t qb = ((size_t)n_queries * h->dim * 4 + 255) & ~(size_t)255;
+    size_t osb = ((size_t)n_queries * k * 4 + 255) & ~(size_t)255;
+    size_t oib = ((size_t)n_queries * k * 8 + 255) & ~(size_t)255;
+    float *q_dev = reinterpret_cast<float *>(base);
+    float *os_dev = reinterpret_cast<float *>(base + qb);
+    int64_t *oi_dev = reinterpret_cast<int64_t *>(base + qb + osb);
+    void *ws = reinterpret_cast<void *>(base + qb + osb + oib);
+    size_t ws_bytes = staging_bytes - (size_t)(reinterpret_cast<uintptr_t>(ws) - reinterpret_cast<uintptr_t>(staging_dev));
+    CUDA_TRY(cudaMemcpyAsync(q_dev, queries_host, (size_t)n_queries * h->dim * 4, cudaMemcpyHostToDevice, st));
+    rc = vqa_search(h, q_dev, h->dim, n_queries, k, mode, os_dev, oi_dev, ws, ws_bytes, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_scores_host, os_dev, (size_t)n_queries * k * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_ids_host, oi_dev, (size_t)n_queries * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VQA_OK;
+}
+
+int vqa_merge_topk(const float *cand_scores_dev, const int64_t *cand_ids_dev, int32_t n_lists, int32_t n_queries,
+                   int32_t k_in, int32_t k_out, float *out_scores_dev, int64_t *out_ids_dev, int32_t device,
+                   void *stream) {
+    if (!cand_scores_dev || !cand_ids_dev || !out_scores_dev || !out_ids_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (n_lists < 1 || n_queries < 1 || k_in < 1) return fail(VQA_E_INVALID, "n_lists, n_queries, k_in must be >= 1");
+    if (k_out < 1 || k_out > vqa::kMaxK) return fail(VQA_E_INVALID, "k_out must be in [1, %d]", vqa::kMaxK);
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_reduce_i64(cand_scores_dev, (const long long *)cand_ids_dev,
+                                           (long long)n_queries * k_in, k_in, n_lists, k_in, k_out, 0,
+                                           out_scores_dev, (long long *)out_ids_dev, n_queries,
+                                           reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_pool_normalize(const void *hidden_dev, int32_t h_dtype, const void *mask_dev, int32_t m_dtype,
+                       int32_t batch, int32_t seq, int32_t dim, int32_t normalize, float *out_dev, int32_t device,
+                       void *stream) {
+    if (!hidden_dev || !mask_dev || !out_dev) return fail(VQA_E_INVALID, "null device pointer argument");
+    const int es = elem_size(h_dtype);
+    if (!es) return fail(VQA_E_INVALID, "hidden dtype must be F32, BF16 or F16 (got %d)", h_dtype);
+    if (m_dtype != VQA_I64 && m_dtype != VQA_I32 && m_dtype != VQA_U8 && m_dtype != VQA_F32)
+        return fail(VQA_E_INVALID, "mask dtype must be I64, I32, U8 or F32 (got %d)", m_dtype);
+    if (batch < 1 || seq < 1) return fail(VQA_E_INVALID, "batch and seq must be >= 1");
+    if (dim < 1 || (dim * es) % 16 != 0 || dim > 8192)
+        return fail(VQA_E_INVALID, "dim*sizeof(dtype) must be a multiple of 16 bytes and dim <= 8192 (dim=%d)", dim);
+    if (reinterpret_cast<uintptr_t>(hidden_dev) % 16 != 0) return fail(VQA_E_INVALID, "hidden_dev must be 16-byte aligned");
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_pool(hidden_dev, h_dtype, mask_dev, m_dtype, batch, seq, dim, normalize, out_dev,
+                                     reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "pool launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_normalize_rows(const float *in_dev, int64_t in_stride, int64_t n_rows, int32_t dim, float *out_dev,
+                       int64_t out_stride, void *cast_out_dev, int32_t cast_dtype, int64_t cast_stride,
+                       int32_t device, void *stream) {
+    if (!in_dev) return fail(VQA_E_INVALID, "in_dev is null");
+    if (!out_dev && !cast_out_dev) return fail(VQA_E_INVALID, "no output buffer given");
+    if (n_rows < 0) return fail(VQA_E_INVALID, "n_rows must be >= 0");
+    if (dim < 4 || dim % 4 != 0) return fail(VQA_E_INVALID, "dim must be a positive multiple of 4 (dim=%d)", dim);
+    if (in_stride < dim || in_stride % 4 != 0 || (out_dev && (out_stride < dim || out_stride % 4 != 0)))
+        return fail(VQA_E_INVALID, "row strides must be >= dim and multiples of 4 elements");
+    if (reinterpret_cast<uintptr_t>(in_dev) % 16 != 0 || reinterpret_cast<uintptr_t>(out_dev) % 16 != 0)
+        return fail(VQA_E_INVALID, "buffers must be 16-byte aligned");
+    int cast_kind = 0;
+    if (cast_out_dev) {
+        if (cast_dtype == VQA_BF16) cast_kind = 1;
+        else if (cast_dtype == VQA_F16) cast_kind = 2;
+        else return fail(VQA_E_INVALID, "cast dtype must be BF16 or F16 (got %d)", cast_dtype);
+        if (cast_stride < dim || cast_stride % 4 != 0 || reinterpret_cast<uintptr_t>(cast_out_dev) % 8 != 0)
+            return fail(VQA_E_INVALID, "cast buffer must be 8-byte aligned with stride >= dim, multiple of 4");
+    }
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    if (n_rows == 0) return VQA_OK;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_normalize(in_dev, in_stride, n_rows, dim, out_dev, out_stride, cast_out_dev,
+                                          cast_kind, cast_stride, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "normalize launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_agree(const int64_t *ids_a_dev, const float *scores_a_dev, const int64_t *ids_b_dev,
+              const float *scores_b_dev, int64_t n, double threshold, uint8_t *accept_dev, float *combined_dev,
+              int32_t device, void *stream) {
+    if (!ids_a_dev || !scores_a_dev || !ids_b_dev || !scores_b_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (n < 0) return fail(VQA_E_INVALID, "n must be >= 0");
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    if (n == 0) return VQA_OK;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_agree((const long long *)ids_a_dev, scores_a_dev, (const long long *)ids_b_dev,
+                                      scores_b_dev, n, threshold, accept_dev, combined_dev,
+                                      reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "agree launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+// consts.h -- compile-time constants shared by host dispatch and device code.
+#pragma once
+#include <stddef.h>
+
+namespace vqa {
+
+constexpr int kMaxK = 128;                            // fused top-k lists: up to 4 entries per lane
+constexpr int kMaxKpl = kMaxK / 32;
+
+// tensor-core path tile geometry
+constexpr int kMmaThreads = 192;
+constexpr int kTileRows = 128;                        // documents per MMA tile (UMMA M)
+constexpr int kBlockK = 64;                           // elements per k-block (128 bytes, one swizzle row)
+constexpr int kStageBytes = kTileRows * kBlockK * 2;  // 16 KB per TMA stage
+constexpr int kMaxStages = 12;
+constexpr int kMaxAccStages = 8;
+
+inline size_t list_bytes_rt(int nq, int k, int id_bytes) {
+    int kcap = ((k + 31) / 32) * 32;
+    return (size_t)nq * kcap * (4 + id_bytes) + (size_t)nq * 8;
+}
+// shared memory of the tensor-core kernel: [align slack][Q tiles][A ring][barriers][lists]
+inline size_t mma_smem_bytes_rt(int ncol, int dim, int k, int stages) {
+    return 1024 + (size_t)(dim / kBlockK) * ncol * 128 + (size_t)stages * kStageBytes + 1024 +
+           list_bytes_rt(ncol, k, 4);
+}
+
+}  // namespace vqa

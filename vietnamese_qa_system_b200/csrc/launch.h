@@ -1,0 +1,66 @@
+// launch.h -- host-side launch interface between api.cu and the kernel
+// translation units (one per storage type so they compile in parallel).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "consts.h"
+
+namespace vqa {
+
+struct ScanLaunch {
+    int dtype;  // vqa_dtype of the rows
+    int bt;     // queries per pass: 1, 2, 4, 8
+    int grid;
+    const void *rows;
+    long long n_rows;
+    long long row_stride_bytes;
+    int dim;
+    const float *q;
+    long long q_stride;
+    int nq;
+    int k;
+    float *cand_s;
+    uint32_t *cand_i;
+    long long cand_stride;
+};
+
+struct MmaLaunch {
+    const CUtensorMap *tmap;
+    bool bf16;
+    int ncol;
+    int stages;
+    int grid;
+    const float *q;
+    long long q_stride;
+    int nq;
+    int k;
+    long long n_rows;
+    int dim;
+    float *cand_s;
+    uint32_t *cand_i;
+    long long cand_stride;
+};
+
+cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st);
+cudaError_t launch_scan_f32(const ScanLaunch &a, cudaStream_t st);
+cudaError_t launch_scan_bf16(const ScanLaunch &a, cudaStream_t st);
+cudaError_t launch_scan_f16(const ScanLaunch &a, cudaStream_t st);
+cudaError_t launch_mma(const MmaLaunch &a, cudaStream_t st);
+
+cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
+                              long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                              float *out_s, long long *out_i, int n_queries, cudaStream_t st);
+cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
+                              long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                              float *out_s, long long *out_i, int n_queries, cudaStream_t st);
+cudaError_t launch_pool(const void *hidden, int h_dtype, const void *mask, int m_dtype, int batch, int seq,
+                        int dim, int normalize, float *out, cudaStream_t st);
+cudaError_t launch_normalize(const float *in, long long in_stride, long long n_rows, int dim, float *out,
+                             long long out_stride, void *cast_out, int cast_kind, long long cast_stride,
+                             cudaStream_t st);
+cudaError_t launch_agree(const long long *ids_a, const float *sa, const long long *ids_b, const float *sb,
+                         long long n, double threshold, unsigned char *accept, float *combined, cudaStream_t st);
+
+}  // namespace vqa

@@ -1,0 +1,109 @@
+// misc_launch.cu -- scan dispatch by dtype, cross-CTA / cross-rank reduce,
+// pooling, normalise, agreement rule.
+#include "../../include/vqa.h"
+#include "launch.h"
+#include "pool.cuh"
+#include "scan.cuh"
+
+namespace vqa {
+
+cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st) {
+    switch (a.dtype) {
+        case VQA_F32: return launch_scan_f32(a, st);
+        case VQA_BF16: return launch_scan_bf16(a, st);
+        case VQA_F16: return launch_scan_f16(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename IdT>
+static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long long list_stride,
+                                   long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                                   float *out_s, long long *out_i, int n_queries, cudaStream_t st) {
+    ReduceParams<IdT> p;
+    p.cand_s = cand_s;
+    p.cand_i = cand_i;
+    p.list_stride = list_stride;
+    p.query_stride = query_stride;
+    p.n_lists = n_lists;
+    p.k_in = k_in;
+    p.k_out = k_out;
+    p.id_base = id_base;
+    p.out_s = out_s;
+    p.out_i = out_i;
+    const size_t smem = list_smem_bytes<IdT>(1, k_out);
+    reduce_topk_kernel<IdT><<<n_queries, kReduceThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
+                              long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                              float *out_s, long long *out_i, int n_queries, cudaStream_t st) {
+    return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
+                                     out_i, n_queries, st);
+}
+cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
+                              long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                              float *out_s, long long *out_i, int n_queries, cudaStream_t st) {
+    return launch_reduce_t<long long>(cand_s, cand_i, list_stride, query_stride, n_lists, k_in, k_out, id_base,
+                                      out_s, out_i, n_queries, st);
+}
+
+template <typename T, typename MT>
+static cudaError_t launch_pool_tm(const void *hidden, const void *mask, int batch, int seq, int dim, int normalize,
+                                  float *out, cudaStream_t st) {
+    constexpr int E = Elem<T>::E;
+    const int nchunks = dim / E;
+    const int cw = nchunks < kPoolThreads ? nchunks : kPoolThreads;
+    const int G = kPoolThreads / cw;
+    const size_t smem = ((size_t)(G + 1) * dim + 32) * sizeof(float);
+    auto kern = pool_normalize_kernel<T, MT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<batch, kPoolThreads, smem, st>>>(static_cast<const unsigned char *>(hidden),
+                                           static_cast<const MT *>(mask), seq, dim, normalize, out);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_pool_t(const void *hidden, const void *mask, int m_dtype, int batch, int seq, int dim,
+                                 int normalize, float *out, cudaStream_t st) {
+    switch (m_dtype) {
+        case VQA_I64: return launch_pool_tm<T, long long>(hidden, mask, batch, seq, dim, normalize, out, st);
+        case VQA_I32: return launch_pool_tm<T, int>(hidden, mask, batch, seq, dim, normalize, out, st);
+        case VQA_U8: return launch_pool_tm<T, unsigned char>(hidden, mask, batch, seq, dim, normalize, out, st);
+        case VQA_F32: return launch_pool_tm<T, float>(hidden, mask, batch, seq, dim, normalize, out, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_pool(const void *hidden, int h_dtype, const void *mask, int m_dtype, int batch, int seq, int dim,
+                        int normalize, float *out, cudaStream_t st) {
+    switch (h_dtype) {
+        case VQA_F32: return launch_pool_t<float>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+        case VQA_BF16: return launch_pool_t<__nv_bfloat16>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+        case VQA_F16: return launch_pool_t<__half>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_normalize(const float *in, long long in_stride, long long n_rows, int dim, float *out,
+                             long long out_stride, void *cast_out, int cast_kind, long long cast_stride,
+                             cudaStream_t st) {
+    const int rows_per_block = 256 / 32;
+    const long long blocks = (n_rows + rows_per_block - 1) / rows_per_block;
+    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, in_stride, n_rows, dim, out, out_stride, cast_out,
+                                                           cast_kind, cast_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_agree(const long long *ids_a, const float *sa, const long long *ids_b, const float *sb,
+                         long long n, double threshold, unsigned char *accept, float *combined, cudaStream_t st) {
+    const long long blocks = (n + 255) / 256;
+    agree_kernel<<<(unsigned)blocks, 256, 0, st>>>(ids_a, sa, ids_b, sb, n, threshold, accept, combined);
+    return cudaGetLastError();
+}
+
+}  // namespace vqa

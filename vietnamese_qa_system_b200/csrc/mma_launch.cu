@@ -1,0 +1,47 @@
+// mma_launch.cu -- instantiations + launch of the tcgen05 tensor-core kernel.
+#include "launch.h"
+#include "mma.cuh"
+
+namespace vqa {
+
+template <bool BF16, int NCOL>
+static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
+    MmaParams p;
+    p.q = a.q;
+    p.q_stride = a.q_stride;
+    p.nq = a.nq;
+    p.k = a.k;
+    p.n_rows = a.n_rows;
+    p.dim = a.dim;
+    p.split = 1;
+    // fp16's 11-bit significand leaves a residual near its subnormal range: scale it up (exactly)
+    p.lo_scale = BF16 ? 1.0f : 2048.0f;
+    p.lo_inv_scale = BF16 ? 1.0f : 1.0f / 2048.0f;
+    p.cand_s = a.cand_s;
+    p.cand_i = a.cand_i;
+    p.cand_stride = a.cand_stride;
+    p.n_tiles = (int)((a.n_rows + kTileRows - 1) / kTileRows);
+    p.n_stages = a.stages;
+    const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages);
+    auto kern = mma_topk_kernel<BF16, NCOL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<a.grid, kMmaThreads, smem, st>>>(*a.tmap, p);
+    return cudaGetLastError();
+}
+
+template <bool BF16>
+static cudaError_t launch_mma_t(const MmaLaunch &a, cudaStream_t st) {
+    switch (a.ncol) {
+        case 16: return launch_mma_one<BF16, 16>(a, st);
+        case 32: return launch_mma_one<BF16, 32>(a, st);
+        case 64: return launch_mma_one<BF16, 64>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_mma(const MmaLaunch &a, cudaStream_t st) {
+    return a.bf16 ? launch_mma_t<true>(a, st) : launch_mma_t<false>(a, st);
+}
+
+}  // namespace vqa

@@ -1,0 +1,283 @@
+// scan.cuh -- K2a + K3: HBM-streaming similarity scan with fused top-k.
+//
+// Replaces faiss IndexFlatIP search (sgemm + heap) under txtai ann.search, i.e.
+// the work behind Embeddings.search at heavy_ranker.py:98,100, for SMALL query
+// batches where the pass over the document matrix is purely HBM-bound.
+//
+// One persistent CTA per SM.  Each warp streams R whole rows per step with
+// 128-bit no-allocate loads (lane l owns 16-byte chunks l, l+32, ... of a row),
+// multiplies against BT fp32 queries held in shared memory, reduces the 32
+// partials with the XOR butterfly (transposed, so R*BT values cost R*BT-1
+// shuffles instead of 5*R*BT), and offers a score to the CTA-shared top-k list
+// only when it beats that query's published threshold.  The [B,N] score matrix
+// never exists.  Arithmetic order is the canonical order of SURVEY.md App. C, so
+// in fp32 the scores are bit-identical to oracle.c's oracle_dot_canonical.
+//
+// Roofline: HBM.  Algorithmic bytes per launch = n_rows * dim * sizeof(T).
+#pragma once
+
+#include "common.cuh"
+
+namespace vqa {
+
+struct ScanParams {
+    const unsigned char *rows;
+    long long n_rows;
+    long long row_stride_bytes;
+    int dim;
+    const float *q;      // first query of this pass
+    long long q_stride;  // elements
+    int nq;              // queries in this pass (<= BT)
+    int k;
+    float *cand_s;       // [grid][cand_stride] ; this pass writes [.., nq*k) at its offset
+    uint32_t *cand_i;
+    long long cand_stride;  // elements between consecutive CTAs' blocks
+};
+
+constexpr int kScanThreads = 512;
+constexpr int kScanWarps = kScanThreads / 32;
+
+// Transposed XOR-butterfly reduction of NV per-lane partials across the warp.
+// Order of masks is 16,8,4,2,1 (canonical).  On return v[0] of lane l holds the
+// full sum of value index (l >> (5 - log2(NV))).
+template <int NV, int CNT, int M>
+struct TReduce {
+    __device__ __forceinline__ static void run(float (&v)[NV], int lane) {
+        if constexpr (CNT > 1) {
+            constexpr int half = CNT / 2;
+            const bool upper = (lane & M) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float keep = upper ? v[i + half] : v[i];
+                const float send = upper ? v[i] : v[i + half];
+                v[i] = __fadd_rn(keep, __shfl_xor_sync(kFullMask, send, M));
+            }
+            if constexpr (M > 1) TReduce<NV, half, M / 2>::run(v, lane);
+        } else {
+            v[0] = __fadd_rn(v[0], __shfl_xor_sync(kFullMask, v[0], M));
+            if constexpr (M > 1) TReduce<NV, 1, M / 2>::run(v, lane);
+        }
+    }
+};
+
+constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
+
+// shared-memory layout of one query, permuted so that lane l's float4 loads are
+// conflict free: float4 index = ((it * H + h) * 32 + lane), H = E/4.
+template <typename T>
+__host__ __device__ inline int scan_q_floats(int dim) {
+    constexpr int E = 16 / (int)sizeof(T);
+    int nchunks = dim / E;
+    int iters = (nchunks + 31) / 32;
+    return iters * 32 * E;
+}
+
+template <typename T, int BT>
+__host__ __device__ inline size_t scan_smem_bytes(int dim, int k) {
+    return (size_t)BT * scan_q_floats<T>(dim) * sizeof(float) + list_smem_bytes<uint32_t>(BT, k);
+}
+
+// ITERS > 0: dim*sizeof(T) == ITERS*512 exactly (fully unrolled, all loads of a
+// step in flight at once).  ITERS == 0: any dim with dim*sizeof(T) % 16 == 0.
+template <typename T, int BT, int R, int ITERS>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
+    constexpr int E = Elem<T>::E;
+    constexpr int H = E / 4;
+    constexpr int NV = R * BT;
+    static_assert(NV <= 32 && (NV & (NV - 1)) == 0, "R*BT must be a power of two <= 32");
+    constexpr int SH = 5 - ilog2(NV);  // lanes per value after the reduction
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nchunks = p.dim / E;
+    const int iters = ITERS > 0 ? ITERS : (nchunks + 31) / 32;
+    const int qfl = iters * 32 * E;
+
+    float4 *qs = reinterpret_cast<float4 *>(smem);
+    ListView<uint32_t> L = list_carve<uint32_t>(smem + (size_t)BT * qfl * sizeof(float), BT, p.k);
+    list_init(L, BT, tid, kScanThreads);
+
+    // stage the queries (zero-fill beyond nq / beyond dim)
+    for (int idx = tid; idx < BT * iters * H * 32; idx += kScanThreads) {
+        const int ln = idx & 31;
+        const int h = (idx >> 5) % H;
+        const int it = (idx / (32 * H)) % iters;
+        const int b = idx / (32 * H * iters);
+        const int chunk = it * 32 + ln;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < p.nq && chunk < nchunks)
+            v = *reinterpret_cast<const float4 *>(p.q + (long long)b * p.q_stride + chunk * E + h * 4);
+        qs[idx] = v;
+    }
+    __syncthreads();
+
+    const long long gw = (long long)blockIdx.x * kScanWarps + warp;
+    const long long nwarps = (long long)gridDim.x * kScanWarps;
+    const long long ngroups = (p.n_rows + R - 1) / R;
+
+    for (long long g = gw; g < ngroups; g += nwarps) {
+        const long long row0 = g * R;
+        float acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+
+        if constexpr (ITERS > 0) {
+            uint4 w[R][ITERS];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // rows past the end re-read the last row (their scores are discarded)
+                const long long row = row0 + r < p.n_rows ? row0 + r : p.n_rows - 1;
+                const unsigned char *rp = p.rows + row * p.row_stride_bytes + lane * 16;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) w[r][it] = ldg_stream(rp + it * 512);
+            }
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                float x[R][E];
+#pragma unroll
+                for (int r = 0; r < R; ++r) Elem<T>::unpack(w[r][it], x[r]);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) {
+                        const float4 qv = qs[((b * ITERS + it) * H + h) * 32 + lane];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            float a = acc[r * BT + b];
+                            a = __fmaf_rn(qv.x, x[r][h * 4 + 0], a);
+                            a = __fmaf_rn(qv.y, x[r][h * 4 + 1], a);
+                            a = __fmaf_rn(qv.z, x[r][h * 4 + 2], a);
+                            a = __fmaf_rn(qv.w, x[r][h * 4 + 3], a);
+                            acc[r * BT + b] = a;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int it = 0; it < iters; ++it) {
+                const int chunk = it * 32 + lane;
+                if (chunk < nchunks) {
+                    uint4 w[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const long long row = row0 + r < p.n_rows ? row0 + r : p.n_rows - 1;
+                        w[r] = ldg_stream(p.rows + row * p.row_stride_bytes + (long long)chunk * 16);
+                    }
+                    float x[R][E];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) Elem<T>::unpack(w[r], x[r]);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) {
+                            const float4 qv = qs[((b * iters + it) * H + h) * 32 + lane];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                float a = acc[r * BT + b];
+                                a = __fmaf_rn(qv.x, x[r][h * 4 + 0], a);
+                                a = __fmaf_rn(qv.y, x[r][h * 4 + 1], a);
+                                a = __fmaf_rn(qv.z, x[r][h * 4 + 2], a);
+                                a = __fmaf_rn(qv.w, x[r][h * 4 + 3], a);
+                                acc[r * BT + b] = a;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        TReduce<NV, NV, 16>::run(acc, lane);
+        const float sc = acc[0];
+        const int vi = lane >> SH;  // value index = r*BT + b
+        const int r = vi / BT;
+        const int b = vi % BT;
+        const long long row = row0 + r;
+        const bool rep = (lane & ((1 << SH) - 1)) == 0;
+        const float thr = *(volatile float *)(L.tau + b);
+        const bool pass = rep && row < p.n_rows && b < p.nq && sc >= thr;
+        unsigned m = __ballot_sync(kFullMask, pass);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cs = __shfl_sync(kFullMask, sc, src);
+            const int cvi = src >> SH;
+            list_insert<uint32_t>(L, cvi % BT, cs, (uint32_t)(row0 + cvi / BT));
+        }
+    }
+
+    __syncthreads();
+    // publish this CTA's lists: cand[cta][b][k]
+    float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride;
+    uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride;
+    for (int idx = tid; idx < p.nq * p.k; idx += kScanThreads) {
+        const int b = idx / p.k, e = idx % p.k;
+        cs[idx] = L.s[b * L.kcap + e];
+        ci[idx] = L.i[b * L.kcap + e];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Cross-CTA reduce: one CTA per query merges n_lists candidate lists of length
+// k_in (u32 local row index, or i64 global id for the cross-rank merge K4) into
+// the final top k_out, writes float32 scores and int64 ids (id_base + index).
+// ---------------------------------------------------------------------------
+constexpr int kReduceThreads = 256;
+
+template <typename IdT>
+struct ReduceParams {
+    const float *cand_s;
+    const IdT *cand_i;
+    long long list_stride;   // elements between lists
+    long long query_stride;  // elements between queries inside a list
+    int n_lists;
+    int k_in;
+    int k_out;
+    long long id_base;
+    float *out_s;     // [nq][k_out]
+    long long *out_i;
+};
+
+template <typename IdT>
+__global__ void __launch_bounds__(kReduceThreads) reduce_topk_kernel(const ReduceParams<IdT> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x;
+    ListView<IdT> L = list_carve<IdT>(smem, 1, p.k_out);
+    list_init(L, 1, tid, kReduceThreads);
+    __syncthreads();
+
+    const int kin_pad = ((p.k_in + 31) / 32) * 32;
+    for (int l = warp; l < p.n_lists; l += kReduceThreads / 32) {
+        const float *ls = p.cand_s + (long long)l * p.list_stride + (long long)q * p.query_stride;
+        const IdT *li = p.cand_i + (long long)l * p.list_stride + (long long)q * p.query_stride;
+        for (int e0 = 0; e0 < kin_pad; e0 += 32) {
+            const int e = e0 + lane;
+            float s = neg_inf();
+            IdT id = invalid_id<IdT>();
+            if (e < p.k_in) {
+                s = ls[e];
+                id = li[e];
+            }
+            bool valid = e < p.k_in && id != invalid_id<IdT>();
+            if constexpr (sizeof(IdT) == 8) valid = valid && id >= 0;
+            const float thr = *(volatile float *)L.tau;
+            unsigned m = __ballot_sync(kFullMask, valid && s >= thr);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                list_insert<IdT>(L, 0, __shfl_sync(kFullMask, s, src), shfl_any(id, src));
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < p.k_out; e += kReduceThreads) {
+        const IdT id = L.i[e];
+        const bool ok = id != invalid_id<IdT>();
+        p.out_s[(long long)q * p.k_out + e] = ok ? L.s[e] : neg_inf();
+        p.out_i[(long long)q * p.k_out + e] = ok ? (long long)id + p.id_base : -1LL;
+    }
+}
+
+}  // namespace vqa

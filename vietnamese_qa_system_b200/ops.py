@@ -1,0 +1,224 @@
+"""Tensor-level entry points over the C ABI.
+
+PyTorch is used for device memory, streams and nothing else: every function here
+hands raw device pointers (``tensor.data_ptr()``) and the current CUDA stream to
+``libvqa_b200.so``.  No function computes anything in torch, and none falls back
+to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_TORCH_TO_VQA = {torch.float32: N.F32, torch.bfloat16: N.BF16, torch.float16: N.F16}
+_MASK_TO_VQA = {torch.int64: N.I64, torch.int32: N.I32, torch.uint8: N.U8, torch.bool: N.U8, torch.float32: N.F32}
+DTYPES = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16,
+          "fp16": torch.float16, "float16": torch.float16}
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (this engine has no CPU path); got device {t.device}")
+
+
+def mode_id(mode) -> int:
+    if isinstance(mode, int):
+        return mode
+    try:
+        return N.MODES[str(mode).lower()]
+    except KeyError:
+        raise ValueError(f"unknown search mode {mode!r}; expected one of {sorted(N.MODES)}") from None
+
+
+class FlatShard:
+    """One row shard of the document-embedding matrix bound to a native index handle.
+
+    Replaces the faiss index object txtai keeps per ``Embeddings``
+    (reference call sites: heavy_ranker.py:86,88 build; :91-94 load; :98,100 search).
+    ``rows`` is borrowed by the native side; this object keeps it alive.
+    """
+
+    def __init__(self, rows: torch.Tensor, first_global_id: int = 0):
+        _need_cuda(rows, "rows")
+        if rows.dim() != 2:
+            raise ValueError(f"rows must be [n, dim]; got shape {tuple(rows.shape)}")
+        if rows.dtype not in _TORCH_TO_VQA:
+            raise ValueError(f"rows dtype must be float32, bfloat16 or float16; got {rows.dtype}")
+        if rows.stride(1) != 1 and rows.shape[0] > 0:
+            raise ValueError("rows must be row-major (unit stride along dim)")
+        self.rows = rows
+        self.n, self.dim = int(rows.shape[0]), int(rows.shape[1])
+        self.first_global_id = int(first_global_id)
+        self.device = rows.device
+        L = N.lib()
+        h = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        N.check(L.vqa_index_create(ctypes.byref(h), self.n, self.dim, _TORCH_TO_VQA[rows.dtype], dev_index,
+                                   self.first_global_id))
+        self._h = h
+        stride_bytes = (rows.stride(0) if self.n > 1 else self.dim) * rows.element_size()
+        N.check(L.vqa_index_bind(self._h, ctypes.c_void_p(rows.data_ptr() if self.n else 0), self.n, stride_bytes))
+        self._ws = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and N._lib is not None:
+            N._lib.vqa_index_destroy(h)
+            self._h = None
+
+    # -- planning / workspace -------------------------------------------------
+    def plan(self, n_queries: int, k: int, mode="fast") -> Tuple[int, int]:
+        fam, nl = ctypes.c_int32(), ctypes.c_int32()
+        N.check(N.lib().vqa_search_plan(self._h, n_queries, k, mode_id(mode), ctypes.byref(fam), ctypes.byref(nl)))
+        return fam.value, nl.value
+
+    def workspace(self, n_queries: int, k: int, mode: int) -> torch.Tensor:
+        key = (n_queries, k)
+        ws = self._ws.get(key)
+        if ws is None:
+            need = ctypes.c_size_t()
+            N.check(N.lib().vqa_workspace_bytes(self._h, n_queries, k, mode, ctypes.byref(need)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    # -- search ---------------------------------------------------------------
+    def search(self, queries: torch.Tensor, k: int, mode="fast", out_scores: Optional[torch.Tensor] = None,
+               out_ids: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """queries: float32 [B, dim] CUDA, L2-normalised.  Returns (scores f32 [B,k], ids i64 [B,k])."""
+        _need_cuda(queries, "queries")
+        if queries.dtype != torch.float32:
+            raise ValueError(f"queries must be float32; got {queries.dtype}")
+        if queries.dim() == 1:
+            queries = queries.unsqueeze(0)
+        if queries.dim() != 2 or queries.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B, {self.dim}]; got {tuple(queries.shape)}")
+        if queries.stride(1) != 1 or queries.stride(0) % 4 != 0 or queries.data_ptr() % 16 != 0:
+            queries = queries.contiguous()
+        b = int(queries.shape[0])
+        m = mode_id(mode)
+        if out_scores is None:
+            out_scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
+        if out_ids is None:
+            out_ids = torch.empty((b, k), dtype=torch.int64, device=self.device)
+        ws = self.workspace(b, k, m)
+        q_stride = queries.stride(0) if b > 1 else self.dim
+        N.check(N.lib().vqa_search(self._h, ctypes.c_void_p(queries.data_ptr()), q_stride, b, k, m,
+                                   ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(out_ids.data_ptr()),
+                                   ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(_stream(self.device))))
+        return out_scores, out_ids
+
+    def search_host(self, queries_host: torch.Tensor, k: int, mode="fast"):
+        """Host-buffer search through ``vqa_search_host``: pinned fp32 [B,dim] in,
+        pinned (scores, ids) out; H2D + search + D2H + stream sync inside the call."""
+        if queries_host.is_cuda or queries_host.dtype != torch.float32 or not queries_host.is_contiguous():
+            raise ValueError("queries_host must be a contiguous float32 CPU tensor")
+        b = int(queries_host.shape[0])
+        m = mode_id(mode)
+        key = ("host", b, k)
+        st = self._ws.get(key)
+        if st is None:
+            need = ctypes.c_size_t()
+            N.check(N.lib().vqa_search_host_staging_bytes(self._h, b, k, m, ctypes.byref(need)))
+            st = (torch.empty(need.value, dtype=torch.uint8, device=self.device),
+                  torch.empty((b, k), dtype=torch.float32).pin_memory(),
+                  torch.empty((b, k), dtype=torch.int64).pin_memory())
+            self._ws[key] = st
+        staging, hs, hi = st
+        N.check(N.lib().vqa_search_host(self._h, ctypes.c_void_p(queries_host.data_ptr()), b, k, m,
+                                        ctypes.c_void_p(hs.data_ptr()), ctypes.c_void_p(hi.data_ptr()),
+                                        ctypes.c_void_p(staging.data_ptr()), staging.numel(),
+                                        ctypes.c_void_p(_stream(self.device))))
+        return hs, hi
+
+
+def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int):
+    """K4: cand_* [lists, B, k_in] (float32 / int64, CUDA) -> (scores [B,k], ids [B,k])."""
+    _need_cuda(cand_scores, "cand_scores")
+    _need_cuda(cand_ids, "cand_ids")
+    if cand_scores.dtype != torch.float32 or cand_ids.dtype != torch.int64:
+        raise ValueError("cand_scores must be float32 and cand_ids int64")
+    if cand_scores.dim() != 3 or cand_scores.shape != cand_ids.shape:
+        raise ValueError("cand_scores / cand_ids must both be [lists, B, k_in]")
+    cand_scores, cand_ids = cand_scores.contiguous(), cand_ids.contiguous()
+    lists, b, k_in = (int(x) for x in cand_scores.shape)
+    dev = cand_scores.device
+    out_s = torch.empty((b, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((b, k), dtype=torch.int64, device=dev)
+    N.check(N.lib().vqa_merge_topk(ctypes.c_void_p(cand_scores.data_ptr()), ctypes.c_void_p(cand_ids.data_ptr()),
+                                   lists, b, k_in, k, ctypes.c_void_p(out_s.data_ptr()),
+                                   ctypes.c_void_p(out_i.data_ptr()), dev.index or 0, ctypes.c_void_p(_stream(dev))))
+    return out_s, out_i
+
+
+def pool_normalize(hidden: torch.Tensor, mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """K1: hidden [B,S,D] (f32/bf16/f16), mask [B,S] (int64/int32/bool/uint8/f32) -> float32 [B,D]."""
+    _need_cuda(hidden, "hidden")
+    _need_cuda(mask, "mask")
+    if hidden.dim() != 3 or mask.dim() != 2 or mask.shape != hidden.shape[:2]:
+        raise ValueError(f"hidden must be [B,S,D] and mask [B,S]; got {tuple(hidden.shape)} / {tuple(mask.shape)}")
+    if hidden.dtype not in _TORCH_TO_VQA:
+        raise ValueError(f"hidden dtype must be float32/bfloat16/float16; got {hidden.dtype}")
+    if mask.dtype not in _MASK_TO_VQA:
+        raise ValueError(f"mask dtype must be int64/int32/uint8/bool/float32; got {mask.dtype}")
+    hidden, mask = hidden.contiguous(), mask.contiguous()
+    b, s, d = (int(x) for x in hidden.shape)
+    out = torch.empty((b, d), dtype=torch.float32, device=hidden.device)
+    N.check(N.lib().vqa_pool_normalize(ctypes.c_void_p(hidden.data_ptr()), _TORCH_TO_VQA[hidden.dtype],
+                                       ctypes.c_void_p(mask.data_ptr()), _MASK_TO_VQA[mask.dtype], b, s, d,
+                                       int(normalize), ctypes.c_void_p(out.data_ptr()), hidden.device.index or 0,
+                                       ctypes.c_void_p(_stream(hidden.device))))
+    return out
+
+
+def normalize_rows(x: torch.Tensor, cast_dtype: Optional[torch.dtype] = None, inplace: bool = False):
+    """Row-wise fp32 L2 normalise on device.  Returns the fp32 result, or the cast copy
+    (bf16/fp16 storage rows) when ``cast_dtype`` is given."""
+    _need_cuda(x, "x")
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise ValueError("x must be a float32 [n, dim] tensor")
+    x = x if x.is_contiguous() else x.contiguous()
+    n, d = int(x.shape[0]), int(x.shape[1])
+    out = x if inplace else torch.empty_like(x)
+    cast = None
+    cast_kind = 0
+    if cast_dtype is not None and cast_dtype != torch.float32:
+        if cast_dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError(f"cast_dtype must be bfloat16 or float16; got {cast_dtype}")
+        cast = torch.empty((n, d), dtype=cast_dtype, device=x.device)
+        cast_kind = _TORCH_TO_VQA[cast_dtype]
+    N.check(N.lib().vqa_normalize_rows(ctypes.c_void_p(x.data_ptr()), d, n, d, ctypes.c_void_p(out.data_ptr()), d,
+                                       ctypes.c_void_p(cast.data_ptr()) if cast is not None else None, cast_kind, d,
+                                       x.device.index or 0, ctypes.c_void_p(_stream(x.device))))
+    return cast if cast is not None else out
+
+
+def agree(ids_a: torch.Tensor, scores_a: torch.Tensor, ids_b: torch.Tensor, scores_b: torch.Tensor,
+          threshold: float = 0.4):
+    """Batched two-index agreement rule (heavy_ranker.py:110).  Returns (accept bool[n], combined f32[n])."""
+    for t, nme in ((ids_a, "ids_a"), (scores_a, "scores_a"), (ids_b, "ids_b"), (scores_b, "scores_b")):
+        _need_cuda(t, nme)
+    ids_a, ids_b = ids_a.contiguous().view(-1), ids_b.contiguous().view(-1)
+    scores_a, scores_b = scores_a.contiguous().view(-1), scores_b.contiguous().view(-1)
+    if ids_a.dtype != torch.int64 or ids_b.dtype != torch.int64 or scores_a.dtype != torch.float32 \
+            or scores_b.dtype != torch.float32:
+        raise ValueError("ids must be int64 and scores float32")
+    n = ids_a.numel()
+    if not (ids_b.numel() == scores_a.numel() == scores_b.numel() == n):
+        raise ValueError("all inputs must have the same length")
+    dev = ids_a.device
+    acc = torch.empty(n, dtype=torch.uint8, device=dev)
+    comb = torch.empty(n, dtype=torch.float32, device=dev)
+    N.check(N.lib().vqa_agree(ctypes.c_void_p(ids_a.data_ptr()), ctypes.c_void_p(scores_a.data_ptr()),
+                              ctypes.c_void_p(ids_b.data_ptr()), ctypes.c_void_p(scores_b.data_ptr()), n,
+                              float(threshold), ctypes.c_void_p(acc.data_ptr()), ctypes.c_void_p(comb.data_ptr()),
+                              dev.index or 0, ctypes.c_void_p(_stream(dev))))
+    return acc.view(torch.bool), comb

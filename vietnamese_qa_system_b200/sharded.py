@@ -1,0 +1,93 @@
+"""Row-sharded exact search across the GPUs of one box.
+
+Rank r of G holds the contiguous row block ``[r*ceil(N/G), min((r+1)*ceil(N/G), N))``
+of the document matrix.  A search is: local scan + fused top-k on every rank ->
+ONE all-gather of the packed ``[B, k]`` candidates (NCCL over NVLink/NVSwitch,
+through ``torch.distributed``) -> merge-top-k kernel (K4) -> identical ``[B, k]`` on
+every rank.  There is no other collective on the data path.
+
+The reference is single-process (heavy_ranker.py:97-101); this module is what
+lets its one index grow past one GPU.  The partition arithmetic and the
+exchange are backend-agnostic so that world_size-2 ``gloo`` tests can drive them
+on CPU with the oracle standing in for the two device steps (tests only).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row block of ``rank``: [lo, hi)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    per = -(-n_total // world) if n_total > 0 else 0
+    lo = min(rank * per, n_total)
+    hi = min(lo + per, n_total)
+    return lo, hi
+
+
+def exchange_candidates(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One all-gather of the per-rank ``[B, k]`` results.
+
+    Scores (fp32) and ids (int64) are packed into a single int64 ``[B, k, 2]`` buffer so
+    that exactly one collective is issued.  Returns ``([G,B,k] scores, [G,B,k] ids)``.
+    """
+    world = dist.get_world_size(group)
+    b, k = scores.shape
+    packed = torch.empty((b, k, 2), dtype=torch.int64, device=scores.device)
+    packed[..., 0] = scores.contiguous().view(torch.int32).to(torch.int64)
+    packed[..., 1] = ids
+    gathered = torch.empty((world, b, k, 2), dtype=torch.int64, device=scores.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    g_scores = gathered[..., 0].to(torch.int32).view(torch.float32).contiguous()
+    g_ids = gathered[..., 1].contiguous()
+    return g_scores, g_ids
+
+
+class ShardedSearch:
+    """Host-side driver of the sharded search; device steps are injected.
+
+    ``local_search(queries, k) -> (scores [B,k], ids [B,k])`` with GLOBAL ids, padded with
+    ``(-inf, -1)``; ``merge(cand_scores [G,B,k], cand_ids [G,B,k], k) -> (scores, ids)``.
+    """
+
+    def __init__(self, local_search: Callable, merge: Callable, group=None):
+        self.local_search = local_search
+        self.merge = merge
+        self.group = group
+
+    def search(self, queries: torch.Tensor, k: int):
+        s, i = self.local_search(queries, k)
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return s, i
+        gs, gi = exchange_candidates(s, i, self.group)
+        return self.merge(gs, gi, k)
+
+
+class ShardedFlat:
+    """The product wiring: ``ops.FlatShard`` scan + NCCL all-gather + ``ops.merge_topk``.
+
+    One process per GPU (torchrun); ``rows`` is THIS rank's block, already in storage dtype.
+    """
+
+    def __init__(self, rows: torch.Tensor, n_total: int, group=None, mode="fast"):
+        from . import ops
+
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi = shard_bounds(n_total, self.world, self.rank)
+        if rows.shape[0] != hi - lo:
+            raise ValueError(f"rank {self.rank} must hold rows [{lo},{hi}) = {hi - lo} rows; got {rows.shape[0]}")
+        self.n_total = n_total
+        self.shard = ops.FlatShard(rows, first_global_id=lo)
+        self.mode = mode
+        self._driver = ShardedSearch(lambda q, k: self.shard.search(q, k, self.mode),
+                                     lambda gs, gi, k: ops.merge_topk(gs, gi, k), group)
+
+    def search(self, queries: torch.Tensor, k: int, mode: Optional[str] = None):
+        if mode is not None:
+            self.mode = mode
+        return self._driver.search(queries, k)
