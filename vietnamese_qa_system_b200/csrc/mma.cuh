@@ -186,6 +186,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     }
     if (warp == 4) {
         if (lane == 0) ptx::prefetch_tmap(&tmap_docs);
+        __syncwarp();
         ptx::tmem_alloc(tmem_slot, TMEM_COLS);
         ptx::tmem_relinquish();
     }
@@ -334,6 +335,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         ci[idx] = L.i[b * L.kcap + e];
     }
     if (warp == 4) {
+        __syncwarp();
         ptx::tc_fence_after_sync();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
