@@ -1,0 +1,91 @@
+"""The C-ABI library loads and exports every symbol include/vqa.h declares; argument and
+no-device error behaviour.  No compute calls (CPU only)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tests.conftest import ROOT
+from vietnamese_qa_system_b200 import _native as N
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "vqa.h")) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"VQA_API\s+[\w\s\*]+?\b(vqa_\w+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported():
+    syms = declared_symbols()
+    assert len(syms) >= 15 and set(syms) == set(N.EXPORTS)
+    L = N.lib()
+    for s in syms:
+        assert getattr(L, s) is not None, s
+
+
+def test_version_and_last_error():
+    L = N.lib()
+    assert L.vqa_version() == 100
+    assert isinstance(N.last_error(), str)
+
+
+def test_library_is_built_for_sm100a():
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", N.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def has_gpu():
+    return N.device_count() > 0
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device error path")
+def test_no_device_fails_loudly_not_silently():
+    L = N.lib()
+    h = ctypes.c_void_p()
+    rc = L.vqa_index_create(ctypes.byref(h), 10, 768, N.BF16, 0, 0)
+    assert rc == N.E_CUDA and "no CPU fallback" in N.last_error()
+    with pytest.raises(N.VqaError):
+        N.check(rc)
+    with pytest.raises(N.VqaError):
+        N.require_cuda()
+    # compute entry points also refuse (nothing is computed on the host)
+    buf = (ctypes.c_float * 16)()
+    ids = (ctypes.c_int64 * 16)()
+    rc = L.vqa_merge_topk(buf, ids, 1, 1, 4, 4, buf, ids, 0, None)
+    assert rc == N.E_CUDA
+    rc = L.vqa_normalize_rows(buf, 4, 4, 4, buf, 4, None, 0, 0, 0, None)
+    assert rc == N.E_CUDA
+
+
+def test_argument_validation_precedes_device_use():
+    L = N.lib()
+    h = ctypes.c_void_p()
+    assert L.vqa_index_create(ctypes.byref(h), 10, 768, 9, 0, 0) == N.E_INVALID       # bad dtype
+    assert L.vqa_index_create(ctypes.byref(h), 10, 7, N.BF16, 0, 0) == N.E_INVALID     # 14-byte rows
+    assert "multiple of 16" in N.last_error()
+    assert L.vqa_index_create(ctypes.byref(h), -1, 768, N.F32, 0, 0) == N.E_INVALID
+    assert L.vqa_index_create(None, 1, 768, N.F32, 0, 0) == N.E_INVALID
+    assert L.vqa_search(None, None, 0, 1, 1, 0, None, None, None, 0, None) == N.E_INVALID
+    assert L.vqa_merge_topk(None, None, 1, 1, 1, 1, None, None, 0, None) == N.E_INVALID
+    buf = (ctypes.c_float * 16)()
+    ids = (ctypes.c_int64 * 16)()
+    assert L.vqa_merge_topk(buf, ids, 1, 1, 4, 4096, buf, ids, 0, None) == N.E_INVALID  # k_out > 128
+    assert L.vqa_pool_normalize(buf, 7, buf, N.I64, 1, 1, 8, 1, buf, 0, None) == N.E_INVALID
+    with pytest.raises(ValueError):
+        N.check(N.E_INVALID)
+    with pytest.raises(NotImplementedError):
+        N.check(N.E_UNSUPPORTED)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vietnamese_qa_system_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dp, fn), encoding="utf-8") as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), fn
+                assert "liboracle" not in src, fn

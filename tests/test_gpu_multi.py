@@ -1,0 +1,60 @@
+"""Row-sharded search over NCCL on real GPUs (needs >= 2 GPUs on the box; skipped otherwise)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist, numpy as np
+sys.path.insert(0, os.environ["VQA_ROOT"])
+from vietnamese_qa_system_b200 import ops
+from vietnamese_qa_system_b200.sharded import ShardedFlat, shard_bounds
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank); dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+N, D, B, K = 200_003, 768, 32, 10
+g = torch.Generator(device="cpu").manual_seed(3)
+docs = torch.randn(N, D, generator=g); docs[N - 1] = docs[0]; docs[N // 2] = docs[0]
+q = torch.randn(B, D, generator=g); q[0] = docs[0]
+rows = ops.normalize_rows(docs.to(dev)); qd = ops.normalize_rows(q.to(dev))
+lo, hi = shard_bounds(N, world, rank)
+ok = True
+for storage, mode in ((torch.float32, "verify"), (torch.bfloat16, "verify"), (torch.bfloat16, "fast")):
+    full = ops.FlatShard(rows.to(storage))
+    fs, fi = full.search(qd, K, mode)
+    sh = ShardedFlat(rows[lo:hi].to(storage).contiguous(), N, mode=mode)
+    s, i = sh.search(qd, K)
+    if mode == "verify":
+        ok = ok and torch.equal(i, fi) and torch.equal(s, fs)
+    else:
+        rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / K for a, b in zip(i.cpu(), fi.cpu())])
+        ok = ok and rec >= 0.999
+    ok = ok and i[0, :3].tolist() == [0, N // 2, N - 1]
+t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if int(t.item()) == 1 else 1)
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_nccl_matches_single_gpu(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(SCRIPT)
+    env = dict(os.environ, VQA_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -40,8 +40,9 @@ def exchange_candidates(scores: torch.Tensor, ids: torch.Tensor, group=None) -> 
     packed = torch.empty((b, k, 2), dtype=torch.int64, device=scores.device)
     packed[..., 0] = scores.contiguous().view(torch.int32).to(torch.int64)
     packed[..., 1] = ids
-    gathered = torch.empty((world, b, k, 2), dtype=torch.int64, device=scores.device)
-    dist.all_gather_into_tensor(gathered, packed, group=group)
+    flat = torch.empty((world * b, k, 2), dtype=torch.int64, device=scores.device)
+    dist.all_gather_into_tensor(flat, packed, group=group)  # rank-major concatenation along dim 0
+    gathered = flat.view(world, b, k, 2)
     g_scores = gathered[..., 0].to(torch.int32).view(torch.float32).contiguous()
     g_ids = gathered[..., 1].contiguous()
     return g_scores, g_ids
