@@ -1,6 +1,7 @@
 """The reference-facing surface: Embeddings (txtai call shapes used at heavy_ranker.py:78-101),
 the ANN plugin B200Flat, and the batched heavy_ranker flow -- results against the oracle."""
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -23,7 +24,7 @@ class FakeEncoder:
     def __call__(self, texts):
         out = np.empty((len(texts), self.dim), np.float32)
         for r, t in enumerate(texts):
-            seed = int.from_bytes(t.encode("utf-8"), "little") % (2 ** 32)
+            seed = zlib.crc32(t.encode("utf-8"))
             out[r] = np.random.default_rng(seed).standard_normal(self.dim)
         return out
 

@@ -97,7 +97,7 @@ def test_agree_rule_vs_oracle():
     ia, ib = rng.integers(0, 5, n), rng.integers(0, 5, n)
     sa = rng.uniform(0, 0.5, n).astype(np.float32)
     sb = rng.uniform(0, 0.5, n).astype(np.float32)
-    sa[:4], sb[:4] = [0.2, 0.25, 0.125, 0.4], [0.2, 0.2, 0.25, 0.0]
+    sa[:4], sb[:4] = [0.2, 0.25, 0.125, 0.25], [0.2, 0.2, 0.25, 0.125]
     ia[:4] = ib[:4] = 1
     acc, comb = ops.agree(torch.from_numpy(ia).to(DEV), torch.from_numpy(sa).to(DEV),
                           torch.from_numpy(ib).to(DEV), torch.from_numpy(sb).to(DEV), 0.4)

@@ -18,6 +18,11 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 
+// programmatic dependent launch (PDL): the consumer grid blocks in grid_dependency_wait() until the
+// producer grid has finished and its writes are visible; the producer may release the launch early.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <typename IdT>
 __device__ __forceinline__ constexpr IdT invalid_id();
 template <>

@@ -30,7 +30,8 @@ struct MmaLaunch {
     const CUtensorMap *tmap;
     bool bf16;
     int ncol;
-    int stages;
+    int stages;  // ring stages, each kps x 16 KB
+    int kps;
     int grid;
     const float *q;
     long long q_stride;

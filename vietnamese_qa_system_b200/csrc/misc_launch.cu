@@ -26,14 +26,31 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
     p.list_stride = list_stride;
     p.query_stride = query_stride;
     p.n_lists = n_lists;
+    p.n_queries = n_queries;
     p.k_in = k_in;
     p.k_out = k_out;
     p.id_base = id_base;
     p.out_s = out_s;
     p.out_i = out_i;
-    const size_t smem = list_smem_bytes<IdT>(1, k_out);
-    reduce_topk_kernel<IdT><<<n_queries, kReduceThreads, smem, st>>>(p);
-    return cudaGetLastError();
+    // programmatic dependent launch: the reduce grid is scheduled while the scan drains and
+    // blocks in griddepcontrol.wait until the scan's candidates are visible
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (k_out <= 32) {
+        cfg.gridDim = dim3((n_queries + kReduceWarpsPerCta - 1) / kReduceWarpsPerCta);
+        cfg.blockDim = dim3(kReduceWarpsPerCta * 32);
+        cfg.dynamicSmemBytes = 0;
+        return cudaLaunchKernelEx(&cfg, reduce_topk_warp_kernel<IdT>, p);
+    }
+    cfg.gridDim = dim3(n_queries);
+    cfg.blockDim = dim3(32);
+    cfg.dynamicSmemBytes = list_smem_bytes<IdT>(1, k_out);
+    return cudaLaunchKernelEx(&cfg, reduce_topk_kernel<IdT>, p);
 }
 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,

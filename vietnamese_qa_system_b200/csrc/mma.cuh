@@ -16,8 +16,9 @@
 //              AS TMEM accumulator stages, tcgen05.commit frees smem / hands the
 //              accumulator to the epilogue.
 // The queries stay resident in shared memory for the whole kernel, converted
-// on the fly from fp32 to the storage type as a hi + lo pair (two MMA columns
-// per query) so that the only rounding left is the documents' own storage
+// on the fly from fp32 to the storage type as a hi + lo pair; both parts are
+// multiplied against the same document block and accumulate into the SAME TMEM
+// columns, so that the only rounding left is the documents' own storage
 // rounding -- this is what keeps recall@k >= 0.999 against the fp32 verify mode.
 // The [B, n_rows] score matrix never leaves the SM.
 //
@@ -35,18 +36,18 @@ namespace vqa {
 struct MmaParams {
     const float *q;
     long long q_stride;
-    int nq;  // queries in this pass: nq <= NCOL / (split ? 2 : 1)
+    int nq;  // queries in this pass: nq <= NCOL
     int k;
     long long n_rows;
     int dim;  // multiple of 64
-    int split;  // 1: hi/lo query columns
-    float lo_inv_scale;  // score = acc_hi + acc_lo * lo_inv_scale
-    float lo_scale;
+    int split;  // 1: hi + lo query parts (2 MMAs per K step), 0: hi only
     float *cand_s;
     uint32_t *cand_i;
     long long cand_stride;
     int n_tiles;
     int n_stages;  // smem ring depth
+    int kps;       // k-blocks (16 KB TMA boxes) per ring stage
+    unsigned long long tma_policy;  // L2 cache hint for the document stream
 };
 
 template <int NCOL>
@@ -68,7 +69,7 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 
 // hi/lo split of 8 consecutive fp32 values into two 16-byte chunks
 template <bool BF16>
-__device__ __forceinline__ void split8(const float (&x)[8], float lo_scale, uint4 &hi, uint4 &lo) {
+__device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
     float h[8], l[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -77,7 +78,7 @@ __device__ __forceinline__ void split8(const float (&x)[8], float lo_scale, uint
         } else {
             h[j] = __half2float(__float2half_rn(x[j]));
         }
-        l[j] = (x[j] - h[j]) * lo_scale;
+        l[j] = x[j] - h[j];  // exact in fp32; fp16's residual may be subnormal (still ~2^-19 relative overall)
     }
     if constexpr (BF16) {
         hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
@@ -157,9 +158,12 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int KB = p.dim / kBlockK;
     const int S = p.n_stages;
-    unsigned char *q_smem = smem;                                   // KB tiles of NCOL*128 B
-    unsigned char *a_smem = q_smem + (size_t)KB * NCOL * 128;       // S stages of 16 KB
-    uint64_t *bars = reinterpret_cast<uint64_t *>(a_smem + (size_t)S * kStageBytes);
+    const int KPS = p.kps;                 // KB % KPS == 0
+    const int KG = KB / KPS;               // ring stages consumed per tile
+    const uint32_t stage_bytes = (uint32_t)KPS * kStageBytes;
+    unsigned char *q_smem = smem;                                   // KB x {hi, lo} tiles of NCOL*128 B
+    unsigned char *a_smem = q_smem + (size_t)KB * 2 * NCOL * 128;   // S stages of KPS x 16 KB
+    uint64_t *bars = reinterpret_cast<uint64_t *>(a_smem + (size_t)S * stage_bytes);
     uint64_t *full = bars;                       // [kMaxStages]
     uint64_t *empty = bars + kMaxStages;         // [kMaxStages]
     uint64_t *tfull = bars + 2 * kMaxStages;     // [kMaxAccStages]
@@ -170,7 +174,6 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int NQH = p.split ? NCOL / 2 : NCOL;  // query columns (hi part)
 
     // ---- one-time setup ------------------------------------------------------
     if (warp == 5 && lane == 0) {
@@ -191,6 +194,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         ptx::tmem_relinquish();
     }
     list_init(L, NCOL, tid, kMmaThreads);
+    grid_launch_dependents();  // lets the (PDL) candidate-reduce grid be scheduled as SMs drain
     // padding columns never produce candidates (same thread wrote tau[q] in list_init)
     for (int q = tid; q < NCOL; q += kMmaThreads)
         if (q >= p.nq) L.tau[q] = __int_as_float(0x7f800000);
@@ -199,7 +203,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     // unit of work: one 16-byte chunk (8 elements) of one query row.
     {
         const int chunks_per_row = p.dim / 8;
-        const int total = NQH * chunks_per_row;
+        const int total = NCOL * chunks_per_row;
         for (int idx = tid; idx < total; idx += kMmaThreads) {
             const int j = idx / chunks_per_row;   // query row
             const int cg = idx % chunks_per_row;  // global chunk
@@ -209,14 +213,12 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 const float4 *src = reinterpret_cast<const float4 *>(p.q + (long long)j * p.q_stride + cg * 8);
                 const float4 v0 = src[0], v1 = src[1];
                 const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                split8<BF16>(x, p.lo_scale, hi, lo);
+                split8<BF16>(x, hi, lo);
             }
-            unsigned char *tile = q_smem + (size_t)kb * NCOL * 128;
-            *reinterpret_cast<uint4 *>(tile + j * 128 + ((c ^ (j & 7)) << 4)) = hi;
-            if (p.split) {
-                const int jl = NQH + j;
-                *reinterpret_cast<uint4 *>(tile + jl * 128 + ((c ^ (jl & 7)) << 4)) = lo;
-            }
+            unsigned char *tile = q_smem + (size_t)kb * 2 * NCOL * 128;
+            const int off = j * 128 + ((c ^ (j & 7)) << 4);
+            *reinterpret_cast<uint4 *>(tile + off) = hi;
+            *reinterpret_cast<uint4 *>(tile + NCOL * 128 + off) = lo;
         }
     }
     ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -230,13 +232,14 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                for (int kg = 0; kg < KG; ++kg, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     ptx::mbar_wait(empty + s, ph ^ 1);
-                    ptx::mbar_arrive_expect_tx(full + s, kStageBytes);
-                    ptx::tma_load_2d(a_smem + (size_t)s * kStageBytes, &tmap_docs, kb * kBlockK,
-                                     tile * kTileRows, full + s, ptx::kEvictFirst);
+                    ptx::mbar_arrive_expect_tx(full + s, stage_bytes);
+                    for (int j = 0; j < KPS; ++j)
+                        ptx::tma_load_2d(a_smem + (size_t)s * stage_bytes + (size_t)j * kStageBytes, &tmap_docs,
+                                         (kg * KPS + j) * kBlockK, tile * kTileRows, full + s, p.tma_policy);
                 }
             }
         }
@@ -251,18 +254,25 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 ptx::mbar_wait(tempty + as, aph ^ 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * NCOL);
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                for (int kg = 0; kg < KG; ++kg, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     ptx::mbar_wait(full + s, ph);
                     ptx::tc_fence_after_sync();
-                    const uint32_t a_addr = ptx::smem_u32(a_smem + (size_t)s * kStageBytes);
-                    const uint32_t b_addr = ptx::smem_u32(q_smem + (size_t)kb * NCOL * 128);
+                    for (int j = 0; j < KPS; ++j) {
+                        const int kb = kg * KPS + j;
+                        const uint32_t a_addr = ptx::smem_u32(a_smem + (size_t)s * stage_bytes + (size_t)j * kStageBytes);
+                        const uint32_t b_addr = ptx::smem_u32(q_smem + (size_t)kb * 2 * NCOL * 128);
 #pragma unroll
-                    for (int k4 = 0; k4 < kBlockK / 16; ++k4) {
-                        const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k4 * 32);
-                        const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k4 * 32);
-                        ptx::umma_f16(d_tmem, da, db, IDESC, (kb | k4) != 0 ? 1u : 0u);
+                        for (int k4 = 0; k4 < kBlockK / 16; ++k4) {
+                            const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k4 * 32);
+                            const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k4 * 32);
+                            ptx::umma_f16(d_tmem, da, db, IDESC, (kb | k4) != 0 ? 1u : 0u);
+                            if (p.split) {  // + docs x q_lo into the same accumulator columns
+                                const uint64_t dl = ptx::umma_desc_k_sw128(b_addr + NCOL * 128 + k4 * 32);
+                                ptx::umma_f16(d_tmem, da, dl, IDESC, 1u);
+                            }
+                        }
                     }
                     ptx::umma_commit(empty + s);  // smem stage reusable once these MMAs retire
                 }
@@ -281,17 +291,15 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             const long long row = (long long)tile * kTileRows + warp * 32 + lane;
             const bool valid = row < p.n_rows;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NCOL);
-            for (int c0 = 0; c0 < NQH; c0 += 16) {
-                uint32_t hi[16], lo[16];
-                ptx::tmem_ld16(taddr + c0, hi);
-                if (p.split) ptx::tmem_ld16(taddr + NQH + c0, lo);
+            for (int c0 = 0; c0 < NCOL; c0 += 16) {
+                uint32_t acc[16];
+                ptx::tmem_ld16(taddr + c0, acc);
                 ptx::tmem_ld_wait();
                 float v[16];
                 bool any = false;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    v[j] = __uint_as_float(hi[j]);
-                    if (p.split) v[j] = __fmaf_rn(__uint_as_float(lo[j]), p.lo_inv_scale, v[j]);
+                    v[j] = __uint_as_float(acc[j]);
                     const float thr = *(volatile float *)(L.tau + c0 + j);
                     any |= (v[j] >= thr);
                 }

@@ -2,7 +2,20 @@
 #include "launch.h"
 #include "mma.cuh"
 
+#include <cstdlib>
+
 namespace vqa {
+
+// L2 policy for the document stream (tuning knob VQA_TMA_HINT: 0 normal, 1 evict-first, 2 evict-last)
+static unsigned long long tma_policy() {
+    static unsigned long long pol = 0;
+    if (!pol) {
+        const char *e = std::getenv("VQA_TMA_HINT");
+        int v = e ? std::atoi(e) : 1;
+        pol = v == 0 ? 0x1000000000000000ull : (v == 2 ? 0x14F0000000000000ull : 0x12F0000000000000ull);
+    }
+    return pol;
+}
 
 template <bool BF16, int NCOL>
 static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
@@ -14,15 +27,14 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     p.n_rows = a.n_rows;
     p.dim = a.dim;
     p.split = 1;
-    // fp16's 11-bit significand leaves a residual near its subnormal range: scale it up (exactly)
-    p.lo_scale = BF16 ? 1.0f : 2048.0f;
-    p.lo_inv_scale = BF16 ? 1.0f : 1.0f / 2048.0f;
     p.cand_s = a.cand_s;
     p.cand_i = a.cand_i;
     p.cand_stride = a.cand_stride;
     p.n_tiles = (int)((a.n_rows + kTileRows - 1) / kTileRows);
     p.n_stages = a.stages;
-    const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages);
+    p.kps = a.kps;
+    p.tma_policy = tma_policy();
+    const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps);
     auto kern = mma_topk_kernel<BF16, NCOL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

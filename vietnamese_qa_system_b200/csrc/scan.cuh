@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     float4 *qs = reinterpret_cast<float4 *>(smem);
     ListView<uint32_t> L = list_carve<uint32_t>(smem + (size_t)BT * qfl * sizeof(float), BT, p.k);
     list_init(L, BT, tid, kScanThreads);
+    grid_launch_dependents();  // lets the (PDL) candidate-reduce grid be scheduled as SMs drain
 
     // stage the queries (zero-fill beyond nq / beyond dim)
     for (int idx = tid; idx < BT * iters * H * 32; idx += kScanThreads) {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 // k_in (u32 local row index, or i64 global id for the cross-rank merge K4) into
 // the final top k_out, writes float32 scores and int64 ids (id_base + index).
 // ---------------------------------------------------------------------------
-constexpr int kReduceThreads = 256;
+constexpr int kReduceWarpsPerCta = 4;
 
 template <typename IdT>
 struct ReduceParams {
@@ -232,6 +233,7 @@ struct ReduceParams {
     long long list_stride;   // elements between lists
     long long query_stride;  // elements between queries inside a list
     int n_lists;
+    int n_queries;
     int k_in;
     int k_out;
     long long id_base;
@@ -239,20 +241,97 @@ struct ReduceParams {
     long long *out_i;
 };
 
+__device__ __forceinline__ float shfl_xor_any(float v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
+__device__ __forceinline__ uint32_t shfl_xor_any(uint32_t v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
+__device__ __forceinline__ long long shfl_xor_any(long long v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
+
 template <typename IdT>
-__global__ void __launch_bounds__(kReduceThreads) reduce_topk_kernel(const ReduceParams<IdT> p) {
+__device__ __forceinline__ void bitonic_step_t(float &s, IdT &i, int stride, bool keep_before) {
+    const float ps = shfl_xor_any(s, stride);
+    const IdT pi = shfl_xor_any(i, stride);
+    const bool mine_before = ranks_before<IdT>(s, i, ps, pi);
+    if (mine_before != keep_before) {
+        s = ps;
+        i = pi;
+    }
+}
+
+// k_out <= 32: ONE WARP per query, the running top-32 lives in registers (lane e = rank e).
+// Candidates are visited entry-major (every list's best first), 32 at a time; a chunk with no
+// candidate beating the current k-th is skipped by one ballot, otherwise it is bitonic-sorted and
+// bitonic-merged into the list.  No shared memory, no locks.
+template <typename IdT>
+__global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kernel(const ReduceParams<IdT> p) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kReduceWarpsPerCta + (threadIdx.x >> 5);
+    grid_dependency_wait();
+    if (q >= p.n_queries) return;
+    float ls = neg_inf();
+    IdT li = invalid_id<IdT>();
+    float tau = neg_inf();
+    const long long total = (long long)p.n_lists * p.k_in;
+    const float *qs = p.cand_s + (long long)q * p.query_stride;
+    const IdT *qi = p.cand_i + (long long)q * p.query_stride;
+    for (long long base = 0; base < total; base += 32) {
+        const long long idx = base + lane;
+        float s = neg_inf();
+        IdT id = invalid_id<IdT>();
+        if (idx < total) {
+            const int e = (int)(idx / p.n_lists);
+            const int l = (int)(idx - (long long)e * p.n_lists);
+            s = qs[(long long)l * p.list_stride + e];
+            id = qi[(long long)l * p.list_stride + e];
+        }
+        bool valid = id != invalid_id<IdT>();
+        if constexpr (sizeof(IdT) == 8) valid = valid && id >= 0;
+        const bool pass = valid && s >= tau;
+        if (__ballot_sync(kFullMask, pass) == 0) continue;
+        float cs = pass ? s : neg_inf();
+        IdT ci = pass ? id : invalid_id<IdT>();
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const bool desc = (lane & size) == 0 || size == 32;
+                bitonic_step_t<IdT>(cs, ci, stride, ((lane & stride) == 0) == desc);
+            }
+        }
+        const float rs = __shfl_sync(kFullMask, ls, 31 - lane);
+        const IdT ri = shfl_any(li, 31 - lane);
+        if (ranks_before<IdT>(rs, ri, cs, ci)) {
+            cs = rs;
+            ci = ri;
+        }
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) bitonic_step_t<IdT>(cs, ci, stride, (lane & stride) == 0);
+        ls = cs;
+        li = ci;
+        const IdT last = shfl_any(li, p.k_out - 1);
+        tau = last != invalid_id<IdT>() ? __shfl_sync(kFullMask, ls, p.k_out - 1) : neg_inf();
+    }
+    if (lane < p.k_out) {
+        const bool ok = li != invalid_id<IdT>();
+        p.out_s[(long long)q * p.k_out + lane] = ok ? ls : neg_inf();
+        p.out_i[(long long)q * p.k_out + lane] = ok ? (long long)li + p.id_base : -1LL;
+    }
+}
+
+// k_out in (32, 128]: one warp per query (one CTA of 32 threads), sorted list in shared memory.
+template <typename IdT>
+__global__ void __launch_bounds__(32) reduce_topk_kernel(const ReduceParams<IdT> p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x;
     const int q = blockIdx.x;
     ListView<IdT> L = list_carve<IdT>(smem, 1, p.k_out);
-    list_init(L, 1, tid, kReduceThreads);
-    __syncthreads();
-
+    list_init(L, 1, lane, 32);
+    __syncwarp();
+    grid_dependency_wait();
     const int kin_pad = ((p.k_in + 31) / 32) * 32;
-    for (int l = warp; l < p.n_lists; l += kReduceThreads / 32) {
-        const float *ls = p.cand_s + (long long)l * p.list_stride + (long long)q * p.query_stride;
-        const IdT *li = p.cand_i + (long long)l * p.list_stride + (long long)q * p.query_stride;
-        for (int e0 = 0; e0 < kin_pad; e0 += 32) {
+    // entry-major over chunks of 32 entries so that every list's best candidates come first
+    for (int e0 = 0; e0 < kin_pad; e0 += 32) {
+        for (int l = 0; l < p.n_lists; ++l) {
+            const float *ls = p.cand_s + (long long)l * p.list_stride + (long long)q * p.query_stride;
+            const IdT *li = p.cand_i + (long long)l * p.list_stride + (long long)q * p.query_stride;
             const int e = e0 + lane;
             float s = neg_inf();
             IdT id = invalid_id<IdT>();
@@ -271,8 +350,8 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_topk_kernel(const Reduc
             }
         }
     }
-    __syncthreads();
-    for (int e = tid; e < p.k_out; e += kReduceThreads) {
+    __syncwarp();
+    for (int e = lane; e < p.k_out; e += 32) {
         const IdT id = L.i[e];
         const bool ok = id != invalid_id<IdT>();
         p.out_s[(long long)q * p.k_out + e] = ok ? L.s[e] : neg_inf();
