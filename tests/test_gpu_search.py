@@ -155,7 +155,10 @@ def test_clustered_queries_recall_bf16_tensor():
 def test_family_selection_and_launch_count():
     rows = torch.zeros((4096, 768), dtype=torch.bfloat16, device=DEV)
     shard = ops.FlatShard(rows)
-    assert shard.plan(1, 10, "fast")[0] == 2 and shard.plan(32, 10, "fast")[0] == 3   # stream / tensor
+    assert shard.plan(1, 10, "fast")[0] == 3 and shard.plan(32, 10, "fast")[0] == 3   # 16-bit rows: tcgen05
+    assert shard.plan(1, 10, "stream")[0] == 2
+    odd = ops.FlatShard(torch.zeros((64, 72), dtype=torch.bfloat16, device=DEV))
+    assert odd.plan(8, 10, "fast")[0] == 2                                            # dim % 64 != 0: streaming
     assert shard.plan(32, 10, "verify")[0] == 2
     assert shard.plan(32, 10, "fast")[1] == 2            # one scan launch + one reduce launch
     rows32 = torch.zeros((4096, 768), dtype=torch.float32, device=DEV)

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -122,11 +123,11 @@ bool tensor_eligible(const vqa_index *h) {
 
 // pick the widest MMA N (<= what the batch needs) whose smem ring still has >= 4 stages
 bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
-    const int cands[3] = {64, 32, 16};
-    int want = nq;  // one accumulator column per query (hi and lo parts accumulate together)
-    for (int ci = 0; ci < 3; ++ci) {
+    const int cands[4] = {128, 64, 32, 16};
+    int want = nq * 2;  // hi + lo column per query
+    for (int ci = 0; ci < 4; ++ci) {
         int ncol = cands[ci];
-        if (ci < 2 && cands[ci + 1] >= want) continue;  // a narrower tile still covers the batch
+        if (ci < 3 && cands[ci + 1] >= want) continue;  // a narrower tile still covers the batch
         size_t fixed = vqa::mma_smem_bytes_rt(ncol, h->dim, k, 0);
         if (fixed >= (size_t)h->max_smem) continue;
         int blocks = (int)(((size_t)h->max_smem - fixed) / vqa::kStageBytes);  // 16 KB boxes that fit
@@ -143,7 +144,7 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
         if (stages < 2) continue;
         pl->family = VQA_MODE_FAST_TENSOR;
         pl->ncol = ncol;
-        pl->pass_nq = ncol;
+        pl->pass_nq = ncol / 2;
         pl->stages = stages;
         pl->kps = kps;
         pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
@@ -176,9 +177,10 @@ int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
         return VQA_OK;
     }
     if (mode == VQA_MODE_FAST) {
-        // CUDA-core FMA keeps up with HBM only for a handful of queries per streamed
-        // element; beyond that the contraction goes to the tensor cores.
-        if (nq > 4 && tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
+        // Measured on B200 (profiles/): the TMA-fed tcgen05 kernel streams the documents at the HBM
+        // roofline for every batch size, so 16-bit indexes always take it; the CUDA-core streaming
+        // kernel serves fp32 rows (verify mode's native storage) and dims that are not multiples of 64.
+        if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
         return VQA_OK;
     }
@@ -305,8 +307,8 @@ int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int3
     if (rc) return rc;
     if (!bytes) return fail(VQA_E_INVALID, "bytes is null");
     (void)mode;
-    // candidates: per CTA, per query, k entries of (float score, u32 row)
-    *bytes = cand_elems(h, n_queries, k) * 8 + 256;
+    // candidates: per CTA, per query, k entries of (float score, u32 row); + one shared-threshold slot per query
+    *bytes = cand_elems(h, n_queries, k) * 8 + (size_t)n_queries * 8 + 512;
     return VQA_OK;
 }
 
@@ -335,7 +337,11 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     uintptr_t ws = (reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~(uintptr_t)255;
     float *cand_s = reinterpret_cast<float *>(ws);
     uint32_t *cand_i = reinterpret_cast<uint32_t *>(cand_s + cand_elems(h, n_queries, k));
+    unsigned long long *tau_g = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(cand_i + cand_elems(h, n_queries, k)) + 255) & ~(uintptr_t)255);
     const long long cand_stride = (long long)n_queries * k;
+    static std::atomic<uint32_t> g_epoch{1};
+    const uint32_t epoch = g_epoch.fetch_add(2, std::memory_order_relaxed);  // odd, unique, never 0 (0 = cleared slot)
 
     int n_lists = 0;
     if (h->n_rows > 0) {
@@ -360,6 +366,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
                 a.cand_s = cand_s + (long long)p0 * k;
                 a.cand_i = cand_i + (long long)p0 * k;
                 a.cand_stride = cand_stride;
+                a.tau_g = tau_g + p0;
+                a.epoch = epoch;
                 e = vqa::launch_mma(a, st);
             } else {
                 vqa::ScanLaunch a;
@@ -383,7 +391,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
         }
     }
     cudaError_t e = vqa::launch_reduce_u32(cand_s, cand_i, cand_stride, k, n_lists, k, k, h->first_id,
-                                           out_scores_dev, (long long *)out_ids_dev, n_queries, st);
+                                           out_scores_dev, (long long *)out_ids_dev, n_queries,
+                                           pl.family == VQA_MODE_FAST_TENSOR ? tau_g : nullptr, st);
     if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
     return VQA_OK;
 }

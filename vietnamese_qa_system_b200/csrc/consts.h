@@ -19,11 +19,11 @@ inline size_t list_bytes_rt(int nq, int k, int id_bytes) {
     int kcap = ((k + 31) / 32) * 32;
     return (size_t)nq * kcap * (4 + id_bytes) + (size_t)nq * 8;
 }
-// shared memory of the tensor-core kernel: [align slack][Q hi+lo tiles][A ring][barriers][lists]
-// `boxes` = number of 16 KB document boxes in the ring
+// shared memory of the tensor-core kernel: [align slack][Q tiles (hi|lo columns)][A ring][barriers][lists]
+// `ncol` = MMA N = 2 x queries per pass; `boxes` = number of 16 KB document boxes in the ring
 inline size_t mma_smem_bytes_rt(int ncol, int dim, int k, int boxes) {
-    return 1024 + (size_t)(dim / kBlockK) * 2 * ncol * 128 + (size_t)boxes * kStageBytes + 1024 +
-           list_bytes_rt(ncol, k, 4);
+    return 1024 + (size_t)(dim / kBlockK) * ncol * 128 + (size_t)boxes * kStageBytes + 1024 +
+           list_bytes_rt(ncol / 2, k, 4);
 }
 
 }  // namespace vqa

@@ -42,6 +42,8 @@ struct MmaLaunch {
     float *cand_s;
     uint32_t *cand_i;
     long long cand_stride;
+    unsigned long long *tau_g;  // [nq] shared thresholds for this pass (or nullptr)
+    uint32_t epoch;
 };
 
 cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st);
@@ -52,7 +54,8 @@ cudaError_t launch_mma(const MmaLaunch &a, cudaStream_t st);
 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
-                              float *out_s, long long *out_i, int n_queries, cudaStream_t st);
+                              float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
+                              cudaStream_t st);
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, cudaStream_t st);

@@ -16,10 +16,12 @@
 //              AS TMEM accumulator stages, tcgen05.commit frees smem / hands the
 //              accumulator to the epilogue.
 // The queries stay resident in shared memory for the whole kernel, converted
-// on the fly from fp32 to the storage type as a hi + lo pair; both parts are
-// multiplied against the same document block and accumulate into the SAME TMEM
-// columns, so that the only rounding left is the documents' own storage
-// rounding -- this is what keeps recall@k >= 0.999 against the fp32 verify mode.
+// on the fly from fp32 to the storage type as a hi + lo pair (two MMA columns
+// per query, added in the epilogue) so that the only rounding left is the
+// documents' own storage rounding -- this is what keeps recall@k >= 0.999
+// against the fp32 verify mode.  (Column pairs rather than a second MMA into the
+// same columns: the issue rate of small tcgen05.mma instructions, not the tensor
+// pipe, is what limits this kernel, so fewer, wider MMAs win.)
 // The [B, n_rows] score matrix never leaves the SM.
 //
 // Roofline: HBM up to B ~ 200 (algorithmic bytes = n_rows*dim*2 per launch),
@@ -36,11 +38,12 @@ namespace vqa {
 struct MmaParams {
     const float *q;
     long long q_stride;
-    int nq;  // queries in this pass: nq <= NCOL
+    int nq;  // queries in this pass: nq <= NCOL / 2 (hi and lo column per query)
     int k;
     long long n_rows;
     int dim;  // multiple of 64
-    int split;  // 1: hi + lo query parts (2 MMAs per K step), 0: hi only
+    float lo_scale;      // q_lo is stored as (q - q_hi) * lo_scale ...
+    float lo_inv_scale;  // ... and score = acc_hi + acc_lo * lo_inv_scale
     float *cand_s;
     uint32_t *cand_i;
     long long cand_stride;
@@ -48,7 +51,34 @@ struct MmaParams {
     int n_stages;  // smem ring depth
     int kps;       // k-blocks (16 KB TMA boxes) per ring stage
     unsigned long long tma_policy;  // L2 cache hint for the document stream
+    // GPU-wide per-query thresholds shared by all CTAs: (epoch << 32) | ordered(score of some list's
+    // k-th best).  A document scoring below any list's k-th best cannot be in the global top-k.
+    unsigned long long *tau_g;  // [nq] for this pass, or nullptr
+    uint32_t epoch;
 };
+
+// order-preserving float -> uint32 (larger float <=> larger uint), tagged with the search epoch
+__device__ __forceinline__ unsigned long long tau_encode(float f, uint32_t epoch) {
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t ord = (u >> 31) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)epoch << 32) | ord;
+}
+__device__ __forceinline__ float tau_decode(unsigned long long v, uint32_t epoch) {
+    if ((uint32_t)(v >> 32) != epoch) return neg_inf();  // stale / uninitialised slot
+    const uint32_t ord = (uint32_t)v;
+    return __uint_as_float((ord >> 31) ? (ord & 0x7fffffffu) : ~ord);
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 template <int NCOL>
 __host__ __device__ constexpr int mma_acc_stages() {
@@ -69,7 +99,7 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 
 // hi/lo split of 8 consecutive fp32 values into two 16-byte chunks
 template <bool BF16>
-__device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
+__device__ __forceinline__ void split8(const float (&x)[8], float lo_scale, uint4 &hi, uint4 &lo) {
     float h[8], l[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -78,7 +108,7 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo
         } else {
             h[j] = __half2float(__float2half_rn(x[j]));
         }
-        l[j] = x[j] - h[j];  // exact in fp32; fp16's residual may be subnormal (still ~2^-19 relative overall)
+        l[j] = (x[j] - h[j]) * lo_scale;  // the subtraction is exact in fp32
     }
     if constexpr (BF16) {
         hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
@@ -144,11 +174,81 @@ __device__ __noinline__ void list_insert_bulk32(ListView<uint32_t> L, int q, flo
     if (lane == 0) atomicExch(L.lock + q, 0);
 }
 
+// ---- register-resident per-warp lists (k <= 32, <= 32 queries per pass) ---------------------
+// Lane e of the warp holds rank e of a sorted (descending) 32-entry list: no shared memory, no
+// locks, no fences on the (rare) insert path.
+struct Entry {
+    float s;
+    uint32_t i;
+};
+
+__device__ __noinline__ Entry reglist_insert_one(float ls, uint32_t li, float cs, uint32_t ci) {
+    const int lane = threadIdx.x & 31;
+    const int pos = __popc(__ballot_sync(kFullMask, ranks_before<uint32_t>(ls, li, cs, ci)));
+    const float ups = __shfl_up_sync(kFullMask, ls, 1);
+    const uint32_t upi = __shfl_up_sync(kFullMask, li, 1);
+    Entry e;
+    e.s = lane < pos ? ls : (lane == pos ? cs : ups);
+    e.i = lane < pos ? li : (lane == pos ? ci : upi);
+    return e;
+}
+
+// merge up to 32 unsorted candidates (one per lane, (-inf, invalid) where none) into the list
+__device__ __noinline__ Entry reglist_merge32(float ls, uint32_t li, float cs, uint32_t ci, bool cand_sorted) {
+    const int lane = threadIdx.x & 31;
+    if (!cand_sorted) {
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const bool desc = (lane & size) == 0 || size == 32;
+                bitonic_step(cs, ci, stride, ((lane & stride) == 0) == desc);
+            }
+        }
+    }
+    const float rs = __shfl_sync(kFullMask, ls, 31 - lane);
+    const uint32_t ri = __shfl_sync(kFullMask, li, 31 - lane);
+    if (ranks_before<uint32_t>(rs, ri, cs, ci)) {
+        cs = rs;
+        ci = ri;
+    }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) bitonic_step(cs, ci, stride, (lane & stride) == 0);
+    Entry e;
+    e.s = cs;
+    e.i = ci;
+    return e;
+}
+
+// one 16-column group of this thread's document row: score = acc_hi + acc_lo * lo_inv_scale
+template <int NCOL>
+__device__ __forceinline__ void load_scores16(uint32_t taddr, int c0, float lo_inv_scale, float (&v)[16]) {
+    constexpr int NQ = NCOL / 2;
+    if constexpr (NQ >= 16) {
+        uint32_t hi[16], lo[16];
+        ptx::tmem_ld16(taddr + c0, hi);
+        ptx::tmem_ld16(taddr + NQ + c0, lo);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __fmaf_rn(__uint_as_float(lo[j]), lo_inv_scale, __uint_as_float(hi[j]));
+    } else {  // NCOL == 16: one load brings hi (cols 0..7) and lo (cols 8..15)
+        uint32_t hl[16];
+        ptx::tmem_ld16(taddr, hl);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = __fmaf_rn(__uint_as_float(hl[8 + j]), lo_inv_scale, __uint_as_float(hl[j]));
+            v[8 + j] = neg_inf();
+        }
+    }
+}
+
 template <bool BF16, int NCOL>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p) {
+    constexpr int NQ = NCOL / 2;                 // queries per pass: column j = q_hi[j], column NQ + j = q_lo[j]
     constexpr int AS = mma_acc_stages<NCOL>();
-    constexpr uint32_t TMEM_COLS = AS * NCOL;  // power of two, 128..512
+    constexpr uint32_t TMEM_COLS = AS * NCOL;    // power of two, 128..512
     static_assert(NCOL % 16 == 0 && NCOL >= 16 && NCOL <= 256, "MMA N");
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM cols");
     constexpr uint32_t IDESC = ptx::umma_idesc_f16(kTileRows, NCOL, BF16);
@@ -161,50 +261,55 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     const int KPS = p.kps;                 // KB % KPS == 0
     const int KG = KB / KPS;               // ring stages consumed per tile
     const uint32_t stage_bytes = (uint32_t)KPS * kStageBytes;
-    unsigned char *q_smem = smem;                                   // KB x {hi, lo} tiles of NCOL*128 B
-    unsigned char *a_smem = q_smem + (size_t)KB * 2 * NCOL * 128;   // S stages of KPS x 16 KB
+    unsigned char *q_smem = smem;                                   // KB tiles of NCOL*128 B
+    unsigned char *a_smem = q_smem + (size_t)KB * NCOL * 128;       // S stages of KPS x 16 KB
     uint64_t *bars = reinterpret_cast<uint64_t *>(a_smem + (size_t)S * stage_bytes);
     uint64_t *full = bars;                       // [kMaxStages]
     uint64_t *empty = bars + kMaxStages;         // [kMaxStages]
     uint64_t *tfull = bars + 2 * kMaxStages;     // [kMaxAccStages]
     uint64_t *tempty = tfull + kMaxAccStages;    // [kMaxAccStages]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kMaxAccStages);
-    ListView<uint32_t> L = list_carve<uint32_t>(reinterpret_cast<unsigned char *>(bars) + 1024, NCOL, p.k);
+    ListView<uint32_t> L = list_carve<uint32_t>(reinterpret_cast<unsigned char *>(bars) + 1024, NQ, p.k);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int warp = __shfl_sync(kFullMask, tid >> 5, 0);  // warp-uniform by construction
 
     // ---- one-time setup ------------------------------------------------------
-    if (warp == 5 && lane == 0) {
-        for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(full + s, 1);
-            ptx::mbar_init(empty + s, 1);
-        }
-        for (int a = 0; a < AS; ++a) {
-            ptx::mbar_init(tfull + a, 1);
-            ptx::mbar_init(tempty + a, 4);
-        }
-        ptx::fence_mbar_init();
-    }
+    // Warp 4 (TMA producer) sets up the barriers and TMEM, then starts streaming documents at once;
+    // the other five warps stage the queries meanwhile and meet it at named barrier 1.
+    uint32_t tmem_base = 0;
     if (warp == 4) {
-        if (lane == 0) ptx::prefetch_tmap(&tmap_docs);
+        if (lane == 0) {
+            ptx::prefetch_tmap(&tmap_docs);
+            for (int s = 0; s < S; ++s) {
+                ptx::mbar_init(full + s, 1);
+                ptx::mbar_init(empty + s, 1);
+            }
+            for (int a = 0; a < AS; ++a) {
+                ptx::mbar_init(tfull + a, 1);
+                ptx::mbar_init(tempty + a, 4);
+            }
+            ptx::fence_mbar_init();
+        }
         __syncwarp();
         ptx::tmem_alloc(tmem_slot, TMEM_COLS);
         ptx::tmem_relinquish();
-    }
-    list_init(L, NCOL, tid, kMmaThreads);
-    grid_launch_dependents();  // lets the (PDL) candidate-reduce grid be scheduled as SMs drain
-    // padding columns never produce candidates (same thread wrote tau[q] in list_init)
-    for (int q = tid; q < NCOL; q += kMmaThreads)
-        if (q >= p.nq) L.tau[q] = __int_as_float(0x7f800000);
-
-    // queries -> shared memory, K-major, 128B-swizzled, hi (and lo) parts.
-    // unit of work: one 16-byte chunk (8 elements) of one query row.
-    {
+        ptx::tc_fence_before_sync();
+        named_bar_arrive(1, kMmaThreads);
+    } else {
+        const int stid = tid < 128 ? tid : tid - 32;  // 0..159 over warps 0-3 and 5
+        constexpr int NST = kMmaThreads - 32;
+        list_init(L, NQ, stid, NST);
+        grid_launch_dependents();  // lets the (PDL) candidate-reduce grid be scheduled as SMs drain
+        // padding queries never produce candidates (same thread wrote tau[q] in list_init)
+        for (int q = stid; q < NQ; q += NST)
+            if (q >= p.nq) L.tau[q] = __int_as_float(0x7f800000);
+        // queries -> shared memory, K-major, 128B-swizzled, hi and lo parts.
+        // unit of work: one 16-byte chunk (8 elements) of one query row.
         const int chunks_per_row = p.dim / 8;
-        const int total = NCOL * chunks_per_row;
-        for (int idx = tid; idx < total; idx += kMmaThreads) {
+        const int total = NQ * chunks_per_row;
+        for (int idx = stid; idx < total; idx += NST) {
             const int j = idx / chunks_per_row;   // query row
             const int cg = idx % chunks_per_row;  // global chunk
             const int kb = cg >> 3, c = cg & 7;
@@ -213,75 +318,158 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 const float4 *src = reinterpret_cast<const float4 *>(p.q + (long long)j * p.q_stride + cg * 8);
                 const float4 v0 = src[0], v1 = src[1];
                 const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                split8<BF16>(x, hi, lo);
+                split8<BF16>(x, p.lo_scale, hi, lo);
             }
-            unsigned char *tile = q_smem + (size_t)kb * 2 * NCOL * 128;
-            const int off = j * 128 + ((c ^ (j & 7)) << 4);
-            *reinterpret_cast<uint4 *>(tile + off) = hi;
-            *reinterpret_cast<uint4 *>(tile + NCOL * 128 + off) = lo;
+            unsigned char *tile = q_smem + (size_t)kb * NCOL * 128;
+            const int jl = NQ + j;
+            *reinterpret_cast<uint4 *>(tile + j * 128 + ((c ^ (j & 7)) << 4)) = hi;
+            *reinterpret_cast<uint4 *>(tile + jl * 128 + ((c ^ (jl & 7)) << 4)) = lo;
         }
+        ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        ptx::tc_fence_before_sync();
+        named_bar_sync(1, kMmaThreads);
+        ptx::tc_fence_after_sync();
+        // broadcast through a shuffle so the compiler keeps the TMEM base in a uniform register
+        tmem_base = __shfl_sync(kFullMask, *reinterpret_cast<volatile uint32_t *>(tmem_slot), 0);
     }
-    ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    ptx::tc_fence_after_sync();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
-    // ---- roles ---------------------------------------------------------------
+    // ---- roles: whole warps run the role loops (uniform control flow and uniform operands
+    // for UTMALDG / UTCHMMA); one elected lane issues the asynchronous instructions ----------
     if (warp == 4) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int kg = 0; kg < KG; ++kg, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    ptx::mbar_wait(empty + s, ph ^ 1);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int kg = 0; kg < KG; ++kg, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                ptx::mbar_wait(empty + s, ph ^ 1);
+                if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(full + s, stage_bytes);
                     for (int j = 0; j < KPS; ++j)
                         ptx::tma_load_2d(a_smem + (size_t)s * stage_bytes + (size_t)j * kStageBytes, &tmap_docs,
                                          (kg * KPS + j) * kBlockK, tile * kTileRows, full + s, p.tma_policy);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp == 5) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            uint32_t lt = 0;  // local tile counter
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
-                const int as = lt % AS;
-                const uint32_t aph = (lt / AS) & 1;
-                ptx::mbar_wait(tempty + as, aph ^ 1);
+        uint32_t it = 0;
+        uint32_t lt = 0;  // local tile counter
+        const uint32_t q_base = ptx::smem_u32(q_smem);
+        const uint32_t a_base = ptx::smem_u32(a_smem);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+            const int as = lt % AS;
+            const uint32_t aph = (lt / AS) & 1;
+            ptx::mbar_wait(tempty + as, aph ^ 1);
+            ptx::tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * NCOL);
+            for (int kg = 0; kg < KG; ++kg, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                ptx::mbar_wait(full + s, ph);
                 ptx::tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * NCOL);
-                for (int kg = 0; kg < KG; ++kg, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    ptx::mbar_wait(full + s, ph);
-                    ptx::tc_fence_after_sync();
+                if (ptx::elect_one()) {
                     for (int j = 0; j < KPS; ++j) {
                         const int kb = kg * KPS + j;
-                        const uint32_t a_addr = ptx::smem_u32(a_smem + (size_t)s * stage_bytes + (size_t)j * kStageBytes);
-                        const uint32_t b_addr = ptx::smem_u32(q_smem + (size_t)kb * 2 * NCOL * 128);
+                        const uint64_t da0 = ptx::umma_desc_k_sw128(a_base + (uint32_t)s * stage_bytes + (uint32_t)j * kStageBytes);
+                        const uint64_t db0 = ptx::umma_desc_k_sw128(q_base + (uint32_t)kb * (NCOL * 128));
 #pragma unroll
-                        for (int k4 = 0; k4 < kBlockK / 16; ++k4) {
-                            const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k4 * 32);
-                            const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k4 * 32);
-                            ptx::umma_f16(d_tmem, da, db, IDESC, (kb | k4) != 0 ? 1u : 0u);
-                            if (p.split) {  // + docs x q_lo into the same accumulator columns
-                                const uint64_t dl = ptx::umma_desc_k_sw128(b_addr + NCOL * 128 + k4 * 32);
-                                ptx::umma_f16(d_tmem, da, dl, IDESC, 1u);
+                        for (int k4 = 0; k4 < kBlockK / 16; ++k4)  // +32 bytes along K = +2 in the address field
+                            ptx::umma_f16(d_tmem, da0 + (uint64_t)(k4 * 2), db0 + (uint64_t)(k4 * 2), IDESC,
+                                          (kb | k4) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(empty + s);  // smem stage reusable once these MMAs retire
+                    if (kg == KG - 1) ptx::umma_commit(tfull + as);  // accumulator ready for the epilogue
+                }
+                __syncwarp();
+            }
+        }
+    } else if (NQ <= 32 && p.k <= 32) {
+        // epilogue warps 0..3 (TMEM lane quadrant = warp), per-warp top-k lists in REGISTERS
+        constexpr int RQ = NQ <= 32 ? NQ : 1;  // (keeps the arrays small when this branch is dead)
+        float ls[RQ], tau[RQ];
+        uint32_t li[RQ];
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            ls[q] = neg_inf();
+            li[q] = invalid_id<uint32_t>();
+            tau[q] = q < p.nq ? neg_inf() : __int_as_float(0x7f800000);
+        }
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+            const int as = lt % AS;
+            const uint32_t aph = (lt / AS) & 1;
+            // pick up the other CTAs' thresholds (one coalesced load per warp, issued before the wait)
+            unsigned long long graw = 0;
+            if (p.tau_g != nullptr && lane < p.nq) graw = ld_volatile_u64(p.tau_g + lane);
+            ptx::mbar_wait(tfull + as, aph);
+            ptx::tc_fence_after_sync();
+            if (p.tau_g != nullptr) {
+                const float tg = tau_decode(graw, p.epoch);
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) tau[q] = fmaxf(tau[q], __shfl_sync(kFullMask, tg, q));
+            }
+            const long long row = (long long)tile * kTileRows + warp * 32 + lane;
+            const bool valid = row < p.n_rows;
+            const uint32_t base_row = (uint32_t)(tile * kTileRows + warp * 32);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NCOL);
+#pragma unroll
+            for (int c0 = 0; c0 < RQ; c0 += 16) {
+                float v[16];
+                load_scores16<NCOL>(taddr, c0, p.lo_inv_scale, v);
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < RQ) any |= (v[j] >= tau[c0 + j]);
+                if (__ballot_sync(kFullMask, any && valid) == 0) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (c0 + j < RQ) {
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int q = c0 + j;
+                        const bool pass = valid && v[j] >= tau[q];
+                        unsigned m = __ballot_sync(kFullMask, pass);
+                        if (m != 0) {
+                            if (__popc(m) >= 4) {
+                                const Entry e = reglist_merge32(ls[q], li[q], pass ? v[j] : neg_inf(),
+                                                                pass ? base_row + lane : invalid_id<uint32_t>(), false);
+                                ls[q] = e.s;
+                                li[q] = e.i;
+                            } else {
+                                while (m) {
+                                    const int src = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const Entry e = reglist_insert_one(ls[q], li[q], __shfl_sync(kFullMask, v[j], src),
+                                                                       base_row + src);
+                                    ls[q] = e.s;
+                                    li[q] = e.i;
+                                }
+                            }
+                            const uint32_t last = __shfl_sync(kFullMask, li[q], p.k - 1);
+                            const float ts = __shfl_sync(kFullMask, ls[q], p.k - 1);
+                            if (last != invalid_id<uint32_t>() && ts > tau[q]) {
+                                tau[q] = ts;
+                                if (p.tau_g != nullptr && lane == 0) atomicMax(p.tau_g + q, tau_encode(ts, p.epoch));
                             }
                         }
                     }
-                    ptx::umma_commit(empty + s);  // smem stage reusable once these MMAs retire
                 }
-                ptx::umma_commit(tfull + as);  // accumulator ready for the epilogue
             }
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty + as);
         }
-        __syncwarp();
+        // Every MMA (hence every TMA write) of this CTA has retired once the last accumulator was
+        // handed over: the document ring is free, park this warp's lists there for the CTA merge.
+        float *ms = reinterpret_cast<float *>(a_smem);
+        uint32_t *mi = reinterpret_cast<uint32_t *>(a_smem + 4 * RQ * 32 * sizeof(float));
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            ms[(warp * RQ + q) * 32 + lane] = ls[q];
+            mi[(warp * RQ + q) * 32 + lane] = li[q];
+        }
     } else {
-        // epilogue warps 0..3: TMEM lane quadrant = warp
+        // epilogue warps 0..3: TMEM lane quadrant = warp; CTA-shared lists in shared memory (k > 32)
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
             const int as = lt % AS;
@@ -291,17 +479,17 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             const long long row = (long long)tile * kTileRows + warp * 32 + lane;
             const bool valid = row < p.n_rows;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NCOL);
-            for (int c0 = 0; c0 < NCOL; c0 += 16) {
-                uint32_t acc[16];
-                ptx::tmem_ld16(taddr + c0, acc);
-                ptx::tmem_ld_wait();
+#pragma unroll 1
+            for (int c0 = 0; c0 < NQ; c0 += 16) {
                 float v[16];
+                load_scores16<NCOL>(taddr, c0, p.lo_inv_scale, v);
                 bool any = false;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    v[j] = __uint_as_float(acc[j]);
-                    const float thr = *(volatile float *)(L.tau + c0 + j);
-                    any |= (v[j] >= thr);
+                    if (c0 + j < NQ) {
+                        const float thr = *(volatile float *)(L.tau + c0 + j);
+                        any |= (v[j] >= thr);
+                    }
                 }
                 any = any && valid;
                 if (__ballot_sync(kFullMask, any) == 0) continue;
@@ -337,15 +525,34 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     __syncthreads();
     float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride;
     uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride;
-    for (int idx = tid; idx < p.nq * p.k; idx += kMmaThreads) {
-        const int b = idx / p.k, e = idx % p.k;
-        cs[idx] = L.s[b * L.kcap + e];
-        ci[idx] = L.i[b * L.kcap + e];
+    if (NQ <= 32 && p.k <= 32) {
+        // merge the four epilogue warps' lists per query (bitonic, in registers) and publish
+        const float *ms = reinterpret_cast<const float *>(a_smem);
+        const uint32_t *mi = reinterpret_cast<const uint32_t *>(a_smem + 4 * NQ * 32 * sizeof(float));
+        for (int q = warp; q < p.nq; q += kMmaThreads / 32) {
+            float s0 = ms[q * 32 + lane];
+            uint32_t i0 = mi[q * 32 + lane];
+            for (int w = 1; w < 4; ++w) {
+                const Entry e = reglist_merge32(s0, i0, ms[(w * NQ + q) * 32 + lane], mi[(w * NQ + q) * 32 + lane], true);
+                s0 = e.s;
+                i0 = e.i;
+            }
+            if (lane < p.k) {
+                cs[q * p.k + lane] = s0;
+                ci[q * p.k + lane] = i0;
+            }
+        }
+    } else {
+        for (int idx = tid; idx < p.nq * p.k; idx += kMmaThreads) {
+            const int b = idx / p.k, e = idx % p.k;
+            cs[idx] = L.s[b * L.kcap + e];
+            ci[idx] = L.i[b * L.kcap + e];
+        }
     }
     if (warp == 4) {
         __syncwarp();
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        ptx::tmem_dealloc(*reinterpret_cast<volatile uint32_t *>(tmem_slot), TMEM_COLS);
     }
 }
 

@@ -26,13 +26,17 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     p.k = a.k;
     p.n_rows = a.n_rows;
     p.dim = a.dim;
-    p.split = 1;
+    // fp16's 11-bit significand leaves the residual near its subnormal range: scale it up (exactly)
+    p.lo_scale = BF16 ? 1.0f : 2048.0f;
+    p.lo_inv_scale = BF16 ? 1.0f : 1.0f / 2048.0f;
     p.cand_s = a.cand_s;
     p.cand_i = a.cand_i;
     p.cand_stride = a.cand_stride;
     p.n_tiles = (int)((a.n_rows + kTileRows - 1) / kTileRows);
     p.n_stages = a.stages;
     p.kps = a.kps;
+    p.tau_g = a.tau_g;
+    p.epoch = a.epoch;
     p.tma_policy = tma_policy();
     const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps);
     auto kern = mma_topk_kernel<BF16, NCOL>;
@@ -48,6 +52,7 @@ static cudaError_t launch_mma_t(const MmaLaunch &a, cudaStream_t st) {
         case 16: return launch_mma_one<BF16, 16>(a, st);
         case 32: return launch_mma_one<BF16, 32>(a, st);
         case 64: return launch_mma_one<BF16, 64>(a, st);
+        case 128: return launch_mma_one<BF16, 128>(a, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -239,6 +239,7 @@ struct ReduceParams {
     long long id_base;
     float *out_s;     // [nq][k_out]
     long long *out_i;
+    unsigned long long *tau_g_reset;  // [n_queries] shared-threshold slots to clear for the next search, or nullptr
 };
 
 __device__ __forceinline__ float shfl_xor_any(float v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
         p.out_s[(long long)q * p.k_out + lane] = ok ? ls : neg_inf();
         p.out_i[(long long)q * p.k_out + lane] = ok ? (long long)li + p.id_base : -1LL;
     }
+    if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;  // a graph replay reuses the epoch
 }
 
 // k_out in (32, 128]: one warp per query (one CTA of 32 threads), sorted list in shared memory.
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(32) reduce_topk_kernel(const ReduceParams<IdT>
         p.out_s[(long long)q * p.k_out + e] = ok ? L.s[e] : neg_inf();
         p.out_i[(long long)q * p.k_out + e] = ok ? (long long)id + p.id_base : -1LL;
     }
+    if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;
 }
 
 }  // namespace vqa

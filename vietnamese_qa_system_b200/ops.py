@@ -70,8 +70,9 @@ class FlatShard:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h is not None and N._lib is not None:
-            N._lib.vqa_index_destroy(h)
+        lib = getattr(N, "_lib", None) if N is not None else None  # module globals may be gone at exit
+        if h is not None and lib is not None:
+            lib.vqa_index_destroy(h)
             self._h = None
 
     # -- planning / workspace -------------------------------------------------
