@@ -286,6 +286,36 @@ def run_ours(args):
             except Exception as exc:  # noqa: BLE001
                 sweep.append({"batch": b_, "error": f"{type(exc).__name__}: {exc}"})
 
+    # ---- K1 (fused mean-pool + L2 normalise) on BASELINE configs[4]'s shape, then search --
+    pool = None
+    if args.sweep:
+        try:
+            gp = torch.Generator(device=device).manual_seed(5)
+            hb, hs = 256, 256
+            hidden = torch.randn((hb, hs, DIM), generator=gp, device=device, dtype=torch.float32).to(torch.bfloat16)
+            lens = torch.randint(16, hs + 1, (hb,), generator=gp, device=device)
+            mask = (torch.arange(hs, device=device)[None, :] < lens[:, None]).to(torch.int64)
+            valid_bytes = int(lens.sum().item()) * DIM * 2
+            # a second copy so that consecutive timed calls do not find the 100 MB input in the 126 MB L2
+            hidden2 = hidden.clone()
+            flip = [hidden, hidden2]
+            cnt = [0]
+
+            def pool_step():
+                cnt[0] += 1
+                return ops.pool_normalize(flip[cnt[0] & 1], mask)
+
+            pms = timed(pool_step, 40, 4) / 40
+            e2e_q = ops.pool_normalize(hidden, mask)
+            ems = timed(lambda: index.search(ops.pool_normalize(flip[0], mask), TOPK), 5, 2) / 5
+            pool = {"shape": [hb, hs, DIM], "dtype": "bf16", "ms": pms, "valid_token_bytes": valid_bytes,
+                    "achieved_gbs": valid_bytes / (pms / 1e3) / 1e9, "frac_of_hbm_peak": valid_bytes / (pms / 1e3) / 1e9 / hbm_peak,
+                    "full_tensor_bytes": hb * hs * DIM * 2, "pool_then_search_b256_ms": ems,
+                    "note": "masked tokens are never loaded; alternating two input copies (201 MB > L2)"}
+            del hidden, hidden2, e2e_q
+        except Exception as exc:  # noqa: BLE001
+            pool = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -307,7 +337,7 @@ def run_ours(args):
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB per GPU streamed per step)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": K * (launches + merge_launches),
-            "recall_at_10": recall, "fast_vs_verify_max_rel_score_err": max_rel, "sweep": sweep,
+            "recall_at_10": recall, "fast_vs_verify_max_rel_score_err": max_rel, "sweep": sweep, "pool_k1": pool,
             "lib": f"libvqa_b200.so v{vqa._native.lib().vqa_version()}",
         }
         print(json.dumps(line), flush=True)

@@ -157,6 +157,17 @@ VQA_API int vqa_merge_topk(const float *cand_scores_dev, const int64_t *cand_ids
                            void *stream);
 
 /*
+ * Same merge over a strided layout: list l's scores start at cand_scores_dev + l*list_stride_scores
+ * (float elements) and its ids at cand_ids_dev + l*list_stride_ids (int64 elements).  This is the
+ * layout one all-gather of each rank's packed [scores | ids] result block produces, so the exchange
+ * step needs no repacking kernel.
+ */
+VQA_API int vqa_merge_topk_strided(const float *cand_scores_dev, const int64_t *cand_ids_dev,
+                                   int64_t list_stride_scores, int64_t list_stride_ids, int32_t n_lists,
+                                   int32_t n_queries, int32_t k_in, int32_t k_out, float *out_scores_dev,
+                                   int64_t *out_ids_dev, int32_t device, void *stream);
+
+/*
  * Fused masked mean-pool (+ optional L2 normalise) over encoder hidden states:
  *   e[b,:] = sum_s h[b,s,:]*m[b,s] / max(sum_s m[b,s], 1e-9);  e /= ||e||_2
  * Replaces: txtai MeanPooling.forward + normalize under Embeddings.search()/

@@ -440,22 +440,31 @@ int vqa_search_host(const vqa_index_t *h, const float *queries_host, int32_t n_q
     return VQA_OK;
 }
 
-int vqa_merge_topk(const float *cand_scores_dev, const int64_t *cand_ids_dev, int32_t n_lists, int32_t n_queries,
-                   int32_t k_in, int32_t k_out, float *out_scores_dev, int64_t *out_ids_dev, int32_t device,
-                   void *stream) {
+int vqa_merge_topk_strided(const float *cand_scores_dev, const int64_t *cand_ids_dev, int64_t list_stride_scores,
+                           int64_t list_stride_ids, int32_t n_lists, int32_t n_queries, int32_t k_in, int32_t k_out,
+                           float *out_scores_dev, int64_t *out_ids_dev, int32_t device, void *stream) {
     if (!cand_scores_dev || !cand_ids_dev || !out_scores_dev || !out_ids_dev)
         return fail(VQA_E_INVALID, "null device pointer argument");
     if (n_lists < 1 || n_queries < 1 || k_in < 1) return fail(VQA_E_INVALID, "n_lists, n_queries, k_in must be >= 1");
     if (k_out < 1 || k_out > vqa::kMaxK) return fail(VQA_E_INVALID, "k_out must be in [1, %d]", vqa::kMaxK);
+    if (list_stride_scores < (int64_t)n_queries * k_in || list_stride_ids < (int64_t)n_queries * k_in)
+        return fail(VQA_E_INVALID, "list strides must be >= n_queries * k_in elements");
     if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
-    cudaError_t e = vqa::launch_reduce_i64(cand_scores_dev, (const long long *)cand_ids_dev,
-                                           (long long)n_queries * k_in, k_in, n_lists, k_in, k_out, 0,
-                                           out_scores_dev, (long long *)out_ids_dev, n_queries,
+    cudaError_t e = vqa::launch_reduce_i64(cand_scores_dev, (const long long *)cand_ids_dev, list_stride_scores,
+                                           list_stride_ids, k_in, n_lists, k_in, k_out, 0, out_scores_dev,
+                                           (long long *)out_ids_dev, n_queries,
                                            reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(VQA_E_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
     return VQA_OK;
+}
+
+int vqa_merge_topk(const float *cand_scores_dev, const int64_t *cand_ids_dev, int32_t n_lists, int32_t n_queries,
+                   int32_t k_in, int32_t k_out, float *out_scores_dev, int64_t *out_ids_dev, int32_t device,
+                   void *stream) {
+    return vqa_merge_topk_strided(cand_scores_dev, cand_ids_dev, (int64_t)n_queries * k_in, (int64_t)n_queries * k_in,
+                                  n_lists, n_queries, k_in, k_out, out_scores_dev, out_ids_dev, device, stream);
 }
 
 int vqa_pool_normalize(const void *hidden_dev, int32_t h_dtype, const void *mask_dev, int32_t m_dtype,

@@ -57,7 +57,7 @@ cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long 
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                               cudaStream_t st);
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
-                              long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                              long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, cudaStream_t st);
 cudaError_t launch_pool(const void *hidden, int h_dtype, const void *mask, int m_dtype, int batch, int seq,
                         int dim, int normalize, float *out, cudaStream_t st);

@@ -18,7 +18,7 @@ cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st) {
 
 template <typename IdT>
 static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long long list_stride,
-                                   long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                                   long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                                    float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                                    cudaStream_t st) {
     ReduceParams<IdT> p;
@@ -26,6 +26,7 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
     p.cand_s = cand_s;
     p.cand_i = cand_i;
     p.list_stride = list_stride;
+    p.list_stride_i = list_stride_i;
     p.query_stride = query_stride;
     p.n_lists = n_lists;
     p.n_queries = n_queries;
@@ -59,13 +60,13 @@ cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long 
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                               cudaStream_t st) {
-    return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
+    return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
                                      out_i, n_queries, tau_g_reset, st);
 }
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
-                              long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
+                              long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, cudaStream_t st) {
-    return launch_reduce_t<long long>(cand_s, cand_i, list_stride, query_stride, n_lists, k_in, k_out, id_base,
+    return launch_reduce_t<long long>(cand_s, cand_i, list_stride, list_stride_i, query_stride, n_lists, k_in, k_out, id_base,
                                       out_s, out_i, n_queries, nullptr, st);
 }
 
@@ -87,9 +88,33 @@ static cudaError_t launch_pool_tm(const void *hidden, const void *mask, int batc
     return cudaGetLastError();
 }
 
+template <typename T, int ITERS>
+static cudaError_t launch_pool_warp(const void *hidden, const void *mask, int m_dtype, int batch, int seq, int dim,
+                                    int normalize, float *out, cudaStream_t st) {
+    const size_t smem = ((size_t)(kPoolWarps + 1) * dim + 40) * sizeof(float);
+    auto kern = pool_normalize_warp_kernel<T, ITERS>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<batch, kPoolFastThreads, smem, st>>>(static_cast<const unsigned char *>(hidden), mask, m_dtype, seq, dim,
+                                               normalize, out);
+    return cudaGetLastError();
+}
+
 template <typename T>
 static cudaError_t launch_pool_t(const void *hidden, const void *mask, int m_dtype, int batch, int seq, int dim,
                                  int normalize, float *out, cudaStream_t st) {
+    // rows of up to 2 KB (16-bit) / 4 KB (fp32): warp-per-token fast path
+    const int iters = (dim / Elem<T>::E + 31) / 32;
+    if (iters <= 1) return launch_pool_warp<T, 1>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+    if (iters <= 2) return launch_pool_warp<T, 2>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+    if (iters <= 3) return launch_pool_warp<T, 3>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+    if (iters <= 4) return launch_pool_warp<T, 4>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+    if constexpr (Elem<T>::E == 4) {
+        if (iters <= 6) return launch_pool_warp<T, 6>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+        if (iters <= 8) return launch_pool_warp<T, 8>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
+    }
     switch (m_dtype) {
         case VQA_I64: return launch_pool_tm<T, long long>(hidden, mask, batch, seq, dim, normalize, out, st);
         case VQA_I32: return launch_pool_tm<T, int>(hidden, mask, batch, seq, dim, normalize, out, st);

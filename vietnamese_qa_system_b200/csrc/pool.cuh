@@ -120,6 +120,105 @@ pool_normalize_kernel(const unsigned char *__restrict__ hidden, const MT *__rest
     }
 }
 
+// mask element by runtime dtype code (vqa_dtype): I64=3, I32=4, U8=5, F32=0
+__device__ __forceinline__ float mask_at(const void *m, int mdt, long long idx) {
+    switch (mdt) {
+        case 3: return (float)static_cast<const long long *>(m)[idx];
+        case 4: return (float)static_cast<const int *>(m)[idx];
+        case 5: return (float)static_cast<const unsigned char *>(m)[idx];
+        default: return static_cast<const float *>(m)[idx];
+    }
+}
+
+// Fast path (row of <= ITERS*512 bytes): one warp per TOKEN, lanes stride over the row's 16-byte
+// chunks, 4 tokens in flight per warp (ITERS*4 independent 128-bit loads per lane), 16 warps per CTA
+// splitting the sequence, fp32 partial sums combined through shared memory.  grid = B.
+// dynamic smem: (16 + 1) * dim + 40 floats.
+constexpr int kPoolFastThreads = 512;
+constexpr int kPoolWarps = kPoolFastThreads / 32;
+constexpr int kPoolUnroll = 4;
+
+template <typename T, int ITERS>
+__global__ void __launch_bounds__(kPoolFastThreads, (ITERS * (16 / (int)sizeof(T)) <= 24) ? 2 : 1)
+pool_normalize_warp_kernel(const unsigned char *__restrict__ hidden, const void *__restrict__ mask, int mdt, int seq,
+                           int dim, int normalize, float *__restrict__ out) {
+    constexpr int E = Elem<T>::E;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *part = reinterpret_cast<float *>(smem);          // [kPoolWarps][dim]
+    float *pooled = part + (size_t)kPoolWarps * dim;        // [dim]
+    float *red = pooled + dim;                              // [32]
+    float *cntw = red + 32;                                 // [kPoolWarps]
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchunks = dim / E;
+    const unsigned char *hrow = hidden + (long long)b * seq * dim * sizeof(T);
+    const long long mbase = (long long)b * seq;
+
+    float acc[ITERS][E];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[i][e] = 0.f;
+    float cnt = 0.f;
+    for (int s0 = warp * kPoolUnroll; s0 < seq; s0 += kPoolWarps * kPoolUnroll) {
+        float m[kPoolUnroll];
+        uint4 w[kPoolUnroll][ITERS];
+#pragma unroll
+        for (int u = 0; u < kPoolUnroll; ++u) m[u] = s0 + u < seq ? mask_at(mask, mdt, mbase + s0 + u) : 0.f;
+#pragma unroll
+        for (int u = 0; u < kPoolUnroll; ++u) {
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i) {
+                w[u][i] = make_uint4(0, 0, 0, 0);
+                const int c = i * 32 + lane;
+                if (m[u] != 0.f && c < nchunks)
+                    w[u][i] = ldg_stream(hrow + ((long long)(s0 + u) * dim + (long long)c * E) * sizeof(T));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPoolUnroll; ++u) {
+            cnt += m[u];
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i) {
+                float x[E];
+                Elem<T>::unpack(w[u][i], x);
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[i][e] = fmaf(x[e], m[u], acc[i][e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) part[(size_t)warp * dim + c * E + e] = acc[i][e];
+        }
+    }
+    if (lane == 0) cntw[warp] = cnt;
+    __syncthreads();
+    float total_cnt = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < kPoolWarps; ++w2) total_cnt += cntw[w2];
+    const float den = fmaxf(total_cnt, 1e-9f);
+    float ss = 0.f;
+    for (int d = tid; d < dim; d += kPoolFastThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < kPoolWarps; ++w2) t += part[(size_t)w2 * dim + d];
+        const float mean = t / den;
+        pooled[d] = mean;
+        ss += mean * mean;
+    }
+    ss = block_sum(ss, red);
+    float *orow = out + (long long)b * dim;
+    if (normalize) {
+        const float nrm = sqrtf(ss);
+        for (int d = tid; d < dim; d += kPoolFastThreads) orow[d] = nrm > 0.f ? pooled[d] / nrm : 0.f;
+    } else {
+        for (int d = tid; d < dim; d += kPoolFastThreads) orow[d] = pooled[d];
+    }
+}
+
 // Row-wise L2 normalise: one warp per row, float4 accesses.  Optional cast copy.
 // cast_kind: 0 none, 1 bf16, 2 f16.
 __global__ void __launch_bounds__(256)

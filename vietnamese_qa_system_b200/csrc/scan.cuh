@@ -230,8 +230,9 @@ template <typename IdT>
 struct ReduceParams {
     const float *cand_s;
     const IdT *cand_i;
-    long long list_stride;   // elements between lists
-    long long query_stride;  // elements between queries inside a list
+    long long list_stride;    // score elements between lists
+    long long list_stride_i;  // id elements between lists
+    long long query_stride;   // elements between queries inside a list
     int n_lists;
     int n_queries;
     int k_in;
@@ -273,16 +274,27 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
     const long long total = (long long)p.n_lists * p.k_in;
     const float *qs = p.cand_s + (long long)q * p.query_stride;
     const IdT *qi = p.cand_i + (long long)q * p.query_stride;
-    for (long long base = 0; base < total; base += 32) {
-        const long long idx = base + lane;
-        float s = neg_inf();
-        IdT id = invalid_id<IdT>();
-        if (idx < total) {
-            const int e = (int)(idx / p.n_lists);
-            const int l = (int)(idx - (long long)e * p.n_lists);
-            s = qs[(long long)l * p.list_stride + e];
-            id = qi[(long long)l * p.list_stride + e];
-        }
+    constexpr int PF = 8;  // chunks whose (independent) loads are issued together: hides the L2 latency
+    for (long long base0 = 0; base0 < total; base0 += 32 * PF) {
+      float sv[PF];
+      IdT iv[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+          const long long idx = base0 + u * 32 + lane;
+          sv[u] = neg_inf();
+          iv[u] = invalid_id<IdT>();
+          if (idx < total) {
+              const int e = (int)(idx / p.n_lists);
+              const int l = (int)(idx - (long long)e * p.n_lists);
+              sv[u] = qs[(long long)l * p.list_stride + e];
+              iv[u] = qi[(long long)l * p.list_stride_i + e];
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (base0 + u * 32 >= total) break;  // warp-uniform
+        const float s = sv[u];
+        const IdT id = iv[u];
         bool valid = id != invalid_id<IdT>();
         if constexpr (sizeof(IdT) == 8) valid = valid && id >= 0;
         const bool pass = valid && s >= tau;
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
         li = ci;
         const IdT last = shfl_any(li, p.k_out - 1);
         tau = last != invalid_id<IdT>() ? __shfl_sync(kFullMask, ls, p.k_out - 1) : neg_inf();
+      }
     }
     if (lane < p.k_out) {
         const bool ok = li != invalid_id<IdT>();
@@ -333,7 +346,7 @@ __global__ void __launch_bounds__(32) reduce_topk_kernel(const ReduceParams<IdT>
     for (int e0 = 0; e0 < kin_pad; e0 += 32) {
         for (int l = 0; l < p.n_lists; ++l) {
             const float *ls = p.cand_s + (long long)l * p.list_stride + (long long)q * p.query_stride;
-            const IdT *li = p.cand_i + (long long)l * p.list_stride + (long long)q * p.query_stride;
+            const IdT *li = p.cand_i + (long long)l * p.list_stride_i + (long long)q * p.query_stride;
             const int e = e0 + lane;
             float s = neg_inf();
             IdT id = invalid_id<IdT>();

@@ -160,6 +160,27 @@ def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int):
     return out_s, out_i
 
 
+def merge_topk_packed(gathered: torch.Tensor, n_lists: int, n_queries: int, k: int, ids_offset: int,
+                      out_scores: Optional[torch.Tensor] = None, out_ids: Optional[torch.Tensor] = None):
+    """K4 over the all-gathered packed blocks: ``gathered`` is uint8 ``[n_lists * block]`` where each rank's
+    block holds float32 ``[B,k]`` scores at byte 0 and int64 ``[B,k]`` ids at byte ``ids_offset``."""
+    _need_cuda(gathered, "gathered")
+    block = gathered.numel() // n_lists
+    if gathered.dtype != torch.uint8 or block * n_lists != gathered.numel() or block % 8 or ids_offset % 8:
+        raise ValueError("gathered must be uint8 [n_lists * block] with 8-byte aligned blocks")
+    dev = gathered.device
+    if out_scores is None:
+        out_scores = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+    if out_ids is None:
+        out_ids = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+    base = gathered.data_ptr()
+    N.check(N.lib().vqa_merge_topk_strided(ctypes.c_void_p(base), ctypes.c_void_p(base + ids_offset), block // 4,
+                                           block // 8, n_lists, n_queries, k, k,
+                                           ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(out_ids.data_ptr()),
+                                           dev.index or 0, ctypes.c_void_p(_stream(dev))))
+    return out_scores, out_ids
+
+
 def pool_normalize(hidden: torch.Tensor, mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:
     """K1: hidden [B,S,D] (f32/bf16/f16), mask [B,S] (int64/int32/bool/uint8/f32) -> float32 [B,D]."""
     _need_cuda(hidden, "hidden")

@@ -69,14 +69,19 @@ class ShardedSearch:
 
 
 class ShardedFlat:
-    """The product wiring: ``ops.FlatShard`` scan + NCCL all-gather + ``ops.merge_topk``.
+    """The product wiring: ``ops.FlatShard`` scan + ONE NCCL all-gather + merge-top-k (K4).
 
     One process per GPU (torchrun); ``rows`` is THIS rank's block, already in storage dtype.
+    The local search writes its ``[B,k]`` scores and ids straight into one packed byte block, the
+    all-gather moves that block, and the merge kernel reads the gathered blocks in place: four
+    kernels per search (scan, candidate reduce, all-gather, merge) and no repacking.
     """
 
     def __init__(self, rows: torch.Tensor, n_total: int, group=None, mode="fast"):
         from . import ops
 
+        self._ops = ops
+        self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         lo, hi = shard_bounds(n_total, self.world, self.rank)
@@ -85,10 +90,34 @@ class ShardedFlat:
         self.n_total = n_total
         self.shard = ops.FlatShard(rows, first_global_id=lo)
         self.mode = mode
-        self._driver = ShardedSearch(lambda q, k: self.shard.search(q, k, self.mode),
-                                     lambda gs, gi, k: ops.merge_topk(gs, gi, k), group)
+        self._bufs = {}
+
+    def _buffers(self, b: int, k: int):
+        key = (b, k)
+        buf = self._bufs.get(key)
+        if buf is None:
+            dev = self.shard.device
+            ids_off = (b * k * 4 + 15) // 16 * 16
+            block = (ids_off + b * k * 8 + 15) // 16 * 16
+            local = torch.zeros(block, dtype=torch.uint8, device=dev)
+            gathered = torch.empty(block * self.world, dtype=torch.uint8, device=dev)
+            s_view = local[:b * k * 4].view(torch.float32).view(b, k)
+            i_view = local[ids_off:ids_off + b * k * 8].view(torch.int64).view(b, k)
+            out_s = torch.empty((b, k), dtype=torch.float32, device=dev)
+            out_i = torch.empty((b, k), dtype=torch.int64, device=dev)
+            buf = (local, gathered, s_view, i_view, ids_off, out_s, out_i)
+            self._bufs[key] = buf
+        return buf
 
     def search(self, queries: torch.Tensor, k: int, mode: Optional[str] = None):
+        """Returns (scores [B,k], ids [B,k]) -- identical on every rank.  The returned tensors are
+        reused by the next search with the same (B, k)."""
         if mode is not None:
             self.mode = mode
-        return self._driver.search(queries, k)
+        if self.world == 1:
+            return self.shard.search(queries, k, self.mode)
+        b = int(queries.shape[0]) if queries.dim() == 2 else 1
+        local, gathered, s_view, i_view, ids_off, out_s, out_i = self._buffers(b, k)
+        self.shard.search(queries, k, self.mode, s_view, i_view)
+        dist.all_gather_into_tensor(gathered, local, group=self.group)
+        return self._ops.merge_topk_packed(gathered, self.world, b, k, ids_off, out_s, out_i)
