@@ -109,6 +109,7 @@ struct Plan {
     int stages;   // tensor: smem ring depth (stages of kps x 16 KB)
     int kps;      // tensor: k-blocks per stage
     int passes;
+    int groups;   // tensor: query chunks handled side by side per launch (documents shared through L2)
     int grid;
 };
 
@@ -148,6 +149,9 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
         pl->stages = stages;
         pl->kps = kps;
         pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
+        int gmax = env_int("VQA_MMA_GROUPS", 4);
+        if (gmax < 1) gmax = 1;
+        pl->groups = pl->passes < gmax ? pl->passes : gmax;
         long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
         pl->grid = (int)(tiles < h->sm_count ? (tiles > 0 ? tiles : 1) : h->sm_count);
         return true;
@@ -161,6 +165,7 @@ void plan_stream(const vqa_index *h, int nq, Plan *pl) {
     pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
     pl->ncol = 0;
     pl->stages = 0;
+    pl->groups = 1;
     pl->grid = h->sm_count;
 }
 
@@ -298,7 +303,8 @@ int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t 
     rc = make_plan(h, n_queries, k, mode, &pl);
     if (rc) return rc;
     if (family) *family = pl.family;
-    if (n_launches) *n_launches = pl.passes + 1;
+    if (n_launches)
+        *n_launches = pl.family == VQA_MODE_FAST_TENSOR ? 2 * ((pl.passes + pl.groups - 1) / pl.groups) : pl.passes + 1;
     return VQA_OK;
 }
 
@@ -343,56 +349,72 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     static std::atomic<uint32_t> g_epoch{1};
     const uint32_t epoch = g_epoch.fetch_add(2, std::memory_order_relaxed);  // odd, unique, never 0 (0 = cleared slot)
 
+    if (pl.family == VQA_MODE_FAST_TENSOR && h->n_rows > 0) {
+        // Each launch covers up to groups * pass_nq queries: CTA c scans tile stream c / g for query chunk
+        // c % g, so one pass over HBM serves the whole launch; its candidate lists are reduced right away.
+        const int per_launch = pl.groups * pl.pass_nq;
+        const long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
+        for (int l0 = 0; l0 < n_queries; l0 += per_launch) {
+            const int nq = n_queries - l0 < per_launch ? n_queries - l0 : per_launch;
+            const int g = (nq + pl.pass_nq - 1) / pl.pass_nq;
+            long long streams = h->sm_count / g;
+            if (streams > tiles) streams = tiles;
+            if (streams < 1) streams = 1;
+            vqa::MmaLaunch a;
+            a.tmap = &h->tmap;
+            a.bf16 = h->dtype == VQA_BF16;
+            a.ncol = pl.ncol;
+            a.stages = pl.stages;
+            a.kps = pl.kps;
+            a.grid = (int)streams * g;
+            a.n_groups = g;
+            a.q = queries_dev + (long long)l0 * q_stride;
+            a.q_stride = q_stride;
+            a.nq = nq;
+            a.k = k;
+            a.n_rows = h->n_rows;
+            a.dim = h->dim;
+            a.cand_s = cand_s + (long long)l0 * k;
+            a.cand_i = cand_i + (long long)l0 * k;
+            a.cand_stride = cand_stride;
+            a.tau_g = tau_g + l0;
+            a.epoch = epoch;
+            cudaError_t e = vqa::launch_mma(a, st);
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
+            e = vqa::launch_reduce_u32(cand_s + (long long)l0 * k, cand_i + (long long)l0 * k, cand_stride, k, a.grid, k, k,
+                                       h->first_id, out_scores_dev + (long long)l0 * k,
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st);
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+        }
+        return VQA_OK;
+    }
+
     int n_lists = 0;
     if (h->n_rows > 0) {
         n_lists = pl.grid;
         for (int p0 = 0; p0 < n_queries; p0 += pl.pass_nq) {
             const int nq = n_queries - p0 < pl.pass_nq ? n_queries - p0 : pl.pass_nq;
-            cudaError_t e;
-            if (pl.family == VQA_MODE_FAST_TENSOR) {
-                vqa::MmaLaunch a;
-                a.tmap = &h->tmap;
-                a.bf16 = h->dtype == VQA_BF16;
-                a.ncol = pl.ncol;
-                a.stages = pl.stages;
-                a.kps = pl.kps;
-                a.grid = pl.grid;
-                a.q = queries_dev + (long long)p0 * q_stride;
-                a.q_stride = q_stride;
-                a.nq = nq;
-                a.k = k;
-                a.n_rows = h->n_rows;
-                a.dim = h->dim;
-                a.cand_s = cand_s + (long long)p0 * k;
-                a.cand_i = cand_i + (long long)p0 * k;
-                a.cand_stride = cand_stride;
-                a.tau_g = tau_g + p0;
-                a.epoch = epoch;
-                e = vqa::launch_mma(a, st);
-            } else {
-                vqa::ScanLaunch a;
-                a.dtype = h->dtype;
-                a.bt = pl.pass_nq;
-                a.grid = pl.grid;
-                a.rows = h->rows;
-                a.n_rows = h->n_rows;
-                a.row_stride_bytes = h->stride;
-                a.dim = h->dim;
-                a.q = queries_dev + (long long)p0 * q_stride;
-                a.q_stride = q_stride;
-                a.nq = nq;
-                a.k = k;
-                a.cand_s = cand_s + (long long)p0 * k;
-                a.cand_i = cand_i + (long long)p0 * k;
-                a.cand_stride = cand_stride;
-                e = vqa::launch_scan(a, st);
-            }
+            vqa::ScanLaunch a;
+            a.dtype = h->dtype;
+            a.bt = pl.pass_nq;
+            a.grid = pl.grid;
+            a.rows = h->rows;
+            a.n_rows = h->n_rows;
+            a.row_stride_bytes = h->stride;
+            a.dim = h->dim;
+            a.q = queries_dev + (long long)p0 * q_stride;
+            a.q_stride = q_stride;
+            a.nq = nq;
+            a.k = k;
+            a.cand_s = cand_s + (long long)p0 * k;
+            a.cand_i = cand_i + (long long)p0 * k;
+            a.cand_stride = cand_stride;
+            cudaError_t e = vqa::launch_scan(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
         }
     }
-    cudaError_t e = vqa::launch_reduce_u32(cand_s, cand_i, cand_stride, k, n_lists, k, k, h->first_id,
-                                           out_scores_dev, (long long *)out_ids_dev, n_queries,
-                                           pl.family == VQA_MODE_FAST_TENSOR ? tau_g : nullptr, st);
+    cudaError_t e = vqa::launch_reduce_u32(cand_s, cand_i, cand_stride, k, n_lists, k, k, h->first_id, out_scores_dev,
+                                           (long long *)out_ids_dev, n_queries, nullptr, 1, 1, st);
     if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
     return VQA_OK;
 }

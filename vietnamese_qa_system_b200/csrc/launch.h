@@ -33,6 +33,7 @@ struct MmaLaunch {
     int stages;  // ring stages, each kps x 16 KB
     int kps;
     int grid;
+    int n_groups;  // query chunks of ncol/2 handled side by side in one launch (grid % n_groups == 0)
     const float *q;
     long long q_stride;
     int nq;
@@ -55,7 +56,7 @@ cudaError_t launch_mma(const MmaLaunch &a, cudaStream_t st);
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              cudaStream_t st);
+                              int list_mod, int queries_per_group, cudaStream_t st);
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, cudaStream_t st);

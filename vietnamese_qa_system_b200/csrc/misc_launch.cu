@@ -20,9 +20,11 @@ template <typename IdT>
 static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long long list_stride,
                                    long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                                    float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                                   cudaStream_t st) {
+                                   int list_mod, int queries_per_group, cudaStream_t st) {
     ReduceParams<IdT> p;
     p.tau_g_reset = tau_g_reset;
+    p.list_mod = list_mod;
+    p.queries_per_group = queries_per_group;
     p.cand_s = cand_s;
     p.cand_i = cand_i;
     p.list_stride = list_stride;
@@ -59,15 +61,15 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              cudaStream_t st) {
+                              int list_mod, int queries_per_group, cudaStream_t st) {
     return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
-                                     out_i, n_queries, tau_g_reset, st);
+                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st);
 }
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, cudaStream_t st) {
     return launch_reduce_t<long long>(cand_s, cand_i, list_stride, list_stride_i, query_stride, n_lists, k_in, k_out, id_base,
-                                      out_s, out_i, n_queries, nullptr, st);
+                                      out_s, out_i, n_queries, nullptr, 1, 1, st);
 }
 
 template <typename T, typename MT>

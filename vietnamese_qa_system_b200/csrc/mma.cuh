@@ -38,7 +38,10 @@ namespace vqa {
 struct MmaParams {
     const float *q;
     long long q_stride;
-    int nq;  // queries in this pass: nq <= NCOL / 2 (hi and lo column per query)
+    int nq;  // queries in this LAUNCH: n_groups chunks of NCOL / 2 (hi and lo column per query); the last may be short
+    int n_groups;  // query chunks processed side by side: CTA c works on chunk c % n_groups, tile stream
+                   // c / n_groups, so the chunks' CTAs read the same document tiles at the same time and
+                   // all but the first read hit L2 (one HBM pass serves n_groups * NCOL/2 queries)
     int k;
     long long n_rows;
     int dim;  // multiple of 64
@@ -274,6 +277,13 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);  // warp-uniform by construction
+    const int grp = blockIdx.x % p.n_groups;               // query chunk of this CTA
+    const int stream0 = blockIdx.x / p.n_groups;           // first document tile of this CTA
+    const int n_streams = gridDim.x / p.n_groups;
+    const int q0 = grp * NQ;                               // first query of the chunk
+    const int nq = p.nq - q0 < NQ ? (p.nq - q0 > 0 ? p.nq - q0 : 0) : NQ;  // queries in this CTA's chunk
+    const float *qsrc = p.q + (long long)q0 * p.q_stride;
+    unsigned long long *tau_g = p.tau_g != nullptr ? p.tau_g + q0 : nullptr;
 
     // ---- one-time setup ------------------------------------------------------
     // Warp 4 (TMA producer) sets up the barriers and TMEM, then starts streaming documents at once;
@@ -304,7 +314,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         grid_launch_dependents();  // lets the (PDL) candidate-reduce grid be scheduled as SMs drain
         // padding queries never produce candidates (same thread wrote tau[q] in list_init)
         for (int q = stid; q < NQ; q += NST)
-            if (q >= p.nq) L.tau[q] = __int_as_float(0x7f800000);
+            if (q >= nq) L.tau[q] = __int_as_float(0x7f800000);
         // queries -> shared memory, K-major, 128B-swizzled, hi and lo parts.
         // unit of work: one 16-byte chunk (8 elements) of one query row.
         const int chunks_per_row = p.dim / 8;
@@ -314,8 +324,8 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             const int cg = idx % chunks_per_row;  // global chunk
             const int kb = cg >> 3, c = cg & 7;
             uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-            if (j < p.nq) {
-                const float4 *src = reinterpret_cast<const float4 *>(p.q + (long long)j * p.q_stride + cg * 8);
+            if (j < nq) {
+                const float4 *src = reinterpret_cast<const float4 *>(qsrc + (long long)j * p.q_stride + cg * 8);
                 const float4 v0 = src[0], v1 = src[1];
                 const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                 split8<BF16>(x, p.lo_scale, hi, lo);
@@ -337,7 +347,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     // for UTMALDG / UTCHMMA); one elected lane issues the asynchronous instructions ----------
     if (warp == 4) {
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = stream0; tile < p.n_tiles; tile += n_streams) {
             for (int kg = 0; kg < KG; ++kg, ++it) {
                 const int s = it % S;
                 const uint32_t ph = (it / S) & 1;
@@ -356,7 +366,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         uint32_t lt = 0;  // local tile counter
         const uint32_t q_base = ptx::smem_u32(q_smem);
         const uint32_t a_base = ptx::smem_u32(a_smem);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
             ptx::mbar_wait(tempty + as, aph ^ 1);
@@ -392,18 +402,18 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         for (int q = 0; q < RQ; ++q) {
             ls[q] = neg_inf();
             li[q] = invalid_id<uint32_t>();
-            tau[q] = q < p.nq ? neg_inf() : __int_as_float(0x7f800000);
+            tau[q] = q < nq ? neg_inf() : __int_as_float(0x7f800000);
         }
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
             // pick up the other CTAs' thresholds (one coalesced load per warp, issued before the wait)
             unsigned long long graw = 0;
-            if (p.tau_g != nullptr && lane < p.nq) graw = ld_volatile_u64(p.tau_g + lane);
+            if (tau_g != nullptr && lane < nq) graw = ld_volatile_u64(tau_g + lane);
             ptx::mbar_wait(tfull + as, aph);
             ptx::tc_fence_after_sync();
-            if (p.tau_g != nullptr) {
+            if (tau_g != nullptr) {
                 const float tg = tau_decode(graw, p.epoch);
 #pragma unroll
                 for (int q = 0; q < RQ; ++q) tau[q] = fmaxf(tau[q], __shfl_sync(kFullMask, tg, q));
@@ -449,7 +459,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                             const float ts = __shfl_sync(kFullMask, ls[q], p.k - 1);
                             if (last != invalid_id<uint32_t>() && ts > tau[q]) {
                                 tau[q] = ts;
-                                if (p.tau_g != nullptr && lane == 0) atomicMax(p.tau_g + q, tau_encode(ts, p.epoch));
+                                if (tau_g != nullptr && lane == 0) atomicMax(tau_g + q, tau_encode(ts, p.epoch));
                             }
                         }
                     }
@@ -471,7 +481,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     } else {
         // epilogue warps 0..3: TMEM lane quadrant = warp; CTA-shared lists in shared memory (k > 32)
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
             ptx::mbar_wait(tfull + as, aph);
@@ -496,7 +506,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int qi = c0 + j;
-                    if (qi >= p.nq) break;  // warp-uniform
+                    if (qi >= nq) break;  // warp-uniform
                     const float thr = *(volatile float *)(L.tau + qi);
                     const bool pass = valid && v[j] >= thr;
                     unsigned m = __ballot_sync(kFullMask, pass);
@@ -523,13 +533,13 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     // ---- teardown --------------------------------------------------------------
     ptx::tc_fence_before_sync();
     __syncthreads();
-    float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride;
-    uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride;
+    float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride + (long long)q0 * p.k;
+    uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride + (long long)q0 * p.k;
     if (NQ <= 32 && p.k <= 32) {
         // merge the four epilogue warps' lists per query (bitonic, in registers) and publish
         const float *ms = reinterpret_cast<const float *>(a_smem);
         const uint32_t *mi = reinterpret_cast<const uint32_t *>(a_smem + 4 * NQ * 32 * sizeof(float));
-        for (int q = warp; q < p.nq; q += kMmaThreads / 32) {
+        for (int q = warp; q < nq; q += kMmaThreads / 32) {
             float s0 = ms[q * 32 + lane];
             uint32_t i0 = mi[q * 32 + lane];
             for (int w = 1; w < 4; ++w) {
@@ -543,7 +553,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             }
         }
     } else {
-        for (int idx = tid; idx < p.nq * p.k; idx += kMmaThreads) {
+        for (int idx = tid; idx < nq * p.k; idx += kMmaThreads) {
             const int b = idx / p.k, e = idx % p.k;
             cs[idx] = L.s[b * L.kcap + e];
             ci[idx] = L.i[b * L.kcap + e];

@@ -23,6 +23,7 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     p.q = a.q;
     p.q_stride = a.q_stride;
     p.nq = a.nq;
+    p.n_groups = a.n_groups;
     p.k = a.k;
     p.n_rows = a.n_rows;
     p.dim = a.dim;
@@ -37,7 +38,8 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     p.kps = a.kps;
     p.tau_g = a.tau_g;
     p.epoch = a.epoch;
-    p.tma_policy = tma_policy();
+    // side-by-side chunks re-read each tile from L2: keep it there (normal policy) instead of evict-first
+    p.tma_policy = a.n_groups > 1 ? 0x1000000000000000ull : tma_policy();
     const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps);
     auto kern = mma_topk_kernel<BF16, NCOL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

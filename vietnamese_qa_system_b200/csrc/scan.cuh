@@ -234,6 +234,8 @@ struct ReduceParams {
     long long list_stride_i;  // id elements between lists
     long long query_stride;   // elements between queries inside a list
     int n_lists;
+    int list_mod;           // > 1: query q only appears in lists l with l % list_mod == q / queries_per_group
+    int queries_per_group;
     int n_queries;
     int k_in;
     int k_out;
@@ -271,7 +273,10 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
     float ls = neg_inf();
     IdT li = invalid_id<IdT>();
     float tau = neg_inf();
-    const long long total = (long long)p.n_lists * p.k_in;
+    const int lmod = p.list_mod > 1 ? p.list_mod : 1;
+    const int lgrp = p.list_mod > 1 ? q / p.queries_per_group : 0;
+    const int n_eff = p.n_lists / lmod;  // lists that hold this query
+    const long long total = (long long)n_eff * p.k_in;
     const float *qs = p.cand_s + (long long)q * p.query_stride;
     const IdT *qi = p.cand_i + (long long)q * p.query_stride;
     constexpr int PF = 8;  // chunks whose (independent) loads are issued together: hides the L2 latency
@@ -284,8 +289,8 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
           sv[u] = neg_inf();
           iv[u] = invalid_id<IdT>();
           if (idx < total) {
-              const int e = (int)(idx / p.n_lists);
-              const int l = (int)(idx - (long long)e * p.n_lists);
+              const int e = (int)(idx / n_eff);
+              const int l = lgrp + (int)(idx - (long long)e * n_eff) * lmod;
               sv[u] = qs[(long long)l * p.list_stride + e];
               iv[u] = qi[(long long)l * p.list_stride_i + e];
           }
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(32) reduce_topk_kernel(const ReduceParams<IdT>
     const int kin_pad = ((p.k_in + 31) / 32) * 32;
     // entry-major over chunks of 32 entries so that every list's best candidates come first
     for (int e0 = 0; e0 < kin_pad; e0 += 32) {
-        for (int l = 0; l < p.n_lists; ++l) {
+        for (int l = (p.list_mod > 1 ? q / p.queries_per_group : 0); l < p.n_lists; l += (p.list_mod > 1 ? p.list_mod : 1)) {
             const float *ls = p.cand_s + (long long)l * p.list_stride + (long long)q * p.query_stride;
             const IdT *li = p.cand_i + (long long)l * p.list_stride_i + (long long)q * p.query_stride;
             const int e = e0 + lane;
