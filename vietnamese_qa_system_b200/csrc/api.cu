@@ -96,7 +96,9 @@ struct vqa_index {
     int sm_count = 0;
     int max_smem = 0;
     bool tmap_ok = false;
-    alignas(64) CUtensorMap tmap;
+    // tmap[j]: TMA box of 64 columns x (128 >> j) rows -- j = log2(cluster size) of the multicast launch
+    alignas(64) CUtensorMap tmap[4];
+    mutable int max_clusters[4][5] = {};  // cached cudaOccupancyMaxActiveClusters by [log2 cluster][ncol slot]
 };
 
 namespace {
@@ -274,17 +276,21 @@ int vqa_index_bind(vqa_index_t *h, const void *rows_dev, int64_t n_rows, int64_t
     if (n_rows > 0 && es == 2 && h->dim % 64 == 0) {
         EncodeTiledFn enc = get_encode_fn();
         if (enc) {
-            cuuint64_t gdim[2] = {(cuuint64_t)h->dim, (cuuint64_t)n_rows};
-            cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
-            cuuint32_t box[2] = {(cuuint32_t)vqa::kBlockK, (cuuint32_t)vqa::kTileRows};
-            cuuint32_t estr[2] = {1, 1};
-            CUresult r = enc(&h->tmap, h->dtype == VQA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                            : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                             2, const_cast<void *>(rows_dev), gdim, gstride, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             (CUtensorMapL2promotion)env_int("VQA_TMA_L2PROMO", (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            h->tmap_ok = (r == CUDA_SUCCESS);
+            bool ok = true;
+            for (int j = 0; j < 4 && ok; ++j) {
+                cuuint64_t gdim[2] = {(cuuint64_t)h->dim, (cuuint64_t)n_rows};
+                cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
+                cuuint32_t box[2] = {(cuuint32_t)vqa::kBlockK, (cuuint32_t)(vqa::kTileRows >> j)};
+                cuuint32_t estr[2] = {1, 1};
+                CUresult r = enc(&h->tmap[j], h->dtype == VQA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                 2, const_cast<void *>(rows_dev), gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 (CUtensorMapL2promotion)env_int("VQA_TMA_L2PROMO", (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                ok = (r == CUDA_SUCCESS);
+            }
+            h->tmap_ok = ok;
         }
     }
     return VQA_OK;
@@ -354,20 +360,38 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
         // c % g, so one pass over HBM serves the whole launch; its candidate lists are reduced right away.
         const int per_launch = pl.groups * pl.pass_nq;
         const long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
+        const bool use_mc = env_int("VQA_MMA_MULTICAST", 1) != 0;
         for (int l0 = 0; l0 < n_queries; l0 += per_launch) {
             const int nq = n_queries - l0 < per_launch ? n_queries - l0 : per_launch;
-            const int g = (nq + pl.pass_nq - 1) / pl.pass_nq;
+            const int chunks = (nq + pl.pass_nq - 1) / pl.pass_nq;
+            int g = chunks, lg = 0;
+            if (use_mc && chunks > 1) {  // cluster sizes are powers of two; a short launch gets empty chunks
+                while ((1 << lg) < chunks) ++lg;
+                g = 1 << lg;
+            }
+            const bool mc = use_mc && g > 1;
             long long streams = h->sm_count / g;
+            if (mc) {
+                const int slot = pl.ncol == 16 ? 0 : (pl.ncol == 32 ? 1 : (pl.ncol == 64 ? 2 : 3));
+                int &cached = h->max_clusters[lg][slot];
+                if (cached == 0) {
+                    cached = vqa::mma_max_active_clusters(h->dtype == VQA_BF16, pl.ncol, g,
+                                                          vqa::mma_smem_bytes_rt(pl.ncol, h->dim, k, pl.stages * pl.kps));
+                    if (cached <= 0) cached = -1;
+                }
+                if (cached > 0 && cached < streams) streams = cached;
+            }
             if (streams > tiles) streams = tiles;
             if (streams < 1) streams = 1;
             vqa::MmaLaunch a;
-            a.tmap = &h->tmap;
+            a.tmap = &h->tmap[mc ? lg : 0];
             a.bf16 = h->dtype == VQA_BF16;
             a.ncol = pl.ncol;
             a.stages = pl.stages;
             a.kps = pl.kps;
             a.grid = (int)streams * g;
             a.n_groups = g;
+            a.multicast = mc ? 1 : 0;
             a.q = queries_dev + (long long)l0 * q_stride;
             a.q_stride = q_stride;
             a.nq = nq;

@@ -34,6 +34,7 @@ struct MmaLaunch {
     int kps;
     int grid;
     int n_groups;  // query chunks of ncol/2 handled side by side in one launch (grid % n_groups == 0)
+    int multicast; // 1: launch as clusters of n_groups CTAs with TMA multicast (tmap box = 128/n_groups rows)
     const float *q;
     long long q_stride;
     int nq;
@@ -52,6 +53,8 @@ cudaError_t launch_scan_f32(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_bf16(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_f16(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_mma(const MmaLaunch &a, cudaStream_t st);
+// clusters of `cluster` CTAs of the tensor-core kernel that can be co-resident (0 if the query fails)
+int mma_max_active_clusters(bool bf16, int ncol, int cluster, size_t smem_bytes);
 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,

@@ -40,8 +40,11 @@ struct MmaParams {
     long long q_stride;
     int nq;  // queries in this LAUNCH: n_groups chunks of NCOL / 2 (hi and lo column per query); the last may be short
     int n_groups;  // query chunks processed side by side: CTA c works on chunk c % n_groups, tile stream
-                   // c / n_groups, so the chunks' CTAs read the same document tiles at the same time and
-                   // all but the first read hit L2 (one HBM pass serves n_groups * NCOL/2 queries)
+                   // c / n_groups (one HBM pass serves n_groups * NCOL/2 queries)
+    int multicast; // 1: launched as clusters of n_groups CTAs; every document box is fetched ONCE per
+                   // cluster -- each CTA issues a 128/n_groups-row slice of it as a TMA multicast into all
+                   // the cluster's shared memories -- so L2->SM traffic does not grow with n_groups.
+                   // 0: plain CTAs, the chunks' CTAs re-read the tiles through L2.
     int k;
     long long n_rows;
     int dim;  // multiple of 64
@@ -289,19 +292,23 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     // Warp 4 (TMA producer) sets up the barriers and TMEM, then starts streaming documents at once;
     // the other five warps stage the queries meanwhile and meet it at named barrier 1.
     uint32_t tmem_base = 0;
-    if (warp == 4) {
-        if (lane == 0) {
-            ptx::prefetch_tmap(&tmap_docs);
-            for (int s = 0; s < S; ++s) {
-                ptx::mbar_init(full + s, 1);
-                ptx::mbar_init(empty + s, 1);
-            }
-            for (int a = 0; a < AS; ++a) {
-                ptx::mbar_init(tfull + a, 1);
-                ptx::mbar_init(tempty + a, 4);
-            }
-            ptx::fence_mbar_init();
+    const uint16_t cta_mask = (uint16_t)((1u << p.n_groups) - 1u);
+    const int slice_rows = kTileRows / (p.multicast ? p.n_groups : 1);  // rows of each box this CTA fetches
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_docs);
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(full + s, 1);
+            ptx::mbar_init(empty + s, p.multicast ? p.n_groups : 1);  // every consumer CTA of the cluster
         }
+        for (int a = 0; a < AS; ++a) {
+            ptx::mbar_init(tfull + a, 1);
+            ptx::mbar_init(tempty + a, 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    if (p.multicast) ptx::cluster_sync_all();  // peers signal these barriers: they must exist cluster-wide first
+    if (warp == 4) {
         __syncwarp();
         ptx::tmem_alloc(tmem_slot, TMEM_COLS);
         ptx::tmem_relinquish();
@@ -354,9 +361,17 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 ptx::mbar_wait(empty + s, ph ^ 1);
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(full + s, stage_bytes);
-                    for (int j = 0; j < KPS; ++j)
-                        ptx::tma_load_2d(a_smem + (size_t)s * stage_bytes + (size_t)j * kStageBytes, &tmap_docs,
-                                         (kg * KPS + j) * kBlockK, tile * kTileRows, full + s, p.tma_policy);
+                    if (p.multicast) {
+                        for (int j = 0; j < KPS; ++j)
+                            ptx::tma_load_2d_multicast(
+                                a_smem + (size_t)s * stage_bytes + (size_t)j * kStageBytes + (size_t)grp * slice_rows * 128,
+                                &tmap_docs, (kg * KPS + j) * kBlockK, tile * kTileRows + grp * slice_rows, full + s,
+                                cta_mask, p.tma_policy);
+                    } else {
+                        for (int j = 0; j < KPS; ++j)
+                            ptx::tma_load_2d(a_smem + (size_t)s * stage_bytes + (size_t)j * kStageBytes, &tmap_docs,
+                                             (kg * KPS + j) * kBlockK, tile * kTileRows, full + s, p.tma_policy);
+                    }
                 }
                 __syncwarp();
             }
@@ -387,7 +402,9 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                             ptx::umma_f16(d_tmem, da0 + (uint64_t)(k4 * 2), db0 + (uint64_t)(k4 * 2), IDESC,
                                           (kb | k4) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(empty + s);  // smem stage reusable once these MMAs retire
+                    // smem stage reusable once these MMAs retire -- in every CTA that multicasts into it
+                    if (p.multicast) ptx::umma_commit_multicast(empty + s, cta_mask);
+                    else ptx::umma_commit(empty + s);
                     if (kg == KG - 1) ptx::umma_commit(tfull + as);  // accumulator ready for the epilogue
                 }
                 __syncwarp();
@@ -564,6 +581,8 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         ptx::tc_fence_after_sync();
         ptx::tmem_dealloc(*reinterpret_cast<volatile uint32_t *>(tmem_slot), TMEM_COLS);
     }
+    // peers may still multicast-commit into this CTA's barriers: nobody leaves before everybody is done
+    if (p.multicast) ptx::cluster_sync_all();
 }
 
 }  // namespace vqa

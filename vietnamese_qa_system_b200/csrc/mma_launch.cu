@@ -40,12 +40,69 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     p.epoch = a.epoch;
     // side-by-side chunks re-read each tile from L2: keep it there (normal policy) instead of evict-first
     p.tma_policy = a.n_groups > 1 ? 0x1000000000000000ull : tma_policy();
+    p.multicast = a.multicast;
     const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps);
     auto kern = mma_topk_kernel<BF16, NCOL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<a.grid, kMmaThreads, smem, st>>>(*a.tmap, p);
-    return cudaGetLastError();
+    if (!a.multicast) {
+        kern<<<a.grid, kMmaThreads, smem, st>>>(*a.tmap, p);
+        return cudaGetLastError();
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.n_groups;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.grid);
+    cfg.blockDim = dim3(kMmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, *a.tmap, p);
+}
+
+template <bool BF16, int NCOL>
+static int max_clusters_one(int cluster, size_t smem) {
+    auto kern = mma_topk_kernel<BF16, NCOL>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cluster * 64));
+    cfg.blockDim = dim3(kMmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+template <bool BF16>
+static int max_clusters_t(int ncol, int cluster, size_t smem) {
+    switch (ncol) {
+        case 16: return max_clusters_one<BF16, 16>(cluster, smem);
+        case 32: return max_clusters_one<BF16, 32>(cluster, smem);
+        case 64: return max_clusters_one<BF16, 64>(cluster, smem);
+        case 128: return max_clusters_one<BF16, 128>(cluster, smem);
+        default: return 0;
+    }
+}
+
+int mma_max_active_clusters(bool bf16, int ncol, int cluster, size_t smem_bytes) {
+    return bf16 ? max_clusters_t<true>(ncol, cluster, smem_bytes) : max_clusters_t<false>(ncol, cluster, smem_bytes);
 }
 
 template <bool BF16>
