@@ -71,7 +71,9 @@ typedef enum vqa_mode {
     VQA_MODE_FAST = 1,
     /* FAST, but force one kernel family (benchmarks / tests). */
     VQA_MODE_FAST_STREAM = 2,
-    VQA_MODE_FAST_TENSOR = 3
+    VQA_MODE_FAST_TENSOR = 3,
+    /* tcgen05 with the query block resident in tensor memory (large batches, dim <= 768) */
+    VQA_MODE_FAST_TS = 4
 } vqa_mode;
 
 typedef struct vqa_index vqa_index_t; /* opaque */

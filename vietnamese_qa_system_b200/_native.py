@@ -18,10 +18,10 @@ OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
 # vqa_dtype
 F32, BF16, F16, I64, I32, U8 = 0, 1, 2, 3, 4, 5
 # vqa_mode
-MODE_VERIFY, MODE_FAST, MODE_FAST_STREAM, MODE_FAST_TENSOR = 0, 1, 2, 3
+MODE_VERIFY, MODE_FAST, MODE_FAST_STREAM, MODE_FAST_TENSOR, MODE_FAST_TS = 0, 1, 2, 3, 4
 
 MODES = {"verify": MODE_VERIFY, "fp32": MODE_VERIFY, "fast": MODE_FAST, "stream": MODE_FAST_STREAM,
-         "tensor": MODE_FAST_TENSOR}
+         "tensor": MODE_FAST_TENSOR, "ts": MODE_FAST_TS}
 
 EXPORTS = [
     "vqa_version", "vqa_last_error", "vqa_device_count", "vqa_index_create", "vqa_index_bind",

@@ -112,6 +112,8 @@ struct Plan {
     int kps;      // tensor: k-blocks per stage
     int passes;
     int groups;   // tensor: query chunks handled side by side per launch (documents shared through L2)
+    int ts_split; // TS family: hi+lo rows (64 queries per CTA) or storage-precision queries (128 per CTA)
+    int ts_afp16;
     int grid;
 };
 
@@ -161,6 +163,39 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
     return false;
 }
 
+bool ts_eligible(const vqa_index *h) { return tensor_eligible(h) && h->dim <= 768; }
+
+// TMEM-resident queries: shared memory holds only the document ring and the per-row lists
+bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
+    // k <= 16: screen with storage-precision queries (128 per CTA), keep 32 candidates per query and
+    // re-score them exactly in the reduce.  Larger k: hi + lo rows (64 queries per CTA).
+    const int split = env_int("VQA_TS_SPLIT", k <= 16 ? 0 : 1) != 0;
+    const int kscan = split ? k : k + env_int("VQA_TS_EXTRA", 6);
+    const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split);
+    if (fixed >= (size_t)h->max_smem) return false;
+    int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
+    const int kb = h->dim / vqa::kBlockK;
+    int kps = env_int("VQA_MMA_KPS", kb % 2 == 0 ? 2 : (kb % 3 == 0 ? 3 : 1));
+    if (kps < 1 || kb % kps != 0) kps = 1;
+    int stages = boxes / kps;
+    if (stages > vqa::kMaxStages) stages = vqa::kMaxStages;
+    if (stages < 2) return false;
+    pl->family = VQA_MODE_FAST_TS;
+    pl->ts_split = split;
+    pl->ts_afp16 = env_int("VQA_TS_AFP16", 0) != 0;
+    pl->pass_nq = split ? 64 : 128;
+    pl->ncol = 0;
+    pl->stages = stages;
+    pl->kps = kps;
+    pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
+    int gmax = env_int("VQA_TS_GROUPS", 2);
+    if (gmax < 1) gmax = 1;
+    if (gmax > 4) gmax = 4;
+    pl->groups = pl->passes < gmax ? pl->passes : gmax;
+    pl->grid = h->sm_count;
+    return true;
+}
+
 void plan_stream(const vqa_index *h, int nq, Plan *pl) {
     pl->family = VQA_MODE_FAST_STREAM;
     pl->pass_nq = nq >= 5 ? 8 : (nq >= 3 ? 4 : (nq == 2 ? 2 : 1));
@@ -183,6 +218,11 @@ int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
                         h->dim, h->dtype);
         return VQA_OK;
     }
+    if (mode == VQA_MODE_FAST_TS) {
+        if (!ts_eligible(h) || !plan_ts(h, nq, k, pl))
+            return fail(VQA_E_UNSUPPORTED, "TMEM-resident-query path needs bf16/fp16 rows and dim %% 64 == 0, dim <= 768");
+        return VQA_OK;
+    }
     if (mode == VQA_MODE_FAST) {
         // Measured on B200 (profiles/): the TMA-fed tcgen05 kernel streams the documents at the HBM
         // roofline for every batch size, so 16-bit indexes always take it; the CUDA-core streaming
@@ -201,7 +241,8 @@ int check_search_args(const vqa_index *h, int nq, int k) {
     return VQA_OK;
 }
 
-size_t cand_elems(const vqa_index *h, int nq, int k) { return (size_t)h->sm_count * nq * k; }
+// candidate lists are kept at least 32 wide so that the screen-then-rescore path can over-fetch
+size_t cand_elems(const vqa_index *h, int nq, int k) { return (size_t)h->sm_count * nq * (k < 32 ? 32 : k); }
 
 }  // namespace
 
@@ -310,7 +351,9 @@ int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t 
     if (rc) return rc;
     if (family) *family = pl.family;
     if (n_launches)
-        *n_launches = pl.family == VQA_MODE_FAST_TENSOR ? 2 * ((pl.passes + pl.groups - 1) / pl.groups) : pl.passes + 1;
+        *n_launches = (pl.family == VQA_MODE_FAST_TENSOR || pl.family == VQA_MODE_FAST_TS)
+                          ? 2 * ((pl.passes + pl.groups - 1) / pl.groups)
+                          : pl.passes + 1;
     return VQA_OK;
 }
 
@@ -354,6 +397,66 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     const long long cand_stride = (long long)n_queries * k;
     static std::atomic<uint32_t> g_epoch{1};
     const uint32_t epoch = g_epoch.fetch_add(2, std::memory_order_relaxed);  // odd, unique, never 0 (0 = cleared slot)
+
+    if (pl.family == VQA_MODE_FAST_TS && h->n_rows > 0) {
+        // list length inside the scan: with screen-then-rescore a few spare ranks absorb the reordering
+        // that the queries' storage rounding can cause (score error ~5e-5 against rank gaps of ~7e-4)
+        const int kscan = pl.ts_split ? k : k + env_int("VQA_TS_EXTRA", 6);
+        const long long cstride = (long long)n_queries * kscan;
+        const int per_launch = pl.groups * pl.pass_nq;
+        const long long tiles = (h->n_rows + 63) / 64;
+        for (int l0 = 0; l0 < n_queries; l0 += per_launch) {
+            const int nq = n_queries - l0 < per_launch ? n_queries - l0 : per_launch;
+            const int chunks = (nq + pl.pass_nq - 1) / pl.pass_nq;
+            int g = 1, lg = 0;
+            while (g < chunks) {
+                g <<= 1;
+                ++lg;
+            }
+            const bool mc = g > 1;
+            long long streams = h->sm_count / g;
+            if (mc && g == 4 && streams > 32) streams = 32;  // clusters of 4 do not tile every GPC
+            if (streams > tiles) streams = tiles;
+            if (streams < 1) streams = 1;
+            vqa::TsLaunch a;
+            a.tmap = &h->tmap[1 + lg];
+            a.bf16 = h->dtype == VQA_BF16;
+            a.split = pl.ts_split;
+            a.a_fp16 = pl.ts_afp16;
+            a.stages = pl.stages;
+            a.kps = pl.kps;
+            a.grid = (int)streams * g;
+            a.n_groups = g;
+            a.multicast = mc ? 1 : 0;
+            a.q = queries_dev + (long long)l0 * q_stride;
+            a.q_stride = q_stride;
+            a.nq = nq;
+            a.k = kscan;
+            a.n_rows = h->n_rows;
+            a.dim = h->dim;
+            a.cand_s = cand_s + (long long)l0 * kscan;
+            a.cand_i = cand_i + (long long)l0 * kscan;
+            a.cand_stride = cstride;
+            a.tau_g = tau_g + l0;
+            a.epoch = epoch;
+            cudaError_t e = vqa::launch_ts(a, st);
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "TS scan launch failed: %s", cudaGetErrorString(e));
+            vqa::Rescore rs;
+            rs.rows = h->rows;
+            rs.stride = h->stride;
+            rs.dim = h->dim;
+            rs.bf16 = h->dtype == VQA_BF16;
+            rs.q = queries_dev + (long long)l0 * q_stride;
+            rs.q_stride = q_stride;
+            rs.k_final = k;
+            e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
+                                       kscan, pl.ts_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
+                                       pl.ts_split ? nullptr : &rs);
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+        }
+        return VQA_OK;
+    }
 
     if (pl.family == VQA_MODE_FAST_TENSOR && h->n_rows > 0) {
         // Each launch covers up to groups * pass_nq queries: CTA c scans tile stream c / g for query chunk

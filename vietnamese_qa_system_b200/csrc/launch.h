@@ -48,6 +48,31 @@ struct MmaLaunch {
     uint32_t epoch;
 };
 
+struct TsLaunch {
+    const CUtensorMap *tmap;  // box = 64 columns x (64 / cluster) rows
+    bool bf16;
+    int split;    // 1: 64 queries per CTA as hi + lo rows; 0: 128 queries per CTA, storage-precision queries
+    int a_fp16;   // queries as fp16 against bf16 documents
+    int stages;
+    int kps;
+    int grid;
+    int n_groups;
+    int multicast;
+    const float *q;
+    long long q_stride;
+    int nq;
+    int k;
+    long long n_rows;
+    int dim;
+    float *cand_s;
+    uint32_t *cand_i;
+    long long cand_stride;
+    unsigned long long *tau_g;
+    uint32_t epoch;
+};
+
+cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st);
+size_t ts_smem_bytes(int k, int boxes, int split);
 cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_f32(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_bf16(const ScanLaunch &a, cudaStream_t st);
@@ -56,10 +81,21 @@ cudaError_t launch_mma(const MmaLaunch &a, cudaStream_t st);
 // clusters of `cluster` CTAs of the tensor-core kernel that can be co-resident (0 if the query fails)
 int mma_max_active_clusters(bool bf16, int ncol, int cluster, size_t smem_bytes);
 
+// optional exact re-scoring stage of the candidate reduce (see ReduceParams in scan.cuh)
+struct Rescore {
+    const void *rows = nullptr;
+    long long stride = 0;
+    int dim = 0;
+    int bf16 = 1;
+    const float *q = nullptr;
+    long long q_stride = 0;
+    int k_final = 0;
+};
+
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              int list_mod, int queries_per_group, cudaStream_t st);
+                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr);
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, cudaStream_t st);

@@ -20,9 +20,16 @@ template <typename IdT>
 static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long long list_stride,
                                    long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                                    float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                                   int list_mod, int queries_per_group, cudaStream_t st) {
+                                   int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr) {
     ReduceParams<IdT> p;
     p.tau_g_reset = tau_g_reset;
+    p.rs_rows = rs ? static_cast<const unsigned char *>(rs->rows) : nullptr;
+    p.rs_stride = rs ? rs->stride : 0;
+    p.rs_dim = rs ? rs->dim : 0;
+    p.rs_bf16 = rs ? rs->bf16 : 1;
+    p.rs_q = rs ? rs->q : nullptr;
+    p.rs_q_stride = rs ? rs->q_stride : 0;
+    p.k_final = rs ? rs->k_final : 0;
     p.list_mod = list_mod;
     p.queries_per_group = queries_per_group;
     p.cand_s = cand_s;
@@ -61,9 +68,9 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              int list_mod, int queries_per_group, cudaStream_t st) {
+                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs) {
     return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
-                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st);
+                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, rs);
 }
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,

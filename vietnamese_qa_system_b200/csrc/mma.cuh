@@ -142,7 +142,7 @@ __device__ __forceinline__ void bitonic_step(float &s, uint32_t &i, int stride, 
     }
 }
 
-__device__ __noinline__ void list_insert_bulk32(ListView<uint32_t> L, int q, float cs, uint32_t ci) {
+static __device__ __noinline__ void list_insert_bulk32(ListView<uint32_t> L, int q, float cs, uint32_t ci) {
     const int lane = threadIdx.x & 31;
     // sort candidates descending across lanes
 #pragma unroll
@@ -188,7 +188,7 @@ struct Entry {
     uint32_t i;
 };
 
-__device__ __noinline__ Entry reglist_insert_one(float ls, uint32_t li, float cs, uint32_t ci) {
+static __device__ __noinline__ Entry reglist_insert_one(float ls, uint32_t li, float cs, uint32_t ci) {
     const int lane = threadIdx.x & 31;
     const int pos = __popc(__ballot_sync(kFullMask, ranks_before<uint32_t>(ls, li, cs, ci)));
     const float ups = __shfl_up_sync(kFullMask, ls, 1);
@@ -200,7 +200,7 @@ __device__ __noinline__ Entry reglist_insert_one(float ls, uint32_t li, float cs
 }
 
 // merge up to 32 unsorted candidates (one per lane, (-inf, invalid) where none) into the list
-__device__ __noinline__ Entry reglist_merge32(float ls, uint32_t li, float cs, uint32_t ci, bool cand_sorted) {
+static __device__ __noinline__ Entry reglist_merge32(float ls, uint32_t li, float cs, uint32_t ci, bool cand_sorted) {
     const int lane = threadIdx.x & 31;
     if (!cand_sorted) {
 #pragma unroll

@@ -243,6 +243,16 @@ struct ReduceParams {
     float *out_s;     // [nq][k_out]
     long long *out_i;
     unsigned long long *tau_g_reset;  // [n_queries] shared-threshold slots to clear for the next search, or nullptr
+    // Exact re-scoring of the merged candidates (screen-then-rescore): the scan ranked documents with
+    // storage-precision queries; the k_out survivors get their exact fp32 dot product (fp32 query x
+    // stored row) here, are re-sorted, and the best k_final are written.  rs_rows == nullptr: off.
+    const unsigned char *rs_rows;
+    long long rs_stride;   // bytes between rows
+    int rs_dim;
+    int rs_bf16;           // 1 bf16 rows, 0 fp16 rows
+    const float *rs_q;     // fp32 queries of this reduce launch
+    long long rs_q_stride;
+    int k_final;           // entries written per query (<= k_out); out arrays are [n_queries][k_final]
 };
 
 __device__ __forceinline__ float shfl_xor_any(float v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
@@ -328,10 +338,50 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
         tau = last != invalid_id<IdT>() ? __shfl_sync(kFullMask, ls, p.k_out - 1) : neg_inf();
       }
     }
-    if (lane < p.k_out) {
+    if constexpr (sizeof(IdT) == 4) {
+        if (p.rs_rows != nullptr) {
+            // lane e re-scores candidate e exactly: 4 independent fp32 FMA chains over the row
+            float exact = neg_inf();
+            if (lane < p.k_out && li != invalid_id<IdT>()) {
+                const unsigned char *row = p.rs_rows + (long long)li * p.rs_stride;
+                const float *qv = p.rs_q + (long long)q * p.rs_q_stride;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int c = 0; c < p.rs_dim / 8; ++c) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(row + c * 16);
+                    const float4 q0 = *reinterpret_cast<const float4 *>(qv + c * 8);
+                    const float4 q1 = *reinterpret_cast<const float4 *>(qv + c * 8 + 4);
+                    float x[8];
+                    if (p.rs_bf16) Elem<__nv_bfloat16>::unpack(w, x);
+                    else Elem<__half>::unpack(w, x);
+                    a0 = fmaf(q0.x, x[0], a0);
+                    a1 = fmaf(q0.y, x[1], a1);
+                    a2 = fmaf(q0.z, x[2], a2);
+                    a3 = fmaf(q0.w, x[3], a3);
+                    a0 = fmaf(q1.x, x[4], a0);
+                    a1 = fmaf(q1.y, x[5], a1);
+                    a2 = fmaf(q1.z, x[6], a2);
+                    a3 = fmaf(q1.w, x[7], a3);
+                }
+                exact = (a0 + a1) + (a2 + a3);
+            } else {
+                li = invalid_id<IdT>();
+            }
+            ls = exact;
+#pragma unroll
+            for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    const bool desc = (lane & size) == 0 || size == 32;
+                    bitonic_step_t<IdT>(ls, li, stride, ((lane & stride) == 0) == desc);
+                }
+            }
+        }
+    }
+    const int kf = p.k_final > 0 ? p.k_final : p.k_out;
+    if (lane < kf) {
         const bool ok = li != invalid_id<IdT>();
-        p.out_s[(long long)q * p.k_out + lane] = ok ? ls : neg_inf();
-        p.out_i[(long long)q * p.k_out + lane] = ok ? (long long)li + p.id_base : -1LL;
+        p.out_s[(long long)q * kf + lane] = ok ? ls : neg_inf();
+        p.out_i[(long long)q * kf + lane] = ok ? (long long)li + p.id_base : -1LL;
     }
     if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;  // a graph replay reuses the epoch
 }

@@ -1,0 +1,346 @@
+// ts.cuh -- K2c + K3: the large-batch (GEMM-regime) tcgen05 kernel: queries resident in TENSOR
+// MEMORY as the MMA's A operand, documents streamed through the whole of shared memory.
+//
+// Replaces faiss IndexFlatIP search under txtai ann.search (heavy_ranker.py:98,100) for query
+// batches beyond what mma.cuh can keep resident in shared memory.  There the queries (hi + lo,
+// 3 KB each at dim 768) compete with the TMA ring for the SM's 227 KB, and the ring's size over the
+// memory latency bounds how fast one SM can ingest documents (Little's law: measured 1.5x the HBM
+// share, whatever feeds it -- L2 re-reads or cluster multicast).  Here:
+//   * A = the query block, M = 128 query rows x K = dim, written once into TMEM with tcgen05.st
+//     (dim/2 of the 512 columns: 384 at dim 768) and read by `tcgen05.mma [d], [a_tmem], b_desc`;
+//   * B = 64-document x 64-column boxes (8 KB, 128B-swizzled, TMA) -- shared memory holds nothing
+//     but the ring (~200 KB in flight per SM) and the per-thread lists;
+//   * D = 128 queries x 64 documents fp32 in the remaining TMEM columns, (512 - dim/2)/64
+//     accumulator stages (2 at dim 768), so the epilogue of tile t overlaps the MMAs of tile t+1;
+//   * epilogue: thread = one QUERY row: tcgen05.ld gives it its 64 document scores, it keeps a
+//     private threshold in a register and a private sorted top-k list in shared memory -- no
+//     cross-thread traffic at all; thresholds are shared GPU-wide exactly as in mma.cuh.
+// With `split` the 128 rows are 64 queries as hi rows (0..63) and lo rows (64..127); the lo rows'
+// scores reach the hi rows through a 16 KB shared-memory exchange per tile.
+// One HBM pass serves 128 (or 64) queries per CTA, x cluster size with TMA multicast.
+//
+// Roofline: HBM up to ~128 queries per pass (bytes = n_rows*dim*2 per launch), tensor pipe beyond.
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+#include "mma.cuh"
+#include "ptx.cuh"
+
+namespace vqa {
+
+constexpr int kTsRows = 128;       // query rows per CTA (UMMA M)
+constexpr int kTsDocs = 64;        // documents per MMA tile (UMMA N)
+constexpr int kTsBoxBytes = kTsDocs * kBlockK * 2;  // 8 KB per TMA box
+
+struct TsParams {
+    const float *q;
+    long long q_stride;
+    int nq;        // queries in this launch
+    int per_cta;   // queries per CTA: 128, or 64 with split
+    int split;
+    int a_fp16;    // A (queries) stored as fp16 even if documents are bf16 (mixed kind::f16 operands)
+    int k;
+    long long n_rows;
+    int dim;       // multiple of 64, <= 768
+    float *cand_s;
+    uint32_t *cand_i;
+    long long cand_stride;
+    int n_tiles;   // tiles of 64 documents
+    int n_stages;
+    int kps;
+    unsigned long long tma_policy;
+    unsigned long long *tau_g;
+    uint32_t epoch;
+    int n_groups;
+    int multicast;
+};
+
+// [align slack][ring: boxes x 8 KB][barriers 1 KB][exchange 2 x 16 KB if split][lists: rows x k x 8 B]
+inline size_t ts_smem_bytes_rt(int k, int boxes, int split) {
+    return 1024 + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) + (size_t)kTsRows * k * 8;
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <bool DOC_BF16>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int KB = p.dim / kBlockK;
+    const int S = p.n_stages;
+    const int KPS = p.kps;
+    const int KG = KB / KPS;
+    const uint32_t stage_bytes = (uint32_t)KPS * kTsBoxBytes;
+    const int ACOLS = p.dim / 2;                    // TMEM columns of the query block
+    const int AS = (512 - ACOLS) / kTsDocs;         // accumulator stages
+    unsigned char *a_smem = smem;                   // document ring
+    uint64_t *bars = reinterpret_cast<uint64_t *>(a_smem + (size_t)S * stage_bytes);
+    uint64_t *full = bars;
+    uint64_t *empty = bars + kMaxStages;
+    uint64_t *tfull = bars + 2 * kMaxStages;
+    uint64_t *tempty = tfull + kMaxAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kMaxAccStages);
+    float *xchg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 1024);  // [2][64 docs][64 rows]
+    unsigned char *lists = reinterpret_cast<unsigned char *>(xchg) + (p.split ? 2 * 64 * kTsDocs * 4 : 0);
+    // per-thread sorted lists, entry-major so that a warp's accesses are conflict free
+    float *lst_s = reinterpret_cast<float *>(lists);                       // [k][128]
+    uint32_t *lst_i = reinterpret_cast<uint32_t *>(lst_s + (size_t)p.k * kTsRows);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
+    const int grp = blockIdx.x % p.n_groups;
+    const int stream0 = blockIdx.x / p.n_groups;
+    const int n_streams = gridDim.x / p.n_groups;
+    const int q0 = grp * p.per_cta;
+    const int nq = p.nq - q0 < p.per_cta ? (p.nq - q0 > 0 ? p.nq - q0 : 0) : p.per_cta;
+    const uint16_t cta_mask = (uint16_t)((1u << p.n_groups) - 1u);
+    const int slice_rows = kTsDocs / (p.multicast ? p.n_groups : 1);
+    const uint32_t idesc = (1u << 4) | ((p.a_fp16 ? 0u : (DOC_BF16 ? 1u : 0u)) << 7) | ((DOC_BF16 ? 1u : 0u) << 10) |
+                           ((uint32_t)(kTsDocs >> 3) << 17) | ((uint32_t)(kTsRows >> 4) << 24);
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_docs);
+        for (int s = 0; s < S; ++s) {
+            ptx::mbar_init(full + s, 1);
+            ptx::mbar_init(empty + s, p.multicast ? p.n_groups : 1);
+        }
+        for (int a = 0; a < AS; ++a) {
+            ptx::mbar_init(tfull + a, 1);
+            ptx::mbar_init(tempty + a, 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    if (p.multicast) ptx::cluster_sync_all();
+    if (warp == 4) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+        ptx::tc_fence_before_sync();
+    }
+    grid_launch_dependents();
+    __syncthreads();  // TMEM base visible to everyone (the producer has not started yet: cheap, once)
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = __shfl_sync(kFullMask, *reinterpret_cast<volatile uint32_t *>(tmem_slot), 0);
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        uint32_t it = 0;
+        for (int tile = stream0; tile < p.n_tiles; tile += n_streams) {
+            for (int kg = 0; kg < KG; ++kg, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                ptx::mbar_wait(empty + s, ph ^ 1);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(full + s, stage_bytes);
+                    for (int j = 0; j < KPS; ++j) {
+                        unsigned char *dst = a_smem + (size_t)s * stage_bytes + (size_t)j * kTsBoxBytes;
+                        if (p.multicast)
+                            ptx::tma_load_2d_multicast(dst + (size_t)grp * slice_rows * 128, &tmap_docs,
+                                                       (kg * KPS + j) * kBlockK, tile * kTsDocs + grp * slice_rows,
+                                                       full + s, cta_mask, p.tma_policy);
+                        else
+                            ptx::tma_load_2d(dst, &tmap_docs, (kg * KPS + j) * kBlockK, tile * kTsDocs, full + s,
+                                             p.tma_policy);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer: waits for the query block (named barrier 1), then D = Q * docs^T =====
+        named_bar_sync(1, 160);
+        ptx::tc_fence_after_sync();
+        uint32_t it = 0, lt = 0;
+        const uint32_t ring = ptx::smem_u32(a_smem);
+        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
+            const int as = lt % AS;
+            const uint32_t aph = (lt / AS) & 1;
+            ptx::mbar_wait(tempty + as, aph ^ 1);
+            ptx::tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(ACOLS + as * kTsDocs);
+            for (int kg = 0; kg < KG; ++kg, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                ptx::mbar_wait(full + s, ph);
+                ptx::tc_fence_after_sync();
+                if (ptx::elect_one()) {
+                    for (int j = 0; j < KPS; ++j) {
+                        const int kb = kg * KPS + j;
+                        const uint64_t db0 = ptx::umma_desc_k_sw128(ring + (uint32_t)s * stage_bytes + (uint32_t)j * kTsBoxBytes);
+#pragma unroll
+                        for (int k4 = 0; k4 < kBlockK / 16; ++k4)  // 16 K-elements = 8 TMEM columns of A
+                            umma_f16_ts(d_tmem, tmem_base + (uint32_t)(kb * 32 + k4 * 8), db0 + (uint64_t)(k4 * 2), idesc,
+                                        (kb | k4) != 0 ? 1u : 0u);
+                    }
+                    if (p.multicast) ptx::umma_commit_multicast(empty + s, cta_mask);
+                    else ptx::umma_commit(empty + s);
+                    if (kg == KG - 1) ptx::umma_commit(tfull + as);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== warps 0-3: thread = query row =====
+        const int row = warp * 32 + lane;                       // TMEM lane
+        const int qrow = p.split ? (row & 63) : row;            // query of this row within the chunk
+        const bool is_lo = p.split && row >= 64;
+        const bool live = qrow < nq;
+        // 1. write this row of the query block into TMEM (16-bit pairs, K ascending)
+        {
+            const float *src = p.q + (long long)(q0 + (live ? qrow : 0)) * p.q_stride;
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < ACOLS; c0 += 16) {
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) v = *reinterpret_cast<const float4 *>(src + (c0 + j) * 2);
+                    float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float hi;
+                        if (DOC_BF16 && !p.a_fp16) hi = __bfloat162float(__float2bfloat16_rn(x[e]));
+                        else hi = __half2float(__float2half_rn(x[e]));
+                        x[e] = is_lo ? x[e] - hi : hi;
+                    }
+                    if (DOC_BF16 && !p.a_fp16) {
+                        w[j] = pack_bf16x2(x[0], x[1]);
+                        w[j + 1] = pack_bf16x2(x[2], x[3]);
+                    } else {
+                        w[j] = pack_f16x2(x[0], x[1]);
+                        w[j + 1] = pack_f16x2(x[2], x[3]);
+                    }
+                }
+                tmem_st16(trow + (uint32_t)c0, w);
+            }
+            tmem_st_wait();
+            ptx::tc_fence_before_sync();
+            named_bar_sync(1, 160);  // with the MMA warp
+        }
+        // 2. private list + threshold
+        float tau = (live && !is_lo) ? neg_inf() : __int_as_float(0x7f800000);
+        for (int e = 0; e < p.k; ++e) {
+            lst_s[e * kTsRows + row] = neg_inf();
+            lst_i[e * kTsRows + row] = invalid_id<uint32_t>();
+        }
+        unsigned long long *tg = (p.tau_g != nullptr && live && !is_lo) ? p.tau_g + q0 + qrow : nullptr;
+
+        uint32_t lt = 0;
+        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
+            const int as = lt % AS;
+            const uint32_t aph = (lt / AS) & 1;
+            unsigned long long graw = 0;
+            if (tg != nullptr) graw = ld_volatile_u64(tg);
+            ptx::mbar_wait(tfull + as, aph);
+            ptx::tc_fence_after_sync();
+            if (tg != nullptr) tau = fmaxf(tau, tau_decode(graw, p.epoch));
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ACOLS + as * kTsDocs);
+            const long long doc0 = (long long)tile * kTsDocs;
+            const int ndoc = p.n_rows - doc0 < kTsDocs ? (int)(p.n_rows - doc0) : kTsDocs;
+            float *xb = xchg + (size_t)(lt & 1) * 64 * kTsDocs;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kTsDocs; c0 += 16) {
+                uint32_t acc[16];
+                ptx::tmem_ld16(taddr + c0, acc);
+                ptx::tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+                if (p.split) {
+                    // lo rows publish, hi rows add: xb[doc][row & 63]
+                    if (is_lo) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xb[(c0 + j) * 64 + (row & 63)] = v[j];
+                    }
+                    named_bar_sync(2 + (warp & 1), 64);  // warps (0,2) and (1,3) pair up
+                    if (!is_lo) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += xb[(c0 + j) * 64 + row];
+                    }
+                }
+                float m = v[0];
+#pragma unroll
+                for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
+                if (m >= tau) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (v[j] >= tau && c0 + j < ndoc) {
+                            const uint32_t id = (uint32_t)(doc0 + c0 + j);
+                            int pos = p.k - 1;
+                            // candidate must rank before the current last entry to enter
+                            const float last_s = lst_s[pos * kTsRows + row];
+                            const uint32_t last_i = lst_i[pos * kTsRows + row];
+                            if (ranks_before<uint32_t>(v[j], id, last_s, last_i)) {
+                                while (pos > 0) {
+                                    const float ps = lst_s[(pos - 1) * kTsRows + row];
+                                    const uint32_t pi = lst_i[(pos - 1) * kTsRows + row];
+                                    if (!ranks_before<uint32_t>(v[j], id, ps, pi)) break;
+                                    lst_s[pos * kTsRows + row] = ps;
+                                    lst_i[pos * kTsRows + row] = pi;
+                                    --pos;
+                                }
+                                lst_s[pos * kTsRows + row] = v[j];
+                                lst_i[pos * kTsRows + row] = id;
+                                if (lst_i[(p.k - 1) * kTsRows + row] != invalid_id<uint32_t>()) {
+                                    const float nt = lst_s[(p.k - 1) * kTsRows + row];
+                                    if (nt > tau) {
+                                        tau = nt;
+                                        if (tg != nullptr) atomicMax(tg, tau_encode(nt, p.epoch));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty + as);
+        }
+        // 3. publish this row's list
+        if (live && !is_lo) {
+            float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride + (long long)(q0 + qrow) * p.k;
+            uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride + (long long)(q0 + qrow) * p.k;
+            for (int e = 0; e < p.k; ++e) {
+                cs[e] = lst_s[e * kTsRows + row];
+                ci[e] = lst_i[e * kTsRows + row];
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+    if (p.multicast) ptx::cluster_sync_all();
+}
+
+}  // namespace vqa

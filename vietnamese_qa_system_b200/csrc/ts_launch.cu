@@ -1,0 +1,59 @@
+// ts_launch.cu -- instantiation + launch of the TMEM-resident-query tcgen05 kernel (ts.cuh).
+#include "launch.h"
+#include "ts.cuh"
+
+namespace vqa {
+
+template <bool BF16>
+static cudaError_t launch_ts_t(const TsLaunch &a, cudaStream_t st) {
+    TsParams p;
+    p.q = a.q;
+    p.q_stride = a.q_stride;
+    p.nq = a.nq;
+    p.per_cta = a.split ? 64 : 128;
+    p.split = a.split;
+    p.a_fp16 = a.a_fp16;
+    p.k = a.k;
+    p.n_rows = a.n_rows;
+    p.dim = a.dim;
+    p.cand_s = a.cand_s;
+    p.cand_i = a.cand_i;
+    p.cand_stride = a.cand_stride;
+    p.n_tiles = (int)((a.n_rows + kTsDocs - 1) / kTsDocs);
+    p.n_stages = a.stages;
+    p.kps = a.kps;
+    p.tma_policy = a.n_groups > 1 && !a.multicast ? 0x1000000000000000ull : 0x12F0000000000000ull;
+    p.tau_g = a.tau_g;
+    p.epoch = a.epoch;
+    p.n_groups = a.n_groups;
+    p.multicast = a.multicast;
+    const size_t smem = ts_smem_bytes_rt(a.k, a.stages * a.kps, a.split);
+    auto kern = ts_topk_kernel<BF16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (!a.multicast) {
+        kern<<<a.grid, kMmaThreads, smem, st>>>(*a.tmap, p);
+        return cudaGetLastError();
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.n_groups;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.grid);
+    cfg.blockDim = dim3(kMmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, *a.tmap, p);
+}
+
+cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st) {
+    return a.bf16 ? launch_ts_t<true>(a, st) : launch_ts_t<false>(a, st);
+}
+
+size_t ts_smem_bytes(int k, int boxes, int split) { return ts_smem_bytes_rt(k, boxes, split); }
+
+}  // namespace vqa
