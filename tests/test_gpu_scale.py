@@ -30,7 +30,7 @@ def test_kernel_families_agree_with_verify(big):
     rows, q, _ = big
     shard = ops.FlatShard(rows)
     sv, iv = shard.search(q, 10, "verify")
-    for mode in ("stream", "tensor", "fast"):
+    for mode in ("stream", "tensor", "ts", "fast"):
         s, i = shard.search(q, 10, mode)
         rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(i.cpu(), iv.cpu())])
         assert rec >= 0.999, (mode, rec)

@@ -124,13 +124,17 @@ def test_first_global_id_offsets_ids():
 
 
 @pytest.mark.parametrize("storage", ["bf16", "fp16"])
-@pytest.mark.parametrize("mode", ["stream", "tensor", "fast"])
+@pytest.mark.parametrize("mode", ["stream", "tensor", "ts", "fast"])
 @pytest.mark.parametrize("n,d,b,k", [(128, 64, 8, 4), (1000, 768, 1, 10), (10000, 768, 32, 10),
                                      (33333, 768, 16, 10), (5000, 1024, 64, 10), (20000, 768, 100, 10),
                                      (4000, 768, 32, 100), (130, 768, 5, 128)])
 def test_fast_modes_recall_vs_fp32_arithmetic(storage, mode, n, d, b, k):
     rng = np.random.default_rng(n + b)
     docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    if mode == "ts" and d > 768:                  # the query block must fit tensor memory
+        with pytest.raises(NotImplementedError):
+            gpu_search(docs, q, k, mode, storage)
+        return
     s, i, stored = gpu_search(docs, q, k, mode, storage)
     os_, oi = oracle.search(stored, q, k, oracle.CANONICAL, storage)
     assert recall(i, oi) >= 0.999
@@ -161,6 +165,10 @@ def test_family_selection_and_launch_count():
     assert odd.plan(8, 10, "fast")[0] == 2                                            # dim % 64 != 0: streaming
     assert shard.plan(32, 10, "verify")[0] == 2
     assert shard.plan(32, 10, "fast")[1] == 2            # one scan launch + one reduce launch
+    assert shard.plan(128, 10, "fast") == (4, 2)         # > 32 queries: TMEM-resident-query kernel, one pass
+    assert shard.plan(128, 100, "fast")[0] == 3          # k too large to over-fetch for re-scoring
+    wide = ops.FlatShard(torch.zeros((256, 1024), dtype=torch.float16, device=DEV))
+    assert wide.plan(128, 10, "fast")[0] == 3            # dim 1024 does not fit tensor memory
     rows32 = torch.zeros((4096, 768), dtype=torch.float32, device=DEV)
     assert ops.FlatShard(rows32).plan(32, 10, "fast")[0] == 2                         # fp32 rows never use tcgen05
     with pytest.raises(NotImplementedError):

@@ -227,6 +227,10 @@ int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
         // Measured on B200 (profiles/): the TMA-fed tcgen05 kernel streams the documents at the HBM
         // roofline for every batch size, so 16-bit indexes always take it; the CUDA-core streaming
         // kernel serves fp32 rows (verify mode's native storage) and dims that are not multiples of 64.
+        // Beyond the 32 queries the shared-memory-resident kernel holds per CTA, the TMEM-resident-query
+        // kernel serves 128 per CTA from one HBM pass (screen with storage-precision queries, exact
+        // re-scoring of the k+6 best in the reduce); it needs dim <= 768 and k+6 <= 32.
+        if (nq > 32 && k + env_int("VQA_TS_EXTRA", 6) <= 32 && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
         if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
         return VQA_OK;

@@ -57,9 +57,14 @@ struct TsParams {
     int multicast;
 };
 
-// [align slack][ring: boxes x 8 KB][barriers 1 KB][exchange 2 x 16 KB if split][lists: rows x k x 8 B]
+// register-list variants: 16 (k <= 16) or 32 (k <= 32) entries per query row; 0 = list in shared memory
+inline int ts_reg_list_len(int k) { return k <= 16 ? 16 : (k <= 32 ? 32 : 0); }
+
+// [align slack][ring: boxes x 8 KB][barriers 1 KB][exchange 2 x 16 KB if split]
+// [lists: rows x k x 8 B, or the 32-deep candidate buffers (rows x 32 x 8 B) of the register-list variants]
 inline size_t ts_smem_bytes_rt(int k, int boxes, int split) {
-    return 1024 + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) + (size_t)kTsRows * k * 8;
+    const int depth = ts_reg_list_len(k) > 0 ? 32 : k;
+    return 1024 + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) + (size_t)kTsRows * depth * 8;
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -85,7 +90,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 
-template <bool DOC_BF16>
+template <bool DOC_BF16, int KL>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -245,11 +250,66 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         }
         // 2. private list + threshold
         float tau = (live && !is_lo) ? neg_inf() : __int_as_float(0x7f800000);
-        for (int e = 0; e < p.k; ++e) {
-            lst_s[e * kTsRows + row] = neg_inf();
-            lst_i[e * kTsRows + row] = invalid_id<uint32_t>();
-        }
         unsigned long long *tg = (p.tau_g != nullptr && live && !is_lo) ? p.tau_g + q0 + qrow : nullptr;
+        // KL > 0: the sorted list lives in REGISTERS (rs/ri); candidates that beat the threshold are
+        // first appended to a private shared-memory buffer (two predicated stores, no divergence) and the
+        // whole warp folds its buffers into the lists in lockstep when any lane's buffer is half full.
+        // KL == 0: sorted list in shared memory, inserted immediately (any k up to 128).
+        constexpr int KLR = KL > 0 ? KL : 1;
+        constexpr int CAP = 32;
+        float rs[KLR];
+        uint32_t ri[KLR];
+        int cnt = 0;
+        float *buf_s = lst_s;                       // [CAP][128] when KL > 0
+        uint32_t *buf_i = reinterpret_cast<uint32_t *>(lst_s + CAP * kTsRows);
+        if constexpr (KL > 0) {
+#pragma unroll
+            for (int e = 0; e < KLR; ++e) {
+                rs[e] = neg_inf();
+                ri[e] = invalid_id<uint32_t>();
+            }
+        } else {
+            for (int e = 0; e < p.k; ++e) {
+                lst_s[e * kTsRows + row] = neg_inf();
+                lst_i[e * kTsRows + row] = invalid_id<uint32_t>();
+            }
+        }
+        auto flush = [&]() {
+            if constexpr (KL > 0) {
+                const int wmax = __reduce_max_sync(kFullMask, cnt);
+                for (int b = 0; b < wmax; ++b) {
+                    float cs = neg_inf();
+                    uint32_t ci = invalid_id<uint32_t>();
+                    if (b < cnt) {
+                        cs = buf_s[b * kTsRows + row];
+                        ci = buf_i[b * kTsRows + row];
+                    }
+                    bool bef[KLR];
+#pragma unroll
+                    for (int e = 0; e < KLR; ++e) bef[e] = ranks_before<uint32_t>(cs, ci, rs[e], ri[e]);
+#pragma unroll
+                    for (int e = KLR - 1; e >= 0; --e) {
+                        const bool up = e > 0 ? bef[e - 1] : false;  // candidate lands above e: entry e-1 moves down
+                        rs[e] = up ? rs[e > 0 ? e - 1 : 0] : (bef[e] ? cs : rs[e]);
+                        ri[e] = up ? ri[e > 0 ? e - 1 : 0] : (bef[e] ? ci : ri[e]);
+                    }
+                }
+                cnt = 0;
+                // threshold = score of rank k-1 (p.k <= KL), once that slot is filled
+                float ts = neg_inf();
+                uint32_t ti = invalid_id<uint32_t>();
+#pragma unroll
+                for (int e = 0; e < KLR; ++e)
+                    if (e == p.k - 1) {
+                        ts = rs[e];
+                        ti = ri[e];
+                    }
+                if (ti != invalid_id<uint32_t>() && ts > tau) {
+                    tau = ts;
+                    if (tg != nullptr) atomicMax(tg, tau_encode(ts, p.epoch));
+                }
+            }
+        };
 
         uint32_t lt = 0;
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
@@ -287,7 +347,19 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 float m = v[0];
 #pragma unroll
                 for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
-                if (m >= tau) {
+                if constexpr (KL > 0) {
+                    if (__ballot_sync(kFullMask, m >= tau) != 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (v[j] >= tau && c0 + j < ndoc) {
+                                buf_s[cnt * kTsRows + row] = v[j];
+                                buf_i[cnt * kTsRows + row] = (uint32_t)(doc0 + c0 + j);
+                                ++cnt;
+                            }
+                        }
+                        if (__ballot_sync(kFullMask, cnt > CAP - 16) != 0) flush();
+                    }
+                } else if (m >= tau) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (v[j] >= tau && c0 + j < ndoc) {
@@ -323,13 +395,23 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty + as);
         }
+        if constexpr (KL > 0) flush();
         // 3. publish this row's list
         if (live && !is_lo) {
             float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride + (long long)(q0 + qrow) * p.k;
             uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride + (long long)(q0 + qrow) * p.k;
-            for (int e = 0; e < p.k; ++e) {
-                cs[e] = lst_s[e * kTsRows + row];
-                ci[e] = lst_i[e * kTsRows + row];
+            if constexpr (KL > 0) {
+#pragma unroll
+                for (int e = 0; e < KLR; ++e)
+                    if (e < p.k) {
+                        cs[e] = rs[e];
+                        ci[e] = ri[e];
+                    }
+            } else {
+                for (int e = 0; e < p.k; ++e) {
+                    cs[e] = lst_s[e * kTsRows + row];
+                    ci[e] = lst_i[e * kTsRows + row];
+                }
             }
         }
     }

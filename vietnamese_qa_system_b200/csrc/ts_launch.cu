@@ -4,8 +4,8 @@
 
 namespace vqa {
 
-template <bool BF16>
-static cudaError_t launch_ts_t(const TsLaunch &a, cudaStream_t st) {
+template <bool BF16, int KL>
+static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     TsParams p;
     p.q = a.q;
     p.q_stride = a.q_stride;
@@ -28,7 +28,7 @@ static cudaError_t launch_ts_t(const TsLaunch &a, cudaStream_t st) {
     p.n_groups = a.n_groups;
     p.multicast = a.multicast;
     const size_t smem = ts_smem_bytes_rt(a.k, a.stages * a.kps, a.split);
-    auto kern = ts_topk_kernel<BF16>;
+    auto kern = ts_topk_kernel<BF16, KL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (!a.multicast) {
@@ -48,6 +48,15 @@ static cudaError_t launch_ts_t(const TsLaunch &a, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, *a.tmap, p);
+}
+
+template <bool BF16>
+static cudaError_t launch_ts_t(const TsLaunch &a, cudaStream_t st) {
+    switch (ts_reg_list_len(a.k)) {
+        case 16: return launch_ts_tk<BF16, 16>(a, st);
+        case 32: return launch_ts_tk<BF16, 32>(a, st);
+        default: return launch_ts_tk<BF16, 0>(a, st);
+    }
 }
 
 cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st) {
