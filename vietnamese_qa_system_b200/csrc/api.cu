@@ -112,6 +112,7 @@ struct Plan {
     int kps;      // tensor: k-blocks per stage
     int passes;
     int groups;   // tensor: query chunks handled side by side per launch (documents shared through L2)
+    int ss_split; // tensor family: 1 hi/lo column pairs, 0 screen mode (+ exact re-scoring in the reduce)
     int ts_split; // TS family: hi+lo rows (64 queries per CTA) or storage-precision queries (128 per CTA)
     int ts_afp16;
     int grid;
@@ -126,14 +127,24 @@ bool tensor_eligible(const vqa_index *h) {
     return h->tmap_ok && (h->dtype == VQA_BF16 || h->dtype == VQA_F16) && h->dim % 64 == 0 && h->dim >= 64;
 }
 
-// pick the widest MMA N (<= what the batch needs) whose smem ring still has >= 4 stages
+int spare_ranks() { return env_int("VQA_TS_EXTRA", 6); }
+
+// pick the widest MMA N (<= what the batch needs) whose smem ring still has >= 4 boxes.
+// Screen mode (k + spare <= 32): one storage-precision column per query, up to 32 queries per CTA,
+// the k + spare best re-scored exactly in the reduce.  Otherwise hi/lo column pairs.
 bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
+    // Measured (profiles/r1_tune_screen.log): for <= 32 queries per CTA the hi/lo kernel already runs at
+    // the HBM roofline and the re-scoring stage's cold row reads cost ~35 us per search, so screen mode is
+    // opt-in here (VQA_SS_SCREEN=1); it pays off in the TMEM-resident-query kernel, 128 queries per CTA.
+    const bool screen = env_int("VQA_SS_SCREEN", 0) != 0 && k + spare_ranks() <= 32;
+    const int kk = screen ? k + spare_ranks() : k;
     const int cands[4] = {128, 64, 32, 16};
-    int want = nq * 2;  // hi + lo column per query
-    for (int ci = 0; ci < 4; ++ci) {
+    const int first = screen ? 2 : 0;  // screen mode keeps its lists in registers: <= 32 queries per CTA
+    int want = screen ? nq : nq * 2;
+    for (int ci = first; ci < 4; ++ci) {
         int ncol = cands[ci];
         if (ci < 3 && cands[ci + 1] >= want) continue;  // a narrower tile still covers the batch
-        size_t fixed = vqa::mma_smem_bytes_rt(ncol, h->dim, k, 0);
+        size_t fixed = vqa::mma_smem_bytes_rt(ncol, h->dim, kk, 0, screen ? 0 : 1);
         if (fixed >= (size_t)h->max_smem) continue;
         int blocks = (int)(((size_t)h->max_smem - fixed) / vqa::kStageBytes);  // 16 KB boxes that fit
         if (blocks < 4) continue;
@@ -149,7 +160,8 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
         if (stages < 2) continue;
         pl->family = VQA_MODE_FAST_TENSOR;
         pl->ncol = ncol;
-        pl->pass_nq = ncol / 2;
+        pl->ss_split = screen ? 0 : 1;
+        pl->pass_nq = screen ? ncol : ncol / 2;
         pl->stages = stages;
         pl->kps = kps;
         pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
@@ -170,7 +182,7 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     // k <= 16: screen with storage-precision queries (128 per CTA), keep 32 candidates per query and
     // re-score them exactly in the reduce.  Larger k: hi + lo rows (64 queries per CTA).
     const int split = env_int("VQA_TS_SPLIT", k <= 16 ? 0 : 1) != 0;
-    const int kscan = split ? k : k + env_int("VQA_TS_EXTRA", 6);
+    const int kscan = split ? k : k + spare_ranks();
     const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split);
     if (fixed >= (size_t)h->max_smem) return false;
     int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
@@ -203,6 +215,8 @@ void plan_stream(const vqa_index *h, int nq, Plan *pl) {
     pl->ncol = 0;
     pl->stages = 0;
     pl->groups = 1;
+    pl->ss_split = 1;
+    pl->ts_split = 1;
     pl->grid = h->sm_count;
 }
 
@@ -230,7 +244,7 @@ int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
         // Beyond the 32 queries the shared-memory-resident kernel holds per CTA, the TMEM-resident-query
         // kernel serves 128 per CTA from one HBM pass (screen with storage-precision queries, exact
         // re-scoring of the k+6 best in the reduce); it needs dim <= 768 and k+6 <= 32.
-        if (nq > 32 && k + env_int("VQA_TS_EXTRA", 6) <= 32 && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
+        if (nq > 32 && k + spare_ranks() <= 32 && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
         if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
         return VQA_OK;
@@ -405,7 +419,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     if (pl.family == VQA_MODE_FAST_TS && h->n_rows > 0) {
         // list length inside the scan: with screen-then-rescore a few spare ranks absorb the reordering
         // that the queries' storage rounding can cause (score error ~5e-5 against rank gaps of ~7e-4)
-        const int kscan = pl.ts_split ? k : k + env_int("VQA_TS_EXTRA", 6);
+        const int kscan = pl.ts_split ? k : k + spare_ranks();
         const long long cstride = (long long)n_queries * kscan;
         const int per_launch = pl.groups * pl.pass_nq;
         const long long tiles = (h->n_rows + 63) / 64;
@@ -465,6 +479,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     if (pl.family == VQA_MODE_FAST_TENSOR && h->n_rows > 0) {
         // Each launch covers up to groups * pass_nq queries: CTA c scans tile stream c / g for query chunk
         // c % g, so one pass over HBM serves the whole launch; its candidate lists are reduced right away.
+        const int kscan = pl.ss_split ? k : k + spare_ranks();  // list length inside the scan
+        const long long cstride = (long long)n_queries * kscan;
         const int per_launch = pl.groups * pl.pass_nq;
         const long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
         const bool use_mc = env_int("VQA_MMA_MULTICAST", 1) != 0;
@@ -482,8 +498,9 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
                 const int slot = pl.ncol == 16 ? 0 : (pl.ncol == 32 ? 1 : (pl.ncol == 64 ? 2 : 3));
                 int &cached = h->max_clusters[lg][slot];
                 if (cached == 0) {
-                    cached = vqa::mma_max_active_clusters(h->dtype == VQA_BF16, pl.ncol, g,
-                                                          vqa::mma_smem_bytes_rt(pl.ncol, h->dim, k, pl.stages * pl.kps));
+                    cached = vqa::mma_max_active_clusters(
+                        h->dtype == VQA_BF16, pl.ncol, pl.ss_split, g,
+                        vqa::mma_smem_bytes_rt(pl.ncol, h->dim, kscan, pl.stages * pl.kps, pl.ss_split));
                     if (cached <= 0) cached = -1;
                 }
                 if (cached > 0 && cached < streams) streams = cached;
@@ -494,6 +511,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.tmap = &h->tmap[mc ? lg : 0];
             a.bf16 = h->dtype == VQA_BF16;
             a.ncol = pl.ncol;
+            a.split = pl.ss_split;
             a.stages = pl.stages;
             a.kps = pl.kps;
             a.grid = (int)streams * g;
@@ -502,19 +520,28 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.q = queries_dev + (long long)l0 * q_stride;
             a.q_stride = q_stride;
             a.nq = nq;
-            a.k = k;
+            a.k = kscan;
             a.n_rows = h->n_rows;
             a.dim = h->dim;
-            a.cand_s = cand_s + (long long)l0 * k;
-            a.cand_i = cand_i + (long long)l0 * k;
-            a.cand_stride = cand_stride;
+            a.cand_s = cand_s + (long long)l0 * kscan;
+            a.cand_i = cand_i + (long long)l0 * kscan;
+            a.cand_stride = cstride;
             a.tau_g = tau_g + l0;
             a.epoch = epoch;
             cudaError_t e = vqa::launch_mma(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
-            e = vqa::launch_reduce_u32(cand_s + (long long)l0 * k, cand_i + (long long)l0 * k, cand_stride, k, a.grid, k, k,
-                                       h->first_id, out_scores_dev + (long long)l0 * k,
-                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st);
+            vqa::Rescore rs;
+            rs.rows = h->rows;
+            rs.stride = h->stride;
+            rs.dim = h->dim;
+            rs.bf16 = h->dtype == VQA_BF16;
+            rs.q = queries_dev + (long long)l0 * q_stride;
+            rs.q_stride = q_stride;
+            rs.k_final = k;
+            e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
+                                       kscan, pl.ss_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
+                                       pl.ss_split ? nullptr : &rs);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;

@@ -20,10 +20,11 @@ inline size_t list_bytes_rt(int nq, int k, int id_bytes) {
     return (size_t)nq * kcap * (4 + id_bytes) + (size_t)nq * 8;
 }
 // shared memory of the tensor-core kernel: [align slack][Q tiles (hi|lo columns)][A ring][barriers][lists]
-// `ncol` = MMA N = 2 x queries per pass; `boxes` = number of 16 KB document boxes in the ring
-inline size_t mma_smem_bytes_rt(int ncol, int dim, int k, int boxes) {
+// `ncol` = MMA N (2 x queries per CTA with hi/lo columns, 1 x in screen mode); `boxes` = number of
+// 16 KB document boxes in the ring
+inline size_t mma_smem_bytes_rt(int ncol, int dim, int k, int boxes, int split = 1) {
     return 1024 + (size_t)(dim / kBlockK) * ncol * 128 + (size_t)boxes * kStageBytes + 1024 +
-           list_bytes_rt(ncol / 2, k, 4);
+           list_bytes_rt(split ? ncol / 2 : ncol, k, 4);
 }
 
 }  // namespace vqa

@@ -30,6 +30,7 @@ struct MmaLaunch {
     const CUtensorMap *tmap;
     bool bf16;
     int ncol;
+    int split;   // 1: hi/lo column pairs; 0: screen mode (one storage-precision column per query)
     int stages;  // ring stages, each kps x 16 KB
     int kps;
     int grid;
@@ -79,7 +80,7 @@ cudaError_t launch_scan_bf16(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_f16(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_mma(const MmaLaunch &a, cudaStream_t st);
 // clusters of `cluster` CTAs of the tensor-core kernel that can be co-resident (0 if the query fails)
-int mma_max_active_clusters(bool bf16, int ncol, int cluster, size_t smem_bytes);
+int mma_max_active_clusters(bool bf16, int ncol, int split, int cluster, size_t smem_bytes);
 
 // optional exact re-scoring stage of the candidate reduce (see ReduceParams in scan.cuh)
 struct Rescore {

@@ -226,33 +226,46 @@ static __device__ __noinline__ Entry reglist_merge32(float ls, uint32_t li, floa
     return e;
 }
 
-// one 16-column group of this thread's document row: score = acc_hi + acc_lo * lo_inv_scale
-template <int NCOL>
+// one 16-column group of this thread's document row.  SPLIT: score = acc_hi + acc_lo * lo_inv_scale
+// (column j = q_hi[j], column NQ + j = q_lo[j]); otherwise one column per query.
+template <int NCOL, bool SPLIT>
 __device__ __forceinline__ void load_scores16(uint32_t taddr, int c0, float lo_inv_scale, float (&v)[16]) {
-    constexpr int NQ = NCOL / 2;
-    if constexpr (NQ >= 16) {
-        uint32_t hi[16], lo[16];
-        ptx::tmem_ld16(taddr + c0, hi);
-        ptx::tmem_ld16(taddr + NQ + c0, lo);
+    if constexpr (!SPLIT) {
+        uint32_t acc[16];
+        ptx::tmem_ld16(taddr + c0, acc);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __fmaf_rn(__uint_as_float(lo[j]), lo_inv_scale, __uint_as_float(hi[j]));
-    } else {  // NCOL == 16: one load brings hi (cols 0..7) and lo (cols 8..15)
-        uint32_t hl[16];
-        ptx::tmem_ld16(taddr, hl);
-        ptx::tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+    } else {
+        constexpr int NQ = NCOL / 2;
+        if constexpr (NQ >= 16) {
+            uint32_t hi[16], lo[16];
+            ptx::tmem_ld16(taddr + c0, hi);
+            ptx::tmem_ld16(taddr + NQ + c0, lo);
+            ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            v[j] = __fmaf_rn(__uint_as_float(hl[8 + j]), lo_inv_scale, __uint_as_float(hl[j]));
-            v[8 + j] = neg_inf();
+            for (int j = 0; j < 16; ++j)
+                v[j] = __fmaf_rn(__uint_as_float(lo[j]), lo_inv_scale, __uint_as_float(hi[j]));
+        } else {  // NCOL == 16: one load brings hi (cols 0..7) and lo (cols 8..15)
+            uint32_t hl[16];
+            ptx::tmem_ld16(taddr, hl);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = __fmaf_rn(__uint_as_float(hl[8 + j]), lo_inv_scale, __uint_as_float(hl[j]));
+                v[8 + j] = neg_inf();
+            }
         }
     }
 }
 
-template <bool BF16, int NCOL>
+// SPLIT: hi + lo column per query (NCOL / 2 queries per CTA, scores good to fp32 rounding).
+// !SPLIT: one storage-precision column per query (NCOL queries per CTA): a SCREEN whose k + spare best
+// candidates are re-scored exactly by the reduce kernel (screen-then-rescore, k + spare <= 32).
+template <bool BF16, int NCOL, bool SPLIT>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p) {
-    constexpr int NQ = NCOL / 2;                 // queries per pass: column j = q_hi[j], column NQ + j = q_lo[j]
+    constexpr int NQ = SPLIT ? NCOL / 2 : NCOL;  // queries per CTA
     constexpr int AS = mma_acc_stages<NCOL>();
     constexpr uint32_t TMEM_COLS = AS * NCOL;    // power of two, 128..512
     static_assert(NCOL % 16 == 0 && NCOL >= 16 && NCOL <= 256, "MMA N");
@@ -338,9 +351,11 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 split8<BF16>(x, p.lo_scale, hi, lo);
             }
             unsigned char *tile = q_smem + (size_t)kb * NCOL * 128;
-            const int jl = NQ + j;
             *reinterpret_cast<uint4 *>(tile + j * 128 + ((c ^ (j & 7)) << 4)) = hi;
-            *reinterpret_cast<uint4 *>(tile + jl * 128 + ((c ^ (jl & 7)) << 4)) = lo;
+            if constexpr (SPLIT) {
+                const int jl = NQ + j;
+                *reinterpret_cast<uint4 *>(tile + jl * 128 + ((c ^ (jl & 7)) << 4)) = lo;
+            }
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         ptx::tc_fence_before_sync();
@@ -442,7 +457,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
 #pragma unroll
             for (int c0 = 0; c0 < RQ; c0 += 16) {
                 float v[16];
-                load_scores16<NCOL>(taddr, c0, p.lo_inv_scale, v);
+                load_scores16<NCOL, SPLIT>(taddr, c0, p.lo_inv_scale, v);
                 bool any = false;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -509,7 +524,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
 #pragma unroll 1
             for (int c0 = 0; c0 < NQ; c0 += 16) {
                 float v[16];
-                load_scores16<NCOL>(taddr, c0, p.lo_inv_scale, v);
+                load_scores16<NCOL, SPLIT>(taddr, c0, p.lo_inv_scale, v);
                 bool any = false;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {

@@ -17,7 +17,7 @@ static unsigned long long tma_policy() {
     return pol;
 }
 
-template <bool BF16, int NCOL>
+template <bool BF16, int NCOL, bool SPLIT>
 static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     MmaParams p;
     p.q = a.q;
@@ -41,8 +41,8 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     // side-by-side chunks re-read each tile from L2: keep it there (normal policy) instead of evict-first
     p.tma_policy = a.n_groups > 1 ? 0x1000000000000000ull : tma_policy();
     p.multicast = a.multicast;
-    const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps);
-    auto kern = mma_topk_kernel<BF16, NCOL>;
+    const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps, SPLIT ? 1 : 0);
+    auto kern = mma_topk_kernel<BF16, NCOL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (!a.multicast) {
@@ -64,9 +64,9 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     return cudaLaunchKernelEx(&cfg, kern, *a.tmap, p);
 }
 
-template <bool BF16, int NCOL>
+template <bool BF16, int NCOL, bool SPLIT>
 static int max_clusters_one(int cluster, size_t smem) {
-    auto kern = mma_topk_kernel<BF16, NCOL>;
+    auto kern = mma_topk_kernel<BF16, NCOL, SPLIT>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
@@ -91,27 +91,42 @@ static int max_clusters_one(int cluster, size_t smem) {
 }
 
 template <bool BF16>
-static int max_clusters_t(int ncol, int cluster, size_t smem) {
+static int max_clusters_t(int ncol, int split, int cluster, size_t smem) {
+    if (!split) {
+        switch (ncol) {
+            case 16: return max_clusters_one<BF16, 16, false>(cluster, smem);
+            case 32: return max_clusters_one<BF16, 32, false>(cluster, smem);
+            default: return 0;
+        }
+    }
     switch (ncol) {
-        case 16: return max_clusters_one<BF16, 16>(cluster, smem);
-        case 32: return max_clusters_one<BF16, 32>(cluster, smem);
-        case 64: return max_clusters_one<BF16, 64>(cluster, smem);
-        case 128: return max_clusters_one<BF16, 128>(cluster, smem);
+        case 16: return max_clusters_one<BF16, 16, true>(cluster, smem);
+        case 32: return max_clusters_one<BF16, 32, true>(cluster, smem);
+        case 64: return max_clusters_one<BF16, 64, true>(cluster, smem);
+        case 128: return max_clusters_one<BF16, 128, true>(cluster, smem);
         default: return 0;
     }
 }
 
-int mma_max_active_clusters(bool bf16, int ncol, int cluster, size_t smem_bytes) {
-    return bf16 ? max_clusters_t<true>(ncol, cluster, smem_bytes) : max_clusters_t<false>(ncol, cluster, smem_bytes);
+int mma_max_active_clusters(bool bf16, int ncol, int split, int cluster, size_t smem_bytes) {
+    return bf16 ? max_clusters_t<true>(ncol, split, cluster, smem_bytes)
+                : max_clusters_t<false>(ncol, split, cluster, smem_bytes);
 }
 
 template <bool BF16>
 static cudaError_t launch_mma_t(const MmaLaunch &a, cudaStream_t st) {
+    if (!a.split) {
+        switch (a.ncol) {
+            case 16: return launch_mma_one<BF16, 16, false>(a, st);
+            case 32: return launch_mma_one<BF16, 32, false>(a, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (a.ncol) {
-        case 16: return launch_mma_one<BF16, 16>(a, st);
-        case 32: return launch_mma_one<BF16, 32>(a, st);
-        case 64: return launch_mma_one<BF16, 64>(a, st);
-        case 128: return launch_mma_one<BF16, 128>(a, st);
+        case 16: return launch_mma_one<BF16, 16, true>(a, st);
+        case 32: return launch_mma_one<BF16, 32, true>(a, st);
+        case 64: return launch_mma_one<BF16, 64, true>(a, st);
+        case 128: return launch_mma_one<BF16, 128, true>(a, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -346,21 +346,31 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
                 const unsigned char *row = p.rs_rows + (long long)li * p.rs_stride;
                 const float *qv = p.rs_q + (long long)q * p.rs_q_stride;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int c = 0; c < p.rs_dim / 8; ++c) {
-                    const uint4 w = *reinterpret_cast<const uint4 *>(row + c * 16);
-                    const float4 q0 = *reinterpret_cast<const float4 *>(qv + c * 8);
-                    const float4 q1 = *reinterpret_cast<const float4 *>(qv + c * 8 + 4);
-                    float x[8];
-                    if (p.rs_bf16) Elem<__nv_bfloat16>::unpack(w, x);
-                    else Elem<__half>::unpack(w, x);
-                    a0 = fmaf(q0.x, x[0], a0);
-                    a1 = fmaf(q0.y, x[1], a1);
-                    a2 = fmaf(q0.z, x[2], a2);
-                    a3 = fmaf(q0.w, x[3], a3);
-                    a0 = fmaf(q1.x, x[4], a0);
-                    a1 = fmaf(q1.y, x[5], a1);
-                    a2 = fmaf(q1.z, x[6], a2);
-                    a3 = fmaf(q1.w, x[7], a3);
+                const int nch = p.rs_dim / 8;
+                constexpr int RB = 12;  // 16-byte row chunks fetched together (the row is a cold DRAM read)
+                for (int c0 = 0; c0 < nch; c0 += RB) {
+                    uint4 w[RB];
+#pragma unroll
+                    for (int u = 0; u < RB; ++u)
+                        w[u] = c0 + u < nch ? ldg_stream(row + (c0 + u) * 16) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int u = 0; u < RB; ++u) {
+                        if (c0 + u < nch) {
+                            const float4 q0 = *reinterpret_cast<const float4 *>(qv + (c0 + u) * 8);
+                            const float4 q1 = *reinterpret_cast<const float4 *>(qv + (c0 + u) * 8 + 4);
+                            float x[8];
+                            if (p.rs_bf16) Elem<__nv_bfloat16>::unpack(w[u], x);
+                            else Elem<__half>::unpack(w[u], x);
+                            a0 = fmaf(q0.x, x[0], a0);
+                            a1 = fmaf(q0.y, x[1], a1);
+                            a2 = fmaf(q0.z, x[2], a2);
+                            a3 = fmaf(q0.w, x[3], a3);
+                            a0 = fmaf(q1.x, x[4], a0);
+                            a1 = fmaf(q1.y, x[5], a1);
+                            a2 = fmaf(q1.z, x[6], a2);
+                            a3 = fmaf(q1.w, x[7], a3);
+                        }
+                    }
                 }
                 exact = (a0 + a1) + (a2 + a3);
             } else {
