@@ -100,7 +100,7 @@ static cudaError_t launch_pool_tm(const void *hidden, const void *mask, int batc
 template <typename T, int ITERS>
 static cudaError_t launch_pool_warp(const void *hidden, const void *mask, int m_dtype, int batch, int seq, int dim,
                                     int normalize, float *out, cudaStream_t st) {
-    const size_t smem = ((size_t)(kPoolWarps + 1) * dim + 40) * sizeof(float);
+    const size_t smem = ((size_t)(kPoolWarps + 1) * dim + 32 + kPoolWarps) * sizeof(float);  // part, pooled, red[32], cntw
     auto kern = pool_normalize_warp_kernel<T, ITERS>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -326,6 +326,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         ptx::tmem_alloc(tmem_slot, TMEM_COLS);
         ptx::tmem_relinquish();
         ptx::tc_fence_before_sync();
+        __syncwarp();
         named_bar_arrive(1, kMmaThreads);
     } else {
         const int stid = tid < 128 ? tid : tid - 32;  // 0..159 over warps 0-3 and 5
@@ -359,6 +360,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         ptx::tc_fence_before_sync();
+        __syncwarp();  // the staging loops above leave the lanes diverged
         named_bar_sync(1, kMmaThreads);
         ptx::tc_fence_after_sync();
         // broadcast through a shuffle so the compiler keeps the TMEM base in a uniform register

@@ -133,7 +133,7 @@ __device__ __forceinline__ float mask_at(const void *m, int mdt, long long idx) 
 // Fast path (row of <= ITERS*512 bytes): one warp per TOKEN, lanes stride over the row's 16-byte
 // chunks, 4 tokens in flight per warp (ITERS*4 independent 128-bit loads per lane), 16 warps per CTA
 // splitting the sequence, fp32 partial sums combined through shared memory.  grid = B.
-// dynamic smem: (16 + 1) * dim + 40 floats.
+// dynamic smem: (16 + 1) * dim + 32 + 16 floats.
 constexpr int kPoolFastThreads = 512;
 constexpr int kPoolWarps = kPoolFastThreads / 32;
 constexpr int kPoolUnroll = 4;

@@ -155,6 +155,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
 
     if (warp == 4) {
         // ===== TMA producer =====
+        named_bar_arrive(1, kMmaThreads);  // (does not wait for the query block: documents start streaming now)
         uint32_t it = 0;
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams) {
             for (int kg = 0; kg < KG; ++kg, ++it) {
@@ -179,7 +180,8 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         }
     } else if (warp == 5) {
         // ===== MMA issuer: waits for the query block (named barrier 1), then D = Q * docs^T =====
-        named_bar_sync(1, 160);
+        __syncwarp();
+        named_bar_sync(1, kMmaThreads);
         ptx::tc_fence_after_sync();
         uint32_t it = 0, lt = 0;
         const uint32_t ring = ptx::smem_u32(a_smem);
@@ -246,7 +248,8 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             }
             tmem_st_wait();
             ptx::tc_fence_before_sync();
-            named_bar_sync(1, 160);  // with the MMA warp
+            __syncwarp();
+            named_bar_sync(1, kMmaThreads);  // with the MMA warp
         }
         // 2. private list + threshold
         float tau = (live && !is_lo) ? neg_inf() : __int_as_float(0x7f800000);
@@ -338,6 +341,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) xb[(c0 + j) * 64 + (row & 63)] = v[j];
                     }
+                    __syncwarp();
                     named_bar_sync(2 + (warp & 1), 64);  // warps (0,2) and (1,3) pair up
                     if (!is_lo) {
 #pragma unroll
