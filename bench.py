@@ -180,7 +180,7 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, max(3, args.warmup)
     lo, hi = shard_bounds(args.rows, world, rank)
     rows = make_shard(torch, ops, hi - lo, 1234 + rank, device)
-    index = ShardedFlat(rows, args.rows, mode="fast")
+    index = ShardedFlat(rows, args.rows, mode="fast", exchange=os.environ.get("VQA_EXCHANGE", "nccl"))
     gq = torch.Generator(device="cpu").manual_seed(4321)
     q_host_all = torch.randn((max(B, 1024), DIM), generator=gq, dtype=torch.float32)
     q_dev_all = ops.normalize_rows(q_host_all.to(device))
@@ -348,6 +348,10 @@ def run_ours(args):
             "config": {"workload": f"top-{TOPK} exact cosine search over {args.rows}x{DIM} bf16 docs, batch {B}, "
                                    f"row-sharded over {world} GPU(s)", "rows": args.rows, "dim": DIM, "batch": B,
                        "k": TOPK, "rows_per_gpu": hi - lo, "parallelism": f"row-shard x{world}",
+                       "exchange": ("none" if world == 1 else
+                                    ("nvlink peer-memory push + flag-waiting merge kernel"
+                                     if any(b[7] is not None for b in index._bufs.values())
+                                     else "one NCCL all-gather + merge kernel")),
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB per GPU streamed per step)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": K * (launches + merge_launches),

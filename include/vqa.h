@@ -170,6 +170,24 @@ VQA_API int vqa_merge_topk_strided(const float *cand_scores_dev, const int64_t *
                                    int64_t *out_ids_dev, int32_t device, void *stream);
 
 /*
+ * Exchange step over NVLink / NVSwitch PEER MEMORY instead of NCCL (optional; needs buffers mapped on
+ * every rank, e.g. torch symmetric memory).  vqa_exchange_push copies this rank's packed result block
+ * into its slot of every peer's gather buffer with peer stores and then publishes `epoch` in that
+ * peer's flag (release, system scope); vqa_merge_topk_wait is vqa_merge_topk_strided whose kernel
+ * first acquires all n_lists flags (>= epoch).  peer_*_ptrs are HOST arrays of `world` device
+ * pointers (peer r's slot for this rank / peer r's flag for this rank); flags_dev is this rank's own
+ * flag array, one per rank.  k_out <= 32.
+ */
+VQA_API int vqa_exchange_push(const void *local_block_dev, size_t block_bytes, void *const *peer_slot_ptrs,
+                              uint64_t *const *peer_flag_ptrs, int32_t world, uint64_t epoch, int32_t device,
+                              void *stream);
+VQA_API int vqa_merge_topk_wait(const float *cand_scores_dev, const int64_t *cand_ids_dev,
+                                int64_t list_stride_scores, int64_t list_stride_ids, int32_t n_lists,
+                                int32_t n_queries, int32_t k_in, int32_t k_out, float *out_scores_dev,
+                                int64_t *out_ids_dev, const uint64_t *flags_dev, uint64_t epoch,
+                                int32_t device, void *stream);
+
+/*
  * Fused masked mean-pool (+ optional L2 normalise) over encoder hidden states:
  *   e[b,:] = sum_s h[b,s,:]*m[b,s] / max(sum_s m[b,s], 1e-9);  e /= ||e||_2
  * Replaces: txtai MeanPooling.forward + normalize under Embeddings.search()/

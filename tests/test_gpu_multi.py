@@ -26,17 +26,22 @@ q = torch.randn(B, D, generator=g); q[0] = docs[0]
 rows = ops.normalize_rows(docs.to(dev)); qd = ops.normalize_rows(q.to(dev))
 lo, hi = shard_bounds(N, world, rank)
 ok = True
-for storage, mode in ((torch.float32, "verify"), (torch.bfloat16, "verify"), (torch.bfloat16, "fast")):
+for exchange in ("nccl", "p2p"):
+  for storage, mode in ((torch.float32, "verify"), (torch.bfloat16, "verify"), (torch.bfloat16, "fast")):
     full = ops.FlatShard(rows.to(storage))
     fs, fi = full.search(qd, K, mode)
-    sh = ShardedFlat(rows[lo:hi].to(storage).contiguous(), N, mode=mode)
-    s, i = sh.search(qd, K)
+    sh = ShardedFlat(rows[lo:hi].to(storage).contiguous(), N, mode=mode, exchange=exchange)
+    for rep in range(3):                      # repeated searches exercise the epoch / parity protocol
+        s, i = sh.search(qd, K)
     if mode == "verify":
         ok = ok and torch.equal(i, fi) and torch.equal(s, fs)
     else:
         rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / K for a, b in zip(i.cpu(), fi.cpu())])
         ok = ok and rec >= 0.999
     ok = ok and i[0, :3].tolist() == [0, N // 2, N - 1]
+    if not ok:
+        print("FAILED", exchange, storage, mode, rank, flush=True)
+        break
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
 sys.exit(0 if int(t.item()) == 1 else 1)

@@ -26,7 +26,8 @@ MODES = {"verify": MODE_VERIFY, "fp32": MODE_VERIFY, "fast": MODE_FAST, "stream"
 EXPORTS = [
     "vqa_version", "vqa_last_error", "vqa_device_count", "vqa_index_create", "vqa_index_bind",
     "vqa_index_destroy", "vqa_workspace_bytes", "vqa_search", "vqa_search_host_staging_bytes",
-    "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
+    "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_exchange_push", "vqa_merge_topk_wait",
+    "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
     "vqa_search_plan",
 ]
 
@@ -65,6 +66,10 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_merge_topk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
     L.vqa_merge_topk_strided.restype = c.c_int
     L.vqa_merge_topk_strided.argtypes = [vp, vp, i64, i64, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.vqa_exchange_push.restype = c.c_int
+    L.vqa_exchange_push.argtypes = [vp, sz, c.POINTER(vp), c.POINTER(vp), i32, c.c_uint64, i32, vp]
+    L.vqa_merge_topk_wait.restype = c.c_int
+    L.vqa_merge_topk_wait.argtypes = [vp, vp, i64, i64, i32, i32, i32, i32, vp, vp, vp, c.c_uint64, i32, vp]
     L.vqa_pool_normalize.restype = c.c_int
     L.vqa_pool_normalize.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]
     L.vqa_normalize_rows.restype = c.c_int

@@ -194,7 +194,7 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     if (stages < 2) return false;
     pl->family = VQA_MODE_FAST_TS;
     pl->ts_split = split;
-    pl->ts_afp16 = env_int("VQA_TS_AFP16", 0) != 0;
+    pl->ts_afp16 = 0;  // (fp16 queries against bf16 rows would halve the rounding, but the MMA rejects mixed operands)
     pl->pass_nq = split ? 64 : 128;
     pl->ncol = 0;
     pl->stages = stages;
@@ -636,6 +636,51 @@ int vqa_merge_topk_strided(const float *cand_scores_dev, const int64_t *cand_ids
                                            list_stride_ids, k_in, n_lists, k_in, k_out, 0, out_scores_dev,
                                            (long long *)out_ids_dev, n_queries,
                                            reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_exchange_push(const void *local_block_dev, size_t block_bytes, void *const *peer_slot_ptrs,
+                      uint64_t *const *peer_flag_ptrs, int32_t world, uint64_t epoch, int32_t device, void *stream) {
+    if (!local_block_dev || !peer_slot_ptrs || !peer_flag_ptrs) return fail(VQA_E_INVALID, "null pointer argument");
+    if (world < 1 || world > 16) return fail(VQA_E_INVALID, "world must be in [1, 16] (got %d)", world);
+    if (block_bytes == 0 || block_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(local_block_dev) % 16 != 0)
+        return fail(VQA_E_INVALID, "block must be 16-byte aligned and a multiple of 16 bytes");
+    for (int r = 0; r < world; ++r)
+        if (!peer_slot_ptrs[r] || !peer_flag_ptrs[r] || reinterpret_cast<uintptr_t>(peer_slot_ptrs[r]) % 16 != 0)
+            return fail(VQA_E_INVALID, "peer pointer %d is null or misaligned", r);
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_exchange_push(local_block_dev, block_bytes, peer_slot_ptrs,
+                                              reinterpret_cast<unsigned long long *const *>(peer_flag_ptrs), world,
+                                              (unsigned long long)epoch, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "exchange push launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_merge_topk_wait(const float *cand_scores_dev, const int64_t *cand_ids_dev, int64_t list_stride_scores,
+                        int64_t list_stride_ids, int32_t n_lists, int32_t n_queries, int32_t k_in, int32_t k_out,
+                        float *out_scores_dev, int64_t *out_ids_dev, const uint64_t *flags_dev, uint64_t epoch,
+                        int32_t device, void *stream) {
+    if (!cand_scores_dev || !cand_ids_dev || !out_scores_dev || !out_ids_dev || !flags_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (n_lists < 1 || n_lists > 32 || n_queries < 1 || k_in < 1)
+        return fail(VQA_E_INVALID, "n_lists must be in [1, 32]; n_queries, k_in >= 1");
+    if (k_out < 1 || k_out > 32) return fail(VQA_E_INVALID, "k_out must be in [1, 32] for the flag-waiting merge");
+    if (list_stride_scores < (int64_t)n_queries * k_in || list_stride_ids < (int64_t)n_queries * k_in)
+        return fail(VQA_E_INVALID, "list strides must be >= n_queries * k_in elements");
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    vqa::WaitFlags wf;
+    wf.flags = reinterpret_cast<const unsigned long long *>(flags_dev);
+    wf.n = n_lists;
+    wf.epoch = epoch;
+    cudaError_t e = vqa::launch_reduce_i64(cand_scores_dev, (const long long *)cand_ids_dev, list_stride_scores,
+                                           list_stride_ids, k_in, n_lists, k_in, k_out, 0, out_scores_dev,
+                                           (long long *)out_ids_dev, n_queries, reinterpret_cast<cudaStream_t>(stream),
+                                           &wf);
     if (e != cudaSuccess) return fail(VQA_E_CUDA, "merge launch failed: %s", cudaGetErrorString(e));
     return VQA_OK;
 }

@@ -97,9 +97,18 @@ cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long 
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                               int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr);
+struct WaitFlags {
+    const unsigned long long *flags = nullptr;
+    int n = 0;
+    unsigned long long epoch = 0;
+};
+cudaError_t launch_exchange_push(const void *local, size_t bytes, void *const *peer_slots,
+                                 unsigned long long *const *peer_flags, int world, unsigned long long epoch,
+                                 cudaStream_t st);
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
-                              float *out_s, long long *out_i, int n_queries, cudaStream_t st);
+                              float *out_s, long long *out_i, int n_queries, cudaStream_t st,
+                              const WaitFlags *wf = nullptr);
 cudaError_t launch_pool(const void *hidden, int h_dtype, const void *mask, int m_dtype, int batch, int seq,
                         int dim, int normalize, float *out, cudaStream_t st);
 cudaError_t launch_normalize(const float *in, long long in_stride, long long n_rows, int dim, float *out,

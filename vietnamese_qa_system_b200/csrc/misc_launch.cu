@@ -20,8 +20,12 @@ template <typename IdT>
 static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long long list_stride,
                                    long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                                    float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                                   int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr) {
+                                   int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr,
+                                   const WaitFlags *wf = nullptr) {
     ReduceParams<IdT> p;
+    p.wait_flags = wf ? wf->flags : nullptr;
+    p.wait_n = wf ? wf->n : 0;
+    p.wait_epoch = wf ? wf->epoch : 0;
     p.tau_g_reset = tau_g_reset;
     p.rs_rows = rs ? static_cast<const unsigned char *>(rs->rows) : nullptr;
     p.rs_stride = rs ? rs->stride : 0;
@@ -73,10 +77,26 @@ cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long 
                                      out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, rs);
 }
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
-                              long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
-                              float *out_s, long long *out_i, int n_queries, cudaStream_t st) {
+                              long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out,
+                              long long id_base, float *out_s, long long *out_i, int n_queries, cudaStream_t st,
+                              const WaitFlags *wf) {
     return launch_reduce_t<long long>(cand_s, cand_i, list_stride, list_stride_i, query_stride, n_lists, k_in, k_out, id_base,
-                                      out_s, out_i, n_queries, nullptr, 1, 1, st);
+                                      out_s, out_i, n_queries, nullptr, 1, 1, st, nullptr, wf);
+}
+
+cudaError_t launch_exchange_push(const void *local, size_t bytes, void *const *peer_slots,
+                                 unsigned long long *const *peer_flags, int world, unsigned long long epoch,
+                                 cudaStream_t st) {
+    PushParams p;
+    p.local = static_cast<const uint4 *>(local);
+    p.n16 = bytes / 16;
+    for (int r = 0; r < 16; ++r) {
+        p.peer_slot[r] = r < world ? static_cast<uint4 *>(peer_slots[r]) : nullptr;
+        p.peer_flag[r] = r < world ? peer_flags[r] : nullptr;
+    }
+    p.epoch = epoch;
+    exchange_push_kernel<<<world, 256, 0, st>>>(p);
+    return cudaGetLastError();
 }
 
 template <typename T, typename MT>

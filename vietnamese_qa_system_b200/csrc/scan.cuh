@@ -253,7 +253,43 @@ struct ReduceParams {
     const float *rs_q;     // fp32 queries of this reduce launch
     long long rs_q_stride;
     int k_final;           // entries written per query (<= k_out); out arrays are [n_queries][k_final]
+    // Peer-memory exchange: the candidate lists were pushed into this rank's gather buffer by its peers'
+    // push kernels; wait (acquire, system scope) until every one of the wait_n flags has reached wait_epoch.
+    const unsigned long long *wait_flags;
+    int wait_n;
+    unsigned long long wait_epoch;
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exchange step over NVLink / NVSwitch peer memory (no NCCL on the data path): CTA r copies this rank's
+// packed [scores | ids] block into slot `rank` of peer r's gather buffer with 16-byte peer stores, then
+// publishes `epoch` in that peer's flag slot with release semantics at system scope.
+struct PushParams {
+    const uint4 *local;         // this rank's packed block
+    unsigned long long n16;     // its size in 16-byte units
+    uint4 *peer_slot[16];       // peer r's gather buffer, already offset to (parity, slot = my rank)
+    unsigned long long *peer_flag[16];  // peer r's flag for (parity, my rank)
+    unsigned long long epoch;
+};
+
+static __global__ void __launch_bounds__(256) exchange_push_kernel(const PushParams p) {
+    const int r = blockIdx.x;
+    uint4 *dst = p.peer_slot[r];
+    for (unsigned long long i = threadIdx.x; i < p.n16; i += blockDim.x) dst[i] = p.local[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys_u64(p.peer_flag[r], p.epoch);
+    }
+}
 
 __device__ __forceinline__ float shfl_xor_any(float v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
 __device__ __forceinline__ uint32_t shfl_xor_any(uint32_t v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
@@ -280,6 +316,15 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
     const int q = blockIdx.x * kReduceWarpsPerCta + (threadIdx.x >> 5);
     grid_dependency_wait();
     if (q >= p.n_queries) return;
+    if (p.wait_flags != nullptr) {
+        if (lane < p.wait_n) {
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u64(p.wait_flags + lane) < p.wait_epoch) {
+                if (++spins > (1ull << 31)) __trap();  // a peer died: fail the launch instead of hanging
+            }
+        }
+        __syncwarp();
+    }
     float ls = neg_inf();
     IdT li = invalid_id<IdT>();
     float tau = neg_inf();

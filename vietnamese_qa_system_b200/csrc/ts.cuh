@@ -40,7 +40,7 @@ struct TsParams {
     int nq;        // queries in this launch
     int per_cta;   // queries per CTA: 128, or 64 with split
     int split;
-    int a_fp16;    // A (queries) stored as fp16 even if documents are bf16 (mixed kind::f16 operands)
+    int a_fp16;    // must be 0: mixing an fp16 A with bf16 B in one kind::f16 MMA is an illegal instruction on sm_100a
     int k;
     long long n_rows;
     int dim;       // multiple of 64, <= 768

@@ -181,6 +181,50 @@ def merge_topk_packed(gathered: torch.Tensor, n_lists: int, n_queries: int, k: i
     return out_scores, out_ids
 
 
+class PeerExchange:
+    """Symmetric (peer-mapped) gather buffers + flags for the NCCL-free exchange (``vqa_exchange_push`` /
+    ``vqa_merge_topk_wait``).  Layout of every rank's symmetric allocation: two parities x ``world`` slots
+    of ``block`` bytes, then two parities x ``world`` uint64 flags.  Creation is collective."""
+
+    def __init__(self, block: int, rank: int, world: int, device: torch.device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.block, self.rank, self.world, self.device = block, rank, world, device
+        self.data_bytes = 2 * world * block
+        total = self.data_bytes + 2 * world * 8
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group=group if group is not None else dist.group.WORLD)
+        self.peer_bases = [int(p) for p in self.handle.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # everyone's flags are zero before the first push
+        self.epoch = 0
+        self._slots = (ctypes.c_void_p * world)()
+        self._flags = (ctypes.c_void_p * world)()
+
+    def push_and_merge(self, local: torch.Tensor, b: int, k: int, ids_off: int, out_s: torch.Tensor,
+                       out_i: torch.Tensor):
+        self.epoch += 1
+        par = self.epoch & 1
+        w, blk = self.world, self.block
+        for r in range(w):
+            base = self.peer_bases[r]
+            self._slots[r] = base + (par * w + self.rank) * blk
+            self._flags[r] = base + self.data_bytes + (par * w + self.rank) * 8
+        st = ctypes.c_void_p(_stream(self.device))
+        dev = self.device.index or 0
+        N.check(N.lib().vqa_exchange_push(ctypes.c_void_p(local.data_ptr()), blk, self._slots, self._flags, w,
+                                          self.epoch, dev, st))
+        mine = self.buf.data_ptr()
+        gathered = mine + par * w * blk
+        N.check(N.lib().vqa_merge_topk_wait(ctypes.c_void_p(gathered), ctypes.c_void_p(gathered + ids_off), blk // 4,
+                                            blk // 8, w, b, k, k, ctypes.c_void_p(out_s.data_ptr()),
+                                            ctypes.c_void_p(out_i.data_ptr()),
+                                            ctypes.c_void_p(mine + self.data_bytes + par * w * 8), self.epoch, dev, st))
+        return out_s, out_i
+
+
 def pool_normalize(hidden: torch.Tensor, mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:
     """K1: hidden [B,S,D] (f32/bf16/f16), mask [B,S] (int64/int32/bool/uint8/f32) -> float32 [B,D]."""
     _need_cuda(hidden, "hidden")
