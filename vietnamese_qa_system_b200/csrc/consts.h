@@ -23,8 +23,10 @@ inline size_t list_bytes_rt(int nq, int k, int id_bytes) {
 // `ncol` = MMA N (2 x queries per CTA with hi/lo columns, 1 x in screen mode); `boxes` = number of
 // 16 KB document boxes in the ring
 inline size_t mma_smem_bytes_rt(int ncol, int dim, int k, int boxes, int split = 1) {
-    return 1024 + (size_t)(dim / kBlockK) * ncol * 128 + (size_t)boxes * kStageBytes + 1024 +
-           list_bytes_rt(split ? ncol / 2 : ncol, k, 4);
+    const int nq = split ? ncol / 2 : ncol;
+    // k <= 32 and <= 32 queries per CTA: the lists live in registers, no shared-memory lists at all
+    const size_t lists = (nq <= 32 && k <= 32) ? 0 : list_bytes_rt(nq, k, 4);
+    return 1024 + (size_t)(dim / kBlockK) * ncol * 128 + (size_t)boxes * kStageBytes + 1024 + lists;
 }
 
 }  // namespace vqa

@@ -331,31 +331,47 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     } else {
         const int stid = tid < 128 ? tid : tid - 32;  // 0..159 over warps 0-3 and 5
         constexpr int NST = kMmaThreads - 32;
-        list_init(L, NQ, stid, NST);
         grid_launch_dependents();  // lets the (PDL) candidate-reduce grid be scheduled as SMs drain
-        // padding queries never produce candidates (same thread wrote tau[q] in list_init)
-        for (int q = stid; q < NQ; q += NST)
-            if (q >= nq) L.tau[q] = __int_as_float(0x7f800000);
+        if (!(NQ <= 32 && p.k <= 32)) {  // shared-memory lists exist only when the register path is not used
+            list_init(L, NQ, stid, NST);
+            // padding queries never produce candidates (same thread wrote tau[q] in list_init)
+            for (int q = stid; q < NQ; q += NST)
+                if (q >= nq) L.tau[q] = __int_as_float(0x7f800000);
+        }
         // queries -> shared memory, K-major, 128B-swizzled, hi and lo parts.
         // unit of work: one 16-byte chunk (8 elements) of one query row.
         const int chunks_per_row = p.dim / 8;
         const int total = NQ * chunks_per_row;
-        for (int idx = stid; idx < total; idx += NST) {
-            const int j = idx / chunks_per_row;   // query row
-            const int cg = idx % chunks_per_row;  // global chunk
-            const int kb = cg >> 3, c = cg & 7;
-            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
-            if (j < nq) {
-                const float4 *src = reinterpret_cast<const float4 *>(qsrc + (long long)j * p.q_stride + cg * 8);
-                const float4 v0 = src[0], v1 = src[1];
-                const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                split8<BF16>(x, p.lo_scale, hi, lo);
+        constexpr int QU = 4;  // chunks per thread whose (L2-latency) loads are issued together
+        for (int idx0 = stid; idx0 < total; idx0 += NST * QU) {
+            float4 v0[QU], v1[QU];
+#pragma unroll
+            for (int u = 0; u < QU; ++u) {
+                const int idx = idx0 + u * NST;
+                const int j = idx / chunks_per_row, cg = idx % chunks_per_row;
+                v0[u] = v1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < total && j < nq) {
+                    const float4 *src = reinterpret_cast<const float4 *>(qsrc + (long long)j * p.q_stride + cg * 8);
+                    v0[u] = src[0];
+                    v1[u] = src[1];
+                }
             }
-            unsigned char *tile = q_smem + (size_t)kb * NCOL * 128;
-            *reinterpret_cast<uint4 *>(tile + j * 128 + ((c ^ (j & 7)) << 4)) = hi;
-            if constexpr (SPLIT) {
-                const int jl = NQ + j;
-                *reinterpret_cast<uint4 *>(tile + jl * 128 + ((c ^ (jl & 7)) << 4)) = lo;
+#pragma unroll
+            for (int u = 0; u < QU; ++u) {
+                const int idx = idx0 + u * NST;
+                if (idx >= total) break;
+                const int j = idx / chunks_per_row;   // query row
+                const int cg = idx % chunks_per_row;  // global chunk
+                const int kb = cg >> 3, c = cg & 7;
+                uint4 hi, lo;
+                const float x[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+                split8<BF16>(x, p.lo_scale, hi, lo);  // zero rows (padding queries) stay zero
+                unsigned char *tile = q_smem + (size_t)kb * NCOL * 128;
+                *reinterpret_cast<uint4 *>(tile + j * 128 + ((c ^ (j & 7)) << 4)) = hi;
+                if constexpr (SPLIT) {
+                    const int jl = NQ + j;
+                    *reinterpret_cast<uint4 *>(tile + jl * 128 + ((c ^ (jl & 7)) << 4)) = lo;
+                }
             }
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
