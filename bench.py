@@ -265,6 +265,7 @@ def run_ours(args):
 
     # ---- recall@10 of the fast path against fp32-verify arithmetic on the same rows -----
     s_fast, i_fast = index.search(q_dev, TOPK, "fast")
+    s_fast, i_fast = s_fast.clone(), i_fast.clone()  # the sharded index reuses its output buffers
     s_ver, i_ver = index.search(q_dev, TOPK, "verify")
     index.mode = "fast"
     torch.cuda.synchronize()
