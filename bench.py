@@ -331,6 +331,42 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             pool = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- BASELINE configs[0] (the reference's own CPU-runnable case): 10k x 768 fp32, 64 queries, top-5 --
+    config_a = None
+    if rank == 0 and world == 1 and args.sweep and not args.no_cpu:
+        try:
+            import oracle
+            from tests.golden import inputs as golden_inputs
+
+            docs_a, q_a = golden_inputs.config_a()
+            sh_a = ops.FlatShard(torch.from_numpy(docs_a).to(device))
+            qa_dev = torch.from_numpy(q_a).to(device)
+            s_a, i_a = sh_a.search(qa_dev, 5, "verify")
+            os_a, oi_a = oracle.search(docs_a, q_a, 5, oracle.CANONICAL, "fp32")
+            ids_exact = bool(np.array_equal(i_a.cpu().numpy(), oi_a))
+            bits_exact = bool(np.array_equal(s_a.cpu().numpy().view(np.int32), os_a.view(np.int32)))
+            gms = timed(lambda: sh_a.search(qa_dev, 5, "verify"), 50, 5) / 50
+            qa_pin = torch.from_numpy(q_a).pin_memory()
+            hms = timed(lambda: sh_a.search_host(qa_pin, 5, "verify"), 50, 5) / 50
+            t0 = time.perf_counter()
+            for _ in range(3):
+                for r in range(q_a.shape[0]):          # one query at a time, as heavy_ranker.py:97-101 drives it
+                    oracle.np_search(docs_a, q_a[r:r + 1], 5)
+            loop_ms = (time.perf_counter() - t0) / 3 * 1e3
+            t0 = time.perf_counter()
+            for _ in range(10):
+                oracle.np_search_fast(docs_a, q_a, 5)
+            batch_ms = (time.perf_counter() - t0) / 10 * 1e3
+            config_a = {"workload": "10k x 768 fp32 docs, 64 queries, top-5, fp32 verify mode",
+                        "ids_bit_identical_to_oracle": ids_exact, "score_bits_identical_to_oracle": bits_exact,
+                        "gpu_ms_device_resident": gms, "gpu_ms_host_buffers": hms,
+                        "gpu_qps_host_buffers": 64 / hms * 1e3,
+                        "cpu_ms_one_query_at_a_time_numpy": loop_ms, "cpu_qps_one_query_at_a_time": 64 / loop_ms * 1e3,
+                        "cpu_ms_batched_numpy_blas": batch_ms, "cpu_qps_batched": 64 / batch_ms * 1e3,
+                        "cpu_cores": os.cpu_count() or 1}
+        except Exception as exc:  # noqa: BLE001
+            config_a = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -357,7 +393,7 @@ def run_ours(args):
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": K * (launches + merge_launches),
             "recall_at_10": recall, "recall_at_10_batch256": recall_b256, "fast_vs_verify_max_rel_score_err": max_rel,
-            "sweep": sweep, "pool_k1": pool,
+            "sweep": sweep, "pool_k1": pool, "config_a_reference_scale": config_a,
             "lib": f"libvqa_b200.so v{vqa._native.lib().vqa_version()}",
         }
         print(json.dumps(line), flush=True)

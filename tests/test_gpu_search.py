@@ -173,6 +173,8 @@ def test_family_selection_and_launch_count():
     assert ops.FlatShard(rows32).plan(32, 10, "fast")[0] == 2                         # fp32 rows never use tcgen05
     with pytest.raises(NotImplementedError):
         ops.FlatShard(rows32).search(torch.zeros((2, 768), device=DEV), 5, "tensor")
+    with pytest.raises(NotImplementedError):
+        ops.FlatShard(rows32).search(torch.zeros((2, 768), device=DEV), 5, "ts")
 
 
 def test_error_behaviour():
