@@ -373,7 +373,7 @@ int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t 
     if (n_launches)
         *n_launches = (pl.family == VQA_MODE_FAST_TENSOR || pl.family == VQA_MODE_FAST_TS)
                           ? 2 * ((pl.passes + pl.groups - 1) / pl.groups)
-                          : pl.passes + 1;
+                          : 2;  // stream family: one scan launch (grid.y = passes) + one reduce
     return VQA_OK;
 }
 
@@ -551,9 +551,20 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
 
     int n_lists = 0;
     if (h->n_rows > 0) {
+        // All passes of <= pass_nq queries go out as ONE launch (grid.y = passes).  The SMs are divided
+        // among the passes so that they run side by side in one wave -- on a small index no SM sits through
+        // a CTA's fixed cost for nothing, on a large one the passes stream the same rows together and
+        // share them through L2 -- and no CTA gets fewer than ~512 rows.
+        const int passes_total = (n_queries + pl.pass_nq - 1) / pl.pass_nq;
+        long long gx = (h->n_rows + 511) / 512;
+        if (gx > pl.grid) gx = pl.grid;
+        if (passes_total > 1 && gx > pl.grid / passes_total) gx = pl.grid / passes_total;
+        if (gx < 1) gx = 1;
+        pl.grid = (int)gx;
         n_lists = pl.grid;
-        for (int p0 = 0; p0 < n_queries; p0 += pl.pass_nq) {
-            const int nq = n_queries - p0 < pl.pass_nq ? n_queries - p0 : pl.pass_nq;
+        const int per_launch = pl.pass_nq * 32768;
+        for (int p0 = 0; p0 < n_queries; p0 += per_launch) {
+            const int nq = n_queries - p0 < per_launch ? n_queries - p0 : per_launch;
             vqa::ScanLaunch a;
             a.dtype = h->dtype;
             a.bt = pl.pass_nq;

@@ -27,7 +27,7 @@ struct ScanParams {
     int dim;
     const float *q;      // first query of this pass
     long long q_stride;  // elements
-    int nq;              // queries in this pass (<= BT)
+    int nq;              // queries in this LAUNCH; blockIdx.y = pass p handles queries [p*BT, min(nq, (p+1)*BT))
     int k;
     float *cand_s;       // [grid][cand_stride] ; this pass writes [.., nq*k) at its offset
     uint32_t *cand_i;
@@ -95,6 +95,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     const int iters = ITERS > 0 ? ITERS : (nchunks + 31) / 32;
     const int qfl = iters * 32 * E;
 
+    // one launch covers every pass of <= BT queries (grid.y): no launch gaps on small indexes
+    const int q0 = blockIdx.y * BT;
+    const int nq = p.nq - q0 < BT ? p.nq - q0 : BT;
+    const float *qsrc = p.q + (long long)q0 * p.q_stride;
     float4 *qs = reinterpret_cast<float4 *>(smem);
     ListView<uint32_t> L = list_carve<uint32_t>(smem + (size_t)BT * qfl * sizeof(float), BT, p.k);
     list_init(L, BT, tid, kScanThreads);
@@ -108,8 +112,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         const int b = idx / (32 * H * iters);
         const int chunk = it * 32 + ln;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < p.nq && chunk < nchunks)
-            v = *reinterpret_cast<const float4 *>(p.q + (long long)b * p.q_stride + chunk * E + h * 4);
+        if (b < nq && chunk < nchunks)
+            v = *reinterpret_cast<const float4 *>(qsrc + (long long)b * p.q_stride + chunk * E + h * 4);
         qs[idx] = v;
     }
     __syncthreads();
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         const long long row = row0 + r;
         const bool rep = (lane & ((1 << SH) - 1)) == 0;
         const float thr = *(volatile float *)(L.tau + b);
-        const bool pass = rep && row < p.n_rows && b < p.nq && sc >= thr;
+        const bool pass = rep && row < p.n_rows && b < nq && sc >= thr;
         unsigned m = __ballot_sync(kFullMask, pass);
         while (m) {
             const int src = __ffs(m) - 1;
@@ -210,9 +214,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 
     __syncthreads();
     // publish this CTA's lists: cand[cta][b][k]
-    float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride;
-    uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride;
-    for (int idx = tid; idx < p.nq * p.k; idx += kScanThreads) {
+    float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride + (long long)q0 * p.k;
+    uint32_t *ci = p.cand_i + (long long)blockIdx.x * p.cand_stride + (long long)q0 * p.k;
+    for (int idx = tid; idx < nq * p.k; idx += kScanThreads) {
         const int b = idx / p.k, e = idx % p.k;
         cs[idx] = L.s[b * L.kcap + e];
         ci[idx] = L.i[b * L.kcap + e];

@@ -26,7 +26,8 @@ cudaError_t launch_scan_one(const ScanLaunch &a, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<a.grid, kScanThreads, smem, st>>>(p);
+    const int passes = (a.nq + BT - 1) / BT;
+    kern<<<dim3((unsigned)a.grid, (unsigned)passes), kScanThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
