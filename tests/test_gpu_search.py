@@ -166,7 +166,8 @@ def test_family_selection_and_launch_count():
     assert shard.plan(32, 10, "verify")[0] == 2
     assert shard.plan(32, 10, "fast")[1] == 2            # one scan launch + one reduce launch
     assert shard.plan(128, 10, "fast") == (4, 2)         # > 32 queries: TMEM-resident-query kernel, one pass
-    assert shard.plan(128, 100, "fast")[0] == 3          # k too large to over-fetch for re-scoring
+    assert shard.plan(128, 100, "fast")[0] == 4          # k > 32: same kernel with hi/lo rows and heap lists
+    assert shard.plan(8, 100, "fast")[0] == 4 and shard.plan(8, 32, "fast")[0] == 3
     wide = ops.FlatShard(torch.zeros((256, 1024), dtype=torch.float16, device=DEV))
     assert wide.plan(128, 10, "fast")[0] == 3            # dim 1024 does not fit tensor memory
     rows32 = torch.zeros((4096, 768), dtype=torch.float32, device=DEV)

@@ -181,7 +181,7 @@ bool ts_eligible(const vqa_index *h) { return tensor_eligible(h) && h->dim <= 76
 bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     // k <= 16: screen with storage-precision queries (128 per CTA), keep 32 candidates per query and
     // re-score them exactly in the reduce.  Larger k: hi + lo rows (64 queries per CTA).
-    const int split = env_int("VQA_TS_SPLIT", k <= 16 ? 0 : 1) != 0;
+    const int split = env_int("VQA_TS_SPLIT", k + spare_ranks() <= 32 ? 0 : 1) != 0;
     const int kscan = split ? k : k + spare_ranks();
     const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split);
     if (fixed >= (size_t)h->max_smem) return false;
@@ -246,7 +246,9 @@ int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
         // Beyond the 32 queries the shared-memory-resident kernel holds per CTA, the TMEM-resident-query
         // kernel serves 128 per CTA from one HBM pass (screen with storage-precision queries, exact
         // re-scoring of the k+6 best in the reduce); it needs dim <= 768 and k+6 <= 32.
-        if (nq > 32 && k + spare_ranks() <= 32 && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
+        // k > 32 goes there too (hi/lo rows, heap lists): the smem-resident kernel's lock-guarded sorted
+        // lists are ~4x slower at top-100.
+        if ((nq > 32 || k > 32) && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
         if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
         return VQA_OK;

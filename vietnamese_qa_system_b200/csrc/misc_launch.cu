@@ -64,8 +64,8 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
         return cudaLaunchKernelEx(&cfg, reduce_topk_warp_kernel<IdT>, p);
     }
     cfg.gridDim = dim3(n_queries);
-    cfg.blockDim = dim3(32);
-    cfg.dynamicSmemBytes = list_smem_bytes<IdT>(1, k_out);
+    cfg.blockDim = dim3(kReduceBigWarps * 32);
+    cfg.dynamicSmemBytes = list_smem_bytes<IdT>(kReduceBigWarps, k_out);
     return cudaLaunchKernelEx(&cfg, reduce_topk_kernel<IdT>, p);
 }
 

@@ -445,48 +445,80 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
     if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;  // a graph replay reuses the epoch
 }
 
-// k_out in (32, 128]: one warp per query (one CTA of 32 threads), sorted list in shared memory.
+// k_out in (32, 128]: one CTA of 8 warps per query.  Phase 1: warp w folds the candidate lists
+// l = w, w+8, ... (all of a list's entries loaded up front) into ITS OWN sorted shared-memory list
+// (uncontended lock).  Phase 2: warp 0 folds the other seven lists into its own and writes the result.
+// The input lists need not be sorted.
+constexpr int kReduceBigWarps = 8;
+
 template <typename IdT>
-__global__ void __launch_bounds__(32) reduce_topk_kernel(const ReduceParams<IdT> p) {
+__global__ void __launch_bounds__(kReduceBigWarps * 32) reduce_topk_kernel(const ReduceParams<IdT> p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = blockIdx.x;
-    ListView<IdT> L = list_carve<IdT>(smem, 1, p.k_out);
-    list_init(L, 1, lane, 32);
-    __syncwarp();
+    ListView<IdT> L = list_carve<IdT>(smem, kReduceBigWarps, p.k_out);
+    list_init(L, kReduceBigWarps, tid, kReduceBigWarps * 32);
+    __syncthreads();
     grid_dependency_wait();
-    const int kin_pad = ((p.k_in + 31) / 32) * 32;
-    // entry-major over chunks of 32 entries so that every list's best candidates come first
-    for (int e0 = 0; e0 < kin_pad; e0 += 32) {
-        for (int l = (p.list_mod > 1 ? q / p.queries_per_group : 0); l < p.n_lists; l += (p.list_mod > 1 ? p.list_mod : 1)) {
-            const float *ls = p.cand_s + (long long)l * p.list_stride + (long long)q * p.query_stride;
-            const IdT *li = p.cand_i + (long long)l * p.list_stride_i + (long long)q * p.query_stride;
-            const int e = e0 + lane;
-            float s = neg_inf();
-            IdT id = invalid_id<IdT>();
+    const int lmod = p.list_mod > 1 ? p.list_mod : 1;
+    const int lgrp = p.list_mod > 1 ? q / p.queries_per_group : 0;
+    const int n_eff = p.n_lists / lmod;
+    constexpr int CH = kMaxK / 32;  // chunks of 32 entries per list (k_in <= 128)
+    for (int j = warp; j < n_eff; j += kReduceBigWarps) {
+        const int l = lgrp + j * lmod;
+        const float *ls = p.cand_s + (long long)l * p.list_stride + (long long)q * p.query_stride;
+        const IdT *li = p.cand_i + (long long)l * p.list_stride_i + (long long)q * p.query_stride;
+        float sv[CH];
+        IdT iv[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int e = c * 32 + lane;
+            sv[c] = neg_inf();
+            iv[c] = invalid_id<IdT>();
             if (e < p.k_in) {
-                s = ls[e];
-                id = li[e];
+                sv[c] = ls[e];
+                iv[c] = li[e];
             }
-            bool valid = e < p.k_in && id != invalid_id<IdT>();
-            if constexpr (sizeof(IdT) == 8) valid = valid && id >= 0;
-            const float thr = *(volatile float *)L.tau;
-            unsigned m = __ballot_sync(kFullMask, valid && s >= thr);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (c * 32 >= p.k_in) break;  // warp-uniform
+            bool valid = iv[c] != invalid_id<IdT>();
+            if constexpr (sizeof(IdT) == 8) valid = valid && iv[c] >= 0;
+            const float thr = *(volatile float *)(L.tau + warp);
+            unsigned m = __ballot_sync(kFullMask, valid && sv[c] >= thr);
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
-                list_insert<IdT>(L, 0, __shfl_sync(kFullMask, s, src), shfl_any(id, src));
+                list_insert<IdT>(L, warp, __shfl_sync(kFullMask, sv[c], src), shfl_any(iv[c], src));
             }
         }
     }
-    __syncwarp();
-    for (int e = lane; e < p.k_out; e += 32) {
-        const IdT id = L.i[e];
-        const bool ok = id != invalid_id<IdT>();
-        p.out_s[(long long)q * p.k_out + e] = ok ? L.s[e] : neg_inf();
-        p.out_i[(long long)q * p.k_out + e] = ok ? (long long)id + p.id_base : -1LL;
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < kReduceBigWarps; ++w) {
+            for (int e0 = 0; e0 < L.kcap; e0 += 32) {  // list w is sorted: stop at the first chunk with no taker
+                const float s = L.s[w * L.kcap + e0 + lane];
+                const IdT id = L.i[w * L.kcap + e0 + lane];
+                const float thr = *(volatile float *)L.tau;
+                unsigned m = __ballot_sync(kFullMask, id != invalid_id<IdT>() && s >= thr);
+                if (m == 0) break;
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    list_insert<IdT>(L, 0, __shfl_sync(kFullMask, s, src), shfl_any(id, src));
+                }
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < p.k_out; e += 32) {
+            const IdT id = L.i[e];
+            const bool ok = id != invalid_id<IdT>();
+            p.out_s[(long long)q * p.k_out + e] = ok ? L.s[e] : neg_inf();
+            p.out_i[(long long)q * p.k_out + e] = ok ? (long long)id + p.id_base : -1LL;
+        }
+        if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;
     }
-    if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;
 }
 
 }  // namespace vqa

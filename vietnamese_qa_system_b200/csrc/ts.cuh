@@ -62,9 +62,12 @@ inline int ts_reg_list_len(int k) { return k <= 16 ? 16 : (k <= 32 ? 32 : 0); }
 
 // [align slack][ring: boxes x 8 KB][barriers 1 KB][exchange 2 x 16 KB if split]
 // [lists: rows x k x 8 B, or the 32-deep candidate buffers (rows x 32 x 8 B) of the register-list variants]
+// shared-memory lists (k > 32) are kept for the live rows only: 64 with hi/lo rows, else 128; every
+// variant also has 32-deep candidate buffers for those rows
 inline size_t ts_smem_bytes_rt(int k, int boxes, int split) {
-    const int depth = ts_reg_list_len(k) > 0 ? 32 : k;
-    return 1024 + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) + (size_t)kTsRows * depth * 8;
+    const int depth = ts_reg_list_len(k) > 0 ? 32 : k + 32;
+    const int rows = (ts_reg_list_len(k) == 0 && split) ? 64 : kTsRows;
+    return 1024 + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) + (size_t)rows * depth * 8;
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -112,9 +115,11 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kMaxAccStages);
     float *xchg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 1024);  // [2][64 docs][64 rows]
     unsigned char *lists = reinterpret_cast<unsigned char *>(xchg) + (p.split ? 2 * 64 * kTsDocs * 4 : 0);
-    // per-thread sorted lists, entry-major so that a warp's accesses are conflict free
-    float *lst_s = reinterpret_cast<float *>(lists);                       // [k][128]
-    uint32_t *lst_i = reinterpret_cast<uint32_t *>(lst_s + (size_t)p.k * kTsRows);
+    // per-thread sorted lists (KL == 0) and candidate buffers, entry-major so that a warp's accesses are
+    // conflict free; LR = rows that own a list (64 when the upper 64 rows are the queries' lo parts)
+    const int LR = (KL == 0 && p.split) ? 64 : kTsRows;
+    float *lst_s = reinterpret_cast<float *>(lists);                       // [k][LR]        (KL == 0)
+    uint32_t *lst_i = reinterpret_cast<uint32_t *>(lst_s + (size_t)p.k * LR);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -257,24 +262,27 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         // KL > 0: the sorted list lives in REGISTERS (rs/ri); candidates that beat the threshold are
         // first appended to a private shared-memory buffer (two predicated stores, no divergence) and the
         // whole warp folds its buffers into the lists in lockstep when any lane's buffer is half full.
-        // KL == 0: sorted list in shared memory, inserted immediately (any k up to 128).
+        // KL == 0 (k > 32): same buffers; the list is a worst-at-root binary heap in shared memory.
         constexpr int KLR = KL > 0 ? KL : 1;
         constexpr int CAP = 32;
         float rs[KLR];
         uint32_t ri[KLR];
         int cnt = 0;
-        float *buf_s = lst_s;                       // [CAP][128] when KL > 0
-        uint32_t *buf_i = reinterpret_cast<uint32_t *>(lst_s + CAP * kTsRows);
+        float worst_s = neg_inf();                  // KL == 0: the heap's root = the worst kept entry
+        uint32_t worst_i = invalid_id<uint32_t>();
+        const int lrow = row & (LR - 1);            // this thread's list / buffer column
+        float *buf_s = KL > 0 ? lst_s : reinterpret_cast<float *>(lst_i + (size_t)p.k * LR);   // [CAP][LR]
+        uint32_t *buf_i = reinterpret_cast<uint32_t *>(buf_s + CAP * LR);
         if constexpr (KL > 0) {
 #pragma unroll
             for (int e = 0; e < KLR; ++e) {
                 rs[e] = neg_inf();
                 ri[e] = invalid_id<uint32_t>();
             }
-        } else {
+        } else if (!is_lo) {
             for (int e = 0; e < p.k; ++e) {
-                lst_s[e * kTsRows + row] = neg_inf();
-                lst_i[e * kTsRows + row] = invalid_id<uint32_t>();
+                lst_s[e * LR + lrow] = neg_inf();
+                lst_i[e * LR + lrow] = invalid_id<uint32_t>();
             }
         }
         auto flush = [&]() {
@@ -284,8 +292,8 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                     float cs = neg_inf();
                     uint32_t ci = invalid_id<uint32_t>();
                     if (b < cnt) {
-                        cs = buf_s[b * kTsRows + row];
-                        ci = buf_i[b * kTsRows + row];
+                        cs = buf_s[b * LR + lrow];
+                        ci = buf_i[b * LR + lrow];
                     }
                     bool bef[KLR];
 #pragma unroll
@@ -311,6 +319,52 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                     tau = ts;
                     if (tg != nullptr) atomicMax(tg, tau_encode(ts, p.epoch));
                 }
+            } else {
+                // The list is a binary HEAP in shared memory with the WORST kept entry at the root (parent
+                // ranks after both children): a candidate that ranks before the root replaces it and sifts
+                // down -- O(log k) dependent steps, usually one or two because a candidate that barely beats
+                // the worst entry rarely beats that entry's children.  (Sorted insertion costs a ~k/2-entry
+                // shift; the reduce kernel re-ranks the published candidates anyway.)
+                const int wmax = __reduce_max_sync(kFullMask, cnt);
+                const int k = p.k;
+                for (int b = 0; b < wmax; ++b) {
+                    if (b < cnt) {
+                        const float cs = buf_s[b * LR + lrow];
+                        const uint32_t ci = buf_i[b * LR + lrow];
+                        if (ranks_before<uint32_t>(cs, ci, worst_s, worst_i)) {
+                            int i = 0;
+                            while (true) {
+                                int c = 2 * i + 1;
+                                if (c >= k) break;
+                                float s1 = lst_s[c * LR + lrow];
+                                uint32_t i1 = lst_i[c * LR + lrow];
+                                if (c + 1 < k) {
+                                    const float s2 = lst_s[(c + 1) * LR + lrow];
+                                    const uint32_t i2 = lst_i[(c + 1) * LR + lrow];
+                                    if (ranks_before<uint32_t>(s1, i1, s2, i2)) {  // child c+1 is the worse one
+                                        c = c + 1;
+                                        s1 = s2;
+                                        i1 = i2;
+                                    }
+                                }
+                                if (!ranks_before<uint32_t>(cs, ci, s1, i1)) break;  // candidate is no better: it stays here
+                                lst_s[i * LR + lrow] = s1;                            // the worse child moves up
+                                lst_i[i * LR + lrow] = i1;
+                                i = c;
+                            }
+                            lst_s[i * LR + lrow] = cs;
+                            lst_i[i * LR + lrow] = ci;
+                            worst_s = lst_s[lrow];
+                            worst_i = lst_i[lrow];
+                        }
+                    }
+                }
+                // threshold = score of the worst kept entry once all k slots are filled
+                if (cnt > 0 && worst_i != invalid_id<uint32_t>() && worst_s > tau) {
+                    tau = worst_s;
+                    if (tg != nullptr) atomicMax(tg, tau_encode(worst_s, p.epoch));
+                }
+                cnt = 0;
             }
         };
 
@@ -351,55 +405,23 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 float m = v[0];
 #pragma unroll
                 for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
-                if constexpr (KL > 0) {
-                    if (__ballot_sync(kFullMask, m >= tau) != 0) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (v[j] >= tau && c0 + j < ndoc) {
-                                buf_s[cnt * kTsRows + row] = v[j];
-                                buf_i[cnt * kTsRows + row] = (uint32_t)(doc0 + c0 + j);
-                                ++cnt;
-                            }
-                        }
-                        if (__ballot_sync(kFullMask, cnt > CAP - 16) != 0) flush();
-                    }
-                } else if (m >= tau) {
+                if (__ballot_sync(kFullMask, m >= tau) != 0) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (v[j] >= tau && c0 + j < ndoc) {
-                            const uint32_t id = (uint32_t)(doc0 + c0 + j);
-                            int pos = p.k - 1;
-                            // candidate must rank before the current last entry to enter
-                            const float last_s = lst_s[pos * kTsRows + row];
-                            const uint32_t last_i = lst_i[pos * kTsRows + row];
-                            if (ranks_before<uint32_t>(v[j], id, last_s, last_i)) {
-                                while (pos > 0) {
-                                    const float ps = lst_s[(pos - 1) * kTsRows + row];
-                                    const uint32_t pi = lst_i[(pos - 1) * kTsRows + row];
-                                    if (!ranks_before<uint32_t>(v[j], id, ps, pi)) break;
-                                    lst_s[pos * kTsRows + row] = ps;
-                                    lst_i[pos * kTsRows + row] = pi;
-                                    --pos;
-                                }
-                                lst_s[pos * kTsRows + row] = v[j];
-                                lst_i[pos * kTsRows + row] = id;
-                                if (lst_i[(p.k - 1) * kTsRows + row] != invalid_id<uint32_t>()) {
-                                    const float nt = lst_s[(p.k - 1) * kTsRows + row];
-                                    if (nt > tau) {
-                                        tau = nt;
-                                        if (tg != nullptr) atomicMax(tg, tau_encode(nt, p.epoch));
-                                    }
-                                }
-                            }
+                            buf_s[cnt * LR + lrow] = v[j];
+                            buf_i[cnt * LR + lrow] = (uint32_t)(doc0 + c0 + j);
+                            ++cnt;
                         }
                     }
+                    if (__ballot_sync(kFullMask, cnt > CAP - 16) != 0) flush();
                 }
             }
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty + as);
         }
-        if constexpr (KL > 0) flush();
+        flush();
         // 3. publish this row's list
         if (live && !is_lo) {
             float *cs = p.cand_s + (long long)blockIdx.x * p.cand_stride + (long long)(q0 + qrow) * p.k;
@@ -413,8 +435,8 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                     }
             } else {
                 for (int e = 0; e < p.k; ++e) {
-                    cs[e] = lst_s[e * kTsRows + row];
-                    ci[e] = lst_i[e * kTsRows + row];
+                    cs[e] = lst_s[e * LR + lrow];
+                    ci[e] = lst_i[e * LR + lrow];
                 }
             }
         }
