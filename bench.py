@@ -51,6 +51,13 @@ def cpu_sample_qps(batch: int, k: int, budget_s: float, sample_rows: int, seed: 
     the 10M x 768 workload; throughput is scaled by sample_rows / N_ROWS (the scan is linear in rows)."""
     import oracle
 
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host threads
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:  # noqa: BLE001
+        pass
     rng = np.random.default_rng(seed)
     docs = rng.standard_normal((sample_rows, DIM), dtype=np.float32)
     docs /= np.linalg.norm(docs, axis=1, keepdims=True)
