@@ -23,7 +23,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host threads,
+    # and OpenBLAS sizes its pool when numpy is first imported
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
