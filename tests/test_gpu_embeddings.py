@@ -1,6 +1,5 @@
 """The reference-facing surface: Embeddings (txtai call shapes used at heavy_ranker.py:78-101),
 the ANN plugin B200Flat, and the batched heavy_ranker flow -- results against the oracle."""
-import os
 import zlib
 
 import numpy as np

@@ -27,7 +27,7 @@ from __future__ import annotations
 import json
 import os
 import sqlite3
-from typing import Any, Iterable, List, Optional, Sequence, Tuple, Union
+from typing import Any, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -152,7 +152,7 @@ class Embeddings:
         """Build the index.  ``documents``: iterable of dict{id,text,...} (the reference's form),
         (id, data, tags) tuples, strings, or vectors.  ``embeddings`` (optional, [N,D]) supplies
         pre-computed vectors for text documents (config A-D path)."""
-        self.ids, rows, texts = [], [], []
+        self.ids, rows = [], []
         for n, doc in enumerate(documents):
             uid, data, _ = self._unpack(doc, n)
             self.ids.append(uid)
