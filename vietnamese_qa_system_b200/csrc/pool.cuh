@@ -159,11 +159,24 @@ pool_normalize_warp_kernel(const unsigned char *__restrict__ hidden, const void 
 #pragma unroll
         for (int e = 0; e < E; ++e) acc[i][e] = 0.f;
     float cnt = 0.f;
-    for (int s0 = warp * kPoolUnroll; s0 < seq; s0 += kPoolWarps * kPoolUnroll) {
+    // Tokens after the last unmasked one (right padding, the usual layout) are not visited at all:
+    // s_end = 1 + last index with a non-zero mask weight.
+    int last = -1;
+    for (int s = tid; s < seq; s += kPoolFastThreads)
+        if (mask_at(mask, mdt, mbase + s) != 0.f) last = s;
+    last = __reduce_max_sync(kFullMask, last);
+    int *lastw = reinterpret_cast<int *>(cntw);  // (cntw is written only after the token loop)
+    if (lane == 0) lastw[warp] = last;
+    __syncthreads();
+    int s_end = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kPoolWarps; ++w2) s_end = max(s_end, lastw[w2] + 1);
+    __syncthreads();
+    for (int s0 = warp * kPoolUnroll; s0 < s_end; s0 += kPoolWarps * kPoolUnroll) {
         float m[kPoolUnroll];
         uint4 w[kPoolUnroll][ITERS];
 #pragma unroll
-        for (int u = 0; u < kPoolUnroll; ++u) m[u] = s0 + u < seq ? mask_at(mask, mdt, mbase + s0 + u) : 0.f;
+        for (int u = 0; u < kPoolUnroll; ++u) m[u] = s0 + u < s_end ? mask_at(mask, mdt, mbase + s0 + u) : 0.f;
 #pragma unroll
         for (int u = 0; u < kPoolUnroll; ++u) {
 #pragma unroll
