@@ -43,7 +43,7 @@ extern "C" {
 #define VQA_API __attribute__((visibility("default")))
 #endif
 
-#define VQA_VERSION 100 /* 0.1.0 */
+#define VQA_VERSION 110 /* 0.1.1: + sparse leg, hybrid fusion */
 
 typedef enum vqa_status {
     VQA_OK = 0,
@@ -224,6 +224,87 @@ VQA_API int vqa_agree(const int64_t *ids_a_dev, const float *scores_a_dev,
  * (VQA_MODE_FAST_STREAM or VQA_MODE_FAST_TENSOR), how many kernels one search launches. */
 VQA_API int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode,
                             int32_t *family, int32_t *n_launches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse (BM25) leg and hybrid fusion -- SURVEY.md 8(f) rank 3.
+ * The reference builds its indexes with txtai.Embeddings(hybrid=True, ...)
+ * (inference_pipeline/db_utils/heavy_ranker.py:78-83): next to the dense index txtai keeps a BM25
+ * term index (scoring = {"method": "bm25", "terms": True, "normalize": True}), asks each leg for
+ * 10 x limit candidates at :98,100 and adds the scores per id with weights [0.5, 0.5].
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct vqa_sparse vqa_sparse_t; /* opaque */
+
+/* Compile-time limits: distinct known terms per query, candidates kept per query. */
+VQA_API int vqa_sparse_limits(int32_t *max_query_terms, int32_t *max_candidates);
+
+/*
+ * Term-index descriptor over document positions [0, n_docs): CSR postings
+ *   offsets int64[n_terms + 1], docs int32[n_postings] (ascending within a term),
+ *   weights float32[n_postings] (BM25 weight of the (term, document) pair).
+ * Replaces: txtai scoring.Terms (the sqlite-backed term index built under Embeddings.index(),
+ *           heavy_ranker.py:86,88).  The buffers are BORROWED.
+ */
+VQA_API int vqa_sparse_create(vqa_sparse_t **out, int64_t n_docs, int64_t n_terms, int64_t n_postings,
+                              int32_t device);
+VQA_API int vqa_sparse_bind(vqa_sparse_t *h, const int64_t *offsets_dev, const int32_t *docs_dev,
+                            const float *weights_dev);
+VQA_API int vqa_sparse_destroy(vqa_sparse_t *h);
+
+/*
+ * Build side: BM25 weight of every posting, evaluated in float64 in txtai's operation order
+ *   k = k1 * ((1 - b) + b * doc_len / avgdl);  w = idf * (freq * (k1 + 1)) / (freq + k)
+ * and rounded once to float32.  Replaces: txtai BM25.score under Terms.weights.
+ *   idf_dev float64[n_terms], doc_len_dev int32[n_docs], freqs_dev int32[n_postings].
+ */
+VQA_API int vqa_bm25_weights(const int64_t *offsets_dev, int64_t n_terms, const int32_t *docs_dev,
+                             const int32_t *freqs_dev, int64_t n_postings, const double *idf_dev,
+                             const int32_t *doc_len_dev, double k1, double b, double avgdl,
+                             float *weights_out_dev, int32_t device, void *stream);
+
+VQA_API int vqa_sparse_workspace_bytes(const vqa_sparse_t *h, int32_t n_queries, int32_t k_cand_max,
+                                       size_t *bytes);
+
+/*
+ * Score n_queries tokenised queries against the term index and select the best `limit` documents.
+ * Replaces: txtai Terms.search + TFIDF.search (score normalisation) under Embeddings.search()
+ *           (heavy_ranker.py:98,100).
+ *   q_terms_dev  int32 [n_queries, max_terms]  term ids; per query first the n_rare terms that are
+ *                accumulated over all their documents (in the query's first-occurrence order), then
+ *                the n_common terms (document frequency > cutoff * n_docs) that are merged only
+ *                into the surviving candidates.  Ids outside [0, n_terms) count as unknown terms.
+ *   q_freqs_dev  float32 [n_queries, max_terms] occurrences of the term in the query
+ *   q_meta_dev   int32 [n_queries, 4]           n_rare, n_common, k_cand (candidates kept before
+ *                the common-term merge: limit, or 5 x limit when n_common > 0), unused
+ *   out_scores_dev float64 [n_queries, limit]   descending; normalize != 0 applies
+ *                min(score / min(top + avgscore, 6 * avgscore), 1); documents with score 0 are
+ *                never returned: unused slots hold score -inf, id -1
+ *   out_ids_dev  int64 [n_queries, limit]       document positions
+ * Accumulation is fp32 multiply-then-add in term order (no fused multiply-add), so scores are
+ * bit-identical to the CPU accumulation they replace.  No allocation, no host synchronisation.
+ */
+VQA_API int vqa_sparse_search(const vqa_sparse_t *h, const int32_t *q_terms_dev, const float *q_freqs_dev,
+                              const int32_t *q_meta_dev, int32_t max_terms, int32_t n_queries,
+                              int32_t k_cand_max, int32_t limit, int32_t normalize, double avgscore,
+                              double *out_scores_dev, int64_t *out_ids_dev, void *workspace_dev,
+                              size_t workspace_bytes, void *stream);
+
+/*
+ * Hybrid fusion of the two legs' candidate lists (ids < 0 are padding):
+ *   fused[id] = 0.0 + dense * w_dense (+ sparse * w_sparse), float64 like the Python floats it replaces;
+ *   order = fused descending, ties keep insertion order (dense candidates first, then sparse-only).
+ * Replaces: txtai Search.search's union/sort under Embeddings.search() with hybrid=True.
+ *   out_scores_dev float64 [n_queries, limit], out_ids_dev int64 [n_queries, limit]; unused slots -inf / -1.
+ */
+VQA_API int vqa_hybrid_fuse(const float *dense_scores_dev, const int64_t *dense_ids_dev, int32_t k_dense,
+                            const double *sparse_scores_dev, const int64_t *sparse_ids_dev, int32_t k_sparse,
+                            int32_t n_queries, double w_dense, double w_sparse, int32_t limit,
+                            double *out_scores_dev, int64_t *out_ids_dev, int32_t device, void *stream);
+
+/* The agreement rule (heavy_ranker.py:110) on float64 scores -- what hybrid indexes return. */
+VQA_API int vqa_agree_f64(const int64_t *ids_a_dev, const double *scores_a_dev, const int64_t *ids_b_dev,
+                          const double *scores_b_dev, int64_t n, double threshold, uint8_t *accept_dev,
+                          double *combined_dev, int32_t device, void *stream);
 
 #ifdef __cplusplus
 }

@@ -91,8 +91,12 @@ def test_straighten_docs_matches_reference_format():
 def test_embeddings_config_surface_without_gpu():
     e = Embeddings(hybrid=True, content=True, path="sentence-transformers/paraphrase-multilingual-mpnet-base-v2")
     assert e.config["hybrid"] is True and e.content is True and e.count() == 0
-    with pytest.raises(NotImplementedError):       # hybrid is refused, never silently dense-only
+    # hybrid=True configures the BM25 term index exactly as txtai does
+    assert e.config["scoring"] == {"method": "bm25", "normalize": True, "terms": True}
+    with pytest.raises(RuntimeError):              # empty index
         e.search("xin chào", 1)
+    with pytest.raises(NotImplementedError):
+        Embeddings(scoring="tfidf")
     e2 = Embeddings({"content": False}, dtype="fp32")
     assert e2.config["dtype"] == "fp32"
     with pytest.raises(RuntimeError):

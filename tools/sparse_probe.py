@@ -1,0 +1,79 @@
+"""GPU probe of the sparse (BM25) leg at scale: synthetic Zipf postings built directly as CSR, timed with
+CUDA events.  Writes gpurun_out/sparse_probe.json.  Usage: python tools/sparse_probe.py [n_docs] [avg_len]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vietnamese_qa_system_b200.scoring import BM25  # noqa: E402
+
+
+def synth(n_docs, avg_len, vocab, seed=1):
+    rng = np.random.default_rng(seed)
+    p = np.arange(1, vocab + 1, dtype=np.float64) ** -1.1
+    p /= p.sum()
+    n_tok = n_docs * avg_len
+    terms = rng.choice(vocab, size=n_tok, p=p).astype(np.int64)
+    docs = np.repeat(np.arange(n_docs, dtype=np.int64), avg_len)
+    key, freq = np.unique(terms * n_docs + docs, return_counts=True)   # sorted by (term, doc)
+    t, d = key // n_docs, key % n_docs
+    used, df = np.unique(t, return_counts=True)
+    offsets = np.zeros(len(used) + 1, np.int64)
+    np.cumsum(df, out=offsets[1:])
+    lengths = np.full(n_docs, avg_len, np.int32)
+    return offsets, d.astype(np.int32), freq.astype(np.int32), lengths, [f"w{int(u)}" for u in used]
+
+
+def main():
+    n_docs = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+    avg_len = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    t0 = time.time()
+    offsets, docs, freqs, lengths, vocab = synth(n_docs, avg_len, 200_000)
+    bm = BM25({"method": "bm25", "terms": True, "normalize": True})
+    bm.index_postings(offsets, docs, freqs, lengths, vocab)
+    build_s = time.time() - t0
+    df = np.diff(offsets)
+    rng = np.random.default_rng(2)
+    rare_ids = np.flatnonzero((df > 50) & (df <= 0.1 * n_docs))
+    common_ids = np.flatnonzero(df > 0.1 * n_docs)
+    out = {"n_docs": n_docs, "postings": int(len(docs)), "terms": len(vocab), "build_s": round(build_s, 2),
+           "common_terms": int(len(common_ids)), "rows": []}
+    for batch in (1, 32, 256):
+        for kind in ("rare", "mixed"):
+            qs = []
+            for _ in range(batch):
+                q = [vocab[int(i)] for i in rng.choice(rare_ids, 4, replace=False)]
+                if kind == "mixed" and len(common_ids):
+                    q.append(vocab[int(rng.choice(common_ids))])
+                qs.append(q)
+            q_terms, _, q_meta, _ = bm.plan_queries(qs, 10)
+            bytes_ = 0
+            for r in range(batch):
+                for j in range(int(q_meta[r, 0])):                       # accumulate-everywhere terms
+                    bytes_ += int(df[q_terms[r, j]]) * 8
+            for _ in range(3):
+                bm.search_tensors(qs, 10)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            ev0.record()
+            for _ in range(reps):
+                bm.search_tensors(qs, 10)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / reps
+            out["rows"].append({"batch": batch, "kind": kind, "ms_per_batch_incl_host_planning": round(ms, 4),
+                                "qps": round(batch / ms * 1e3, 1), "posting_bytes": bytes_,
+                                "posting_gbs": round(bytes_ / ms / 1e6, 2)})
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/sparse_probe.json", "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,8 @@ EXPORTS = [
     "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_exchange_push", "vqa_merge_topk_wait",
     "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
     "vqa_search_plan",
+    "vqa_sparse_limits", "vqa_sparse_create", "vqa_sparse_bind", "vqa_sparse_destroy", "vqa_bm25_weights",
+    "vqa_sparse_workspace_bytes", "vqa_sparse_search", "vqa_hybrid_fuse", "vqa_agree_f64",
 ]
 
 _lib = None
@@ -78,6 +80,24 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_agree.argtypes = [vp, vp, vp, vp, i64, c.c_double, vp, vp, i32, vp]
     L.vqa_search_plan.restype = c.c_int
     L.vqa_search_plan.argtypes = [vp, i32, i32, i32, c.POINTER(i32), c.POINTER(i32)]
+    L.vqa_sparse_limits.restype = c.c_int
+    L.vqa_sparse_limits.argtypes = [c.POINTER(i32), c.POINTER(i32)]
+    L.vqa_sparse_create.restype = c.c_int
+    L.vqa_sparse_create.argtypes = [c.POINTER(vp), i64, i64, i64, i32]
+    L.vqa_sparse_bind.restype = c.c_int
+    L.vqa_sparse_bind.argtypes = [vp, vp, vp, vp]
+    L.vqa_sparse_destroy.restype = c.c_int
+    L.vqa_sparse_destroy.argtypes = [vp]
+    L.vqa_bm25_weights.restype = c.c_int
+    L.vqa_bm25_weights.argtypes = [vp, i64, vp, vp, i64, vp, vp, c.c_double, c.c_double, c.c_double, vp, i32, vp]
+    L.vqa_sparse_workspace_bytes.restype = c.c_int
+    L.vqa_sparse_workspace_bytes.argtypes = [vp, i32, i32, c.POINTER(sz)]
+    L.vqa_sparse_search.restype = c.c_int
+    L.vqa_sparse_search.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, c.c_double, vp, vp, vp, sz, vp]
+    L.vqa_agree_f64.restype = c.c_int
+    L.vqa_agree_f64.argtypes = [vp, vp, vp, vp, i64, c.c_double, vp, vp, i32, vp]
+    L.vqa_hybrid_fuse.restype = c.c_int
+    L.vqa_hybrid_fuse.argtypes = [vp, vp, i32, vp, vp, i32, i32, c.c_double, c.c_double, i32, vp, vp, i32, vp]
 
 
 def lib() -> ctypes.CDLL:

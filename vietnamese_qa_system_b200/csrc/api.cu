@@ -101,6 +101,18 @@ struct vqa_index {
     mutable int max_clusters[4][5] = {};  // cached cudaOccupancyMaxActiveClusters by [log2 cluster][ncol slot]
 };
 
+// sparse (BM25) term index: CSR postings borrowed from the caller
+struct vqa_sparse {
+    int64_t n_docs = 0;
+    int64_t n_terms = 0;
+    int64_t n_postings = 0;
+    int device = 0;
+    int sm_count = 0;
+    const long long *offsets = nullptr;
+    const int *docs = nullptr;
+    const float *weights = nullptr;
+};
+
 namespace {
 
 // ---- planning -----------------------------------------------------------------
@@ -770,6 +782,178 @@ int vqa_agree(const int64_t *ids_a_dev, const float *scores_a_dev, const int64_t
     cudaError_t e = vqa::launch_agree((const long long *)ids_a_dev, scores_a_dev, (const long long *)ids_b_dev,
                                       scores_b_dev, n, threshold, accept_dev, combined_dev,
                                       reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "agree launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+// ---- sparse (BM25) leg + hybrid fusion ----------------------------------------------------------
+
+int vqa_sparse_limits(int32_t *max_query_terms, int32_t *max_candidates) {
+    if (max_query_terms) *max_query_terms = vqa::sparse_max_terms();
+    if (max_candidates) *max_candidates = vqa::sparse_max_cand();
+    return VQA_OK;
+}
+
+int vqa_sparse_create(vqa_sparse_t **out, int64_t n_docs, int64_t n_terms, int64_t n_postings, int32_t device) {
+    if (!out) return fail(VQA_E_INVALID, "out is null");
+    *out = nullptr;
+    if (n_docs < 0 || n_docs > 0x7fffffffLL)
+        return fail(VQA_E_INVALID, "n_docs must be in [0, 2^31) (got %lld)", (long long)n_docs);
+    if (n_terms < 0 || n_terms > 0x7fffffffLL)
+        return fail(VQA_E_INVALID, "n_terms must be in [0, 2^31) (got %lld)", (long long)n_terms);
+    if (n_postings < 0) return fail(VQA_E_INVALID, "n_postings must be >= 0");
+    int ndev = vqa_device_count();
+    if (ndev == 0) return fail(VQA_E_CUDA, "no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(VQA_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(VQA_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    vqa_sparse *h = new (std::nothrow) vqa_sparse();
+    if (!h) return fail(VQA_E_NOMEM, "host allocation failed");
+    h->n_docs = n_docs;
+    h->n_terms = n_terms;
+    h->n_postings = n_postings;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return VQA_OK;
+}
+
+int vqa_sparse_bind(vqa_sparse_t *h, const int64_t *offsets_dev, const int32_t *docs_dev, const float *weights_dev) {
+    if (!h) return fail(VQA_E_INVALID, "null sparse handle");
+    if (!offsets_dev) return fail(VQA_E_INVALID, "offsets_dev is null");
+    if (h->n_postings > 0 && (!docs_dev || !weights_dev)) return fail(VQA_E_INVALID, "null postings pointer");
+    h->offsets = reinterpret_cast<const long long *>(offsets_dev);
+    h->docs = docs_dev;
+    h->weights = weights_dev;
+    return VQA_OK;
+}
+
+int vqa_sparse_destroy(vqa_sparse_t *h) {
+    delete h;
+    return VQA_OK;
+}
+
+int vqa_bm25_weights(const int64_t *offsets_dev, int64_t n_terms, const int32_t *docs_dev, const int32_t *freqs_dev,
+                     int64_t n_postings, const double *idf_dev, const int32_t *doc_len_dev, double k1, double b,
+                     double avgdl, float *weights_out_dev, int32_t device, void *stream) {
+    if (n_terms < 0 || n_postings < 0) return fail(VQA_E_INVALID, "n_terms and n_postings must be >= 0");
+    if (n_postings > 0 && (!offsets_dev || !docs_dev || !freqs_dev || !idf_dev || !doc_len_dev || !weights_out_dev))
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (n_postings > 0 && n_terms < 1) return fail(VQA_E_INVALID, "postings without terms");
+    if (!(avgdl > 0.0) && n_postings > 0) return fail(VQA_E_INVALID, "avgdl must be > 0");
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    if (n_postings == 0) return VQA_OK;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_bm25_weights(reinterpret_cast<const long long *>(offsets_dev), n_terms, docs_dev,
+                                             freqs_dev, n_postings, idf_dev, doc_len_dev, k1, b, avgdl,
+                                             weights_out_dev, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "bm25 weights launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+static int sparse_check_shape(const vqa_sparse_t *h, int32_t n_queries, int32_t max_terms, int32_t k_cand_max) {
+    if (!h) return fail(VQA_E_INVALID, "null sparse handle");
+    if (n_queries < 1 || n_queries > 65535) return fail(VQA_E_INVALID, "n_queries must be in [1, 65535]");
+    if (max_terms < 1 || max_terms > vqa::sparse_max_terms())
+        return fail(VQA_E_INVALID, "max_terms must be in [1, %d] (got %d)", vqa::sparse_max_terms(), max_terms);
+    if (k_cand_max < 1 || k_cand_max > vqa::sparse_max_cand())
+        return fail(VQA_E_INVALID, "k_cand_max must be in [1, %d] (got %d)", vqa::sparse_max_cand(), k_cand_max);
+    return VQA_OK;
+}
+
+int vqa_sparse_workspace_bytes(const vqa_sparse_t *h, int32_t n_queries, int32_t k_cand_max, size_t *bytes) {
+    if (!bytes) return fail(VQA_E_INVALID, "bytes is null");
+    int rc = sparse_check_shape(h, n_queries, 1, k_cand_max);
+    if (rc != VQA_OK) return rc;
+    int cpq = 1, tpc = 1;
+    vqa::sparse_plan(h->n_docs, n_queries, h->sm_count, &cpq, &tpc);
+    *bytes = (size_t)n_queries * cpq * k_cand_max * sizeof(unsigned long long);
+    return VQA_OK;
+}
+
+int vqa_sparse_search(const vqa_sparse_t *h, const int32_t *q_terms_dev, const float *q_freqs_dev,
+                      const int32_t *q_meta_dev, int32_t max_terms, int32_t n_queries, int32_t k_cand_max,
+                      int32_t limit, int32_t normalize, double avgscore, double *out_scores_dev,
+                      int64_t *out_ids_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+    int rc = sparse_check_shape(h, n_queries, max_terms, k_cand_max);
+    if (rc != VQA_OK) return rc;
+    if (!h->offsets) return fail(VQA_E_INVALID, "sparse index has no postings bound (call vqa_sparse_bind)");
+    if (!q_terms_dev || !q_freqs_dev || !q_meta_dev || !out_scores_dev || !out_ids_dev || !workspace_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (limit < 1 || limit > k_cand_max) return fail(VQA_E_INVALID, "limit must be in [1, k_cand_max]");
+    if (normalize && !(avgscore > 0.0)) return fail(VQA_E_INVALID, "normalize needs avgscore > 0");
+    size_t need = 0;
+    rc = vqa_sparse_workspace_bytes(h, n_queries, k_cand_max, &need);
+    if (rc != VQA_OK) return rc;
+    if (workspace_bytes < need)
+        return fail(VQA_E_NOMEM, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+    if (reinterpret_cast<uintptr_t>(workspace_dev) % 8 != 0) return fail(VQA_E_INVALID, "workspace must be 8-byte aligned");
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    vqa::SparseLaunch a;
+    a.offsets = h->offsets;
+    a.docs = h->docs;
+    a.weights = h->weights;
+    a.n_docs = h->n_docs;
+    a.n_terms = h->n_terms;
+    a.q_terms = q_terms_dev;
+    a.q_freqs = q_freqs_dev;
+    a.q_meta = q_meta_dev;
+    a.max_terms = max_terms;
+    a.n_queries = n_queries;
+    a.kcap = k_cand_max;
+    vqa::sparse_plan(h->n_docs, n_queries, h->sm_count, &a.ctas_per_query, &a.tiles_per_cta);
+    a.cand = static_cast<unsigned long long *>(workspace_dev);
+    a.limit = limit;
+    a.normalize = normalize ? 1 : 0;
+    a.avgscore = avgscore;
+    a.out_s = out_scores_dev;
+    a.out_i = reinterpret_cast<long long *>(out_ids_dev);
+    cudaError_t e = vqa::launch_sparse_search(a, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "sparse search launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_hybrid_fuse(const float *dense_scores_dev, const int64_t *dense_ids_dev, int32_t k_dense,
+                    const double *sparse_scores_dev, const int64_t *sparse_ids_dev, int32_t k_sparse,
+                    int32_t n_queries, double w_dense, double w_sparse, int32_t limit, double *out_scores_dev,
+                    int64_t *out_ids_dev, int32_t device, void *stream) {
+    if (!dense_scores_dev || !dense_ids_dev || !sparse_scores_dev || !sparse_ids_dev || !out_scores_dev || !out_ids_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (n_queries < 1) return fail(VQA_E_INVALID, "n_queries must be >= 1");
+    if (k_dense < 1 || k_sparse < 1 || k_dense + k_sparse > 2048)
+        return fail(VQA_E_INVALID, "k_dense, k_sparse must be >= 1 and sum to <= 2048");
+    if (limit < 1 || limit > k_dense + k_sparse) return fail(VQA_E_INVALID, "limit must be in [1, k_dense + k_sparse]");
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_hybrid_fuse(dense_scores_dev, reinterpret_cast<const long long *>(dense_ids_dev), k_dense,
+                                            sparse_scores_dev, reinterpret_cast<const long long *>(sparse_ids_dev),
+                                            k_sparse, n_queries, w_dense, w_sparse, limit, out_scores_dev,
+                                            reinterpret_cast<long long *>(out_ids_dev),
+                                            reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "hybrid fuse launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
+int vqa_agree_f64(const int64_t *ids_a_dev, const double *scores_a_dev, const int64_t *ids_b_dev,
+                  const double *scores_b_dev, int64_t n, double threshold, uint8_t *accept_dev, double *combined_dev,
+                  int32_t device, void *stream) {
+    if (!ids_a_dev || !scores_a_dev || !ids_b_dev || !scores_b_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (n < 0) return fail(VQA_E_INVALID, "n must be >= 0");
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    if (n == 0) return VQA_OK;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_agree_f64((const long long *)ids_a_dev, scores_a_dev, (const long long *)ids_b_dev,
+                                          scores_b_dev, n, threshold, accept_dev, combined_dev,
+                                          reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(VQA_E_CUDA, "agree launch failed: %s", cudaGetErrorString(e));
     return VQA_OK;
 }

@@ -117,4 +117,41 @@ cudaError_t launch_normalize(const float *in, long long in_stride, long long n_r
 cudaError_t launch_agree(const long long *ids_a, const float *sa, const long long *ids_b, const float *sb,
                          long long n, double threshold, unsigned char *accept, float *combined, cudaStream_t st);
 
+
+// ---- sparse (BM25) leg + hybrid fusion (sparse.cuh) ----
+struct SparseLaunch {
+    const long long *offsets;
+    const int *docs;
+    const float *weights;
+    long long n_docs;
+    long long n_terms;
+    const int *q_terms;
+    const float *q_freqs;
+    const int *q_meta;
+    int max_terms;
+    int n_queries;
+    int kcap;
+    int ctas_per_query;
+    int tiles_per_cta;
+    unsigned long long *cand;
+    int limit;
+    int normalize;
+    double avgscore;
+    double *out_s;
+    long long *out_i;
+};
+int sparse_max_terms();
+int sparse_max_cand();
+void sparse_plan(long long n_docs, int n_queries, int sm_count, int *ctas_per_query, int *tiles_per_cta);
+cudaError_t launch_sparse_search(const SparseLaunch &a, cudaStream_t st);
+cudaError_t launch_bm25_weights(const long long *offsets, long long n_terms, const int *docs, const int *freqs,
+                                long long n_postings, const double *idf, const int *doc_len, double k1, double b,
+                                double avgdl, float *weights, cudaStream_t st);
+cudaError_t launch_hybrid_fuse(const float *dense_s, const long long *dense_i, int kd, const double *sparse_s,
+                               const long long *sparse_i, int ks, int n_queries, double w_dense, double w_sparse,
+                               int limit, double *out_s, long long *out_i, cudaStream_t st);
+
+cudaError_t launch_agree_f64(const long long *ids_a, const double *sa, const long long *ids_b, const double *sb,
+                             long long n, double threshold, unsigned char *accept, double *combined, cudaStream_t st);
+
 }  // namespace vqa

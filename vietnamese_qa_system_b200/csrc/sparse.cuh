@@ -1,0 +1,402 @@
+// sparse.cuh -- the sparse (BM25) leg of hybrid search and the dense/sparse fusion.
+//
+// Reference: the saved indexes are built with txtai.Embeddings(hybrid=True, ...)
+// (inference_pipeline/db_utils/heavy_ranker.py:78-83); behind that flag txtai keeps a BM25 term
+// index next to the dense one, asks each for 10 x limit candidates and adds the scores per id
+// (SURVEY.md 8(f) rank 3, Appendix A).  txtai's Terms.search fills a dense fp32 score array of
+// N entries per query on the CPU and argpartitions it.
+//
+// Here the postings live in HBM as CSR (offsets int64[T+1], docs int32[P] ascending per term,
+// weights fp32[P] = the BM25 weight of that (term, document) pair) and the score array never
+// exists in memory: a CTA owns a run of 16 K-document tiles, finds each query term's posting
+// sub-range for the tile by binary search, accumulates the tile's scores in SHARED memory in the
+// query's term order (fp32 multiply then add, no contraction: bit-identical to the CPU
+// accumulation) and selects from the tile straight away.  HBM traffic = the query terms' postings,
+// read once, coalesced (8 bytes per posting).
+//
+// Selection: candidates are 64-bit keys (order-preserving score bits << 32 | ~position), so one
+// unsigned compare implements "score descending, ties -> lower position".  A CTA keeps its best
+// k_cand keys plus an append buffer in shared memory and bitonic-sorts the 2048 slots when the
+// buffer could overflow; after the first tiles the running threshold rejects almost everything.
+#pragma once
+
+#include "common.cuh"
+
+namespace vqa {
+
+constexpr int kSpThreads = 512;
+constexpr int kSpTile = 16384;                    // documents per shared-memory score tile (64 KB)
+constexpr int kSpSort = 2048;                     // key slots per CTA (16 KB)
+constexpr int kSpMaxCand = 1024;                  // most candidates a query may keep (k_cand)
+constexpr int kSpMaxTerms = 64;                   // distinct known terms per query
+constexpr int kSpTileGroup = 8;                   // tiles whose posting boundaries are searched together
+constexpr int kSpMetaStride = 4;                  // q_meta row: n_rare, n_common, k_cand, unused
+
+struct SparseParams {
+    const long long *offsets;
+    const int *docs;
+    const float *weights;
+    long long n_docs;
+    long long n_terms;
+    const int *q_terms;    // [B, max_terms]: the n_rare accumulate-everywhere terms in query order, then the n_common
+    const float *q_freqs;  // [B, max_terms]: occurrences of the term in the query
+    const int *q_meta;     // [B, kSpMetaStride]
+    int max_terms;
+    int kcap;              // key slots per (query, CTA) in `cand` (>= every k_cand)
+    int ctas_per_query;
+    int tiles_per_cta;
+    unsigned long long *cand;  // [B, ctas_per_query, kcap]
+    // finish stage
+    int limit;
+    int normalize;
+    double avgscore;
+    double *out_s;     // [B, limit]
+    long long *out_i;  // [B, limit]
+};
+
+__device__ __forceinline__ unsigned long long sp_make_key(float s, uint32_t doc) {
+    uint32_t u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(~doc);
+}
+__device__ __forceinline__ float sp_key_score(unsigned long long key) {
+    uint32_t u = (uint32_t)(key >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint32_t sp_key_doc(unsigned long long key) { return ~(uint32_t)key; }
+
+// first index in [lo, hi) whose document is >= v
+__device__ __forceinline__ long long sp_lower_bound(const int *docs, long long lo, long long hi, long long v) {
+    while (lo < hi) {
+        const long long mid = lo + ((hi - lo) >> 1);
+        if ((long long)__ldg(docs + mid) < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// posting range of a query term; ids outside the vocabulary (the caller's arrays are not validated on
+// the host -- they live in device memory) read as an empty list instead of out of bounds
+__device__ __forceinline__ void sp_term_range(const SparseParams &p, int term, long long &lo, long long &hi) {
+    lo = hi = 0;
+    if (term >= 0 && term < p.n_terms) {
+        lo = p.offsets[term];
+        hi = p.offsets[term + 1];
+    }
+}
+
+struct SpQuery {
+    int n_rare, n_common, k_cand;
+};
+__device__ __forceinline__ SpQuery sp_query(const SparseParams &p, int b) {
+    const int *meta = p.q_meta + (size_t)b * kSpMetaStride;
+    SpQuery q;
+    q.n_rare = max(0, min(meta[0], p.max_terms));
+    q.n_common = max(0, min(meta[1], p.max_terms - q.n_rare));
+    q.k_cand = max(1, min(meta[2], p.kcap));
+    return q;
+}
+
+// Bitonic sort of all kSpSort keys, descending (empty slots are 0 and sink to the end), then keep the
+// best k_cand.  `count` and `thr` are CTA-uniform registers.  Ends with a barrier.
+__device__ __forceinline__ void sp_flush(unsigned long long *keys, int &count, int k_cand, unsigned long long &thr,
+                                         int *s_count) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    for (int k = 2; k <= kSpSort; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < kSpSort; i += kSpThreads) {
+                const int x = i ^ j;
+                if (x > i) {
+                    const unsigned long long a = keys[i], b = keys[x];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) {
+                        keys[i] = b;
+                        keys[x] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (count > k_cand) {
+        for (int i = k_cand + tid; i < count; i += kSpThreads) keys[i] = 0ull;
+        count = k_cand;
+    }
+    thr = (count >= k_cand) ? keys[k_cand - 1] : 0ull;
+    if (tid == 0) *s_count = count;
+    __syncthreads();
+}
+
+// One CTA-wide offer round: each thread proposes at most one key.  Returns with a barrier; `count`
+// stays uniform because the barrier itself counts the appends.
+__device__ __forceinline__ void sp_offer(unsigned long long *keys, int &count, unsigned long long thr, int *s_count,
+                                         bool have, unsigned long long key) {
+    const bool pass = have && key > thr;
+    if (pass) keys[atomicAdd(s_count, 1)] = key;
+    count += __syncthreads_count(pass);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1: tile accumulate + select.  grid = (ctas_per_query, B), 512 threads, ~83 KB smem.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    float *acc = reinterpret_cast<float *>(sp_smem);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(sp_smem + (size_t)kSpTile * sizeof(float));
+    int *bound = reinterpret_cast<int *>(keys + kSpSort);  // [kSpMaxTerms][kSpTileGroup + 1], relative to the term's first posting
+    __shared__ int s_count;
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const SpQuery qm = sp_query(p, b);
+    const int n_rare = qm.n_rare, k_cand = qm.k_cand;
+    const int *terms = p.q_terms + (size_t)b * p.max_terms;
+    const float *freqs = p.q_freqs + (size_t)b * p.max_terms;
+
+    const long long n_tiles = (p.n_docs + kSpTile - 1) / kSpTile;
+    const long long first_tile = (long long)blockIdx.x * p.tiles_per_cta;
+    const long long last_tile = min(n_tiles, first_tile + p.tiles_per_cta);
+
+    for (int i = tid; i < kSpSort; i += kSpThreads) keys[i] = 0ull;
+    if (tid == 0) s_count = 0;
+    int count = 0;
+    unsigned long long thr = 0ull;
+    __syncthreads();
+
+    for (long long g0 = first_tile; g0 < last_tile; g0 += kSpTileGroup) {
+        const int ng = (int)min((long long)kSpTileGroup, last_tile - g0);
+        // posting boundaries of every term at the ng + 1 tile edges of this group
+        for (int w = tid; w < n_rare * (ng + 1); w += kSpThreads) {
+            const int j = w / (ng + 1), t = w - j * (ng + 1);
+            long long lo, hi;
+            sp_term_range(p, terms[j], lo, hi);
+            const long long edge = (g0 + t) * (long long)kSpTile;
+            bound[j * (kSpTileGroup + 1) + t] = (int)(sp_lower_bound(p.docs, lo, hi, edge) - lo);
+        }
+        __syncthreads();
+        for (int t = 0; t < ng; ++t) {
+            const long long base = (g0 + t) * (long long)kSpTile;
+            const int lim = (int)min((long long)kSpTile, p.n_docs - base);
+            bool any = false;
+            for (int j = 0; j < n_rare; ++j)
+                any |= bound[j * (kSpTileGroup + 1) + t + 1] > bound[j * (kSpTileGroup + 1) + t];
+            // a tile without postings holds only zero scores; once the list's threshold is at or above
+            // (0, first position of the tile) none of them can enter (uniform decision)
+            if (!any && sp_make_key(0.0f, (uint32_t)base) <= thr) continue;
+            for (int e = tid; e < lim; e += kSpThreads) acc[e] = 0.0f;
+            __syncthreads();
+            for (int j = 0; j < n_rare; ++j) {
+                const int a = bound[j * (kSpTileGroup + 1) + t], z = bound[j * (kSpTileGroup + 1) + t + 1];
+                if (z > a) {  // uniform
+                    const long long off = p.offsets[terms[j]];  // z > a implies a valid term
+                    const float qf = freqs[j];
+                    for (int pp = a + tid; pp < z; pp += kSpThreads) {
+                        const int d = __ldg(p.docs + off + pp) - (int)base;
+                        // a document appears once per term: no two threads touch the same slot
+                        acc[d] = __fadd_rn(acc[d], __fmul_rn(qf, __ldg(p.weights + off + pp)));
+                    }
+                    __syncthreads();
+                }
+            }
+            // common case once the list is warm: nothing in the tile beats the threshold -> one barrier
+            bool mine = false;
+            for (int e = tid; e < lim; e += kSpThreads) mine |= sp_make_key(acc[e], (uint32_t)(base + e)) > thr;
+            if (!__syncthreads_or(mine)) continue;
+            for (int c0 = 0; c0 < lim; c0 += kSpThreads) {
+                if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count);
+                const int e = c0 + tid;
+                const bool have = e < lim;
+                sp_offer(keys, count, thr, &s_count, have, have ? sp_make_key(acc[e], (uint32_t)(base + e)) : 0ull);
+            }
+        }
+        __syncthreads();  // bound[] is rewritten by the next group
+    }
+    sp_flush(keys, count, k_cand, thr, &s_count);
+    unsigned long long *out = p.cand + ((size_t)b * p.ctas_per_query + blockIdx.x) * p.kcap;
+    for (int i = tid; i < p.kcap; i += kSpThreads) out[i] = i < count ? keys[i] : 0ull;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 2: one CTA per query.  Merge the CTA lists, add the deferred common terms to the surviving
+// candidates (binary search per candidate and term, in query order), re-sort, drop zero scores,
+// normalise (txtai: min(score / min(top + avgscore, 6 * avgscore), 1)) and emit `limit` results.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSpThreads) sparse_finish_kernel(SparseParams p) {
+    __shared__ unsigned long long keys[kSpSort];
+    __shared__ int s_count;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const SpQuery qm = sp_query(p, b);
+    const int n_rare = qm.n_rare, n_common = qm.n_common, k_cand = qm.k_cand;
+    const int *terms = p.q_terms + (size_t)b * p.max_terms;
+    const float *freqs = p.q_freqs + (size_t)b * p.max_terms;
+
+    for (int i = tid; i < kSpSort; i += kSpThreads) keys[i] = 0ull;
+    if (tid == 0) s_count = 0;
+    int count = 0;
+    unsigned long long thr = 0ull;
+    __syncthreads();
+
+    const long long total = (long long)p.ctas_per_query * p.kcap;
+    const unsigned long long *cand = p.cand + (size_t)b * total;
+    constexpr int U = 4;  // keys loaded per thread before the offer rounds (independent loads in flight)
+    for (long long c0 = 0; c0 < total; c0 += (long long)U * kSpThreads) {
+        unsigned long long mine[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long e = c0 + (long long)u * kSpThreads + tid;
+            mine[u] = e < total ? cand[e] : 0ull;  // 0 = empty slot, never above the threshold
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count);
+            sp_offer(keys, count, thr, &s_count, true, mine[u]);
+        }
+    }
+    sp_flush(keys, count, k_cand, thr, &s_count);
+
+    if (n_common > 0) {
+        for (int i = tid; i < count; i += kSpThreads) {
+            const unsigned long long key = keys[i];
+            float s = sp_key_score(key);
+            const uint32_t doc = sp_key_doc(key);
+            for (int j = 0; j < n_common; ++j) {
+                long long lo, hi;
+                sp_term_range(p, terms[n_rare + j], lo, hi);
+                const long long at = sp_lower_bound(p.docs, lo, hi, (long long)doc);
+                if (at < hi && (uint32_t)__ldg(p.docs + at) == doc)
+                    s = __fadd_rn(s, __fmul_rn(freqs[n_rare + j], __ldg(p.weights + at)));
+            }
+            keys[i] = sp_make_key(s, doc);
+        }
+        sp_flush(keys, count, k_cand, thr, &s_count);
+    }
+
+    const float top = count > 0 ? sp_key_score(keys[0]) : 0.0f;
+    double maxscore = 1.0;
+    if (p.normalize) maxscore = fmin(__dadd_rn((double)top, p.avgscore), __dmul_rn(6.0, p.avgscore));
+    for (int r = tid; r < p.limit; r += kSpThreads) {
+        double s = __longlong_as_double(0xfff0000000000000LL);  // -inf
+        long long id = -1;
+        if (r < count) {
+            const float f = sp_key_score(keys[r]);
+            if (f > 0.0f) {
+                s = p.normalize ? fmin(__ddiv_rn((double)f, maxscore), 1.0) : (double)f;
+                id = (long long)sp_key_doc(keys[r]);
+            }
+        }
+        p.out_s[(size_t)b * p.limit + r] = s;
+        p.out_i[(size_t)b * p.limit + r] = id;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Build side: BM25 weight of every posting, in the double-precision operation order of txtai's
+// BM25.score, rounded once to fp32 (Terms.weights' astype(float32)).
+//   k = k1 * ((1 - b) + b * len / avgdl);  w = idf * (f * (k1 + 1)) / (f + k)
+// ---------------------------------------------------------------------------------------------
+__global__ void bm25_weights_kernel(const long long *offsets, long long n_terms, const int *docs, const int *freqs,
+                                    long long n_postings, const double *idf, const int *doc_len, double k1,
+                                    double k1_plus_1, double one_minus_b, double bb, double avgdl, float *weights) {
+    for (long long pidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; pidx < n_postings;
+         pidx += (long long)gridDim.x * blockDim.x) {
+        // term of this posting: last t with offsets[t] <= pidx
+        long long lo = 0, hi = n_terms;
+        while (lo < hi) {
+            const long long mid = lo + ((hi - lo) >> 1);
+            if (offsets[mid + 1] <= pidx) lo = mid + 1;
+            else hi = mid;
+        }
+        const double f = (double)freqs[pidx];
+        const double len = (double)doc_len[docs[pidx]];
+        const double k = __dmul_rn(k1, __dadd_rn(one_minus_b, __ddiv_rn(__dmul_rn(bb, len), avgdl)));
+        const double w = __ddiv_rn(__dmul_rn(idf[lo], __dmul_rn(f, k1_plus_1)), __dadd_rn(f, k));
+        weights[pidx] = __double2float_rn(w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hybrid fusion (txtai Search): per query, fused[id] = 0.0 + dense * w_dense (+ sparse * w_sparse), in
+// doubles like the Python floats it replaces; order = fused descending, ties keep insertion order
+// (dense candidates first, then sparse-only ones) as Python's stable sort does.  One CTA per query.
+// ---------------------------------------------------------------------------------------------
+struct FuseParams {
+    const float *dense_s;
+    const long long *dense_i;
+    int kd;
+    const double *sparse_s;
+    const long long *sparse_i;
+    int ks;
+    double w_dense, w_sparse;
+    int limit;
+    double *out_s;
+    long long *out_i;
+};
+
+__global__ void __launch_bounds__(256) hybrid_fuse_kernel(FuseParams p) {
+    extern __shared__ __align__(16) unsigned char fz_smem[];
+    const int n = p.kd + p.ks;
+    double *fused = reinterpret_cast<double *>(fz_smem);
+    long long *ids = reinterpret_cast<long long *>(fused + n);
+    int *valid = reinterpret_cast<int *>(ids + n);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *ds = p.dense_s + (size_t)b * p.kd;
+    const long long *di = p.dense_i + (size_t)b * p.kd;
+    const double *ss = p.sparse_s + (size_t)b * p.ks;
+    const long long *si = p.sparse_i + (size_t)b * p.ks;
+
+    for (int e = tid; e < n; e += blockDim.x) ids[e] = e < p.kd ? di[e] : si[e - p.kd];
+    for (int r = tid; r < p.limit; r += blockDim.x) {
+        p.out_s[(size_t)b * p.limit + r] = __longlong_as_double(0xfff0000000000000LL);
+        p.out_i[(size_t)b * p.limit + r] = -1;
+    }
+    __syncthreads();
+    for (int e = tid; e < n; e += blockDim.x) {
+        const long long id = ids[e];
+        int ok = id >= 0;
+        double f = 0.0;
+        if (ok && e < p.kd) {
+            f = __dadd_rn(0.0, __dmul_rn((double)ds[e], p.w_dense));
+            for (int j = 0; j < p.ks; ++j)
+                if (ids[p.kd + j] == id) {
+                    f = __dadd_rn(f, __dmul_rn(ss[j], p.w_sparse));
+                    break;
+                }
+        } else if (ok) {
+            f = __dadd_rn(0.0, __dmul_rn(ss[e - p.kd], p.w_sparse));
+            for (int j = 0; j < p.kd; ++j)
+                if (ids[j] == id) {  // already fused into the dense entry
+                    ok = 0;
+                    break;
+                }
+        }
+        fused[e] = f;
+        valid[e] = ok;
+    }
+    __syncthreads();
+    for (int e = tid; e < n; e += blockDim.x) {
+        if (!valid[e]) continue;
+        const double f = fused[e];
+        int rank = 0;
+        for (int o = 0; o < n; ++o)
+            rank += valid[o] && (fused[o] > f || (fused[o] == f && o < e));
+        if (rank < p.limit) {
+            p.out_s[(size_t)b * p.limit + rank] = f;
+            p.out_i[(size_t)b * p.limit + rank] = ids[e];
+        }
+    }
+}
+
+// heavy_ranker.py:110 with hybrid indexes: the two scores are already Python-float (double) sums
+__global__ void agree_f64_kernel(const long long *ids_a, const double *sa, const long long *ids_b, const double *sb,
+                                 long long n, double threshold, unsigned char *accept, double *combined) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double sum = __dadd_rn(sa[i], sb[i]);
+    if (accept) accept[i] = (ids_a[i] == ids_b[i] && sum > threshold) ? 1 : 0;
+    if (combined) combined[i] = sum;
+}
+
+}  // namespace vqa

@@ -13,9 +13,10 @@ This class keeps those names, positional orders, defaults (``limit=3``) and resu
 shapes (``[{"id","text","score"}]`` with ``content=True``, else ``[(id, score)]``) so
 that ``import vietnamese_qa_system_b200 as txtai`` leaves heavy_ranker.py unchanged.
 The dense leg (encode -> pool -> normalise -> score -> top-k) runs on the GPU
-through ``libvqa_b200.so``; the sparse BM25 leg of ``hybrid=True`` is outside the
-hot path and raises ``NotImplementedError`` rather than
-silently returning dense-only scores.
+through ``libvqa_b200.so``.  ``hybrid=True`` (how the reference builds its indexes,
+:78,81) adds the sparse BM25 leg (``scoring.BM25``): both legs
+fetch ``10 * limit`` candidates on the GPU and ``vqa_hybrid_fuse`` adds their scores per
+id with weights ``[w, 1 - w]`` (w = 0.5), as txtai does.
 
 Vectors: queries / documents may be given as text (needs an encoder: ``transform=``
 callable, or a HuggingFace ``path`` loaded by ``vectors.HFEncoder``) or directly as
@@ -34,11 +35,14 @@ import torch
 
 from . import ops
 from .ann import B200Flat
+from .scoring import BM25
 
 _CONFIG_FILE = "config.json"
 _ANN_FILE = "embeddings"
 _DB_FILE = "documents"
 _IDS_FILE = "ids.json"
+_SCORING_FILE = "scoring"
+_HYBRID_CANDIDATES = 10  # each leg fetches limit * 10 candidates (txtai Search)
 _PERSISTED_KEYS_SKIP = {"transform", "device"}
 
 
@@ -54,17 +58,28 @@ class Embeddings:
         self.ids: List[Any] = []          # ANN position -> caller's id (heavy_ranker.py:74-76)
         self._id_is_position = True
         self.database: Optional[sqlite3.Connection] = None
+        self.scoring: Optional[BM25] = None  # sparse leg (hybrid=True / keyword=True / scoring={...})
         self._encoder = None
         self.configure({**(config or {}), **kwargs})
 
     # ------------------------------------------------------------------ config
     def configure(self, config: dict) -> None:
         self.config = dict(config)
-        if self.config.get("hybrid"):
-            # accepted (the reference's saved indexes were built hybrid=True) but the sparse leg is
-            # not part of the accelerated path: refuse at query time instead of returning dense scores
-            self.config.setdefault("scoring", {"method": "bm25", "normalize": True, "terms": True})
+        if self.config.get("hybrid") or self.config.get("keyword"):
+            # txtai: hybrid=True -> dense index + BM25 term index with normalised scores;
+            # keyword=True -> the term index alone
+            self.config.setdefault("scoring", {"method": "bm25", "normalize": bool(self.config.get("hybrid")),
+                                               "terms": True})
+        sc = self.config.get("scoring")
+        if isinstance(sc, str):
+            self.config["scoring"] = sc = {"method": sc, "terms": True}
+        if sc is not None and str(sc.get("method", "bm25")).lower() != "bm25":
+            raise NotImplementedError(f"scoring method {sc.get('method')!r}: only bm25 is built")
         self._transform = self.config.get("transform")
+
+    @property
+    def _dense(self) -> bool:
+        return not self.config.get("keyword")
 
     @property
     def content(self) -> bool:
@@ -159,6 +174,16 @@ class Embeddings:
             rows.append(data)
         self._id_is_position = all(isinstance(u, int) and u == p for p, u in enumerate(self.ids))
         payload = [r.get("text") if isinstance(r, dict) else r for r in rows]
+        self.scoring = None
+        if self.config.get("scoring"):
+            if not all(isinstance(t, str) for t in payload):
+                raise ValueError("hybrid / keyword indexes need text documents (the sparse leg scores terms)")
+            self.scoring = BM25(self.config["scoring"], device=self.config.get("device"))
+            self.scoring.index(payload)
+        if not self._dense:
+            self.ann = None
+            self._store_content(rows)
+            return
         if embeddings is not None:
             vecs = self.batchtransform(embeddings)
             if vecs.shape[0] != len(rows):
@@ -171,6 +196,9 @@ class Embeddings:
         self.config["dimensions"] = int(vecs.shape[1])
         self.ann = B200Flat(self._ann_config())
         self.ann.index(vecs)
+        self._store_content(rows)
+
+    def _store_content(self, rows: List[Any]) -> None:
         if self.content:
             self.database = self._open_db()
             recs = []
@@ -183,7 +211,9 @@ class Embeddings:
                 self.database.executemany("INSERT INTO sections VALUES (?, ?, ?, ?)", recs)
 
     def count(self) -> int:
-        return 0 if self.ann is None else self.ann.count()
+        if self.ann is not None:
+            return self.ann.count()
+        return 0 if self.scoring is None else self.scoring.count()
 
     # ------------------------------------------------------------------ query
     def search(self, query: Any, limit: Optional[int] = None, weights=None, index=None, parameters=None,
@@ -193,25 +223,46 @@ class Embeddings:
 
     def batchsearch(self, queries: Sequence[Any], limit: Optional[int] = None, weights=None, index=None,
                     parameters=None, graph: bool = False):
-        if self.config.get("hybrid"):
-            raise NotImplementedError(
-                "hybrid=True (dense + BM25 fusion) is outside the accelerated dense path; build with hybrid=False")
         if graph:
             raise NotImplementedError("graph search is not part of the retrieval hot path")
-        if self.ann is None:
-            raise RuntimeError("index is empty: call index() or load() first")
         limit = 3 if limit is None else int(limit)
-        if limit < 1:
-            raise ValueError(f"limit must be >= 1; got {limit}")
-        k = min(limit, max(self.count(), 1))
-        q = self.batchtransform(queries if isinstance(queries, (np.ndarray, torch.Tensor)) else list(queries))
-        scores, pos = self.ann.search_tensors(q, k)
+        scores, pos = self.search_tensors(queries, limit, weights)
         s_np, p_np = scores.cpu().numpy(), pos.cpu().numpy()
         results = []
         for b in range(s_np.shape[0]):
             hits = [(int(p), float(s)) for p, s in zip(p_np[b].tolist(), s_np[b].tolist()) if p >= 0]
             results.append(self._resolve(hits))
         return results
+
+    def search_tensors(self, queries: Sequence[Any], limit: int, weights=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device-resident search: ``(scores [B, k], positions int64 [B, k])`` with ``k = min(limit, count)``;
+        scores are float32 cosines for a dense index and float64 for hybrid / keyword indexes (the Python
+        floats txtai returns); unused slots hold ``-inf`` / ``-1``."""
+        if self.ann is None and self.scoring is None:
+            raise RuntimeError("index is empty: call index() or load() first")
+        limit = int(limit)
+        if limit < 1:
+            raise ValueError(f"limit must be >= 1; got {limit}")
+        queries = queries if isinstance(queries, (np.ndarray, torch.Tensor)) else list(queries)
+        k = min(limit, max(self.count(), 1))
+        if self.scoring is None:
+            return self.ann.search_tensors(self.batchtransform(queries), k)
+        if isinstance(queries, (np.ndarray, torch.Tensor)) or not all(isinstance(q, str) for q in queries):
+            raise ValueError("hybrid / keyword search needs text queries (the sparse leg scores terms)")
+        if self.ann is None:
+            return self.scoring.search_tensors(queries, k)
+        cand = limit * _HYBRID_CANDIDATES
+        kd = min(cand, self.count())
+        if kd > 128:
+            raise NotImplementedError(f"hybrid search fetches {_HYBRID_CANDIDATES} x limit dense candidates; "
+                                      f"limit <= 12 is supported (got {limit})")
+        if weights is None:
+            weights = 0.5
+        if isinstance(weights, (int, float)):
+            weights = [weights, 1 - weights]
+        ds, dp = self.ann.search_tensors(self.batchtransform(queries), kd)
+        ss, sp = self.scoring.search_tensors(queries, cand)
+        return ops.hybrid_fuse(ds, dp, ss, sp, min(limit, kd + cand), float(weights[0]), float(weights[1]))
 
     def _resolve(self, hits: List[Tuple[int, float]]):
         """ANN position -> caller's id (a6), and the content join when content=True."""
@@ -232,7 +283,8 @@ class Embeddings:
 
     def similarity(self, query: Any, data: Sequence[Any]) -> List[Tuple[int, float]]:
         """Score ``query`` against ad-hoc ``data`` (txtai API): [(index, score)] descending."""
-        tmp = Embeddings({**self.config, "content": False, "hybrid": False}, transform=self._transform)
+        tmp = Embeddings({**{k: v for k, v in self.config.items() if k not in ("scoring", "keyword")},
+                          "content": False, "hybrid": False}, transform=self._transform)
         tmp._encoder = self._encoder
         tmp.index(list(data))
         return tmp.search(query, len(data))
@@ -240,13 +292,16 @@ class Embeddings:
     # ------------------------------------------------------------------ persistence
     def save(self, path: str) -> None:
         """Directory with config + embeddings (+ documents when content=True)."""
-        if self.ann is None:
+        if self.ann is None and self.scoring is None:
             raise RuntimeError("nothing to save")
         os.makedirs(path, exist_ok=True)
         cfg = {k: v for k, v in self.config.items() if k not in _PERSISTED_KEYS_SKIP and _jsonable(v)}
         with open(os.path.join(path, _CONFIG_FILE), "w", encoding="utf-8") as f:
             json.dump(cfg, f, ensure_ascii=False)
-        self.ann.save(os.path.join(path, _ANN_FILE))
+        if self.ann is not None:
+            self.ann.save(os.path.join(path, _ANN_FILE))
+        if self.scoring is not None:
+            self.scoring.save(os.path.join(path, _SCORING_FILE))
         with open(os.path.join(path, _IDS_FILE), "w", encoding="utf-8") as f:
             json.dump(None if self._id_is_position else self.ids, f, ensure_ascii=False)
         if self.content and self.database is not None:
@@ -263,12 +318,17 @@ class Embeddings:
             cfg = json.load(f)
         keep = {k: v for k, v in self.config.items() if k in _PERSISTED_KEYS_SKIP}
         self.configure({**cfg, **keep})
-        self.ann = B200Flat(self._ann_config())
-        self.ann.load(os.path.join(path, _ANN_FILE))
+        self.ann = self.scoring = None
+        if self._dense:
+            self.ann = B200Flat(self._ann_config())
+            self.ann.load(os.path.join(path, _ANN_FILE))
+        if self.config.get("scoring"):
+            self.scoring = BM25(self.config["scoring"], device=self.config.get("device"))
+            self.scoring.load(os.path.join(path, _SCORING_FILE))
         with open(os.path.join(path, _IDS_FILE), "r", encoding="utf-8") as f:
             ids = json.load(f)
         self._id_is_position = ids is None
-        self.ids = list(range(self.ann.count())) if ids is None else ids
+        self.ids = list(range(self.count())) if ids is None else ids
         db = os.path.join(path, _DB_FILE)
         self.database = None
         if self.content and os.path.exists(db):
@@ -285,7 +345,7 @@ class Embeddings:
         if self.database is not None:
             self.database.close()
             self.database = None
-        self.ann = None
+        self.ann = self.scoring = None
 
 
 def _jsonable(v: Any) -> bool:

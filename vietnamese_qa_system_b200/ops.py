@@ -274,17 +274,46 @@ def agree(ids_a: torch.Tensor, scores_a: torch.Tensor, ids_b: torch.Tensor, scor
         _need_cuda(t, nme)
     ids_a, ids_b = ids_a.contiguous().view(-1), ids_b.contiguous().view(-1)
     scores_a, scores_b = scores_a.contiguous().view(-1), scores_b.contiguous().view(-1)
-    if ids_a.dtype != torch.int64 or ids_b.dtype != torch.int64 or scores_a.dtype != torch.float32 \
-            or scores_b.dtype != torch.float32:
-        raise ValueError("ids must be int64 and scores float32")
+    if ids_a.dtype != torch.int64 or ids_b.dtype != torch.int64 or scores_a.dtype != scores_b.dtype \
+            or scores_a.dtype not in (torch.float32, torch.float64):
+        raise ValueError("ids must be int64 and both score vectors float32 (dense) or float64 (hybrid)")
     n = ids_a.numel()
     if not (ids_b.numel() == scores_a.numel() == scores_b.numel() == n):
         raise ValueError("all inputs must have the same length")
     dev = ids_a.device
     acc = torch.empty(n, dtype=torch.uint8, device=dev)
-    comb = torch.empty(n, dtype=torch.float32, device=dev)
-    N.check(N.lib().vqa_agree(ctypes.c_void_p(ids_a.data_ptr()), ctypes.c_void_p(scores_a.data_ptr()),
-                              ctypes.c_void_p(ids_b.data_ptr()), ctypes.c_void_p(scores_b.data_ptr()), n,
-                              float(threshold), ctypes.c_void_p(acc.data_ptr()), ctypes.c_void_p(comb.data_ptr()),
-                              dev.index or 0, ctypes.c_void_p(_stream(dev))))
+    comb = torch.empty(n, dtype=scores_a.dtype, device=dev)
+    fn = N.lib().vqa_agree if scores_a.dtype == torch.float32 else N.lib().vqa_agree_f64
+    N.check(fn(ctypes.c_void_p(ids_a.data_ptr()), ctypes.c_void_p(scores_a.data_ptr()),
+               ctypes.c_void_p(ids_b.data_ptr()), ctypes.c_void_p(scores_b.data_ptr()), n,
+               float(threshold), ctypes.c_void_p(acc.data_ptr()), ctypes.c_void_p(comb.data_ptr()),
+               dev.index or 0, ctypes.c_void_p(_stream(dev))))
     return acc.view(torch.bool), comb
+
+
+def hybrid_fuse(dense_scores: torch.Tensor, dense_ids: torch.Tensor, sparse_scores: torch.Tensor,
+                sparse_ids: torch.Tensor, limit: int, w_dense: float = 0.5, w_sparse: float = 0.5):
+    """Dense + sparse candidate fusion (txtai ``Search`` with ``hybrid=True``; heavy_ranker.py:78-83,98,100):
+    dense [B,kd] float32 / int64, sparse [B,ks] float64 / int64 -> (scores float64 [B,limit], ids int64 [B,limit])."""
+    for t, nme in ((dense_scores, "dense_scores"), (dense_ids, "dense_ids"), (sparse_scores, "sparse_scores"),
+                   (sparse_ids, "sparse_ids")):
+        _need_cuda(t, nme)
+    if dense_scores.dtype != torch.float32 or sparse_scores.dtype != torch.float64 \
+            or dense_ids.dtype != torch.int64 or sparse_ids.dtype != torch.int64:
+        raise ValueError("dense scores must be float32, sparse scores float64, ids int64")
+    if dense_scores.dim() != 2 or dense_scores.shape != dense_ids.shape or sparse_scores.dim() != 2 \
+            or sparse_scores.shape != sparse_ids.shape or dense_scores.shape[0] != sparse_scores.shape[0]:
+        raise ValueError("expected dense [B,kd] and sparse [B,ks] score/id pairs")
+    dense_scores, dense_ids = dense_scores.contiguous(), dense_ids.contiguous()
+    sparse_scores, sparse_ids = sparse_scores.contiguous(), sparse_ids.contiguous()
+    b, kd = (int(x) for x in dense_scores.shape)
+    ks = int(sparse_scores.shape[1])
+    dev = dense_scores.device
+    out_s = torch.empty((b, limit), dtype=torch.float64, device=dev)
+    out_i = torch.empty((b, limit), dtype=torch.int64, device=dev)
+    N.check(N.lib().vqa_hybrid_fuse(ctypes.c_void_p(dense_scores.data_ptr()), ctypes.c_void_p(dense_ids.data_ptr()), kd,
+                                    ctypes.c_void_p(sparse_scores.data_ptr()), ctypes.c_void_p(sparse_ids.data_ptr()),
+                                    ks, b, float(w_dense), float(w_sparse), int(limit),
+                                    ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()),
+                                    dev.index or 0, ctypes.c_void_p(_stream(dev))))
+    return out_s, out_i

@@ -42,10 +42,11 @@ class HeavyRanker:
         """``queries_a`` / ``queries_b``: the same queries as each index's encoder sees them (texts, or
         per-index vectors since the two indexes have different dimensions)."""
         queries_b = queries_a if queries_b is None else queries_b
-        qa = self.a.batchtransform(queries_a if not isinstance(queries_a, (list, tuple)) else list(queries_a))
-        qb = self.b.batchtransform(queries_b if not isinstance(queries_b, (list, tuple)) else list(queries_b))
-        sa, pa = self.a.ann.search_tensors(qa, limit)
-        sb, pb = self.b.ann.search_tensors(qb, limit)
+        as_list = lambda q: list(q) if isinstance(q, (list, tuple)) else q  # noqa: E731
+        sa, pa = self.a.search_tensors(as_list(queries_a), limit)   # float32 (dense) or float64 (hybrid) scores
+        sb, pb = self.b.search_tensors(as_list(queries_b), limit)
+        if sa.dtype != sb.dtype:                                   # one dense, one hybrid index
+            sa, sb = sa.double(), sb.double()
         # map ANN positions to caller ids before comparing (heavy_ranker.py:99,101 compare r['id'])
         ida = self._user_ids(self.a, pa[:, 0])
         idb = self._user_ids(self.b, pb[:, 0])
