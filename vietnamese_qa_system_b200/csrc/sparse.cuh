@@ -29,7 +29,7 @@ constexpr int kSpTile = 16384;                    // documents per shared-memory
 constexpr int kSpSort = 2048;                     // key slots per CTA (16 KB)
 constexpr int kSpMaxCand = 1024;                  // most candidates a query may keep (k_cand)
 constexpr int kSpMaxTerms = 64;                   // distinct known terms per query
-constexpr int kSpTileGroup = 8;                   // tiles whose posting boundaries are searched together
+constexpr int kSpBoundSlots = 4096;               // tile-edge posting offsets held in shared memory (16 KB)
 constexpr int kSpMetaStride = 4;                  // q_meta row: n_rare, n_common, k_cand, unused
 
 struct SparseParams {
@@ -99,9 +99,10 @@ __device__ __forceinline__ SpQuery sp_query(const SparseParams &p, int b) {
 }
 
 // Bitonic sort of all kSpSort keys, descending (empty slots are 0 and sink to the end), then keep the
-// best k_cand.  `count` and `thr` are CTA-uniform registers.  Ends with a barrier.
+// best k_cand.  `count` and `thr` are CTA-uniform registers; the threshold never drops below `floor_key`.
+// Ends with a barrier.
 __device__ __forceinline__ void sp_flush(unsigned long long *keys, int &count, int k_cand, unsigned long long &thr,
-                                         int *s_count) {
+                                         int *s_count, unsigned long long floor_key = 0ull) {
     const int tid = threadIdx.x;
     __syncthreads();
     for (int k = 2; k <= kSpSort; k <<= 1) {
@@ -125,6 +126,7 @@ __device__ __forceinline__ void sp_flush(unsigned long long *keys, int &count, i
         count = k_cand;
     }
     thr = (count >= k_cand) ? keys[k_cand - 1] : 0ull;
+    if (thr < floor_key) thr = floor_key;
     if (tid == 0) *s_count = count;
     __syncthreads();
 }
@@ -139,13 +141,13 @@ __device__ __forceinline__ void sp_offer(unsigned long long *keys, int &count, u
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 1: tile accumulate + select.  grid = (ctas_per_query, B), 512 threads, ~83 KB smem.
+// Stage 1: tile accumulate + select.  grid = (ctas_per_query, B), 512 threads, 96 KB smem.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     float *acc = reinterpret_cast<float *>(sp_smem);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sp_smem + (size_t)kSpTile * sizeof(float));
-    int *bound = reinterpret_cast<int *>(keys + kSpSort);  // [kSpMaxTerms][kSpTileGroup + 1], relative to the term's first posting
+    int *bound = reinterpret_cast<int *>(keys + kSpSort);  // [n_rare][group + 1] <= kSpBoundSlots, relative to the term's first posting
     __shared__ int s_count;
 
     const int tid = threadIdx.x;
@@ -162,33 +164,41 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
     for (int i = tid; i < kSpSort; i += kSpThreads) keys[i] = 0ull;
     if (tid == 0) s_count = 0;
     int count = 0;
-    unsigned long long thr = 0ull;
+    // Zero-score documents never reach the result (the finish stage drops score 0) except as the
+    // zero-fill of a candidate list that a deferred common term may still lift -- and then only the
+    // first k_cand positions of the whole index can be among the k_cand best.  So the threshold
+    // starts at (0, k_cand) [common terms present] or (0, 0) [none]: only positive scores, or those
+    // first positions, ever pass, and posting-free tiles are skipped from the start.
+    const unsigned long long floor_key = sp_make_key(0.0f, qm.n_common > 0 ? (uint32_t)k_cand : 0u);
+    unsigned long long thr = floor_key;
     __syncthreads();
 
-    for (long long g0 = first_tile; g0 < last_tile; g0 += kSpTileGroup) {
-        const int ng = (int)min((long long)kSpTileGroup, last_tile - g0);
-        // posting boundaries of every term at the ng + 1 tile edges of this group
+    // tile edges whose posting offsets fit the shared-memory table at once
+    const int group = max(1, min(p.tiles_per_cta, kSpBoundSlots / max(n_rare, 1) - 1));
+    for (long long g0 = first_tile; g0 < last_tile; g0 += group) {
+        const int ng = (int)min((long long)group, last_tile - g0);
+        // posting boundaries of every term at the ng + 1 tile edges of this group (independent binary
+        // searches, one per thread, all in flight together)
         for (int w = tid; w < n_rare * (ng + 1); w += kSpThreads) {
             const int j = w / (ng + 1), t = w - j * (ng + 1);
             long long lo, hi;
             sp_term_range(p, terms[j], lo, hi);
             const long long edge = (g0 + t) * (long long)kSpTile;
-            bound[j * (kSpTileGroup + 1) + t] = (int)(sp_lower_bound(p.docs, lo, hi, edge) - lo);
+            bound[j * (group + 1) + t] = (int)(sp_lower_bound(p.docs, lo, hi, edge) - lo);
         }
         __syncthreads();
         for (int t = 0; t < ng; ++t) {
             const long long base = (g0 + t) * (long long)kSpTile;
             const int lim = (int)min((long long)kSpTile, p.n_docs - base);
             bool any = false;
-            for (int j = 0; j < n_rare; ++j)
-                any |= bound[j * (kSpTileGroup + 1) + t + 1] > bound[j * (kSpTileGroup + 1) + t];
-            // a tile without postings holds only zero scores; once the list's threshold is at or above
-            // (0, first position of the tile) none of them can enter (uniform decision)
+            for (int j = 0; j < n_rare; ++j) any |= bound[j * (group + 1) + t + 1] > bound[j * (group + 1) + t];
+            // a tile without postings holds only zero scores: none can enter once the threshold is at or
+            // above (0, first position of the tile) (uniform decision)
             if (!any && sp_make_key(0.0f, (uint32_t)base) <= thr) continue;
             for (int e = tid; e < lim; e += kSpThreads) acc[e] = 0.0f;
             __syncthreads();
             for (int j = 0; j < n_rare; ++j) {
-                const int a = bound[j * (kSpTileGroup + 1) + t], z = bound[j * (kSpTileGroup + 1) + t + 1];
+                const int a = bound[j * (group + 1) + t], z = bound[j * (group + 1) + t + 1];
                 if (z > a) {  // uniform
                     const long long off = p.offsets[terms[j]];  // z > a implies a valid term
                     const float qf = freqs[j];
@@ -200,12 +210,12 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
                     __syncthreads();
                 }
             }
-            // common case once the list is warm: nothing in the tile beats the threshold -> one barrier
+            // common case: nothing in the tile beats the threshold -> one barrier
             bool mine = false;
             for (int e = tid; e < lim; e += kSpThreads) mine |= sp_make_key(acc[e], (uint32_t)(base + e)) > thr;
             if (!__syncthreads_or(mine)) continue;
             for (int c0 = 0; c0 < lim; c0 += kSpThreads) {
-                if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count);
+                if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
                 const int e = c0 + tid;
                 const bool have = e < lim;
                 sp_offer(keys, count, thr, &s_count, have, have ? sp_make_key(acc[e], (uint32_t)(base + e)) : 0ull);
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
         }
         __syncthreads();  // bound[] is rewritten by the next group
     }
-    sp_flush(keys, count, k_cand, thr, &s_count);
+    sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
     unsigned long long *out = p.cand + ((size_t)b * p.ctas_per_query + blockIdx.x) * p.kcap;
     for (int i = tid; i < p.kcap; i += kSpThreads) out[i] = i < count ? keys[i] : 0ull;
 }

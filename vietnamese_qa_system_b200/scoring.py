@@ -281,7 +281,11 @@ class BM25:
         queries = list(queries)
         if not queries:
             raise ValueError("no queries given")
-        q_terms, q_freqs, q_meta, k_cand_max = self.plan_queries(queries, limit)
+        return self.search_planned(*self.plan_queries(queries, limit), limit)
+
+    def search_planned(self, q_terms: np.ndarray, q_freqs: np.ndarray, q_meta: np.ndarray, k_cand_max: int,
+                       limit: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The device half of a search: one small H2D copy of the packed query plan, ``vqa_sparse_search``."""
         k_cand_max = max(k_cand_max, min(limit, self.total))
         dev = self.device
         b, width = q_terms.shape
