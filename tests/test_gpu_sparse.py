@@ -265,3 +265,30 @@ def test_index_postings_equals_index():
     assert bm2.batchsearch(queries, 9) == bm.batchsearch(queries, 9)
     with pytest.raises(ValueError):
         bm2.index_postings(h["offsets"][:-1], h["docs"], h["freqs"], h["lengths"])
+
+
+def test_sparse_both_accumulate_paths_and_zero_fill():
+    """Crafted corpus that forces each stage-1 path: a CTA whose document range holds <= 2048 postings of
+    the query merges them by sorting, otherwise it accumulates dense score tiles.  'needle' (3 documents) +
+    the deferred common term 'all' needs the zero-fill candidates (positions < k_cand)."""
+    n = 140_000
+    docs = []
+    for i in range(n):
+        d = ["pad%d" % (i % 7)]
+        if i % 12 == 0:
+            d.append("mid")                   # 8.3 % of the documents: accumulated everywhere, ~2.7 k per 32 k range
+        if i % 2 == 0:
+            d += ["all"] * (1 + i % 3)        # 50 %: deferred common term, varying frequency
+        if i in (77, 50_001, 139_999):
+            d.append("needle")
+        docs.append(d)
+    bm, ref = build(docs)
+    queries = [["needle", "all"], ["mid", "all"], ["needle", "mid", "all", "all"], ["mid"], ["all"], ["needle"],
+               ["pad3", "mid"], ["nothing"]]
+    for batch_mult in (1, 8):                  # 8 queries: 1 tile per CTA (sorted merge); 64: 2 tiles per CTA (tiles)
+        qs = queries * batch_mult
+        for limit in (1, 10, 30):
+            assert_same(bm, ref, qs, limit)
+    r = bm.search(["needle", "all"], 10)
+    assert [p for p, _ in r[:3]] == sorted([77, 50_001, 139_999], key=lambda x: -dict(r)[x])
+    assert len(r) == 10                        # 3 needle documents + zero-fill positions lifted by 'all'

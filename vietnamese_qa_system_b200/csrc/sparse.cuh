@@ -30,6 +30,7 @@ constexpr int kSpSort = 2048;                     // key slots per CTA (16 KB)
 constexpr int kSpMaxCand = 1024;                  // most candidates a query may keep (k_cand)
 constexpr int kSpMaxTerms = 64;                   // distinct known terms per query
 constexpr int kSpBoundSlots = 4096;               // tile-edge posting offsets held in shared memory (16 KB)
+constexpr int kSpFastMax = 2048;                  // postings in a CTA's document range merged by sorting instead of tiles
 constexpr int kSpMetaStride = 4;                  // q_meta row: n_rare, n_common, k_cand, unused
 
 struct SparseParams {
@@ -131,6 +132,28 @@ __device__ __forceinline__ void sp_flush(unsigned long long *keys, int &count, i
     __syncthreads();
 }
 
+// Bitonic sort of a[0..n) ascending, n a power of two <= kSpSort.  Starts and ends with a barrier.
+__device__ __forceinline__ void sp_sort_asc(unsigned long long *a, int n) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += kSpThreads) {
+                const int x = i ^ j;
+                if (x > i) {
+                    const unsigned long long u = a[i], v = a[x];
+                    const bool asc = (i & k) == 0;
+                    if (asc ? (u > v) : (u < v)) {
+                        a[i] = v;
+                        a[x] = u;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // One CTA-wide offer round: each thread proposes at most one key.  Returns with a barrier; `count`
 // stays uniform because the barrier itself counts the appends.
 __device__ __forceinline__ void sp_offer(unsigned long long *keys, int &count, unsigned long long thr, int *s_count,
@@ -141,13 +164,14 @@ __device__ __forceinline__ void sp_offer(unsigned long long *keys, int &count, u
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 1: tile accumulate + select.  grid = (ctas_per_query, B), 512 threads, 96 KB smem.
+// Stage 1: accumulate + select.  grid = (ctas_per_query, B), 512 threads, 97 KB smem.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     float *acc = reinterpret_cast<float *>(sp_smem);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sp_smem + (size_t)kSpTile * sizeof(float));
     int *bound = reinterpret_cast<int *>(keys + kSpSort);  // [n_rare][group + 1] <= kSpBoundSlots, relative to the term's first posting
+    long long *crange = reinterpret_cast<long long *>(bound + kSpBoundSlots);  // [2 * kSpMaxTerms] posting range of each term in this CTA's documents
     __shared__ int s_count;
 
     const int tid = threadIdx.x;
@@ -173,7 +197,80 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
     unsigned long long thr = floor_key;
     __syncthreads();
 
-    // tile edges whose posting offsets fit the shared-memory table at once
+    // posting sub-range of every term inside this CTA's document range
+    const long long doc_lo = min(p.n_docs, first_tile * (long long)kSpTile);
+    const long long doc_hi = min(p.n_docs, max(first_tile, last_tile) * (long long)kSpTile);
+    for (int w = tid; w < 2 * n_rare; w += kSpThreads) {
+        long long lo, hi;
+        sp_term_range(p, terms[w >> 1], lo, hi);
+        crange[w] = sp_lower_bound(p.docs, lo, hi, (w & 1) ? doc_hi : doc_lo);
+    }
+    __syncthreads();
+    long long p_cta = 0;
+    for (int j = 0; j < n_rare; ++j) p_cta += crange[2 * j + 1] - crange[2 * j];
+
+    if (p_cta <= kSpFastMax) {
+        // ---- few postings in this range (the usual case for rare terms): no score tile at all.  Stage the
+        // postings as (position, term slot, staging index) keys, sort, and sum each position's run in term
+        // order -- work proportional to the postings, not to the documents.
+        unsigned long long *sk = reinterpret_cast<unsigned long long *>(acc);  // [kSpFastMax], aliases the tile
+        float *wbuf = acc + 2 * kSpFastMax;                                    // [kSpFastMax]
+        const int P = (int)p_cta;
+        int n = 2;
+        while (n < P) n <<= 1;
+        int prefix = 0;
+        for (int j = 0; j < n_rare; ++j) {
+            const long long a = crange[2 * j], z = crange[2 * j + 1];
+            for (long long pp = a + tid; pp < z; pp += kSpThreads) {
+                const int i = prefix + (int)(pp - a);
+                sk[i] = ((unsigned long long)(uint32_t)__ldg(p.docs + pp) << 32) | ((unsigned long long)j << 16) |
+                        (unsigned long long)i;
+                wbuf[i] = __ldg(p.weights + pp);
+            }
+            prefix += (int)(z - a);
+        }
+        for (int i = P + tid; i < n; i += kSpThreads) sk[i] = ~0ull;
+        sp_sort_asc(sk, n);
+        for (int i0 = 0; i0 < P; i0 += kSpThreads) {
+            if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
+            const int i = i0 + tid;
+            bool head = false;
+            unsigned long long key = 0ull;
+            if (i < P) {
+                const uint32_t doc = (uint32_t)(sk[i] >> 32);
+                head = i == 0 || (uint32_t)(sk[i - 1] >> 32) != doc;
+                if (head) {
+                    float sum = 0.0f;
+                    for (int t = i; t < P && (uint32_t)(sk[t] >> 32) == doc; ++t) {
+                        const unsigned long long e = sk[t];
+                        sum = __fadd_rn(sum, __fmul_rn(freqs[(int)((e >> 16) & 0xffffu)], wbuf[(int)(e & 0xffffu)]));
+                    }
+                    key = sp_make_key(sum, doc);
+                }
+            }
+            sp_offer(keys, count, thr, &s_count, head, key);
+        }
+        if (qm.n_common > 0) {
+            // zero-fill positions (see floor_key): documents below k_cand without a posting here
+            const long long zhi = min(doc_hi, (long long)k_cand);
+            for (long long p0 = doc_lo; p0 < zhi; p0 += kSpThreads) {
+                if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
+                const long long d = p0 + tid;
+                bool have = false;
+                if (d < zhi) {
+                    int lo = 0, hi = P;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((uint32_t)(sk[mid] >> 32) < (uint32_t)d) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    have = !(lo < P && (uint32_t)(sk[lo] >> 32) == (uint32_t)d);
+                }
+                sp_offer(keys, count, thr, &s_count, have, sp_make_key(0.0f, (uint32_t)d));
+            }
+        }
+    } else {
+    // ---- many postings: dense score tiles.  Tile edges whose posting offsets fit the shared-memory table at once
     const int group = max(1, min(p.tiles_per_cta, kSpBoundSlots / max(n_rare, 1) - 1));
     for (long long g0 = first_tile; g0 < last_tile; g0 += group) {
         const int ng = (int)min((long long)group, last_tile - g0);
@@ -184,7 +281,7 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
             long long lo, hi;
             sp_term_range(p, terms[j], lo, hi);
             const long long edge = (g0 + t) * (long long)kSpTile;
-            bound[j * (group + 1) + t] = (int)(sp_lower_bound(p.docs, lo, hi, edge) - lo);
+            bound[j * (group + 1) + t] = (int)(sp_lower_bound(p.docs, crange[2 * j], crange[2 * j + 1], edge) - lo);
         }
         __syncthreads();
         for (int t = 0; t < ng; ++t) {
@@ -202,10 +299,20 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
                 if (z > a) {  // uniform
                     const long long off = p.offsets[terms[j]];  // z > a implies a valid term
                     const float qf = freqs[j];
-                    for (int pp = a + tid; pp < z; pp += kSpThreads) {
-                        const int d = __ldg(p.docs + off + pp) - (int)base;
-                        // a document appears once per term: no two threads touch the same slot
-                        acc[d] = __fadd_rn(acc[d], __fmul_rn(qf, __ldg(p.weights + off + pp)));
+                    constexpr int U = 4;  // postings per thread whose loads are in flight together
+                    for (int p0 = a; p0 < z; p0 += U * kSpThreads) {
+                        int dd[U];
+                        float ww[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int pp = p0 + u * kSpThreads + tid;
+                            dd[u] = pp < z ? __ldg(p.docs + off + pp) - (int)base : -1;
+                            ww[u] = pp < z ? __ldg(p.weights + off + pp) : 0.0f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            // a document appears once per term: no two threads touch the same slot
+                            if (dd[u] >= 0) acc[dd[u]] = __fadd_rn(acc[dd[u]], __fmul_rn(qf, ww[u]));
                     }
                     __syncthreads();
                 }
@@ -222,6 +329,7 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
             }
         }
         __syncthreads();  // bound[] is rewritten by the next group
+    }
     }
     sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
     unsigned long long *out = p.cand + ((size_t)b * p.ctas_per_query + blockIdx.x) * p.kcap;

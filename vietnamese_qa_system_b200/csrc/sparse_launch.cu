@@ -22,7 +22,7 @@ void sparse_plan(long long n_docs, int n_queries, int sm_count, int *ctas_per_qu
 
 static size_t scan_smem_bytes() {
     return (size_t)kSpTile * sizeof(float) + (size_t)kSpSort * sizeof(unsigned long long) +
-           (size_t)kSpBoundSlots * sizeof(int);
+           (size_t)kSpBoundSlots * sizeof(int) + (size_t)2 * kSpMaxTerms * sizeof(long long);
 }
 
 cudaError_t launch_sparse_search(const SparseLaunch &a, cudaStream_t st) {
