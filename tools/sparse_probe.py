@@ -42,7 +42,8 @@ def main():
     common_ids = np.flatnonzero(df > 0.1 * n_docs)
     out = {"n_docs": n_docs, "postings": int(len(docs)), "terms": len(vocab), "build_s": round(build_s, 2),
            "common_terms": int(len(common_ids)), "rows": []}
-    for batch in (1, 32, 256):
+    profile_only = os.environ.get("SPARSE_PROBE_PROFILE") == "1"   # under ncu: one warm + one measured launch per config
+    for batch in ((256,) if profile_only else (1, 32, 256)):
         for kind in ("rare", "mixed", "common-only"):
             qs = []
             for _ in range(batch):
@@ -53,6 +54,12 @@ def main():
                     if kind == "mixed":
                         q.append(vocab[int(rng.choice(common_ids))])
                 qs.append(q)
+            if profile_only:
+                st = bm.stage_plan(*bm.plan_queries(qs, 10), 10)
+                bm.launch_staged(st)
+                bm.launch_staged(st)
+                torch.cuda.synchronize()
+                continue
             t0 = time.perf_counter()
             for _ in range(5):
                 plan = bm.plan_queries(qs, 10)
@@ -73,9 +80,22 @@ def main():
             ev1.record()
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / reps
-            out["rows"].append({"batch": batch, "kind": kind, "device_ms_per_batch": round(ms, 4),
+            st = bm.stage_plan(*plan, 10)                                 # kernels only: plan already on the device
+            bm.launch_staged(st)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                bm.launch_staged(st)
+            ev1.record()
+            torch.cuda.synchronize()
+            kms = ev0.elapsed_time(ev1) / reps
+            out["rows"].append({"batch": batch, "kind": kind, "kernels_ms_per_batch": round(kms, 4),
+                                "kernel_posting_gbs": round(bytes_ / kms / 1e6, 2),
+                                "device_ms_per_batch": round(ms, 4),
                                 "host_planning_ms": round(plan_ms, 4), "device_qps": round(batch / ms * 1e3, 1),
                                 "posting_bytes": bytes_, "posting_gbs": round(bytes_ / ms / 1e6, 2)})
+    if profile_only:
+        return
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/sparse_probe.json", "w") as f:
         json.dump(out, f, indent=1)

@@ -99,16 +99,19 @@ __device__ __forceinline__ SpQuery sp_query(const SparseParams &p, int b) {
     return q;
 }
 
-// Bitonic sort of all kSpSort keys, descending (empty slots are 0 and sink to the end), then keep the
+// Bitonic sort of the occupied keys, descending (empty slots are 0 and stay at the end), then keep the
 // best k_cand.  `count` and `thr` are CTA-uniform registers; the threshold never drops below `floor_key`.
 // Ends with a barrier.
 __device__ __forceinline__ void sp_flush(unsigned long long *keys, int &count, int k_cand, unsigned long long &thr,
                                          int *s_count, unsigned long long floor_key = 0ull) {
     const int tid = threadIdx.x;
+    // slots >= count are always 0, so sorting the power-of-two prefix that covers `count` is enough
+    int n = 2;
+    while (n < count) n <<= 1;
     __syncthreads();
-    for (int k = 2; k <= kSpSort; k <<= 1) {
+    for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < kSpSort; i += kSpThreads) {
+            for (int i = tid; i < n; i += kSpThreads) {
                 const int x = i ^ j;
                 if (x > i) {
                     const unsigned long long a = keys[i], b = keys[x];
@@ -293,30 +296,45 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
             // above (0, first position of the tile) (uniform decision)
             if (!any && sp_make_key(0.0f, (uint32_t)base) <= thr) continue;
             for (int e = tid; e < lim; e += kSpThreads) acc[e] = 0.0f;
-            __syncthreads();
-            for (int j = 0; j < n_rare; ++j) {
-                const int a = bound[j * (group + 1) + t], z = bound[j * (group + 1) + t + 1];
-                if (z > a) {  // uniform
-                    const long long off = p.offsets[terms[j]];  // z > a implies a valid term
-                    const float qf = freqs[j];
-                    constexpr int U = 4;  // postings per thread whose loads are in flight together
-                    for (int p0 = a; p0 < z; p0 += U * kSpThreads) {
-                        int dd[U];
-                        float ww[U];
+            // Accumulate in term order.  A "round" is 512 consecutive postings of one term; the loads of U
+            // rounds -- across terms -- are issued together so that one memory round trip covers them, then
+            // they are applied in order with a barrier wherever the term changes (a document appears once
+            // per term, so within a term no two threads touch the same slot).
+            constexpr int U = 8;
+            int jj = 0;
+            int pp = n_rare > 0 ? bound[t] : 0;
+            while (true) {
+                int rterm[U], dd[U];
+                float ww[U], qq[U];
 #pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const int pp = p0 + u * kSpThreads + tid;
-                            dd[u] = pp < z ? __ldg(p.docs + off + pp) - (int)base : -1;
-                            ww[u] = pp < z ? __ldg(p.weights + off + pp) : 0.0f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            // a document appears once per term: no two threads touch the same slot
-                            if (dd[u] >= 0) acc[dd[u]] = __fadd_rn(acc[dd[u]], __fmul_rn(qf, ww[u]));
+                for (int u = 0; u < U; ++u) {
+                    while (jj < n_rare && pp >= bound[jj * (group + 1) + t + 1]) {  // uniform
+                        ++jj;
+                        if (jj < n_rare) pp = bound[jj * (group + 1) + t];
                     }
-                    __syncthreads();
+                    rterm[u] = jj < n_rare ? jj : -1;
+                    dd[u] = -1;
+                    ww[u] = qq[u] = 0.0f;
+                    if (jj < n_rare) {
+                        const int idx = pp + tid;
+                        if (idx < bound[jj * (group + 1) + t + 1]) {
+                            const long long at = p.offsets[terms[jj]] + idx;
+                            dd[u] = __ldg(p.docs + at) - (int)base;
+                            ww[u] = __ldg(p.weights + at);
+                            qq[u] = freqs[jj];
+                        }
+                        pp += kSpThreads;
+                    }
+                }
+                if (rterm[0] < 0) break;  // uniform: nothing left
+                __syncthreads();          // zero-fill / previous batch complete
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (u > 0 && rterm[u] >= 0 && rterm[u] != rterm[u - 1]) __syncthreads();  // uniform
+                    if (dd[u] >= 0) acc[dd[u]] = __fadd_rn(acc[dd[u]], __fmul_rn(qq[u], ww[u]));
                 }
             }
+            __syncthreads();
             // common case: nothing in the tile beats the threshold -> one barrier
             bool mine = false;
             for (int e = tid; e < lim; e += kSpThreads) mine |= sp_make_key(acc[e], (uint32_t)(base + e)) > thr;

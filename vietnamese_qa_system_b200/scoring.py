@@ -286,16 +286,17 @@ class BM25:
     def search_planned(self, q_terms: np.ndarray, q_freqs: np.ndarray, q_meta: np.ndarray, k_cand_max: int,
                        limit: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """The device half of a search: one small H2D copy of the packed query plan, ``vqa_sparse_search``."""
+        return self.launch_staged(self.stage_plan(q_terms, q_freqs, q_meta, k_cand_max, limit))
+
+    def stage_plan(self, q_terms: np.ndarray, q_freqs: np.ndarray, q_meta: np.ndarray, k_cand_max: int, limit: int):
+        """Upload a query plan (one H2D copy) and allocate workspace / outputs; returns the launch arguments."""
         k_cand_max = max(k_cand_max, min(limit, self.total))
         dev = self.device
         b, width = q_terms.shape
         lim = min(limit, k_cand_max)
         packed = np.concatenate([q_terms.view(np.uint8).ravel(), q_freqs.view(np.uint8).ravel(),
                                  q_meta.view(np.uint8).ravel()])
-        blob = torch.from_numpy(packed).to(dev)  # one H2D copy for the three small arrays
-        base = blob.data_ptr()
-        off_f = q_terms.nbytes
-        off_m = off_f + q_freqs.nbytes
+        blob = torch.from_numpy(packed).to(dev)
         key = (b, k_cand_max)
         ws = self._ws.get(key)
         if ws is None:
@@ -304,12 +305,20 @@ class BM25:
             ws = self._ws[key] = torch.empty(max(need.value, 8), dtype=torch.uint8, device=dev)
         out_s = torch.empty((b, lim), dtype=torch.float64, device=dev)
         out_i = torch.empty((b, lim), dtype=torch.int64, device=dev)
+        return {"blob": blob, "off_f": q_terms.nbytes, "off_m": q_terms.nbytes + q_freqs.nbytes, "width": width,
+                "b": b, "k_cand_max": k_cand_max, "lim": lim, "limit": limit, "ws": ws, "out_s": out_s,
+                "out_i": out_i}
+
+    def launch_staged(self, st) -> Tuple[torch.Tensor, torch.Tensor]:
+        dev = self.device
+        base = st["blob"].data_ptr()
+        out_s, out_i, b, lim, limit = st["out_s"], st["out_i"], st["b"], st["lim"], st["limit"]
         normalize = bool(self.normalize and self.avgscore)
         N.check(N.lib().vqa_sparse_search(
-            self._h, ctypes.c_void_p(base), ctypes.c_void_p(base + off_f), ctypes.c_void_p(base + off_m), width, b,
-            k_cand_max, lim, int(normalize), float(self.avgscore or 0.0), ctypes.c_void_p(out_s.data_ptr()),
-            ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
-            ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            self._h, ctypes.c_void_p(base), ctypes.c_void_p(base + st["off_f"]), ctypes.c_void_p(base + st["off_m"]),
+            st["width"], b, st["k_cand_max"], lim, int(normalize), float(self.avgscore or 0.0),
+            ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()), ctypes.c_void_p(st["ws"].data_ptr()),
+            st["ws"].numel(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         if lim < limit:
             pad_s = torch.full((b, limit - lim), float("-inf"), dtype=torch.float64, device=dev)
             pad_i = torch.full((b, limit - lim), -1, dtype=torch.int64, device=dev)
