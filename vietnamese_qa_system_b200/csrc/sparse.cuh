@@ -295,49 +295,47 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
             // a tile without postings holds only zero scores: none can enter once the threshold is at or
             // above (0, first position of the tile) (uniform decision)
             if (!any && sp_make_key(0.0f, (uint32_t)base) <= thr) continue;
-            for (int e = tid; e < lim; e += kSpThreads) acc[e] = 0.0f;
-            // Accumulate in term order.  A "round" is 512 consecutive postings of one term; the loads of U
-            // rounds -- across terms -- are issued together so that one memory round trip covers them, then
-            // they are applied in order with a barrier wherever the term changes (a document appears once
-            // per term, so within a term no two threads touch the same slot).
-            constexpr int U = 8;
-            int jj = 0;
-            int pp = n_rare > 0 ? bound[t] : 0;
-            while (true) {
-                int rterm[U], dd[U];
-                float ww[U], qq[U];
+            for (int e = tid * 4; e < lim; e += kSpThreads * 4)  // lim <= kSpTile: the 16-byte store stays inside the tile
+                *reinterpret_cast<float4 *>(acc + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            __syncthreads();
+            for (int j = 0; j < n_rare; ++j) {
+                const int a = bound[j * (group + 1) + t], z = bound[j * (group + 1) + t + 1];
+                if (z > a) {  // uniform
+                    const long long off = p.offsets[terms[j]];  // z > a implies a valid term
+                    const float qf = freqs[j];
+                    constexpr int U = 4;  // postings per thread whose loads are in flight together
+                    for (int p0 = a; p0 < z; p0 += U * kSpThreads) {
+                        int dd[U];
+                        float ww[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    while (jj < n_rare && pp >= bound[jj * (group + 1) + t + 1]) {  // uniform
-                        ++jj;
-                        if (jj < n_rare) pp = bound[jj * (group + 1) + t];
-                    }
-                    rterm[u] = jj < n_rare ? jj : -1;
-                    dd[u] = -1;
-                    ww[u] = qq[u] = 0.0f;
-                    if (jj < n_rare) {
-                        const int idx = pp + tid;
-                        if (idx < bound[jj * (group + 1) + t + 1]) {
-                            const long long at = p.offsets[terms[jj]] + idx;
-                            dd[u] = __ldg(p.docs + at) - (int)base;
-                            ww[u] = __ldg(p.weights + at);
-                            qq[u] = freqs[jj];
+                        for (int u = 0; u < U; ++u) {
+                            const int pp = p0 + u * kSpThreads + tid;
+                            dd[u] = pp < z ? __ldg(p.docs + off + pp) - (int)base : -1;
+                            ww[u] = pp < z ? __ldg(p.weights + off + pp) : 0.0f;
                         }
-                        pp += kSpThreads;
-                    }
-                }
-                if (rterm[0] < 0) break;  // uniform: nothing left
-                __syncthreads();          // zero-fill / previous batch complete
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (u > 0 && rterm[u] >= 0 && rterm[u] != rterm[u - 1]) __syncthreads();  // uniform
-                    if (dd[u] >= 0) acc[dd[u]] = __fadd_rn(acc[dd[u]], __fmul_rn(qq[u], ww[u]));
+                        for (int u = 0; u < U; ++u)
+                            // a document appears once per term: no two threads touch the same slot
+                            if (dd[u] >= 0) acc[dd[u]] = __fadd_rn(acc[dd[u]], __fmul_rn(qf, ww[u]));
+                    }
+                    __syncthreads();
                 }
             }
-            __syncthreads();
-            // common case: nothing in the tile beats the threshold -> one barrier
+            // Common case: nothing in the tile beats the threshold -> one barrier.  Screened on the score
+            // alone (a float compare per element, 16-byte loads): in a tile that lies wholly after the
+            // threshold's position an equal score loses the tie, so the compare is strict there.
+            const float thr_s = sp_key_score(thr);
+            const bool strict = (uint32_t)base >= sp_key_doc(thr);
             bool mine = false;
-            for (int e = tid; e < lim; e += kSpThreads) mine |= sp_make_key(acc[e], (uint32_t)(base + e)) > thr;
+            for (int e = tid * 4; e < lim; e += kSpThreads * 4) {
+                if (e + 3 < lim) {
+                    const float4 v = *reinterpret_cast<const float4 *>(acc + e);
+                    const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                    mine |= strict ? (m > thr_s) : (m >= thr_s);
+                } else {
+                    for (int r = e; r < lim; ++r) mine |= strict ? (acc[r] > thr_s) : (acc[r] >= thr_s);
+                }
+            }
             if (!__syncthreads_or(mine)) continue;
             for (int c0 = 0; c0 < lim; c0 += kSpThreads) {
                 if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
