@@ -58,6 +58,19 @@ def test_no_device_fails_loudly_not_silently():
     assert rc == N.E_CUDA
     rc = L.vqa_normalize_rows(buf, 4, 4, 4, buf, 4, None, 0, 0, 0, None)
     assert rc == N.E_CUDA
+    # the sparse (BM25) leg and the fusion refuse the same way
+    hs = ctypes.c_void_p()
+    assert L.vqa_sparse_create(ctypes.byref(hs), 10, 2, 3, 0) == N.E_CUDA and "no CPU fallback" in N.last_error()
+    dbl = (ctypes.c_double * 16)()
+    assert L.vqa_hybrid_fuse(buf, ids, 4, dbl, ids, 4, 1, 0.5, 0.5, 2, dbl, ids, 0, None) == N.E_CUDA
+    assert L.vqa_bm25_weights(ids, 1, ids, ids, 1, dbl, ids, 1.2, 0.75, 2.0, buf, 0, None) == N.E_CUDA
+    assert L.vqa_agree_f64(ids, dbl, ids, dbl, 4, 0.4, None, None, 0, None) == N.E_CUDA
+    from vietnamese_qa_system_b200.scoring import BM25
+
+    bm = BM25({"terms": True})
+    bm.build_postings([["a", "b"], ["a"]])       # host half works anywhere ...
+    with pytest.raises(N.VqaError):
+        bm.index([["a", "b"], ["a"]])            # ... scoring needs the device
 
 
 def test_argument_validation_precedes_device_use():
@@ -74,6 +87,13 @@ def test_argument_validation_precedes_device_use():
     ids = (ctypes.c_int64 * 16)()
     assert L.vqa_merge_topk(buf, ids, 1, 1, 4, 4096, buf, ids, 0, None) == N.E_INVALID  # k_out > 128
     assert L.vqa_pool_normalize(buf, 7, buf, N.I64, 1, 1, 8, 1, buf, 0, None) == N.E_INVALID
+    hs = ctypes.c_void_p()
+    assert L.vqa_sparse_create(ctypes.byref(hs), 2 ** 31, 1, 1, 0) == N.E_INVALID      # > 2^31 - 1 documents
+    assert L.vqa_sparse_create(None, 1, 1, 1, 0) == N.E_INVALID
+    assert L.vqa_sparse_search(None, None, None, None, 1, 1, 1, 1, 0, 0.0, None, None, None, 0, None) == N.E_INVALID
+    assert L.vqa_hybrid_fuse(None, None, 1, None, None, 1, 1, 0.5, 0.5, 1, None, None, 0, None) == N.E_INVALID
+    mt, mc = ctypes.c_int32(), ctypes.c_int32()
+    assert L.vqa_sparse_limits(ctypes.byref(mt), ctypes.byref(mc)) == N.OK and (mt.value, mc.value) == (64, 1024)
     with pytest.raises(ValueError):
         N.check(N.E_INVALID)
     with pytest.raises(NotImplementedError):
