@@ -170,6 +170,82 @@ def make_shard(torch, ops, n_local: int, seed: int, device):
     return rows
 
 
+def synth_postings(n_docs: int, avg_len: int, vocab: int, seed: int = 1):
+    """Zipf-distributed synthetic corpus laid out directly as CSR postings (term-major, positions ascending)."""
+    rng = np.random.default_rng(seed)
+    p = np.arange(1, vocab + 1, dtype=np.float64) ** -1.1
+    p /= p.sum()
+    terms = rng.choice(vocab, size=n_docs * avg_len, p=p).astype(np.int64)
+    docs = np.repeat(np.arange(n_docs, dtype=np.int64), avg_len)
+    key, freq = np.unique(terms * n_docs + docs, return_counts=True)
+    t, d = key // n_docs, key % n_docs
+    used, df = np.unique(t, return_counts=True)
+    offsets = np.zeros(len(used) + 1, np.int64)
+    np.cumsum(df, out=offsets[1:])
+    return offsets, d.astype(np.int32), freq.astype(np.int32), np.full(n_docs, avg_len, np.int32), \
+        [f"w{int(u)}" for u in used]
+
+
+def hybrid_leg_section(torch, ops, shard, q_dev, timed, with_cpu: bool):
+    """The extra work of ``hybrid=True`` (heavy_ranker.py:78-83) on top of the dense search: BM25 leg over a
+    synthetic 1 M-document term index + the fusion kernel, at the reference's ``limit = 1`` (10 candidates per
+    leg).  Reported next to the headline, never part of it."""
+    from vietnamese_qa_system_b200.scoring import BM25
+
+    n_docs, avg_len, limit = 1_000_000, 20, 1
+    cand = 10 * limit
+    offsets, docs, freqs, lengths, vocab = synth_postings(n_docs, avg_len, 100_000)
+    bm = BM25({"method": "bm25", "terms": True, "normalize": True})
+    bm.index_postings(offsets, docs, freqs, lengths, vocab)
+    df = np.diff(offsets)
+    rng = np.random.default_rng(2)
+    rare_ids = np.flatnonzero((df > 50) & (df <= 0.1 * n_docs))
+    common_ids = np.flatnonzero(df > 0.1 * n_docs)
+    batch = int(q_dev.shape[0])
+    qs = []
+    for _ in range(batch):                          # a question: four content words + one very common word
+        q = [vocab[int(i)] for i in rng.choice(rare_ids, 4, replace=False)]
+        if len(common_ids):
+            q.append(vocab[int(rng.choice(common_ids))])
+        qs.append(q)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        plan = bm.plan_queries(qs, cand)
+    plan_ms = (time.perf_counter() - t0) / 5 * 1e3
+    st = bm.stage_plan(*plan, cand)
+    sparse_ms = timed(lambda: bm.launch_staged(st), 50, 5) / 50
+    ss, sp = bm.launch_staged(st)
+    ds, di = shard.search(q_dev, cand, "fast")
+    fuse_ms = timed(lambda: ops.hybrid_fuse(ds, di, ss, sp, limit), 50, 5) / 50
+    q_terms, _, q_meta, _ = plan
+    posting_bytes = int(sum(int(df[q_terms[r, j]]) * 8 for r in range(batch) for j in range(int(q_meta[r, 0]))))
+    out = {"workload": f"BM25 leg over {n_docs} synthetic documents ({len(docs)} postings, {len(vocab)} terms), "
+                       f"batch {batch}, limit {limit} ({cand} candidates per leg) + dense/sparse fusion",
+           "sparse_kernels_ms": sparse_ms, "fuse_kernel_ms": fuse_ms, "host_planning_ms": plan_ms,
+           "sparse_qps_kernels": batch / sparse_ms * 1e3, "posting_bytes_per_batch": posting_bytes}
+    if with_cpu:
+        from oracle import sparse as osp  # checker / CPU baseline only
+
+        ref = osp.BM25()
+        ref.total, ref.avgdl = n_docs, float(bm.avgdl)
+        ref._lengths = lengths.astype(np.int64)
+        need = sorted({int(t) for t in q_terms.ravel() if t >= 0})
+        for t in need:                                 # only the queried terms' postings, as Python lists
+            lo, hi = int(offsets[t]), int(offsets[t + 1])
+            ref.postings[vocab[t]] = (docs[lo:hi].tolist(), freqs[lo:hi].tolist())
+            ref.idf[vocab[t]] = float(bm.idf_host[t])
+        ref.avgscore = bm.avgscore
+        nq = min(batch, 8)
+        t0 = time.perf_counter()
+        want = [ref.search(q, cand) for q in qs[:nq]]
+        cpu_ms = (time.perf_counter() - t0) / nq * 1e3
+        got = [[(int(p), float(x)) for p, x in zip(ir, sr) if p >= 0]
+               for sr, ir in zip(ss[:nq].cpu().tolist(), sp[:nq].cpu().tolist())]
+        out.update({"cpu_ms_per_query_numpy_restatement": cpu_ms, "cpu_qps": 1e3 / cpu_ms,
+                    "results_identical_to_cpu_restatement": bool(got == want), "cpu_queries_checked": nq})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -380,6 +456,14 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             config_a = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- hybrid=True's extra work (BM25 leg + fusion), reported beside the dense headline ----
+    hybrid = None
+    if rank == 0 and world == 1 and args.sweep:
+        try:
+            hybrid = hybrid_leg_section(torch, ops, shard, q_dev, timed, with_cpu=not args.no_cpu)
+        except Exception as exc:  # noqa: BLE001
+            hybrid = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -406,7 +490,7 @@ def run_ours(args):
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": K * (launches + merge_launches),
             "recall_at_10": recall, "recall_at_10_batch256": recall_b256, "fast_vs_verify_max_rel_score_err": max_rel,
-            "sweep": sweep, "pool_k1": pool, "config_a_reference_scale": config_a,
+            "sweep": sweep, "pool_k1": pool, "config_a_reference_scale": config_a, "hybrid_leg": hybrid,
             "lib": f"libvqa_b200.so v{vqa._native.lib().vqa_version()}",
         }
         print(json.dumps(line), flush=True)
