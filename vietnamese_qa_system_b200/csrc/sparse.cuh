@@ -8,11 +8,12 @@
 //
 // Here the postings live in HBM as CSR (offsets int64[T+1], docs int32[P] ascending per term,
 // weights fp32[P] = the BM25 weight of that (term, document) pair) and the score array never
-// exists in memory: a CTA owns a run of 16 K-document tiles, finds each query term's posting
-// sub-range for the tile by binary search, accumulates the tile's scores in SHARED memory in the
-// query's term order (fp32 multiply then add, no contraction: bit-identical to the CPU
-// accumulation) and selects from the tile straight away.  HBM traffic = the query terms' postings,
-// read once, coalesced (8 bytes per posting).
+// exists in memory: a CTA owns a contiguous document range, finds each query term's posting
+// sub-range for it by binary search and either (few postings) sorts them by position in shared
+// memory and sums each position's run, or (many) accumulates 16 K-document score tiles in SHARED
+// memory -- in both cases in the query's term order with fp32 multiply then add, no contraction:
+// bit-identical to the CPU accumulation -- and selects straight away.  HBM traffic = the query
+// terms' postings, read once, coalesced (8 bytes per posting).
 //
 // Selection: candidates are 64-bit keys (order-preserving score bits << 32 | ~position), so one
 // unsigned compare implements "score descending, ties -> lower position".  A CTA keeps its best
@@ -173,8 +174,10 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
     extern __shared__ __align__(16) unsigned char sp_smem[];
     float *acc = reinterpret_cast<float *>(sp_smem);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sp_smem + (size_t)kSpTile * sizeof(float));
-    int *bound = reinterpret_cast<int *>(keys + kSpSort);  // [n_rare][group + 1] <= kSpBoundSlots, relative to the term's first posting
-    long long *crange = reinterpret_cast<long long *>(bound + kSpBoundSlots);  // [2 * kSpMaxTerms] posting range of each term in this CTA's documents
+    // bound: [n_rare][group + 1] <= kSpBoundSlots posting offsets at tile edges, relative to the term's first posting
+    int *bound = reinterpret_cast<int *>(keys + kSpSort);
+    // crange: [2 * kSpMaxTerms] posting range of each term inside this CTA's document range
+    long long *crange = reinterpret_cast<long long *>(bound + kSpBoundSlots);
     __shared__ int s_count;
 
     const int tid = threadIdx.x;
@@ -273,79 +276,81 @@ __global__ void __launch_bounds__(kSpThreads) sparse_scan_kernel(SparseParams p)
             }
         }
     } else {
-    // ---- many postings: dense score tiles.  Tile edges whose posting offsets fit the shared-memory table at once
-    const int group = max(1, min(p.tiles_per_cta, kSpBoundSlots / max(n_rare, 1) - 1));
-    for (long long g0 = first_tile; g0 < last_tile; g0 += group) {
-        const int ng = (int)min((long long)group, last_tile - g0);
-        // posting boundaries of every term at the ng + 1 tile edges of this group (independent binary
-        // searches, one per thread, all in flight together)
-        for (int w = tid; w < n_rare * (ng + 1); w += kSpThreads) {
-            const int j = w / (ng + 1), t = w - j * (ng + 1);
-            long long lo, hi;
-            sp_term_range(p, terms[j], lo, hi);
-            const long long edge = (g0 + t) * (long long)kSpTile;
-            bound[j * (group + 1) + t] = (int)(sp_lower_bound(p.docs, crange[2 * j], crange[2 * j + 1], edge) - lo);
-        }
-        __syncthreads();
-        for (int t = 0; t < ng; ++t) {
-            const long long base = (g0 + t) * (long long)kSpTile;
-            const int lim = (int)min((long long)kSpTile, p.n_docs - base);
-            bool any = false;
-            for (int j = 0; j < n_rare; ++j) any |= bound[j * (group + 1) + t + 1] > bound[j * (group + 1) + t];
-            // a tile without postings holds only zero scores: none can enter once the threshold is at or
-            // above (0, first position of the tile) (uniform decision)
-            if (!any && sp_make_key(0.0f, (uint32_t)base) <= thr) continue;
-            for (int e = tid * 4; e < lim; e += kSpThreads * 4)  // lim <= kSpTile: the 16-byte store stays inside the tile
-                *reinterpret_cast<float4 *>(acc + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        // ---- many postings: dense score tiles.  `group` = tile edges whose posting offsets fit the
+        // shared-memory table at once
+        const int group = max(1, min(p.tiles_per_cta, kSpBoundSlots / max(n_rare, 1) - 1));
+        for (long long g0 = first_tile; g0 < last_tile; g0 += group) {
+            const int ng = (int)min((long long)group, last_tile - g0);
+            // posting boundaries of every term at the ng + 1 tile edges of this group (independent binary
+            // searches, one per thread, all in flight together)
+            for (int w = tid; w < n_rare * (ng + 1); w += kSpThreads) {
+                const int j = w / (ng + 1), t = w - j * (ng + 1);
+                long long lo, hi;
+                sp_term_range(p, terms[j], lo, hi);
+                const long long edge = (g0 + t) * (long long)kSpTile;
+                bound[j * (group + 1) + t] = (int)(sp_lower_bound(p.docs, crange[2 * j], crange[2 * j + 1], edge) - lo);
+            }
             __syncthreads();
-            for (int j = 0; j < n_rare; ++j) {
-                const int a = bound[j * (group + 1) + t], z = bound[j * (group + 1) + t + 1];
-                if (z > a) {  // uniform
-                    const long long off = p.offsets[terms[j]];  // z > a implies a valid term
-                    const float qf = freqs[j];
-                    constexpr int U = 4;  // postings per thread whose loads are in flight together
-                    for (int p0 = a; p0 < z; p0 += U * kSpThreads) {
-                        int dd[U];
-                        float ww[U];
+            for (int t = 0; t < ng; ++t) {
+                const long long base = (g0 + t) * (long long)kSpTile;
+                const int lim = (int)min((long long)kSpTile, p.n_docs - base);
+                bool any = false;
+                for (int j = 0; j < n_rare; ++j) any |= bound[j * (group + 1) + t + 1] > bound[j * (group + 1) + t];
+                // a tile without postings holds only zero scores: none can enter once the threshold is at or
+                // above (0, first position of the tile) (uniform decision)
+                if (!any && sp_make_key(0.0f, (uint32_t)base) <= thr) continue;
+                // lim <= kSpTile, so the 16-byte stores stay inside the tile buffer
+                for (int e = tid * 4; e < lim; e += kSpThreads * 4)
+                    *reinterpret_cast<float4 *>(acc + e) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                __syncthreads();
+                for (int j = 0; j < n_rare; ++j) {
+                    const int a = bound[j * (group + 1) + t], z = bound[j * (group + 1) + t + 1];
+                    if (z > a) {  // uniform
+                        const long long off = p.offsets[terms[j]];  // z > a implies a valid term
+                        const float qf = freqs[j];
+                        constexpr int U = 4;  // postings per thread whose loads are in flight together
+                        for (int p0 = a; p0 < z; p0 += U * kSpThreads) {
+                            int dd[U];
+                            float ww[U];
 #pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const int pp = p0 + u * kSpThreads + tid;
-                            dd[u] = pp < z ? __ldg(p.docs + off + pp) - (int)base : -1;
-                            ww[u] = pp < z ? __ldg(p.weights + off + pp) : 0.0f;
+                            for (int u = 0; u < U; ++u) {
+                                const int pp = p0 + u * kSpThreads + tid;
+                                dd[u] = pp < z ? __ldg(p.docs + off + pp) - (int)base : -1;
+                                ww[u] = pp < z ? __ldg(p.weights + off + pp) : 0.0f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+                                // a document appears once per term: no two threads touch the same slot
+                                if (dd[u] >= 0) acc[dd[u]] = __fadd_rn(acc[dd[u]], __fmul_rn(qf, ww[u]));
                         }
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            // a document appears once per term: no two threads touch the same slot
-                            if (dd[u] >= 0) acc[dd[u]] = __fadd_rn(acc[dd[u]], __fmul_rn(qf, ww[u]));
+                        __syncthreads();
                     }
-                    __syncthreads();
+                }
+                // Common case: nothing in the tile beats the threshold -> one barrier.  Screened on the score
+                // alone (a float compare per element, 16-byte loads): in a tile that lies wholly after the
+                // threshold's position an equal score loses the tie, so the compare is strict there.
+                const float thr_s = sp_key_score(thr);
+                const bool strict = (uint32_t)base >= sp_key_doc(thr);
+                bool mine = false;
+                for (int e = tid * 4; e < lim; e += kSpThreads * 4) {
+                    if (e + 3 < lim) {
+                        const float4 v = *reinterpret_cast<const float4 *>(acc + e);
+                        const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                        mine |= strict ? (m > thr_s) : (m >= thr_s);
+                    } else {
+                        for (int r = e; r < lim; ++r) mine |= strict ? (acc[r] > thr_s) : (acc[r] >= thr_s);
+                    }
+                }
+                if (!__syncthreads_or(mine)) continue;
+                for (int c0 = 0; c0 < lim; c0 += kSpThreads) {
+                    if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
+                    const int e = c0 + tid;
+                    const bool have = e < lim;
+                    sp_offer(keys, count, thr, &s_count, have, have ? sp_make_key(acc[e], (uint32_t)(base + e)) : 0ull);
                 }
             }
-            // Common case: nothing in the tile beats the threshold -> one barrier.  Screened on the score
-            // alone (a float compare per element, 16-byte loads): in a tile that lies wholly after the
-            // threshold's position an equal score loses the tie, so the compare is strict there.
-            const float thr_s = sp_key_score(thr);
-            const bool strict = (uint32_t)base >= sp_key_doc(thr);
-            bool mine = false;
-            for (int e = tid * 4; e < lim; e += kSpThreads * 4) {
-                if (e + 3 < lim) {
-                    const float4 v = *reinterpret_cast<const float4 *>(acc + e);
-                    const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-                    mine |= strict ? (m > thr_s) : (m >= thr_s);
-                } else {
-                    for (int r = e; r < lim; ++r) mine |= strict ? (acc[r] > thr_s) : (acc[r] >= thr_s);
-                }
-            }
-            if (!__syncthreads_or(mine)) continue;
-            for (int c0 = 0; c0 < lim; c0 += kSpThreads) {
-                if (count + kSpThreads > kSpSort) sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
-                const int e = c0 + tid;
-                const bool have = e < lim;
-                sp_offer(keys, count, thr, &s_count, have, have ? sp_make_key(acc[e], (uint32_t)(base + e)) : 0ull);
-            }
+            __syncthreads();  // bound[] is rewritten by the next group
         }
-        __syncthreads();  // bound[] is rewritten by the next group
-    }
     }
     sp_flush(keys, count, k_cand, thr, &s_count, floor_key);
     unsigned long long *out = p.cand + ((size_t)b * p.ctas_per_query + blockIdx.x) * p.kcap;
