@@ -155,3 +155,53 @@ def test_query_planning_limits():
     bm2.build_postings([["r%d" % i, "c"] for i in range(3000)])
     with pytest.raises(ValueError):
         bm2.plan_queries([["r1", "c"]], 300)                     # 5 x 300 candidates > 1024
+
+
+# ---- the oracle against the textbook definition (independent code path) ---------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+def definitional_scores(docs, query, k1=1.2, b=0.75):
+    """BM25 straight from the formula, document by document (no postings, no arrays): fp32 weight per
+    (term, document), fp32 accumulation in the query's first-occurrence order."""
+    n = len(docs)
+    avgdl = sum(len(d) for d in docs) / n
+    out = []
+    for d in docs:
+        s = np.float32(0.0)
+        for term, qf in Counter(query).items():
+            df = sum(1 for x in docs if term in x)
+            tf = d.count(term)
+            if df == 0 or tf == 0:
+                continue
+            idf = float(np.log(1 + (n - df + 0.5) / (df + 0.5)))
+            k = k1 * ((1 - b) + b * len(d) / avgdl)
+            w = np.float32(idf * (tf * (k1 + 1)) / (tf + k))
+            s = np.float32(s + np.float32(np.float32(qf) * w))
+        out.append(float(s))
+    return out
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 10_000), st.integers(12, 60), st.integers(3, 12))
+def test_oracle_equals_definition_when_no_term_is_deferred(seed, n_docs, vocab):
+    rng = np.random.default_rng(seed)
+    docs = [[f"t{int(x)}" for x in rng.integers(0, vocab, int(rng.integers(1, 9)))] for _ in range(n_docs)]
+    query = [f"t{int(x)}" for x in rng.integers(0, vocab + 2, int(rng.integers(1, 5)))]
+    bm = osp.BM25(normalize=False, cutoff=1.0).index(docs)          # cutoff 1.0: nothing is "common"
+    want = definitional_scores(docs, query)
+    order = sorted((i for i in range(n_docs) if want[i] > 0), key=lambda i: (-want[i], i))
+    got = bm.search(query, n_docs)
+    assert got == [(i, want[i]) for i in order]
+    assert bm.search(query, 3) == [(i, want[i]) for i in order[:3]]
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 10_000))
+def test_only_common_terms_are_scored_over_all_documents(seed):
+    rng = np.random.default_rng(seed)
+    docs = [["c"] * int(rng.integers(1, 4)) + [f"r{int(x)}" for x in rng.integers(0, 50, 3)] for _ in range(40)]
+    bm = osp.BM25(normalize=False).index(docs)                       # "c" is in every document -> deferred
+    want = definitional_scores(docs, ["c"])
+    order = sorted(range(40), key=lambda i: (-want[i], i))
+    assert bm.search(["c"], 7) == [(i, want[i]) for i in order[:7]]
