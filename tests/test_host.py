@@ -153,3 +153,45 @@ def test_sharded_search_gloo_world2(n, k):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_heavy_ranker_build_and_load_orchestration(tmp_path):
+    """heavy_ranker.py:70-94 as HeavyRanker.build / .load, with a recording stand-in for Embeddings (the
+    device-backed class is exercised by the GPU tests)."""
+    from vietnamese_qa_system_b200 import corpus
+    from vietnamese_qa_system_b200.ranker import REFERENCE_INDEXES, HeavyRanker, load_passages
+
+    path = str(tmp_path / "documents.db")
+    docs = corpus.insert_doc(path, texts=["Hà_Nội là thủ_đô. " * 40, "Sông Hồng chảy qua Hà_Nội. " * 30])
+    rows = load_passages(path)
+    assert [r["id"] for r in rows] == list(range(1, len(docs) + 1)) and [r["text"] for r in rows] == docs
+    assert set(rows[0]) == {"id", "text", "source"}                                   # heavy_ranker.py:76
+
+    calls = []
+
+    class Recorder:
+        def __init__(self, **cfg):
+            self.cfg = cfg
+            calls.append(("init", cfg))
+
+        def index(self, data):
+            calls.append(("index", len(data)))
+
+        def save(self, p):
+            calls.append(("save", p))
+
+        def load(self, p):
+            calls.append(("load", p))
+
+    hr = HeavyRanker.build(path, str(tmp_path / "ix"), embeddings_cls=Recorder, dtype="fp32",
+                           transform={"mini_lm": "enc384", "mpnet": "enc768"})
+    assert [c[0] for c in calls] == ["init", "index", "save", "init", "index", "save"]
+    assert calls[0][1] == {**REFERENCE_INDEXES["mini_lm"], "dtype": "fp32", "transform": "enc384"}
+    assert calls[3][1] == {**REFERENCE_INDEXES["mpnet"], "dtype": "fp32", "transform": "enc768"}
+    assert calls[0][1]["hybrid"] is True and calls[0][1]["content"] is True          # :78-83
+    assert calls[1] == ("index", len(docs)) and calls[2] == ("save", str(tmp_path / "ix" / "mini_lm"))
+    assert hr.database_path == path and hr.threshold == 0.4
+    calls.clear()
+    HeavyRanker.load(path, str(tmp_path / "ix"), embeddings_cls=Recorder)
+    assert calls == [("init", {}), ("load", str(tmp_path / "ix" / "mini_lm")),
+                     ("init", {}), ("load", str(tmp_path / "ix" / "mpnet"))]

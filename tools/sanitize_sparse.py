@@ -3,7 +3,6 @@ usage: compute-sanitizer --tool memcheck|racecheck|synccheck python tools/saniti
 import os
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

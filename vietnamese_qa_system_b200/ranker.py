@@ -14,9 +14,25 @@ from typing import Any, Dict, List, Optional, Sequence
 
 import torch
 
+import os
+
 from . import ops
-from .db import fetch_docs
+from .db import fetch_docs, query
 from .embeddings import Embeddings
+
+# heavy_ranker.py:78-83 -- the two encoders and the configuration the reference builds its indexes with
+REFERENCE_INDEXES = {
+    "mini_lm": {"hybrid": True, "content": True,
+                "path": "sentence-transformers/paraphrase-multilingual-MiniLM-L12-v2"},
+    "mpnet": {"hybrid": True, "content": True,
+              "path": "sentence-transformers/paraphrase-multilingual-mpnet-base-v2"},
+}
+
+
+def load_passages(database_path: str, fetch_size: int = 50000) -> List[Dict[str, Any]]:
+    """``documents.db`` rows as the dicts the reference indexes (heavy_ranker.py:70-76)."""
+    data = query(database_path, query_string="SELECT * FROM documents", fetch_size=fetch_size)
+    return [{"id": row[0], "text": row[1], "source": row[2]} for row in data]
 
 # src/data/configs/response_template.py:285 (NO_DOCS_MESSAGE1, what get_no_docs_msg(id=1) returns)
 NO_DOCS_MESSAGE = " Không documents nào có điểm đủ cao để query cho câu hỏi. "
@@ -37,6 +53,37 @@ class HeavyRanker:
         self.a, self.b = embeddings_a, embeddings_b
         self.database_path = database_path
         self.threshold = float(threshold)
+
+    @classmethod
+    def build(cls, database_path: str, index_dir: str, configs: Optional[Dict[str, dict]] = None,
+              embeddings_cls=Embeddings, threshold: float = 0.4, **overrides) -> "HeavyRanker":
+        """The build half of heavy_ranker.py (:70-89): read the passages, index them with each of the two
+        configurations, save under ``index_dir/<name>``.  ``overrides`` (e.g. ``transform=``, ``dtype=``) are
+        merged into both configurations."""
+        configs = configs or REFERENCE_INDEXES
+        if len(configs) != 2:
+            raise ValueError("the agreement rule (heavy_ranker.py:110) is defined over exactly two indexes")
+        data_str = load_passages(database_path)
+        built = []
+        for name, cfg in configs.items():
+            per = {k: (v[name] if isinstance(v, dict) and set(v) == set(configs) else v) for k, v in overrides.items()}
+            emb = embeddings_cls(**{**cfg, **per})
+            emb.index(data_str)
+            emb.save(os.path.join(index_dir, name))
+            built.append(emb)
+        return cls(built[0], built[1], database_path=database_path, threshold=threshold)
+
+    @classmethod
+    def load(cls, database_path: str, index_dir: str, names=("mini_lm", "mpnet"), embeddings_cls=Embeddings,
+             threshold: float = 0.4, **overrides) -> "HeavyRanker":
+        """The load half (heavy_ranker.py:91-94)."""
+        loaded = []
+        for name in names:
+            per = {k: (v[name] if isinstance(v, dict) and set(v) == set(names) else v) for k, v in overrides.items()}
+            emb = embeddings_cls(**per)
+            emb.load(os.path.join(index_dir, name))
+            loaded.append(emb)
+        return cls(loaded[0], loaded[1], database_path=database_path, threshold=threshold)
 
     def rank(self, queries_a: Any, queries_b: Any = None, limit: int = 1) -> List[Dict[str, Any]]:
         """``queries_a`` / ``queries_b``: the same queries as each index's encoder sees them (texts, or
