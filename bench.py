@@ -446,7 +446,28 @@ def run_ours(args):
             for _ in range(10):
                 oracle.np_search_fast(docs_a, q_a, 5)
             batch_ms = (time.perf_counter() - t0) / 10 * 1e3
+            docs_t, q_t = torch.from_numpy(docs_a), torch.from_numpy(q_a)      # (ii) torch CPU mm + topk, all cores
+            torch.set_num_threads(os.cpu_count() or 1)
+            torch.topk(q_t @ docs_t.T, 5, dim=1)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                torch.topk(q_t @ docs_t.T, 5, dim=1)
+            torch_ms = (time.perf_counter() - t0) / 20 * 1e3
+            try:
+                import faiss  # noqa: F401  (iii) what txtai would use; not in this image
+
+                faiss_note = "importable (not timed)"
+            except Exception:  # noqa: BLE001
+                faiss_note = "not installed in this image: IndexFlatIP / IVF256,Flat legs skipped"
+            cpu_model = ""
+            try:
+                with open("/proc/cpuinfo") as f:
+                    cpu_model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
+            except OSError:
+                pass
             config_a = {"workload": "10k x 768 fp32 docs, 64 queries, top-5, fp32 verify mode",
+                        "cpu_ms_torch_mm_topk": torch_ms, "cpu_qps_torch_mm_topk": 64 / torch_ms * 1e3,
+                        "torch_threads": torch.get_num_threads(), "cpu_model": cpu_model, "faiss": faiss_note,
                         "ids_bit_identical_to_oracle": ids_exact, "score_bits_identical_to_oracle": bits_exact,
                         "gpu_ms_device_resident": gms, "gpu_ms_host_buffers": hms,
                         "gpu_qps_host_buffers": 64 / hms * 1e3,
