@@ -206,6 +206,7 @@ class BM25:
             k = self.k1 * ((1 - self.b) + self.b * self.avgdl / self.avgdl)
             self.avgscore = float(self.avgidf * (self.avgfreq * (self.k1 + 1)) / (self.avgfreq + k))
         self._df = df
+        self._common = None
 
     def _upload(self) -> None:
         """Device half of ``index`` / ``load``: postings to HBM, BM25 weight per posting (``vqa_bm25_weights``)."""
@@ -243,32 +244,50 @@ class BM25:
         N.lib().vqa_sparse_limits(ctypes.byref(lims[0]), ctypes.byref(lims[1]))
         max_terms, max_cand = lims[0].value, lims[1].value
         n = self.total
-        plans = []
+        common_flag = self._common_flag()
+        vocab_get = self.vocab.get
+        t_rows, f_rows, meta, width, kmax = [], [], [], 1, 1
         for q in queries:
-            rare, common = [], []
+            rare_t, rare_f, com_t, com_f = [], [], [], []
             for term, freq in Counter(self.tokenize(q)).items():
-                tid = self.vocab.get(term)
+                tid = vocab_get(term)
                 if tid is None:
                     continue
-                (rare if self._df[tid] <= self.cutoff * n else common).append((tid, freq))
-            if not rare:  # only common terms: they are scored over all their documents
-                rare, common = common, []
-            if len(rare) + len(common) > max_terms:
-                raise ValueError(f"a query may hold at most {max_terms} distinct indexed terms; "
-                                 f"got {len(rare) + len(common)}")
-            k_cand = max(1, min(n, limit * 5 if common else limit))
+                if common_flag[tid]:
+                    com_t.append(tid)
+                    com_f.append(freq)
+                else:
+                    rare_t.append(tid)
+                    rare_f.append(freq)
+            if not rare_t:  # only common terms: they are scored over all their documents
+                rare_t, rare_f, com_t, com_f = com_t, com_f, [], []
+            total = len(rare_t) + len(com_t)
+            if total > max_terms:
+                raise ValueError(f"a query may hold at most {max_terms} distinct indexed terms; got {total}")
+            k_cand = max(1, min(n, limit * 5 if com_t else limit))
             if k_cand > max_cand:
                 raise ValueError(f"limit {limit} needs {k_cand} sparse candidates; at most {max_cand} supported")
-            plans.append((rare, common, k_cand))
-        width = max(1, max(len(r) + len(c) for r, c, _ in plans))
-        q_terms = np.full((len(plans), width), -1, dtype=np.int32)
-        q_freqs = np.zeros((len(plans), width), dtype=np.float32)
-        q_meta = np.zeros((len(plans), _META_STRIDE), dtype=np.int32)
-        for i, (rare, common, k_cand) in enumerate(plans):
-            for j, (tid, freq) in enumerate(rare + common):
-                q_terms[i, j], q_freqs[i, j] = tid, freq
-            q_meta[i, :3] = (len(rare), len(common), k_cand)
-        return q_terms, q_freqs, q_meta, max(p[2] for p in plans)
+            t_rows.append(rare_t + com_t)
+            f_rows.append(rare_f + com_f)
+            meta.append((len(rare_t), len(com_t), k_cand, 0))
+            width = max(width, total)
+            kmax = max(kmax, k_cand)
+        for tr, fr in zip(t_rows, f_rows):  # pad the rows: one array conversion instead of per-element stores
+            pad = width - len(tr)
+            if pad:
+                tr.extend([-1] * pad)
+                fr.extend([0] * pad)
+        q_terms = np.asarray(t_rows, dtype=np.int32).reshape(len(t_rows), width)
+        q_freqs = np.asarray(f_rows, dtype=np.float32).reshape(len(f_rows), width)
+        q_meta = np.asarray(meta, dtype=np.int32).reshape(len(meta), _META_STRIDE)
+        return q_terms, q_freqs, q_meta, kmax
+
+    def _common_flag(self) -> List[bool]:
+        """Per term: document frequency above ``cutoff * N`` (txtai ``Terms``: such terms are deferred)."""
+        flags = getattr(self, "_common", None)
+        if flags is None or len(flags) != len(self._df):
+            flags = self._common = (self._df > self.cutoff * self.total).tolist()
+        return flags
 
     def search_tensors(self, queries: Sequence[Any], limit: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Device-resident sparse search: ``(scores float64 [B, limit], positions int64 [B, limit])``;
