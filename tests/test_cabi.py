@@ -109,3 +109,47 @@ def test_product_never_imports_the_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), fn
                 assert "liboracle" not in src, fn
+
+
+def test_ctypes_bindings_match_header_prototypes():
+    """Every prototype in include/vqa.h against the ctypes binding: same parameter count, pointer parameters
+    bound as pointers, double as c_double, integer widths as declared (catches binding drift)."""
+    with open(os.path.join(ROOT, "include", "vqa.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    protos = re.findall(r"VQA_API\s+[\w\s\*]+?\b(vqa_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(N.EXPORTS)
+    L = N.lib()
+    for name, params in protos:
+        params = " ".join(params.split())
+        plist = [] if params in ("void", "") else [p.strip() for p in params.split(",")]
+        fn = getattr(L, name)
+        assert fn.argtypes is not None and len(fn.argtypes) == len(plist), (name, plist, fn.argtypes)
+        for decl, ct in zip(plist, fn.argtypes):
+            if "*" in decl:
+                assert ct is ctypes.c_void_p or hasattr(ct, "contents") or ct is ctypes.c_char_p, (name, decl, ct)
+            elif decl.startswith("double"):
+                assert ct is ctypes.c_double, (name, decl)
+            elif decl.startswith("int64_t"):
+                assert ct is ctypes.c_int64, (name, decl)
+            elif decl.startswith("int32_t"):
+                assert ct is ctypes.c_int32, (name, decl)
+            elif decl.startswith("uint64_t"):
+                assert ct is ctypes.c_uint64, (name, decl)
+            elif decl.startswith("size_t"):
+                assert ct is ctypes.c_size_t, (name, decl)
+            else:
+                raise AssertionError(f"unhandled parameter type in {name}: {decl}")
+
+
+def test_no_kernel_spills_registers_in_a_hot_loop():
+    """ptxas' own accounting of the last build (build/*.ptxas.log): no kernel may spill more than a few bytes.
+    (A fixed 4-token unroll once made the 768-dim bf16 pooling kernel spill ~400 bytes per thread inside its
+    streaming loop without anyone noticing, because the warning was not surfaced.)"""
+    from vietnamese_qa_system_b200 import build as vbuild
+
+    rep = vbuild.spill_report()
+    if not rep:
+        pytest.skip("no ptxas logs next to the library (prebuilt .so)")
+    assert len(rep) >= 80                                  # every kernel instantiation is accounted for
+    worst = {k: v for k, v in rep.items() if v[1] > 32 or v[2] > 32}
+    assert not worst, worst

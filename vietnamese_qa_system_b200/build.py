@@ -35,12 +35,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(BUILD, exist_ok=True)
     flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
-             "-Xptxas", "-v" if verbose else "-warn-spills"] + ARCH
+             "-Xptxas", "-v"] + ARCH
 
     def compile_one(src: str) -> str:
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
         cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj] + flags
         r = subprocess.run(cmd, capture_output=True, text=True)
+        # per-kernel registers / shared memory / spills of this translation unit (read by spill_report())
+        with open(os.path.join(BUILD, src.replace(".cu", ".ptxas.log")), "w") as f:
+            f.write(r.stdout + r.stderr)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode != 0:
@@ -54,7 +57,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    for name, (regs, st, ld) in sorted(spill_report().items()):
+        if st or ld:  # never silent: a spill inside a streaming loop costs real bandwidth
+            sys.stderr.write(f"[vqa build] register spills: {name}: {st} B stores / {ld} B loads at {regs} registers\n")
     return LIB
+
+
+def spill_report() -> dict:
+    """{mangled kernel name: (registers, spill store bytes, spill load bytes)} from the last build's ptxas logs."""
+    import re
+
+    out = {}
+    if not os.path.isdir(BUILD):
+        return out
+    for fn in sorted(os.listdir(BUILD)):
+        if not fn.endswith(".ptxas.log"):
+            continue
+        with open(os.path.join(BUILD, fn)) as f:
+            txt = f.read()
+        for block in re.split(r"ptxas info\s+: Compiling entry function '", txt)[1:]:
+            name = block.split("'")[0]
+            regs = re.search(r"Used (\d+) registers", block)
+            sp = re.search(r"(\d+) bytes spill stores, (\d+) bytes spill loads", block)
+            if regs and sp:
+                out[name] = (int(regs.group(1)), int(sp.group(1)), int(sp.group(2)))
+    return out
 
 
 if __name__ == "__main__":

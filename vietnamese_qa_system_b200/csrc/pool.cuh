@@ -131,18 +131,24 @@ __device__ __forceinline__ float mask_at(const void *m, int mdt, long long idx) 
 }
 
 // Fast path (row of <= ITERS*512 bytes): one warp per TOKEN, lanes stride over the row's 16-byte
-// chunks, 4 tokens in flight per warp (ITERS*4 independent 128-bit loads per lane), 16 warps per CTA
+// chunks, up to 4 tokens in flight per warp (as many as the register budget holds: ITERS * kPoolUnroll
+// independent 128-bit loads per lane, 6 at dim 768 bf16), 16 warps per CTA
 // splitting the sequence, fp32 partial sums combined through shared memory.  grid = B.
 // dynamic smem: (16 + 1) * dim + 32 + 16 floats.
 constexpr int kPoolFastThreads = 512;
 constexpr int kPoolWarps = kPoolFastThreads / 32;
-constexpr int kPoolUnroll = 4;
 
 template <typename T, int ITERS>
 __global__ void __launch_bounds__(kPoolFastThreads, (ITERS * (16 / (int)sizeof(T)) <= 24) ? 2 : 1)
 pool_normalize_warp_kernel(const unsigned char *__restrict__ hidden, const void *__restrict__ mask, int mdt, int seq,
                            int dim, int normalize, float *__restrict__ out) {
     constexpr int E = Elem<T>::E;
+    // Tokens in flight per warp: the 16-byte loads (4 registers each) of kPoolUnroll tokens plus the ITERS * E
+    // accumulators must fit the register budget (64 per thread at 2 CTAs per SM, 128 at 1) -- with a fixed 4
+    // the 768-dim bf16 instantiation spilled ~400 bytes per thread inside the token loop.
+    constexpr int kRegBudget = (ITERS * E <= 24) ? 44 : 100;
+    constexpr int kFit = (kRegBudget - ITERS * E) / (ITERS * 4);
+    constexpr int kPoolUnroll = kFit < 1 ? 1 : (kFit > 4 ? 4 : kFit);
     extern __shared__ __align__(16) unsigned char smem[];
     float *part = reinterpret_cast<float *>(smem);          // [kPoolWarps][dim]
     float *pooled = part + (size_t)kPoolWarps * dim;        // [dim]
