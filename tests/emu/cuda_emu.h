@@ -1,0 +1,321 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE: a single-OS-thread functional emulator of the CUDA subset the
+// CUDA-core kernels of this repository use (1-D thread blocks, __syncthreads and its count/or forms,
+// full-mask warp collectives, shared-memory atomics, streaming loads, IEEE intrinsics).
+//
+// Every CUDA thread of a block is a ucontext fiber; a barrier or a warp collective yields to the next
+// fiber until the rendezvous completes.  Fibers run in thread order and only switch at barriers /
+// collectives / spin waits, which is an adversarial schedule for a missing __syncthreads (thread 0 runs a
+// whole phase before thread 1 starts), and makes every run deterministic.  A rendezvous that cannot
+// complete (divergent barrier) is reported as a deadlock instead of hanging.
+//
+// Nothing under vietnamese_qa_system_b200/ includes this file; tests/emu/build.py compiles the product's
+// kernel headers against it (after a mechanical source transform of `extern __shared__` declarations and
+// the three inline-PTX helpers) into tests/emu/_build/libvqa_emu.so for the CPU tests.
+#pragma once
+#include <cuda_runtime.h>  // vector types, dim3, qualifiers as host no-ops
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#undef __shared__
+#define __shared__ static
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+
+namespace emu {
+
+constexpr int kMaxThreads = 1024;
+constexpr size_t kStackBytes = 256 * 1024;
+
+struct Fiber {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    bool done = true;
+};
+
+struct State {
+    Fiber f[kMaxThreads];
+    ucontext_t sched;
+    int cur = 0, n = 0, alive = 0;
+    std::function<void()> body;
+    // block barrier
+    int bar_arrived = 0, bar_gen = 0, acc_cnt = 0, acc_or = 0, res_cnt = 0, res_or = 0;
+    // warp collectives
+    int w_arrived[kMaxThreads / 32] = {}, w_gen[kMaxThreads / 32] = {};
+    unsigned long long wbuf[kMaxThreads / 32][32] = {};
+    long progress = 0;
+    std::string error;
+    // dynamic shared memory of the running block
+    alignas(128) unsigned char dyn_smem[232 * 1024];
+};
+inline State &S() {
+    static State s;
+    return s;
+}
+
+inline void yield() {
+    State &s = S();
+    swapcontext(&s.f[s.cur].ctx, &s.sched);
+}
+
+inline void complete_barrier(State &s) {
+    s.res_cnt = s.acc_cnt;
+    s.res_or = s.acc_or;
+    s.acc_cnt = s.acc_or = 0;
+    s.bar_arrived = 0;
+    ++s.bar_gen;
+    ++s.progress;
+}
+
+inline void block_barrier(int pred) {
+    State &s = S();
+    const int gen = s.bar_gen;
+    s.acc_cnt += pred != 0;
+    s.acc_or |= pred != 0;
+    if (++s.bar_arrived == s.alive) complete_barrier(s);
+    else
+        while (s.bar_gen == gen) yield();
+}
+
+inline void warp_barrier() {
+    State &s = S();
+    const int w = s.cur >> 5;
+    const int gen = s.w_gen[w];
+    if (++s.w_arrived[w] == 32) {
+        s.w_arrived[w] = 0;
+        ++s.w_gen[w];
+        ++s.progress;
+    } else
+        while (s.w_gen[w] == gen) yield();
+}
+
+template <typename T>
+inline void warp_gather(T v, T (&all)[32]) {
+    static_assert(sizeof(T) <= 8, "warp collectives carry at most 8 bytes");
+    State &s = S();
+    const int w = s.cur >> 5, l = s.cur & 31;
+    s.wbuf[w][l] = 0;
+    std::memcpy(&s.wbuf[w][l], &v, sizeof(T));
+    warp_barrier();
+    for (int i = 0; i < 32; ++i) std::memcpy(&all[i], &s.wbuf[w][i], sizeof(T));
+    warp_barrier();
+}
+
+inline void trampoline() {
+    State &s = S();
+    try {
+        s.body();
+    } catch (const std::exception &e) {  // an exception must not unwind past the fiber's first frame
+        if (s.error.empty()) s.error = e.what();
+    }
+    s.f[s.cur].done = true;
+}
+
+}  // namespace emu
+
+// ---- built-in variables (1-D blocks; 2-D grids) ----------------------------------------------------
+inline uint3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+namespace emu {
+
+// Run one thread block: `body` is executed once per CUDA thread.
+inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::function<void()> &body) {
+    State &s = S();
+    if (nthreads == 0 || nthreads > (unsigned)kMaxThreads || nthreads % 32 != 0)
+        throw std::runtime_error("emu: block size must be a multiple of 32 and <= 1024");
+    s.n = s.alive = (int)nthreads;
+    s.body = body;
+    s.bar_arrived = s.acc_cnt = s.acc_or = 0;
+    for (auto &x : s.w_arrived) x = 0;
+    blockIdx.x = bx;
+    blockIdx.y = by;
+    blockIdx.z = 0;
+    blockDim = dim3(nthreads, 1, 1);
+    for (int t = 0; t < s.n; ++t) {
+        Fiber &f = s.f[t];
+        if (!f.stack) f.stack = static_cast<char *>(std::malloc(kStackBytes));
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = kStackBytes;
+        f.ctx.uc_link = &s.sched;
+        makecontext(&f.ctx, trampoline, 0);
+        f.done = false;
+    }
+    int remaining = s.n;
+    long last_progress = -1;
+    int idle_rounds = 0;
+    while (remaining > 0) {
+        const long before = s.progress;
+        for (int t = 0; t < s.n; ++t) {
+            if (s.f[t].done) continue;
+            s.cur = t;
+            threadIdx.x = (unsigned)t;
+            threadIdx.y = threadIdx.z = 0;
+            swapcontext(&s.sched, &s.f[t].ctx);
+            if (!s.error.empty()) {  // abandon the block: the other fibers' stacks are simply dropped
+                const std::string msg = s.error;
+                s.error.clear();
+                for (int u = 0; u < s.n; ++u) s.f[u].done = true;
+                throw std::runtime_error(msg);
+            }
+            if (s.f[t].done) {
+                --remaining;
+                --s.alive;
+                ++s.progress;
+                // exited threads no longer take part in block barriers
+                if (s.alive > 0 && s.bar_arrived == s.alive) complete_barrier(s);
+            }
+        }
+        if (s.progress == before) {
+            if (++idle_rounds > 4) {
+                for (int u = 0; u < s.n; ++u) s.f[u].done = true;
+                throw std::runtime_error("emu: deadlock (divergent barrier or warp collective)");
+            }
+        } else
+            idle_rounds = 0;
+        (void)last_progress;
+    }
+}
+
+template <typename F>
+inline void launch(dim3 grid, unsigned nthreads, const F &body) {
+    gridDim = grid;
+    for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) run_block(nthreads, bx, by, body);
+}
+
+}  // namespace emu
+
+// ---- synchronisation --------------------------------------------------------------------------------
+inline void __syncthreads() { emu::block_barrier(0); }
+inline int __syncthreads_count(int pred) {
+    emu::block_barrier(pred);
+    return emu::S().res_cnt;
+}
+inline int __syncthreads_or(int pred) {
+    emu::block_barrier(pred);
+    return emu::S().res_or;
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
+inline void __threadfence_block() {}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+[[noreturn]] inline void __trap() { throw std::runtime_error("emu: __trap()"); }
+inline void __nanosleep(unsigned) { emu::yield(); }  // spin waits make progress by letting the others run
+
+// ---- warp collectives (full mask only) --------------------------------------------------------------
+inline void emu_check_mask(unsigned m) {
+    if (m != 0xffffffffu) throw std::runtime_error("emu: only full-mask warp collectives are emulated");
+}
+template <typename T>
+inline T __shfl_sync(unsigned m, T v, int src, int = 32) {
+    emu_check_mask(m);
+    T all[32];
+    emu::warp_gather(v, all);
+    return all[src & 31];
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned m, T v, int lane_mask, int = 32) {
+    emu_check_mask(m);
+    T all[32];
+    emu::warp_gather(v, all);
+    return all[(threadIdx.x & 31) ^ (lane_mask & 31)];
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned m, T v, unsigned delta, int = 32) {
+    emu_check_mask(m);
+    T all[32];
+    emu::warp_gather(v, all);
+    const int l = threadIdx.x & 31;
+    return l >= (int)delta ? all[l - delta] : v;
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned m, T v, unsigned delta, int = 32) {
+    emu_check_mask(m);
+    T all[32];
+    emu::warp_gather(v, all);
+    const int l = threadIdx.x & 31;
+    return l + (int)delta < 32 ? all[l + delta] : v;
+}
+inline unsigned __ballot_sync(unsigned m, int pred) {
+    emu_check_mask(m);
+    int all[32];
+    emu::warp_gather(pred != 0 ? 1 : 0, all);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= (unsigned)all[i] << i;
+    return r;
+}
+inline int __reduce_max_sync(unsigned m, int v) {
+    emu_check_mask(m);
+    int all[32];
+    emu::warp_gather(v, all);
+    int r = all[0];
+    for (int i = 1; i < 32; ++i) r = all[i] > r ? all[i] : r;
+    return r;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+
+// ---- atomics (cooperative fibers: plain read-modify-write) --------------------------------------------
+template <typename T>
+inline T atomicAdd(T *p, T v) {
+    T o = *p;
+    *p = o + v;
+    return o;
+}
+template <typename T>
+inline T atomicMax(T *p, T v) {
+    T o = *p;
+    if (v > o) *p = v;
+    return o;
+}
+template <typename T>
+inline T atomicCAS(T *p, T cmp, T v) {
+    T o = *p;
+    if (o == cmp) *p = v;
+    return o;
+}
+template <typename T>
+inline T atomicExch(T *p, T v) {
+    T o = *p;
+    *p = v;
+    return o;
+}
+
+// ---- loads and IEEE intrinsics (compile with -ffp-contract=off) ----------------------------------------
+template <typename T>
+inline T __ldg(const T *p) { return *p; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }  // single rounding, like FFMA
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline float __double2float_rn(double a) { return (float)a; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }

@@ -1,0 +1,167 @@
+// emu_kernels.cpp -- TEST INFRASTRUCTURE: host entry points that run the product's CUDA-core kernels
+// (transformed copies under _build/gen/, see build.py) on the fiber emulator.  All pointers are HOST
+// pointers.  Loaded by tests/test_emu_kernels.py through ctypes; never part of the product.
+#include "cuda_emu.h"
+
+// the CUDA runtime calls the launchers make: no device here, launches go to the emulator
+#define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
+#define cudaFuncSetAttribute(...) cudaSuccess
+#define cudaGetLastError() cudaSuccess
+
+// cudaLaunchKernelEx (the PDL launch of the reduce kernels): same grid / block, attributes ignored
+template <typename K, typename P>
+static cudaError_t emu_launch_kernel_ex(const cudaLaunchConfig_t *cfg, K kernel, P p) {
+    emu::launch(cfg->gridDim, cfg->blockDim.x, [&]() { kernel(p); });
+    return cudaSuccess;
+}
+#define cudaLaunchKernelEx emu_launch_kernel_ex
+
+#include "sparse_launch.cu"  // includes launch.h, sparse.cuh -> common.cuh (generated copies)
+#include "scan_f32.cu"       // launch_scan_f32 / _bf16 / _f16 (scan_launch.cuh -> scan.cuh)
+#include "scan_bf16.cu"
+#include "scan_f16.cu"
+#include "misc_launch.cu"    // launch_scan, launch_reduce_*, launch_pool, launch_normalize, launch_agree
+
+namespace {
+thread_local std::string g_emu_err;
+template <typename F>
+int guarded(F f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &e) {
+        g_emu_err = e.what();
+        return -1;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char *emu_last_error() { return g_emu_err.c_str(); }
+
+// vqa_sparse_search with the same planning (vqa::sparse_plan) and launcher (vqa::launch_sparse_search)
+int emu_sparse_search(const long long *offsets, const int *docs, const float *weights, long long n_docs,
+                      long long n_terms, const int *q_terms, const float *q_freqs, const int *q_meta, int max_terms,
+                      int n_queries, int k_cand_max, int limit, int normalize, double avgscore, int sm_count,
+                      double *out_s, long long *out_i) {
+    return guarded([&] {
+        vqa::SparseLaunch a;
+        a.offsets = offsets;
+        a.docs = docs;
+        a.weights = weights;
+        a.n_docs = n_docs;
+        a.n_terms = n_terms;
+        a.q_terms = q_terms;
+        a.q_freqs = q_freqs;
+        a.q_meta = q_meta;
+        a.max_terms = max_terms;
+        a.n_queries = n_queries;
+        a.kcap = k_cand_max;
+        vqa::sparse_plan(n_docs, n_queries, sm_count, &a.ctas_per_query, &a.tiles_per_cta);
+        std::vector<unsigned long long> ws((size_t)n_queries * a.ctas_per_query * k_cand_max);
+        a.cand = ws.data();
+        a.limit = limit;
+        a.normalize = normalize;
+        a.avgscore = avgscore;
+        a.out_s = out_s;
+        a.out_i = out_i;
+        if (vqa::launch_sparse_search(a, nullptr) != cudaSuccess) throw std::runtime_error("launch failed");
+    });
+}
+
+int emu_bm25_weights(const long long *offsets, long long n_terms, const int *docs, const int *freqs,
+                     long long n_postings, const double *idf, const int *doc_len, double k1, double b, double avgdl,
+                     float *weights) {
+    return guarded([&] {
+        if (vqa::launch_bm25_weights(offsets, n_terms, docs, freqs, n_postings, idf, doc_len, k1, b, avgdl, weights,
+                                     nullptr) != cudaSuccess)
+            throw std::runtime_error("launch failed");
+    });
+}
+
+int emu_hybrid_fuse(const float *ds, const long long *di, int kd, const double *ss, const long long *si, int ks,
+                    int n_queries, double wd, double wsp, int limit, double *out_s, long long *out_i) {
+    return guarded([&] {
+        if (vqa::launch_hybrid_fuse(ds, di, kd, ss, si, ks, n_queries, wd, wsp, limit, out_s, out_i, nullptr) !=
+            cudaSuccess)
+            throw std::runtime_error("launch failed");
+    });
+}
+
+// K1 through the product's dispatch (launch_pool: warp-per-token kernel by row length, generic kernel otherwise)
+int emu_pool_normalize(const void *hidden, int h_dtype, const void *mask, int m_dtype, int batch, int seq, int dim,
+                       int normalize, float *out) {
+    return guarded([&] {
+        if (vqa::launch_pool(hidden, h_dtype, mask, m_dtype, batch, seq, dim, normalize, out, nullptr) != cudaSuccess)
+            throw std::runtime_error("launch failed");
+    });
+}
+
+int emu_normalize_rows(const float *in, long long n_rows, int dim, float *out, void *cast_out, int cast_kind) {
+    return guarded([&] {
+        if (vqa::launch_normalize(in, dim, n_rows, dim, out, dim, cast_out, cast_kind, dim, nullptr) != cudaSuccess)
+            throw std::runtime_error("launch failed");
+    });
+}
+
+int emu_agree(const long long *ids_a, const float *sa, const long long *ids_b, const float *sb, long long n,
+              double threshold, unsigned char *accept, float *combined) {
+    return guarded([&] {
+        if (vqa::launch_agree(ids_a, sa, ids_b, sb, n, threshold, accept, combined, nullptr) != cudaSuccess)
+            throw std::runtime_error("launch failed");
+    });
+}
+
+int emu_merge_topk(const float *cand_s, const long long *cand_i, int n_lists, int n_queries, int k_in, int k_out,
+                   float *out_s, long long *out_i) {
+    return guarded([&] {
+        const long long stride = (long long)n_queries * k_in;
+        if (vqa::launch_reduce_i64(cand_s, cand_i, stride, stride, k_in, n_lists, k_in, k_out, 0, out_s, out_i,
+                                   n_queries, nullptr) != cudaSuccess)
+            throw std::runtime_error("launch failed");
+    });
+}
+
+// vqa_search in VERIFY / FAST_STREAM mode: the CUDA-core scan kernel + the candidate reduce, planned exactly as
+// api.cu does it (plan_stream + the grid rule of the stream family).
+int emu_search_stream(const void *rows, int dtype, long long n_rows, int dim, const float *q, int n_queries, int k,
+                      long long first_id, int sm_count, float *out_s, long long *out_i) {
+    return guarded([&] {
+        const int es = dtype == VQA_F32 ? 4 : 2;
+        const int pass_nq = n_queries >= 5 ? 8 : (n_queries >= 3 ? 4 : (n_queries == 2 ? 2 : 1));
+        const int passes_total = (n_queries + pass_nq - 1) / pass_nq;
+        long long gx = (n_rows + 511) / 512;
+        if (gx > sm_count) gx = sm_count;
+        if (passes_total > 1 && gx > sm_count / passes_total) gx = sm_count / passes_total;
+        if (gx < 1) gx = 1;
+        const long long cand_stride = (long long)n_queries * k;
+        std::vector<float> cand_s((size_t)gx * cand_stride);
+        std::vector<uint32_t> cand_i((size_t)gx * cand_stride);
+        int n_lists = 0;
+        if (n_rows > 0) {
+            n_lists = (int)gx;
+            vqa::ScanLaunch a;
+            a.dtype = dtype;
+            a.bt = pass_nq;
+            a.grid = (int)gx;
+            a.rows = rows;
+            a.n_rows = n_rows;
+            a.row_stride_bytes = (long long)dim * es;
+            a.dim = dim;
+            a.q = q;
+            a.q_stride = dim;
+            a.nq = n_queries;
+            a.k = k;
+            a.cand_s = cand_s.data();
+            a.cand_i = cand_i.data();
+            a.cand_stride = cand_stride;
+            if (vqa::launch_scan(a, nullptr) != cudaSuccess) throw std::runtime_error("scan launch failed");
+        }
+        if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cand_stride, k, n_lists, k, k, first_id, out_s, out_i,
+                                   n_queries, nullptr, 1, 1, nullptr) != cudaSuccess)
+            throw std::runtime_error("reduce launch failed");
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+"""The product's CUDA-core kernels executed on the host by the fiber emulator (tests/emu/) and checked against
+the oracle -- kernel LOGIC parity on a machine without a GPU (the GPU tests remain the parity tests proper).
+The emulator is test infrastructure: built from generated copies of the kernel headers, never used by the
+product.  Covered: sparse_scan_kernel (sorted-merge and dense-tile paths) + sparse_finish_kernel,
+bm25_weights_kernel, hybrid_fuse_kernel, pool_normalize_warp_kernel (K1)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import sparse as osp
+from tests.emu import build as emu_build
+from tests.golden import sparse_inputs as si
+from vietnamese_qa_system_b200.scoring import BM25
+
+c = ctypes
+_vp, _i32, _i64, _dbl = c.c_void_p, c.c_int32, c.c_int64, c.c_double
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = ctypes.CDLL(emu_build.build())
+    L.emu_last_error.restype = c.c_char_p
+    L.emu_sparse_search.argtypes = [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32,
+                                    _vp, _vp]
+    L.emu_bm25_weights.argtypes = [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp]
+    L.emu_hybrid_fuse.argtypes = [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _dbl, _dbl, _i32, _vp, _vp]
+    L.emu_pool_normalize.argtypes = [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
+    return L
+
+
+def ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+def ok(L, rc):
+    assert rc == 0, L.emu_last_error().decode()
+
+
+class EmuBM25:
+    """The product's host half (tokenise, CSR, statistics, query planning) + the emulated device half."""
+
+    def __init__(self, L, docs, normalize=True, sm_count=148):
+        self.L, self.sm = L, sm_count
+        self.bm = BM25({"method": "bm25", "terms": True, "normalize": normalize})
+        self.bm.build_postings(docs)
+        h = self.bm._host
+        self.weights = np.zeros(max(len(h["docs"]), 1), np.float32)
+        self.idf = np.ascontiguousarray(self.bm.idf_host)
+        ok(L, L.emu_bm25_weights(ptr(h["offsets"]), len(self.idf), ptr(h["docs"]), ptr(h["freqs"]), len(h["docs"]),
+                                 ptr(self.idf), ptr(h["lengths"]), self.bm.k1, self.bm.b, float(self.bm.avgdl),
+                                 ptr(self.weights)))
+
+    def search(self, queries, limit):
+        bm, h = self.bm, self.bm._host
+        q_terms, q_freqs, q_meta, kmax = bm.plan_queries(queries, limit)
+        kmax = max(kmax, min(limit, bm.total))
+        lim = min(limit, kmax)
+        b = len(queries)
+        out_s, out_i = np.empty((b, lim), np.float64), np.empty((b, lim), np.int64)
+        normalize = bool(bm.normalize and bm.avgscore)
+        ok(self.L, self.L.emu_sparse_search(ptr(h["offsets"]), ptr(h["docs"]), ptr(self.weights), bm.total,
+                                            len(self.idf), ptr(q_terms), ptr(q_freqs), ptr(q_meta), q_terms.shape[1],
+                                            b, kmax, lim, int(normalize), float(bm.avgscore or 0.0), self.sm,
+                                            ptr(out_s), ptr(out_i)))
+        return [[(int(p), float(s)) for p, s in zip(ir, sr) if p >= 0] for sr, ir in zip(out_s, out_i)]
+
+
+def test_emulated_bm25_weights_bit_exact(emu):
+    docs, _ = si.corpus_small()
+    e = EmuBM25(emu, docs)
+    ref = osp.BM25().index(docs)
+    off = e.bm._host["offsets"]
+    for term, tid in e.bm.vocab.items():
+        _, want = ref.weights(term)
+        assert np.array_equal(e.weights[off[tid]:off[tid + 1]].view(np.uint32), want.view(np.uint32)), term
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_emulated_sparse_search_small_corpus(emu, normalize):
+    """One tile, one CTA per query: the sorted-merge path, zero-fill, common-term merge, normalisation."""
+    docs, queries = si.corpus_small()
+    e = EmuBM25(emu, docs, normalize)
+    ref = osp.BM25(normalize=normalize).index(docs)
+    queries = queries[:10] + [["unknown-token"], []]
+    for limit in (1, 10, 100, 1000):
+        got = e.search(queries, limit)
+        for q, g in zip(queries, got):
+            assert g == ref.search(q, limit), (q, limit)
+
+
+def test_emulated_sparse_search_both_paths_many_ctas(emu):
+    """40 k documents = 3 tiles; a small 'SM count' gives one CTA per query (3 tiles each: > 2048 postings of a
+    common term -> dense tiles), a large one gives 3 CTAs per query (sorted merge where the range is sparse)."""
+    n = 40_000
+    docs = []
+    for i in range(n):
+        d = ["pad%d" % (i % 5)]
+        if i % 2 == 0:
+            d += ["all"] * (1 + i % 3)
+        if i % 9 == 0:
+            d.append("mid")
+        if i in (77, 20_001, 39_999):
+            d.append("needle")
+        docs.append(d)
+    ref = osp.BM25().index(docs)
+    queries = [["needle", "all"], ["mid", "all"], ["all"], ["needle"], ["needle", "mid", "all", "all"], ["pad3", "mid"]]
+    for sm in (1, 148):
+        e = EmuBM25(emu, docs, sm_count=sm)
+        for limit in (1, 10):
+            got = e.search(queries, limit)
+            for q, g in zip(queries, got):
+                assert g == ref.search(q, limit), (sm, q, limit)
+
+
+def test_emulated_hybrid_fuse(emu):
+    rng = np.random.default_rng(5)
+    b, kd, ks = 9, 10, 10
+    ds = np.sort(rng.random((b, kd)).astype(np.float32), axis=1)[:, ::-1].copy()
+    di = np.stack([rng.choice(40, kd, replace=False) for _ in range(b)]).astype(np.int64)
+    ss = np.sort(rng.random((b, ks)), axis=1)[:, ::-1].copy()
+    spi = np.stack([rng.choice(40, ks, replace=False) for _ in range(b)]).astype(np.int64)
+    spi[2, 4:], ss[2, 4:] = -1, -np.inf
+    ds[3, :], ss[3, :] = 0.5, 0.5
+    for limit, w in ((1, 0.5), (5, 0.7), (20, 0.0)):
+        out_s, out_i = np.empty((b, limit), np.float64), np.empty((b, limit), np.int64)
+        ok(emu, emu.emu_hybrid_fuse(ptr(ds), ptr(di), kd, ptr(ss), ptr(spi), ks, b, w, 1 - w, limit, ptr(out_s),
+                                    ptr(out_i)))
+        for r in range(b):
+            dense = [(int(i), float(s)) for i, s in zip(di[r], ds[r]) if i >= 0]
+            sparse = [(int(i), float(s)) for i, s in zip(spi[r], ss[r]) if i >= 0]
+            got = [(int(i), float(s)) for i, s in zip(out_i[r], out_s[r]) if i >= 0]
+            assert got == osp.hybrid(dense, sparse, limit, w), (r, limit, w)
+
+
+def _to_storage(x, kind):
+    """fp32 -> (raw storage array, fp32 values it holds)."""
+    if kind == "f32":
+        return x.copy(), x
+    if kind == "f16":
+        h = x.astype(np.float16)
+        return h, h.astype(np.float32)
+    u = x.view(np.uint32)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)            # round to nearest even -> bf16 bits
+    return r, (r.astype(np.uint32) << 16).view(np.float32)
+
+
+@pytest.mark.parametrize("kind,dim", [("bf16", 768), ("bf16", 384), ("bf16", 1024), ("f16", 768), ("f32", 768),
+                                      ("f32", 384), ("f32", 512), ("f32", 1024), ("f16", 1024), ("bf16", 64)])
+def test_emulated_k1_pool_normalize(emu, kind, dim):
+    """K1 for every token-unroll the register budget picks (2 at 768 bf16, 3 at 384 bf16, 4 at 1024 bf16, ...),
+    right- and middle-masked sequences, an all-padding row and a single-token row."""
+    rng = np.random.default_rng(dim)
+    b, s = 6, 70
+    raw, vals = _to_storage(rng.standard_normal((b, s, dim)).astype(np.float32), kind)
+    lens = [70, 1, 0, 33, 17, 64]
+    mask = (np.arange(s)[None, :] < np.array(lens)[:, None]).astype(np.int64)
+    mask[3, 5:9] = 0                                                          # holes inside the valid range
+    code = {"f32": 0, "bf16": 1, "f16": 2}[kind]
+    for normalize in (1, 0):
+        out = np.empty((b, dim), np.float32)
+        ok(emu, emu.emu_pool_normalize(ptr(raw), code, ptr(mask), 3, b, s, dim, normalize, ptr(out)))
+        want = oracle.mean_pool(vals, mask, bool(normalize))
+        assert np.abs(out - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+        assert np.all(out[2] == 0)                                            # all-padding row
+    m8 = mask.astype(np.uint8)
+    out8 = np.empty((b, dim), np.float32)
+    ok(emu, emu.emu_pool_normalize(ptr(raw), code, ptr(m8), 5, b, s, dim, 1, ptr(out8)))
+    assert np.array_equal(out8, out) or np.abs(out8 - oracle.mean_pool(vals, mask, True)).max() < 1e-5
+
+
+# ---- the fp32 verify kernel family (scan_topk_kernel + reduce) on the emulator ---------------------------
+def _bind_search(L):
+    L.emu_search_stream.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp]
+    L.emu_merge_topk.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]
+    L.emu_normalize_rows.argtypes = [_vp, _i64, _i32, _vp, _vp, _i32]
+    L.emu_agree.argtypes = [_vp, _vp, _vp, _vp, _i64, _dbl, _vp, _vp]
+    return L
+
+
+def _unit(rng, n, d):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("kind,dim,n,b,k,sm", [
+    ("f32", 768, 700, 1, 10, 148), ("f32", 768, 900, 8, 5, 3), ("f32", 384, 1500, 3, 10, 2), ("f32", 200, 600, 2, 7, 4),
+    ("bf16", 768, 1100, 5, 10, 2), ("f16", 1024, 520, 11, 3, 6), ("f32", 768, 37, 4, 64, 148), ("bf16", 64, 2100, 9, 40, 4),
+])
+def test_emulated_verify_search_is_bit_identical_to_the_canonical_oracle(emu, kind, dim, n, b, k, sm):
+    """north_star: 'an fp32 verification mode gives bit-identical top-k ids (ties broken by lower doc_id)' --
+    here ids AND score bits, for every storage type, unrolled and generic row lengths, 1..11 queries (1/2/4/8
+    per pass, several passes), one or several CTAs, k up to and beyond the row count, planted duplicates."""
+    L = _bind_search(emu)
+    rng = np.random.default_rng(n + dim + b)
+    docs = _unit(rng, n, dim)
+    docs[n // 3] = docs[5]                                  # exact duplicates: equal scores, lower id first
+    docs[n - 1] = docs[5]
+    q = _unit(rng, b, dim)
+    q[0] = docs[5]
+    raw, vals = _to_storage(docs, kind)
+    code = {"f32": 0, "bf16": 1, "f16": 2}[kind]
+    out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+    ok(L, L.emu_search_stream(ptr(raw), code, n, dim, ptr(q), b, k, 1000, sm, ptr(out_s), ptr(out_i)))
+    storage = {"f32": "fp32", "bf16": "bf16", "f16": "fp16"}[kind]
+    want_s, want_i = oracle.search(vals, q, k, oracle.CANONICAL, storage, first_id=1000)
+    assert np.array_equal(out_i, want_i)
+    assert np.array_equal(out_s.view(np.uint32), want_s.view(np.uint32))
+    top = out_i[0, :3].tolist()
+    if k >= 3 and n > 10:
+        assert top == sorted(top) and set(top) == {1005, 1000 + n // 3, 1000 + n - 1}
+
+
+def test_emulated_merge_normalize_agree(emu):
+    L = _bind_search(emu)
+    rng = np.random.default_rng(3)
+    lists, b, k = 5, 6, 10
+    cs = -np.sort(-rng.random((lists, b, k)).astype(np.float32), axis=2)
+    ci = rng.permutation(lists * b * k).reshape(lists, b, k).astype(np.int64)
+    cs[1, :, 7:], ci[1, :, 7:] = -np.inf, -1                                 # padded tails
+    cs[2, 0, :] = cs[3, 0, :]                                                # ties across lists -> lower id first
+    out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+    ok(L, L.emu_merge_topk(ptr(cs), ptr(ci), lists, b, k, k, ptr(out_s), ptr(out_i)))
+    ws, wi = oracle.merge_topk(cs, ci, k)
+    assert np.array_equal(out_i, wi) and np.array_equal(out_s, ws)
+    x = rng.standard_normal((9, 768)).astype(np.float32)
+    x[4] = 0
+    out = np.empty_like(x)
+    cast = np.empty((9, 768), np.uint16)
+    ok(L, L.emu_normalize_rows(ptr(x), 9, 768, ptr(out), ptr(cast), 1))
+    want = oracle.normalize_rows(x)
+    assert np.abs(out - want).max() < 1e-6 and np.all(out[4] == 0)
+    assert np.array_equal(cast, _to_storage(out, "bf16")[0])                  # bf16 cast = round to nearest even
+    ida = np.array([1, 2, 3, 4], np.int64)
+    idb = np.array([1, 2, 9, 4], np.int64)
+    sa = np.array([0.25, 0.2, 0.9, 0.125], np.float32)
+    sb = np.array([0.2, 0.2, 0.9, 0.25], np.float32)
+    acc, comb = np.empty(4, np.uint8), np.empty(4, np.float32)
+    ok(L, L.emu_agree(ptr(ida), ptr(sa), ptr(idb), ptr(sb), 4, 0.4, ptr(acc), ptr(comb)))
+    assert acc.tolist() == [int(oracle.agree(a, x_, b_, y)) for a, x_, b_, y in zip(ida, sa, idb, sb)] == [1, 1, 0, 0]
