@@ -153,3 +153,13 @@ def test_no_kernel_spills_registers_in_a_hot_loop():
     assert len(rep) >= 80                                  # every kernel instantiation is accounted for
     worst = {k: v for k, v in rep.items() if v[1] > 32 or v[2] > 32}
     assert not worst, worst
+
+
+def test_product_never_references_the_emulator():
+    pkg = os.path.join(ROOT, "vietnamese_qa_system_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dp, fn), encoding="utf-8") as f:
+                    src = f.read()
+                assert "cuda_emu" not in src and "tests/emu" not in src and "tests.emu" not in src, fn
