@@ -58,6 +58,10 @@ struct State {
     unsigned long long wbuf[kMaxThreads / 32][32] = {};
     long progress = 0;
     std::string error;
+    // fiber order inside a scheduling pass: 0 thread order, 1 reverse, 2 a fresh random permutation per pass
+    int schedule = 0;
+    unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    int order[kMaxThreads];
     // dynamic shared memory of the running block
     alignas(128) unsigned char dyn_smem[232 * 1024];
 };
@@ -156,11 +160,23 @@ inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::fu
         f.done = false;
     }
     int remaining = s.n;
-    long last_progress = -1;
     int idle_rounds = 0;
+    for (int t = 0; t < s.n; ++t) s.order[t] = s.schedule == 1 ? s.n - 1 - t : t;
     while (remaining > 0) {
         const long before = s.progress;
-        for (int t = 0; t < s.n; ++t) {
+        if (s.schedule == 2) {  // Fisher-Yates with xorshift64*: a different interleaving on every pass
+            for (int t = s.n - 1; t > 0; --t) {
+                s.rng ^= s.rng >> 12;
+                s.rng ^= s.rng << 25;
+                s.rng ^= s.rng >> 27;
+                const int j = (int)((s.rng * 0x2545F4914F6CDD1Dull >> 33) % (unsigned)(t + 1));
+                const int tmp = s.order[t];
+                s.order[t] = s.order[j];
+                s.order[j] = tmp;
+            }
+        }
+        for (int oi = 0; oi < s.n; ++oi) {
+            const int t = s.order[oi];
             if (s.f[t].done) continue;
             s.cur = t;
             threadIdx.x = (unsigned)t;
@@ -187,7 +203,6 @@ inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::fu
             }
         } else
             idle_rounds = 0;
-        (void)last_progress;
     }
 }
 

@@ -40,6 +40,12 @@ extern "C" {
 
 const char *emu_last_error() { return g_emu_err.c_str(); }
 
+// fiber order inside a scheduling pass: 0 thread order, 1 reverse, 2 random permutation per pass (seeded)
+void emu_set_schedule(int mode, unsigned long long seed) {
+    emu::S().schedule = mode;
+    emu::S().rng = seed ? seed : 0x9E3779B97F4A7C15ull;
+}
+
 // vqa_sparse_search with the same planning (vqa::sparse_plan) and launcher (vqa::launch_sparse_search)
 int emu_sparse_search(const long long *offsets, const int *docs, const float *weights, long long n_docs,
                       long long n_terms, const int *q_terms, const float *q_freqs, const int *q_meta, int max_terms,

@@ -18,9 +18,13 @@ c = ctypes
 _vp, _i32, _i64, _dbl = c.c_void_p, c.c_int32, c.c_int64, c.c_double
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=["thread order", "reverse order", "random interleaving"])
+def emu(request):
+    """Every test runs under three fiber schedules: kernels whose result depended on which thread reaches a
+    barrier-free region first (a missing __syncthreads, an unordered shared-memory update) would differ."""
     L = ctypes.CDLL(emu_build.build())
+    L.emu_set_schedule.argtypes = [_i32, c.c_uint64]
+    L.emu_set_schedule({"thread order": 0, "reverse order": 1, "random interleaving": 2}[request.param], 12345)
     L.emu_last_error.restype = c.c_char_p
     L.emu_sparse_search.argtypes = [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32,
                                     _vp, _vp]
