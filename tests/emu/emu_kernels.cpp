@@ -129,6 +129,27 @@ int emu_merge_topk(const float *cand_s, const long long *cand_i, int n_lists, in
     });
 }
 
+// The candidate reduce with the exact re-scoring stage (what follows the TMEM-resident tensor-core scan in
+// screen mode): cand_* [n_lists][n_queries][k_in] with u32 row ids, rows in 16-bit storage.
+int emu_reduce_rescore(const float *cand_s, const uint32_t *cand_i, int n_lists, int n_queries, int k_in, int k_out,
+                       int k_final, long long id_base, const void *rows, int dim, int bf16, const float *q,
+                       float *out_s, long long *out_i) {
+    return guarded([&] {
+        vqa::Rescore rs;
+        rs.rows = rows;
+        rs.stride = (long long)dim * 2;
+        rs.dim = dim;
+        rs.bf16 = bf16;
+        rs.q = q;
+        rs.q_stride = dim;
+        rs.k_final = k_final;
+        const long long stride = (long long)n_queries * k_in;
+        if (vqa::launch_reduce_u32(cand_s, cand_i, stride, k_in, n_lists, k_in, k_out, id_base, out_s, out_i, n_queries,
+                                   nullptr, 1, 1, nullptr, &rs) != cudaSuccess)
+            throw std::runtime_error("reduce launch failed");
+    });
+}
+
 // vqa_search in VERIFY / FAST_STREAM mode: the CUDA-core scan kernel + the candidate reduce, planned exactly as
 // api.cu does it (plan_stream + the grid rule of the stream family).
 int emu_search_stream(const void *rows, int dtype, long long n_rows, int dim, const float *q, int n_queries, int k,

@@ -243,3 +243,34 @@ def test_emulated_merge_normalize_agree(emu):
     acc, comb = np.empty(4, np.uint8), np.empty(4, np.float32)
     ok(L, L.emu_agree(ptr(ida), ptr(sa), ptr(idb), ptr(sb), 4, 0.4, ptr(acc), ptr(comb)))
     assert acc.tolist() == [int(oracle.agree(a, x_, b_, y)) for a, x_, b_, y in zip(ida, sa, idb, sb)] == [1, 1, 0, 0]
+
+
+@pytest.mark.parametrize("kind", ["bf16", "f16"])
+def test_emulated_reduce_with_exact_rescoring(emu, kind):
+    """The screen-then-rescore stage behind the large-batch tensor-core scan: the 16 best candidates by their
+    (storage-precision) screen scores are re-scored exactly in fp32 against the stored rows, re-sorted and the
+    best 10 emitted -- so a true neighbour that the screen ranked 11th..16th is recovered."""
+    emu.emu_reduce_rescore.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]
+    rng = np.random.default_rng(8)
+    n, dim, b, lists, k_in, k_out, k_final = 400, 768, 3, 5, 16, 16, 10
+    raw, vals = _to_storage(_unit(rng, n, dim), kind)
+    q = _unit(rng, b, dim)
+    exact = vals.astype(np.float64) @ q.astype(np.float64).T                  # [n, b]
+    screen = (exact + rng.normal(0, 2e-3, exact.shape)).astype(np.float32)    # perturbed order inside the top 16
+    cand_s = np.full((lists, b, k_in), -np.inf, np.float32)
+    cand_i = np.full((lists, b, k_in), 0xFFFFFFFF, np.uint32)
+    per = n // lists
+    for l in range(lists):                                                    # list l = rows [l*per, (l+1)*per)
+        for j in range(b):
+            ids = np.arange(l * per, (l + 1) * per)
+            order = np.lexsort((ids, -screen[ids, j].astype(np.float64)))[:k_in]
+            cand_s[l, j], cand_i[l, j] = screen[ids[order], j], ids[order]
+    out_s, out_i = np.empty((b, k_final), np.float32), np.empty((b, k_final), np.int64)
+    ok(emu, emu.emu_reduce_rescore(ptr(cand_s), ptr(cand_i), lists, b, k_in, k_out, k_final, 50, ptr(raw), dim,
+                                   int(kind == "bf16"), ptr(q), ptr(out_s), ptr(out_i)))
+    for j in range(b):
+        allc = np.arange(n)
+        top16 = allc[np.lexsort((allc, -screen[:, j].astype(np.float64)))[:k_out]]
+        want = top16[np.lexsort((top16, -exact[top16, j]))[:k_final]]
+        assert out_i[j].tolist() == (want + 50).tolist()
+        assert np.abs(out_s[j] - exact[want, j]).max() < 5e-7
