@@ -78,6 +78,16 @@ def transform(name: str, src: str) -> str:
     return src
 
 
+def _cuda_include() -> str:
+    return os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
+
+
+def toolchain_available() -> bool:
+    import shutil
+
+    return shutil.which("g++") is not None and os.path.exists(os.path.join(_cuda_include(), "cuda_runtime.h"))
+
+
 def build(force: bool = False) -> str:
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_kernels.cpp", "build.py")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
@@ -88,7 +98,7 @@ def build(force: bool = False) -> str:
             out = transform(s, f.read())
         with open(os.path.join(GEN, s), "w", encoding="utf-8") as f:
             f.write(out)
-    cuda_inc = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
+    cuda_inc = _cuda_include()
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
            "-Wno-attributes", "-Wno-unused-value", f"-I{cuda_inc}", f"-I{HERE}", f"-I{GEN}",
            os.path.join(HERE, "emu_kernels.cpp"), "-o", LIB]
