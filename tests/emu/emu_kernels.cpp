@@ -129,6 +129,30 @@ int emu_merge_topk(const float *cand_s, const long long *cand_i, int n_lists, in
     });
 }
 
+// Peer-memory exchange (vqa_exchange_push / vqa_merge_topk_wait) with host buffers standing in for the peers'
+// symmetric memory: push this rank's packed block into every peer slot + publish the epoch flag ...
+int emu_exchange_push(const void *local, size_t bytes, void *const *peer_slots, unsigned long long *const *peer_flags,
+                      int world, unsigned long long epoch) {
+    return guarded([&] {
+        if (vqa::launch_exchange_push(local, bytes, peer_slots, peer_flags, world, epoch, nullptr) != cudaSuccess)
+            throw std::runtime_error("push launch failed");
+    });
+}
+// ... and the merge whose kernel first acquires all flags
+int emu_merge_topk_wait(const float *cand_s, const long long *cand_i, long long stride_s, long long stride_i,
+                        int n_lists, int n_queries, int k, float *out_s, long long *out_i,
+                        const unsigned long long *flags, unsigned long long epoch) {
+    return guarded([&] {
+        vqa::WaitFlags wf;
+        wf.flags = flags;
+        wf.n = n_lists;
+        wf.epoch = epoch;
+        if (vqa::launch_reduce_i64(cand_s, cand_i, stride_s, stride_i, k, n_lists, k, k, 0, out_s, out_i, n_queries,
+                                   nullptr, &wf) != cudaSuccess)
+            throw std::runtime_error("merge launch failed");
+    });
+}
+
 // The candidate reduce with the exact re-scoring stage (what follows the TMEM-resident tensor-core scan in
 // screen mode): cand_* [n_lists][n_queries][k_in] with u32 row ids, rows in 16-bit storage.
 int emu_reduce_rescore(const float *cand_s, const uint32_t *cand_i, int n_lists, int n_queries, int k_in, int k_out,

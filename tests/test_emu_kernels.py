@@ -276,3 +276,37 @@ def test_emulated_reduce_with_exact_rescoring(emu, kind):
         want = top16[np.lexsort((top16, -exact[top16, j]))[:k_final]]
         assert out_i[j].tolist() == (want + 50).tolist()
         assert np.abs(out_s[j] - exact[want, j]).max() < 5e-7
+
+
+def test_emulated_peer_memory_exchange_and_flag_waiting_merge(emu):
+    """ShardedFlat(exchange="p2p") on one host: every 'rank' pushes its packed [scores | ids] block into its slot
+    of every peer's gather buffer and publishes the epoch; each rank's merge kernel acquires the flags and merges
+    the gathered blocks in place -- identical result on every rank, equal to the oracle merge."""
+    emu.emu_exchange_push.argtypes = [_vp, c.c_size_t, _vp, _vp, _i32, c.c_uint64]
+    emu.emu_merge_topk_wait.argtypes = [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, c.c_uint64]
+    rng = np.random.default_rng(4)
+    world, b, k, epoch = 4, 5, 10, 7
+    ids_off = (b * k * 4 + 15) // 16 * 16
+    block = (ids_off + b * k * 8 + 15) // 16 * 16
+    scores = -np.sort(-rng.random((world, b, k)).astype(np.float32), axis=2)
+    ids = rng.permutation(world * b * k).reshape(world, b, k).astype(np.int64)
+    locals_ = []
+    for r in range(world):
+        blk = np.zeros(block, np.uint8)
+        blk[:b * k * 4] = scores[r].view(np.uint8).ravel()
+        blk[ids_off:ids_off + b * k * 8] = ids[r].view(np.uint8).ravel()
+        locals_.append(blk)
+    gather = [np.zeros(world * block, np.uint8) for _ in range(world)]       # rank p's gather buffer
+    flags = [np.zeros(world, np.uint64) for _ in range(world)]               # rank p's flags, one per source rank
+    for r in range(world):                                                   # rank r pushes to every peer p
+        slots = (_vp * world)(*[gather[p].ctypes.data + r * block for p in range(world)])
+        flg = (_vp * world)(*[flags[p].ctypes.data + r * 8 for p in range(world)])
+        ok(emu, emu.emu_exchange_push(ptr(locals_[r]), block, slots, flg, world, epoch))
+    assert all(f.tolist() == [epoch] * world for f in flags)
+    ws, wi = oracle.merge_topk(scores, ids, k)
+    for p in range(world):
+        out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+        base = gather[p].ctypes.data
+        ok(emu, emu.emu_merge_topk_wait(_vp(base), _vp(base + ids_off), block // 4, block // 8, world, b, k,
+                                        ptr(out_s), ptr(out_i), ptr(flags[p]), epoch))
+        assert np.array_equal(out_i, wi) and np.array_equal(out_s, ws)
