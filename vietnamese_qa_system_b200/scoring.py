@@ -214,7 +214,8 @@ class BM25:
         n_terms = len(self._df)
         dev = self.device
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-        d = {"offsets": up(h["offsets"]), "docs": up(h["docs"]) if len(h["docs"]) else torch.zeros(1, dtype=torch.int32, device=dev)}
+        d = {"offsets": up(h["offsets"]),
+             "docs": up(h["docs"]) if len(h["docs"]) else torch.zeros(1, dtype=torch.int32, device=dev)}
         n_post = int(len(h["docs"]))
         weights = torch.zeros(max(n_post, 1), dtype=torch.float32, device=dev)
         if n_post:
