@@ -22,7 +22,7 @@ OUT = os.path.join(HERE, "_build")
 GEN = os.path.join(OUT, "gen")
 LIB = os.path.join(OUT, "libvqa_emu.so")
 SOURCES = ["consts.h", "common.cuh", "launch.h", "sparse.cuh", "sparse_launch.cu", "pool.cuh", "scan.cuh",
-           "scan_launch.cuh", "scan_f32.cu", "scan_bf16.cu", "scan_f16.cu", "misc_launch.cu"]
+           "scan_launch.cuh", "scan_f32.cu", "scan_bf16.cu", "scan_f16.cu", "misc_launch.cu", "mma.cuh", "mma_launch.cu"]
 
 
 def _split_top_level(s: str):
@@ -54,7 +54,7 @@ def _launches(src: str) -> str:
 
 def transform(name: str, src: str) -> str:
     n_ext = len(re.findall(r"extern\s+__shared__", src))
-    src, n = re.subn(r"extern\s+__shared__\s+__align__\(\d+\)\s+unsigned char\s+(\w+)\[\];",
+    src, n = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char\s+(\w+)\[\];",
                      r"unsigned char *\1 = emu::S().dyn_smem;", src)
     assert n == n_ext, f"{name}: {n_ext} extern __shared__ declarations, {n} transformed"
     if name == "common.cuh":
@@ -69,6 +69,14 @@ def transform(name: str, src: str) -> str:
         src, b = re.subn(r'asm volatile\("st\.release\.sys\.global\.u64.*?: "memory"\);',
                          "*static_cast<volatile unsigned long long *>(p) = v;", src, flags=re.S)
         assert (a, b) == (1, 1), (a, b)
+    if name == "mma.cuh":
+        src, a = re.subn(r'unsigned long long v;\s*asm volatile\("ld\.volatile\.global\.u64 %0, \[%1\];" : "=l"\(v\) : "l"\(p\)\);\s*return v;',
+                         "return *static_cast<const volatile unsigned long long *>(p);", src)
+        src, b = re.subn(r'asm volatile\("bar\.sync %0, %1;" ::"r"\(id\), "r"\(count\) : "memory"\);',
+                         "emu::named_bar_sync(id, count);", src)
+        src, c = re.subn(r'asm volatile\("bar\.arrive %0, %1;" ::"r"\(id\), "r"\(count\) : "memory"\);',
+                         "emu::named_bar_arrive(id, count);", src)
+        assert (a, b, c) == (1, 1, 1), (a, b, c)
     assert "asm volatile" not in src, f"{name}: untransformed inline PTX"
     if "<<<" in src:
         src = _launches(src)
@@ -88,11 +96,28 @@ def toolchain_available() -> bool:
     return shutil.which("g++") is not None and os.path.exists(os.path.join(_cuda_include(), "cuda_runtime.h"))
 
 
+def _install_ptx_model() -> None:
+    """gen/ptx.cuh = tests/emu/ptx_emu.cuh, after checking that it models every wrapper of the real ptx.cuh."""
+    with open(os.path.join(CSRC, "ptx.cuh"), encoding="utf-8") as f:
+        real = f.read()
+    with open(os.path.join(HERE, "ptx_emu.cuh"), encoding="utf-8") as f:
+        model = f.read()
+    pat = r"^(?:__host__ )?__device__ (?:__forceinline__ )?(?:constexpr )?[\w:]+ (\w+)\("
+    real_fns = set(re.findall(pat, real, flags=re.M))
+    model_fns = set(re.findall(r"^(?:inline|constexpr) [\w:]+ (\w+)\(", model, flags=re.M))
+    missing = sorted(real_fns - model_fns)
+    assert len(real_fns) >= 25 and not missing, f"ptx.cuh wrappers without a host model: {missing}"
+    with open(os.path.join(GEN, "ptx.cuh"), "w", encoding="utf-8") as f:
+        f.write(model)
+
+
 def build(force: bool = False) -> str:
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "emu_kernels.cpp", "build.py")]
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "ptx_emu.cuh", "emu_kernels.cpp", "build.py")] + \
+        [os.path.join(CSRC, "ptx.cuh")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(GEN, exist_ok=True)
+    _install_ptx_model()
     for s in SOURCES:
         with open(os.path.join(CSRC, s), encoding="utf-8") as f:
             out = transform(s, f.read())

@@ -63,7 +63,7 @@ struct State {
     unsigned long long rng = 0x9E3779B97F4A7C15ull;
     int order[kMaxThreads];
     // dynamic shared memory of the running block
-    alignas(128) unsigned char dyn_smem[232 * 1024];
+    alignas(1024) unsigned char dyn_smem[232 * 1024];  // 1024: offsets and addresses share their low bits (swizzle)
 };
 inline State &S() {
     static State s;

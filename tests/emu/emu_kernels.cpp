@@ -8,19 +8,22 @@
 #define cudaFuncSetAttribute(...) cudaSuccess
 #define cudaGetLastError() cudaSuccess
 
-// cudaLaunchKernelEx (the PDL launch of the reduce kernels): same grid / block, attributes ignored
-template <typename K, typename P>
-static cudaError_t emu_launch_kernel_ex(const cudaLaunchConfig_t *cfg, K kernel, P p) {
-    emu::launch(cfg->gridDim, cfg->blockDim.x, [&]() { kernel(p); });
+// cudaLaunchKernelEx (PDL launch of the reduce kernels, cluster launch of the tensor kernels): same grid / block,
+// attributes ignored (clusters are not modelled: the drivers below never ask for multicast)
+template <typename K, typename... P>
+static cudaError_t emu_launch_kernel_ex(const cudaLaunchConfig_t *cfg, K kernel, P... p) {
+    emu::launch(cfg->gridDim, cfg->blockDim.x, [&]() { kernel(p...); });
     return cudaSuccess;
 }
 #define cudaLaunchKernelEx emu_launch_kernel_ex
+#define cudaOccupancyMaxActiveClusters(...) cudaErrorNotSupported
 
 #include "sparse_launch.cu"  // includes launch.h, sparse.cuh -> common.cuh (generated copies)
 #include "scan_f32.cu"       // launch_scan_f32 / _bf16 / _f16 (scan_launch.cuh -> scan.cuh)
 #include "scan_bf16.cu"
 #include "scan_f16.cu"
 #include "misc_launch.cu"    // launch_scan, launch_reduce_*, launch_pool, launch_normalize, launch_agree
+#include "mma_launch.cu"     // launch_mma (mma.cuh over the host models of ptx.cuh: tests/emu/ptx_emu.cuh)
 
 namespace {
 thread_local std::string g_emu_err;
@@ -170,6 +173,63 @@ int emu_reduce_rescore(const float *cand_s, const uint32_t *cand_i, int n_lists,
         const long long stride = (long long)n_queries * k_in;
         if (vqa::launch_reduce_u32(cand_s, cand_i, stride, k_in, n_lists, k_in, k_out, id_base, out_s, out_i, n_queries,
                                    nullptr, 1, 1, nullptr, &rs) != cudaSuccess)
+            throw std::runtime_error("reduce launch failed");
+    });
+}
+
+// vqa_search in FAST_TENSOR mode (hi/lo column pairs, no clusters): mma_topk_kernel + the candidate reduce, wired
+// as api.cu does it.  rows: 16-bit storage [n_rows][dim]; ncol in {16, 32, 64, 128}; the batch is cut into chunks
+// of ncol / 2 queries handled side by side (n_groups = chunks).
+int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, const float *q, int n_queries, int k,
+                      long long first_id, int sm_count, int ncol, int stages, int kps, float *out_s, long long *out_i) {
+    return guarded([&] {
+        const int pass_nq = ncol / 2;
+        const int g = (n_queries + pass_nq - 1) / pass_nq;
+        const long long tiles = (n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
+        long long streams = sm_count / g;
+        if (streams > tiles) streams = tiles;
+        if (streams < 1) streams = 1;
+        CUtensorMap tmap;
+        std::memset(&tmap, 0, sizeof(tmap));
+        emu::EmuTmap m;
+        m.base = static_cast<const unsigned char *>(rows);
+        m.dim0 = (unsigned long long)dim;
+        m.dim1 = (unsigned long long)n_rows;
+        m.stride1_bytes = (unsigned long long)dim * 2;
+        m.box0 = 64;
+        m.box1 = vqa::kTileRows;
+        m.elem_bytes = 2;
+        m.magic = emu::kTmapMagic;
+        std::memcpy(&tmap, &m, sizeof(m));
+        const int grid = (int)streams * g;
+        const long long cstride = (long long)n_queries * k;
+        std::vector<float> cand_s((size_t)grid * cstride);
+        std::vector<uint32_t> cand_i((size_t)grid * cstride);
+        std::vector<unsigned long long> tau_g((size_t)n_queries, 0ull);
+        vqa::MmaLaunch a;
+        a.tmap = &tmap;
+        a.bf16 = bf16 != 0;
+        a.ncol = ncol;
+        a.split = 1;
+        a.stages = stages;
+        a.kps = kps;
+        a.grid = grid;
+        a.n_groups = g;
+        a.multicast = 0;
+        a.q = q;
+        a.q_stride = dim;
+        a.nq = n_queries;
+        a.k = k;
+        a.n_rows = n_rows;
+        a.dim = dim;
+        a.cand_s = cand_s.data();
+        a.cand_i = cand_i.data();
+        a.cand_stride = cstride;
+        a.tau_g = tau_g.data();
+        a.epoch = 1;
+        if (vqa::launch_mma(a, nullptr) != cudaSuccess) throw std::runtime_error("tensor scan launch failed");
+        if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, k, grid, k, k, first_id, out_s, out_i,
+                                   n_queries, tau_g.data(), g, pass_nq, nullptr, nullptr) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }

@@ -310,3 +310,38 @@ def test_emulated_peer_memory_exchange_and_flag_waiting_merge(emu):
         ok(emu, emu.emu_merge_topk_wait(_vp(base), _vp(base + ids_off), block // 4, block // 8, world, b, k,
                                         ptr(out_s), ptr(out_i), ptr(flags[p]), epoch))
         assert np.array_equal(out_i, wi) and np.array_equal(out_s, ws)
+
+
+# ---- the tcgen05 / TMA kernels on host models of the PTX wrappers (tests/emu/ptx_emu.cuh) --------------------
+def _recall(got, want):
+    k = want.shape[1]
+    return float(np.mean([len(set(got[r]) & set(want[r])) / k for r in range(want.shape[0])]))
+
+
+@pytest.mark.parametrize("kind,dim,n,b,k,sm,ncol,stages,kps", [
+    ("bf16", 128, 300, 3, 5, 2, 16, 4, 2),       # NCOL 16: hi and lo in one TMEM load; last tile partly outside
+    ("bf16", 768, 1000, 8, 10, 3, 16, 4, 2),     # the headline shape in miniature (dim 768, top-10), 3 CTAs
+    ("f16", 768, 700, 20, 10, 4, 64, 3, 2),      # fp16 rows (scaled residual), 32 queries per CTA
+    ("bf16", 256, 1100, 40, 10, 8, 32, 4, 1),    # 3 query chunks side by side (n_groups = 3), one box per stage
+    ("bf16", 192, 90, 5, 32, 148, 16, 4, 3),     # fewer rows than one tile, k = 32 (full register lists), kps = 3
+    ("f16", 128, 600, 6, 40, 2, 16, 5, 2),       # k > 32: CTA-shared sorted lists behind the spin lock
+    ("bf16", 64, 2000, 70, 3, 4, 128, 6, 1),     # NCOL 128: 64 queries per CTA, 2 chunks, shared-memory lists
+])
+def test_emulated_tcgen05_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, ncol, stages, kps):
+    """mma_topk_kernel (TMA producer / MMA issuer / TMEM epilogue with register top-k lists and GPU-wide
+    thresholds) + the reduce, on the host models of mbarrier, TMA (128-byte swizzle), tcgen05.mma / commit / ld and
+    named barriers.  Bar of the GPU tests: recall against fp32 arithmetic on the stored rows, rank-wise scores
+    within 1e-5 relative; here the ids are in fact identical, duplicates lower id first."""
+    emu.emu_search_tensor.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]
+    rng = np.random.default_rng(dim + n + b)
+    docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    raw, vals = _to_storage(docs, kind)
+    out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+    ok(emu, emu.emu_search_tensor(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, ncol, stages, kps,
+                                  ptr(out_s), ptr(out_i)))
+    want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
+    assert _recall(out_i, want_i) >= 0.999
+    assert np.abs(out_s - want_s).max() <= 1e-5 * np.abs(want_s).max() + 2e-6
+    assert out_i[0, :2].tolist() == [103, 100 + n // 2] and np.all(np.diff(out_s, axis=1) <= 0)
