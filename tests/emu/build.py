@@ -22,7 +22,8 @@ OUT = os.path.join(HERE, "_build")
 GEN = os.path.join(OUT, "gen")
 LIB = os.path.join(OUT, "libvqa_emu.so")
 SOURCES = ["consts.h", "common.cuh", "launch.h", "sparse.cuh", "sparse_launch.cu", "pool.cuh", "scan.cuh",
-           "scan_launch.cuh", "scan_f32.cu", "scan_bf16.cu", "scan_f16.cu", "misc_launch.cu", "mma.cuh", "mma_launch.cu"]
+           "scan_launch.cuh", "scan_f32.cu", "scan_bf16.cu", "scan_f16.cu", "misc_launch.cu", "mma.cuh", "mma_launch.cu", "ts.cuh",
+           "ts_launch.cu"]
 
 
 def _split_top_level(s: str):
@@ -76,6 +77,14 @@ def transform(name: str, src: str) -> str:
                          "emu::named_bar_sync(id, count);", src)
         src, c = re.subn(r'asm volatile\("bar\.arrive %0, %1;" ::"r"\(id\), "r"\(count\) : "memory"\);',
                          "emu::named_bar_arrive(id, count);", src)
+        assert (a, b, c) == (1, 1, 1), (a, b, c)
+    if name == "ts.cuh":
+        src, a = re.subn(r'asm volatile\(\s*"tcgen05\.st\.sync\.aligned\.32x32b\.x16\.b32.*?: "memory"\);',
+                         "ptx::model_tmem_st16(taddr, r);", src, flags=re.S)
+        src, b = re.subn(r'asm volatile\("tcgen05\.wait::st\.sync\.aligned;" ::: "memory"\);', ";", src)
+        src, c = re.subn(r'asm volatile\(\s*"\{\\n\\t"\s*"\.reg \.pred p;\\n\\t"\s*"setp\.ne\.b32 p, %4, 0;\\n\\t"\s*'
+                         r'"tcgen05\.mma\.cta_group::1\.kind::f16 \[%0\], \[%1\], %2, %3, p;\\n\\t".*?: "memory"\);',
+                         "ptx::model_umma_f16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);", src, flags=re.S)
         assert (a, b, c) == (1, 1, 1), (a, b, c)
     assert "asm volatile" not in src, f"{name}: untransformed inline PTX"
     if "<<<" in src:

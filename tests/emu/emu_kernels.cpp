@@ -24,6 +24,7 @@ static cudaError_t emu_launch_kernel_ex(const cudaLaunchConfig_t *cfg, K kernel,
 #include "scan_f16.cu"
 #include "misc_launch.cu"    // launch_scan, launch_reduce_*, launch_pool, launch_normalize, launch_agree
 #include "mma_launch.cu"     // launch_mma (mma.cuh over the host models of ptx.cuh: tests/emu/ptx_emu.cuh)
+#include "ts_launch.cu"      // launch_ts  (ts.cuh: queries resident in tensor memory)
 
 namespace {
 thread_local std::string g_emu_err;
@@ -230,6 +231,74 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
         if (vqa::launch_mma(a, nullptr) != cudaSuccess) throw std::runtime_error("tensor scan launch failed");
         if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, k, grid, k, k, first_id, out_s, out_i,
                                    n_queries, tau_g.data(), g, pass_nq, nullptr, nullptr) != cudaSuccess)
+            throw std::runtime_error("reduce launch failed");
+    });
+}
+
+// vqa_search in FAST_TS mode (queries resident in tensor memory, no clusters): ts_topk_kernel + the reduce, wired
+// as api.cu does it.  split = 0: storage-precision screen with k + spare candidates per query, the 32 best
+// re-scored exactly by the reduce; split = 1: hi + lo query rows (64 queries per CTA), no re-scoring.
+int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const float *q, int n_queries, int k,
+                  long long first_id, int sm_count, int split, int spare, int stages, int kps, float *out_s,
+                  long long *out_i) {
+    return guarded([&] {
+        const int pass_nq = split ? 64 : 128;
+        const int kscan = split ? k : k + spare;
+        const int g = (n_queries + pass_nq - 1) / pass_nq;
+        const long long tiles = (n_rows + 63) / 64;
+        long long streams = sm_count / g;
+        if (streams > tiles) streams = tiles;
+        if (streams < 1) streams = 1;
+        CUtensorMap tmap;
+        std::memset(&tmap, 0, sizeof(tmap));
+        emu::EmuTmap m;
+        m.base = static_cast<const unsigned char *>(rows);
+        m.dim0 = (unsigned long long)dim;
+        m.dim1 = (unsigned long long)n_rows;
+        m.stride1_bytes = (unsigned long long)dim * 2;
+        m.box0 = 64;
+        m.box1 = 64;
+        m.elem_bytes = 2;
+        m.magic = emu::kTmapMagic;
+        std::memcpy(&tmap, &m, sizeof(m));
+        const int grid = (int)streams * g;
+        const long long cstride = (long long)n_queries * kscan;
+        std::vector<float> cand_s((size_t)grid * cstride);
+        std::vector<uint32_t> cand_i((size_t)grid * cstride);
+        std::vector<unsigned long long> tau_g((size_t)n_queries, 0ull);
+        vqa::TsLaunch a;
+        a.tmap = &tmap;
+        a.bf16 = bf16 != 0;
+        a.split = split;
+        a.a_fp16 = 0;
+        a.stages = stages;
+        a.kps = kps;
+        a.grid = grid;
+        a.n_groups = g;
+        a.multicast = 0;
+        a.q = q;
+        a.q_stride = dim;
+        a.nq = n_queries;
+        a.k = kscan;
+        a.n_rows = n_rows;
+        a.dim = dim;
+        a.cand_s = cand_s.data();
+        a.cand_i = cand_i.data();
+        a.cand_stride = cstride;
+        a.tau_g = tau_g.data();
+        a.epoch = 1;
+        if (vqa::launch_ts(a, nullptr) != cudaSuccess) throw std::runtime_error("TS scan launch failed");
+        vqa::Rescore rs;
+        rs.rows = rows;
+        rs.stride = (long long)dim * 2;
+        rs.dim = dim;
+        rs.bf16 = bf16;
+        rs.q = q;
+        rs.q_stride = dim;
+        rs.k_final = k;
+        if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, kscan, grid, kscan, split ? kscan : 32, first_id,
+                                   out_s, out_i, n_queries, tau_g.data(), g, pass_nq, nullptr,
+                                   split ? nullptr : &rs) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }

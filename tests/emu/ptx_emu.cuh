@@ -250,5 +250,43 @@ inline void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 inline void tmem_ld_wait() {}
 
+// ---- models of the three inline-PTX helpers that live in ts.cuh (build.py routes them here) ----------------
+// tcgen05.st 32x32b.x16: thread t of the warp writes lane (taddr.lane + t), 16 columns
+inline void model_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31u), col = taddr & 0xFFFFu;
+    if (lane >= 128 || col + 16 > 512) throw std::runtime_error("emu: tcgen05.st outside tensor memory");
+    for (int j = 0; j < 16; ++j) emu::T().tmem[lane][col + j] = r[j];
+}
+// tcgen05.mma with the A operand in tensor memory: row m of A is lane m, one K = 16 step is 8 consecutive
+// 32-bit columns holding the 16 sixteen-bit elements in order (element 2c in the low half of column c)
+inline void model_umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    const int n = (int)((idesc >> 17) & 0x3Fu) << 3, m = (int)((idesc >> 24) & 0x1Fu) << 4;
+    const bool a_bf16 = ((idesc >> 7) & 7u) == 1u, b_bf16 = ((idesc >> 10) & 7u) == 1u;
+    const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xFFFFu;
+    const uint32_t alane0 = tmem_a >> 16, acol0 = tmem_a & 0xFFFFu;
+    if (lane0 + (uint32_t)m > 128 || col0 + (uint32_t)n > 512 || alane0 + (uint32_t)m > 128 || acol0 + 8 > 512)
+        throw std::runtime_error("emu: MMA outside tensor memory");
+    float b[256][16];
+    for (int j = 0; j < n; ++j)
+        for (int kk = 0; kk < 16; ++kk) b[j][kk] = emu_operand(desc_b, j, kk, b_bf16);
+    for (int i = 0; i < m; ++i) {
+        float a[16];
+        for (int kk = 0; kk < 16; ++kk) {
+            const uint32_t cell = emu::T().tmem[alane0 + i][acol0 + kk / 2];
+            const uint16_t h = (uint16_t)(kk & 1 ? cell >> 16 : cell & 0xFFFFu);
+            a[kk] = emu_elem16(reinterpret_cast<const unsigned char *>(&h), a_bf16);
+        }
+        for (int j = 0; j < n; ++j) {
+            float acc = 0.0f;
+            for (int kk = 0; kk < 16; ++kk) acc = std::fmaf(a[kk], b[j][kk], acc);
+            uint32_t &cell = emu::T().tmem[lane0 + i][col0 + j];
+            float d;
+            std::memcpy(&d, &cell, 4);
+            d = accumulate ? d + acc : acc;
+            std::memcpy(&cell, &d, 4);
+        }
+    }
+}
+
 }  // namespace ptx
 }  // namespace vqa

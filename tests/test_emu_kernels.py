@@ -345,3 +345,31 @@ def test_emulated_tcgen05_search_matches_the_oracle(emu, kind, dim, n, b, k, sm,
     assert _recall(out_i, want_i) >= 0.999
     assert np.abs(out_s - want_s).max() <= 1e-5 * np.abs(want_s).max() + 2e-6
     assert out_i[0, :2].tolist() == [103, 100 + n // 2] and np.all(np.diff(out_s, axis=1) <= 0)
+
+
+@pytest.mark.parametrize("kind,dim,n,b,k,sm,split,stages,kps", [
+    ("bf16", 128, 300, 40, 10, 2, 0, 4, 2),      # screen (k + 6 candidates, 16-entry register lists) + exact re-score
+    ("bf16", 768, 500, 70, 10, 3, 0, 4, 4),      # dim 768: the query block fills 384 of the 512 TMEM columns
+    ("f16", 256, 500, 150, 5, 4, 0, 3, 2),       # two query chunks of 128 side by side, fp16 rows
+    ("bf16", 192, 300, 20, 30, 2, 1, 4, 3),      # k = 30: hi + lo query rows (64 queries per CTA), 32-entry lists
+    ("bf16", 128, 200, 10, 100, 2, 1, 4, 2),     # k = 100: binary heaps in shared memory, 8-warp reduce
+])
+def test_emulated_tmem_resident_query_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, split, stages, kps):
+    """ts_topk_kernel (query block written to tensor memory with tcgen05.st and used as the MMA's A operand,
+    thread-per-query-row epilogue with register lists / append buffers / heaps) + the reduce with the exact
+    re-scoring stage, on the host models.  Screen mode returns the exact fp32 scores (abs err ~1e-7)."""
+    emu.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
+    rng = np.random.default_rng(dim + n + b + k)
+    docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    raw, vals = _to_storage(docs, kind)
+    out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+    ok(emu, emu.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps,
+                              ptr(out_s), ptr(out_i)))
+    want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
+    assert _recall(out_i, want_i) >= 0.999
+    assert np.abs(out_s - want_s).max() <= (5e-7 if not split else 1e-5)
+    assert out_i[0, :2].tolist() == [103, 100 + n // 2] and np.all(np.diff(out_s, axis=1) <= 0)
+    if not split:
+        assert np.array_equal(out_i, want_i)
