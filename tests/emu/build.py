@@ -48,7 +48,8 @@ def _launches(src: str) -> str:
     def repl(m):
         cfg = _split_top_level(" ".join(m.group(2).split()))
         assert len(cfg) in (2, 3, 4), cfg
-        return f"emu::launch(dim3({cfg[0]}), (unsigned)({cfg[1]}), [&]() {{ {m.group(1)}({m.group(3)}); }});"
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        return f"emu::launch(dim3({cfg[0]}), (unsigned)({cfg[1]}), (size_t)({smem}), [&]() {{ {m.group(1)}({m.group(3)}); }});"
 
     return pat.sub(repl, src)
 

@@ -206,8 +206,13 @@ inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::fu
     }
 }
 
+constexpr size_t kMaxDynSmem = 227 * 1024;  // what a CTA can opt in to on sm_100
+
 template <typename F>
-inline void launch(dim3 grid, unsigned nthreads, const F &body) {
+inline void launch(dim3 grid, unsigned nthreads, size_t dyn_smem_bytes, const F &body) {
+    if (dyn_smem_bytes > kMaxDynSmem)
+        throw std::runtime_error("emu: launch asks for " + std::to_string(dyn_smem_bytes) +
+                                 " bytes of dynamic shared memory (limit " + std::to_string(kMaxDynSmem) + ")");
     gridDim = grid;
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) run_block(nthreads, bx, by, body);

@@ -12,7 +12,7 @@
 // attributes ignored (clusters are not modelled: the drivers below never ask for multicast)
 template <typename K, typename... P>
 static cudaError_t emu_launch_kernel_ex(const cudaLaunchConfig_t *cfg, K kernel, P... p) {
-    emu::launch(cfg->gridDim, cfg->blockDim.x, [&]() { kernel(p...); });
+    emu::launch(cfg->gridDim, cfg->blockDim.x, cfg->dynamicSmemBytes, [&]() { kernel(p...); });
     return cudaSuccess;
 }
 #define cudaLaunchKernelEx emu_launch_kernel_ex

@@ -20,11 +20,13 @@ L.emu_sparse_search.argtypes = [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, 
 L.emu_bm25_weights.argtypes = [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp]
 L.emu_pool_normalize.argtypes = [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
 T._bind_search(L)
+L.emu_search_tensor.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]
+L.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 t_end = time.time() + float(sys.argv[2]) if len(sys.argv) > 2 else time.time() + 120
 n_ok = 0
 while time.time() < t_end:
-    which = rng.integers(3)
+    which = rng.integers(5)
     if which == 0:   # verify search
         kind = ["f32", "bf16", "f16"][rng.integers(3)]
         dim = int(rng.choice([8, 16, 64, 128, 200, 384, 512, 768, 1024])) if kind == "f32" else int(rng.choice([8, 64, 128, 384, 768, 1024, 1032]))
@@ -49,6 +51,43 @@ while time.time() < t_end:
         got = e.search(qs, limit)
         for qq, g in zip(qs, got):
             assert g == ref.search(qq, limit), ("sparse", n_docs, vocab, normalize, sm, limit, qq)
+    elif which in (3, 4):  # tcgen05 kernels on the host models of ptx.cuh
+        kind = ["bf16", "f16"][rng.integers(2)]
+        dim = int(rng.choice([64, 128, 192, 256, 384, 512, 768]))
+        n = int(rng.integers(1, 900)); sm = int(rng.choice([1, 2, 3, 7, 148]))
+        kb = dim // 64
+        docs = T._unit(rng, n, dim)
+        if n > 4: docs[n // 2] = docs[0]
+        raw, vals = T._to_storage(docs, kind)
+        if which == 3:
+            ncol = int(rng.choice([16, 32, 64, 128])); b = int(rng.integers(1, 2 * ncol)); k = int(rng.choice([1, 3, 10, 32, 40]))
+            kps = int(rng.choice([d for d in (1, 2, 3) if kb % d == 0])); stages = int(rng.integers(2, 7))
+            if b > 4 * (ncol // 2): b = 4 * (ncol // 2)
+            nq_cta = ncol // 2
+            lists = 0 if (nq_cta <= 32 and k <= 32) else nq_cta * ((k + 31) // 32 * 32) * 8 + nq_cta * 8
+            boxes = (227 * 1024 - (1024 + kb * ncol * 128 + 1024 + lists)) // 16384     # as plan_tensor sizes the ring
+            stages = min(stages, boxes // kps)
+            if stages < 2: continue
+            q = T._unit(rng, b, dim)
+            out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+            if os.environ.get("FUZZ_VERBOSE"): print("mma", kind, dim, n, b, k, sm, ncol, stages, kps, flush=True)
+            rc = L.emu_search_tensor(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, ncol, stages, kps, T.ptr(out_s), T.ptr(out_i))
+            tag = ("mma", kind, dim, n, b, k, sm, ncol, stages, kps); tol = 1e-5
+        else:
+            split = int(rng.integers(2)); k = int(rng.choice([1, 5, 10, 26])) if not split else int(rng.choice([3, 20, 32, 50]))
+            b = int(rng.integers(1, 200)); kps = int(rng.choice([d for d in (1, 2, 3, 4) if kb % d == 0])); stages = int(rng.integers(2, 6))
+            q = T._unit(rng, b, dim)
+            out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+            if os.environ.get("FUZZ_VERBOSE"): print("ts", kind, dim, n, b, k, sm, split, stages, kps, flush=True)
+            rc = L.emu_search_ts(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, split, 6, stages, kps, T.ptr(out_s), T.ptr(out_i))
+            tag = ("ts", kind, dim, n, b, k, sm, split, stages, kps); tol = 1e-5 if split else 5e-7
+        assert rc == 0, (L.emu_last_error(), tag)
+        ws, wi = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=7)
+        fin = wi >= 0
+        assert np.array_equal(out_i >= 0, fin), tag
+        rec = np.mean([len(set(out_i[r][fin[r]]) & set(wi[r][fin[r]])) / max(1, fin[r].sum()) for r in range(b)])
+        assert rec >= 0.999 or (np.abs(np.sort(out_s[fin]) - np.sort(ws[fin])).max() <= 2e-6), (tag, rec)
+        assert np.abs(out_s[fin] - ws[fin]).max() <= tol * max(1.0, np.abs(ws[fin]).max()) + 2e-6, tag
     else:  # K1
         kind = ["f32", "bf16", "f16"][rng.integers(3)]
         dim = int(rng.choice([8, 64, 128, 384, 512, 768, 1024, 2048]))
