@@ -214,8 +214,20 @@ inline void launch(dim3 grid, unsigned nthreads, size_t dyn_smem_bytes, const F 
         throw std::runtime_error("emu: launch asks for " + std::to_string(dyn_smem_bytes) +
                                  " bytes of dynamic shared memory (limit " + std::to_string(kMaxDynSmem) + ")");
     gridDim = grid;
+    State &s = S();
+    // everything past the bytes the launch asked for is a guard zone: a kernel whose shared-memory layout
+    // outgrows its size formula is caught here instead of silently corrupting (or faulting) on the device
+    unsigned char *guard = s.dyn_smem + dyn_smem_bytes;
+    const size_t guard_len = sizeof(s.dyn_smem) - dyn_smem_bytes;
     for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx) run_block(nthreads, bx, by, body);
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+            std::memset(guard, 0xCB, guard_len);
+            run_block(nthreads, bx, by, body);
+            for (size_t i = 0; i < guard_len; ++i)
+                if (guard[i] != 0xCB)
+                    throw std::runtime_error("emu: shared memory written at byte " + std::to_string(dyn_smem_bytes + i) +
+                                             " but the launch asked for only " + std::to_string(dyn_smem_bytes));
+        }
 }
 
 }  // namespace emu
