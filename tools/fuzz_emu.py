@@ -76,6 +76,12 @@ while time.time() < t_end:
         else:
             split = int(rng.integers(2)); k = int(rng.choice([1, 5, 10, 26])) if not split else int(rng.choice([3, 20, 32, 50]))
             b = int(rng.integers(1, 200)); kps = int(rng.choice([d for d in (1, 2, 3, 4) if kb % d == 0])); stages = int(rng.integers(2, 6))
+            kscan = k if split else k + 6
+            depth = 32 if kscan <= 32 else kscan + 32
+            lrows = 64 if (kscan > 32 and split) else 128
+            fixed = 1024 + 1024 + (2 * 64 * 64 * 4 if split else 0) + lrows * depth * 8    # ts_smem_bytes_rt without the ring
+            stages = min(stages, ((227 * 1024 - fixed) // 8192) // kps)                    # as plan_ts sizes the ring
+            if stages < 2: continue
             q = T._unit(rng, b, dim)
             out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
             if os.environ.get("FUZZ_VERBOSE"): print("ts", kind, dim, n, b, k, sm, split, stages, kps, flush=True)
