@@ -57,7 +57,7 @@ def _launches(src: str) -> str:
 def transform(name: str, src: str) -> str:
     n_ext = len(re.findall(r"extern\s+__shared__", src))
     src, n = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char\s+(\w+)\[\];",
-                     r"unsigned char *\1 = emu::S().dyn_smem;", src)
+                     r"unsigned char *\1 = emu::cur_smem();", src)
     assert n == n_ext, f"{name}: {n_ext} extern __shared__ declarations, {n} transformed"
     if name == "common.cuh":
         src, a = re.subn(r'asm volatile\("griddepcontrol\.wait;" ::: "memory"\);', ";", src)

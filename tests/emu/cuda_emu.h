@@ -46,14 +46,21 @@ struct Fiber {
     bool done = true;
 };
 
+constexpr int kMaxCluster = 4;
+
+struct CtaBarrier {  // __syncthreads and its count / or forms, per CTA
+    int arrived = 0, gen = 0, acc_cnt = 0, acc_or = 0, res_cnt = 0, res_or = 0, alive = 0;
+};
+
 struct State {
     Fiber f[kMaxThreads];
     ucontext_t sched;
-    int cur = 0, n = 0, alive = 0;
+    int cur = 0, n = 0;            // running fiber, fibers in flight (= cluster * nthr)
+    int nthr = 0, cluster = 1;     // threads per CTA, CTAs that run together (a thread-block cluster)
     std::function<void()> body;
-    // block barrier
-    int bar_arrived = 0, bar_gen = 0, acc_cnt = 0, acc_or = 0, res_cnt = 0, res_or = 0;
-    // warp collectives
+    CtaBarrier bar[kMaxCluster];
+    int cl_arrived = 0, cl_gen = 0;  // barrier.cluster
+    // warp collectives (warps never straddle CTAs: block sizes are multiples of 32)
     int w_arrived[kMaxThreads / 32] = {}, w_gen[kMaxThreads / 32] = {};
     unsigned long long wbuf[kMaxThreads / 32][32] = {};
     long progress = 0;
@@ -62,36 +69,51 @@ struct State {
     int schedule = 0;
     unsigned long long rng = 0x9E3779B97F4A7C15ull;
     int order[kMaxThreads];
-    // dynamic shared memory of the running block
-    alignas(1024) unsigned char dyn_smem[232 * 1024];  // 1024: offsets and addresses share their low bits (swizzle)
+    // dynamic shared memory of every CTA of the running cluster
+    // (1024-aligned: offsets and addresses share their low bits, which the 128-byte swizzle works on)
+    alignas(1024) unsigned char dyn_smem[kMaxCluster][232 * 1024];
 };
 inline State &S() {
     static State s;
     return s;
 }
+inline int cur_cta() { return S().nthr ? S().cur / S().nthr : 0; }
+inline unsigned char *cur_smem() { return S().dyn_smem[cur_cta()]; }
 
 inline void yield() {
     State &s = S();
     swapcontext(&s.f[s.cur].ctx, &s.sched);
 }
 
-inline void complete_barrier(State &s) {
-    s.res_cnt = s.acc_cnt;
-    s.res_or = s.acc_or;
-    s.acc_cnt = s.acc_or = 0;
-    s.bar_arrived = 0;
-    ++s.bar_gen;
+inline void complete_barrier(State &s, CtaBarrier &b) {
+    b.res_cnt = b.acc_cnt;
+    b.res_or = b.acc_or;
+    b.acc_cnt = b.acc_or = 0;
+    b.arrived = 0;
+    ++b.gen;
     ++s.progress;
 }
 
 inline void block_barrier(int pred) {
     State &s = S();
-    const int gen = s.bar_gen;
-    s.acc_cnt += pred != 0;
-    s.acc_or |= pred != 0;
-    if (++s.bar_arrived == s.alive) complete_barrier(s);
+    CtaBarrier &b = s.bar[cur_cta()];
+    const int gen = b.gen;
+    b.acc_cnt += pred != 0;
+    b.acc_or |= pred != 0;
+    if (++b.arrived == b.alive) complete_barrier(s, b);
     else
-        while (s.bar_gen == gen) yield();
+        while (b.gen == gen) yield();
+}
+
+inline void cluster_barrier() {  // all threads of all CTAs of the cluster
+    State &s = S();
+    const int gen = s.cl_gen;
+    if (++s.cl_arrived == s.n) {
+        s.cl_arrived = 0;
+        ++s.cl_gen;
+        ++s.progress;
+    } else
+        while (s.cl_gen == gen) yield();
 }
 
 inline void warp_barrier() {
@@ -136,16 +158,23 @@ inline dim3 blockDim, gridDim;
 
 namespace emu {
 
-// Run one thread block: `body` is executed once per CUDA thread.
-inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::function<void()> &body) {
+// Run one cluster of `cluster` thread blocks (blockIdx.x = first_bx .. first_bx + cluster - 1) together: `body` is
+// executed once per CUDA thread; a plain launch is a cluster of one.
+inline void run_cluster(unsigned nthreads, unsigned first_bx, unsigned by, int cluster, const std::function<void()> &body) {
     State &s = S();
-    if (nthreads == 0 || nthreads > (unsigned)kMaxThreads || nthreads % 32 != 0)
-        throw std::runtime_error("emu: block size must be a multiple of 32 and <= 1024");
-    s.n = s.alive = (int)nthreads;
+    if (nthreads == 0 || nthreads % 32 != 0 || cluster < 1 || cluster > kMaxCluster ||
+        nthreads * (unsigned)cluster > (unsigned)kMaxThreads)
+        throw std::runtime_error("emu: block size must be a multiple of 32, cluster <= 4, <= 1024 threads in flight");
+    s.nthr = (int)nthreads;
+    s.cluster = cluster;
+    s.n = (int)nthreads * cluster;
     s.body = body;
-    s.bar_arrived = s.acc_cnt = s.acc_or = 0;
+    for (int c = 0; c < cluster; ++c) {
+        s.bar[c] = CtaBarrier();
+        s.bar[c].alive = (int)nthreads;
+    }
+    s.cl_arrived = 0;
     for (auto &x : s.w_arrived) x = 0;
-    blockIdx.x = bx;
     blockIdx.y = by;
     blockIdx.z = 0;
     blockDim = dim3(nthreads, 1, 1);
@@ -179,10 +208,11 @@ inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::fu
             const int t = s.order[oi];
             if (s.f[t].done) continue;
             s.cur = t;
-            threadIdx.x = (unsigned)t;
+            threadIdx.x = (unsigned)(t % s.nthr);
             threadIdx.y = threadIdx.z = 0;
+            blockIdx.x = first_bx + (unsigned)(t / s.nthr);
             swapcontext(&s.sched, &s.f[t].ctx);
-            if (!s.error.empty()) {  // abandon the block: the other fibers' stacks are simply dropped
+            if (!s.error.empty()) {  // abandon the cluster: the other fibers' stacks are simply dropped
                 const std::string msg = s.error;
                 s.error.clear();
                 for (int u = 0; u < s.n; ++u) s.f[u].done = true;
@@ -190,16 +220,17 @@ inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::fu
             }
             if (s.f[t].done) {
                 --remaining;
-                --s.alive;
                 ++s.progress;
-                // exited threads no longer take part in block barriers
-                if (s.alive > 0 && s.bar_arrived == s.alive) complete_barrier(s);
+                // exited threads no longer take part in their CTA's barriers
+                CtaBarrier &b = s.bar[t / s.nthr];
+                --b.alive;
+                if (b.alive > 0 && b.arrived == b.alive) complete_barrier(s, b);
             }
         }
         if (s.progress == before) {
             if (++idle_rounds > 4) {
                 for (int u = 0; u < s.n; ++u) s.f[u].done = true;
-                throw std::runtime_error("emu: deadlock (divergent barrier or warp collective)");
+                throw std::runtime_error("emu: deadlock (divergent barrier, warp collective or mbarrier wait)");
             }
         } else
             idle_rounds = 0;
@@ -209,24 +240,27 @@ inline void run_block(unsigned nthreads, unsigned bx, unsigned by, const std::fu
 constexpr size_t kMaxDynSmem = 227 * 1024;  // what a CTA can opt in to on sm_100
 
 template <typename F>
-inline void launch(dim3 grid, unsigned nthreads, size_t dyn_smem_bytes, const F &body) {
+inline void launch(dim3 grid, unsigned nthreads, size_t dyn_smem_bytes, const F &body, int cluster = 1) {
     if (dyn_smem_bytes > kMaxDynSmem)
         throw std::runtime_error("emu: launch asks for " + std::to_string(dyn_smem_bytes) +
                                  " bytes of dynamic shared memory (limit " + std::to_string(kMaxDynSmem) + ")");
+    if (cluster < 1 || cluster > kMaxCluster || grid.x % (unsigned)cluster != 0)
+        throw std::runtime_error("emu: grid.x must be a multiple of the cluster size (<= 4)");
     gridDim = grid;
     State &s = S();
     // everything past the bytes the launch asked for is a guard zone: a kernel whose shared-memory layout
     // outgrows its size formula is caught here instead of silently corrupting (or faulting) on the device
-    unsigned char *guard = s.dyn_smem + dyn_smem_bytes;
-    const size_t guard_len = sizeof(s.dyn_smem) - dyn_smem_bytes;
+    const size_t guard_len = sizeof(s.dyn_smem[0]) - dyn_smem_bytes;
     for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx) {
-            std::memset(guard, 0xCB, guard_len);
-            run_block(nthreads, bx, by, body);
-            for (size_t i = 0; i < guard_len; ++i)
-                if (guard[i] != 0xCB)
-                    throw std::runtime_error("emu: shared memory written at byte " + std::to_string(dyn_smem_bytes + i) +
-                                             " but the launch asked for only " + std::to_string(dyn_smem_bytes));
+        for (unsigned bx = 0; bx < grid.x; bx += (unsigned)cluster) {
+            for (int c = 0; c < cluster; ++c) std::memset(s.dyn_smem[c] + dyn_smem_bytes, 0xCB, guard_len);
+            run_cluster(nthreads, bx, by, cluster, body);
+            for (int c = 0; c < cluster; ++c)
+                for (size_t i = 0; i < guard_len; ++i)
+                    if (s.dyn_smem[c][dyn_smem_bytes + i] != 0xCB)
+                        throw std::runtime_error("emu: shared memory written at byte " +
+                                                 std::to_string(dyn_smem_bytes + i) + " but the launch asked for only " +
+                                                 std::to_string(dyn_smem_bytes));
         }
 }
 
@@ -236,11 +270,11 @@ inline void launch(dim3 grid, unsigned nthreads, size_t dyn_smem_bytes, const F 
 inline void __syncthreads() { emu::block_barrier(0); }
 inline int __syncthreads_count(int pred) {
     emu::block_barrier(pred);
-    return emu::S().res_cnt;
+    return emu::S().bar[emu::cur_cta()].res_cnt;
 }
 inline int __syncthreads_or(int pred) {
     emu::block_barrier(pred);
-    return emu::S().res_or;
+    return emu::S().bar[emu::cur_cta()].res_or;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 inline void __threadfence_block() {}

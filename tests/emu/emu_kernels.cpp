@@ -9,10 +9,13 @@
 #define cudaGetLastError() cudaSuccess
 
 // cudaLaunchKernelEx (PDL launch of the reduce kernels, cluster launch of the tensor kernels): same grid / block,
-// attributes ignored (clusters are not modelled: the drivers below never ask for multicast)
+// the cluster dimension attribute is honoured, the others are ignored
 template <typename K, typename... P>
 static cudaError_t emu_launch_kernel_ex(const cudaLaunchConfig_t *cfg, K kernel, P... p) {
-    emu::launch(cfg->gridDim, cfg->blockDim.x, cfg->dynamicSmemBytes, [&]() { kernel(p...); });
+    int cluster = 1;
+    for (unsigned i = 0; i < cfg->numAttrs; ++i)
+        if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) cluster = (int)cfg->attrs[i].val.clusterDim.x;
+    emu::launch(cfg->gridDim, cfg->blockDim.x, cfg->dynamicSmemBytes, [&]() { kernel(p...); }, cluster);
     return cudaSuccess;
 }
 #define cudaLaunchKernelEx emu_launch_kernel_ex
@@ -182,10 +185,17 @@ int emu_reduce_rescore(const float *cand_s, const uint32_t *cand_i, int n_lists,
 // as api.cu does it.  rows: 16-bit storage [n_rows][dim]; ncol in {16, 32, 64, 128}; the batch is cut into chunks
 // of ncol / 2 queries handled side by side (n_groups = chunks).
 int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, const float *q, int n_queries, int k,
-                      long long first_id, int sm_count, int ncol, int stages, int kps, float *out_s, long long *out_i) {
+                      long long first_id, int sm_count, int ncol, int stages, int kps, int multicast, float *out_s,
+                      long long *out_i) {
     return guarded([&] {
         const int pass_nq = ncol / 2;
-        const int g = (n_queries + pass_nq - 1) / pass_nq;
+        int g = (n_queries + pass_nq - 1) / pass_nq;
+        if (multicast) {  // cluster sizes are powers of two; a short launch gets empty chunks (api.cu)
+            int lg = 0;
+            while ((1 << lg) < g) ++lg;
+            g = 1 << lg;
+        }
+        const bool mc = multicast && g > 1;
         const long long tiles = (n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
         long long streams = sm_count / g;
         if (streams > tiles) streams = tiles;
@@ -198,7 +208,7 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
         m.dim1 = (unsigned long long)n_rows;
         m.stride1_bytes = (unsigned long long)dim * 2;
         m.box0 = 64;
-        m.box1 = vqa::kTileRows;
+        m.box1 = vqa::kTileRows / (mc ? g : 1);  // multicast: each CTA fetches a slice of the box for everybody
         m.elem_bytes = 2;
         m.magic = emu::kTmapMagic;
         std::memcpy(&tmap, &m, sizeof(m));
@@ -216,7 +226,7 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
         a.kps = kps;
         a.grid = grid;
         a.n_groups = g;
-        a.multicast = 0;
+        a.multicast = mc ? 1 : 0;
         a.q = q;
         a.q_stride = dim;
         a.nq = n_queries;
@@ -239,12 +249,18 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
 // as api.cu does it.  split = 0: storage-precision screen with k + spare candidates per query, the 32 best
 // re-scored exactly by the reduce; split = 1: hi + lo query rows (64 queries per CTA), no re-scoring.
 int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const float *q, int n_queries, int k,
-                  long long first_id, int sm_count, int split, int spare, int stages, int kps, float *out_s,
-                  long long *out_i) {
+                  long long first_id, int sm_count, int split, int spare, int stages, int kps, int multicast,
+                  float *out_s, long long *out_i) {
     return guarded([&] {
         const int pass_nq = split ? 64 : 128;
         const int kscan = split ? k : k + spare;
-        const int g = (n_queries + pass_nq - 1) / pass_nq;
+        int g = (n_queries + pass_nq - 1) / pass_nq;
+        if (multicast) {
+            int lg = 0;
+            while ((1 << lg) < g) ++lg;
+            g = 1 << lg;
+        }
+        const bool mc = multicast && g > 1;
         const long long tiles = (n_rows + 63) / 64;
         long long streams = sm_count / g;
         if (streams > tiles) streams = tiles;
@@ -257,7 +273,7 @@ int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const f
         m.dim1 = (unsigned long long)n_rows;
         m.stride1_bytes = (unsigned long long)dim * 2;
         m.box0 = 64;
-        m.box1 = 64;
+        m.box1 = 64 / (mc ? g : 1);
         m.elem_bytes = 2;
         m.magic = emu::kTmapMagic;
         std::memcpy(&tmap, &m, sizeof(m));
@@ -275,7 +291,7 @@ int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const f
         a.kps = kps;
         a.grid = grid;
         a.n_groups = g;
-        a.multicast = 0;
+        a.multicast = mc ? 1 : 0;
         a.q = q;
         a.q_stride = dim;
         a.nq = n_queries;

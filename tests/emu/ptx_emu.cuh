@@ -14,7 +14,9 @@
 //                                  through K-major SWIZZLE_128B shared-memory descriptors, executed at issue;
 //                                  tcgen05.commit therefore arrives at once
 //   * tcgen05.ld 32x32b.x16     -- thread t of the warp reads lane (taddr.lane + t), 16 columns
-// Not modelled: clusters / multicast (the emulated launches use cluster size 1), cache policies, proxies.
+//   * thread-block clusters     -- up to 4 CTAs run together, each with its own shared and tensor memory;
+//                                  TMA multicast and multicast commits address the same offset in every CTA
+// Not modelled: cache policies, memory proxies, timing.
 #pragma once
 
 #include <cuda.h>
@@ -42,20 +44,25 @@ struct MBar {  // the 8 bytes of an mbarrier
 };
 static_assert(sizeof(MBar) == 8, "mbarrier is 8 bytes");
 
-struct TensorState {
+struct TensorState {  // per CTA
     uint32_t tmem[128][512];
     int nb_arrived[16] = {}, nb_gen[16] = {};
 };
 inline TensorState &T() {
-    static TensorState t;
-    return t;
+    static TensorState t[kMaxCluster];
+    return t[cur_cta()];
 }
 
-inline unsigned char *smem_base() { return S().dyn_smem; }
+inline unsigned char *smem_base() { return cur_smem(); }
+inline unsigned char *smem_base_of(int cta) { return S().dyn_smem[cta]; }
+// offset of a shared-memory pointer inside its CTA's window (the same offset names the same object in a peer CTA)
 inline uint32_t smem_off(const void *p) {
-    const long long d = static_cast<const unsigned char *>(p) - smem_base();
-    if (d < 0 || d >= (long long)sizeof(S().dyn_smem)) throw std::runtime_error("emu: pointer outside shared memory");
-    return (uint32_t)d;
+    const unsigned char *c = static_cast<const unsigned char *>(p);
+    for (int k = 0; k < kMaxCluster; ++k) {
+        const long long d = c - S().dyn_smem[k];
+        if (d >= 0 && d < (long long)sizeof(S().dyn_smem[k])) return (uint32_t)d;
+    }
+    throw std::runtime_error("emu: pointer outside shared memory");
 }
 // SWIZZLE_128B: bits [4,7) of the address XOR bits [7,10)
 inline uint32_t swz128(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
@@ -146,16 +153,15 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 inline void prefetch_tmap(const void *) {}
-inline void tma_load_2d(void *smem_dst, const void *tmap, int32_t c0, int32_t c1, uint64_t *bar, uint64_t) {
-    const emu::EmuTmap *m = static_cast<const emu::EmuTmap *>(tmap);
-    if (m->magic != emu::kTmapMagic) throw std::runtime_error("emu: not an emulated tensor map");
+// copy one box into CTA `cta`'s shared memory at offset `dst` and complete its bytes on that CTA's mbarrier
+inline void emu_tma_box(int cta, uint32_t dst, const emu::EmuTmap *m, int32_t c0, int32_t c1, uint32_t bar_off) {
     const uint32_t row_bytes = m->box0 * m->elem_bytes;
     if (row_bytes != 128) throw std::runtime_error("emu: only 128-byte box rows (SWIZZLE_128B) are modelled");
-    const uint32_t dst = emu::smem_off(smem_dst);
+    unsigned char *base = emu::smem_base_of(cta);
     for (uint32_t r = 0; r < m->box1; ++r) {
         const long long row = (long long)c1 + r;
         for (uint32_t ch = 0; ch < 8; ++ch) {
-            unsigned char *out = emu::smem_base() + emu::swz128(dst + r * 128 + ch * 16);
+            unsigned char *out = base + emu::swz128(dst + r * 128 + ch * 16);
             const long long col = (long long)c0 + (long long)ch * (16 / m->elem_bytes);
             const bool inside = row >= 0 && row < (long long)m->dim1 && col >= 0 &&
                                 col + (16 / m->elem_bytes) <= (long long)m->dim0;
@@ -163,17 +169,29 @@ inline void tma_load_2d(void *smem_dst, const void *tmap, int32_t c0, int32_t c1
             else std::memset(out, 0, 16);
         }
     }
-    emu::MBar *b = reinterpret_cast<emu::MBar *>(bar);
+    emu::MBar *b = reinterpret_cast<emu::MBar *>(base + bar_off);
     b->tx -= (int32_t)(m->box1 * row_bytes);
     emu::mbar_check(b);
 }
-inline void tma_load_2d_multicast(void *, const void *, int32_t, int32_t, uint64_t *, uint16_t, uint64_t) {
-    throw std::runtime_error("emu: TMA multicast (clusters) is not modelled");
+inline const emu::EmuTmap *emu_tmap(const void *tmap) {
+    const emu::EmuTmap *m = static_cast<const emu::EmuTmap *>(tmap);
+    if (m->magic != emu::kTmapMagic) throw std::runtime_error("emu: not an emulated tensor map");
+    return m;
+}
+inline void tma_load_2d(void *smem_dst, const void *tmap, int32_t c0, int32_t c1, uint64_t *bar, uint64_t) {
+    emu_tma_box(emu::cur_cta(), emu::smem_off(smem_dst), emu_tmap(tmap), c0, c1, emu::smem_off(bar));
+}
+// multicast: the box lands at the same offset in every CTA of the mask and completes on the mbarrier at the
+// same offset in each of them
+inline void tma_load_2d_multicast(void *smem_dst, const void *tmap, int32_t c0, int32_t c1, uint64_t *bar,
+                                  uint16_t cta_mask, uint64_t) {
+    for (int c = 0; c < emu::S().cluster; ++c)
+        if (cta_mask & (1u << c)) emu_tma_box(c, emu::smem_off(smem_dst), emu_tmap(tmap), c0, c1, emu::smem_off(bar));
 }
 
-// ---- thread-block clusters (size 1 only) -------------------------------------------
-inline uint32_t cluster_ctarank() { return 0; }
-inline void cluster_sync_all() { __syncthreads(); }
+// ---- thread-block clusters ------------------------------------------------------------
+inline uint32_t cluster_ctarank() { return (uint32_t)emu::cur_cta(); }
+inline void cluster_sync_all() { emu::cluster_barrier(); }
 
 // ---- tcgen05: TMEM allocation -----------------------------------------------
 inline void tmem_alloc(uint32_t *smem_dst, uint32_t) { *smem_dst = 0; }  // lane 0, column 0
@@ -238,8 +256,11 @@ inline void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t
     }
 }
 inline void umma_commit(uint64_t *bar) { mbar_arrive(bar); }  // MMAs execute at issue: nothing is in flight
-inline void umma_commit_multicast(uint64_t *, uint16_t) {
-    throw std::runtime_error("emu: multicast commit (clusters) is not modelled");
+// arrive on the mbarrier at this offset in every CTA of the mask
+inline void umma_commit_multicast(uint64_t *bar, uint16_t cta_mask) {
+    const uint32_t off = emu::smem_off(bar);
+    for (int c = 0; c < emu::S().cluster; ++c)
+        if (cta_mask & (1u << c)) mbar_arrive(reinterpret_cast<uint64_t *>(emu::smem_base_of(c) + off));
 }
 
 // ---- tcgen05: TMEM -> registers ----------------------------------------------

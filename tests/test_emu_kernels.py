@@ -318,28 +318,31 @@ def _recall(got, want):
     return float(np.mean([len(set(got[r]) & set(want[r])) / k for r in range(want.shape[0])]))
 
 
-@pytest.mark.parametrize("kind,dim,n,b,k,sm,ncol,stages,kps", [
-    ("bf16", 128, 300, 3, 5, 2, 16, 4, 2),       # NCOL 16: hi and lo in one TMEM load; last tile partly outside
-    ("bf16", 768, 1000, 8, 10, 3, 16, 4, 2),     # the headline shape in miniature (dim 768, top-10), 3 CTAs
-    ("f16", 768, 700, 20, 10, 4, 64, 3, 2),      # fp16 rows (scaled residual), 32 queries per CTA
-    ("bf16", 256, 1100, 40, 10, 8, 32, 4, 1),    # 3 query chunks side by side (n_groups = 3), one box per stage
-    ("bf16", 192, 90, 5, 32, 148, 16, 4, 3),     # fewer rows than one tile, k = 32 (full register lists), kps = 3
-    ("f16", 128, 600, 6, 40, 2, 16, 5, 2),       # k > 32: CTA-shared sorted lists behind the spin lock
-    ("bf16", 64, 2000, 70, 3, 4, 128, 6, 1),     # NCOL 128: 64 queries per CTA, 2 chunks, shared-memory lists
+@pytest.mark.parametrize("kind,dim,n,b,k,sm,ncol,stages,kps,mc", [
+    ("bf16", 128, 300, 3, 5, 2, 16, 4, 2, 0),       # NCOL 16: hi and lo in one TMEM load; last tile partly outside
+    ("bf16", 768, 1000, 8, 10, 3, 16, 4, 2, 0),     # the headline shape in miniature (dim 768, top-10), 3 CTAs
+    ("f16", 768, 700, 20, 10, 4, 64, 3, 2, 0),      # fp16 rows (scaled residual), 32 queries per CTA
+    ("bf16", 256, 1100, 40, 10, 8, 32, 4, 1, 0),    # 3 query chunks side by side through L2 (n_groups = 3)
+    ("bf16", 192, 90, 5, 32, 148, 16, 4, 3, 0),     # fewer rows than one tile, k = 32 (full register lists), kps = 3
+    ("f16", 128, 600, 6, 40, 2, 16, 5, 2, 0),       # k > 32: CTA-shared sorted lists behind the spin lock
+    ("bf16", 64, 2000, 70, 3, 4, 128, 6, 1, 0),     # NCOL 128: 64 queries per CTA, 2 chunks, shared-memory lists
+    ("bf16", 256, 900, 30, 10, 8, 32, 4, 2, 1),     # cluster of 2: each CTA multicasts half of every box
+    ("f16", 128, 700, 40, 5, 16, 32, 3, 1, 1),      # cluster of 4 (3 chunks + an empty one), quarter-box slices
 ])
-def test_emulated_tcgen05_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, ncol, stages, kps):
+def test_emulated_tcgen05_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, ncol, stages, kps, mc):
     """mma_topk_kernel (TMA producer / MMA issuer / TMEM epilogue with register top-k lists and GPU-wide
-    thresholds) + the reduce, on the host models of mbarrier, TMA (128-byte swizzle), tcgen05.mma / commit / ld and
-    named barriers.  Bar of the GPU tests: recall against fp32 arithmetic on the stored rows, rank-wise scores
+    thresholds) + the reduce, on the host models of mbarrier, TMA (128-byte swizzle; multicast across a cluster),
+    tcgen05.mma / commit / ld and named barriers.  Bar of the GPU tests: recall against fp32 arithmetic on the stored rows, rank-wise scores
     within 1e-5 relative; here the ids are in fact identical, duplicates lower id first."""
-    emu.emu_search_tensor.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]
+    emu.emu_search_tensor.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp,
+                                      _vp]
     rng = np.random.default_rng(dim + n + b)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
     docs[n // 2] = docs[3]
     q[0] = docs[3]
     raw, vals = _to_storage(docs, kind)
     out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-    ok(emu, emu.emu_search_tensor(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, ncol, stages, kps,
+    ok(emu, emu.emu_search_tensor(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, ncol, stages, kps, mc,
                                   ptr(out_s), ptr(out_i)))
     want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
     assert _recall(out_i, want_i) >= 0.999
@@ -347,25 +350,27 @@ def test_emulated_tcgen05_search_matches_the_oracle(emu, kind, dim, n, b, k, sm,
     assert out_i[0, :2].tolist() == [103, 100 + n // 2] and np.all(np.diff(out_s, axis=1) <= 0)
 
 
-@pytest.mark.parametrize("kind,dim,n,b,k,sm,split,stages,kps", [
-    ("bf16", 128, 300, 40, 10, 2, 0, 4, 2),      # screen (k + 6 candidates, 16-entry register lists) + exact re-score
-    ("bf16", 768, 500, 70, 10, 3, 0, 4, 4),      # dim 768: the query block fills 384 of the 512 TMEM columns
-    ("f16", 256, 500, 150, 5, 4, 0, 3, 2),       # two query chunks of 128 side by side, fp16 rows
-    ("bf16", 192, 300, 20, 30, 2, 1, 4, 3),      # k = 30: hi + lo query rows (64 queries per CTA), 32-entry lists
-    ("bf16", 128, 200, 10, 100, 2, 1, 4, 2),     # k = 100: binary heaps in shared memory, 8-warp reduce
+@pytest.mark.parametrize("kind,dim,n,b,k,sm,split,stages,kps,mc", [
+    ("bf16", 128, 300, 40, 10, 2, 0, 4, 2, 0),      # screen (k + 6 candidates, 16-entry register lists) + exact re-score
+    ("bf16", 768, 500, 70, 10, 3, 0, 4, 4, 0),      # dim 768: the query block fills 384 of the 512 TMEM columns
+    ("f16", 256, 500, 150, 5, 4, 0, 3, 2, 0),       # two query chunks of 128 side by side through L2, fp16 rows
+    ("bf16", 192, 300, 20, 30, 2, 1, 4, 3, 0),      # k = 30: hi + lo query rows (64 queries per CTA), 32-entry lists
+    ("bf16", 128, 200, 10, 100, 2, 1, 4, 2, 0),     # k = 100: binary heaps in shared memory, 8-warp reduce
+    ("bf16", 256, 600, 200, 10, 6, 0, 4, 2, 1),     # cluster of 2 with TMA multicast (the default for B > 128)
 ])
-def test_emulated_tmem_resident_query_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, split, stages, kps):
+def test_emulated_tmem_resident_query_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, split, stages, kps, mc):
     """ts_topk_kernel (query block written to tensor memory with tcgen05.st and used as the MMA's A operand,
     thread-per-query-row epilogue with register lists / append buffers / heaps) + the reduce with the exact
     re-scoring stage, on the host models.  Screen mode returns the exact fp32 scores (abs err ~1e-7)."""
-    emu.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
+    emu.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
+                                  _vp]
     rng = np.random.default_rng(dim + n + b + k)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
     docs[n // 2] = docs[3]
     q[0] = docs[3]
     raw, vals = _to_storage(docs, kind)
     out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-    ok(emu, emu.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps,
+    ok(emu, emu.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps, mc,
                               ptr(out_s), ptr(out_i)))
     want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
     assert _recall(out_i, want_i) >= 0.999

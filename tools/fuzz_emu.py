@@ -20,8 +20,8 @@ L.emu_sparse_search.argtypes = [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, 
 L.emu_bm25_weights.argtypes = [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp]
 L.emu_pool_normalize.argtypes = [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
 T._bind_search(L)
-L.emu_search_tensor.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _vp, _vp]
-L.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
+L.emu_search_tensor.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
+L.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 t_end = time.time() + float(sys.argv[2]) if len(sys.argv) > 2 else time.time() + 120
 n_ok = 0
@@ -59,6 +59,7 @@ while time.time() < t_end:
         docs = T._unit(rng, n, dim)
         if n > 4: docs[n // 2] = docs[0]
         raw, vals = T._to_storage(docs, kind)
+        mc = int(rng.integers(2))          # thread-block clusters with TMA multicast
         if which == 3:
             ncol = int(rng.choice([16, 32, 64, 128])); b = int(rng.integers(1, 2 * ncol)); k = int(rng.choice([1, 3, 10, 32, 40]))
             kps = int(rng.choice([d for d in (1, 2, 3) if kb % d == 0])); stages = int(rng.integers(2, 7))
@@ -70,9 +71,9 @@ while time.time() < t_end:
             if stages < 2: continue
             q = T._unit(rng, b, dim)
             out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-            if os.environ.get("FUZZ_VERBOSE"): print("mma", kind, dim, n, b, k, sm, ncol, stages, kps, flush=True)
-            rc = L.emu_search_tensor(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, ncol, stages, kps, T.ptr(out_s), T.ptr(out_i))
-            tag = ("mma", kind, dim, n, b, k, sm, ncol, stages, kps); tol = 1e-5
+            if os.environ.get("FUZZ_VERBOSE"): print("mma", kind, dim, n, b, k, sm, ncol, stages, kps, mc, flush=True)
+            rc = L.emu_search_tensor(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, ncol, stages, kps, mc, T.ptr(out_s), T.ptr(out_i))
+            tag = ("mma", kind, dim, n, b, k, sm, ncol, stages, kps, mc); tol = 1e-5
         else:
             split = int(rng.integers(2)); k = int(rng.choice([1, 5, 10, 26])) if not split else int(rng.choice([3, 20, 32, 50]))
             b = int(rng.integers(1, 200)); kps = int(rng.choice([d for d in (1, 2, 3, 4) if kb % d == 0])); stages = int(rng.integers(2, 6))
@@ -84,9 +85,9 @@ while time.time() < t_end:
             if stages < 2: continue
             q = T._unit(rng, b, dim)
             out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-            if os.environ.get("FUZZ_VERBOSE"): print("ts", kind, dim, n, b, k, sm, split, stages, kps, flush=True)
-            rc = L.emu_search_ts(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, split, 6, stages, kps, T.ptr(out_s), T.ptr(out_i))
-            tag = ("ts", kind, dim, n, b, k, sm, split, stages, kps); tol = 1e-5 if split else 5e-7
+            if os.environ.get("FUZZ_VERBOSE"): print("ts", kind, dim, n, b, k, sm, split, stages, kps, mc, flush=True)
+            rc = L.emu_search_ts(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, split, 6, stages, kps, mc, T.ptr(out_s), T.ptr(out_i))
+            tag = ("ts", kind, dim, n, b, k, sm, split, stages, kps, mc); tol = 1e-5 if split else 5e-7
         assert rc == 0, (L.emu_last_error(), tag)
         ws, wi = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=7)
         fin = wi >= 0
