@@ -325,6 +325,14 @@ inline unsigned __ballot_sync(unsigned m, int pred) {
     for (int i = 0; i < 32; ++i) r |= (unsigned)all[i] << i;
     return r;
 }
+inline unsigned __match_any_sync(unsigned m, unsigned v) {
+    emu_check_mask(m);
+    unsigned all[32];
+    emu::warp_gather(v, all);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= (unsigned)(all[i] == v) << i;
+    return r;
+}
 inline int __reduce_max_sync(unsigned m, int v) {
     emu_check_mask(m);
     int all[32];

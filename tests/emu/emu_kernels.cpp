@@ -181,6 +181,20 @@ int emu_reduce_rescore(const float *cand_s, const uint32_t *cand_i, int n_lists,
     });
 }
 
+// The cross-CTA candidate reduce alone (u32 row ids, no re-scoring): cand_* [n_lists][n_queries][k_in]; with
+// list_mod > 1 query j only appears in the lists l with l % list_mod == j / queries_per_group (api.cu's
+// side-by-side query chunks).  k_out > 32 takes reduce_topk_kernel or, under VQA_REDUCE_SELECT=1, the radix select.
+int emu_reduce_u32(const float *cand_s, const uint32_t *cand_i, int n_lists, int n_queries, int k_in, int k_out,
+                   long long id_base, int list_mod, int queries_per_group, unsigned long long *tau_g, float *out_s,
+                   long long *out_i) {
+    return guarded([&] {
+        const long long stride = (long long)n_queries * k_in;
+        if (vqa::launch_reduce_u32(cand_s, cand_i, stride, k_in, n_lists, k_in, k_out, id_base, out_s, out_i, n_queries,
+                                   tau_g, list_mod, queries_per_group, nullptr, nullptr) != cudaSuccess)
+            throw std::runtime_error("reduce launch failed");
+    });
+}
+
 // vqa_search in FAST_TENSOR mode (hi/lo column pairs, no clusters): mma_topk_kernel + the candidate reduce, wired
 // as api.cu does it.  rows: 16-bit storage [n_rows][dim]; ncol in {16, 32, 64, 128}; the batch is cut into chunks
 // of ncol / 2 queries handled side by side (n_groups = chunks).

@@ -278,6 +278,58 @@ def test_emulated_reduce_with_exact_rescoring(emu, kind):
         assert np.abs(out_s[j] - exact[want, j]).max() < 5e-7
 
 
+@pytest.mark.parametrize("lists,b,k_in,k_out,lmod", [
+    (148, 3, 100, 100, 1),     # top-100 over the lists of 148 CTAs (BASELINE configs[3]'s k; hybrid search's 10 x limit)
+    (7, 4, 128, 128, 1),       # the largest k
+    (12, 6, 40, 33, 3),        # three query chunks side by side: query j lives in the lists l % 3 == j // 2
+    (3, 2, 64, 64, 1),         # fewer valid candidates than k_out: padded with (-inf, -1)
+])
+def test_emulated_radix_select_reduce_equals_the_list_insertion_reduce(emu, monkeypatch, lists, b, k_in, k_out, lmod):
+    """reduce_select_kernel (k > 32: 64-bit keys in shared memory, MSB radix select, bitonic sort of the survivors)
+    returns exactly what reduce_topk_kernel returns -- ids, score bits, padding -- on unsorted candidate lists with
+    heavy score ties (decided by the lower row), empty slots, +0.0 / -0.0 scores and negative scores; and both
+    equal numpy's lexsort."""
+    emu.emu_reduce_u32.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp]
+    rng = np.random.default_rng(lists * 1000 + k_in)
+    qpg = 2 if lmod > 1 else 1
+    cand_s = np.full((lists, b, k_in), -np.inf, np.float32)
+    cand_i = np.full((lists, b, k_in), 0xFFFFFFFF, np.uint32)
+    for j in range(b):
+        mine = [l for l in range(lists) if lmod == 1 or l % lmod == j // qpg]
+        total = len(mine) * k_in
+        n_valid = total if lists > 3 else k_out - 9                    # (3, 2, 64, 64): too few candidates
+        rows = rng.permutation(1 << 20)[:total].astype(np.uint32)      # distinct rows, unsorted lists
+        rows[:2] = [0, 0x7FFFFFFE]                                     # extreme ids
+        sc = rng.choice(np.array([0.75, 0.5, 0.25, 0.0, -0.0, -0.125, 0.5000001], np.float32), total)
+        sc = np.where(rng.random(total) < 0.5, sc, rng.normal(0.3, 0.2, total).astype(np.float32)).astype(np.float32)
+        keep = rng.permutation(total) < n_valid
+        flat_s = np.where(keep, sc, -np.inf).astype(np.float32)
+        flat_i = np.where(keep, rows, 0xFFFFFFFF).astype(np.uint32)
+        for t, l in enumerate(mine):
+            cand_s[l, j], cand_i[l, j] = flat_s[t * k_in:(t + 1) * k_in], flat_i[t * k_in:(t + 1) * k_in]
+    outs = []
+    for select in ("0", "1"):
+        monkeypatch.setenv("VQA_REDUCE_SELECT", select)
+        out_s, out_i = np.empty((b, k_out), np.float32), np.empty((b, k_out), np.int64)
+        tau_g = np.full(b, 77, np.uint64)
+        ok(emu, emu.emu_reduce_u32(ptr(cand_s), ptr(cand_i), lists, b, k_in, k_out, 1000, lmod, qpg, ptr(tau_g),
+                                   ptr(out_s), ptr(out_i)))
+        assert not tau_g.any()                                          # shared-threshold slots cleared for the next search
+        outs.append((out_s.copy(), out_i.copy()))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))   # score BITS, incl. the sign of zero
+    for j in range(b):
+        mine = [l for l in range(lists) if lmod == 1 or l % lmod == j // qpg]
+        s = np.concatenate([cand_s[l, j] for l in mine])
+        i = np.concatenate([cand_i[l, j] for l in mine]).astype(np.int64)
+        s, i = s[i != 0xFFFFFFFF], i[i != 0xFFFFFFFF]
+        order = np.lexsort((i, -s.astype(np.float64)))[:k_out]
+        n = len(order)
+        assert outs[1][1][j, :n].tolist() == (i[order] + 1000).tolist()
+        assert np.array_equal(outs[1][0][j, :n], s[order])             # (-0.0 == 0.0 here; the bit check is above)
+        assert np.all(outs[1][1][j, n:] == -1) and np.all(np.isneginf(outs[1][0][j, n:]))
+
+
 def test_emulated_peer_memory_exchange_and_flag_waiting_merge(emu):
     """ShardedFlat(exchange="p2p") on one host: every 'rank' pushes its packed [scores | ids] block into its slot
     of every peer's gather buffer and publishes the epoch; each rank's merge kernel acquires the flags and merges

@@ -5,7 +5,11 @@
 #include "pool.cuh"
 #include "scan.cuh"
 
+#include <cstdlib>
+
 namespace vqa {
+
+constexpr size_t kSelectSmemLimit = 227 * 1024;  // dynamic shared memory one CTA may opt in to on sm_100
 
 cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st) {
     switch (a.dtype) {
@@ -62,6 +66,21 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
         cfg.blockDim = dim3(kReduceWarpsPerCta * 32);
         cfg.dynamicSmemBytes = 0;
         return cudaLaunchKernelEx(&cfg, reduce_topk_warp_kernel<IdT>, p);
+    }
+    if constexpr (sizeof(IdT) == 4) {
+        // radix-select reduce (scan.cuh): opt-in until it has been timed on a B200 (VQA_REDUCE_SELECT=1);
+        // needs every candidate of a query in shared memory at once and no peer flags to wait for
+        const long long n_cand = (long long)(n_lists / (list_mod > 1 ? list_mod : 1)) * k_in;
+        const size_t smem = select_smem_bytes(n_cand);
+        const char *env = std::getenv("VQA_REDUCE_SELECT");
+        if (env != nullptr && std::atoi(env) != 0 && wf == nullptr && smem <= kSelectSmemLimit) {
+            cudaError_t e = cudaFuncSetAttribute(reduce_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            cfg.gridDim = dim3(n_queries);
+            cfg.blockDim = dim3(kSelThreads);
+            cfg.dynamicSmemBytes = smem;
+            return cudaLaunchKernelEx(&cfg, reduce_select_kernel, p);
+        }
     }
     cfg.gridDim = dim3(n_queries);
     cfg.blockDim = dim3(kReduceBigWarps * 32);

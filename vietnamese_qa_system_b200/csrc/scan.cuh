@@ -521,4 +521,203 @@ __global__ void __launch_bounds__(kReduceBigWarps * 32) reduce_topk_kernel(const
     }
 }
 
+// k_out in (32, 128], u32 row ids: RADIX SELECT, one CTA of 256 threads per query (opt-in: VQA_REDUCE_SELECT=1).
+// reduce_topk_kernel above inserts the ~n_lists * k_in candidates of a query one by one into lock-guarded
+// sorted lists (0.5 ms at top-100 over 148 lists).  Here every candidate becomes one 64-bit key
+//     ordered(score) << 32 | (0x7fffffff - row) << 1 | (score was -0.0)
+// whose unsigned order IS the ranking (score descending, ties -> lower row; rows are < 2^31, distinct across
+// lists, so the last bit never decides).  The keys are staged in shared memory, an MSB-first 8-bit radix
+// select finds the k-th largest (warp-aggregated histogram updates; stops as soon as the chosen bin holds
+// exactly the keys still wanted), the survivors are compacted, optionally re-scored exactly (screen mode),
+// bitonic-sorted and written.  Same total order as ranks_before, so the result is identical to the other
+// reduce kernels' -- including the sign of a zero score.
+constexpr int kSelThreads = 256;
+constexpr int kSelWarps = kSelThreads / 32;
+
+__device__ __forceinline__ uint32_t ord_f32(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(uint32_t o) {
+    return __uint_as_float((o >> 31) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ unsigned long long select_key(float s, uint32_t row) {
+    const bool negzero = __float_as_uint(s) == 0x80000000u;
+    return ((unsigned long long)ord_f32(negzero ? 0.f : s) << 32) | ((unsigned long long)(0x7fffffffu - row) << 1) |
+           (negzero ? 1ull : 0ull);
+}
+
+// [keys: n_cand x 8 B][selected: kMaxK x 8 B][histogram: 256 x 4 B][control words: 16 x 4 B]
+inline size_t select_smem_bytes(long long n_cand) { return (size_t)n_cand * 8 + (size_t)kMaxK * 8 + 256 * 4 + 64; }
+
+static __global__ void __launch_bounds__(kSelThreads) reduce_select_kernel(const ReduceParams<uint32_t> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x;
+    const int lmod = p.list_mod > 1 ? p.list_mod : 1;
+    const int lgrp = p.list_mod > 1 ? q / p.queries_per_group : 0;
+    const int n_eff = p.n_lists / lmod;
+    const int n_cand = n_eff * p.k_in;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
+    unsigned long long *sel = keys + n_cand;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(sel + kMaxK);
+    uint32_t *ctl = hist + 256;  // 0: valid candidates, 1: digit, 2: still wanted, 3: done, 4: selected
+    if (tid < 16) ctl[tid] = 0;
+    __syncthreads();
+    grid_dependency_wait();
+
+    // 1. candidates -> keys (0 = empty slot)
+    int nv = 0;
+    for (int i = tid; i < n_cand; i += kSelThreads) {
+        const int j = i / p.k_in, e = i - j * p.k_in;
+        const int l = lgrp + j * lmod;
+        const float s = p.cand_s[(long long)l * p.list_stride + (long long)q * p.query_stride + e];
+        const uint32_t id = p.cand_i[(long long)l * p.list_stride_i + (long long)q * p.query_stride + e];
+        unsigned long long key = 0;
+        if (id != invalid_id<uint32_t>()) {
+            key = select_key(s, id);
+            ++nv;
+        }
+        keys[i] = key;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nv += __shfl_xor_sync(kFullMask, nv, m);
+    if (lane == 0 && nv > 0) atomicAdd(&ctl[0], (uint32_t)nv);
+    __syncthreads();
+    const int n_valid = (int)ctl[0];
+    const int k_eff = n_valid < p.k_out ? n_valid : p.k_out;
+    const int kf = p.k_final > 0 ? p.k_final : p.k_out;
+
+    // 2. radix select of the k_eff-th largest key, most significant byte first
+    unsigned long long prefix = 0, mask = 0;
+    uint32_t wanted = (uint32_t)k_eff;
+    bool done = k_eff == 0;
+    for (int shift = 56; shift >= 0 && !done; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < n_cand; i0 += kSelThreads) {  // uniform trip count: the warp votes below
+            const int i = i0 + tid;
+            uint32_t d = 256;  // not a member
+            if (i < n_cand) {
+                const unsigned long long key = keys[i];
+                if (key != 0 && (key & mask) == prefix) d = (uint32_t)(key >> shift) & 255u;
+            }
+            const unsigned peers = __match_any_sync(kFullMask, d);
+            if (d < 256 && lane == __ffs((int)peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane L owns bins 255-8L ... 248-8L (descending); `above` = members in higher bins than its own
+            uint32_t c[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = hist[255 - (lane * 8 + j)];
+                tot += c[j];
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFullMask, incl, off);
+                if (lane >= off) incl += t;
+            }
+            uint32_t above = incl - tot;
+            if (above < wanted && wanted <= above + tot) {  // exactly one lane
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (wanted > above && wanted <= above + c[j]) {
+                        ctl[1] = (uint32_t)(255 - (lane * 8 + j));
+                        ctl[2] = wanted - above;
+                        ctl[3] = c[j] == wanted - above ? 1u : 0u;  // the whole bin is wanted: stop here
+                    }
+                    above += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)ctl[1] << shift;
+        mask |= 255ull << shift;
+        wanted = ctl[2];
+        done = ctl[3] != 0;
+    }
+
+    // 3. survivors: every key whose selected leading bytes are >= the prefix (exactly k_eff of them)
+    for (int i0 = 0; i0 < n_cand; i0 += kSelThreads) {
+        const int i = i0 + tid;
+        unsigned long long key = 0;
+        if (i < n_cand && k_eff > 0) key = keys[i];
+        const bool in = key != 0 && (key & mask) >= prefix;
+        const unsigned m = __ballot_sync(kFullMask, in);
+        uint32_t base = 0;
+        if (lane == 0 && m != 0) base = atomicAdd(&ctl[4], (uint32_t)__popc(m));
+        base = __shfl_sync(kFullMask, base, 0);
+        const uint32_t pos = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (in && pos < (uint32_t)kMaxK) sel[pos] = key;
+    }
+    __syncthreads();
+    const int n_sel = ctl[4] < (uint32_t)kMaxK ? (int)ctl[4] : kMaxK;
+    if (tid < kMaxK && tid >= n_sel) sel[tid] = 0;
+    __syncthreads();
+
+    // 4. screen mode: the survivors' exact fp32 scores (fp32 query x stored row), one warp per candidate
+    if (p.rs_rows != nullptr) {
+        const float *qv = p.rs_q + (long long)q * p.rs_q_stride;
+        const int nch = p.rs_dim / 8;
+        for (int e = warp; e < n_sel; e += kSelWarps) {
+            const unsigned long long key = sel[e];
+            const uint32_t row = 0x7fffffffu - (uint32_t)((key >> 1) & 0x7fffffffull);
+            const unsigned char *rp = p.rs_rows + (long long)row * p.rs_stride;
+            float a0 = 0.f, a1 = 0.f;
+            for (int c = lane; c < nch; c += 32) {
+                const uint4 w = ldg_stream(rp + c * 16);
+                const float4 q0 = *reinterpret_cast<const float4 *>(qv + c * 8);
+                const float4 q1 = *reinterpret_cast<const float4 *>(qv + c * 8 + 4);
+                float x[8];
+                if (p.rs_bf16) Elem<__nv_bfloat16>::unpack(w, x);
+                else Elem<__half>::unpack(w, x);
+                a0 = fmaf(q0.x, x[0], a0);
+                a1 = fmaf(q0.y, x[1], a1);
+                a0 = fmaf(q0.z, x[2], a0);
+                a1 = fmaf(q0.w, x[3], a1);
+                a0 = fmaf(q1.x, x[4], a0);
+                a1 = fmaf(q1.y, x[5], a1);
+                a0 = fmaf(q1.z, x[6], a0);
+                a1 = fmaf(q1.w, x[7], a1);
+            }
+            float exact = a0 + a1;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) exact += __shfl_xor_sync(kFullMask, exact, m);
+            if (lane == 0) sel[e] = select_key(exact, row);
+        }
+        __syncthreads();
+    }
+
+    // 5. bitonic sort of the kMaxK slots, best first (empty slots = 0 sink to the end)
+    for (int size = 2; size <= kMaxK; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (tid < kMaxK) {
+                const int partner = tid ^ stride;
+                if (partner > tid) {
+                    const unsigned long long a = sel[tid], b = sel[partner];
+                    const bool desc = (tid & size) == 0;
+                    if ((a < b) == desc) {
+                        sel[tid] = b;
+                        sel[partner] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < kf) {
+        const unsigned long long key = sel[tid];
+        const bool ok = key != 0;
+        const float s = (key & 1ull) ? __uint_as_float(0x80000000u) : unord_f32((uint32_t)(key >> 32));
+        const uint32_t row = 0x7fffffffu - (uint32_t)((key >> 1) & 0x7fffffffull);
+        p.out_s[(long long)q * kf + tid] = ok ? s : neg_inf();
+        p.out_i[(long long)q * kf + tid] = ok ? (long long)row + p.id_base : -1LL;
+    }
+    if (p.tau_g_reset != nullptr && tid == 0) p.tau_g_reset[q] = 0ull;
+}
+
+
 }  // namespace vqa
