@@ -262,9 +262,11 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
 // vqa_search in FAST_TS mode (queries resident in tensor memory, no clusters): ts_topk_kernel + the reduce, wired
 // as api.cu does it.  split = 0: storage-precision screen with k + spare candidates per query, the 32 best
 // re-scored exactly by the reduce; split = 1: hi + lo query rows (64 queries per CTA), no re-scoring.
+// qs = 1: the QS kernel variant with the last ks 64-column blocks of the query block in shared memory; with
+// k + spare > 32 and split = 0 the radix-select reduce (VQA_REDUCE_SELECT=1) re-scores the 128 best.
 int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const float *q, int n_queries, int k,
                   long long first_id, int sm_count, int split, int spare, int stages, int kps, int multicast,
-                  float *out_s, long long *out_i) {
+                  int qs, int ks, float *out_s, long long *out_i) {
     return guarded([&] {
         const int pass_nq = split ? 64 : 128;
         const int kscan = split ? k : k + spare;
@@ -317,6 +319,10 @@ int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const f
         a.cand_stride = cstride;
         a.tau_g = tau_g.data();
         a.epoch = 1;
+        a.qs = qs;
+        a.ks = ks;
+        if (vqa::ts_smem_bytes(kscan, stages * kps, split, qs ? ks : 0, n_queries, qs) > 227 * 1024)
+            throw std::runtime_error("TS plan does not fit shared memory");
         if (vqa::launch_ts(a, nullptr) != cudaSuccess) throw std::runtime_error("TS scan launch failed");
         vqa::Rescore rs;
         rs.rows = rows;
@@ -326,7 +332,8 @@ int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const f
         rs.q = q;
         rs.q_stride = dim;
         rs.k_final = k;
-        if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, kscan, grid, kscan, split ? kscan : 32, first_id,
+        if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, kscan, grid, kscan,
+                                   split ? kscan : (kscan > 32 ? vqa::kMaxK : 32), first_id,
                                    out_s, out_i, n_queries, tau_g.data(), g, pass_nq, nullptr,
                                    split ? nullptr : &rs) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");

@@ -365,6 +365,9 @@ def test_emulated_peer_memory_exchange_and_flag_waiting_merge(emu):
 
 
 # ---- the tcgen05 / TMA kernels on host models of the PTX wrappers (tests/emu/ptx_emu.cuh) --------------------
+_TS_ARGS = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
+
+
 def _recall(got, want):
     k = want.shape[1]
     return float(np.mean([len(set(got[r]) & set(want[r])) / k for r in range(want.shape[0])]))
@@ -414,8 +417,7 @@ def test_emulated_tmem_resident_query_search_matches_the_oracle(emu, kind, dim, 
     """ts_topk_kernel (query block written to tensor memory with tcgen05.st and used as the MMA's A operand,
     thread-per-query-row epilogue with register lists / append buffers / heaps) + the reduce with the exact
     re-scoring stage, on the host models.  Screen mode returns the exact fp32 scores (abs err ~1e-7)."""
-    emu.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
-                                  _vp]
+    emu.emu_search_ts.argtypes = _TS_ARGS
     rng = np.random.default_rng(dim + n + b + k)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
     docs[n // 2] = docs[3]
@@ -423,10 +425,48 @@ def test_emulated_tmem_resident_query_search_matches_the_oracle(emu, kind, dim, 
     raw, vals = _to_storage(docs, kind)
     out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
     ok(emu, emu.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps, mc,
-                              ptr(out_s), ptr(out_i)))
+                              0, 0, ptr(out_s), ptr(out_i)))
     want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
     assert _recall(out_i, want_i) >= 0.999
     assert np.abs(out_s - want_s).max() <= (5e-7 if not split else 1e-5)
     assert out_i[0, :2].tolist() == [103, 100 + n // 2] and np.all(np.diff(out_s, axis=1) <= 0)
     if not split:
         assert np.array_equal(out_i, want_i)
+
+
+@pytest.mark.parametrize("kind,dim,n,b,k,sm,split,stages,kps,mc,ks", [
+    ("f16", 1024, 400, 64, 100, 3, 0, 5, 2, 0, 4),   # BASELINE configs[3] in miniature: dim 1024 fp16, B = 64, top-100:
+                                                     # 12 query blocks in TMEM + 4 in shared memory, heaps for 64 rows,
+                                                     # big-k screen -> radix-select reduce re-scores the 128 best
+    ("bf16", 1024, 300, 40, 10, 2, 0, 4, 4, 0, 4),   # dim 1024 bf16 top-10: register lists, warp reduce re-scores 32
+    ("bf16", 1024, 300, 30, 40, 2, 1, 3, 2, 0, 4),   # dim 1024 hi/lo rows, k = 40 heaps (bf16 keeps hi/lo for big k)
+    ("bf16", 768, 500, 130, 10, 4, 0, 4, 4, 0, 4),   # dim 768 with ks = 4: 8 blocks in TMEM -> 4 accumulator stages; 2 chunks
+    ("f16", 768, 400, 200, 10, 6, 0, 4, 2, 1, 6),    # cluster of 2 with TMA multicast, ks = 6 (5 accumulator stages)
+    ("bf16", 128, 200, 20, 10, 2, 0, 4, 2, 0, 2),    # every query block in shared memory (ks = dim / 64): nothing in TMEM
+    ("f16", 832, 200, 10, 5, 2, 0, 4, 1, 0, 1),      # dim 832 = 13 blocks: ks = 1
+])
+def test_emulated_query_block_split_between_tmem_and_smem(emu, monkeypatch, kind, dim, n, b, k, sm, split, stages, kps,
+                                                         mc, ks):
+    """ts_topk_kernel<.., QS = true> (opt-in, VQA_TS_QS=1): the last ks 64-column blocks of the query block are staged
+    in shared memory (128-byte swizzle) and multiplied with the smem-A form of tcgen05.mma into the same accumulator
+    as the TMEM-A blocks -- what makes dim 1024 fit.  Same bars as the all-TMEM kernel."""
+    emu.emu_search_ts.argtypes = _TS_ARGS
+    monkeypatch.setenv("VQA_REDUCE_SELECT", "1")
+    rng = np.random.default_rng(dim + n + b + k)
+    docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    raw, vals = _to_storage(docs, kind)
+    out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+    ok(emu, emu.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps, mc,
+                              1, ks, ptr(out_s), ptr(out_i)))
+    want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
+    assert _recall(out_i, want_i) >= 0.999
+    assert np.abs(out_s - want_s).max() <= (5e-7 if not split else 1e-5)
+    assert out_i[0, :2].tolist() == [103, 100 + n // 2] and np.all(np.diff(out_s, axis=1) <= 0)
+    if not split:   # exact re-scoring: the oracle's ids, up to swaps of neighbours whose fp64 scores agree to 2e-7
+        assert _recall(out_i, want_i) == 1.0
+        swapped = out_i != want_i
+        assert swapped.mean() < 0.01
+        pos = {(r, int(i)): s_ for r in range(b) for i, s_ in zip(want_i[r], want_s[r])}
+        assert all(abs(pos[(r, int(out_i[r, c]))] - want_s[r, c]) < 2e-7 for r, c in zip(*np.nonzero(swapped)))

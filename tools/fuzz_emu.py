@@ -21,7 +21,7 @@ L.emu_bm25_weights.argtypes = [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _dbl, _dbl, 
 L.emu_pool_normalize.argtypes = [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
 T._bind_search(L)
 L.emu_search_tensor.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
-L.emu_search_ts.argtypes = [_vp, _i32, _i64, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]
+L.emu_search_ts.argtypes = T._TS_ARGS
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 t_end = time.time() + float(sys.argv[2]) if len(sys.argv) > 2 else time.time() + 120
 n_ok = 0
@@ -53,7 +53,9 @@ while time.time() < t_end:
             assert g == ref.search(qq, limit), ("sparse", n_docs, vocab, normalize, sm, limit, qq)
     elif which in (3, 4):  # tcgen05 kernels on the host models of ptx.cuh
         kind = ["bf16", "f16"][rng.integers(2)]
-        dim = int(rng.choice([64, 128, 192, 256, 384, 512, 768]))
+        qs = int(which == 4 and rng.integers(2))     # opt-in QS variant of the TMEM-resident-query kernel (dims up to 1024)
+        dim = int(rng.choice([64, 128, 192, 256, 384, 512, 768] + ([832, 1024] if qs else [])))
+        os.environ["VQA_REDUCE_SELECT"] = str(int(qs or rng.integers(2)))   # k > 32: either reduce kernel
         n = int(rng.integers(1, 900)); sm = int(rng.choice([1, 2, 3, 7, 148]))
         kb = dim // 64
         docs = T._unit(rng, n, dim)
@@ -75,19 +77,20 @@ while time.time() < t_end:
             rc = L.emu_search_tensor(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, ncol, stages, kps, mc, T.ptr(out_s), T.ptr(out_i))
             tag = ("mma", kind, dim, n, b, k, sm, ncol, stages, kps, mc); tol = 1e-5
         else:
-            split = int(rng.integers(2)); k = int(rng.choice([1, 5, 10, 26])) if not split else int(rng.choice([3, 20, 32, 50]))
+            split = int(rng.integers(2)); k = int(rng.choice([1, 5, 10, 26] + ([40, 100] if qs else []))) if not split else int(rng.choice([3, 20, 32, 50]))
             b = int(rng.integers(1, 200)); kps = int(rng.choice([d for d in (1, 2, 3, 4) if kb % d == 0])); stages = int(rng.integers(2, 6))
+            ks = int(rng.integers(max(0, kb - 12), kb + 1)) if qs else 0
             kscan = k if split else k + 6
             depth = 32 if kscan <= 32 else kscan + 32
-            lrows = 64 if (kscan > 32 and split) else 128
-            fixed = 1024 + 1024 + (2 * 64 * 64 * 4 if split else 0) + lrows * depth * 8    # ts_smem_bytes_rt without the ring
+            lrows = 64 if (kscan > 32 and (split or (qs and b <= 64))) else 128
+            fixed = 1024 + ks * 16384 + 1024 + (2 * 64 * 64 * 4 if split else 0) + lrows * depth * 8    # ts_smem_bytes_rt without the ring
             stages = min(stages, ((227 * 1024 - fixed) // 8192) // kps)                    # as plan_ts sizes the ring
             if stages < 2: continue
             q = T._unit(rng, b, dim)
             out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-            if os.environ.get("FUZZ_VERBOSE"): print("ts", kind, dim, n, b, k, sm, split, stages, kps, mc, flush=True)
-            rc = L.emu_search_ts(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, split, 6, stages, kps, mc, T.ptr(out_s), T.ptr(out_i))
-            tag = ("ts", kind, dim, n, b, k, sm, split, stages, kps, mc); tol = 1e-5 if split else 5e-7
+            if os.environ.get("FUZZ_VERBOSE"): print("ts", kind, dim, n, b, k, sm, split, stages, kps, mc, qs, ks, flush=True)
+            rc = L.emu_search_ts(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, split, 6, stages, kps, mc, qs, ks, T.ptr(out_s), T.ptr(out_i))
+            tag = ("ts", kind, dim, n, b, k, sm, split, stages, kps, mc, qs, ks); tol = 1e-5 if split else 5e-7
         assert rc == 0, (L.emu_last_error(), tag)
         ws, wi = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=7)
         fin = wi >= 0

@@ -127,6 +127,8 @@ struct Plan {
     int ss_split; // tensor family: 1 hi/lo column pairs, 0 screen mode (+ exact re-scoring in the reduce)
     int ts_split; // TS family: hi+lo rows (64 queries per CTA) or storage-precision queries (128 per CTA)
     int ts_afp16;
+    int ts_qs;    // TS family: the opt-in QS kernel variant (part of the query block in shared memory)
+    int ts_ks;    // QS: 64-column blocks of the query block kept in shared memory
     int grid;
 };
 
@@ -187,27 +189,55 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
     return false;
 }
 
-bool ts_eligible(const vqa_index *h) { return tensor_eligible(h) && h->dim <= 768; }
+// Opt-in paths that have passed the CPU emulator but have not been timed on a B200 yet (ts.cuh QS variant,
+// scan.cuh radix-select reduce).  Off by default: the default routing is exactly what round 1 measured.
+bool ts_qs_enabled() { return env_int("VQA_TS_QS", 0) != 0; }
+bool reduce_select_enabled() { return env_int("VQA_REDUCE_SELECT", 0) != 0; }
+
+bool ts_eligible(const vqa_index *h) {
+    return tensor_eligible(h) && (h->dim <= 768 || (ts_qs_enabled() && h->dim <= 1024));
+}
 
 // TMEM-resident queries: shared memory holds only the document ring and the per-row lists
 bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     // k <= 16: screen with storage-precision queries (128 per CTA), keep 32 candidates per query and
     // re-score them exactly in the reduce.  Larger k: hi + lo rows (64 queries per CTA).
-    const int split = env_int("VQA_TS_SPLIT", k + spare_ranks() <= 32 ? 0 : 1) != 0;
+    const int kb = h->dim / vqa::kBlockK;
+    // QS variant (opt-in): ks of the kb query blocks in shared memory; at most 12 stay in TMEM (384 columns,
+    // two 64-column accumulator stages next to them), so dim 1024 needs ks >= 4
+    const int qs = ts_qs_enabled() ? 1 : 0;
+    int ks = 0;
+    if (qs) {
+        const int ks_min = kb > 12 ? kb - 12 : 0;
+        ks = env_int("VQA_TS_KS", ks_min);
+        if (ks < ks_min) ks = ks_min;
+        if (ks > kb) ks = kb;
+    } else if (h->dim > 768) {
+        return false;
+    }
+    // Screen mode beyond the register lists (k + spare > 32) re-scores through the radix-select reduce, the only
+    // big-k reduce with a re-scoring stage: fp16 rows only (11-bit queries; bf16 queries would need ~28 spare
+    // ranks at top-100), and only when both opt-ins are set.  Anything else with k + spare > 32: hi/lo rows.
+    const bool big_screen_ok = qs && reduce_select_enabled() && k + spare_ranks() <= vqa::kMaxK;
+    int split = env_int("VQA_TS_SPLIT", (k + spare_ranks() <= 32 || (big_screen_ok && h->dtype == VQA_F16)) ? 0 : 1) != 0;
+    if (!split && k + spare_ranks() > 32 && !big_screen_ok) split = 1;
     const int kscan = split ? k : k + spare_ranks();
-    const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split);
+    const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split, ks, nq, qs);
     if (fixed >= (size_t)h->max_smem) return false;
     int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
-    const int kb = h->dim / vqa::kBlockK;
     // 8 KB boxes: four column blocks per ring stage halve the per-byte handshakes (measured 2.74 -> 2.57 ms
     // at B = 128, 5.17 -> 4.38 ms at B = 256 on 10M x 768)
     int kps = env_int("VQA_MMA_KPS", kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
     if (kps < 1 || kb % kps != 0) kps = 1;
+    // QS: the query blocks shrink the ring; keep at least three stages in flight before widening them
+    while (qs && kps > 1 && boxes / kps < 3) kps = (kps % 2 == 0) ? kps / 2 : 1;
     int stages = boxes / kps;
     if (stages > vqa::kMaxStages) stages = vqa::kMaxStages;
     if (stages < 2) return false;
     pl->family = VQA_MODE_FAST_TS;
     pl->ts_split = split;
+    pl->ts_qs = qs;
+    pl->ts_ks = ks;
     pl->ts_afp16 = 0;  // (fp16 queries against bf16 rows would halve the rounding, but the MMA rejects mixed operands)
     pl->pass_nq = split ? 64 : 128;
     pl->ncol = 0;
@@ -231,6 +261,8 @@ void plan_stream(const vqa_index *h, int nq, Plan *pl) {
     pl->groups = 1;
     pl->ss_split = 1;
     pl->ts_split = 1;
+    pl->ts_qs = 0;
+    pl->ts_ks = 0;
     pl->grid = h->sm_count;
 }
 
@@ -248,7 +280,8 @@ int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
     }
     if (mode == VQA_MODE_FAST_TS) {
         if (!ts_eligible(h) || !plan_ts(h, nq, k, pl))
-            return fail(VQA_E_UNSUPPORTED, "TMEM-resident-query path needs bf16/fp16 rows and dim %% 64 == 0, dim <= 768");
+            return fail(VQA_E_UNSUPPORTED, "TMEM-resident-query path needs bf16/fp16 rows and dim %% 64 == 0, dim <= 768 "
+                                           "(dim <= 1024 with the opt-in VQA_TS_QS=1)");
         return VQA_OK;
     }
     if (mode == VQA_MODE_FAST) {
@@ -275,8 +308,13 @@ int check_search_args(const vqa_index *h, int nq, int k) {
     return VQA_OK;
 }
 
-// candidate lists are kept at least 32 wide so that the screen-then-rescore path can over-fetch
-size_t cand_elems(const vqa_index *h, int nq, int k) { return (size_t)h->sm_count * nq * (k < 32 ? 32 : k); }
+// candidate lists are kept at least 32 wide so that the screen-then-rescore path can over-fetch; beyond the
+// register lists the (opt-in) big-k screen mode keeps k + spare candidates per list
+size_t cand_elems(const vqa_index *h, int nq, int k) {
+    int w = k + spare_ranks() <= 32 ? 32 : k + spare_ranks();
+    if (w > vqa::kMaxK) w = k < 32 ? 32 : k;
+    return (size_t)h->sm_count * nq * w;
+}
 
 }  // namespace
 
@@ -457,6 +495,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.bf16 = h->dtype == VQA_BF16;
             a.split = pl.ts_split;
             a.a_fp16 = pl.ts_afp16;
+            a.qs = pl.ts_qs;
+            a.ks = pl.ts_ks;
             a.stages = pl.stages;
             a.kps = pl.kps;
             a.grid = (int)streams * g;
@@ -484,7 +524,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             rs.q_stride = q_stride;
             rs.k_final = k;
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
-                                       kscan, pl.ts_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
+                                       kscan, pl.ts_split ? kscan : (kscan > 32 ? vqa::kMaxK : 32), h->first_id,
+                                       out_scores_dev + (long long)l0 * k,
                                        (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
                                        pl.ts_split ? nullptr : &rs);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));

@@ -70,10 +70,12 @@ struct TsLaunch {
     long long cand_stride;
     unsigned long long *tau_g;
     uint32_t epoch;
+    int qs = 0;   // 1: the QS kernel variant (part of the query block in shared memory); opt-in, see ts.cuh
+    int ks = 0;   // QS: 64-column blocks of the query block kept in shared memory
 };
 
 cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st);
-size_t ts_smem_bytes(int k, int boxes, int split);
+size_t ts_smem_bytes(int k, int boxes, int split, int ks = 0, int nq = 1 << 30, int qs = 0);
 cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_f32(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_bf16(const ScanLaunch &a, cudaStream_t st);

@@ -82,6 +82,7 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
             return cudaLaunchKernelEx(&cfg, reduce_select_kernel, p);
         }
     }
+    if (rs != nullptr) return cudaErrorInvalidValue;  // only the radix-select reduce re-scores beyond 32 candidates
     cfg.gridDim = dim3(n_queries);
     cfg.blockDim = dim3(kReduceBigWarps * 32);
     cfg.dynamicSmemBytes = list_smem_bytes<IdT>(kReduceBigWarps, k_out);

@@ -55,19 +55,29 @@ struct TsParams {
     uint32_t epoch;
     int n_groups;
     int multicast;
+    int ks;        // QS variants: the LAST ks 64-column blocks of the query block live in shared memory, not TMEM
 };
+
+constexpr int kTsQBlockBytes = kTsRows * kBlockK * 2;  // 16 KB: 128 query rows x one 64-column block, 128B-swizzled
 
 // register-list variants: 16 (k <= 16) or 32 (k <= 32) entries per query row; 0 = list in shared memory
 inline int ts_reg_list_len(int k) { return k <= 16 ? 16 : (k <= 32 ? 32 : 0); }
 
-// [align slack][ring: boxes x 8 KB][barriers 1 KB][exchange 2 x 16 KB if split]
+// rows that own a shared-memory list / candidate buffer: 64 when at most 64 rows of the CTA are queries (hi/lo
+// rows, or -- QS variants only -- a launch of at most 64 queries) and the lists are in shared memory (k > 32)
+inline int ts_list_rows(int k, int split, int nq, int qs) {
+    return (ts_reg_list_len(k) == 0 && (split || (qs && nq <= 64))) ? 64 : kTsRows;
+}
+
+// [align slack][QS: ks query blocks x 16 KB][ring: boxes x 8 KB][barriers 1 KB][exchange 2 x 16 KB if split]
 // [lists: rows x k x 8 B, or the 32-deep candidate buffers (rows x 32 x 8 B) of the register-list variants]
 // shared-memory lists (k > 32) are kept for the live rows only: 64 with hi/lo rows, else 128; every
 // variant also has 32-deep candidate buffers for those rows
-inline size_t ts_smem_bytes_rt(int k, int boxes, int split) {
+inline size_t ts_smem_bytes_rt(int k, int boxes, int split, int ks = 0, int nq = 1 << 30, int qs = 0) {
     const int depth = ts_reg_list_len(k) > 0 ? 32 : k + 32;
-    const int rows = (ts_reg_list_len(k) == 0 && split) ? 64 : kTsRows;
-    return 1024 + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) + (size_t)rows * depth * 8;
+    const int rows = ts_list_rows(k, split, nq, qs);
+    return 1024 + (size_t)ks * kTsQBlockBytes + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) +
+           (size_t)rows * depth * 8;
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -93,7 +103,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 
-template <bool DOC_BF16, int KL>
+// QS ("query block partly in Shared memory", opt-in until timed on a B200): the last p.ks 64-column blocks of
+// the query block are staged in shared memory (K-major, 128B-swizzled, 16 KB each) and multiplied with the
+// shared-memory-A form of the MMA into the same accumulator; only the first dim/64 - ks blocks occupy TMEM.
+// That (a) fits dim 1024 (BASELINE configs[3]: 12 blocks = 384 columns in TMEM + 4 blocks = 64 KB in shared
+// memory, 2 accumulator stages) and (b) is a knob at dim 768: ks = 4 leaves 256 TMEM columns = 4 accumulator
+// stages instead of 2.  QS = false compiles exactly the kernel measured in round 1.
+template <bool DOC_BF16, int KL, bool QS = false>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -104,9 +120,12 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     const int KPS = p.kps;
     const int KG = KB / KPS;
     const uint32_t stage_bytes = (uint32_t)KPS * kTsBoxBytes;
-    const int ACOLS = p.dim / 2;                    // TMEM columns of the query block
-    const int AS = (512 - ACOLS) / kTsDocs;         // accumulator stages
-    unsigned char *a_smem = smem;                   // document ring
+    const int KSB = QS ? p.ks : 0;                  // query blocks in shared memory
+    const int KT = KB - KSB;                        // query blocks in tensor memory
+    const int ACOLS = QS ? KT * (kBlockK / 2) : p.dim / 2;  // TMEM columns of the query block
+    const int AS = (QS && (512 - ACOLS) / kTsDocs > kMaxAccStages) ? kMaxAccStages : (512 - ACOLS) / kTsDocs;  // accumulator stages
+    unsigned char *q_smem = smem;                   // QS: KSB blocks of 128 query rows x 128 bytes
+    unsigned char *a_smem = smem + (size_t)KSB * kTsQBlockBytes;  // document ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(a_smem + (size_t)S * stage_bytes);
     uint64_t *full = bars;
     uint64_t *empty = bars + kMaxStages;
@@ -117,7 +136,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     unsigned char *lists = reinterpret_cast<unsigned char *>(xchg) + (p.split ? 2 * 64 * kTsDocs * 4 : 0);
     // per-thread sorted lists (KL == 0) and candidate buffers, entry-major so that a warp's accesses are
     // conflict free; LR = rows that own a list (64 when the upper 64 rows are the queries' lo parts)
-    const int LR = (KL == 0 && p.split) ? 64 : kTsRows;
+    const int LR = (KL == 0 && (p.split || (QS && p.nq <= 64))) ? 64 : kTsRows;
     float *lst_s = reinterpret_cast<float *>(lists);                       // [k][LR]        (KL == 0)
     uint32_t *lst_i = reinterpret_cast<uint32_t *>(lst_s + (size_t)p.k * LR);
 
@@ -190,6 +209,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         ptx::tc_fence_after_sync();
         uint32_t it = 0, lt = 0;
         const uint32_t ring = ptx::smem_u32(a_smem);
+        const uint32_t qs_base = ptx::smem_u32(q_smem);
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
@@ -205,6 +225,14 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                     for (int j = 0; j < KPS; ++j) {
                         const int kb = kg * KPS + j;
                         const uint64_t db0 = ptx::umma_desc_k_sw128(ring + (uint32_t)s * stage_bytes + (uint32_t)j * kTsBoxBytes);
+                        if (QS && kb >= KT) {  // this block of the queries is in shared memory
+                            const uint64_t da0 = ptx::umma_desc_k_sw128(qs_base + (uint32_t)(kb - KT) * kTsQBlockBytes);
+#pragma unroll
+                            for (int k4 = 0; k4 < kBlockK / 16; ++k4)  // +32 bytes along K = +2 in the address field
+                                ptx::umma_f16(d_tmem, da0 + (uint64_t)(k4 * 2), db0 + (uint64_t)(k4 * 2), idesc,
+                                              (kb | k4) != 0 ? 1u : 0u);
+                            continue;
+                        }
 #pragma unroll
                         for (int k4 = 0; k4 < kBlockK / 16; ++k4)  // 16 K-elements = 8 TMEM columns of A
                             umma_f16_ts(d_tmem, tmem_base + (uint32_t)(kb * 32 + k4 * 8), db0 + (uint64_t)(k4 * 2), idesc,
@@ -252,6 +280,34 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 tmem_st16(trow + (uint32_t)c0, w);
             }
             tmem_st_wait();
+            if constexpr (QS) {
+                // the remaining blocks of this row -> shared memory, K-major, 128-byte swizzle (16-byte chunk c of
+                // row r at r * 128 + ((c ^ (r & 7)) << 4)), same 16-bit values as the TMEM part
+                for (int kb = KT; kb < KB; ++kb) {
+                    unsigned char *tile = q_smem + (size_t)(kb - KT) * kTsQBlockBytes;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                        if (live) {
+                            v0 = *reinterpret_cast<const float4 *>(src + kb * kBlockK + c * 8);
+                            v1 = *reinterpret_cast<const float4 *>(src + kb * kBlockK + c * 8 + 4);
+                        }
+                        float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float hi;
+                            if (DOC_BF16 && !p.a_fp16) hi = __bfloat162float(__float2bfloat16_rn(x[e]));
+                            else hi = __half2float(__float2half_rn(x[e]));
+                            x[e] = is_lo ? x[e] - hi : hi;
+                        }
+                        uint4 w;
+                        if (DOC_BF16 && !p.a_fp16) w = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                        else w = make_uint4(pack_f16x2(x[0], x[1]), pack_f16x2(x[2], x[3]), pack_f16x2(x[4], x[5]), pack_f16x2(x[6], x[7]));
+                        *reinterpret_cast<uint4 *>(tile + row * 128 + ((c ^ (row & 7)) << 4)) = w;
+                    }
+                }
+                ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            }
             ptx::tc_fence_before_sync();
             __syncwarp();
             named_bar_sync(1, kMmaThreads);  // with the MMA warp

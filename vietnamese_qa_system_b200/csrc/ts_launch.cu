@@ -4,7 +4,7 @@
 
 namespace vqa {
 
-template <bool BF16, int KL>
+template <bool BF16, int KL, bool QS>
 static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     TsParams p;
     p.q = a.q;
@@ -27,8 +27,9 @@ static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     p.epoch = a.epoch;
     p.n_groups = a.n_groups;
     p.multicast = a.multicast;
-    const size_t smem = ts_smem_bytes_rt(a.k, a.stages * a.kps, a.split);
-    auto kern = ts_topk_kernel<BF16, KL>;
+    p.ks = QS ? a.ks : 0;
+    const size_t smem = ts_smem_bytes_rt(a.k, a.stages * a.kps, a.split, p.ks, a.nq, QS ? 1 : 0);
+    auto kern = ts_topk_kernel<BF16, KL, QS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (!a.multicast) {
@@ -50,19 +51,28 @@ static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     return cudaLaunchKernelEx(&cfg, kern, *a.tmap, p);
 }
 
-template <bool BF16>
+template <bool BF16, bool QS>
 static cudaError_t launch_ts_t(const TsLaunch &a, cudaStream_t st) {
     switch (ts_reg_list_len(a.k)) {
-        case 16: return launch_ts_tk<BF16, 16>(a, st);
-        case 32: return launch_ts_tk<BF16, 32>(a, st);
-        default: return launch_ts_tk<BF16, 0>(a, st);
+        case 16: return launch_ts_tk<BF16, 16, QS>(a, st);
+        case 32: return launch_ts_tk<BF16, 32, QS>(a, st);
+        default: return launch_ts_tk<BF16, 0, QS>(a, st);
     }
 }
 
 cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st) {
-    return a.bf16 ? launch_ts_t<true>(a, st) : launch_ts_t<false>(a, st);
+    const int kb = a.dim / kBlockK;
+    if (a.qs) {
+        // the TMEM part of the query block must leave at least one accumulator stage
+        if (a.ks < 0 || a.ks > kb || (kb - a.ks) * (kBlockK / 2) + kTsDocs > 512) return cudaErrorInvalidValue;
+        return a.bf16 ? launch_ts_t<true, true>(a, st) : launch_ts_t<false, true>(a, st);
+    }
+    if (a.dim / 2 + kTsDocs > 512) return cudaErrorInvalidValue;
+    return a.bf16 ? launch_ts_t<true, false>(a, st) : launch_ts_t<false, false>(a, st);
 }
 
-size_t ts_smem_bytes(int k, int boxes, int split) { return ts_smem_bytes_rt(k, boxes, split); }
+size_t ts_smem_bytes(int k, int boxes, int split, int ks, int nq, int qs) {
+    return ts_smem_bytes_rt(k, boxes, split, ks, nq, qs);
+}
 
 }  // namespace vqa
