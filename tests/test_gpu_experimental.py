@@ -1,0 +1,106 @@
+"""GPU parity tests of the OPT-IN kernels: paths that pass the CPU emulator (tests/test_emu_kernels.py) but have
+not yet been run or timed on a B200, so the default routing does not use them:
+  * VQA_REDUCE_SELECT=1 -- radix-select candidate reduce for k > 32 (scan.cuh reduce_select_kernel)
+  * VQA_TS_QS=1 [VQA_TS_KS=n] -- TMEM-resident-query kernel with part of the query block in shared memory
+    (ts.cuh, QS variants): dim <= 1024, more accumulator stages at dim 768
+Skipped unless VQA_EXPERIMENTAL=1 (tools/r2_experiments.sh sets it): a kernel that has never met the hardware
+must not be able to take the round-end `pytest -m gpu` run down with it.  Same bars as tests/test_gpu_search.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.conftest import unit_rows
+from tests.test_gpu_search import gpu_search, recall
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("VQA_EXPERIMENTAL") != "1", reason="opt-in kernels: set VQA_EXPERIMENTAL=1")]
+DEV = "cuda:0"
+
+
+def _check(docs, q, k, mode, storage, exact_scores=True):
+    s, i, stored = gpu_search(docs, q, k, mode, storage)
+    os_, oi = oracle.search(stored, q, k, oracle.CANONICAL, storage)
+    assert recall(i, oi) >= 0.999
+    fin = np.isfinite(os_)
+    assert np.all(np.abs(s[fin] - os_[fin]) <= 1e-5 * np.abs(os_[fin]) + 2e-6)
+    assert np.all(np.diff(s[:, :min(k, docs.shape[0])], axis=1) <= 0)
+    return s, i
+
+
+@pytest.mark.parametrize("storage", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("n,d,b,k", [(4000, 768, 32, 100), (130, 768, 5, 128), (50000, 384, 9, 33), (20, 64, 3, 40)])
+def test_radix_select_reduce_is_bit_identical_to_the_list_insertion_reduce(monkeypatch, storage, n, d, b, k):
+    """k > 32 in every kernel family: same ids and score bits with either reduce kernel; verify mode stays
+    bit-identical to the canonical oracle."""
+    rng = np.random.default_rng(n + k)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[1]                                     # a tie, decided by the lower id
+    for mode in ("verify", "fast") if storage != "fp32" else ("verify",):
+        out = []
+        for sel in ("0", "1"):
+            monkeypatch.setenv("VQA_REDUCE_SELECT", sel)
+            s, i, stored = gpu_search(docs, q, k, mode, storage)
+            out.append((s, i))
+        assert np.array_equal(out[0][1], out[1][1])
+        assert np.array_equal(out[0][0].view(np.int32), out[1][0].view(np.int32))
+        if mode == "verify":
+            os_, oi = oracle.search(stored, q, k, oracle.CANONICAL, storage)
+            assert np.array_equal(out[1][1], oi) and np.array_equal(out[1][0].view(np.int32), os_.view(np.int32))
+
+
+@pytest.mark.parametrize("storage,n,d,b,k,ks,select", [
+    ("fp16", 30000, 1024, 64, 100, 4, 1),    # BASELINE configs[3] in miniature: big-k screen + radix-select re-score
+    ("fp16", 30000, 1024, 64, 100, 8, 1),
+    ("bf16", 30000, 1024, 64, 100, 4, 1),    # bf16 keeps hi/lo rows for big k
+    ("bf16", 20000, 1024, 64, 10, 4, 0),     # dim 1024 top-10: register lists, warp reduce re-scores 32
+    ("bf16", 20000, 1024, 300, 10, 4, 0),    # three chunks of 128: cluster of 4 with TMA multicast
+    ("fp16", 5000, 832, 40, 5, 1, 0),        # 13 query blocks
+    ("bf16", 20000, 768, 100, 10, 4, 0),     # dim 768, 4 accumulator stages
+    ("bf16", 20000, 768, 256, 10, 6, 0),     # 5 accumulator stages, cluster of 2
+    ("fp16", 20000, 768, 130, 10, 12, 0),    # nothing in TMEM but accumulators
+    ("bf16", 4000, 768, 32, 100, 2, 1),      # k = 100 at dim 768 with the QS variant (hi/lo heaps)
+])
+def test_query_block_split_between_tmem_and_smem(monkeypatch, storage, n, d, b, k, ks, select):
+    monkeypatch.setenv("VQA_TS_QS", "1")
+    monkeypatch.setenv("VQA_TS_KS", str(ks))
+    monkeypatch.setenv("VQA_REDUCE_SELECT", str(select))
+    rng = np.random.default_rng(n + b + ks)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    s, i = _check(docs, q, k, "ts", storage)
+    assert i[0, :2].tolist() == [3, n // 2]
+    s2, i2 = _check(docs, q, k, "fast", storage)               # FAST routes the same shapes to the same kernel
+    assert np.array_equal(i, i2) and np.array_equal(s, s2)
+
+
+def test_full_size_config_d_shard_properties(monkeypatch):
+    """2 M x 1024 fp16, B = 64, top-100 on the QS path: planted duplicates come back lower id first, results are
+    idempotent and independent of the batch they were asked in, and agree with the default kernel family."""
+    from vietnamese_qa_system_b200 import ops
+
+    n, d, b, k = 2_000_000, 1024, 64, 100
+    g = torch.Generator(device=DEV).manual_seed(3)
+    rows = torch.empty((n, d), dtype=torch.float16, device=DEV)
+    for lo in range(0, n, 500_000):
+        rows[lo:lo + 500_000] = ops.normalize_rows(torch.randn((500_000, d), generator=g, device=DEV)).half()
+    rows[1_500_000] = rows[17]
+    q = ops.normalize_rows(torch.randn((b, d), generator=g, device=DEV))
+    q[0] = rows[17].float()
+    shard = ops.FlatShard(rows)
+    s_ref, i_ref = shard.search(q, k, "fast")                  # default routing (smem-resident kernel)
+    monkeypatch.setenv("VQA_TS_QS", "1")
+    monkeypatch.setenv("VQA_REDUCE_SELECT", "1")
+    s1, i1 = shard.search(q, k, "fast")
+    s2, i2 = shard.search(q, k, "fast")
+    s3, i3 = shard.search(q[:7], k, "fast")
+    torch.cuda.synchronize()
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    assert torch.equal(i1[:7], i3) and torch.equal(s1[:7], s3)
+    assert i1[0, :2].tolist() == [17, 1_500_000]
+    a, r = i1.cpu().tolist(), i_ref.cpu().tolist()
+    assert sum(len(set(x) & set(y)) for x, y in zip(a, r)) / (b * k) >= 0.999
+    assert float(((s1 - s_ref).abs() / s_ref.abs()).max()) < 1e-5

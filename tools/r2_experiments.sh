@@ -1,0 +1,30 @@
+#!/bin/bash
+# Round-2 first GPU call: time the opt-in paths that so far only ran on the CPU emulator, next to the defaults.
+#   gpurun --timeout 1500 -- 'bash tools/r2_experiments.sh > gpurun_out/r2_experiments.log 2>&1'
+# Each line: knobs -> {batch: {ms, GBps, recall, max_rel_err}} (CUDA events around vqa_search, recall vs verify mode).
+cd "$(dirname "$0")/.."
+run() { echo -n "$* -> "; env "$@" CHECK=1 timeout 600 python tools/tune_worker.py 2>&1 | tail -n 1; }
+
+echo "== correctness first: the experimental GPU tests"
+VQA_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -x -q 2>&1 | tail -n 5
+
+echo "== top-100, 4M x 768 bf16: list-insertion reduce vs radix select (default kernel family = TS hi/lo heaps)"
+for SEL in 0 1; do run ROWS=4000000 K=100 MODE=fast BATCHES=8,64 ITERS=10 VQA_REDUCE_SELECT=$SEL; done
+
+echo "== BASELINE configs[3] shard: 12.5M x 1024 fp16, B = 64, top-100 (HBM floor 3.9 ms)"
+run ROWS=12500000 DIM=1024 DTYPE=fp16 K=100 MODE=fast BATCHES=64 ITERS=5
+run ROWS=12500000 DIM=1024 DTYPE=fp16 K=100 MODE=fast BATCHES=64 ITERS=5 VQA_REDUCE_SELECT=1
+for KS in 4 6 8; do
+  run ROWS=12500000 DIM=1024 DTYPE=fp16 K=100 MODE=fast BATCHES=64 ITERS=5 VQA_REDUCE_SELECT=1 VQA_TS_QS=1 VQA_TS_KS=$KS
+done
+run ROWS=12500000 DIM=1024 DTYPE=fp16 K=100 MODE=fast BATCHES=64 ITERS=5 VQA_REDUCE_SELECT=1 VQA_TS_QS=1 VQA_TS_SPLIT=1
+
+echo "== dim 1024 bf16 top-10, B = 32..256 (default: smem-resident kernel with multicast groups)"
+run ROWS=8000000 DIM=1024 K=10 MODE=fast BATCHES=32,64,128,256 ITERS=5
+run ROWS=8000000 DIM=1024 K=10 MODE=fast BATCHES=32,64,128,256 ITERS=5 VQA_TS_QS=1
+
+echo "== 10M x 768 bf16 top-10, B = 64..512: accumulator stages (ks = 0: 2 stages, 2: 3, 4: 4, 6: 5)"
+run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256,512 ITERS=5
+for KS in 0 2 4 6; do
+  run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256,512 ITERS=5 VQA_TS_QS=1 VQA_TS_KS=$KS
+done

@@ -35,4 +35,11 @@ for b in [int(x) for x in os.environ.get("BATCHES", "8,32").split(",")]:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     res[b] = {"ms": round(ms, 4), "GBps": round(n * d * rows.element_size() / ms / 1e6)}
+    if os.environ.get("CHECK"):  # recall@k and score error against the fp32 verify kernel on the same rows
+        s1, i1 = shard.search(q, k, mode)
+        s0, i0 = shard.search(q, k, "verify")
+        torch.cuda.synchronize()
+        a, r = i1.cpu().tolist(), i0.cpu().tolist()
+        res[b]["recall"] = round(sum(len(set(x) & set(y)) for x, y in zip(a, r)) / (len(r) * k), 5)
+        res[b]["max_rel_err"] = float(((s1 - s0).abs() / s0.abs().clamp_min(1e-3)).max())
 print(json.dumps(res))
