@@ -225,6 +225,18 @@ VQA_API int vqa_agree(const int64_t *ids_a_dev, const float *scores_a_dev,
 VQA_API int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode,
                             int32_t *family, int32_t *n_launches);
 
+/* The same planning WITHOUT a device or a bound index (host arithmetic only): what vqa_search would do
+ * for an index of n_rows x dim `dtype` rows on a GPU with `sm_count` SMs and `max_smem` bytes of opt-in
+ * dynamic shared memory per CTA (B200: 148, 232448).  Lets the CPU test suite check the routing and that
+ * every planned launch fits shared and tensor memory.  out[16] (int32): 0 family, 1 queries per pass,
+ * 2 passes, 3 side-by-side groups, 4 ring stages, 5 k-blocks per stage, 6 MMA N (tensor family),
+ * 7 hi/lo split (tensor: ss_split, TS: ts_split), 8 QS variant, 9 query blocks in shared memory,
+ * 10 list length inside the scan, 11 candidates kept by the reduce (k_out), 12 reduce re-scores (0/1),
+ * 13 TMEM columns used, 14 reserved, 15 reserved; *smem_bytes = dynamic shared memory of the scan kernel. */
+VQA_API int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k,
+                              int32_t mode, int32_t sm_count, int32_t max_smem, int32_t *out,
+                              size_t *smem_bytes);
+
 /* ------------------------------------------------------------------------------------------------
  * Sparse (BM25) leg and hybrid fusion -- SURVEY.md 8(f) rank 3.
  * The reference builds its indexes with txtai.Embeddings(hybrid=True, ...)

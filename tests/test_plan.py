@@ -1,0 +1,97 @@
+"""The search planner on the CPU (vqa_plan_describe: host arithmetic only, no device): which kernel family a
+FAST search takes, and that EVERY planned launch fits the B200's shared memory (227 KB opt-in per CTA) and tensor
+memory (512 columns) -- with the default routing and with the opt-in kernels (VQA_TS_QS, VQA_REDUCE_SELECT)
+switched on.  A plan that does not fit would only fail on the GPU, as a launch error."""
+import ctypes
+import itertools
+
+import pytest
+
+from vietnamese_qa_system_b200 import _native as N
+
+F32, BF16, F16 = 0, 1, 2
+VERIFY, FAST, STREAM, TENSOR, TS = 0, 1, 2, 3, 4
+SMS, SMEM = 148, 232448
+
+
+def plan(n, dim, dtype, b, k, mode=FAST):
+    out = (ctypes.c_int32 * 16)()
+    smem = ctypes.c_size_t()
+    rc = N.lib().vqa_plan_describe(n, dim, dtype, b, k, mode, SMS, SMEM, out, ctypes.byref(smem))
+    if rc != 0:
+        return None
+    keys = ["family", "pass_nq", "passes", "groups", "stages", "kps", "ncol", "split", "qs", "ks", "kscan", "k_out",
+            "rescore", "tmem_query_cols"]
+    d = dict(zip(keys, list(out)))
+    d["smem"] = smem.value
+    return d
+
+
+def test_default_routing_is_the_measured_round1_routing(monkeypatch):
+    for v in ("VQA_TS_QS", "VQA_TS_KS", "VQA_REDUCE_SELECT", "VQA_TS_SPLIT", "VQA_TS_EXTRA"):
+        monkeypatch.delenv(v, raising=False)
+    n = 10_000_000
+    for b in (1, 8, 32):                                   # headline: smem-resident tcgen05 kernel, hi/lo columns
+        p = plan(n, 768, BF16, b, 10)
+        assert p["family"] == TENSOR and p["split"] == 1 and p["smem"] <= SMEM
+    for b in (33, 64, 128, 256, 1024):                     # large batches: queries in TMEM, screen + re-score of 32
+        p = plan(n, 768, BF16, b, 10)
+        assert (p["family"], p["split"], p["qs"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 0, 16, 32, 1)
+        assert p["tmem_query_cols"] == 384 and p["stages"] * p["kps"] == 24 and p["smem"] <= SMEM
+    p = plan(n, 768, BF16, 8, 100)                         # k > 32: TS with hi/lo rows and heaps, no re-scoring
+    assert (p["family"], p["split"], p["qs"], p["kscan"], p["rescore"]) == (TS, 1, 0, 100, 0)
+    p = plan(12_500_000, 1024, F16, 64, 100)               # BASELINE configs[3]: dim 1024 does not fit TMEM -> smem-resident
+    assert p["family"] == TENSOR and p["qs"] == 0
+    assert plan(n, 1024, BF16, 64, 10, TS) is None         # asking for TS explicitly at dim 1024: unsupported by default
+    assert plan(n, 768, F32, 4, 10)["family"] == STREAM and plan(n, 776, BF16, 4, 10)["family"] == STREAM
+    assert plan(n, 768, BF16, 4, 10, VERIFY)["family"] == STREAM
+
+
+@pytest.mark.parametrize("qs,select", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_every_plan_fits_shared_and_tensor_memory(monkeypatch, qs, select):
+    monkeypatch.setenv("VQA_TS_QS", str(qs))
+    monkeypatch.setenv("VQA_REDUCE_SELECT", str(select))
+    seen = set()
+    dims = [64, 128, 192, 256, 384, 512, 640, 768, 832, 896, 960, 1024, 1088, 2048]
+    for dim, dtype, b, k in itertools.product(dims, (BF16, F16), (1, 7, 32, 33, 64, 65, 128, 129, 300, 1024),
+                                              (1, 10, 16, 26, 27, 32, 33, 64, 100, 122, 123, 128)):
+        for ks in ([None] if not qs else [None, 0, 2, 4, 8, 16]):
+            if ks is None:
+                monkeypatch.delenv("VQA_TS_KS", raising=False)
+            else:
+                monkeypatch.setenv("VQA_TS_KS", str(ks))
+            p = plan(2_000_000, dim, dtype, b, k)
+            assert p is not None, (dim, dtype, b, k, ks)
+            assert p["smem"] <= SMEM, (dim, dtype, b, k, ks, p)
+            seen.add((p["family"], p["qs"], p["split"], p["rescore"]))
+            if p["family"] == TS:
+                kb = dim // 64
+                assert p["stages"] >= 2 and kb % p["kps"] == 0 and 0 <= p["ks"] <= kb
+                assert p["tmem_query_cols"] + 64 <= 512                       # at least one accumulator stage
+                assert qs or (p["qs"] == 0 and p["ks"] == 0 and dim <= 768)
+                assert p["kscan"] <= 128 and p["k_out"] <= 128 and p["kscan"] >= k
+                if p["rescore"] and p["k_out"] > 32:                          # only the radix select re-scores > 32
+                    assert select and qs and dtype == F16
+                if dim > 768:
+                    assert p["tmem_query_cols"] <= 384                        # two accumulator stages
+            if p["family"] == TENSOR:
+                assert p["stages"] >= 2 and p["ncol"] in (16, 32, 64, 128)
+    assert (TENSOR, 0, 1, 0) in seen
+    if qs:
+        assert (TS, 1, 0, 1) in seen and (TS, 1, 1, 0) in seen
+    else:
+        assert (TS, 0, 0, 1) in seen and (TS, 0, 1, 0) in seen
+
+
+def test_config_d_plan_with_the_opt_in_kernels(monkeypatch):
+    """BASELINE configs[3] (12.5 M x 1024 fp16 per GPU, B = 64, top-100) under VQA_TS_QS=1 VQA_REDUCE_SELECT=1:
+    one pass of the TMEM-resident-query kernel -- 12 query blocks in tensor memory, 4 in shared memory, heaps for
+    64 rows, 106 candidates per list, the 128 best re-scored exactly by the radix-select reduce."""
+    monkeypatch.setenv("VQA_TS_QS", "1")
+    monkeypatch.setenv("VQA_REDUCE_SELECT", "1")
+    monkeypatch.delenv("VQA_TS_KS", raising=False)
+    p = plan(12_500_000, 1024, F16, 64, 100)
+    assert (p["family"], p["qs"], p["ks"], p["split"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 1, 4, 0, 106, 128, 1)
+    assert p["passes"] == 1 and p["tmem_query_cols"] == 384 and p["stages"] >= 3 and p["smem"] <= SMEM
+    q = plan(12_500_000, 1024, BF16, 64, 100)              # bf16 rows: 8-bit queries would need ~28 spare ranks -> hi/lo rows
+    assert (q["family"], q["qs"], q["split"], q["rescore"]) == (TS, 1, 1, 0) and q["smem"] <= SMEM

@@ -28,7 +28,7 @@ EXPORTS = [
     "vqa_index_destroy", "vqa_workspace_bytes", "vqa_search", "vqa_search_host_staging_bytes",
     "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_exchange_push", "vqa_merge_topk_wait",
     "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
-    "vqa_search_plan",
+    "vqa_search_plan", "vqa_plan_describe",
     "vqa_sparse_limits", "vqa_sparse_create", "vqa_sparse_bind", "vqa_sparse_destroy", "vqa_bm25_weights",
     "vqa_sparse_workspace_bytes", "vqa_sparse_search", "vqa_hybrid_fuse", "vqa_agree_f64",
 ]
@@ -80,6 +80,8 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_agree.argtypes = [vp, vp, vp, vp, i64, c.c_double, vp, vp, i32, vp]
     L.vqa_search_plan.restype = c.c_int
     L.vqa_search_plan.argtypes = [vp, i32, i32, i32, c.POINTER(i32), c.POINTER(i32)]
+    L.vqa_plan_describe.restype = c.c_int
+    L.vqa_plan_describe.argtypes = [i64, i32, i32, i32, i32, i32, i32, i32, c.POINTER(i32), c.POINTER(sz)]
     L.vqa_sparse_limits.restype = c.c_int
     L.vqa_sparse_limits.argtypes = [c.POINTER(i32), c.POINTER(i32)]
     L.vqa_sparse_create.restype = c.c_int

@@ -429,6 +429,60 @@ int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t 
     return VQA_OK;
 }
 
+int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k, int32_t mode,
+                      int32_t sm_count, int32_t max_smem, int32_t *out, size_t *smem_bytes) {
+    if (!out || !smem_bytes) return fail(VQA_E_INVALID, "null output pointer");
+    const int es = elem_size(dtype);
+    if (!es) return fail(VQA_E_INVALID, "row dtype must be F32, BF16 or F16 (got %d)", dtype);
+    if (n_rows < 0 || n_rows > 0x7fffffffLL || dim < 1 || ((int64_t)dim * es) % 16 != 0 || dim > 8192)
+        return fail(VQA_E_INVALID, "bad index shape");
+    if (sm_count < 1 || max_smem < 1) return fail(VQA_E_INVALID, "bad device description");
+    vqa_index fake;
+    fake.n_rows = n_rows;
+    fake.dim = dim;
+    fake.dtype = dtype;
+    fake.sm_count = sm_count;
+    fake.max_smem = max_smem;
+    fake.tmap_ok = n_rows > 0 && es == 2 && dim % 64 == 0;  // what vqa_index_bind would have built
+    int rc = check_search_args(&fake, n_queries, k);
+    if (rc) return rc;
+    Plan pl;
+    rc = make_plan(&fake, n_queries, k, mode, &pl);
+    if (rc) return rc;
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    out[0] = pl.family;
+    out[1] = pl.pass_nq;
+    out[2] = pl.passes;
+    out[3] = pl.groups;
+    out[4] = pl.stages;
+    out[5] = pl.kps;
+    out[6] = pl.ncol;
+    *smem_bytes = 0;
+    if (pl.family == VQA_MODE_FAST_TS) {
+        const int kscan = pl.ts_split ? k : k + spare_ranks();
+        const int nq_launch = n_queries < pl.groups * pl.pass_nq ? n_queries : pl.groups * pl.pass_nq;
+        out[7] = pl.ts_split;
+        out[8] = pl.ts_qs;
+        out[9] = pl.ts_ks;
+        out[10] = kscan;
+        out[11] = pl.ts_split ? kscan : (kscan > 32 ? vqa::kMaxK : 32);
+        out[12] = pl.ts_split ? 0 : 1;
+        out[13] = (dim / vqa::kBlockK - pl.ts_ks) * (vqa::kBlockK / 2);  // query block; the rest are accumulators
+        *smem_bytes = vqa::ts_smem_bytes(kscan, pl.stages * pl.kps, pl.ts_split, pl.ts_ks, nq_launch, pl.ts_qs);
+    } else if (pl.family == VQA_MODE_FAST_TENSOR) {
+        const int kscan = pl.ss_split ? k : k + spare_ranks();
+        out[7] = pl.ss_split;
+        out[10] = kscan;
+        out[11] = pl.ss_split ? kscan : 32;
+        out[12] = pl.ss_split ? 0 : 1;
+        *smem_bytes = vqa::mma_smem_bytes_rt(pl.ncol, dim, kscan, pl.stages * pl.kps, pl.ss_split);
+    } else {
+        out[10] = k;
+        out[11] = k;
+    }
+    return VQA_OK;
+}
+
 int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode, size_t *bytes) {
     int rc = check_search_args(h, n_queries, k);
     if (rc) return rc;

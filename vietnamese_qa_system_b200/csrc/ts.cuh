@@ -437,6 +437,70 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             const long long doc0 = (long long)tile * kTsDocs;
             const int ndoc = p.n_rows - doc0 < kTsDocs ? (int)(p.n_rows - doc0) : kTsDocs;
             float *xb = xchg + (size_t)(lt & 1) * 64 * kTsDocs;
+            if constexpr (QS) {
+                // QS variants: all 64 scores of the row -> registers, then the accumulator stage goes back to the
+                // MMA warp BEFORE the scores are looked at (the classic loop below holds it through every flush).
+                // Hot path: one max tree + one ballot per tile; the append / flush code exists once, in a rolled loop.
+                float v[kTsDocs];
+                {
+                    uint32_t acc[4][16];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ptx::tmem_ld16(taddr + c * 16, acc[c]);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[c * 16 + j] = __uint_as_float(acc[c][j]);
+                }
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty + as);
+                if (p.split) {
+                    // lo rows publish, hi rows add: xb[doc][row & 63]
+                    if (is_lo) {
+#pragma unroll
+                        for (int j = 0; j < kTsDocs; ++j) xb[j * 64 + (row & 63)] = v[j];
+                    }
+                    __syncwarp();
+                    named_bar_sync(2 + (warp & 1), 64);  // warps (0,2) and (1,3) pair up
+                    if (!is_lo) {
+#pragma unroll
+                        for (int j = 0; j < kTsDocs; ++j) v[j] += xb[j * 64 + row];
+                    }
+                }
+                float mx[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mx[j] = fmaxf(fmaxf(v[j], v[16 + j]), fmaxf(v[32 + j], v[48 + j]));
+#pragma unroll
+                for (int st = 8; st >= 1; st >>= 1)
+#pragma unroll
+                    for (int j = 0; j < st; ++j) mx[j] = fmaxf(mx[j], mx[j + st]);
+                if (__ballot_sync(kFullMask, mx[0] >= tau) != 0) {
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        const int c0 = c * 16;
+                        float w[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            w[j] = c == 0 ? v[j] : (c == 1 ? v[16 + j] : (c == 2 ? v[32 + j] : v[48 + j]));
+                        float m = w[0];
+#pragma unroll
+                        for (int j = 1; j < 16; ++j) m = fmaxf(m, w[j]);
+                        if (__ballot_sync(kFullMask, m >= tau) != 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (w[j] >= tau && c0 + j < ndoc) {
+                                    buf_s[cnt * LR + lrow] = w[j];
+                                    buf_i[cnt * LR + lrow] = (uint32_t)(doc0 + c0 + j);
+                                    ++cnt;
+                                }
+                            }
+                            if (__ballot_sync(kFullMask, cnt > CAP - 16) != 0) flush();
+                        }
+                    }
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < kTsDocs; c0 += 16) {
                 uint32_t acc[16];
