@@ -11,6 +11,10 @@ VQA_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -
 echo "== top-100, 4M x 768 bf16: list-insertion reduce vs radix select (default kernel family = TS hi/lo heaps)"
 for SEL in 0 1; do run ROWS=4000000 K=100 MODE=fast BATCHES=8,64 ITERS=10 VQA_REDUCE_SELECT=$SEL; done
 
+echo "== top-100, 4M x 768 bf16 on the QS kernel: hi/lo heaps with early accumulator release; screen (128 candidates) + exact re-score"
+run ROWS=4000000 K=100 MODE=fast BATCHES=8,64 ITERS=10 VQA_REDUCE_SELECT=1 VQA_TS_QS=1
+run ROWS=4000000 K=100 MODE=fast BATCHES=8,64 ITERS=10 VQA_REDUCE_SELECT=1 VQA_TS_QS=1 VQA_TS_SPLIT=0 VQA_TS_EXTRA=28
+
 echo "== BASELINE configs[3] shard: 12.5M x 1024 fp16, B = 64, top-100 (HBM floor 3.9 ms)"
 run ROWS=12500000 DIM=1024 DTYPE=fp16 K=100 MODE=fast BATCHES=64 ITERS=5
 run ROWS=12500000 DIM=1024 DTYPE=fp16 K=100 MODE=fast BATCHES=64 ITERS=5 VQA_REDUCE_SELECT=1
@@ -28,3 +32,6 @@ run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256,512 ITERS=5
 for KS in 0 2 4 6; do
   run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256,512 ITERS=5 VQA_TS_QS=1 VQA_TS_KS=$KS
 done
+
+echo "== regression check of the default path: the headline bench line"
+timeout 900 python bench.py --steps 50 --warmup 5 2>&1 | tail -n 1 | cut -c1-600
