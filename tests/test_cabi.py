@@ -163,3 +163,29 @@ def test_product_never_references_the_emulator():
                 with open(os.path.join(dp, fn), encoding="utf-8") as f:
                     src = f.read()
                 assert "cuda_emu" not in src and "tests/emu" not in src and "tests.emu" not in src, fn
+
+
+def test_measured_kernels_are_unchanged():
+    """The tensor-core kernels on the DEFAULT routing are instruction-for-instruction the ones measured on the
+    B200 in round 1 (profiles/r1_measured_kernel_sass.json): the opt-in variants added since (QS, radix select)
+    must not perturb them.  Compares SASS instruction streams of the current build; skipped when the toolchain
+    differs from the one that produced the fingerprints."""
+    import json
+    import shutil
+    import sys
+
+    if shutil.which("cuobjdump") is None or shutil.which("nvcc") is None:
+        pytest.skip("cuobjdump / nvcc not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_fingerprint as sf
+
+    N.lib()  # make sure the objects exist
+    with open(sf.GOLD) as f:
+        gold = json.load(f)
+    if sf.nvcc_version() != gold["nvcc"]:
+        pytest.skip(f"nvcc {sf.nvcc_version()} != {gold['nvcc']} (fingerprints are compiler specific)")
+    cur = sf.fingerprints()
+    assert len(gold["kernels"]) >= 10
+    for name, want in gold["kernels"].items():
+        assert name in cur, name
+        assert cur[name] == want, f"{name}: default-path kernel changed ({cur[name]['instructions']} vs {want['instructions']} instructions)"

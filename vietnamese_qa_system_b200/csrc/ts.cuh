@@ -335,7 +335,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 rs[e] = neg_inf();
                 ri[e] = invalid_id<uint32_t>();
             }
-        } else if (!is_lo) {
+        } else if (!is_lo && (!QS || row < LR)) {  // (QS with <= 64 queries: rows 64.. own no list column)
             for (int e = 0; e < p.k; ++e) {
                 lst_s[e * LR + lrow] = neg_inf();
                 lst_i[e * LR + lrow] = invalid_id<uint32_t>();
@@ -499,8 +499,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                         }
                     }
                 }
-                continue;
-            }
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < kTsDocs; c0 += 16) {
                 uint32_t acc[16];
@@ -540,6 +539,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty + as);
+            }  // classic epilogue (QS = false)
         }
         flush();
         // 3. publish this row's list
