@@ -20,7 +20,7 @@ pytestmark = [pytest.mark.gpu,
 DEV = "cuda:0"
 
 
-def _check(docs, q, k, mode, storage, exact_scores=True):
+def _check(docs, q, k, mode, storage):
     s, i, stored = gpu_search(docs, q, k, mode, storage)
     os_, oi = oracle.search(stored, q, k, oracle.CANONICAL, storage)
     assert recall(i, oi) >= 0.999

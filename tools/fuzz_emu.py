@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE: randomised differential run of the emulated CUDA-core kernels (tests/emu) against the oracle.
-Random shapes for the fp32-verify search (all storage types), the BM25 leg and K1; bit-exact / tolerance checks as in
-tests/test_emu_kernels.py.  usage: python tools/fuzz_emu.py [seed] [seconds]   (CPU only, no GPU needed)"""
+Random shapes for the fp32-verify search (all storage types), the BM25 leg, K1 and the tcgen05 kernels (smem-resident and
+TMEM-resident queries, incl. the opt-in QS variants up to dim 1024 and both k > 32 reduce kernels); bit-exact / tolerance
+checks as in tests/test_emu_kernels.py.  usage: python tools/fuzz_emu.py [seed] [seconds]   (CPU only, no GPU needed)"""
 import ctypes
 import os
 import sys
