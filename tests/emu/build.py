@@ -79,6 +79,10 @@ def transform(name: str, src: str) -> str:
         src, c = re.subn(r'asm volatile\("bar\.arrive %0, %1;" ::"r"\(id\), "r"\(count\) : "memory"\);',
                          "emu::named_bar_arrive(id, count);", src)
         assert (a, b, c) == (1, 1, 1), (a, b, c)
+        # count list updates of the register-list epilogue (lane 0 only: one event per warp-wide call)
+        src, d = re.subn(r"(static __device__ __noinline__ Entry reglist_(?:insert_one|merge32)\([^)]*\) \{\n)",
+                         r"\1    if ((threadIdx.x & 31) == 0) ++emu_event_counter();\n", src)
+        assert d == 2, d
     if name == "ts.cuh":
         src, a = re.subn(r'asm volatile\(\s*"tcgen05\.st\.sync\.aligned\.32x32b\.x16\.b32.*?: "memory"\);',
                          "ptx::model_tmem_st16(taddr, r);", src, flags=re.S)

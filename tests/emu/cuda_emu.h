@@ -325,6 +325,11 @@ inline unsigned __ballot_sync(unsigned m, int pred) {
     for (int i = 0; i < 32; ++i) r |= (unsigned)all[i] << i;
     return r;
 }
+// event counter for tests (tests/emu/build.py injects increments into selected device functions)
+inline long long &emu_event_counter() {
+    static long long c = 0;
+    return c;
+}
 inline unsigned __match_any_sync(unsigned m, unsigned v) {
     emu_check_mask(m);
     unsigned all[32];

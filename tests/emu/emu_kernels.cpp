@@ -47,6 +47,13 @@ extern "C" {
 
 const char *emu_last_error() { return g_emu_err.c_str(); }
 
+// list-update events of the register-list tensor-core epilogue since the last call (see build.py)
+long long emu_events_read_reset() {
+    const long long c = emu_event_counter();
+    emu_event_counter() = 0;
+    return c;
+}
+
 // fiber order inside a scheduling pass: 0 thread order, 1 reverse, 2 random permutation per pass (seeded)
 void emu_set_schedule(int mode, unsigned long long seed) {
     emu::S().schedule = mode;
@@ -199,8 +206,9 @@ int emu_reduce_u32(const float *cand_s, const uint32_t *cand_i, int n_lists, int
 // as api.cu does it.  rows: 16-bit storage [n_rows][dim]; ncol in {16, 32, 64, 128}; the batch is cut into chunks
 // of ncol / 2 queries handled side by side (n_groups = chunks).
 int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, const float *q, int n_queries, int k,
-                      long long first_id, int sm_count, int ncol, int stages, int kps, int multicast, float *out_s,
-                      long long *out_i) {
+                      long long first_id, int sm_count, int ncol, int stages, int kps, int multicast, int tb,
+                      unsigned long long *slots /* [n_queries][32], caller-initialised (zeros or garbage) */,
+                      float *out_s, long long *out_i) {
     return guarded([&] {
         const int pass_nq = ncol / 2;
         int g = (n_queries + pass_nq - 1) / pass_nq;
@@ -252,9 +260,10 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
         a.cand_stride = cstride;
         a.tau_g = tau_g.data();
         a.epoch = 1;
+        a.slot_g = (tb && pass_nq <= 32 && k <= 32) ? slots : nullptr;  // api.cu's rule for the TB variants
         if (vqa::launch_mma(a, nullptr) != cudaSuccess) throw std::runtime_error("tensor scan launch failed");
         if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, k, grid, k, k, first_id, out_s, out_i,
-                                   n_queries, tau_g.data(), g, pass_nq, nullptr, nullptr) != cudaSuccess)
+                                   n_queries, tau_g.data(), g, pass_nq, nullptr, nullptr, a.slot_g) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }

@@ -3,6 +3,8 @@ not yet been run or timed on a B200, so the default routing does not use them:
   * VQA_REDUCE_SELECT=1 -- radix-select candidate reduce for k > 32 (scan.cuh reduce_select_kernel)
   * VQA_TS_QS=1 [VQA_TS_KS=n] -- TMEM-resident-query kernel with part of the query block in shared memory
     (ts.cuh, QS variants): dim <= 1024, more accumulator stages at dim 768
+  * VQA_MMA_TB=1 -- tournament bound in the smem-resident tcgen05 kernel (mma.cuh, TB variants): every list publishes
+    its best score into slot (list % k); the minimum of a query's k slots is shared as a threshold
 Skipped unless VQA_EXPERIMENTAL=1 (tools/r2_experiments.sh sets it): a kernel that has never met the hardware
 must not be able to take the round-end `pytest -m gpu` run down with it.  Same bars as tests/test_gpu_search.py."""
 import os
@@ -104,3 +106,49 @@ def test_full_size_config_d_shard_properties(monkeypatch):
     a, r = i1.cpu().tolist(), i_ref.cpu().tolist()
     assert sum(len(set(x) & set(y)) for x, y in zip(a, r)) / (b * k) >= 0.999
     assert float(((s1 - s_ref).abs() / s_ref.abs()).max()) < 1e-5
+
+
+@pytest.mark.parametrize("storage,n,d,b,k", [("bf16", 200000, 768, 32, 10), ("bf16", 50000, 768, 1, 10),
+                                             ("fp16", 100000, 384, 16, 32), ("bf16", 3000, 768, 8, 5),
+                                             ("bf16", 150000, 768, 100, 10)])
+def test_tournament_bound_leaves_results_unchanged(monkeypatch, storage, n, d, b, k):
+    """A valid lower bound of the k-th best score cannot change the answer: ids and score bits equal the run without
+    it, twice in a row (the reduce clears the slots), and under CUDA-graph replay (the epoch is baked in)."""
+    rng = np.random.default_rng(n + b)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    monkeypatch.setenv("VQA_MMA_TB", "0")
+    s0, i0, _ = gpu_search(docs, q, k, "tensor", storage)
+    monkeypatch.setenv("VQA_MMA_TB", "1")
+    for _ in range(2):
+        s1, i1, _ = gpu_search(docs, q, k, "tensor", storage)
+        assert np.array_equal(i0, i1) and np.array_equal(s0.view(np.int32), s1.view(np.int32))
+    assert i1[0, :2].tolist() == [3, n // 2]
+
+
+def test_tournament_bound_under_graph_replay(monkeypatch):
+    from vietnamese_qa_system_b200 import ops
+
+    monkeypatch.setenv("VQA_MMA_TB", "1")
+    rng = np.random.default_rng(5)
+    rows = torch.from_numpy(unit_rows(rng, 100000, 768)).to(DEV).to(torch.bfloat16)
+    shard = ops.FlatShard(rows)
+    q = torch.from_numpy(unit_rows(rng, 32, 768)).to(DEV)
+    want_s, want_i = (t.clone() for t in shard.search(q, 10, "tensor"))
+    out_s, out_i = torch.empty_like(want_s), torch.empty_like(want_i)
+    shard.search(q, 10, "tensor", out_s, out_i)             # warm-up outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        shard.search(q, 10, "tensor", out_s, out_i)
+    for rep in range(3):
+        q2 = torch.from_numpy(unit_rows(np.random.default_rng(rep), 32, 768)).to(DEV)
+        q.copy_(q2)                                         # new queries, same captured epoch: stale slots would be wrong
+        g.replay()
+        torch.cuda.synchronize()
+        monkeypatch.setenv("VQA_MMA_TB", "0")
+        ref_s, ref_i = shard.search(q, 10, "tensor")
+        monkeypatch.setenv("VQA_MMA_TB", "1")
+        torch.cuda.synchronize()
+        assert torch.equal(out_i, ref_i) and torch.equal(out_s, ref_s)

@@ -8,6 +8,10 @@ run() { echo -n "$* -> "; env "$@" CHECK=1 timeout 600 python tools/tune_worker.
 echo "== correctness first: the experimental GPU tests"
 VQA_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -x -q 2>&1 | tail -n 5
 
+echo "== headline kernel, 8-GPU shard size (1.25 M rows) and full size: tournament bound off / on (B-dependent list-update cost)"
+for TB in 0 1; do run ROWS=1250000 K=10 MODE=tensor BATCHES=1,8,16,32 ITERS=50 VQA_MMA_TB=$TB; done
+for TB in 0 1; do run ROWS=10000000 K=10 MODE=tensor BATCHES=1,32 ITERS=10 VQA_MMA_TB=$TB; done
+
 echo "== top-100, 4M x 768 bf16: list-insertion reduce vs radix select (default kernel family = TS hi/lo heaps)"
 for SEL in 0 1; do run ROWS=4000000 K=100 MODE=fast BATCHES=8,64 ITERS=10 VQA_REDUCE_SELECT=$SEL; done
 

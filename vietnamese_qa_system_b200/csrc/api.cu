@@ -193,6 +193,7 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
 // scan.cuh radix-select reduce).  Off by default: the default routing is exactly what round 1 measured.
 bool ts_qs_enabled() { return env_int("VQA_TS_QS", 0) != 0; }
 bool reduce_select_enabled() { return env_int("VQA_REDUCE_SELECT", 0) != 0; }
+bool mma_tb_enabled() { return env_int("VQA_MMA_TB", 0) != 0; }  // tournament bound in the smem-resident kernel (mma.cuh)
 
 bool ts_eligible(const vqa_index *h) {
     return tensor_eligible(h) && (h->dim <= 768 || (ts_qs_enabled() && h->dim <= 1024));
@@ -489,7 +490,8 @@ int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int3
     if (!bytes) return fail(VQA_E_INVALID, "bytes is null");
     (void)mode;
     // candidates: per CTA, per query, k entries of (float score, u32 row); + one shared-threshold slot per query
-    *bytes = cand_elems(h, n_queries, k) * 8 + (size_t)n_queries * 8 + 512;
+    // (+ 32 tournament slots per query for the opt-in TB scan variants)
+    *bytes = cand_elems(h, n_queries, k) * 8 + (size_t)n_queries * 8 + 512 + (size_t)n_queries * 32 * 8 + 256;
     return VQA_OK;
 }
 
@@ -520,6 +522,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     uint32_t *cand_i = reinterpret_cast<uint32_t *>(cand_s + cand_elems(h, n_queries, k));
     unsigned long long *tau_g = reinterpret_cast<unsigned long long *>(
         (reinterpret_cast<uintptr_t>(cand_i + cand_elems(h, n_queries, k)) + 255) & ~(uintptr_t)255);
+    unsigned long long *slot_g = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(tau_g + n_queries) + 255) & ~(uintptr_t)255);  // [n_queries][32]
     const long long cand_stride = (long long)n_queries * k;
     static std::atomic<uint32_t> g_epoch{1};
     const uint32_t epoch = g_epoch.fetch_add(2, std::memory_order_relaxed);  // odd, unique, never 0 (0 = cleared slot)
@@ -639,6 +643,9 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.cand_stride = cstride;
             a.tau_g = tau_g + l0;
             a.epoch = epoch;
+            // opt-in tournament bound: register-list path only (<= 32 queries per CTA, list length <= 32)
+            const bool tb = mma_tb_enabled() && pl.pass_nq <= 32 && kscan <= 32;
+            a.slot_g = tb ? slot_g + (long long)l0 * 32 : nullptr;
             cudaError_t e = vqa::launch_mma(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
             vqa::Rescore rs;
@@ -652,7 +659,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, pl.ss_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
                                        (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
-                                       pl.ss_split ? nullptr : &rs);
+                                       pl.ss_split ? nullptr : &rs, a.slot_g);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;

@@ -47,6 +47,7 @@ struct MmaLaunch {
     long long cand_stride;
     unsigned long long *tau_g;  // [nq] shared thresholds for this pass (or nullptr)
     uint32_t epoch;
+    unsigned long long *slot_g = nullptr;  // opt-in TB variants: [nq][32] tournament slots (see MmaParams), else nullptr
 };
 
 struct TsLaunch {
@@ -98,7 +99,8 @@ struct Rescore {
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr);
+                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr,
+                              unsigned long long *slot_reset = nullptr);
 struct WaitFlags {
     const unsigned long long *flags = nullptr;
     int n = 0;

@@ -25,8 +25,9 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
                                    long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                                    float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                                    int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr,
-                                   const WaitFlags *wf = nullptr) {
+                                   const WaitFlags *wf = nullptr, unsigned long long *slot_reset = nullptr) {
     ReduceParams<IdT> p;
+    p.slot_reset = k_out <= 32 ? slot_reset : nullptr;
     p.wait_flags = wf ? wf->flags : nullptr;
     p.wait_n = wf ? wf->n : 0;
     p.wait_epoch = wf ? wf->epoch : 0;
@@ -92,9 +93,10 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs) {
+                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs,
+                              unsigned long long *slot_reset) {
     return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
-                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, rs);
+                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, rs, nullptr, slot_reset);
 }
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out,

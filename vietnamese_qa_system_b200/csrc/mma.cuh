@@ -61,7 +61,14 @@ struct MmaParams {
     // k-th best).  A document scoring below any list's k-th best cannot be in the global top-k.
     unsigned long long *tau_g;  // [nq] for this pass, or nullptr
     uint32_t epoch;
+    // TB variants ("tournament bound", opt-in): [nq][kSlotStride] slots, same encoding as tau_g.  List l of a
+    // query publishes its BEST score into slot l % k; the k slots then hold the scores of k distinct documents,
+    // so their minimum is a lower bound of the global k-th best -- close to the exact one, because the top-k
+    // documents mostly sit in different lists -- long before any single list's own k-th best gets there.
+    unsigned long long *slot_g;
 };
+
+constexpr int kSlotStride = 32;  // slots reserved per query (k <= 32 on the register-list path)
 
 // order-preserving float -> uint32 (larger float <=> larger uint), tagged with the search epoch
 __device__ __forceinline__ unsigned long long tau_encode(float f, uint32_t epoch) {
@@ -262,7 +269,7 @@ __device__ __forceinline__ void load_scores16(uint32_t taddr, int c0, float lo_i
 // SPLIT: hi + lo column per query (NCOL / 2 queries per CTA, scores good to fp32 rounding).
 // !SPLIT: one storage-precision column per query (NCOL queries per CTA): a SCREEN whose k + spare best
 // candidates are re-scored exactly by the reduce kernel (screen-then-rescore, k + spare <= 32).
-template <bool BF16, int NCOL, bool SPLIT>
+template <bool BF16, int NCOL, bool SPLIT, bool TB = false>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p) {
     constexpr int NQ = SPLIT ? NCOL / 2 : NCOL;  // queries per CTA
@@ -490,6 +497,8 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                         const bool pass = valid && v[j] >= tau[q];
                         unsigned m = __ballot_sync(kFullMask, pass);
                         if (m != 0) {
+                            float top_before = 0.f;
+                            if constexpr (TB) top_before = __shfl_sync(kFullMask, ls[q], 0);
                             if (__popc(m) >= 4) {
                                 const Entry e = reglist_merge32(ls[q], li[q], pass ? v[j] : neg_inf(),
                                                                 pass ? base_row + lane : invalid_id<uint32_t>(), false);
@@ -510,6 +519,25 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                             if (last != invalid_id<uint32_t>() && ts > tau[q]) {
                                 tau[q] = ts;
                                 if (tau_g != nullptr && lane == 0) atomicMax(tau_g + q, tau_encode(ts, p.epoch));
+                            }
+                            if constexpr (TB) {
+                                // this list's best improved (rare: ~ln(n) times per list): publish it into the
+                                // list's slot, re-read the query's k slots and share their minimum as a threshold
+                                const float top_after = __shfl_sync(kFullMask, ls[q], 0);
+                                if (top_after > top_before && p.slot_g != nullptr && tau_g != nullptr) {
+                                    unsigned long long *sl = p.slot_g + (long long)(q0 + q) * kSlotStride;
+                                    const int my_slot = (stream0 * 4 + warp) % p.k;
+                                    if (lane == 0) atomicMax(sl + my_slot, tau_encode(top_after, p.epoch));
+                                    float b = __int_as_float(0x7f800000);
+                                    if (lane < p.k) b = tau_decode(ld_volatile_u64(sl + lane), p.epoch);
+                                    if (lane == my_slot) b = fmaxf(b, top_after);  // (lane 0's atomic may not be visible yet)
+#pragma unroll
+                                    for (int sh = 16; sh >= 1; sh >>= 1) b = fminf(b, __shfl_xor_sync(kFullMask, b, sh));
+                                    if (b > tau[q]) {
+                                        tau[q] = b;
+                                        if (lane == 0) atomicMax(tau_g + q, tau_encode(b, p.epoch));
+                                    }
+                                }
                             }
                         }
                     }

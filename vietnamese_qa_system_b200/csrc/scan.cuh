@@ -247,6 +247,7 @@ struct ReduceParams {
     float *out_s;     // [nq][k_out]
     long long *out_i;
     unsigned long long *tau_g_reset;  // [n_queries] shared-threshold slots to clear for the next search, or nullptr
+    unsigned long long *slot_reset;   // [n_queries][32] tournament slots of the TB scan variants to clear, or nullptr
     // Exact re-scoring of the merged candidates (screen-then-rescore): the scan ranked documents with
     // storage-precision queries; the k_out survivors get their exact fp32 dot product (fp32 query x
     // stored row) here, are re-sorted, and the best k_final are written.  rs_rows == nullptr: off.
@@ -443,6 +444,7 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
         p.out_i[(long long)q * kf + lane] = ok ? (long long)li + p.id_base : -1LL;
     }
     if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;  // a graph replay reuses the epoch
+    if (p.slot_reset != nullptr) p.slot_reset[(long long)q * 32 + lane] = 0ull;
 }
 
 // k_out in (32, 128]: one CTA of 8 warps per query.  Phase 1: warp w folds the candidate lists
