@@ -279,7 +279,7 @@ def test_emulated_reduce_with_exact_rescoring(emu, kind):
 
 
 @pytest.mark.parametrize("lists,b,k_in,k_out,lmod", [
-    (148, 3, 100, 100, 1),     # top-100 over the lists of 148 CTAs (BASELINE configs[3]'s k; hybrid search's 10 x limit)
+    (148, 2, 100, 100, 1),     # top-100 over the lists of 148 CTAs (BASELINE configs[3]'s k; hybrid search's 10 x limit)
     (7, 4, 128, 128, 1),       # the largest k
     (12, 6, 40, 33, 3),        # three query chunks side by side: query j lives in the lists l % 3 == j // 2
     (3, 2, 64, 64, 1),         # fewer valid candidates than k_out: padded with (-inf, -1)
@@ -473,9 +473,9 @@ def test_emulated_query_block_split_between_tmem_and_smem(emu, monkeypatch, kind
 
 
 @pytest.mark.parametrize("kind,dim,n,b,k,sm,ncol,stages,kps,mc,init", [
-    ("bf16", 768, 3000, 8, 10, 12, 16, 4, 2, 0, "zeros"),      # 48 lists, 10 slots: the bound becomes live after a few CTAs
-    ("bf16", 128, 4000, 32, 10, 20, 64, 3, 2, 0, "garbage"),   # B = 32 (the headline shape); uninitialised workspace
-    ("f16", 256, 2500, 40, 5, 16, 32, 4, 1, 1, "zeros"),       # cluster of 4, three query chunks: lists per chunk
+    ("bf16", 256, 3000, 8, 10, 12, 16, 4, 2, 0, "zeros"),      # 48 lists, 10 slots: the bound becomes live after a few CTAs
+    ("bf16", 64, 900, 32, 10, 6, 64, 3, 1, 0, "garbage"),      # B = 32 (the headline shape); uninitialised workspace
+    ("f16", 128, 2100, 40, 5, 12, 32, 4, 1, 1, "zeros"),       # cluster of 4, three query chunks: lists per chunk
     ("bf16", 64, 700, 3, 32, 6, 16, 4, 1, 0, "zeros"),         # k = 32 > number of lists (24): some slots never fill
     ("f16", 128, 900, 5, 1, 8, 16, 4, 2, 0, "stale"),          # k = 1: slot 0 is the running global maximum; stale-epoch slots
 ])
