@@ -330,6 +330,41 @@ def test_emulated_radix_select_reduce_equals_the_list_insertion_reduce(emu, monk
         assert np.all(outs[1][1][j, n:] == -1) and np.all(np.isneginf(outs[1][0][j, n:]))
 
 
+@pytest.mark.parametrize("lists,b,k_in,k_out", [(148, 3, 10, 10), (148, 2, 16, 32), (33, 4, 32, 32), (5, 3, 7, 5)])
+def test_emulated_warp_reduce_early_exit_is_exact(emu, monkeypatch, lists, b, k_in, k_out):
+    """Opt-in VQA_REDUCE_EARLY=1: the k <= 32 reduce stops reading once a window holding one entry of every
+    (best-first sorted) list offered nothing above the running k-th best.  Same ids and score bits as the full pass,
+    and as numpy -- with ties, short lists and winners buried deep in one list."""
+    emu.emu_reduce_u32.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp]
+    rng = np.random.default_rng(lists + k_in)
+    cand_s = np.full((lists, b, k_in), -np.inf, np.float32)
+    cand_i = np.full((lists, b, k_in), 0xFFFFFFFF, np.uint32)
+    for j in range(b):
+        rows = rng.permutation(1 << 20)[:lists * k_in].astype(np.uint32).reshape(lists, k_in)
+        sc = rng.choice(np.linspace(0, 1, 40, dtype=np.float32), (lists, k_in))        # heavy ties
+        if j == 1:
+            sc[lists // 2] = 2.0                                                       # every winner in ONE list
+        fill = rng.integers(0, k_in + 1, lists)                                        # short lists (padding last)
+        fill[lists // 2] = k_in
+        for l in range(lists):
+            order = np.lexsort((rows[l], -sc[l].astype(np.float64)))
+            n = fill[l]
+            cand_s[l, j, :n], cand_i[l, j, :n] = sc[l][order][:n], rows[l][order][:n]
+    outs = []
+    for early in ("0", "1"):
+        monkeypatch.setenv("VQA_REDUCE_EARLY", early)
+        out_s, out_i = np.empty((b, k_out), np.float32), np.empty((b, k_out), np.int64)
+        ok(emu, emu.emu_reduce_u32(ptr(cand_s), ptr(cand_i), lists, b, k_in, k_out, 0, 1, 1, None, ptr(out_s), ptr(out_i)))
+        outs.append((out_s, out_i))
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    for j in range(b):
+        s_, i_ = cand_s[:, j].ravel(), cand_i[:, j].ravel().astype(np.int64)
+        s_, i_ = s_[i_ != 0xFFFFFFFF], i_[i_ != 0xFFFFFFFF]
+        order = np.lexsort((i_, -s_.astype(np.float64)))[:k_out]
+        assert outs[1][1][j, :len(order)].tolist() == i_[order].tolist()
+        assert np.all(outs[1][1][j, len(order):] == -1)
+
+
 def test_emulated_peer_memory_exchange_and_flag_waiting_merge(emu):
     """ShardedFlat(exchange="p2p") on one host: every 'rank' pushes its packed [scores | ids] block into its slot
     of every peer's gather buffer and publishes the epoch; each rank's merge kernel acquires the flags and merges

@@ -12,6 +12,10 @@ echo "== headline kernel, 8-GPU shard size (1.25 M rows) and full size: tourname
 for TB in 0 1; do run ROWS=1250000 K=10 MODE=tensor BATCHES=1,8,16,32 ITERS=50 VQA_MMA_TB=$TB; done
 for TB in 0 1; do run ROWS=10000000 K=10 MODE=tensor BATCHES=1,32 ITERS=10 VQA_MMA_TB=$TB; done
 
+echo "== same, with the early-exit reduce (and both)"
+run ROWS=1250000 K=10 MODE=tensor BATCHES=1,8,16,32 ITERS=50 VQA_REDUCE_EARLY=1
+run ROWS=1250000 K=10 MODE=tensor BATCHES=1,8,16,32 ITERS=50 VQA_REDUCE_EARLY=1 VQA_MMA_TB=1
+
 echo "== top-100, 4M x 768 bf16: list-insertion reduce vs radix select (default kernel family = TS hi/lo heaps)"
 for SEL in 0 1; do run ROWS=4000000 K=100 MODE=fast BATCHES=8,64 ITERS=10 VQA_REDUCE_SELECT=$SEL; done
 

@@ -28,6 +28,11 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
                                    const WaitFlags *wf = nullptr, unsigned long long *slot_reset = nullptr) {
     ReduceParams<IdT> p;
     p.slot_reset = k_out <= 32 ? slot_reset : nullptr;
+    {
+        const char *ee = std::getenv("VQA_REDUCE_EARLY");  // opt-in until timed on a B200
+        // internal (u32 row id) lists only: the scans emit them sorted; the public merge API does not require it
+        p.early_exit = (sizeof(IdT) == 4 && ee != nullptr && std::atoi(ee) != 0) ? 1 : 0;
+    }
     p.wait_flags = wf ? wf->flags : nullptr;
     p.wait_n = wf ? wf->n : 0;
     p.wait_epoch = wf ? wf->epoch : 0;

@@ -248,6 +248,10 @@ struct ReduceParams {
     long long *out_i;
     unsigned long long *tau_g_reset;  // [n_queries] shared-threshold slots to clear for the next search, or nullptr
     unsigned long long *slot_reset;   // [n_queries][32] tournament slots of the TB scan variants to clear, or nullptr
+    // Opt-in (VQA_REDUCE_EARLY=1), k_out <= 32 kernel: every candidate list is sorted best-first, and the lists are
+    // visited entry-major, so once ceil(n_lists / 32) consecutive chunks -- a window that holds one entry of EVERY
+    // list -- offered nothing that beats the running k-th best, no later entry of any list can: stop reading.
+    int early_exit;
     // Exact re-scoring of the merged candidates (screen-then-rescore): the scan ranked documents with
     // storage-precision queries; the k_out survivors get their exact fp32 dot product (fp32 query x
     // stored row) here, are re-sorted, and the best k_final are written.  rs_rows == nullptr: off.
@@ -340,7 +344,10 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
     const float *qs = p.cand_s + (long long)q * p.query_stride;
     const IdT *qi = p.cand_i + (long long)q * p.query_stride;
     constexpr int PF = 8;  // chunks whose (independent) loads are issued together: hides the L2 latency
-    for (long long base0 = 0; base0 < total; base0 += 32 * PF) {
+    const int quiet_need = (n_eff + 31) / 32;
+    int quiet = 0;       // consecutive chunks without a passing candidate (warp-uniform)
+    bool stop = false;
+    for (long long base0 = 0; base0 < total && !stop; base0 += 32 * PF) {
       float sv[PF];
       IdT iv[PF];
 #pragma unroll
@@ -363,7 +370,14 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
         bool valid = id != invalid_id<IdT>();
         if constexpr (sizeof(IdT) == 8) valid = valid && id >= 0;
         const bool pass = valid && s >= tau;
-        if (__ballot_sync(kFullMask, pass) == 0) continue;
+        if (__ballot_sync(kFullMask, pass) == 0) {
+            if (p.early_exit && ++quiet >= quiet_need) {
+                stop = true;
+                break;
+            }
+            continue;
+        }
+        quiet = 0;
         float cs = pass ? s : neg_inf();
         IdT ci = pass ? id : invalid_id<IdT>();
 #pragma unroll
