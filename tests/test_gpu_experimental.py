@@ -5,6 +5,7 @@ not yet been run or timed on a B200, so the default routing does not use them:
     (ts.cuh, QS variants): dim <= 1024, more accumulator stages at dim 768
   * VQA_MMA_TB=1 -- tournament bound in the smem-resident tcgen05 kernel (mma.cuh, TB variants): every list publishes
     its best score into slot (list % k); the minimum of a query's k slots is shared as a threshold
+  * VQA_REDUCE_EARLY=1 -- early exit in the k <= 32 candidate reduce
 Skipped unless VQA_EXPERIMENTAL=1 (tools/r2_experiments.sh sets it): a kernel that has never met the hardware
 must not be able to take the round-end `pytest -m gpu` run down with it.  Same bars as tests/test_gpu_search.py."""
 import os
@@ -152,3 +153,17 @@ def test_tournament_bound_under_graph_replay(monkeypatch):
         monkeypatch.setenv("VQA_MMA_TB", "1")
         torch.cuda.synchronize()
         assert torch.equal(out_i, ref_i) and torch.equal(out_s, ref_s)
+
+
+@pytest.mark.parametrize("storage,mode,n,d,b,k", [("bf16", "tensor", 300000, 768, 32, 10), ("fp16", "ts", 100000, 768, 100, 10),
+                                                  ("fp32", "verify", 60000, 384, 7, 32), ("bf16", "stream", 5000, 200, 3, 5)])
+def test_early_exit_reduce_is_exact(monkeypatch, storage, mode, n, d, b, k):
+    rng = np.random.default_rng(n + b)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    monkeypatch.setenv("VQA_REDUCE_EARLY", "0")
+    s0, i0, _ = gpu_search(docs, q, k, mode, storage)
+    monkeypatch.setenv("VQA_REDUCE_EARLY", "1")
+    s1, i1, _ = gpu_search(docs, q, k, mode, storage)
+    assert np.array_equal(i0, i1) and np.array_equal(s0.view(np.int32), s1.view(np.int32))
