@@ -145,6 +145,15 @@ VQA_API int vqa_search_host(const vqa_index_t *h, const float *queries_host, int
                             int32_t k, int32_t mode, float *out_scores_host,
                             int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
                             void *stream);
+/* The same three copies and launches WITHOUT the final synchronisation: the call returns as soon as the
+ * work is enqueued, and the host buffers (which must be pinned for the copies to be asynchronous) hold the
+ * result once `stream` -- or an event recorded on it after the call -- has completed.  Lets a serving loop
+ * overlap its own post-processing (id -> passage fetch) and the next batch's enqueue with the search; each
+ * in-flight call needs its own staging and output buffers. */
+VQA_API int vqa_search_host_async(const vqa_index_t *h, const float *queries_host, int32_t n_queries,
+                                  int32_t k, int32_t mode, float *out_scores_host,
+                                  int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
+                                  void *stream);
 
 /*
  * Merge `n_lists` candidate lists per query (the row shards' results after the

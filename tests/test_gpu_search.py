@@ -207,6 +207,24 @@ def test_search_host_matches_device_call():
     assert np.array_equal(hi.numpy(), i.cpu().numpy()) and np.array_equal(hs.numpy(), s.cpu().numpy())
 
 
+def test_search_host_async_two_batches_in_flight():
+    """vqa_search_host_async: same copies and launches without the final sync; two calls in flight on one stream
+    with their own buffer slots, results valid once each call's event has completed."""
+    rng = np.random.default_rng(15)
+    docs = unit_rows(rng, 30000, 768)
+    shard = ops.FlatShard(torch.from_numpy(docs).to(DEV).to(torch.bfloat16))
+    qa, qb = (torch.from_numpy(unit_rows(rng, 32, 768)).pin_memory() for _ in range(2))
+    want = [tuple(t.clone() for t in shard.search_host(q, 10, "fast")) for q in (qa, qb)]
+    sa, ia, ea = shard.search_host_async(qa, 10, "fast", slot=0)
+    sb, ib, eb = shard.search_host_async(qb, 10, "fast", slot=1)
+    ea.synchronize()
+    assert torch.equal(ia, want[0][1]) and torch.equal(sa, want[0][0])
+    eb.synchronize()
+    assert torch.equal(ib, want[1][1]) and torch.equal(sb, want[1][0])
+    with pytest.raises(ValueError):
+        shard.search_host_async(torch.from_numpy(unit_rows(rng, 4, 768)), 10)      # not pinned
+
+
 def test_cuda_graph_capture_of_search():
     rng = np.random.default_rng(6)
     docs, q = unit_rows(rng, 20000, 768), unit_rows(rng, 32, 768)

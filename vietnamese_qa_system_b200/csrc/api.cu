@@ -718,9 +718,27 @@ int vqa_search_host_staging_bytes(const vqa_index_t *h, int32_t n_queries, int32
     return VQA_OK;
 }
 
+static int search_host_impl(const vqa_index_t *h, const float *queries_host, int32_t n_queries, int32_t k, int32_t mode,
+                            float *out_scores_host, int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
+                            void *stream, bool sync);
+
 int vqa_search_host(const vqa_index_t *h, const float *queries_host, int32_t n_queries, int32_t k, int32_t mode,
                     float *out_scores_host, int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
                     void *stream) {
+    return search_host_impl(h, queries_host, n_queries, k, mode, out_scores_host, out_ids_host, staging_dev,
+                            staging_bytes, stream, true);
+}
+
+int vqa_search_host_async(const vqa_index_t *h, const float *queries_host, int32_t n_queries, int32_t k, int32_t mode,
+                          float *out_scores_host, int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
+                          void *stream) {
+    return search_host_impl(h, queries_host, n_queries, k, mode, out_scores_host, out_ids_host, staging_dev,
+                            staging_bytes, stream, false);
+}
+
+static int search_host_impl(const vqa_index_t *h, const float *queries_host, int32_t n_queries, int32_t k, int32_t mode,
+                            float *out_scores_host, int64_t *out_ids_host, void *staging_dev, size_t staging_bytes,
+                            void *stream, bool sync) {
     size_t need = 0;
     int rc = vqa_search_host_staging_bytes(h, n_queries, k, mode, &need);
     if (rc) return rc;
@@ -745,7 +763,7 @@ int vqa_search_host(const vqa_index_t *h, const float *queries_host, int32_t n_q
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_scores_host, os_dev, (size_t)n_queries * k * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(out_ids_host, oi_dev, (size_t)n_queries * k * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (sync) CUDA_TRY(cudaStreamSynchronize(st));
     return VQA_OK;
 }
 

@@ -140,6 +140,36 @@ class FlatShard:
                                         ctypes.c_void_p(_stream(self.device))))
         return hs, hi
 
+    def search_host_async(self, queries_host: torch.Tensor, k: int, mode="fast", slot: int = 0):
+        """``vqa_search_host_async``: enqueue H2D + search + D2H on the current stream and return at once.
+        Returns ``(scores, ids, event)`` -- pinned host tensors that hold the result once ``event`` (recorded
+        after the copies) has completed.  ``slot`` selects one of several independent staging / output buffer
+        sets so that calls can be in flight together (a serving loop alternates slot 0 / 1).  ``queries_host``
+        must be pinned and must not be modified until the event has completed."""
+        if queries_host.is_cuda or queries_host.dtype != torch.float32 or not queries_host.is_contiguous():
+            raise ValueError("queries_host must be a contiguous float32 CPU tensor")
+        if not queries_host.is_pinned():
+            raise ValueError("queries_host must be pinned (page-locked) for an asynchronous copy")
+        b = int(queries_host.shape[0])
+        m = mode_id(mode)
+        key = ("host_async", b, k, int(slot))
+        st = self._ws.get(key)
+        if st is None:
+            need = ctypes.c_size_t()
+            N.check(N.lib().vqa_search_host_staging_bytes(self._h, b, k, m, ctypes.byref(need)))
+            st = (torch.empty(need.value, dtype=torch.uint8, device=self.device),
+                  torch.empty((b, k), dtype=torch.float32).pin_memory(),
+                  torch.empty((b, k), dtype=torch.int64).pin_memory())
+            self._ws[key] = st
+        staging, hs, hi = st
+        N.check(N.lib().vqa_search_host_async(self._h, ctypes.c_void_p(queries_host.data_ptr()), b, k, m,
+                                              ctypes.c_void_p(hs.data_ptr()), ctypes.c_void_p(hi.data_ptr()),
+                                              ctypes.c_void_p(staging.data_ptr()), staging.numel(),
+                                              ctypes.c_void_p(_stream(self.device))))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return hs, hi, ev
+
 
 def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int):
     """K4: cand_* [lists, B, k_in] (float32 / int64, CUDA) -> (scores [B,k], ids [B,k])."""
