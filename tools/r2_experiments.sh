@@ -41,5 +41,9 @@ for KS in 0 2 4 6; do
   run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256,512 ITERS=5 VQA_TS_QS=1 VQA_TS_KS=$KS
 done
 
+echo "== end-to-end with host buffers: synchronous calls vs two batches in flight"
+ROWS=10000000 BATCH=32 timeout 600 python tools/e2e_pipeline_probe.py 2>&1 | tail -n 1
+ROWS=1250000 BATCH=32 STEPS=1000 timeout 600 python tools/e2e_pipeline_probe.py 2>&1 | tail -n 1
+
 echo "== regression check of the default path: the headline bench line"
 timeout 900 python bench.py --steps 50 --warmup 5 2>&1 | tail -n 1 | cut -c1-600
