@@ -247,12 +247,14 @@ def test_emulated_merge_normalize_agree(emu):
     assert acc.tolist() == [int(oracle.agree(a, x_, b_, y)) for a, x_, b_, y in zip(ida, sa, idb, sb)] == [1, 1, 0, 0]
 
 
+@pytest.mark.parametrize("select", ["0", "1"])
 @pytest.mark.parametrize("kind", ["bf16", "f16"])
-def test_emulated_reduce_with_exact_rescoring(emu, kind):
+def test_emulated_reduce_with_exact_rescoring(emu, monkeypatch, kind, select):
     """The screen-then-rescore stage behind the large-batch tensor-core scan: the 16 best candidates by their
     (storage-precision) screen scores are re-scored exactly in fp32 against the stored rows, re-sorted and the
     best 10 emitted -- so a true neighbour that the screen ranked 11th..16th is recovered."""
     emu.emu_reduce_rescore.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]
+    monkeypatch.setenv("VQA_REDUCE_SELECT", select)   # "1": the CTA-per-query radix-select kernel re-scores (opt-in)
     rng = np.random.default_rng(8)
     n, dim, b, lists, k_in, k_out, k_final = 400, 768, 3, 5, 16, 16, 10
     raw, vals = _to_storage(_unit(rng, n, dim), kind)

@@ -167,3 +167,21 @@ def test_early_exit_reduce_is_exact(monkeypatch, storage, mode, n, d, b, k):
     monkeypatch.setenv("VQA_REDUCE_EARLY", "1")
     s1, i1, _ = gpu_search(docs, q, k, mode, storage)
     assert np.array_equal(i0, i1) and np.array_equal(s0.view(np.int32), s1.view(np.int32))
+
+
+@pytest.mark.parametrize("storage,n,d,b,k", [("bf16", 200000, 768, 128, 10), ("fp16", 50000, 384, 40, 5),
+                                             ("bf16", 30000, 768, 300, 10)])
+def test_screen_mode_rescoring_through_the_select_kernel(monkeypatch, storage, n, d, b, k):
+    """VQA_REDUCE_SELECT=1 also takes over the k <= 32 screen-then-rescore reduce of the (default) TMEM-resident-query
+    kernel: a CTA per query, coalesced row reads, one warp per candidate.  Same bars; ids equal the warp-per-query
+    reduce's, scores to fp32 rounding of a different summation order."""
+    rng = np.random.default_rng(n + b)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    monkeypatch.setenv("VQA_REDUCE_SELECT", "0")
+    s0, i0, _ = gpu_search(docs, q, k, "ts", storage)
+    monkeypatch.setenv("VQA_REDUCE_SELECT", "1")
+    s1, i1 = _check(docs, q, k, "ts", storage)
+    assert recall(i1, i0) >= 0.999 and np.abs(s1 - s0).max() <= 5e-7
+    assert i1[0, :2].tolist() == [3, n // 2]

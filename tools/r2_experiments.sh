@@ -35,6 +35,10 @@ echo "== dim 1024 bf16 top-10, B = 32..256 (default: smem-resident kernel with m
 run ROWS=8000000 DIM=1024 K=10 MODE=fast BATCHES=32,64,128,256 ITERS=5
 run ROWS=8000000 DIM=1024 K=10 MODE=fast BATCHES=32,64,128,256 ITERS=5 VQA_TS_QS=1
 
+echo "== large batches: warp-per-query re-scoring reduce (63 us per 128 queries) vs CTA-per-query select kernel; full size and 8-GPU shard"
+for SEL in 0 1; do run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256 ITERS=5 VQA_REDUCE_SELECT=$SEL; done
+for SEL in 0 1; do run ROWS=1250000 K=10 MODE=fast BATCHES=64,128,256 ITERS=20 VQA_REDUCE_SELECT=$SEL; done
+
 echo "== 10M x 768 bf16 top-10, B = 64..512: accumulator stages (ks = 0: 2 stages, 2: 3, 4: 4, 6: 5)"
 run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256,512 ITERS=5
 for KS in 0 2 4 6; do

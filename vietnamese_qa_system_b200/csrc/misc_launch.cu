@@ -67,19 +67,17 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (k_out <= 32) {
-        cfg.gridDim = dim3((n_queries + kReduceWarpsPerCta - 1) / kReduceWarpsPerCta);
-        cfg.blockDim = dim3(kReduceWarpsPerCta * 32);
-        cfg.dynamicSmemBytes = 0;
-        return cudaLaunchKernelEx(&cfg, reduce_topk_warp_kernel<IdT>, p);
-    }
     if constexpr (sizeof(IdT) == 4) {
         // radix-select reduce (scan.cuh): opt-in until it has been timed on a B200 (VQA_REDUCE_SELECT=1);
-        // needs every candidate of a query in shared memory at once and no peer flags to wait for
+        // needs every candidate of a query in shared memory at once and no peer flags to wait for.
+        // Taken for k_out > 32, and for the screen-then-rescore reduce of any k_out: one CTA per query re-scores
+        // the survivors with coalesced row reads, one warp per candidate (the warp-per-query kernel reads 32 cold
+        // rows with one lane each: 63 us per 128 queries on the B200).
         const long long n_cand = (long long)(n_lists / (list_mod > 1 ? list_mod : 1)) * k_in;
         const size_t smem = select_smem_bytes(n_cand);
         const char *env = std::getenv("VQA_REDUCE_SELECT");
-        if (env != nullptr && std::atoi(env) != 0 && wf == nullptr && smem <= kSelectSmemLimit) {
+        if (env != nullptr && std::atoi(env) != 0 && wf == nullptr && smem <= kSelectSmemLimit &&
+            (k_out > 32 || (rs != nullptr && p.slot_reset == nullptr))) {
             cudaError_t e = cudaFuncSetAttribute(reduce_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             cfg.gridDim = dim3(n_queries);
@@ -87,6 +85,12 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
             cfg.dynamicSmemBytes = smem;
             return cudaLaunchKernelEx(&cfg, reduce_select_kernel, p);
         }
+    }
+    if (k_out <= 32) {
+        cfg.gridDim = dim3((n_queries + kReduceWarpsPerCta - 1) / kReduceWarpsPerCta);
+        cfg.blockDim = dim3(kReduceWarpsPerCta * 32);
+        cfg.dynamicSmemBytes = 0;
+        return cudaLaunchKernelEx(&cfg, reduce_topk_warp_kernel<IdT>, p);
     }
     if (rs != nullptr) return cudaErrorInvalidValue;  // only the radix-select reduce re-scores beyond 32 candidates
     cfg.gridDim = dim3(n_queries);
