@@ -674,35 +674,55 @@ static __global__ void __launch_bounds__(kSelThreads) reduce_select_kernel(const
     if (tid < kMaxK && tid >= n_sel) sel[tid] = 0;
     __syncthreads();
 
-    // 4. screen mode: the survivors' exact fp32 scores (fp32 query x stored row), one warp per candidate
+    // 4. screen mode: the survivors' exact fp32 scores (fp32 query x stored row): one warp per candidate, lanes
+    //    stride over the row's 16-byte chunks (coalesced), four candidates per round so that their cold row
+    //    reads are in flight together
     if (p.rs_rows != nullptr) {
         const float *qv = p.rs_q + (long long)q * p.rs_q_stride;
         const int nch = p.rs_dim / 8;
-        for (int e = warp; e < n_sel; e += kSelWarps) {
-            const unsigned long long key = sel[e];
-            const uint32_t row = 0x7fffffffu - (uint32_t)((key >> 1) & 0x7fffffffull);
-            const unsigned char *rp = p.rs_rows + (long long)row * p.rs_stride;
-            float a0 = 0.f, a1 = 0.f;
+        constexpr int RC = 4;
+        for (int e0 = warp; e0 < n_sel; e0 += kSelWarps * RC) {
+            const unsigned char *rp[RC];
+            uint32_t rowid[RC];
+            bool on[RC];
+            float a0[RC], a1[RC];
+#pragma unroll
+            for (int u = 0; u < RC; ++u) {
+                const int e = e0 + u * kSelWarps;
+                on[u] = e < n_sel;
+                const unsigned long long key = on[u] ? sel[e] : 0ull;
+                rowid[u] = 0x7fffffffu - (uint32_t)((key >> 1) & 0x7fffffffull);
+                rp[u] = p.rs_rows + (long long)(on[u] ? rowid[u] : 0u) * p.rs_stride;
+                a0[u] = a1[u] = 0.f;
+            }
             for (int c = lane; c < nch; c += 32) {
-                const uint4 w = ldg_stream(rp + c * 16);
+                uint4 w[RC];
+#pragma unroll
+                for (int u = 0; u < RC; ++u) w[u] = on[u] ? ldg_stream(rp[u] + c * 16) : make_uint4(0, 0, 0, 0);
                 const float4 q0 = *reinterpret_cast<const float4 *>(qv + c * 8);
                 const float4 q1 = *reinterpret_cast<const float4 *>(qv + c * 8 + 4);
-                float x[8];
-                if (p.rs_bf16) Elem<__nv_bfloat16>::unpack(w, x);
-                else Elem<__half>::unpack(w, x);
-                a0 = fmaf(q0.x, x[0], a0);
-                a1 = fmaf(q0.y, x[1], a1);
-                a0 = fmaf(q0.z, x[2], a0);
-                a1 = fmaf(q0.w, x[3], a1);
-                a0 = fmaf(q1.x, x[4], a0);
-                a1 = fmaf(q1.y, x[5], a1);
-                a0 = fmaf(q1.z, x[6], a0);
-                a1 = fmaf(q1.w, x[7], a1);
-            }
-            float exact = a0 + a1;
 #pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) exact += __shfl_xor_sync(kFullMask, exact, m);
-            if (lane == 0) sel[e] = select_key(exact, row);
+                for (int u = 0; u < RC; ++u) {
+                    float x[8];
+                    if (p.rs_bf16) Elem<__nv_bfloat16>::unpack(w[u], x);
+                    else Elem<__half>::unpack(w[u], x);
+                    a0[u] = fmaf(q0.x, x[0], a0[u]);
+                    a1[u] = fmaf(q0.y, x[1], a1[u]);
+                    a0[u] = fmaf(q0.z, x[2], a0[u]);
+                    a1[u] = fmaf(q0.w, x[3], a1[u]);
+                    a0[u] = fmaf(q1.x, x[4], a0[u]);
+                    a1[u] = fmaf(q1.y, x[5], a1[u]);
+                    a0[u] = fmaf(q1.z, x[6], a0[u]);
+                    a1[u] = fmaf(q1.w, x[7], a1[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RC; ++u) {
+                float exact = a0[u] + a1[u];
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) exact += __shfl_xor_sync(kFullMask, exact, m);
+                if (lane == 0 && on[u]) sel[e0 + u * kSelWarps] = select_key(exact, rowid[u]);
+            }
         }
         __syncthreads();
     }
