@@ -6,6 +6,7 @@ not yet been run or timed on a B200, so the default routing does not use them:
   * VQA_MMA_TB=1 -- tournament bound in the smem-resident tcgen05 kernel (mma.cuh, TB variants): every list publishes
     its best score into slot (list % k); the minimum of a query's k slots is shared as a threshold
   * VQA_REDUCE_EARLY=1 -- early exit in the k <= 32 candidate reduce
+  * VQA_PDL_CHAIN=1 -- consecutive scan launches of one search overlap the previous reduce (PDL without a wait)
 Skipped unless VQA_EXPERIMENTAL=1 (tools/r2_experiments.sh sets it): a kernel that has never met the hardware
 must not be able to take the round-end `pytest -m gpu` run down with it.  Same bars as tests/test_gpu_search.py."""
 import os
@@ -185,3 +186,17 @@ def test_screen_mode_rescoring_through_the_select_kernel(monkeypatch, storage, n
     s1, i1 = _check(docs, q, k, "ts", storage)
     assert recall(i1, i0) >= 0.999 and np.abs(s1 - s0).max() <= 5e-7
     assert i1[0, :2].tolist() == [3, n // 2]
+
+
+@pytest.mark.parametrize("mode,b", [("ts", 600), ("tensor", 300), ("fast", 1024)])
+def test_pdl_chained_scan_launches_give_the_same_results(monkeypatch, mode, b):
+    """VQA_PDL_CHAIN=1: the 2nd, 3rd ... scan launch of one search is a programmatic dependent launch without a wait,
+    so it overlaps the previous launch's reduce; nothing it reads is written by that reduce."""
+    rng = np.random.default_rng(b)
+    docs, q = unit_rows(rng, 150000, 768), unit_rows(rng, b, 768)
+    monkeypatch.setenv("VQA_PDL_CHAIN", "0")
+    s0, i0, _ = gpu_search(docs, q, 10, mode, "bf16")
+    monkeypatch.setenv("VQA_PDL_CHAIN", "1")
+    for _ in range(3):
+        s1, i1, _ = gpu_search(docs, q, 10, mode, "bf16")
+        assert np.array_equal(i0, i1) and np.array_equal(s0.view(np.int32), s1.view(np.int32))

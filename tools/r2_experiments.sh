@@ -39,6 +39,11 @@ echo "== large batches: warp-per-query re-scoring reduce (63 us per 128 queries)
 for SEL in 0 1; do run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256 ITERS=5 VQA_REDUCE_SELECT=$SEL; done
 for SEL in 0 1; do run ROWS=1250000 K=10 MODE=fast BATCHES=64,128,256 ITERS=20 VQA_REDUCE_SELECT=$SEL; done
 
+echo "== BASELINE configs[1]: 1M x 768, B = 1024 (4 launches of 256): scan i+1 overlapping reduce i; + select kernel"
+run ROWS=1000000 K=10 MODE=fast BATCHES=512,1024 ITERS=20
+run ROWS=1000000 K=10 MODE=fast BATCHES=512,1024 ITERS=20 VQA_PDL_CHAIN=1
+run ROWS=1000000 K=10 MODE=fast BATCHES=512,1024 ITERS=20 VQA_PDL_CHAIN=1 VQA_REDUCE_SELECT=1
+
 echo "== 10M x 768 bf16 top-10, B = 64..512: accumulator stages (ks = 0: 2 stages, 2: 3, 4: 4, 6: 5)"
 run ROWS=10000000 K=10 MODE=fast BATCHES=64,128,256,512 ITERS=5
 for KS in 0 2 4 6; do

@@ -193,6 +193,8 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
 // scan.cuh radix-select reduce).  Off by default: the default routing is exactly what round 1 measured.
 bool ts_qs_enabled() { return env_int("VQA_TS_QS", 0) != 0; }
 bool reduce_select_enabled() { return env_int("VQA_REDUCE_SELECT", 0) != 0; }
+// 2nd+ scan launch of one search overlaps the previous launch's reduce (programmatic dependent launch without a wait)
+bool pdl_chain_enabled() { return env_int("VQA_PDL_CHAIN", 0) != 0; }
 bool mma_tb_enabled() { return env_int("VQA_MMA_TB", 0) != 0; }  // tournament bound in the smem-resident kernel (mma.cuh)
 
 bool ts_eligible(const vqa_index *h) {
@@ -555,6 +557,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.a_fp16 = pl.ts_afp16;
             a.qs = pl.ts_qs;
             a.ks = pl.ts_ks;
+            a.pdl = (l0 > 0 && pdl_chain_enabled()) ? 1 : 0;
             a.stages = pl.stages;
             a.kps = pl.kps;
             a.grid = (int)streams * g;
@@ -646,6 +649,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             // opt-in tournament bound: register-list path only (<= 32 queries per CTA, list length <= 32)
             const bool tb = mma_tb_enabled() && pl.pass_nq <= 32 && kscan <= 32;
             a.slot_g = tb ? slot_g + (long long)l0 * 32 : nullptr;
+            a.pdl = (l0 > 0 && pdl_chain_enabled()) ? 1 : 0;
             cudaError_t e = vqa::launch_mma(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
             vqa::Rescore rs;

@@ -48,6 +48,7 @@ struct MmaLaunch {
     unsigned long long *tau_g;  // [nq] shared thresholds for this pass (or nullptr)
     uint32_t epoch;
     unsigned long long *slot_g = nullptr;  // opt-in TB variants: [nq][32] tournament slots (see MmaParams), else nullptr
+    int pdl = 0;  // opt-in: launch with programmatic stream serialization (2nd+ scan of one search, see mma_launch.cu)
 };
 
 struct TsLaunch {
@@ -71,6 +72,7 @@ struct TsLaunch {
     long long cand_stride;
     unsigned long long *tau_g;
     uint32_t epoch;
+    int pdl = 0;  // opt-in: launch with programmatic stream serialization (2nd+ scan of one search)
     int qs = 0;   // 1: the QS kernel variant (part of the query block in shared memory); opt-in, see ts.cuh
     int ks = 0;   // QS: 64-column blocks of the query block kept in shared memory
 };

@@ -32,6 +32,8 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
         const char *ee = std::getenv("VQA_REDUCE_EARLY");  // opt-in until timed on a B200
         // internal (u32 row id) lists only: the scans emit them sorted; the public merge API does not require it
         p.early_exit = (sizeof(IdT) == 4 && ee != nullptr && std::atoi(ee) != 0) ? 1 : 0;
+        const char *pc = std::getenv("VQA_PDL_CHAIN");
+        p.trigger_early = (sizeof(IdT) == 4 && pc != nullptr && std::atoi(pc) != 0) ? 1 : 0;
     }
     p.wait_flags = wf ? wf->flags : nullptr;
     p.wait_n = wf ? wf->n : 0;

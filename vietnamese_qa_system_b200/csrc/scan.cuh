@@ -252,6 +252,10 @@ struct ReduceParams {
     // visited entry-major, so once ceil(n_lists / 32) consecutive chunks -- a window that holds one entry of EVERY
     // list -- offered nothing that beats the running k-th best, no later entry of any list can: stop reading.
     int early_exit;
+    // Opt-in (VQA_PDL_CHAIN=1): release programmatic dependents at once.  The only dependent launched that way
+    // without its own griddepcontrol.wait is the NEXT scan of the same search, which reads nothing this kernel
+    // writes -- it may then overlap this reduce instead of waiting for it.
+    int trigger_early;
     // Exact re-scoring of the merged candidates (screen-then-rescore): the scan ranked documents with
     // storage-precision queries; the k_out survivors get their exact fp32 dot product (fp32 query x
     // stored row) here, are re-sorted, and the best k_final are written.  rs_rows == nullptr: off.
@@ -323,6 +327,7 @@ template <typename IdT>
 __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kernel(const ReduceParams<IdT> p) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * kReduceWarpsPerCta + (threadIdx.x >> 5);
+    if (p.trigger_early) grid_launch_dependents();
     grid_dependency_wait();
     if (q >= p.n_queries) return;
     if (p.wait_flags != nullptr) {
@@ -474,6 +479,7 @@ __global__ void __launch_bounds__(kReduceBigWarps * 32) reduce_topk_kernel(const
     const int q = blockIdx.x;
     ListView<IdT> L = list_carve<IdT>(smem, kReduceBigWarps, p.k_out);
     list_init(L, kReduceBigWarps, tid, kReduceBigWarps * 32);
+    if (p.trigger_early) grid_launch_dependents();
     __syncthreads();
     grid_dependency_wait();
     const int lmod = p.list_mod > 1 ? p.list_mod : 1;
@@ -579,6 +585,7 @@ static __global__ void __launch_bounds__(kSelThreads) reduce_select_kernel(const
     uint32_t *hist = reinterpret_cast<uint32_t *>(sel + kMaxK);
     uint32_t *ctl = hist + 256;  // 0: valid candidates, 1: digit, 2: still wanted, 3: done, 4: selected
     if (tid < 16) ctl[tid] = 0;
+    if (p.trigger_early) grid_launch_dependents();
     __syncthreads();
     grid_dependency_wait();
 

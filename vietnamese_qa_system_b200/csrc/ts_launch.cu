@@ -32,22 +32,34 @@ static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     auto kern = ts_topk_kernel<BF16, KL, QS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (!a.multicast) {
+    if (!a.multicast && !a.pdl) {
         kern<<<a.grid, kMmaThreads, smem, st>>>(*a.tmap, p);
         return cudaGetLastError();
     }
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)a.n_groups;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    // cluster launch (TMA multicast) and / or programmatic dependent launch: a.pdl marks the 2nd, 3rd ... scan of
+    // ONE search, which depends on nothing the previous launch's reduce kernel produces, so it may start while
+    // that reduce is still running (the kernel never executes griddepcontrol.wait)
+    cudaLaunchAttribute attr[2];
+    unsigned n_attr = 0;
+    if (a.multicast) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = (unsigned)a.n_groups;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
+    }
+    if (a.pdl) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.grid);
     cfg.blockDim = dim3(kMmaThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = n_attr;
     return cudaLaunchKernelEx(&cfg, kern, *a.tmap, p);
 }
 
