@@ -18,15 +18,15 @@ c = ctypes
 _vp, _i32, _i64, _dbl = c.c_void_p, c.c_int32, c.c_int64, c.c_double
 
 
-@pytest.fixture(scope="module", params=["thread order", "reverse order", "random interleaving"])
-def emu(request):
-    """Every test runs under three fiber schedules: kernels whose result depended on which thread reaches a
-    barrier-free region first (a missing __syncthreads, an unordered shared-memory update) would differ."""
+_SCHEDULES = {"thread order": 0, "reverse order": 1, "random interleaving": 2}
+
+
+@pytest.fixture(scope="module")
+def _emu_lib():
     if not emu_build.toolchain_available():
         pytest.skip("g++ or the CUDA headers are not available: the kernel emulator cannot be built here")
     L = ctypes.CDLL(emu_build.build())
     L.emu_set_schedule.argtypes = [_i32, c.c_uint64]
-    L.emu_set_schedule({"thread order": 0, "reverse order": 1, "random interleaving": 2}[request.param], 12345)
     L.emu_last_error.restype = c.c_char_p
     L.emu_sparse_search.argtypes = [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32,
                                     _vp, _vp]
@@ -34,6 +34,22 @@ def emu(request):
     L.emu_hybrid_fuse.argtypes = [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _dbl, _dbl, _i32, _vp, _vp]
     L.emu_pool_normalize.argtypes = [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
     return L
+
+
+@pytest.fixture(params=["thread order", "reverse order", "random interleaving"])
+def emu(request, _emu_lib):
+    """Every test runs under three fiber schedules: kernels whose result depended on which thread reaches a
+    barrier-free region first (a missing __syncthreads, an unordered shared-memory update) would differ."""
+    _emu_lib.emu_set_schedule(_SCHEDULES[request.param], 12345)
+    return _emu_lib
+
+
+@pytest.fixture(params=["thread order", "random interleaving"])
+def emu2(request, _emu_lib):
+    """The tensor-core kernel tests (the slowest on the emulator) run under two of the three schedules to keep the
+    CPU suite to a few minutes; tools/fuzz_emu.py and the CUDA-core kernel tests cover all three."""
+    _emu_lib.emu_set_schedule(_SCHEDULES[request.param], 12345)
+    return _emu_lib
 
 
 def ptr(a):
@@ -422,19 +438,19 @@ def _recall(got, want):
     ("bf16", 256, 900, 30, 10, 8, 32, 4, 2, 1),     # cluster of 2: each CTA multicasts half of every box
     ("f16", 128, 700, 40, 5, 16, 32, 3, 1, 1),      # cluster of 4 (3 chunks + an empty one), quarter-box slices
 ])
-def test_emulated_tcgen05_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, ncol, stages, kps, mc):
+def test_emulated_tcgen05_search_matches_the_oracle(emu2, kind, dim, n, b, k, sm, ncol, stages, kps, mc):
     """mma_topk_kernel (TMA producer / MMA issuer / TMEM epilogue with register top-k lists and GPU-wide
     thresholds) + the reduce, on the host models of mbarrier, TMA (128-byte swizzle; multicast across a cluster),
     tcgen05.mma / commit / ld and named barriers.  Bar of the GPU tests: recall against fp32 arithmetic on the stored rows, rank-wise scores
     within 1e-5 relative; here the ids are in fact identical, duplicates lower id first."""
-    emu.emu_search_tensor.argtypes = _MMA_ARGS
+    emu2.emu_search_tensor.argtypes = _MMA_ARGS
     rng = np.random.default_rng(dim + n + b)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
     docs[n // 2] = docs[3]
     q[0] = docs[3]
     raw, vals = _to_storage(docs, kind)
     out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-    ok(emu, emu.emu_search_tensor(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, ncol, stages, kps, mc,
+    ok(emu2, emu2.emu_search_tensor(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, ncol, stages, kps, mc,
                                   0, None, ptr(out_s), ptr(out_i)))
     want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
     assert _recall(out_i, want_i) >= 0.999
@@ -450,18 +466,18 @@ def test_emulated_tcgen05_search_matches_the_oracle(emu, kind, dim, n, b, k, sm,
     ("bf16", 128, 200, 10, 100, 2, 1, 4, 2, 0),     # k = 100: binary heaps in shared memory, 8-warp reduce
     ("bf16", 256, 600, 200, 10, 6, 0, 4, 2, 1),     # cluster of 2 with TMA multicast (the default for B > 128)
 ])
-def test_emulated_tmem_resident_query_search_matches_the_oracle(emu, kind, dim, n, b, k, sm, split, stages, kps, mc):
+def test_emulated_tmem_resident_query_search_matches_the_oracle(emu2, kind, dim, n, b, k, sm, split, stages, kps, mc):
     """ts_topk_kernel (query block written to tensor memory with tcgen05.st and used as the MMA's A operand,
     thread-per-query-row epilogue with register lists / append buffers / heaps) + the reduce with the exact
     re-scoring stage, on the host models.  Screen mode returns the exact fp32 scores (abs err ~1e-7)."""
-    emu.emu_search_ts.argtypes = _TS_ARGS
+    emu2.emu_search_ts.argtypes = _TS_ARGS
     rng = np.random.default_rng(dim + n + b + k)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
     docs[n // 2] = docs[3]
     q[0] = docs[3]
     raw, vals = _to_storage(docs, kind)
     out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-    ok(emu, emu.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps, mc,
+    ok(emu2, emu2.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps, mc,
                               0, 0, ptr(out_s), ptr(out_i)))
     want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
     assert _recall(out_i, want_i) >= 0.999
@@ -482,12 +498,12 @@ def test_emulated_tmem_resident_query_search_matches_the_oracle(emu, kind, dim, 
     ("bf16", 128, 200, 20, 10, 2, 0, 4, 2, 0, 2),    # every query block in shared memory (ks = dim / 64): nothing in TMEM
     ("f16", 832, 200, 10, 5, 2, 0, 4, 1, 0, 1),      # dim 832 = 13 blocks: ks = 1
 ])
-def test_emulated_query_block_split_between_tmem_and_smem(emu, monkeypatch, kind, dim, n, b, k, sm, split, stages, kps,
+def test_emulated_query_block_split_between_tmem_and_smem(emu2, monkeypatch, kind, dim, n, b, k, sm, split, stages, kps,
                                                          mc, ks):
     """ts_topk_kernel<.., QS = true> (opt-in, VQA_TS_QS=1): the last ks 64-column blocks of the query block are staged
     in shared memory (128-byte swizzle) and multiplied with the smem-A form of tcgen05.mma into the same accumulator
     as the TMEM-A blocks -- what makes dim 1024 fit.  Same bars as the all-TMEM kernel."""
-    emu.emu_search_ts.argtypes = _TS_ARGS
+    emu2.emu_search_ts.argtypes = _TS_ARGS
     monkeypatch.setenv("VQA_REDUCE_SELECT", "1")
     rng = np.random.default_rng(dim + n + b + k)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
@@ -495,7 +511,7 @@ def test_emulated_query_block_split_between_tmem_and_smem(emu, monkeypatch, kind
     q[0] = docs[3]
     raw, vals = _to_storage(docs, kind)
     out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-    ok(emu, emu.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps, mc,
+    ok(emu2, emu2.emu_search_ts(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, split, 6, stages, kps, mc,
                               1, ks, ptr(out_s), ptr(out_i)))
     want_s, want_i = oracle.search(vals, q, k, oracle.SEMANTIC, {"bf16": "bf16", "f16": "fp16"}[kind], first_id=100)
     assert _recall(out_i, want_i) >= 0.999
@@ -516,12 +532,12 @@ def test_emulated_query_block_split_between_tmem_and_smem(emu, monkeypatch, kind
     ("bf16", 64, 700, 3, 32, 6, 16, 4, 1, 0, "zeros"),         # k = 32 > number of lists (24): some slots never fill
     ("f16", 128, 900, 5, 1, 8, 16, 4, 2, 0, "stale"),          # k = 1: slot 0 is the running global maximum; stale-epoch slots
 ])
-def test_emulated_tournament_bound_leaves_results_unchanged(emu, kind, dim, n, b, k, sm, ncol, stages, kps, mc, init):
+def test_emulated_tournament_bound_leaves_results_unchanged(emu2, kind, dim, n, b, k, sm, ncol, stages, kps, mc, init):
     """mma_topk_kernel<.., TB = true> (opt-in, VQA_MMA_TB=1): every list publishes its best score into slot
     (list % k); the minimum over a query's k slots is a lower bound of the global k-th best (k distinct documents
     score at least that), shared through tau_g.  A valid bound cannot change the result: ids and score bits equal
     the run without it; the reduce clears the slots for the next search (graph replays reuse the epoch)."""
-    emu.emu_search_tensor.argtypes = _MMA_ARGS
+    emu2.emu_search_tensor.argtypes = _MMA_ARGS
     rng = np.random.default_rng(dim + n + b + k)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
     docs[n // 2] = docs[3]
@@ -529,9 +545,9 @@ def test_emulated_tournament_bound_leaves_results_unchanged(emu, kind, dim, n, b
     q[0] = docs[3]
     raw, vals = _to_storage(docs, kind)
     outs, events = [], []
-    emu.emu_events_read_reset.restype = c.c_longlong
+    emu2.emu_events_read_reset.restype = c.c_longlong
     for tb in (0, 1):
-        emu.emu_events_read_reset()
+        emu2.emu_events_read_reset()
         if init == "zeros":
             slots = np.zeros((b, 32), np.uint64)
         elif init == "garbage":
@@ -540,10 +556,10 @@ def test_emulated_tournament_bound_leaves_results_unchanged(emu, kind, dim, n, b
         else:
             slots = np.full((b, 32), (0 << 32) | 0xFFFFFFFF, np.uint64)  # epoch 0 with a huge score: must read as empty
         out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
-        ok(emu, emu.emu_search_tensor(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, ncol, stages, kps, mc,
+        ok(emu2, emu2.emu_search_tensor(ptr(raw), int(kind == "bf16"), n, dim, ptr(q), b, k, 100, sm, ncol, stages, kps, mc,
                                       tb, ptr(slots), ptr(out_s), ptr(out_i)))
         outs.append((out_s, out_i))
-        events.append(emu.emu_events_read_reset())
+        events.append(emu2.emu_events_read_reset())
         if tb:
             assert not slots.any()                                       # cleared by the reduce
     assert np.array_equal(outs[0][1], outs[1][1])
