@@ -54,5 +54,11 @@ echo "== end-to-end with host buffers: synchronous calls vs two batches in fligh
 ROWS=10000000 BATCH=32 timeout 600 python tools/e2e_pipeline_probe.py 2>&1 | tail -n 1
 ROWS=1250000 BATCH=32 STEPS=1000 timeout 600 python tools/e2e_pipeline_probe.py 2>&1 | tail -n 1
 
+echo "== hardware probe: semantics of tcgen05.mma.cta_group::2 (next step for the tensor-bound regime, DESIGN 8.3)"
+mkdir -p gpurun_out
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o gpurun_out/cta2_probe tools/cta2_probe.cu 2>&1 | grep -i error
+timeout 60 gpurun_out/cta2_probe 2>&1 | tail -n 12
+timeout 60 gpurun_out/cta2_probe --alloc-leader-only 2>&1 | tail -n 12
+
 echo "== regression check of the default path: the headline bench line"
 timeout 900 python bench.py --steps 50 --warmup 5 2>&1 | tail -n 1 | cut -c1-600
