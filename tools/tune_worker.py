@@ -19,27 +19,48 @@ for lo in range(0, n, 500000):
     x = ops.normalize_rows(torch.randn((m, d), generator=g, device=dev))
     rows[lo:lo + m] = x.to(dt)
 shard = ops.FlatShard(rows)
-res = {}
 iters = int(os.environ.get("ITERS", "20"))
-for b in [int(x) for x in os.environ.get("BATCHES", "8,32").split(",")]:
-    q = ops.normalize_rows(torch.randn((b, d), generator=g, device=dev))
-    mode = os.environ.get("MODE", "tensor")
-    for _ in range(3):
-        shard.search(q, k, mode)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        shard.search(q, k, mode)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    res[b] = {"ms": round(ms, 4), "GBps": round(n * d * rows.element_size() / ms / 1e6)}
-    if os.environ.get("CHECK"):  # recall@k and score error against the fp32 verify kernel on the same rows
-        s1, i1 = shard.search(q, k, mode)
-        s0, i0 = shard.search(q, k, "verify")
-        torch.cuda.synchronize()
-        a, r = i1.cpu().tolist(), i0.cpu().tolist()
-        res[b]["recall"] = round(sum(len(set(x) & set(y)) for x, y in zip(a, r)) / (len(r) * k), 5)
-        res[b]["max_rel_err"] = float(((s1 - s0).abs() / s0.abs().clamp_min(1e-3)).max())
-print(json.dumps(res))
+mode = os.environ.get("MODE", "tensor")
+batches = [int(x) for x in os.environ.get("BATCHES", "8,32").split(",")]
+queries = {b: ops.normalize_rows(torch.randn((b, d), generator=g, device=dev)) for b in batches}
+# VARIANTS="-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1,VQA_MMA_TB=1": several knob settings timed on ONE generated index
+# ("-" = the environment as given).  The library reads its knobs at call time.
+variants = [v for v in os.environ.get("VARIANTS", "-").split(";") if v]
+base_env = dict(os.environ)
+out = {}
+for var in variants:
+    os.environ.clear()
+    os.environ.update(base_env)
+    if var != "-":
+        for kv in var.split(","):
+            key, val = kv.split("=", 1)
+            os.environ[key] = val
+    shard._ws.clear()  # workspace size depends on VQA_TS_EXTRA
+    res = {}
+    try:
+        for b in batches:
+            q = queries[b]
+            for _ in range(3):
+                shard.search(q, k, mode)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                shard.search(q, k, mode)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            res[b] = {"ms": round(ms, 4), "GBps": round(n * d * rows.element_size() / ms / 1e6)}
+            if os.environ.get("CHECK"):  # recall@k and score error against the fp32 verify kernel on the same rows
+                s1, i1 = (t.clone() for t in shard.search(q, k, mode))
+                s0, i0 = shard.search(q, k, "verify")
+                torch.cuda.synchronize()
+                a, r = i1.cpu().tolist(), i0.cpu().tolist()
+                res[b]["recall"] = round(sum(len(set(x) & set(y)) for x, y in zip(a, r)) / (len(r) * k), 5)
+                res[b]["max_rel_err"] = float(((s1 - s0).abs() / s0.abs().clamp_min(1e-3)).max())
+    except Exception as exc:  # noqa: BLE001 - report and go on to the next variant
+        res["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    out[var] = res
+    if len(variants) > 1:
+        print(var, "->", json.dumps(res), flush=True)
+print(json.dumps(out if len(variants) > 1 else out[variants[0]]))
