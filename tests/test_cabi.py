@@ -191,3 +191,19 @@ def test_measured_kernels_are_unchanged():
     have = {v["sha256"]: k for k, v in cur.items()}
     for name, want in gold["kernels"].items():
         assert want["sha256"] in have, f"{name}: no kernel in the current build has the measured instruction stream"
+
+
+def test_documented_environment_knobs_exist_in_the_library():
+    """INTEGRATION.md section 6 lists the VQA_* knobs; each must be a string the built library actually reads
+    (and every knob the library reads must be documented)."""
+    import subprocess
+
+    with open(os.path.join(ROOT, "INTEGRATION.md"), encoding="utf-8") as f:
+        doc = f.read().split("## 6. Environment knobs", 1)[1]
+    documented = set(re.findall(r"`(VQA_[A-Z0-9_]+)", doc)) - {"VQA_EXPERIMENTAL"}
+    N.lib()
+    so = os.path.join(ROOT, "vietnamese_qa_system_b200", "libvqa_b200.so")
+    strings = subprocess.run(["strings", "-n", "6", so], capture_output=True, text=True).stdout
+    in_lib = set(re.findall(r"^(VQA_[A-Z0-9_]+)$", strings, flags=re.M)) - {"VQA_SPIN_LIMIT"}
+    assert documented <= in_lib, f"documented but not read by the library: {sorted(documented - in_lib)}"
+    assert in_lib <= documented, f"read by the library but not documented: {sorted(in_lib - documented)}"
