@@ -12,7 +12,10 @@ ranks (strong scaling).
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's CPU path, timed on host cores
 
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  At N = 1 the line also carries secondary sections that are measured AFTER the
+timed steps and never enter `value` / `e2e`: `sweep` (batch sizes), `pool_k1`, `config_a_reference_scale`,
+`hybrid_leg`, and `opt_in_preview` -- the opt-in kernels of DESIGN.md section 3 timed in subprocesses (own CUDA
+context, bounded by a timeout; `--preview 0` skips it).
 """
 from __future__ import annotations
 
@@ -243,6 +246,51 @@ def hybrid_leg_section(torch, ops, shard, q_dev, timed, with_cpu: bool):
                for sr, ir in zip(ss[:nq].cpu().tolist(), sp[:nq].cpu().tolist())]
         out.update({"cpu_ms_per_query_numpy_restatement": cpu_ms, "cpu_qps": 1e3 / cpu_ms,
                     "results_identical_to_cpu_restatement": bool(got == want), "cpu_queries_checked": nq})
+    return out
+
+
+def opt_in_preview(timeout_s: float = 75.0, budget_s: float = 180.0):
+    """Timings of the OPT-IN kernels (written after round 1's GPU budget was spent, verified on
+    the CPU emulator only) next to the defaults, at the 8-GPU shard size.  Not part of `value` / `e2e`: the default
+    routing never uses them.  Each job runs tools/tune_worker.py in a SUBPROCESS -- its own CUDA context, bounded
+    by a timeout -- after every other measurement is finished, so that a kernel that has never met the hardware
+    cannot take the bench line down with it; a job that fails is reported as {"error": ...}."""
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    shard_rows = "1250000"
+    jobs = {
+        "headline_kernel_b1_32_shard": {
+            "ROWS": shard_rows, "K": "10", "MODE": "tensor", "BATCHES": "1,16,32", "ITERS": "50",
+            "VARIANTS": "-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1;VQA_MMA_TB=1,VQA_REDUCE_EARLY=1"},
+        "large_batch_b64_256_shard": {
+            "ROWS": shard_rows, "K": "10", "MODE": "fast", "BATCHES": "64,128,256", "ITERS": "20",
+            "VARIANTS": "-;VQA_REDUCE_SELECT=1;VQA_TS_QS=1,VQA_TS_KS=0;VQA_TS_QS=1,VQA_TS_KS=4,VQA_REDUCE_SELECT=1"},
+        "config_d_like_2M_x_1024_fp16_top100_b64": {
+            "ROWS": "2000000", "DIM": "1024", "DTYPE": "fp16", "K": "100", "MODE": "fast", "BATCHES": "64", "ITERS": "10",
+            "VARIANTS": "-;VQA_REDUCE_SELECT=1;VQA_REDUCE_SELECT=1,VQA_TS_QS=1"},
+    }
+    out = {"note": "opt-in kernels timed in subprocesses after the bench proper; ms = CUDA events around vqa_search, "
+                   "recall / max_rel_err against the fp32 verify kernel; '-' = default routing"}
+    t_start = time.time()
+    for name, knobs in jobs.items():
+        if time.time() - t_start > budget_s - 20.0:  # keep the whole bench within minutes
+            out[name] = {"skipped": "preview time budget used up"}
+            continue
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+        env.update(knobs)
+        env["CHECK"] = "1"
+        try:
+            r = subprocess.run([sys.executable, os.path.join(here, "tools", "tune_worker.py")], env=env,
+                               capture_output=True, text=True, timeout=timeout_s)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and last:
+                out[name] = json.loads(last[-1])
+            else:
+                out[name] = {"error": f"exit {r.returncode}: " + (r.stderr or r.stdout)[-300:]}
+        except Exception as exc:  # noqa: BLE001 - timeout, missing tool, bad JSON: never fatal
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     return out
 
 
@@ -494,6 +542,15 @@ def run_ours(args):
                          f"argpartition (oracle.np_search_fast), {reps} reps of {per_step * 1e3:.1f} ms; QPS scaled by "
                          f"rows ratio"}
 
+    # ---- opt-in kernels, in subprocesses, after everything above is measured (rank 0, N=1 only) ----
+    preview = None
+    if rank == 0 and world == 1 and args.sweep and args.preview:
+        try:
+            torch.cuda.synchronize()
+            preview = opt_in_preview()
+        except Exception as exc:  # noqa: BLE001
+            preview = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         merge_launches = 1 if world > 1 else 0
         line = {
@@ -512,6 +569,7 @@ def run_ours(args):
             "gpu_launches": K * (launches + merge_launches),
             "recall_at_10": recall, "recall_at_10_batch256": recall_b256, "fast_vs_verify_max_rel_score_err": max_rel,
             "sweep": sweep, "pool_k1": pool, "config_a_reference_scale": config_a, "hybrid_leg": hybrid,
+            "opt_in_preview": preview,
             "lib": f"libvqa_b200.so v{vqa._native.lib().vqa_version()}",
         }
         print(json.dumps(line), flush=True)
@@ -529,6 +587,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--sweep", type=int, default=1)
+    ap.add_argument("--preview", type=int, default=1, help="time the opt-in kernels in subprocesses (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=500_000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
