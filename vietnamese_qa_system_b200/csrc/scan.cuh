@@ -553,8 +553,9 @@ __global__ void __launch_bounds__(kReduceBigWarps * 32) reduce_topk_kernel(const
 // exactly the keys still wanted), the survivors are compacted, optionally re-scored exactly (screen mode),
 // bitonic-sorted and written.  Same total order as ranks_before, so the result is identical to the other
 // reduce kernels' -- including the sign of a zero score.
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 256;  // = histogram bins: thread t clears bin t
 constexpr int kSelWarps = kSelThreads / 32;
+static_assert(kSelThreads == 256 && kSelThreads >= kMaxK, "one thread per radix bin and per output slot");
 
 __device__ __forceinline__ uint32_t ord_f32(float f) {
     const uint32_t u = __float_as_uint(f);
