@@ -273,6 +273,10 @@ def opt_in_preview(timeout_s: float = 75.0, budget_s: float = 180.0):
     out = {"note": "opt-in kernels timed in subprocesses after the bench proper; ms = CUDA events around vqa_search, "
                    "recall / max_rel_err against the fp32 verify kernel; '-' = default routing"}
     t_start = time.time()
+    scripts = {name: "tune_worker.py" for name in jobs}
+    # default kernels through the new asynchronous host-buffer call: synchronous vs two batches in flight
+    jobs["e2e_host_buffers_sync_vs_two_in_flight_shard"] = {"ROWS": shard_rows, "BATCH": "32", "STEPS": "500"}
+    scripts["e2e_host_buffers_sync_vs_two_in_flight_shard"] = "e2e_pipeline_probe.py"
     for name, knobs in jobs.items():
         if time.time() - t_start > budget_s - 20.0:  # keep the whole bench within minutes
             out[name] = {"skipped": "preview time budget used up"}
@@ -282,7 +286,7 @@ def opt_in_preview(timeout_s: float = 75.0, budget_s: float = 180.0):
         env.update(knobs)
         env["CHECK"] = "1"
         try:
-            r = subprocess.run([sys.executable, os.path.join(here, "tools", "tune_worker.py")], env=env,
+            r = subprocess.run([sys.executable, os.path.join(here, "tools", scripts[name])], env=env,
                                capture_output=True, text=True, timeout=timeout_s)
             last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             if r.returncode == 0 and last:
