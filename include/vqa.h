@@ -43,7 +43,7 @@ extern "C" {
 #define VQA_API __attribute__((visibility("default")))
 #endif
 
-#define VQA_VERSION 110 /* 0.1.1: + sparse leg, hybrid fusion */
+#define VQA_VERSION 111 /* 0.1.1: + sparse leg, hybrid fusion; 111: + vqa_plan_describe, vqa_search_host_async */
 
 typedef enum vqa_status {
     VQA_OK = 0,

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported():
 
 def test_version_and_last_error():
     L = N.lib()
-    assert L.vqa_version() == 110
+    assert L.vqa_version() == 111
     assert isinstance(N.last_error(), str)
 
 
