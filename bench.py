@@ -249,7 +249,7 @@ def hybrid_leg_section(torch, ops, shard, q_dev, timed, with_cpu: bool):
     return out
 
 
-def opt_in_preview(timeout_s: float = 75.0, budget_s: float = 180.0):
+def opt_in_preview(timeout_s: float = 60.0, budget_s: float = 120.0):
     """Timings of the OPT-IN kernels (written after round 1's GPU budget was spent, verified on
     the CPU emulator only) next to the defaults, at the 8-GPU shard size.  Not part of `value` / `e2e`: the default
     routing never uses them.  Each job runs tools/tune_worker.py in a SUBPROCESS -- its own CUDA context, bounded
