@@ -263,9 +263,10 @@ def opt_in_preview(timeout_s: float = 60.0, budget_s: float = 120.0):
         "headline_kernel_b1_32_shard": {
             "ROWS": shard_rows, "K": "10", "MODE": "tensor", "BATCHES": "1,16,32", "ITERS": "50",
             "VARIANTS": "-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1;VQA_MMA_TB=1,VQA_REDUCE_EARLY=1"},
-        "large_batch_b64_256_shard": {
-            "ROWS": shard_rows, "K": "10", "MODE": "fast", "BATCHES": "64,128,256", "ITERS": "20",
-            "VARIANTS": "-;VQA_REDUCE_SELECT=1;VQA_TS_QS=1,VQA_TS_KS=0;VQA_TS_QS=1,VQA_TS_KS=4,VQA_REDUCE_SELECT=1"},
+        "large_batch_b64_512_shard": {
+            "ROWS": shard_rows, "K": "10", "MODE": "fast", "BATCHES": "64,128,256,512", "ITERS": "20",
+            "VARIANTS": "-;VQA_REDUCE_SELECT=1;VQA_PDL_CHAIN=1;VQA_PDL_CHAIN=1,VQA_REDUCE_SELECT=1;"
+                        "VQA_TS_QS=1,VQA_TS_KS=0;VQA_TS_QS=1,VQA_TS_KS=4,VQA_REDUCE_SELECT=1"},
         "config_d_like_2M_x_1024_fp16_top100_b64": {
             "ROWS": "2000000", "DIM": "1024", "DTYPE": "fp16", "K": "100", "MODE": "fast", "BATCHES": "64", "ITERS": "10",
             "VARIANTS": "-;VQA_REDUCE_SELECT=1;VQA_REDUCE_SELECT=1,VQA_TS_QS=1"},
