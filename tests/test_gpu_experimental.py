@@ -170,7 +170,7 @@ def test_early_exit_reduce_is_exact(monkeypatch, storage, mode, n, d, b, k):
     assert np.array_equal(i0, i1) and np.array_equal(s0.view(np.int32), s1.view(np.int32))
 
 
-@pytest.mark.parametrize("storage,n,d,b,k", [("bf16", 200000, 768, 128, 10), ("fp16", 50000, 384, 40, 5),
+@pytest.mark.parametrize("storage,n,d,b,k", [("bf16", 60000, 768, 128, 10), ("fp16", 50000, 384, 40, 5),
                                              ("bf16", 30000, 768, 300, 10)])
 def test_screen_mode_rescoring_through_the_select_kernel(monkeypatch, storage, n, d, b, k):
     """VQA_REDUCE_SELECT=1 also takes over the k <= 32 screen-then-rescore reduce of the (default) TMEM-resident-query

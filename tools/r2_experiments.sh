@@ -12,7 +12,7 @@ group() {  # title, then ROWS=.. etc. and VARIANTS=..
 }
 
 echo "== correctness first: the experimental GPU tests"
-VQA_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -x -q 2>&1 | tail -n 5
+VQA_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_experimental.py -x -q 2>&1 | tail -n 5
 
 group "headline kernel at the 8-GPU shard size (1.25 M rows): tournament bound, early-exit reduce (B-dependent cost)" \
   ROWS=1250000 K=10 MODE=tensor BATCHES=1,8,16,32 ITERS=50 \
