@@ -26,6 +26,16 @@
  *     (BASELINE.json north_star; txtai NumPy backend's stable sort).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point
  *     returns VQA_E_CUDA.
+ *   - threading: an index handle is immutable between vqa_index_bind /
+ *     vqa_index_set_tuning calls, and any number of threads may call vqa_search*
+ *     on it concurrently PROVIDED each in-flight call has its own workspace (or
+ *     staging buffer) and output buffers -- two searches that share a workspace
+ *     race on its candidate lists, whatever streams they run on.  bind /
+ *     set_tuning / destroy must not overlap any other call on the same handle.
+ *   - the search path reads NO environment variables: kernel-selection knobs are
+ *     a vqa_tuning_t stored in the handle (library defaults, overridden by VQA_*
+ *     variables read ONCE in vqa_index_create, or set explicitly with
+ *     vqa_index_set_tuning).
  */
 #ifndef VQA_H_
 #define VQA_H_
@@ -43,7 +53,7 @@ extern "C" {
 #define VQA_API __attribute__((visibility("default")))
 #endif
 
-#define VQA_VERSION 111 /* 0.1.1: + sparse leg, hybrid fusion; 111: + vqa_plan_describe, vqa_search_host_async */
+#define VQA_VERSION 120 /* 111: + vqa_plan_describe, vqa_search_host_async; 120: + vqa_tuning_t (no getenv on the search path) */
 
 typedef enum vqa_status {
     VQA_OK = 0,
@@ -111,6 +121,44 @@ VQA_API int vqa_index_bind(vqa_index_t *h, const void *rows_dev, int64_t n_rows,
                            int64_t row_stride_bytes);
 
 VQA_API int vqa_index_destroy(vqa_index_t *h);
+
+/*
+ * Kernel-selection knobs of one index handle.  Every field has a measured default (vqa_tuning_default);
+ * they exist for benchmarks and tests -- a drop-in user never touches them.  -1 / 0 = "auto" where noted.
+ * Replaces: nothing in the reference (txtai exposes faiss' `nprobe`/`components` strings the same way,
+ * through Embeddings(**cfg), heavy_ranker.py:78-83).
+ */
+typedef struct vqa_tuning {
+    int32_t size;          /* sizeof(vqa_tuning_t) as the caller compiled it (ABI growth check)                  */
+    int32_t ts_extra;      /* spare candidate ranks kept by the screen-then-rescore scans, 0..96 (6)              */
+    int32_t ss_screen;     /* smem-resident tcgen05 kernel: screen mode instead of hi/lo columns, 0|1 (0)         */
+    int32_t mma_kps;       /* 64-column blocks per TMA ring stage, 0 = auto, else 1..16                           */
+    int32_t mma_stages;    /* cap on ring stages, 0 = auto                                                        */
+    int32_t mma_groups;    /* smem-resident kernel: query chunks side by side per launch, 1..4 (4)                */
+    int32_t mma_multicast; /* those chunks as a cluster with TMA multicast, 0|1 (1)                               */
+    int32_t mma_tb;        /* tournament bound in the smem-resident kernel, 0|1                                   */
+    int32_t ts_qs;         /* TMEM-resident-query kernel: QS variant (part of the query block in smem), 0|1 (1)   */
+    int32_t ts_ks;         /* QS: 64-column query blocks kept in shared memory, -1 = auto, else 0..16             */
+    int32_t ts_split;      /* TS kernel: hi+lo rows (1) or storage-precision screen (0), -1 = auto                */
+    int32_t ts_groups;     /* TS kernel: chunks of 128 queries per launch (cluster size), 1..4 (2)                */
+    int32_t reduce_select; /* radix-select candidate reduce for k > 32 and for re-scoring reduces, 0|1 (1)        */
+    int32_t reduce_early;  /* early exit in the k <= 32 warp reduce over sorted internal lists, 0|1               */
+    int32_t pdl_chain;     /* 2nd+ scan launch of one search overlaps the previous reduce, 0|1                    */
+    int32_t tma_l2promo;   /* CUtensorMapL2promotion of the document tensor map, 0..3 (3 = 256 B)                 */
+    int32_t tma_hint;      /* L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last (1)         */
+    int32_t stream_max_b;  /* FAST: batches up to this size take the CUDA-core streaming kernel, 0..8 (2)         */
+    int32_t pair;          /* FAST: tensor-bound batches take the cta_group::2 pair kernel, 0|1                   */
+    int32_t reserved[5];
+} vqa_tuning_t;
+
+/* Library defaults (no environment). */
+VQA_API int vqa_tuning_default(vqa_tuning_t *t);
+/* Defaults overridden by the VQA_* environment variables of the same names (VQA_TS_EXTRA, VQA_TS_QS ...);
+ * a value that does not parse or is out of range is VQA_E_INVALID.  vqa_index_create calls this once. */
+VQA_API int vqa_tuning_from_env(vqa_tuning_t *t);
+/* Validate and store `t` in the handle (rebuilding the tensor maps if tma_l2promo changed). */
+VQA_API int vqa_index_set_tuning(vqa_index_t *h, const vqa_tuning_t *t);
+VQA_API int vqa_index_get_tuning(const vqa_index_t *h, vqa_tuning_t *t);
 
 /* Bytes of device workspace vqa_search needs for a batch of `n_queries`, top `k`. */
 VQA_API int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode,
@@ -245,6 +293,10 @@ VQA_API int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, 
 VQA_API int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k,
                               int32_t mode, int32_t sm_count, int32_t max_smem, int32_t *out,
                               size_t *smem_bytes);
+/* The same with explicit knobs (tuning == NULL: vqa_tuning_from_env, as vqa_plan_describe). */
+VQA_API int vqa_plan_describe_tuned(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k,
+                                    int32_t mode, int32_t sm_count, int32_t max_smem,
+                                    const vqa_tuning_t *tuning, int32_t *out, size_t *smem_bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Sparse (BM25) leg and hybrid fusion -- SURVEY.md 8(f) rank 3.

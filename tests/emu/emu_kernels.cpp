@@ -41,6 +41,19 @@ int guarded(F f) {
         return -1;
     }
 }
+// The product passes the reduce's knobs from the handle's vqa_tuning_t; this TEST harness takes them from the
+// environment of the test (monkeypatch.setenv), so one emulator build covers every variant.
+vqa::ReduceOpts emu_opts() {
+    auto on = [](const char *name) {
+        const char *e = std::getenv(name);
+        return e != nullptr && std::atoi(e) != 0;
+    };
+    vqa::ReduceOpts o;
+    o.select = on("VQA_REDUCE_SELECT") ? 1 : 0;
+    o.early = on("VQA_REDUCE_EARLY") ? 1 : 0;
+    o.trigger_early = on("VQA_PDL_CHAIN") ? 1 : 0;
+    return o;
+}
 }  // namespace
 
 extern "C" {
@@ -183,7 +196,7 @@ int emu_reduce_rescore(const float *cand_s, const uint32_t *cand_i, int n_lists,
         rs.k_final = k_final;
         const long long stride = (long long)n_queries * k_in;
         if (vqa::launch_reduce_u32(cand_s, cand_i, stride, k_in, n_lists, k_in, k_out, id_base, out_s, out_i, n_queries,
-                                   nullptr, 1, 1, nullptr, &rs) != cudaSuccess)
+                                   nullptr, 1, 1, nullptr, emu_opts(), &rs) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }
@@ -197,7 +210,7 @@ int emu_reduce_u32(const float *cand_s, const uint32_t *cand_i, int n_lists, int
     return guarded([&] {
         const long long stride = (long long)n_queries * k_in;
         if (vqa::launch_reduce_u32(cand_s, cand_i, stride, k_in, n_lists, k_in, k_out, id_base, out_s, out_i, n_queries,
-                                   tau_g, list_mod, queries_per_group, nullptr, nullptr) != cudaSuccess)
+                                   tau_g, list_mod, queries_per_group, nullptr, emu_opts(), nullptr) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }
@@ -263,7 +276,7 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
         a.slot_g = (tb && pass_nq <= 32 && k <= 32) ? slots : nullptr;  // api.cu's rule for the TB variants
         if (vqa::launch_mma(a, nullptr) != cudaSuccess) throw std::runtime_error("tensor scan launch failed");
         if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, k, grid, k, k, first_id, out_s, out_i,
-                                   n_queries, tau_g.data(), g, pass_nq, nullptr, nullptr, a.slot_g) != cudaSuccess)
+                                   n_queries, tau_g.data(), g, pass_nq, nullptr, emu_opts(), nullptr, a.slot_g) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }
@@ -343,7 +356,7 @@ int emu_search_ts(const void *rows, int bf16, long long n_rows, int dim, const f
         rs.k_final = k;
         if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, kscan, grid, kscan,
                                    split ? kscan : (kscan > 32 ? vqa::kMaxK : 32), first_id,
-                                   out_s, out_i, n_queries, tau_g.data(), g, pass_nq, nullptr,
+                                   out_s, out_i, n_queries, tau_g.data(), g, pass_nq, nullptr, emu_opts(),
                                    split ? nullptr : &rs) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
@@ -385,7 +398,7 @@ int emu_search_stream(const void *rows, int dtype, long long n_rows, int dim, co
             if (vqa::launch_scan(a, nullptr) != cudaSuccess) throw std::runtime_error("scan launch failed");
         }
         if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cand_stride, k, n_lists, k, k, first_id, out_s, out_i,
-                                   n_queries, nullptr, 1, 1, nullptr) != cudaSuccess)
+                                   n_queries, nullptr, 1, 1, nullptr, emu_opts()) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }

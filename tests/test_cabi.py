@@ -26,8 +26,52 @@ def test_header_symbols_all_exported():
 
 def test_version_and_last_error():
     L = N.lib()
-    assert L.vqa_version() == 111
+    assert L.vqa_version() == 120 == N.ABI_VERSION
     assert isinstance(N.last_error(), str)
+
+
+def test_tuning_knobs_are_validated_once_not_read_on_the_search_path(monkeypatch):
+    """The kernel-selection knobs are a vqa_tuning_t: library defaults, VQA_* overrides parsed ONCE (index create /
+    vqa_tuning_from_env) and range-checked -- a nonsense value is VQA_E_INVALID, never a silently shortened list."""
+    L = N.lib()
+    for v in ("VQA_TS_EXTRA", "VQA_TS_QS", "VQA_REDUCE_SELECT", "VQA_TMA_L2PROMO", "VQA_TS_KS"):
+        monkeypatch.delenv(v, raising=False)
+    t = N.tuning_default()
+    assert t.size == ctypes.sizeof(N.Tuning) and t.ts_extra == 6 and t.ts_qs == 1 and t.reduce_select == 1
+    assert t.ts_ks == -1 and t.stream_max_b == 2 and t.tma_l2promo == 3
+    assert N.tuning_default(from_env=True).as_dict() == t.as_dict()
+    monkeypatch.setenv("VQA_TS_QS", "0")
+    monkeypatch.setenv("VQA_TS_EXTRA", "12")
+    e = N.tuning_default(from_env=True)
+    assert (e.ts_qs, e.ts_extra) == (0, 12)
+    for name, bad in (("VQA_TS_EXTRA", "-3"), ("VQA_TS_EXTRA", "97"), ("VQA_TMA_L2PROMO", "7"), ("VQA_TS_QS", "yes"),
+                      ("VQA_TS_KS", "4x")):
+        monkeypatch.setenv(name, bad)
+        rc = L.vqa_tuning_from_env(ctypes.byref(N.Tuning()))
+        assert rc == N.E_INVALID and name in N.last_error(), (name, bad, N.last_error())
+        monkeypatch.delenv(name)
+    # explicit tuning through the device-free planner: out-of-range fields and a wrong struct size are refused
+    out, smem = (ctypes.c_int32 * 16)(), ctypes.c_size_t()
+    good = N.tuning_default()
+    assert L.vqa_plan_describe_tuned(1000, 768, N.BF16, 64, 10, N.MODE_FAST, 148, 232448, ctypes.byref(good), out,
+                                     ctypes.byref(smem)) == 0
+    bad = N.tuning_default().update(ts_extra=-1)
+    assert L.vqa_plan_describe_tuned(1000, 768, N.BF16, 64, 10, N.MODE_FAST, 148, 232448, ctypes.byref(bad), out,
+                                     ctypes.byref(smem)) == N.E_INVALID and "ts_extra" in N.last_error().lower()
+    bad = N.tuning_default()
+    bad.size = 8
+    assert L.vqa_plan_describe_tuned(1000, 768, N.BF16, 64, 10, N.MODE_FAST, 148, 232448, ctypes.byref(bad), out,
+                                     ctypes.byref(smem)) == N.E_INVALID
+    with pytest.raises(ValueError):
+        N.tuning_default().update(no_such_knob=1)
+    # the hot path has no getenv: api.cu reads the environment in exactly one function
+    with open(os.path.join(ROOT, "vietnamese_qa_system_b200", "csrc", "api.cu")) as f:
+        api = f.read()
+    assert api.count("getenv(") == 1
+    for fn in os.listdir(os.path.join(ROOT, "vietnamese_qa_system_b200", "csrc")):
+        if fn != "api.cu":
+            with open(os.path.join(ROOT, "vietnamese_qa_system_b200", "csrc", fn)) as f:
+                assert "getenv" not in f.read(), fn
 
 
 def test_library_is_built_for_sm100a():
@@ -199,8 +243,8 @@ def test_documented_environment_knobs_exist_in_the_library():
     import subprocess
 
     with open(os.path.join(ROOT, "INTEGRATION.md"), encoding="utf-8") as f:
-        doc = f.read().split("## 6. Environment knobs", 1)[1]
-    documented = set(re.findall(r"`(VQA_[A-Z0-9_]+)", doc)) - {"VQA_EXPERIMENTAL"}
+        doc = f.read().split("## 6. Tuning knobs", 1)[1]
+    documented = set(re.findall(r"`(VQA_[A-Z0-9_]+)", doc)) - {"VQA_EXPERIMENTAL", "VQA_E_INVALID"}
     N.lib()
     so = os.path.join(ROOT, "vietnamese_qa_system_b200", "libvqa_b200.so")
     strings = subprocess.run(["strings", "-n", "6", so], capture_output=True, text=True).stdout

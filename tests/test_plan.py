@@ -14,10 +14,14 @@ VERIFY, FAST, STREAM, TENSOR, TS = 0, 1, 2, 3, 4
 SMS, SMEM = 148, 232448
 
 
-def plan(n, dim, dtype, b, k, mode=FAST):
+def plan(n, dim, dtype, b, k, mode=FAST, **knobs):
     out = (ctypes.c_int32 * 16)()
     smem = ctypes.c_size_t()
-    rc = N.lib().vqa_plan_describe(n, dim, dtype, b, k, mode, SMS, SMEM, out, ctypes.byref(smem))
+    if knobs:
+        t = N.tuning_default().update(**knobs)
+        rc = N.lib().vqa_plan_describe_tuned(n, dim, dtype, b, k, mode, SMS, SMEM, ctypes.byref(t), out, ctypes.byref(smem))
+    else:
+        rc = N.lib().vqa_plan_describe(n, dim, dtype, b, k, mode, SMS, SMEM, out, ctypes.byref(smem))
     if rc != 0:
         return None
     keys = ["family", "pass_nq", "passes", "groups", "stages", "kps", "ncol", "split", "qs", "ks", "kscan", "k_out",
@@ -27,24 +31,48 @@ def plan(n, dim, dtype, b, k, mode=FAST):
     return d
 
 
-def test_default_routing_is_the_measured_round1_routing(monkeypatch):
-    for v in ("VQA_TS_QS", "VQA_TS_KS", "VQA_REDUCE_SELECT", "VQA_TS_SPLIT", "VQA_TS_EXTRA"):
+KNOB_ENV = ("VQA_TS_QS", "VQA_TS_KS", "VQA_REDUCE_SELECT", "VQA_TS_SPLIT", "VQA_TS_EXTRA", "VQA_STREAM_MAX_B")
+
+
+def test_default_routing(monkeypatch):
+    """Round-2 defaults (flipped by the B200 timings in profiles/r2_*): B <= 2 on the CUDA-core streaming kernel,
+    up to 32 queries on the smem-resident tcgen05 kernel, beyond that the QS variant of the TMEM-resident-query
+    kernel with four accumulator stages at dim 768, and dim 1024 on it too."""
+    for v in KNOB_ENV:
         monkeypatch.delenv(v, raising=False)
     n = 10_000_000
-    for b in (1, 8, 32):                                   # headline: smem-resident tcgen05 kernel, hi/lo columns
+    for b in (1, 2):                                       # north_star's small-batch regime: HBM-streaming warp dot products
+        assert plan(n, 768, BF16, b, 10)["family"] == STREAM
+    for b in (3, 8, 32):                                   # headline: smem-resident tcgen05 kernel, hi/lo columns
         p = plan(n, 768, BF16, b, 10)
         assert p["family"] == TENSOR and p["split"] == 1 and p["smem"] <= SMEM
     for b in (33, 64, 128, 256, 1024):                     # large batches: queries in TMEM, screen + re-score of 32
         p = plan(n, 768, BF16, b, 10)
-        assert (p["family"], p["split"], p["qs"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 0, 16, 32, 1)
-        assert p["tmem_query_cols"] == 384 and p["stages"] * p["kps"] == 24 and p["smem"] <= SMEM
+        assert (p["family"], p["split"], p["qs"], p["ks"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 1, 4, 16, 32, 1)
+        assert p["tmem_query_cols"] == 256 and p["smem"] <= SMEM       # 8 blocks in TMEM -> 4 accumulator stages
     p = plan(n, 768, BF16, 8, 100)                         # k > 32: TS with hi/lo rows and heaps, no re-scoring
-    assert (p["family"], p["split"], p["qs"], p["kscan"], p["rescore"]) == (TS, 1, 0, 100, 0)
-    p = plan(12_500_000, 1024, F16, 64, 100)               # BASELINE configs[3]: dim 1024 does not fit TMEM -> smem-resident
-    assert p["family"] == TENSOR and p["qs"] == 0
-    assert plan(n, 1024, BF16, 64, 10, TS) is None         # asking for TS explicitly at dim 1024: unsupported by default
+    assert (p["family"], p["split"], p["qs"], p["kscan"], p["rescore"]) == (TS, 1, 1, 100, 0)
+    assert plan(n, 768, BF16, 1, 100)["family"] == TS      # big k is never a streaming-kernel case
+    p = plan(12_500_000, 1024, F16, 64, 100)               # BASELINE configs[3]: one pass, 12 blocks in TMEM + 4 in smem
+    assert (p["family"], p["qs"], p["ks"], p["split"], p["rescore"]) == (TS, 1, 4, 0, 1)
+    assert plan(n, 1024, BF16, 64, 10, TS) is not None
     assert plan(n, 768, F32, 4, 10)["family"] == STREAM and plan(n, 776, BF16, 4, 10)["family"] == STREAM
     assert plan(n, 768, BF16, 4, 10, VERIFY)["family"] == STREAM
+
+
+def test_round1_routing_is_still_reachable_through_the_knobs(monkeypatch):
+    for v in KNOB_ENV:
+        monkeypatch.delenv(v, raising=False)
+    r1 = dict(ts_qs=0, reduce_select=0, stream_max_b=0)
+    n = 10_000_000
+    assert plan(n, 768, BF16, 1, 10, **r1)["family"] == TENSOR
+    p = plan(n, 768, BF16, 128, 10, **r1)
+    assert (p["family"], p["split"], p["qs"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 0, 16, 32, 1)
+    assert p["tmem_query_cols"] == 384 and p["stages"] * p["kps"] == 24
+    assert plan(12_500_000, 1024, F16, 64, 100, **r1)["family"] == TENSOR     # dim 1024 does not fit TMEM without QS
+    assert plan(n, 1024, BF16, 64, 10, TS, **r1) is None
+    monkeypatch.setenv("VQA_TS_QS", "0")                   # the environment spelling is read by vqa_plan_describe too
+    assert plan(n, 768, BF16, 128, 10)["qs"] == 0
 
 
 @pytest.mark.parametrize("qs,select", [(0, 0), (0, 1), (1, 0), (1, 1)])
@@ -83,8 +111,8 @@ def test_every_plan_fits_shared_and_tensor_memory(monkeypatch, qs, select):
         assert (TS, 0, 0, 1) in seen and (TS, 0, 1, 0) in seen
 
 
-def test_config_d_plan_with_the_opt_in_kernels(monkeypatch):
-    """BASELINE configs[3] (12.5 M x 1024 fp16 per GPU, B = 64, top-100) under VQA_TS_QS=1 VQA_REDUCE_SELECT=1:
+def test_config_d_plan(monkeypatch):
+    """BASELINE configs[3] (12.5 M x 1024 fp16 per GPU, B = 64, top-100) on the default routing:
     one pass of the TMEM-resident-query kernel -- 12 query blocks in tensor memory, 4 in shared memory, heaps for
     64 rows, 106 candidates per list, the 128 best re-scored exactly by the radix-select reduce."""
     monkeypatch.setenv("VQA_TS_QS", "1")

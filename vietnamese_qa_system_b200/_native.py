@@ -28,10 +28,45 @@ EXPORTS = [
     "vqa_index_destroy", "vqa_workspace_bytes", "vqa_search", "vqa_search_host_staging_bytes", "vqa_search_host_async",
     "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_exchange_push", "vqa_merge_topk_wait",
     "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
-    "vqa_search_plan", "vqa_plan_describe",
+    "vqa_search_plan", "vqa_plan_describe", "vqa_plan_describe_tuned",
+    "vqa_tuning_default", "vqa_tuning_from_env", "vqa_index_set_tuning", "vqa_index_get_tuning",
     "vqa_sparse_limits", "vqa_sparse_create", "vqa_sparse_bind", "vqa_sparse_destroy", "vqa_bm25_weights",
     "vqa_sparse_workspace_bytes", "vqa_sparse_search", "vqa_hybrid_fuse", "vqa_agree_f64",
 ]
+
+ABI_VERSION = 120  # VQA_VERSION this binding was written against (include/vqa.h)
+
+
+class Tuning(ctypes.Structure):
+    """vqa_tuning_t (include/vqa.h): the kernel-selection knobs stored in an index handle."""
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "size", "ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "mma_tb", "ts_qs",
+        "ts_ks", "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
+        "stream_max_b", "pair")] + [("reserved", ctypes.c_int32 * 5)]
+
+    KNOBS = ("ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "mma_tb", "ts_qs", "ts_ks",
+             "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
+             "stream_max_b", "pair")
+
+    def update(self, **knobs) -> "Tuning":
+        for key, val in knobs.items():
+            name = key.lower()
+            if name.startswith("vqa_"):          # the environment spelling, VQA_TS_QS -> ts_qs
+                name = name[4:]
+            if name not in self.KNOBS:
+                raise ValueError(f"unknown tuning knob {key!r}; expected one of {self.KNOBS}")
+            setattr(self, name, int(val))
+        return self
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n in self.KNOBS}
+
+
+def tuning_default(from_env: bool = False) -> Tuning:
+    t = Tuning()
+    check((lib().vqa_tuning_from_env if from_env else lib().vqa_tuning_default)(ctypes.byref(t)))
+    return t
+
 
 _lib = None
 _lock = threading.Lock()
@@ -84,6 +119,17 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_search_plan.argtypes = [vp, i32, i32, i32, c.POINTER(i32), c.POINTER(i32)]
     L.vqa_plan_describe.restype = c.c_int
     L.vqa_plan_describe.argtypes = [i64, i32, i32, i32, i32, i32, i32, i32, c.POINTER(i32), c.POINTER(sz)]
+    L.vqa_plan_describe_tuned.restype = c.c_int
+    L.vqa_plan_describe_tuned.argtypes = [i64, i32, i32, i32, i32, i32, i32, i32, c.POINTER(Tuning), c.POINTER(i32),
+                                          c.POINTER(sz)]
+    L.vqa_tuning_default.restype = c.c_int
+    L.vqa_tuning_default.argtypes = [c.POINTER(Tuning)]
+    L.vqa_tuning_from_env.restype = c.c_int
+    L.vqa_tuning_from_env.argtypes = [c.POINTER(Tuning)]
+    L.vqa_index_set_tuning.restype = c.c_int
+    L.vqa_index_set_tuning.argtypes = [vp, c.POINTER(Tuning)]
+    L.vqa_index_get_tuning.restype = c.c_int
+    L.vqa_index_get_tuning.argtypes = [vp, c.POINTER(Tuning)]
     L.vqa_sparse_limits.restype = c.c_int
     L.vqa_sparse_limits.argtypes = [c.POINTER(i32), c.POINTER(i32)]
     L.vqa_sparse_create.restype = c.c_int
@@ -105,16 +151,23 @@ def _bind(L: ctypes.CDLL) -> None:
 
 
 def lib() -> ctypes.CDLL:
-    """Load (building first if the .so is absent) the native library.  Fails loudly."""
+    """Load the native library, (re)building it first when it is absent or older than its sources
+    (content stamp, see build.build).  Fails loudly; a stale binary is never bound with new prototypes."""
     global _lib
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
-                from . import build as _build  # needs nvcc; raises if it cannot build
+            from . import build as _build
 
-                _build.build()
+            try:
+                _build.build()  # no-op when the stamp matches csrc/ + include/vqa.h; needs nvcc otherwise
+            except Exception as exc:  # noqa: BLE001
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing and cannot be built ({exc}). The CUDA extension is the only "
+                        "compute path of this package (no CPU fallback).") from exc
+                # an existing binary that could not be refreshed is accepted only if it speaks this ABI (checked below)
             try:
                 L = ctypes.CDLL(LIB_PATH)
             except OSError as exc:  # pragma: no cover - depends on the box
@@ -122,6 +175,10 @@ def lib() -> ctypes.CDLL:
                     f"cannot load {LIB_PATH}: {exc}. The CUDA extension is the only compute path of this "
                     "package (no CPU fallback); build it with `python -m vietnamese_qa_system_b200.build`."
                 ) from exc
+            L.vqa_version.restype = ctypes.c_int
+            if L.vqa_version() != ABI_VERSION:
+                raise RuntimeError(f"{LIB_PATH} reports ABI version {L.vqa_version()}, this binding needs {ABI_VERSION}: "
+                                   "rebuild with `python -m vietnamese_qa_system_b200.build --force`")
             _bind(L)
             _lib = L
     return _lib

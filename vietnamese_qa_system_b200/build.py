@@ -22,18 +22,50 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; libvqa_b200.so cannot be built")
 
 
-def _deps_mtime() -> float:
-    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+STAMP = os.path.join(BUILD, "sources.sha256")
+
+
+def _sources_digest() -> str:
+    """Content hash of everything the library is compiled from.  A content stamp instead of mtimes: the
+    snapshot that carries the built .so to the GPU box does not preserve them, and N ranks importing the
+    package there must all find the binary current instead of racing to rebuild it."""
+    import hashlib
+
+    h = hashlib.sha256()
+    paths = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     paths.append(os.path.join(HERE, "..", "include", "vqa.h"))
-    return max(os.path.getmtime(p) for p in paths)
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    try:
+        with open(STAMP) as f:
+            return os.path.exists(LIB) and f.read().strip() == _sources_digest()
+    except OSError:
+        return False
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source with -gencode arch=compute_100a,code=sm_100a -lineinfo."""
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
+    if not force and is_current():
         return LIB
-    nvcc = _nvcc()
     os.makedirs(BUILD, exist_ok=True)
+    import fcntl
+
+    with open(os.path.join(BUILD, ".lock"), "w") as lockf:  # one builder at a time (torchrun ranks, xdist workers)
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        if not force and is_current():
+            return LIB
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
+    digest = _sources_digest()
+    nvcc = _nvcc()
     flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
              "-Xptxas", "-v"] + ARCH
 
@@ -57,6 +89,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    with open(STAMP, "w") as f:
+        f.write(digest + "\n")
     for name, (regs, st, ld) in sorted(spill_report().items()):
         if st or ld:  # never silent: a spill inside a streaming loop costs real bandwidth
             sys.stderr.write(f"[vqa build] register spills: {name}: {st} B stores / {ld} B loads at {regs} registers\n")

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 
@@ -98,7 +99,16 @@ struct vqa_index {
     bool tmap_ok = false;
     // tmap[j]: TMA box of 64 columns x (128 >> j) rows -- j = log2(cluster size) of the multicast launch
     alignas(64) CUtensorMap tmap[4];
-    mutable int max_clusters[4][5] = {};  // cached cudaOccupancyMaxActiveClusters by [log2 cluster][ncol slot]
+    vqa_tuning_t tune;  // kernel-selection knobs: resolved once (create / set_tuning), never read from the environment later
+    // caches filled by the (const) search path; guarded by `mu` so that concurrent searches on one handle are safe
+    mutable std::mutex mu;
+    mutable int max_clusters[4][5] = {};  // cudaOccupancyMaxActiveClusters by [log2 cluster][ncol slot]
+    struct PlanSlot {
+        int nq = 0, k = 0, mode = -1;
+        int plan[16] = {};
+    };
+    mutable PlanSlot plan_cache[8];
+    mutable unsigned plan_next = 0;
 };
 
 // sparse (BM25) term index: CSR postings borrowed from the caller
@@ -132,26 +142,84 @@ struct Plan {
     int grid;
 };
 
-int env_int(const char *name, int dflt) {
-    const char *e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
+// ---- knobs ---------------------------------------------------------------------
+struct KnobSpec {
+    const char *env;
+    int32_t vqa_tuning_t::*field;
+    int lo, hi, dflt;
+};
+// defaults = what the B200 measurements of rounds 1-2 support (profiles/r2_*): QS variant of the TMEM-resident-query
+// kernel and the radix-select / re-scoring reduce on, batches of <= 2 on the CUDA-core streaming kernel
+const KnobSpec kKnobs[] = {
+    {"VQA_TS_EXTRA", &vqa_tuning_t::ts_extra, 0, 96, 6},
+    {"VQA_SS_SCREEN", &vqa_tuning_t::ss_screen, 0, 1, 0},
+    {"VQA_MMA_KPS", &vqa_tuning_t::mma_kps, 0, 16, 0},
+    {"VQA_MMA_STAGES", &vqa_tuning_t::mma_stages, 0, vqa::kMaxStages, 0},
+    {"VQA_MMA_GROUPS", &vqa_tuning_t::mma_groups, 1, 4, 4},
+    {"VQA_MMA_MULTICAST", &vqa_tuning_t::mma_multicast, 0, 1, 1},
+    {"VQA_MMA_TB", &vqa_tuning_t::mma_tb, 0, 1, 0},
+    {"VQA_TS_QS", &vqa_tuning_t::ts_qs, 0, 1, 1},
+    {"VQA_TS_KS", &vqa_tuning_t::ts_ks, -1, 16, -1},
+    {"VQA_TS_SPLIT", &vqa_tuning_t::ts_split, -1, 1, -1},
+    {"VQA_TS_GROUPS", &vqa_tuning_t::ts_groups, 1, 4, 2},
+    {"VQA_REDUCE_SELECT", &vqa_tuning_t::reduce_select, 0, 1, 1},
+    {"VQA_REDUCE_EARLY", &vqa_tuning_t::reduce_early, 0, 1, 0},
+    {"VQA_PDL_CHAIN", &vqa_tuning_t::pdl_chain, 0, 1, 0},
+    {"VQA_TMA_L2PROMO", &vqa_tuning_t::tma_l2promo, 0, 3, 3},
+    {"VQA_TMA_HINT", &vqa_tuning_t::tma_hint, 0, 2, 1},
+    {"VQA_STREAM_MAX_B", &vqa_tuning_t::stream_max_b, 0, 8, 2},
+    {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 0},
+};
+
+void tuning_defaults(vqa_tuning_t *t) {
+    std::memset(t, 0, sizeof(*t));
+    t->size = (int32_t)sizeof(vqa_tuning_t);
+    for (const KnobSpec &kn : kKnobs) t->*(kn.field) = kn.dflt;
+}
+
+int tuning_validate(const vqa_tuning_t *t) {
+    if (!t) return fail(VQA_E_INVALID, "tuning is null");
+    if (t->size != (int32_t)sizeof(vqa_tuning_t))
+        return fail(VQA_E_INVALID, "vqa_tuning_t size mismatch: caller %d, library %d (start from vqa_tuning_default)",
+                    (int)t->size, (int)sizeof(vqa_tuning_t));
+    for (const KnobSpec &kn : kKnobs) {
+        const int v = t->*(kn.field);
+        if (v < kn.lo || v > kn.hi)
+            return fail(VQA_E_INVALID, "tuning knob %s = %d out of range [%d, %d]", kn.env + 4, v, kn.lo, kn.hi);
+    }
+    return VQA_OK;
+}
+
+int tuning_from_env(vqa_tuning_t *t) {
+    tuning_defaults(t);
+    for (const KnobSpec &kn : kKnobs) {
+        const char *e = std::getenv(kn.env);
+        if (!e || !*e) continue;
+        char *end = nullptr;
+        const long v = std::strtol(e, &end, 10);
+        if (end == e || *end != '\0' || v < kn.lo || v > kn.hi)
+            return fail(VQA_E_INVALID, "environment knob %s=\"%s\" is not an integer in [%d, %d]", kn.env, e, kn.lo, kn.hi);
+        t->*(kn.field) = (int32_t)v;
+    }
+    return VQA_OK;
 }
 
 bool tensor_eligible(const vqa_index *h) {
     return h->tmap_ok && (h->dtype == VQA_BF16 || h->dtype == VQA_F16) && h->dim % 64 == 0 && h->dim >= 64;
 }
 
-int spare_ranks() { return env_int("VQA_TS_EXTRA", 6); }
+int spare_ranks(const vqa_index *h) { return h->tune.ts_extra; }
 
 // pick the widest MMA N (<= what the batch needs) whose smem ring still has >= 4 boxes.
 // Screen mode (k + spare <= 32): one storage-precision column per query, up to 32 queries per CTA,
 // the k + spare best re-scored exactly in the reduce.  Otherwise hi/lo column pairs.
 bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
+    const vqa_tuning_t &tu = h->tune;
     // Measured (profiles/r1_tune_screen.log): for <= 32 queries per CTA the hi/lo kernel already runs at
     // the HBM roofline and the re-scoring stage's cold row reads cost ~35 us per search, so screen mode is
-    // opt-in here (VQA_SS_SCREEN=1); it pays off in the TMEM-resident-query kernel, 128 queries per CTA.
-    const bool screen = env_int("VQA_SS_SCREEN", 0) != 0 && k + spare_ranks() <= 32;
-    const int kk = screen ? k + spare_ranks() : k;
+    // opt-in here (ss_screen); it pays off in the TMEM-resident-query kernel, 128 queries per CTA.
+    const bool screen = tu.ss_screen != 0 && k + spare_ranks(h) <= 32;
+    const int kk = screen ? k + spare_ranks(h) : k;
     const int cands[4] = {128, 64, 32, 16};
     const int first = screen ? 2 : 0;  // screen mode keeps its lists in registers: <= 32 queries per CTA
     int want = screen ? nq : nq * 2;
@@ -165,12 +233,11 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
         // two adjacent 128-byte column blocks of the same rows per stage: the pair is requested
         // together, so each 256-byte DRAM/L2 granule is touched once (measured: +24% bandwidth)
         const int kb = h->dim / vqa::kBlockK;
-        int kps = env_int("VQA_MMA_KPS", kb % 2 == 0 ? 2 : (kb % 3 == 0 ? 3 : 1));
+        int kps = tu.mma_kps > 0 ? tu.mma_kps : (kb % 2 == 0 ? 2 : (kb % 3 == 0 ? 3 : 1));
         if (kps < 1 || kb % kps != 0) kps = 1;
         int stages = blocks / kps;
         if (stages > vqa::kMaxStages) stages = vqa::kMaxStages;
-        int cap = env_int("VQA_MMA_STAGES", 0);
-        if (cap > 0 && cap < stages) stages = cap;
+        if (tu.mma_stages > 0 && tu.mma_stages < stages) stages = tu.mma_stages;
         if (stages < 2) continue;
         pl->family = VQA_MODE_FAST_TENSOR;
         pl->ncol = ncol;
@@ -179,9 +246,7 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
         pl->stages = stages;
         pl->kps = kps;
         pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
-        int gmax = env_int("VQA_MMA_GROUPS", 4);
-        if (gmax < 1) gmax = 1;
-        pl->groups = pl->passes < gmax ? pl->passes : gmax;
+        pl->groups = pl->passes < tu.mma_groups ? pl->passes : tu.mma_groups;
         long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
         pl->grid = (int)(tiles < h->sm_count ? (tiles > 0 ? tiles : 1) : h->sm_count);
         return true;
@@ -189,30 +254,26 @@ bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
     return false;
 }
 
-// Opt-in paths that have passed the CPU emulator but have not been timed on a B200 yet (ts.cuh QS variant,
-// scan.cuh radix-select reduce).  Off by default: the default routing is exactly what round 1 measured.
-bool ts_qs_enabled() { return env_int("VQA_TS_QS", 0) != 0; }
-bool reduce_select_enabled() { return env_int("VQA_REDUCE_SELECT", 0) != 0; }
-// 2nd+ scan launch of one search overlaps the previous launch's reduce (programmatic dependent launch without a wait)
-bool pdl_chain_enabled() { return env_int("VQA_PDL_CHAIN", 0) != 0; }
-bool mma_tb_enabled() { return env_int("VQA_MMA_TB", 0) != 0; }  // tournament bound in the smem-resident kernel (mma.cuh)
-
+// The TMEM-resident-query kernel holds at most 12 of the query block's 64-column blocks in tensor memory
+// (384 columns + two accumulator stages); the QS variant keeps the rest in shared memory (dim <= 1024).
 bool ts_eligible(const vqa_index *h) {
-    return tensor_eligible(h) && (h->dim <= 768 || (ts_qs_enabled() && h->dim <= 1024));
+    return tensor_eligible(h) && (h->dim <= 768 || (h->tune.ts_qs != 0 && h->dim <= 1024));
 }
 
 // TMEM-resident queries: shared memory holds only the document ring and the per-row lists
 bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
+    const vqa_tuning_t &tu = h->tune;
     // k <= 16: screen with storage-precision queries (128 per CTA), keep 32 candidates per query and
     // re-score them exactly in the reduce.  Larger k: hi + lo rows (64 queries per CTA).
     const int kb = h->dim / vqa::kBlockK;
-    // QS variant (opt-in): ks of the kb query blocks in shared memory; at most 12 stay in TMEM (384 columns,
-    // two 64-column accumulator stages next to them), so dim 1024 needs ks >= 4
-    const int qs = ts_qs_enabled() ? 1 : 0;
+    // QS variant: ks of the kb query blocks in shared memory.  At most 12 fit tensor memory beside two accumulator
+    // stages; 8 leave FOUR stages (measured, profiles/r2_*: B = 128 at a 1.25 M-row shard 0.431 -> 0.366 ms), so
+    // auto = kb - 8 where shared memory has room for it, else the minimum that fits
+    const int qs = tu.ts_qs != 0 ? 1 : 0;
     int ks = 0;
     if (qs) {
         const int ks_min = kb > 12 ? kb - 12 : 0;
-        ks = env_int("VQA_TS_KS", ks_min);
+        ks = tu.ts_ks >= 0 ? tu.ts_ks : (kb > 8 && kb <= 12 ? kb - 8 : ks_min);
         if (ks < ks_min) ks = ks_min;
         if (ks > kb) ks = kb;
     } else if (h->dim > 768) {
@@ -220,17 +281,18 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     }
     // Screen mode beyond the register lists (k + spare > 32) re-scores through the radix-select reduce, the only
     // big-k reduce with a re-scoring stage: fp16 rows only (11-bit queries; bf16 queries would need ~28 spare
-    // ranks at top-100), and only when both opt-ins are set.  Anything else with k + spare > 32: hi/lo rows.
-    const bool big_screen_ok = qs && reduce_select_enabled() && k + spare_ranks() <= vqa::kMaxK;
-    int split = env_int("VQA_TS_SPLIT", (k + spare_ranks() <= 32 || (big_screen_ok && h->dtype == VQA_F16)) ? 0 : 1) != 0;
-    if (!split && k + spare_ranks() > 32 && !big_screen_ok) split = 1;
-    const int kscan = split ? k : k + spare_ranks();
+    // ranks at top-100).  Anything else with k + spare > 32: hi/lo rows.
+    const int spare = spare_ranks(h);
+    const bool big_screen_ok = qs && tu.reduce_select != 0 && k + spare <= vqa::kMaxK;
+    int split = tu.ts_split >= 0 ? tu.ts_split : ((k + spare <= 32 || (big_screen_ok && h->dtype == VQA_F16)) ? 0 : 1);
+    if (!split && k + spare > 32 && !big_screen_ok) split = 1;
+    const int kscan = split ? k : k + spare;
     const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split, ks, nq, qs);
     if (fixed >= (size_t)h->max_smem) return false;
     int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
     // 8 KB boxes: four column blocks per ring stage halve the per-byte handshakes (measured 2.74 -> 2.57 ms
     // at B = 128, 5.17 -> 4.38 ms at B = 256 on 10M x 768)
-    int kps = env_int("VQA_MMA_KPS", kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
+    int kps = tu.mma_kps > 0 ? tu.mma_kps : (kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
     if (kps < 1 || kb % kps != 0) kps = 1;
     // QS: the query blocks shrink the ring; keep at least three stages in flight before widening them
     while (qs && kps > 1 && boxes / kps < 3) kps = (kps % 2 == 0) ? kps / 2 : 1;
@@ -247,10 +309,7 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     pl->stages = stages;
     pl->kps = kps;
     pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
-    int gmax = env_int("VQA_TS_GROUPS", 2);
-    if (gmax < 1) gmax = 1;
-    if (gmax > 4) gmax = 4;
-    pl->groups = pl->passes < gmax ? pl->passes : gmax;
+    pl->groups = pl->passes < tu.ts_groups ? pl->passes : tu.ts_groups;
     pl->grid = h->sm_count;
     return true;
 }
@@ -261,15 +320,18 @@ void plan_stream(const vqa_index *h, int nq, Plan *pl) {
     pl->passes = (nq + pl->pass_nq - 1) / pl->pass_nq;
     pl->ncol = 0;
     pl->stages = 0;
+    pl->kps = 0;
     pl->groups = 1;
     pl->ss_split = 1;
     pl->ts_split = 1;
+    pl->ts_afp16 = 0;
     pl->ts_qs = 0;
     pl->ts_ks = 0;
     pl->grid = h->sm_count;
 }
 
-int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
+int make_plan_uncached(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
+    std::memset(pl, 0, sizeof(*pl));
     if (mode == VQA_MODE_VERIFY || mode == VQA_MODE_FAST_STREAM) {
         plan_stream(h, nq, pl);
         return VQA_OK;
@@ -283,25 +345,58 @@ int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
     }
     if (mode == VQA_MODE_FAST_TS) {
         if (!ts_eligible(h) || !plan_ts(h, nq, k, pl))
-            return fail(VQA_E_UNSUPPORTED, "TMEM-resident-query path needs bf16/fp16 rows and dim %% 64 == 0, dim <= 768 "
-                                           "(dim <= 1024 with the opt-in VQA_TS_QS=1)");
+            return fail(VQA_E_UNSUPPORTED, "TMEM-resident-query path needs bf16/fp16 rows and dim %% 64 == 0, dim <= 1024 "
+                                           "(dim <= 768 with the QS variant switched off)");
         return VQA_OK;
     }
     if (mode == VQA_MODE_FAST) {
-        // Measured on B200 (profiles/): the TMA-fed tcgen05 kernel streams the documents at the HBM
-        // roofline for every batch size, so 16-bit indexes always take it; the CUDA-core streaming
-        // kernel serves fp32 rows (verify mode's native storage) and dims that are not multiples of 64.
-        // Beyond the 32 queries the shared-memory-resident kernel holds per CTA, the TMEM-resident-query
-        // kernel serves 128 per CTA from one HBM pass (screen with storage-precision queries, exact
-        // re-scoring of the k+6 best in the reduce); it needs dim <= 768 and k+6 <= 32.
-        // k > 32 goes there too (hi/lo rows, heap lists): the smem-resident kernel's lock-guarded sorted
-        // lists are ~4x slower at top-100.
+        // Measured on B200 (profiles/):
+        //  * B <= 2 (stream_max_b): the CUDA-core streaming kernel (128-bit no-allocate loads, warp dot products)
+        //    reads the rows at the HBM roofline with the smallest fixed cost -- 2.18 vs 2.28 ms at 10 M x 768;
+        //  * up to 32 queries, k <= 32: the TMA-fed tcgen05 kernel with the queries resident in shared memory (hi/lo
+        //    columns) -- CUDA cores cannot keep up with HBM beyond ~4 queries per streamed element;
+        //  * beyond that, and k > 32: the TMEM-resident-query kernel serves 128 queries per CTA from one HBM pass
+        //    (screen with storage-precision queries, exact re-scoring in the reduce; hi/lo rows + heaps for big k).
+        //  fp32 rows (verify mode's native storage) and dims that are not multiples of 64: streaming kernel.
+        if (nq <= h->tune.stream_max_b && k <= 32) {
+            plan_stream(h, nq, pl);
+            return VQA_OK;
+        }
         if ((nq > 32 || k > 32) && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
         if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
         return VQA_OK;
     }
     return fail(VQA_E_INVALID, "unknown mode %d", mode);
+}
+
+static_assert(sizeof(Plan) <= 16 * sizeof(int), "Plan must fit a plan-cache slot");
+
+// plans are pure functions of (handle shape, tuning, nq, k, mode): cached per handle, invalidated by bind / set_tuning
+int make_plan(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        for (const auto &sl : h->plan_cache)
+            if (sl.mode == mode && sl.nq == nq && sl.k == k) {
+                std::memcpy(pl, sl.plan, sizeof(Plan));
+                return VQA_OK;
+            }
+    }
+    int rc = make_plan_uncached(h, nq, k, mode, pl);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(h->mu);
+    auto &sl = h->plan_cache[h->plan_next++ % 8];
+    sl.nq = nq;
+    sl.k = k;
+    sl.mode = mode;
+    std::memcpy(sl.plan, pl, sizeof(Plan));
+    return VQA_OK;
+}
+
+void invalidate_plans(vqa_index *h) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (auto &sl : h->plan_cache) sl.mode = -1;
+    std::memset(h->max_clusters, 0, sizeof(h->max_clusters));
 }
 
 int check_search_args(const vqa_index *h, int nq, int k) {
@@ -312,11 +407,37 @@ int check_search_args(const vqa_index *h, int nq, int k) {
 }
 
 // candidate lists are kept at least 32 wide so that the screen-then-rescore path can over-fetch; beyond the
-// register lists the (opt-in) big-k screen mode keeps k + spare candidates per list
+// register lists the big-k screen mode keeps k + spare candidates per list
 size_t cand_elems(const vqa_index *h, int nq, int k) {
-    int w = k + spare_ranks() <= 32 ? 32 : k + spare_ranks();
+    const int spare = spare_ranks(h);
+    int w = k + spare <= 32 ? 32 : k + spare;
     if (w > vqa::kMaxK) w = k < 32 ? 32 : k;
     return (size_t)h->sm_count * nq * w;
+}
+
+int build_tmaps(vqa_index *h) {
+    h->tmap_ok = false;
+    const int es = elem_size(h->dtype);
+    if (h->n_rows > 0 && h->rows && es == 2 && h->dim % 64 == 0) {
+        EncodeTiledFn enc = get_encode_fn();
+        if (enc) {
+            bool ok = true;
+            for (int j = 0; j < 4 && ok; ++j) {
+                cuuint64_t gdim[2] = {(cuuint64_t)h->dim, (cuuint64_t)h->n_rows};
+                cuuint64_t gstride[1] = {(cuuint64_t)h->stride};
+                cuuint32_t box[2] = {(cuuint32_t)vqa::kBlockK, (cuuint32_t)(vqa::kTileRows >> j)};
+                cuuint32_t estr[2] = {1, 1};
+                CUresult r = enc(&h->tmap[j], h->dtype == VQA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                 2, const_cast<void *>(h->rows), gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 (CUtensorMapL2promotion)h->tune.tma_l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                ok = (r == CUDA_SUCCESS);
+            }
+            h->tmap_ok = ok;
+        }
+    }
+    return VQA_OK;
 }
 
 }  // namespace
@@ -371,7 +492,41 @@ int vqa_index_create(vqa_index_t **out, int64_t n_rows, int32_t dim, int32_t dty
     }
     h->sm_count = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    // the ONLY place the search path's knobs meet the environment: once per handle, validated
+    int rc = tuning_from_env(&h->tune);
+    if (rc) {
+        delete h;
+        return rc;
+    }
     *out = h;
+    return VQA_OK;
+}
+
+int vqa_tuning_default(vqa_tuning_t *t) {
+    if (!t) return fail(VQA_E_INVALID, "tuning is null");
+    tuning_defaults(t);
+    return VQA_OK;
+}
+
+int vqa_tuning_from_env(vqa_tuning_t *t) {
+    if (!t) return fail(VQA_E_INVALID, "tuning is null");
+    return tuning_from_env(t);
+}
+
+int vqa_index_set_tuning(vqa_index_t *h, const vqa_tuning_t *t) {
+    if (!h) return fail(VQA_E_INVALID, "null index handle");
+    int rc = tuning_validate(t);
+    if (rc) return rc;
+    const bool remap = t->tma_l2promo != h->tune.tma_l2promo;
+    h->tune = *t;
+    invalidate_plans(h);
+    if (remap && h->rows) build_tmaps(h);
+    return VQA_OK;
+}
+
+int vqa_index_get_tuning(const vqa_index_t *h, vqa_tuning_t *t) {
+    if (!h || !t) return fail(VQA_E_INVALID, "null argument");
+    *t = h->tune;
     return VQA_OK;
 }
 
@@ -388,28 +543,8 @@ int vqa_index_bind(vqa_index_t *h, const void *rows_dev, int64_t n_rows, int64_t
     if (reinterpret_cast<uintptr_t>(rows_dev) % 16 != 0) return fail(VQA_E_INVALID, "rows_dev must be 16-byte aligned");
     h->rows = rows_dev;
     h->stride = row_stride_bytes;
-    h->tmap_ok = false;
-    if (n_rows > 0 && es == 2 && h->dim % 64 == 0) {
-        EncodeTiledFn enc = get_encode_fn();
-        if (enc) {
-            bool ok = true;
-            for (int j = 0; j < 4 && ok; ++j) {
-                cuuint64_t gdim[2] = {(cuuint64_t)h->dim, (cuuint64_t)n_rows};
-                cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
-                cuuint32_t box[2] = {(cuuint32_t)vqa::kBlockK, (cuuint32_t)(vqa::kTileRows >> j)};
-                cuuint32_t estr[2] = {1, 1};
-                CUresult r = enc(&h->tmap[j], h->dtype == VQA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                                 2, const_cast<void *>(rows_dev), gdim, gstride, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 (CUtensorMapL2promotion)env_int("VQA_TMA_L2PROMO", (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                ok = (r == CUDA_SUCCESS);
-            }
-            h->tmap_ok = ok;
-        }
-    }
-    return VQA_OK;
+    invalidate_plans(h);
+    return build_tmaps(h);
 }
 
 int vqa_index_destroy(vqa_index_t *h) {
@@ -432,8 +567,9 @@ int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t 
     return VQA_OK;
 }
 
-int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k, int32_t mode,
-                      int32_t sm_count, int32_t max_smem, int32_t *out, size_t *smem_bytes) {
+int vqa_plan_describe_tuned(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k, int32_t mode,
+                            int32_t sm_count, int32_t max_smem, const vqa_tuning_t *tuning, int32_t *out,
+                            size_t *smem_bytes) {
     if (!out || !smem_bytes) return fail(VQA_E_INVALID, "null output pointer");
     const int es = elem_size(dtype);
     if (!es) return fail(VQA_E_INVALID, "row dtype must be F32, BF16 or F16 (got %d)", dtype);
@@ -447,10 +583,13 @@ int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_quer
     fake.sm_count = sm_count;
     fake.max_smem = max_smem;
     fake.tmap_ok = n_rows > 0 && es == 2 && dim % 64 == 0;  // what vqa_index_bind would have built
-    int rc = check_search_args(&fake, n_queries, k);
+    int rc = tuning ? tuning_validate(tuning) : tuning_from_env(&fake.tune);
+    if (rc) return rc;
+    if (tuning) fake.tune = *tuning;
+    rc = check_search_args(&fake, n_queries, k);
     if (rc) return rc;
     Plan pl;
-    rc = make_plan(&fake, n_queries, k, mode, &pl);
+    rc = make_plan_uncached(&fake, n_queries, k, mode, &pl);
     if (rc) return rc;
     for (int i = 0; i < 16; ++i) out[i] = 0;
     out[0] = pl.family;
@@ -462,7 +601,7 @@ int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_quer
     out[6] = pl.ncol;
     *smem_bytes = 0;
     if (pl.family == VQA_MODE_FAST_TS) {
-        const int kscan = pl.ts_split ? k : k + spare_ranks();
+        const int kscan = pl.ts_split ? k : k + spare_ranks(&fake);
         const int nq_launch = n_queries < pl.groups * pl.pass_nq ? n_queries : pl.groups * pl.pass_nq;
         out[7] = pl.ts_split;
         out[8] = pl.ts_qs;
@@ -473,7 +612,7 @@ int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_quer
         out[13] = (dim / vqa::kBlockK - pl.ts_ks) * (vqa::kBlockK / 2);  // query block; the rest are accumulators
         *smem_bytes = vqa::ts_smem_bytes(kscan, pl.stages * pl.kps, pl.ts_split, pl.ts_ks, nq_launch, pl.ts_qs);
     } else if (pl.family == VQA_MODE_FAST_TENSOR) {
-        const int kscan = pl.ss_split ? k : k + spare_ranks();
+        const int kscan = pl.ss_split ? k : k + spare_ranks(&fake);
         out[7] = pl.ss_split;
         out[10] = kscan;
         out[11] = pl.ss_split ? kscan : 32;
@@ -484,6 +623,11 @@ int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_quer
         out[11] = k;
     }
     return VQA_OK;
+}
+
+int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k, int32_t mode,
+                      int32_t sm_count, int32_t max_smem, int32_t *out, size_t *smem_bytes) {
+    return vqa_plan_describe_tuned(n_rows, dim, dtype, n_queries, k, mode, sm_count, max_smem, nullptr, out, smem_bytes);
 }
 
 int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode, size_t *bytes) {
@@ -527,13 +671,17 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     unsigned long long *slot_g = reinterpret_cast<unsigned long long *>(
         (reinterpret_cast<uintptr_t>(tau_g + n_queries) + 255) & ~(uintptr_t)255);  // [n_queries][32]
     const long long cand_stride = (long long)n_queries * k;
+    vqa::ReduceOpts ropts;
+    ropts.select = h->tune.reduce_select;
+    ropts.early = h->tune.reduce_early;
+    ropts.trigger_early = h->tune.pdl_chain;
     static std::atomic<uint32_t> g_epoch{1};
     const uint32_t epoch = g_epoch.fetch_add(2, std::memory_order_relaxed);  // odd, unique, never 0 (0 = cleared slot)
 
     if (pl.family == VQA_MODE_FAST_TS && h->n_rows > 0) {
         // list length inside the scan: with screen-then-rescore a few spare ranks absorb the reordering
         // that the queries' storage rounding can cause (score error ~5e-5 against rank gaps of ~7e-4)
-        const int kscan = pl.ts_split ? k : k + spare_ranks();
+        const int kscan = pl.ts_split ? k : k + spare_ranks(h);
         const long long cstride = (long long)n_queries * kscan;
         const int per_launch = pl.groups * pl.pass_nq;
         const long long tiles = (h->n_rows + 63) / 64;
@@ -557,7 +705,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.a_fp16 = pl.ts_afp16;
             a.qs = pl.ts_qs;
             a.ks = pl.ts_ks;
-            a.pdl = (l0 > 0 && pdl_chain_enabled()) ? 1 : 0;
+            a.pdl = (l0 > 0 && h->tune.pdl_chain) ? 1 : 0;
             a.stages = pl.stages;
             a.kps = pl.kps;
             a.grid = (int)streams * g;
@@ -588,7 +736,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
                                        kscan, pl.ts_split ? kscan : (kscan > 32 ? vqa::kMaxK : 32), h->first_id,
                                        out_scores_dev + (long long)l0 * k,
                                        (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
-                                       pl.ts_split ? nullptr : &rs);
+                                       ropts, pl.ts_split ? nullptr : &rs);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;
@@ -597,11 +745,11 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     if (pl.family == VQA_MODE_FAST_TENSOR && h->n_rows > 0) {
         // Each launch covers up to groups * pass_nq queries: CTA c scans tile stream c / g for query chunk
         // c % g, so one pass over HBM serves the whole launch; its candidate lists are reduced right away.
-        const int kscan = pl.ss_split ? k : k + spare_ranks();  // list length inside the scan
+        const int kscan = pl.ss_split ? k : k + spare_ranks(h);  // list length inside the scan
         const long long cstride = (long long)n_queries * kscan;
         const int per_launch = pl.groups * pl.pass_nq;
         const long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
-        const bool use_mc = env_int("VQA_MMA_MULTICAST", 1) != 0;
+        const bool use_mc = h->tune.mma_multicast != 0;
         for (int l0 = 0; l0 < n_queries; l0 += per_launch) {
             const int nq = n_queries - l0 < per_launch ? n_queries - l0 : per_launch;
             const int chunks = (nq + pl.pass_nq - 1) / pl.pass_nq;
@@ -614,12 +762,18 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             long long streams = h->sm_count / g;
             if (mc) {
                 const int slot = pl.ncol == 16 ? 0 : (pl.ncol == 32 ? 1 : (pl.ncol == 64 ? 2 : 3));
-                int &cached = h->max_clusters[lg][slot];
+                int cached;
+                {
+                    std::lock_guard<std::mutex> lk(h->mu);
+                    cached = h->max_clusters[lg][slot];
+                }
                 if (cached == 0) {
                     cached = vqa::mma_max_active_clusters(
                         h->dtype == VQA_BF16, pl.ncol, pl.ss_split, g,
                         vqa::mma_smem_bytes_rt(pl.ncol, h->dim, kscan, pl.stages * pl.kps, pl.ss_split));
                     if (cached <= 0) cached = -1;
+                    std::lock_guard<std::mutex> lk(h->mu);
+                    h->max_clusters[lg][slot] = cached;
                 }
                 if (cached > 0 && cached < streams) streams = cached;
             }
@@ -647,9 +801,10 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.tau_g = tau_g + l0;
             a.epoch = epoch;
             // opt-in tournament bound: register-list path only (<= 32 queries per CTA, list length <= 32)
-            const bool tb = mma_tb_enabled() && pl.pass_nq <= 32 && kscan <= 32;
+            const bool tb = h->tune.mma_tb != 0 && pl.pass_nq <= 32 && kscan <= 32;
             a.slot_g = tb ? slot_g + (long long)l0 * 32 : nullptr;
-            a.pdl = (l0 > 0 && pdl_chain_enabled()) ? 1 : 0;
+            a.pdl = (l0 > 0 && h->tune.pdl_chain) ? 1 : 0;
+            a.tma_hint = h->tune.tma_hint;
             cudaError_t e = vqa::launch_mma(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
             vqa::Rescore rs;
@@ -663,7 +818,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, pl.ss_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
                                        (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
-                                       pl.ss_split ? nullptr : &rs, a.slot_g);
+                                       ropts, pl.ss_split ? nullptr : &rs, a.slot_g);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;
@@ -705,7 +860,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
         }
     }
     cudaError_t e = vqa::launch_reduce_u32(cand_s, cand_i, cand_stride, k, n_lists, k, k, h->first_id, out_scores_dev,
-                                           (long long *)out_ids_dev, n_queries, nullptr, 1, 1, st);
+                                           (long long *)out_ids_dev, n_queries, nullptr, 1, 1, st, ropts);
     if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
     return VQA_OK;
 }

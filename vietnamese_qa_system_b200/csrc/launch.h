@@ -49,6 +49,7 @@ struct MmaLaunch {
     uint32_t epoch;
     unsigned long long *slot_g = nullptr;  // opt-in TB variants: [nq][32] tournament slots (see MmaParams), else nullptr
     int pdl = 0;  // opt-in: launch with programmatic stream serialization (2nd+ scan of one search, see mma_launch.cu)
+    int tma_hint = 1;  // L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last
 };
 
 struct TsLaunch {
@@ -98,11 +99,18 @@ struct Rescore {
     int k_final = 0;
 };
 
+// kernel-selection knobs of the candidate reduce (from the handle's vqa_tuning_t; never from the environment)
+struct ReduceOpts {
+    int select = 0;         // radix-select kernel for k_out > 32 and for re-scoring reduces
+    int early = 0;          // early exit over sorted internal lists (k_out <= 32 warp kernel)
+    int trigger_early = 0;  // release PDL dependents at once (the next scan of the same search does not read our output)
+};
+
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr,
-                              unsigned long long *slot_reset = nullptr);
+                              int list_mod, int queries_per_group, cudaStream_t st, const ReduceOpts &opts,
+                              const Rescore *rs = nullptr, unsigned long long *slot_reset = nullptr);
 struct WaitFlags {
     const unsigned long long *flags = nullptr;
     int n = 0;

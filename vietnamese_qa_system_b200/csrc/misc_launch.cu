@@ -5,7 +5,6 @@
 #include "pool.cuh"
 #include "scan.cuh"
 
-#include <cstdlib>
 
 namespace vqa {
 
@@ -24,17 +23,14 @@ template <typename IdT>
 static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long long list_stride,
                                    long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                                    float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                                   int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs = nullptr,
-                                   const WaitFlags *wf = nullptr, unsigned long long *slot_reset = nullptr) {
+                                   int list_mod, int queries_per_group, cudaStream_t st, const ReduceOpts &opts,
+                                   const Rescore *rs = nullptr, const WaitFlags *wf = nullptr,
+                                   unsigned long long *slot_reset = nullptr) {
     ReduceParams<IdT> p;
     p.slot_reset = k_out <= 32 ? slot_reset : nullptr;
-    {
-        const char *ee = std::getenv("VQA_REDUCE_EARLY");  // opt-in until timed on a B200
-        // internal (u32 row id) lists only: the scans emit them sorted; the public merge API does not require it
-        p.early_exit = (sizeof(IdT) == 4 && ee != nullptr && std::atoi(ee) != 0) ? 1 : 0;
-        const char *pc = std::getenv("VQA_PDL_CHAIN");
-        p.trigger_early = (sizeof(IdT) == 4 && pc != nullptr && std::atoi(pc) != 0) ? 1 : 0;
-    }
+    // internal (u32 row id) lists only: the scans emit them sorted; the public merge API does not require it
+    p.early_exit = (sizeof(IdT) == 4 && opts.early) ? 1 : 0;
+    p.trigger_early = (sizeof(IdT) == 4 && opts.trigger_early) ? 1 : 0;
     p.wait_flags = wf ? wf->flags : nullptr;
     p.wait_n = wf ? wf->n : 0;
     p.wait_epoch = wf ? wf->epoch : 0;
@@ -70,15 +66,14 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if constexpr (sizeof(IdT) == 4) {
-        // radix-select reduce (scan.cuh): opt-in until it has been timed on a B200 (VQA_REDUCE_SELECT=1);
+        // radix-select reduce (scan.cuh; default on since the round-2 timings, vqa_tuning_t::reduce_select):
         // needs every candidate of a query in shared memory at once and no peer flags to wait for.
         // Taken for k_out > 32, and for the screen-then-rescore reduce of any k_out: one CTA per query re-scores
         // the survivors with coalesced row reads, one warp per candidate (the warp-per-query kernel reads 32 cold
         // rows with one lane each: 63 us per 128 queries on the B200).
         const long long n_cand = (long long)(n_lists / (list_mod > 1 ? list_mod : 1)) * k_in;
         const size_t smem = select_smem_bytes(n_cand);
-        const char *env = std::getenv("VQA_REDUCE_SELECT");
-        if (env != nullptr && std::atoi(env) != 0 && wf == nullptr && smem <= kSelectSmemLimit &&
+        if (opts.select && wf == nullptr && smem <= kSelectSmemLimit &&
             (k_out > 32 || (rs != nullptr && p.slot_reset == nullptr))) {
             cudaError_t e = cudaFuncSetAttribute(reduce_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -104,17 +99,17 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
-                              int list_mod, int queries_per_group, cudaStream_t st, const Rescore *rs,
-                              unsigned long long *slot_reset) {
+                              int list_mod, int queries_per_group, cudaStream_t st, const ReduceOpts &opts,
+                              const Rescore *rs, unsigned long long *slot_reset) {
     return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
-                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, rs, nullptr, slot_reset);
+                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, opts, rs, nullptr, slot_reset);
 }
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out,
                               long long id_base, float *out_s, long long *out_i, int n_queries, cudaStream_t st,
                               const WaitFlags *wf) {
     return launch_reduce_t<long long>(cand_s, cand_i, list_stride, list_stride_i, query_stride, n_lists, k_in, k_out, id_base,
-                                      out_s, out_i, n_queries, nullptr, 1, 1, st, nullptr, wf);
+                                      out_s, out_i, n_queries, nullptr, 1, 1, st, ReduceOpts(), nullptr, wf);
 }
 
 cudaError_t launch_exchange_push(const void *local, size_t bytes, void *const *peer_slots,

@@ -2,19 +2,12 @@
 #include "launch.h"
 #include "mma.cuh"
 
-#include <cstdlib>
 
 namespace vqa {
 
-// L2 policy for the document stream (tuning knob VQA_TMA_HINT: 0 normal, 1 evict-first, 2 evict-last)
-static unsigned long long tma_policy() {
-    static unsigned long long pol = 0;
-    if (!pol) {
-        const char *e = std::getenv("VQA_TMA_HINT");
-        int v = e ? std::atoi(e) : 1;
-        pol = v == 0 ? 0x1000000000000000ull : (v == 2 ? 0x14F0000000000000ull : 0x12F0000000000000ull);
-    }
-    return pol;
+// L2 policy for the document stream (vqa_tuning_t::tma_hint: 0 normal, 1 evict-first, 2 evict-last)
+static unsigned long long tma_policy(int v) {
+    return v == 0 ? 0x1000000000000000ull : (v == 2 ? 0x14F0000000000000ull : 0x12F0000000000000ull);
 }
 
 template <bool BF16, int NCOL, bool SPLIT, bool TB = false>
@@ -39,7 +32,7 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     p.tau_g = a.tau_g;
     p.epoch = a.epoch;
     // side-by-side chunks re-read each tile from L2: keep it there (normal policy) instead of evict-first
-    p.tma_policy = a.n_groups > 1 ? 0x1000000000000000ull : tma_policy();
+    p.tma_policy = a.n_groups > 1 ? 0x1000000000000000ull : tma_policy(a.tma_hint);
     p.multicast = a.multicast;
     p.slot_g = TB ? a.slot_g : nullptr;
     const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps, SPLIT ? 1 : 0);

@@ -75,6 +75,22 @@ class FlatShard:
             lib.vqa_index_destroy(h)
             self._h = None
 
+    # -- kernel-selection knobs (vqa_tuning_t; benchmarks and tests only) --------
+    def get_tuning(self) -> "N.Tuning":
+        t = N.Tuning()
+        N.check(N.lib().vqa_index_get_tuning(self._h, ctypes.byref(t)))
+        return t
+
+    def set_tuning(self, tuning: "Optional[N.Tuning]" = None, **knobs) -> "N.Tuning":
+        """Store knobs in the native handle: ``shard.set_tuning(ts_qs=0, reduce_select=0)`` changes the named
+        fields of the current tuning; ``set_tuning(N.tuning_default())`` replaces it.  The workspace cache is
+        dropped (its size depends on ``ts_extra``).  Must not overlap searches on this shard."""
+        t = tuning if tuning is not None else self.get_tuning()
+        t.update(**knobs)
+        N.check(N.lib().vqa_index_set_tuning(self._h, ctypes.byref(t)))
+        self._ws.clear()
+        return t
+
     # -- planning / workspace -------------------------------------------------
     def plan(self, n_queries: int, k: int, mode="fast") -> Tuple[int, int]:
         fam, nl = ctypes.c_int32(), ctypes.c_int32()
@@ -82,7 +98,10 @@ class FlatShard:
         return fam.value, nl.value
 
     def workspace(self, n_queries: int, k: int, mode: int) -> torch.Tensor:
-        key = (n_queries, k)
+        """Scratch (candidate lists, thresholds) of one search, cached per (B, k, CUDA stream): searches issued
+        on different streams run concurrently and must not share candidate buffers (include/vqa.h, threading).
+        Two host threads searching on the SAME stream must pass their own ``workspace=`` to ``search``."""
+        key = (n_queries, k, _stream(self.device))
         ws = self._ws.get(key)
         if ws is None:
             need = ctypes.c_size_t()
@@ -91,10 +110,17 @@ class FlatShard:
             self._ws[key] = ws
         return ws
 
+    def workspace_bytes(self, n_queries: int, k: int, mode="fast") -> int:
+        need = ctypes.c_size_t()
+        N.check(N.lib().vqa_workspace_bytes(self._h, n_queries, k, mode_id(mode), ctypes.byref(need)))
+        return int(need.value)
+
     # -- search ---------------------------------------------------------------
     def search(self, queries: torch.Tensor, k: int, mode="fast", out_scores: Optional[torch.Tensor] = None,
-               out_ids: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """queries: float32 [B, dim] CUDA, L2-normalised.  Returns (scores f32 [B,k], ids i64 [B,k])."""
+               out_ids: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """queries: float32 [B, dim] CUDA, L2-normalised.  Returns (scores f32 [B,k], ids i64 [B,k]).
+        ``workspace``: caller-owned uint8 scratch of ``workspace_bytes(B, k)`` (default: per-stream cache)."""
         _need_cuda(queries, "queries")
         if queries.dtype != torch.float32:
             raise ValueError(f"queries must be float32; got {queries.dtype}")
@@ -110,7 +136,7 @@ class FlatShard:
             out_scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
         if out_ids is None:
             out_ids = torch.empty((b, k), dtype=torch.int64, device=self.device)
-        ws = self.workspace(b, k, m)
+        ws = workspace if workspace is not None else self.workspace(b, k, m)
         q_stride = queries.stride(0) if b > 1 else self.dim
         N.check(N.lib().vqa_search(self._h, ctypes.c_void_p(queries.data_ptr()), q_stride, b, k, m,
                                    ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(out_ids.data_ptr()),
@@ -124,7 +150,7 @@ class FlatShard:
             raise ValueError("queries_host must be a contiguous float32 CPU tensor")
         b = int(queries_host.shape[0])
         m = mode_id(mode)
-        key = ("host", b, k)
+        key = ("host", b, k, _stream(self.device))
         st = self._ws.get(key)
         if st is None:
             need = ctypes.c_size_t()
