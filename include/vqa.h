@@ -374,6 +374,17 @@ VQA_API int vqa_hybrid_fuse(const float *dense_scores_dev, const int64_t *dense_
                             int32_t n_queries, double w_dense, double w_sparse, int32_t limit,
                             double *out_scores_dev, int64_t *out_ids_dev, int32_t device, void *stream);
 
+/*
+ * Reciprocal-rank fusion of the same two candidate lists: fused[id] = 0.0 + (1.0 / (rank_dense + 1)) * w_dense
+ * (+ (1.0 / (rank_sparse + 1)) * w_sparse), rank = position in the leg's own list.  What txtai's Search does
+ * instead of the weighted score sum when the scoring index is not normalised (raw BM25 scores are unbounded).
+ * In both fusions a leg whose weight is <= 0 is ignored (txtai: `scores if weights[v] > 0 else []`).
+ */
+VQA_API int vqa_hybrid_fuse_rrf(const int64_t *dense_ids_dev, int32_t k_dense, const int64_t *sparse_ids_dev,
+                                int32_t k_sparse, int32_t n_queries, double w_dense, double w_sparse,
+                                int32_t limit, double *out_scores_dev, int64_t *out_ids_dev, int32_t device,
+                                void *stream);
+
 /* The agreement rule (heavy_ranker.py:110) on float64 scores -- what hybrid indexes return. */
 VQA_API int vqa_agree_f64(const int64_t *ids_a_dev, const double *scores_a_dev, const int64_t *ids_b_dev,
                           const double *scores_b_dev, int64_t n, double threshold, uint8_t *accept_dev,

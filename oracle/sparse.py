@@ -148,14 +148,20 @@ class BM25:
         return scores
 
 
-def hybrid(dense: List[Tuple[int, float]], sparse: List[Tuple[int, float]], limit: int, weights=0.5):
-    """txtai ``Search`` fusion of one query's dense and sparse candidate lists."""
+def hybrid(dense: List[Tuple[int, float]], sparse: List[Tuple[int, float]], limit: int, weights=0.5,
+           normalized: bool = True):
+    """txtai ``Search`` fusion of one query's dense and sparse candidate lists (recalled txtai 6.x
+    embeddings/search/base.py): weighted score sum when the scoring index is normalised,
+    reciprocal-rank fusion ``1 / (rank + 1) * weight`` otherwise; a leg whose weight is not > 0 is skipped."""
     if isinstance(weights, (int, float)):
         weights = [weights, 1 - weights]
     uids: Dict[int, float] = {}
     for v, scores in enumerate((dense, sparse)):
-        for uid, score in scores:
+        for r, (uid, score) in enumerate(scores if weights[v] > 0 else []):
             if uid not in uids:
                 uids[uid] = 0.0
-            uids[uid] += score * weights[v]
+            if normalized:
+                uids[uid] += score * weights[v]
+            else:
+                uids[uid] += (1.0 / (r + 1)) * weights[v]
     return sorted(uids.items(), key=lambda x: x[1], reverse=True)[:limit]

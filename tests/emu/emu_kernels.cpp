@@ -114,9 +114,9 @@ int emu_bm25_weights(const long long *offsets, long long n_terms, const int *doc
 }
 
 int emu_hybrid_fuse(const float *ds, const long long *di, int kd, const double *ss, const long long *si, int ks,
-                    int n_queries, double wd, double wsp, int limit, double *out_s, long long *out_i) {
+                    int n_queries, double wd, double wsp, int limit, int rrf, double *out_s, long long *out_i) {
     return guarded([&] {
-        if (vqa::launch_hybrid_fuse(ds, di, kd, ss, si, ks, n_queries, wd, wsp, limit, out_s, out_i, nullptr) !=
+        if (vqa::launch_hybrid_fuse(ds, di, kd, ss, si, ks, n_queries, wd, wsp, limit, rrf, out_s, out_i, nullptr) !=
             cudaSuccess)
             throw std::runtime_error("launch failed");
     });

@@ -31,7 +31,7 @@ def _emu_lib():
     L.emu_sparse_search.argtypes = [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32,
                                     _vp, _vp]
     L.emu_bm25_weights.argtypes = [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp]
-    L.emu_hybrid_fuse.argtypes = [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _dbl, _dbl, _i32, _vp, _vp]
+    L.emu_hybrid_fuse.argtypes = [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _dbl, _dbl, _i32, _i32, _vp, _vp]
     L.emu_pool_normalize.argtypes = [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
     return L
 
@@ -145,15 +145,17 @@ def test_emulated_hybrid_fuse(emu):
     spi = np.stack([rng.choice(40, ks, replace=False) for _ in range(b)]).astype(np.int64)
     spi[2, 4:], ss[2, 4:] = -1, -np.inf
     ds[3, :], ss[3, :] = 0.5, 0.5
-    for limit, w in ((1, 0.5), (5, 0.7), (20, 0.0)):
-        out_s, out_i = np.empty((b, limit), np.float64), np.empty((b, limit), np.int64)
-        ok(emu, emu.emu_hybrid_fuse(ptr(ds), ptr(di), kd, ptr(ss), ptr(spi), ks, b, w, 1 - w, limit, ptr(out_s),
-                                    ptr(out_i)))
-        for r in range(b):
-            dense = [(int(i), float(s)) for i, s in zip(di[r], ds[r]) if i >= 0]
-            sparse = [(int(i), float(s)) for i, s in zip(spi[r], ss[r]) if i >= 0]
-            got = [(int(i), float(s)) for i, s in zip(out_i[r], out_s[r]) if i >= 0]
-            assert got == osp.hybrid(dense, sparse, limit, w), (r, limit, w)
+    # weighted score sum (normalised sparse scores) and reciprocal-rank fusion (raw BM25); weights 0 / 1 skip a leg
+    for rrf in (0, 1):
+        for limit, w in ((1, 0.5), (5, 0.7), (20, 0.0), (20, 1.0), (7, 0.25)):
+            out_s, out_i = np.empty((b, limit), np.float64), np.empty((b, limit), np.int64)
+            ok(emu, emu.emu_hybrid_fuse(ptr(ds), ptr(di), kd, ptr(ss), ptr(spi), ks, b, w, 1 - w, limit, rrf, ptr(out_s),
+                                        ptr(out_i)))
+            for r in range(b):
+                dense = [(int(i), float(s)) for i, s in zip(di[r], ds[r]) if i >= 0]
+                sparse = [(int(i), float(s)) for i, s in zip(spi[r], ss[r]) if i >= 0]
+                got = [(int(i), float(s)) for i, s in zip(out_i[r], out_s[r]) if i >= 0]
+                assert got == osp.hybrid(dense, sparse, limit, w, normalized=not rrf), (r, limit, w, rrf)
 
 
 def _to_storage(x, kind):

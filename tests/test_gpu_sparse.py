@@ -162,7 +162,7 @@ def corpus_texts(n):
     return out
 
 
-def oracle_hybrid(e, texts, queries, limit, weights=0.5):
+def oracle_hybrid(e, texts, queries, limit, weights=0.5, normalize=True):
     """Dense leg: canonical fp32 oracle on the index's own stored rows / normalised queries; sparse leg and
     fusion: oracle/sparse.py."""
     docs = e.ann.shard.rows.cpu().numpy()
@@ -170,11 +170,11 @@ def oracle_hybrid(e, texts, queries, limit, weights=0.5):
     cand = limit * 10
     kd = min(cand, len(texts))
     s, i = oracle.search(docs, qs, kd, oracle.CANONICAL, "fp32")
-    ref = osp.BM25().index([osp.tokenize(t) for t in texts])
+    ref = osp.BM25(normalize=normalize).index([osp.tokenize(t) for t in texts])
     out = []
     for b, q in enumerate(queries):
         dense = [(int(p), float(x)) for p, x in zip(i[b], s[b]) if p >= 0]
-        out.append(osp.hybrid(dense, ref.search(q, cand), limit, weights))
+        out.append(osp.hybrid(dense, ref.search(q, cand), limit, weights, normalized=normalize))
     return out
 
 
@@ -203,6 +203,28 @@ def test_embeddings_hybrid_matches_oracle(tmp_path):
         e.search(texts[0], 13)                                               # 130 dense candidates > 128
     with pytest.raises(ValueError):
         e.search(np.zeros(384, np.float32), 1)                               # the sparse leg needs text
+
+
+def test_embeddings_hybrid_unnormalised_scoring_fuses_by_reciprocal_rank():
+    """txtai fuses by weighted score sum only when the scoring index is normalised; `scoring="bm25"` next to a dense
+    index (raw, unbounded BM25 scores) is fused by reciprocal rank, and weights 1 / 0 give the single-leg answer."""
+    texts = corpus_texts(900)
+    e = Embeddings(scoring="bm25", content=True, transform=FakeEncoder(384), dtype="fp32")
+    e.index([{"id": i + 1, "text": t} for i, t in enumerate(texts)])
+    assert e.scoring is not None and e.scoring.normalize is False and e.ann is not None
+    queries = [texts[10], "phở bún chả", "mã5 hà nội", "không-có-từ-nào"]
+    for limit, w in ((1, None), (4, 0.7), (10, 1.0), (10, 0.0), (3, [0.3, 0.3])):
+        got = e.batchsearch(queries, limit, w) if w is not None else e.batchsearch(queries, limit)
+        want = oracle_hybrid(e, texts, queries, limit, 0.5 if w is None else w, normalize=False)
+        for g, wv in zip(got, want):
+            assert [(r["id"], r["score"]) for r in g] == [(p + 1, s) for p, s in wv], (limit, w)
+    h = Embeddings(hybrid=True, content=True, transform=FakeEncoder(384), dtype="fp32")   # normalised: weights 1 / 0
+    h.index([{"id": i + 1, "text": t} for i, t in enumerate(texts)])
+    for w in (1.0, 0.0):
+        got = h.batchsearch(queries, 5, w)
+        want = oracle_hybrid(h, texts, queries, 5, w)
+        for g, wv in zip(got, want):
+            assert [(r["id"], r["score"]) for r in g] == [(p + 1, s) for p, s in wv], w
 
 
 def test_embeddings_keyword_only_index():

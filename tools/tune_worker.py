@@ -1,4 +1,6 @@
-"""One timing run; knobs come from the environment (ROWS, BATCHES, MODE, K, VQA_*)."""
+"""One timing run; shape from the environment (ROWS, DIM, DTYPE, BATCHES, MODE, K), kernel variants as
+VARIANTS="-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1,VQA_MMA_TB=1": each is applied to the ONE generated index through
+FlatShard.set_tuning (the library reads its environment only in vqa_index_create; "-" = the handle as created)."""
 import json
 import os
 import sys
@@ -6,7 +8,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vietnamese_qa_system_b200 import ops  # noqa: E402
+from vietnamese_qa_system_b200 import _native as N, ops  # noqa: E402
 
 n, d = int(os.environ.get("ROWS", "4000000")), int(os.environ.get("DIM", "768"))
 k = int(os.environ.get("K", "10"))
@@ -23,19 +25,14 @@ iters = int(os.environ.get("ITERS", "20"))
 mode = os.environ.get("MODE", "tensor")
 batches = [int(x) for x in os.environ.get("BATCHES", "8,32").split(",")]
 queries = {b: ops.normalize_rows(torch.randn((b, d), generator=g, device=dev)) for b in batches}
-# VARIANTS="-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1,VQA_MMA_TB=1": several knob settings timed on ONE generated index
-# ("-" = the environment as given).  The library reads its knobs at call time.
 variants = [v for v in os.environ.get("VARIANTS", "-").split(";") if v]
-base_env = dict(os.environ)
+base = shard.get_tuning()
 out = {}
 for var in variants:
-    os.environ.clear()
-    os.environ.update(base_env)
+    t = N.Tuning.from_buffer_copy(bytes(base))
     if var != "-":
-        for kv in var.split(","):
-            key, val = kv.split("=", 1)
-            os.environ[key] = val
-    shard._ws.clear()  # workspace size depends on VQA_TS_EXTRA
+        t.update(**dict(kv.split("=", 1) for kv in var.split(",")))
+    shard.set_tuning(t)
     res = {}
     try:
         for b in batches:
@@ -58,6 +55,7 @@ for var in variants:
                 a, r = i1.cpu().tolist(), i0.cpu().tolist()
                 res[b]["recall"] = round(sum(len(set(x) & set(y)) for x, y in zip(a, r)) / (len(r) * k), 5)
                 res[b]["max_rel_err"] = float(((s1 - s0).abs() / s0.abs().clamp_min(1e-3)).max())
+            res[b]["family"] = shard.plan(b, k, mode)[0]
     except Exception as exc:  # noqa: BLE001 - report and go on to the next variant
         res["error"] = f"{type(exc).__name__}: {exc}"[:300]
     out[var] = res

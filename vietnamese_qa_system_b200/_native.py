@@ -31,7 +31,7 @@ EXPORTS = [
     "vqa_search_plan", "vqa_plan_describe", "vqa_plan_describe_tuned",
     "vqa_tuning_default", "vqa_tuning_from_env", "vqa_index_set_tuning", "vqa_index_get_tuning",
     "vqa_sparse_limits", "vqa_sparse_create", "vqa_sparse_bind", "vqa_sparse_destroy", "vqa_bm25_weights",
-    "vqa_sparse_workspace_bytes", "vqa_sparse_search", "vqa_hybrid_fuse", "vqa_agree_f64",
+    "vqa_sparse_workspace_bytes", "vqa_sparse_search", "vqa_hybrid_fuse", "vqa_hybrid_fuse_rrf", "vqa_agree_f64",
 ]
 
 ABI_VERSION = 120  # VQA_VERSION this binding was written against (include/vqa.h)
@@ -148,6 +148,8 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_agree_f64.argtypes = [vp, vp, vp, vp, i64, c.c_double, vp, vp, i32, vp]
     L.vqa_hybrid_fuse.restype = c.c_int
     L.vqa_hybrid_fuse.argtypes = [vp, vp, i32, vp, vp, i32, i32, c.c_double, c.c_double, i32, vp, vp, i32, vp]
+    L.vqa_hybrid_fuse_rrf.restype = c.c_int
+    L.vqa_hybrid_fuse_rrf.argtypes = [vp, i32, vp, i32, i32, c.c_double, c.c_double, i32, vp, vp, i32, vp]
 
 
 def lib() -> ctypes.CDLL:

@@ -1198,12 +1198,13 @@ int vqa_sparse_search(const vqa_sparse_t *h, const int32_t *q_terms_dev, const f
     return VQA_OK;
 }
 
-int vqa_hybrid_fuse(const float *dense_scores_dev, const int64_t *dense_ids_dev, int32_t k_dense,
-                    const double *sparse_scores_dev, const int64_t *sparse_ids_dev, int32_t k_sparse,
-                    int32_t n_queries, double w_dense, double w_sparse, int32_t limit, double *out_scores_dev,
-                    int64_t *out_ids_dev, int32_t device, void *stream) {
-    if (!dense_scores_dev || !dense_ids_dev || !sparse_scores_dev || !sparse_ids_dev || !out_scores_dev || !out_ids_dev)
+static int hybrid_fuse_impl(const float *dense_scores_dev, const int64_t *dense_ids_dev, int32_t k_dense,
+                            const double *sparse_scores_dev, const int64_t *sparse_ids_dev, int32_t k_sparse,
+                            int32_t n_queries, double w_dense, double w_sparse, int32_t limit, int rrf,
+                            double *out_scores_dev, int64_t *out_ids_dev, int32_t device, void *stream) {
+    if (!dense_ids_dev || !sparse_ids_dev || !out_scores_dev || !out_ids_dev)
         return fail(VQA_E_INVALID, "null device pointer argument");
+    if (!rrf && (!dense_scores_dev || !sparse_scores_dev)) return fail(VQA_E_INVALID, "null score pointer argument");
     if (n_queries < 1) return fail(VQA_E_INVALID, "n_queries must be >= 1");
     if (k_dense < 1 || k_sparse < 1 || k_dense + k_sparse > 2048)
         return fail(VQA_E_INVALID, "k_dense, k_sparse must be >= 1 and sum to <= 2048");
@@ -1213,11 +1214,26 @@ int vqa_hybrid_fuse(const float *dense_scores_dev, const int64_t *dense_ids_dev,
     if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
     cudaError_t e = vqa::launch_hybrid_fuse(dense_scores_dev, reinterpret_cast<const long long *>(dense_ids_dev), k_dense,
                                             sparse_scores_dev, reinterpret_cast<const long long *>(sparse_ids_dev),
-                                            k_sparse, n_queries, w_dense, w_sparse, limit, out_scores_dev,
+                                            k_sparse, n_queries, w_dense, w_sparse, limit, rrf, out_scores_dev,
                                             reinterpret_cast<long long *>(out_ids_dev),
                                             reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(VQA_E_CUDA, "hybrid fuse launch failed: %s", cudaGetErrorString(e));
     return VQA_OK;
+}
+
+int vqa_hybrid_fuse(const float *dense_scores_dev, const int64_t *dense_ids_dev, int32_t k_dense,
+                    const double *sparse_scores_dev, const int64_t *sparse_ids_dev, int32_t k_sparse,
+                    int32_t n_queries, double w_dense, double w_sparse, int32_t limit, double *out_scores_dev,
+                    int64_t *out_ids_dev, int32_t device, void *stream) {
+    return hybrid_fuse_impl(dense_scores_dev, dense_ids_dev, k_dense, sparse_scores_dev, sparse_ids_dev, k_sparse,
+                            n_queries, w_dense, w_sparse, limit, 0, out_scores_dev, out_ids_dev, device, stream);
+}
+
+int vqa_hybrid_fuse_rrf(const int64_t *dense_ids_dev, int32_t k_dense, const int64_t *sparse_ids_dev, int32_t k_sparse,
+                        int32_t n_queries, double w_dense, double w_sparse, int32_t limit, double *out_scores_dev,
+                        int64_t *out_ids_dev, int32_t device, void *stream) {
+    return hybrid_fuse_impl(nullptr, dense_ids_dev, k_dense, nullptr, sparse_ids_dev, k_sparse, n_queries, w_dense,
+                            w_sparse, limit, 1, out_scores_dev, out_ids_dev, device, stream);
 }
 
 int vqa_agree_f64(const int64_t *ids_a_dev, const double *scores_a_dev, const int64_t *ids_b_dev,

@@ -163,7 +163,7 @@ cudaError_t launch_bm25_weights(const long long *offsets, long long n_terms, con
                                 double avgdl, float *weights, cudaStream_t st);
 cudaError_t launch_hybrid_fuse(const float *dense_s, const long long *dense_i, int kd, const double *sparse_s,
                                const long long *sparse_i, int ks, int n_queries, double w_dense, double w_sparse,
-                               int limit, double *out_s, long long *out_i, cudaStream_t st);
+                               int limit, int rrf, double *out_s, long long *out_i, cudaStream_t st);
 
 cudaError_t launch_agree_f64(const long long *ids_a, const double *sa, const long long *ids_b, const double *sb,
                              long long n, double threshold, unsigned char *accept, double *combined, cudaStream_t st);

@@ -460,6 +460,9 @@ __global__ void bm25_weights_kernel(const long long *offsets, long long n_terms,
 // Hybrid fusion (txtai Search): per query, fused[id] = 0.0 + dense * w_dense (+ sparse * w_sparse), in
 // doubles like the Python floats it replaces; order = fused descending, ties keep insertion order
 // (dense candidates first, then sparse-only ones) as Python's stable sort does.  One CTA per query.
+// rrf: the leg's contribution is (1.0 / (rank + 1)) * w instead of score * w (rank = position in the leg's
+// own candidate list) -- what txtai does when the sparse scores are unbounded raw BM25.  A leg whose weight
+// is <= 0 is skipped altogether, as txtai's `scores if weights[v] > 0 else []` does.
 // ---------------------------------------------------------------------------------------------
 struct FuseParams {
     const float *dense_s;
@@ -470,6 +473,7 @@ struct FuseParams {
     int ks;
     double w_dense, w_sparse;
     int limit;
+    int rrf;  // 1: reciprocal-rank fusion (txtai when the scoring index is NOT normalised): 1/(rank+1) * w per leg
     double *out_s;
     long long *out_i;
 };
@@ -486,7 +490,11 @@ __global__ void __launch_bounds__(256) hybrid_fuse_kernel(FuseParams p) {
     const double *ss = p.sparse_s + (size_t)b * p.ks;
     const long long *si = p.sparse_i + (size_t)b * p.ks;
 
-    for (int e = tid; e < n; e += blockDim.x) ids[e] = e < p.kd ? di[e] : si[e - p.kd];
+    const bool use_d = p.w_dense > 0.0, use_s = p.w_sparse > 0.0;
+    for (int e = tid; e < n; e += blockDim.x) {
+        const long long id = e < p.kd ? di[e] : si[e - p.kd];
+        ids[e] = (e < p.kd ? use_d : use_s) ? id : -1;  // a skipped leg is all padding
+    }
     for (int r = tid; r < p.limit; r += blockDim.x) {
         p.out_s[(size_t)b * p.limit + r] = __longlong_as_double(0xfff0000000000000LL);
         p.out_i[(size_t)b * p.limit + r] = -1;
@@ -497,14 +505,17 @@ __global__ void __launch_bounds__(256) hybrid_fuse_kernel(FuseParams p) {
         int ok = id >= 0;
         double f = 0.0;
         if (ok && e < p.kd) {
-            f = __dadd_rn(0.0, __dmul_rn((double)ds[e], p.w_dense));
+            const double c = p.rrf ? __ddiv_rn(1.0, (double)(e + 1)) : (double)ds[e];
+            f = __dadd_rn(0.0, __dmul_rn(c, p.w_dense));
             for (int j = 0; j < p.ks; ++j)
                 if (ids[p.kd + j] == id) {
-                    f = __dadd_rn(f, __dmul_rn(ss[j], p.w_sparse));
+                    const double cs = p.rrf ? __ddiv_rn(1.0, (double)(j + 1)) : ss[j];
+                    f = __dadd_rn(f, __dmul_rn(cs, p.w_sparse));
                     break;
                 }
         } else if (ok) {
-            f = __dadd_rn(0.0, __dmul_rn(ss[e - p.kd], p.w_sparse));
+            const double cs = p.rrf ? __ddiv_rn(1.0, (double)(e - p.kd + 1)) : ss[e - p.kd];
+            f = __dadd_rn(0.0, __dmul_rn(cs, p.w_sparse));
             for (int j = 0; j < p.kd; ++j)
                 if (ids[j] == id) {  // already fused into the dense entry
                     ok = 0;

@@ -76,8 +76,9 @@ cudaError_t launch_bm25_weights(const long long *offsets, long long n_terms, con
 
 cudaError_t launch_hybrid_fuse(const float *dense_s, const long long *dense_i, int kd, const double *sparse_s,
                                const long long *sparse_i, int ks, int n_queries, double w_dense, double w_sparse,
-                               int limit, double *out_s, long long *out_i, cudaStream_t st) {
+                               int limit, int rrf, double *out_s, long long *out_i, cudaStream_t st) {
     FuseParams p;
+    p.rrf = rrf;
     p.dense_s = dense_s;
     p.dense_i = dense_i;
     p.kd = kd;

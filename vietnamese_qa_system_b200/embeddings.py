@@ -101,9 +101,13 @@ class Embeddings:
                 raise ValueError("text input needs an encoder: pass transform=callable or path=<HF model dir>")
             from .vectors import HFEncoder
 
+            # encoderdtype: precision of the HF forward.  Default fp32 = what the reference runs (txtai never
+            # down-casts the encoder); "bf16"/"fp16" trade ~1e-2 relative embedding error for speed.  The key is
+            # part of the config, so it is saved with the index and a reloaded index encodes queries the same way.
             self._encoder = HFEncoder(path, device=self.config.get("device"),
                                       batch=int(self.config.get("encodebatch", 32)),
-                                      maxlength=self.config.get("maxlength"))
+                                      maxlength=self.config.get("maxlength"),
+                                      dtype=self.config.get("encoderdtype", "fp32"))
         return self._encoder
 
     def _device(self) -> torch.device:
@@ -262,7 +266,11 @@ class Embeddings:
             weights = [weights, 1 - weights]
         ds, dp = self.ann.search_tensors(self.batchtransform(queries), kd)
         ss, sp = self.scoring.search_tensors(queries, cand)
-        return ops.hybrid_fuse(ds, dp, ss, sp, min(limit, kd + cand), float(weights[0]), float(weights[1]))
+        # txtai: weighted score sum only when the sparse scores are normalised to [0, 1]; raw BM25 scores are
+        # unbounded, so an un-normalised scoring index is fused by reciprocal rank.  Legs with weight <= 0 are
+        # ignored by the kernel (weights 1 / 0 = the single-leg answer, as in txtai).
+        rrf = not bool(getattr(self.scoring, "normalize", True))
+        return ops.hybrid_fuse(ds, dp, ss, sp, min(limit, kd + cand), float(weights[0]), float(weights[1]), rrf=rrf)
 
     def _resolve(self, hits: List[Tuple[int, float]]):
         """ANN position -> caller's id (a6), and the content join when content=True."""

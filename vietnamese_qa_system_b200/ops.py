@@ -348,9 +348,11 @@ def agree(ids_a: torch.Tensor, scores_a: torch.Tensor, ids_b: torch.Tensor, scor
 
 
 def hybrid_fuse(dense_scores: torch.Tensor, dense_ids: torch.Tensor, sparse_scores: torch.Tensor,
-                sparse_ids: torch.Tensor, limit: int, w_dense: float = 0.5, w_sparse: float = 0.5):
+                sparse_ids: torch.Tensor, limit: int, w_dense: float = 0.5, w_sparse: float = 0.5, rrf: bool = False):
     """Dense + sparse candidate fusion (txtai ``Search`` with ``hybrid=True``; heavy_ranker.py:78-83,98,100):
-    dense [B,kd] float32 / int64, sparse [B,ks] float64 / int64 -> (scores float64 [B,limit], ids int64 [B,limit])."""
+    dense [B,kd] float32 / int64, sparse [B,ks] float64 / int64 -> (scores float64 [B,limit], ids int64 [B,limit]).
+    ``rrf=True``: reciprocal-rank fusion (txtai's rule for un-normalised sparse scores); a leg with weight <= 0
+    is ignored in either fusion."""
     for t, nme in ((dense_scores, "dense_scores"), (dense_ids, "dense_ids"), (sparse_scores, "sparse_scores"),
                    (sparse_ids, "sparse_ids")):
         _need_cuda(t, nme)
@@ -367,6 +369,12 @@ def hybrid_fuse(dense_scores: torch.Tensor, dense_ids: torch.Tensor, sparse_scor
     dev = dense_scores.device
     out_s = torch.empty((b, limit), dtype=torch.float64, device=dev)
     out_i = torch.empty((b, limit), dtype=torch.int64, device=dev)
+    if rrf:
+        N.check(N.lib().vqa_hybrid_fuse_rrf(ctypes.c_void_p(dense_ids.data_ptr()), kd, ctypes.c_void_p(sparse_ids.data_ptr()),
+                                            ks, b, float(w_dense), float(w_sparse), int(limit),
+                                            ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_i.data_ptr()),
+                                            dev.index or 0, ctypes.c_void_p(_stream(dev))))
+        return out_s, out_i
     N.check(N.lib().vqa_hybrid_fuse(ctypes.c_void_p(dense_scores.data_ptr()), ctypes.c_void_p(dense_ids.data_ptr()), kd,
                                     ctypes.c_void_p(sparse_scores.data_ptr()), ctypes.c_void_p(sparse_ids.data_ptr()),
                                     ks, b, float(w_dense), float(w_sparse), int(limit),

@@ -6,6 +6,12 @@ AutoModel forward -> MeanPooling -> normalize.  The encoder forward itself is th
 model's own (out of scope); everything after the last hidden state is
 ``libvqa_b200.so``'s ``vqa_pool_normalize`` (K1).  Inputs are sorted by length and
 batched by ``encodebatch`` (32), order restored, as txtai does.
+
+Precision: the encoder forward runs in **float32** by default, like the reference's
+(txtai / sentence-transformers load the checkpoint as stored and never down-cast).  A
+bf16 forward moves the embeddings by ~1e-2 relative -- enough to flip a top-1 hit or the
+``score_a + score_b > 0.4`` agreement rule (heavy_ranker.py:110) -- so it is opt-in:
+``Embeddings(..., encoderdtype="bf16")``.
 """
 from __future__ import annotations
 
@@ -20,7 +26,7 @@ class HFEncoder:
     normalized = True  # output is already pooled + L2-normalised on device
 
     def __init__(self, path: str, device=None, batch: int = 32, maxlength: Optional[int] = None,
-                 model=None, tokenizer=None, dtype: torch.dtype = torch.bfloat16):
+                 model=None, tokenizer=None, dtype: torch.dtype = torch.float32):
         from . import _native
 
         _native.require_cuda()
@@ -31,6 +37,9 @@ class HFEncoder:
             tokenizer = tokenizer or AutoTokenizer.from_pretrained(path)
             model = model or AutoModel.from_pretrained(path)
         self.tokenizer = tokenizer
+        if isinstance(dtype, str):
+            dtype = ops.DTYPES[dtype.lower()]
+        self.dtype = dtype
         self.model = model.to(self.device, dtype=dtype).eval()
         self.batch = int(batch)
         self.maxlength = maxlength
