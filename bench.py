@@ -3,19 +3,22 @@
 
 Metric (BASELINE.json): queries/sec, top-10, 10M x 768 bf16 documents, on 1/2/4/8 B200.
 A "step" is one pass of the hot path over one batch of B synthetic queries: scan of this
-rank's row shard with fused top-k (+ for N>1: one NCCL all-gather of the [B,k] candidates
-and the merge-top-k kernel).  The index is fixed at 10M rows and row-sharded over the N
-ranks (strong scaling).
+rank's row shard with fused top-k (+ for N>1: the exchange of the [B,k] candidates over
+NVLink and the merge-top-k kernel).  The index is fixed at 10M rows and row-sharded over
+the N ranks (strong scaling).  Steps are independent batches, so for N>1 the exchange +
+merge of step i runs on a side stream under the scan of step i+1 (ShardedFlat.search_pipelined,
+two buffer slots); every step's result is produced inside the timed region.
 
     python bench.py --gpus 1 --steps 200 --warmup 10
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's CPU path, timed on host cores
+    python bench.py --config D ...            # BASELINE configs[3]: 12.5M x 1024 fp16 rows per GPU, B=64, top-100
 
-Prints ONE JSON line on rank 0.  At N = 1 the line also carries secondary sections that are measured AFTER the
-timed steps and never enter `value` / `e2e`: `sweep` (batch sizes), `pool_k1`, `config_a_reference_scale`,
-`hybrid_leg`, and `opt_in_preview` -- the opt-in kernels of DESIGN.md section 3 timed in subprocesses (own CUDA
-context, bounded by a timeout; `--preview 0` skips it).
+Prints ONE JSON line on rank 0.  Secondary sections are measured AFTER the timed steps and never
+enter `value` / `e2e`: `independent_check` (chunked fp32 torch.matmul + topk on the same rows: the one
+checker that is not this repo's code and runs at full size; also the G0 cuBLAS comparator timing),
+`sharded_equals_single` (N>1), `sweep` (batch sizes), `pool_k1`, `config_a_reference_scale`, `hybrid_leg`.
 """
 from __future__ import annotations
 
@@ -55,11 +58,7 @@ def load_peaks():
 # --------------------------------------------------------------------------------------
 # CPU arm: the reference's retrieval path restated (oracle port), all host threads.
 # --------------------------------------------------------------------------------------
-def cpu_sample_qps(batch: int, k: int, budget_s: float, sample_rows: int, seed: int = 1234):
-    """txtai/faiss flat semantics on the host: fp32 sgemm + top-k over a bounded row sample of
-    the 10M x 768 workload; throughput is scaled by sample_rows / N_ROWS (the scan is linear in rows)."""
-    import oracle
-
+def _cpu_threads():
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host threads
     try:
         from threadpoolctl import threadpool_limits
@@ -67,6 +66,14 @@ def cpu_sample_qps(batch: int, k: int, budget_s: float, sample_rows: int, seed: 
         threadpool_limits(limits=os.cpu_count() or 1)
     except Exception:  # noqa: BLE001
         pass
+
+
+def cpu_sample_qps(batch: int, k: int, budget_s: float, sample_rows: int, seed: int = 1234):
+    """txtai/faiss flat semantics on the host: fp32 sgemm + top-k over a bounded row sample of
+    the 10M x 768 workload; throughput is scaled by sample_rows / N_ROWS (the scan is linear in rows)."""
+    import oracle
+
+    _cpu_threads()
     rng = np.random.default_rng(seed)
     docs = rng.standard_normal((sample_rows, DIM), dtype=np.float32)
     docs /= np.linalg.norm(docs, axis=1, keepdims=True)
@@ -85,30 +92,103 @@ def cpu_sample_qps(batch: int, k: int, budget_s: float, sample_rows: int, seed: 
     return qps_sample * (sample_rows / N_ROWS), per_step, reps
 
 
+def cpu_full_steps(batch: int, k: int, rows: int, dim: int, steps: int, warmup: int, block_rows: int = 500_000):
+    """The CPU arm on the WHOLE workload: every step scores `batch` queries against all `rows` documents
+    (block by block: fp32 sgemm + argpartition top-k per block, then a top-k over the blocks' candidates --
+    oracle.np_search_fast per block, i.e. the flat-index semantics of txtai/faiss) and returns seconds per step.
+    The document matrix is held once in host memory when it fits (rows*dim*4 bytes + 25 % < available); otherwise
+    ONE block is generated and scanned rows/block_rows times per step (same flops and the same bytes streamed from
+    DRAM per step -- a 1.5 GB block does not fit any cache)."""
+    import oracle
+
+    _cpu_threads()
+    rng = np.random.default_rng(1234)
+    n_blocks = -(-rows // block_rows)
+    need = rows * dim * 4
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        avail = 0
+    resident = avail > need * 1.25 + (8 << 30)
+    def gen(b):
+        n = min(block_rows, rows - b * block_rows)
+        x = np.random.default_rng(1234 + b).standard_normal((n, dim), dtype=np.float32)  # releases the GIL
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        return x
+
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        blocks = list(ex.map(gen, range(n_blocks if resident else 1)))
+    q = rng.standard_normal((batch, dim), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+
+    def step():
+        cs, ci = [], []
+        for b in range(n_blocks):
+            blk = blocks[b] if resident else blocks[0]
+            n = min(block_rows, rows - b * block_rows)
+            s_, i_ = oracle.np_search_fast(blk[:n], q, k)
+            cs.append(s_)
+            ci.append(i_ + b * block_rows)
+        s_all, i_all = np.concatenate(cs, axis=1), np.concatenate(ci, axis=1)
+        order = np.argsort(-s_all, axis=1, kind="stable")[:, :k]
+        return np.take_along_axis(s_all, order, 1), np.take_along_axis(i_all, order, 1)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps, resident
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_rows = args.cpu_rows
-    steps = max(1, args.steps)
-    # each step = one bounded sample batch; cap total time at a few minutes
-    budget = min(60.0, 0.25 * steps)
-    qps, per_step, reps = cpu_sample_qps(args.batch, TOPK, budget, sample_rows)
-    sample = (f"{sample_rows} of {N_ROWS} rows x {DIM} fp32, B={args.batch}, k={TOPK}; numpy/OpenBLAS sgemm + "
-              f"argpartition top-k (txtai/faiss flat semantics, oracle.np_search_fast); {reps} reps, "
-              f"{per_step * 1e3:.1f} ms each; QPS scaled by rows ratio")
+    cfg = workload(args)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # every step is a FULL pass over the configured index (10 M x 768 fp32 = 30.7 GB resident, ~2 s per step on 16
+    # cores); steps / warm-up are honoured up to a wall-clock cap so that the run ends within a few minutes
+    cap = args.cpu_cap_seconds
+    est_step = cfg["rows_total"] * cfg["dim"] * cfg["batch"] * 2 / 0.6e12 + cfg["rows_total"] * cfg["dim"] * 4 / 20e9
+    run_steps = max(1, min(steps, int(cap * 0.7 / max(est_step, 1e-3))))
+    run_warm = max(1, min(warm, int(cap * 0.2 / max(est_step, 1e-3))))
+    per_step, resident = cpu_full_steps(cfg["batch"], cfg["k"], cfg["rows_total"], cfg["dim"], run_steps, run_warm)
+    qps = cfg["batch"] / per_step
+    sample = (f"FULL workload per step: {cfg['rows_total']} x {cfg['dim']} fp32 rows, B={cfg['batch']}, k={cfg['k']}; "
+              f"numpy/OpenBLAS sgemm + argpartition top-k per 500k-row block + merge (txtai/faiss flat semantics, "
+              f"oracle.np_search_fast); {run_steps} timed steps of {per_step * 1e3:.0f} ms after {run_warm} warm-up "
+              f"({'matrix resident in host memory' if resident else 'one 500k-row block re-scanned per block position'})")
     line = {
-        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": args.batch / qps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"top-{TOPK} over {N_ROWS}x{DIM} docs, batch {args.batch} (CPU arm scans a bounded "
-                               f"row sample)", "rows": N_ROWS, "dim": DIM, "batch": args.batch, "k": TOPK},
+        "impl": "reference", "metric": cfg["metric"], "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "steps_timed": run_steps, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"top-{cfg['k']} exact cosine search over {cfg['rows_total']}x{cfg['dim']} docs, batch "
+                               f"{cfg['batch']}", "rows": cfg["rows_total"], "dim": cfg["dim"], "batch": cfg["batch"],
+                   "k": cfg["k"], "storage": "fp32 on the host (every step scans all rows)"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload(args):
+    """The configuration being measured: the headline (BASELINE metric, configs[2] at N GPUs) or --config D."""
+    world = int(os.environ.get("WORLD_SIZE", "1")) if args.impl == "ours" else max(1, args.gpus)
+    if args.config == "D":
+        rows_total = 12_500_000 * world if args.rows is None else args.rows
+        return {"name": "D", "metric": "queries/sec top-100 @100Mx1024 fp16 docs (12.5M rows per GPU)", "dim": 1024,
+                "dtype": "fp16", "k": 100, "batch": 64 if args.batch is None else args.batch, "rows_total": rows_total,
+                "scaling": "weak"}
+    return {"name": "headline", "metric": METRIC, "dim": DIM, "dtype": "bf16", "k": TOPK,
+            "batch": 32 if args.batch is None else args.batch, "rows_total": N_ROWS if args.rows is None else args.rows,
+            "scaling": "strong"}
 
 
 # --------------------------------------------------------------------------------------
@@ -158,19 +238,6 @@ class ClockSampler(threading.Thread):
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
-
-
-def make_shard(torch, ops, n_local: int, seed: int, device):
-    """i.i.d. N(0,1) rows, L2-normalised in fp32 on device, stored bf16."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    rows = torch.empty((n_local, DIM), dtype=torch.bfloat16, device=device)
-    blk = 500_000
-    for lo in range(0, n_local, blk):
-        n = min(blk, n_local - lo)
-        x = torch.randn((n, DIM), generator=g, device=device, dtype=torch.float32)
-        rows[lo:lo + n] = ops.normalize_rows(x, cast_dtype=torch.bfloat16)
-        del x
-    return rows
 
 
 def synth_postings(n_docs: int, avg_len: int, vocab: int, seed: int = 1):
@@ -249,53 +316,61 @@ def hybrid_leg_section(torch, ops, shard, q_dev, timed, with_cpu: bool):
     return out
 
 
-def opt_in_preview(timeout_s: float = 60.0, budget_s: float = 120.0):
-    """Timings of the OPT-IN kernels (written after round 1's GPU budget was spent, verified on
-    the CPU emulator only) next to the defaults, at the 8-GPU shard size.  Not part of `value` / `e2e`: the default
-    routing never uses them.  Each job runs tools/tune_worker.py in a SUBPROCESS -- its own CUDA context, bounded
-    by a timeout -- after every other measurement is finished, so that a kernel that has never met the hardware
-    cannot take the bench line down with it; a job that fails is reported as {"error": ...}."""
-    import subprocess
+def make_rows(torch, ops, n_local: int, dim: int, dtype, seed: int, device):
+    """i.i.d. N(0,1) rows, L2-normalised in fp32 on device, stored in `dtype`."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    rows = torch.empty((n_local, dim), dtype=dtype, device=device)
+    blk = 500_000
+    for lo in range(0, n_local, blk):
+        n = min(blk, n_local - lo)
+        x = torch.randn((n, dim), generator=g, device=device, dtype=torch.float32)
+        rows[lo:lo + n] = ops.normalize_rows(x, cast_dtype=dtype) if dtype != torch.float32 else ops.normalize_rows(x)
+        del x
+    return rows
 
-    here = os.path.dirname(os.path.abspath(__file__))
-    shard_rows = "1250000"
-    jobs = {
-        "headline_kernel_b1_32_shard": {
-            "ROWS": shard_rows, "K": "10", "MODE": "tensor", "BATCHES": "1,16,32", "ITERS": "50",
-            "VARIANTS": "-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1;VQA_MMA_TB=1,VQA_REDUCE_EARLY=1"},
-        "large_batch_b64_512_shard": {
-            "ROWS": shard_rows, "K": "10", "MODE": "fast", "BATCHES": "64,128,256,512", "ITERS": "20",
-            "VARIANTS": "-;VQA_REDUCE_SELECT=1;VQA_PDL_CHAIN=1;VQA_PDL_CHAIN=1,VQA_REDUCE_SELECT=1;"
-                        "VQA_TS_QS=1,VQA_TS_KS=0;VQA_TS_QS=1,VQA_TS_KS=4,VQA_REDUCE_SELECT=1"},
-        "config_d_like_2M_x_1024_fp16_top100_b64": {
-            "ROWS": "2000000", "DIM": "1024", "DTYPE": "fp16", "K": "100", "MODE": "fast", "BATCHES": "64", "ITERS": "10",
-            "VARIANTS": "-;VQA_REDUCE_SELECT=1;VQA_REDUCE_SELECT=1,VQA_TS_QS=1"},
-    }
-    out = {"note": "opt-in kernels timed in subprocesses after the bench proper; ms = CUDA events around vqa_search, "
-                   "recall / max_rel_err against the fp32 verify kernel; '-' = default routing"}
-    t_start = time.time()
-    scripts = {name: "tune_worker.py" for name in jobs}
-    # default kernels through the new asynchronous host-buffer call: synchronous vs two batches in flight
-    jobs["e2e_host_buffers_sync_vs_two_in_flight_shard"] = {"ROWS": shard_rows, "BATCH": "32", "STEPS": "500"}
-    scripts["e2e_host_buffers_sync_vs_two_in_flight_shard"] = "e2e_pipeline_probe.py"
-    for name, knobs in jobs.items():
-        if time.time() - t_start > budget_s - 20.0:  # keep the whole bench within minutes
-            out[name] = {"skipped": "preview time budget used up"}
-            continue
-        env = {k: v for k, v in os.environ.items()
-               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
-        env.update(knobs)
-        env["CHECK"] = "1"
-        try:
-            r = subprocess.run([sys.executable, os.path.join(here, "tools", scripts[name])], env=env,
-                               capture_output=True, text=True, timeout=timeout_s)
-            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            if r.returncode == 0 and last:
-                out[name] = json.loads(last[-1])
+
+def torch_topk_fp32(torch, rows, q, k: int, first_id: int, chunk: int = 1_000_000):
+    """INDEPENDENT checker (none of this repo's kernels): exact fp32 scores of the stored rows by chunked
+    torch.matmul (TF32 off) + torch.topk, merged over the chunks.  Returns ([B,k] scores, [B,k] global ids)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    best_s, best_i = None, None
+    for lo in range(0, rows.shape[0], chunk):
+        blk = rows[lo:lo + chunk].float()
+        sc = q @ blk.T                                         # [B, chunk] fp32
+        kk = min(k, sc.shape[1])
+        s_, i_ = torch.topk(sc, kk, dim=1)
+        i_ = i_ + (lo + first_id)
+        if best_s is None:
+            best_s, best_i = s_, i_
+        else:
+            cs, ci = torch.cat([best_s, s_], 1), torch.cat([best_i, i_], 1)
+            s2, o2 = torch.topk(cs, min(k, cs.shape[1]), dim=1)
+            best_s, best_i = s2, torch.gather(ci, 1, o2)
+        del blk, sc
+    return best_s, best_i
+
+
+def compare_topk(ids_a, sc_a, ids_b, sc_b, tol: float = 2e-6):
+    """Row-wise comparison of two top-k answers that were computed with different fp32 summation orders: rows with
+    identical id lists; rows whose id SETS are equal (order of near-equal scores swapped); rows that differ only in
+    documents whose scores are within `tol` of the k-th best (a near-tie at the cut); anything else is a mismatch."""
+    ia, ib, sa, sb = (np.asarray(x) for x in (ids_a, ids_b, sc_a, sc_b))
+    out = {"rows": int(ia.shape[0]), "identical": 0, "same_set_order_differs": 0, "near_tie_at_cut": 0, "mismatch": 0}
+    for r in range(ia.shape[0]):
+        if np.array_equal(ia[r], ib[r]):
+            out["identical"] += 1
+        elif set(ia[r].tolist()) == set(ib[r].tolist()):
+            out["same_set_order_differs"] += 1
+        else:
+            cut = min(sa[r][-1], sb[r][-1])
+            only = [s for i, s in zip(ia[r], sa[r]) if i not in set(ib[r].tolist())] + \
+                   [s for i, s in zip(ib[r], sb[r]) if i not in set(ia[r].tolist())]
+            if all(abs(s - cut) <= tol for s in only):
+                out["near_tie_at_cut"] += 1
             else:
-                out[name] = {"error": f"exit {r.returncode}: " + (r.stderr or r.stdout)[-300:]}
-        except Exception as exc:  # noqa: BLE001 - timeout, missing tool, bad JSON: never fatal
-            out[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                out["mismatch"] += 1
+    out["max_abs_score_diff"] = float(np.max(np.abs(np.sort(sa, 1) - np.sort(sb, 1))))
+    out["tolerance"] = tol
     return out
 
 
@@ -318,13 +393,17 @@ def run_ours(args):
     from vietnamese_qa_system_b200 import ops
     from vietnamese_qa_system_b200.sharded import ShardedFlat, shard_bounds
 
+    cfg = workload(args)
+    headline = cfg["name"] == "headline"
+    dim, topk, n_rows = cfg["dim"], cfg["k"], cfg["rows_total"]
+    tdtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[cfg["dtype"]]
     hbm_peak, tf_peak, peak_kind = load_peaks()
-    B, K, W = args.batch, args.steps, max(3, args.warmup)
-    lo, hi = shard_bounds(args.rows, world, rank)
-    rows = make_shard(torch, ops, hi - lo, 1234 + rank, device)
-    index = ShardedFlat(rows, args.rows, mode="fast", exchange=os.environ.get("VQA_EXCHANGE", "nccl"))
+    B, K, W = cfg["batch"], args.steps, max(3, args.warmup)
+    lo, hi = shard_bounds(n_rows, world, rank)
+    rows = make_rows(torch, ops, hi - lo, dim, tdtype, 1234 + rank, device)
+    index = ShardedFlat(rows, n_rows, mode="fast", exchange=os.environ.get("VQA_EXCHANGE", "auto"))
     gq = torch.Generator(device="cpu").manual_seed(4321)
-    q_host_all = torch.randn((max(B, 1024), DIM), generator=gq, dtype=torch.float32)
+    q_host_all = torch.randn((max(B, 1024), dim), generator=gq, dtype=torch.float32)
     q_dev_all = ops.normalize_rows(q_host_all.to(device))
     q_host_all = q_dev_all.cpu().pin_memory()
     q_dev = q_dev_all[:B].contiguous()
@@ -335,14 +414,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warm):
-        for _ in range(warm):
-            fn()
+    def timed(fn, steps, warm, drain=None):
+        """W warm-up calls, then `steps` calls between a barrier + synchronize on both sides, CUDA events on the
+        launching stream, max over ranks.  `fn(i)` gets the step number; `drain()` waits for work still in flight
+        on other streams (pipelined steps) and runs INSIDE the timed region."""
+        for i in range(warm):
+            fn(i)
+        if drain:
+            drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        for i in range(steps):
+            fn(i)
+        if drain:
+            drain()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -352,92 +438,199 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    # ---- headline: inputs resident in HBM -------------------------------------------
-    step = lambda: index.search(q_dev, TOPK)  # noqa: E731
+    # ---- headline: inputs resident in HBM; N>1: exchange + merge of step i under the scan of step i+1 ----------
+    pend = [None, None]
+
+    def step(i):
+        pend[i & 1] = index.search_pipelined(q_dev, topk, i & 1)
+
+    def drain():
+        main = torch.cuda.current_stream()
+        for p_ in pend:
+            if p_ is not None:
+                main.wait_event(p_[2])       # the timed region ends only when every step's merged result exists
+
     sampler = ClockSampler(local_rank)
-    for _ in range(W):
-        step()
+    for i in range(W):
+        step(i)
+    drain()
     barrier()
     sampler.start()
-    total_ms = timed(step, K, 0)
+    total_ms = timed(step, K, 0, drain)
     clocks = sampler.stop()
     ms_per_step = total_ms / K
     value = B * K / (total_ms / 1e3)
+    # the same steps one at a time (scan -> exchange -> merge serialised on one stream): the latency of a single batch
+    serial_ms = timed(lambda i: index.search(q_dev, topk), K, 3) / K
 
     # ---- dominant kernel alone (local scan+select of this rank's shard), same stream ---
     shard = index.shard
-    scan_ms = timed(lambda: shard.search(q_dev, TOPK, "fast"), K, 3) / K
-    fam, launches = shard.plan(B, TOPK, "fast")
-    alg_bytes = (hi - lo) * DIM * 2
+    scan_ms = timed(lambda i: shard.search(q_dev, topk, "fast"), K, 3) / K
+    fam, launches = shard.plan(B, topk, "fast")
+    alg_bytes = (hi - lo) * dim * rows.element_size()
     achieved = alg_bytes / (scan_ms / 1e3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    if os.path.exists(tpath):
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
+    if os.path.exists(tpath):           # dram__bytes_read + dram__bytes_write of ONE launch, from this round's ncu captures
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get(f"n{world}_b{B}")
+                ent = json.load(f).get(f"{cfg['name']}_rows{hi - lo}_b{B}")
+            if ent:
+                traffic, traffic_src = ent["bytes"], ent["source"]
         except Exception:  # noqa: BLE001
             traffic = None
+    kname = {2: "scan_topk_kernel (CUDA cores)", 3: "mma_topk_kernel (tcgen05, queries in smem)",
+             4: "ts_topk_kernel (tcgen05, queries in TMEM)"}.get(fam, str(fam))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "frac_of_8TBs_datasheet": achieved / 8000.0, "traffic": traffic,
-                "peak_kind": peak_kind,
-                "kernel": {3: "mma_topk_kernel (tcgen05)", 4: "ts_topk_kernel (tcgen05)"}.get(fam, "scan_topk_kernel"),
+                "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": kname,
                 "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "kernel_ms is CUDA-event time of vqa_search on this rank's shard: the scan kernel plus the "
-                        "per-query candidate-reduce kernel (<1% of the step)"}
+                "step_frac": alg_bytes / (ms_per_step / 1e3) / 1e9 / hbm_peak,
+                "tensor_frac_of_sustained_peak": 2.0 * B * (hi - lo) * dim / (scan_ms / 1e3) / 1e12 / tf_peak,
+                "note": "kernel_ms = CUDA-event time of vqa_search on this rank's shard (scan kernel + the per-query "
+                        "candidate reduce, which PDL-overlaps the scan's tail); step_frac = the same bytes over the "
+                        "whole step (exchange + merge included)"}
 
-    # ---- e2e: host buffers through the public API, copies inside the timed region ------
+    # ---- e2e: host buffers through the public API, two steps in flight, all copies inside the timed region ------
+    hpend = [None, None]
+    e2e_sink = [0]
+
+    def e2e_step(i):
+        slot = i & 1
+        if hpend[slot] is not None:            # the result of step i-2 is read on the host before its slot is reused
+            hs, hi_, ev = hpend[slot]
+            ev.synchronize()
+            e2e_sink[0] += int(hi_[0, 0])
+        hpend[slot] = index.search_host_pipelined(q_host, topk, slot)
+
+    def e2e_drain():
+        for p_ in hpend:
+            if p_ is not None:
+                p_[2].synchronize()
+                e2e_sink[0] += int(p_[1][0, 0])
+
+    e2e_ms = timed(e2e_step, K, 3, e2e_drain)
     if world == 1:
-        e2e_step = lambda: shard.search_host(q_host, TOPK, "fast")  # noqa: E731
+        sync_ms = timed(lambda i: shard.search_host(q_host, topk, "fast"), K, 3) / K
     else:
-        out_s = torch.empty((B, TOPK), dtype=torch.float32).pin_memory()
-        out_i = torch.empty((B, TOPK), dtype=torch.int64).pin_memory()
+        def sync_step(i):
+            _, _, ev = index.search_host_pipelined(q_host, topk, 0)
+            ev.synchronize()
+        sync_ms = timed(sync_step, K, 3) / K
+    e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
+           "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": 2,
+           "one_at_a_time_ms_per_step": sync_ms, "one_at_a_time_qps": B / sync_ms * 1e3,
+           "api": ("FlatShard.search_host_async -> vqa_search_host_async (C ABI, pinned host buffers)" if world == 1 else
+                   "ShardedFlat.search_host_pipelined (pinned host buffers; cudaMemcpyAsync H2D -> vqa_search -> "
+                   "exchange -> vqa_merge_topk -> D2H)")}
 
-        def e2e_step():
-            qd = q_host.to(device, non_blocking=True)
-            s, i = index.search(qd, TOPK)
-            out_s.copy_(s, non_blocking=True)
-            out_i.copy_(i, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    e2e_ms = timed(e2e_step, K, 3)
-    e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,
-           "d2h_bytes_per_step": B * TOPK * 12, "ms_per_step": e2e_ms / K,
-           "api": "FlatShard.search_host -> vqa_search_host (C ABI, host buffers)" if world == 1 else
-                  "ShardedFlat.search with pinned H2D/D2H"}
-
-    # ---- recall@10 of the fast path against fp32-verify arithmetic on the same rows -----
-    s_fast, i_fast = index.search(q_dev, TOPK, "fast")
+    # ---- recall@k of the fast path against fp32-verify arithmetic on the same rows -----
+    s_fast, i_fast = index.search(q_dev, topk, "fast")
     s_fast, i_fast = s_fast.clone(), i_fast.clone()  # the sharded index reuses its output buffers
-    s_ver, i_ver = index.search(q_dev, TOPK, "verify")
+    s_ver, i_ver = index.search(q_dev, topk, "verify")
+    s_ver, i_ver = s_ver.clone(), i_ver.clone()
     index.mode = "fast"
     torch.cuda.synchronize()
     a, b = i_fast.cpu().numpy(), i_ver.cpu().numpy()
-    recall = float(np.mean([len(set(a[r]) & set(b[r])) / TOPK for r in range(B)]))
+    recall = float(np.mean([len(set(a[r]) & set(b[r])) / topk for r in range(B)]))
     max_rel = float((torch.abs(s_fast - s_ver) / torch.abs(s_ver).clamp_min(1e-12)).max().item())
 
-    # same check for a large batch (TMEM-resident-query kernel: storage-precision screen + exact re-score)
+    # ---- independent checker at full size: chunked fp32 torch.matmul + topk (not this repo's kernels) ----------
+    independent = None
+    if args.check:
+        try:
+            t0 = time.perf_counter()
+            ls, li = torch_topk_fp32(torch, rows, q_dev, topk, lo)
+            if world > 1:                               # merge the ranks' exact local answers with torch only
+                gs = [torch.empty_like(ls) for _ in range(world)]
+                gi = [torch.empty_like(li) for _ in range(world)]
+                dist.all_gather(gs, ls)
+                dist.all_gather(gi, li)
+                cs, ci = torch.cat(gs, 1), torch.cat(gi, 1)
+                ls, o2 = torch.topk(cs, topk, dim=1)
+                li = torch.gather(ci, 1, o2)
+            torch.cuda.synchronize()
+            chk_s = time.perf_counter() - t0
+            independent = {
+                "checker": "chunked fp32 torch.matmul (TF32 off) + torch.topk over the same stored rows"
+                           + (", per rank, merged with torch.topk after an all_gather" if world > 1 else ""),
+                "queries": B, "rows": n_rows, "seconds": chk_s,
+                "verify_vs_independent": compare_topk(i_ver.cpu().numpy(), s_ver.cpu().numpy(), li.cpu().numpy(),
+                                                      ls.cpu().numpy()),
+                "fast_vs_independent": compare_topk(i_fast.cpu().numpy(), s_fast.cpu().numpy(), li.cpu().numpy(),
+                                                    ls.cpu().numpy())}
+            v = independent["verify_vs_independent"]
+            independent["ids_equal_independent"] = bool(v["mismatch"] == 0)
+            # G0: the cuBLAS comparator -- storage-precision matmul that MATERIALISES the [B, rows] score matrix + topk
+            if world == 1 and (hi - lo) * B * 4 < 8e9:
+                qh = q_dev.to(tdtype)
+
+                def g0(i):
+                    return torch.topk(torch.matmul(qh, rows.T).float(), topk, dim=1)
+                g0_ms = timed(g0, 5, 2) / 5
+                independent["g0_torch_matmul_topk_ms"] = g0_ms
+                independent["g0_note"] = ("torch.matmul (cuBLAS, 16-bit operands, queries rounded to storage precision) "
+                                          "+ torch.topk over the materialised score matrix; context only")
+            del ls, li
+        except Exception as exc:  # noqa: BLE001
+            independent = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    # ---- N>1: the sharded verify answer against ONE index holding all rows (rank 0 rebuilds every shard) --------
+    sharded_single = None
+    if world > 1 and args.check:
+        try:
+            nq = min(B, 8)
+            if rank == 0 and n_rows * dim * rows.element_size() < 60e9:
+                parts = [rows] + [make_rows(torch, ops, shard_bounds(n_rows, world, r)[1] - shard_bounds(n_rows, world, r)[0],
+                                            dim, tdtype, 1234 + r, device) for r in range(1, world)]
+                full_rows = torch.cat(parts, 0)
+                del parts
+                full = ops.FlatShard(full_rows)
+                fs, fi = full.search(q_dev[:nq].contiguous(), topk, "verify")
+                torch.cuda.synchronize()
+                sharded_single = {"queries": nq, "mode": "verify",
+                                  "ids_equal": bool(torch.equal(fi, i_ver[:nq])),
+                                  "score_bits_equal": bool(torch.equal(fs.view(torch.int32), s_ver[:nq].view(torch.int32)))}
+                del full, full_rows
+            dist.barrier()
+        except Exception as exc:  # noqa: BLE001
+            sharded_single = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    # same recall check for a large batch (TMEM-resident-query kernel: storage-precision screen + exact re-score)
     recall_b256 = None
-    if args.sweep:
+    if args.sweep and headline:
         qb = q_dev_all[:256].contiguous()
-        _, i_f = index.search(qb, TOPK, "fast")
+        _, i_f = index.search(qb, topk, "fast")
         i_f = i_f.clone()
-        _, i_v = index.search(qb, TOPK, "verify")
+        _, i_v = index.search(qb, topk, "verify")
         index.mode = "fast"
         torch.cuda.synchronize()
         a2, b2 = i_f.cpu().numpy(), i_v.cpu().numpy()
-        recall_b256 = float(np.mean([len(set(a2[r]) & set(b2[r])) / TOPK for r in range(256)]))
+        recall_b256 = float(np.mean([len(set(a2[r]) & set(b2[r])) / topk for r in range(256)]))
 
     # ---- sweep over batch sizes (reported, not the headline) ---------------------------
     sweep = []
-    if args.sweep:
+    if args.sweep and headline:
         for b_ in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
             qd = q_dev_all[:b_].contiguous()
             try:
-                ms = timed(lambda: index.search(qd, TOPK), max(5, min(K, 50)), 3) / max(5, min(K, 50))
-                fam_b, _ = shard.plan(b_, TOPK, "fast")
-                sweep.append({"batch": b_, "ms": ms, "qps": b_ / ms * 1e3,
+                n_it = max(5, min(K, 50))
+                sp = [None, None]
+
+                def sstep(i):
+                    sp[i & 1] = index.search_pipelined(qd, topk, i & 1)
+
+                def sdrain():
+                    for p_ in sp:
+                        if p_ is not None:
+                            torch.cuda.current_stream().wait_event(p_[2])
+                ms = timed(sstep, n_it, 3, sdrain) / n_it
+                kms = timed(lambda i: shard.search(qd, topk, "fast"), n_it, 2) / n_it
+                fam_b, _ = shard.plan(b_, topk, "fast")
+                sweep.append({"batch": b_, "ms": ms, "qps": b_ / ms * 1e3, "scan_ms": kms,
                               "hbm_frac": alg_bytes / (ms / 1e3) / 1e9 / hbm_peak,
-                              "tensor_frac": 2.0 * b_ * (hi - lo) * DIM / (ms / 1e3) / 1e12 / tf_peak,
+                              "scan_hbm_frac": alg_bytes / (kms / 1e3) / 1e9 / hbm_peak,
+                              "tensor_frac": 2.0 * b_ * (hi - lo) * dim / (ms / 1e3) / 1e12 / tf_peak,
                               "family": {2: "stream (CUDA cores)", 3: "tcgen05, queries in smem (hi/lo)",
                                          4: "tcgen05, queries in TMEM (screen + exact re-score)"}.get(fam_b, str(fam_b))})
             except Exception as exc:  # noqa: BLE001
@@ -445,37 +638,31 @@ def run_ours(args):
 
     # ---- K1 (fused mean-pool + L2 normalise) on BASELINE configs[4]'s shape, then search --
     pool = None
-    if args.sweep:
+    if args.sweep and headline:
         try:
             gp = torch.Generator(device=device).manual_seed(5)
             hb, hs = 256, 256
-            hidden = torch.randn((hb, hs, DIM), generator=gp, device=device, dtype=torch.float32).to(torch.bfloat16)
+            hidden = torch.randn((hb, hs, dim), generator=gp, device=device, dtype=torch.float32).to(torch.bfloat16)
             lens = torch.randint(16, hs + 1, (hb,), generator=gp, device=device)
             mask = (torch.arange(hs, device=device)[None, :] < lens[:, None]).to(torch.int64)
-            valid_bytes = int(lens.sum().item()) * DIM * 2
+            valid_bytes = int(lens.sum().item()) * dim * 2
             # a second copy so that consecutive timed calls do not find the 100 MB input in the 126 MB L2
             hidden2 = hidden.clone()
             flip = [hidden, hidden2]
-            cnt = [0]
 
-            def pool_step():
-                cnt[0] += 1
-                return ops.pool_normalize(flip[cnt[0] & 1], mask)
-
-            pms = timed(pool_step, 40, 4) / 40
-            e2e_q = ops.pool_normalize(hidden, mask)
-            ems = timed(lambda: index.search(ops.pool_normalize(flip[0], mask), TOPK), 5, 2) / 5
-            pool = {"shape": [hb, hs, DIM], "dtype": "bf16", "ms": pms, "valid_token_bytes": valid_bytes,
+            pms = timed(lambda i: ops.pool_normalize(flip[i & 1], mask), 40, 4) / 40
+            ems = timed(lambda i: index.search(ops.pool_normalize(flip[0], mask), topk), 5, 2) / 5
+            pool = {"shape": [hb, hs, dim], "dtype": "bf16", "ms": pms, "valid_token_bytes": valid_bytes,
                     "achieved_gbs": valid_bytes / (pms / 1e3) / 1e9, "frac_of_hbm_peak": valid_bytes / (pms / 1e3) / 1e9 / hbm_peak,
-                    "full_tensor_bytes": hb * hs * DIM * 2, "pool_then_search_b256_ms": ems,
+                    "full_tensor_bytes": hb * hs * dim * 2, "pool_then_search_b256_ms": ems,
                     "note": "masked tokens are never loaded; alternating two input copies (201 MB > L2)"}
-            del hidden, hidden2, e2e_q
+            del hidden, hidden2
         except Exception as exc:  # noqa: BLE001
             pool = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- BASELINE configs[0] (the reference's own CPU-runnable case): 10k x 768 fp32, 64 queries, top-5 --
     config_a = None
-    if rank == 0 and world == 1 and args.sweep and not args.no_cpu:
+    if rank == 0 and world == 1 and args.sweep and headline and not args.no_cpu:
         try:
             import oracle
             from tests.golden import inputs as golden_inputs
@@ -487,9 +674,9 @@ def run_ours(args):
             os_a, oi_a = oracle.search(docs_a, q_a, 5, oracle.CANONICAL, "fp32")
             ids_exact = bool(np.array_equal(i_a.cpu().numpy(), oi_a))
             bits_exact = bool(np.array_equal(s_a.cpu().numpy().view(np.int32), os_a.view(np.int32)))
-            gms = timed(lambda: sh_a.search(qa_dev, 5, "verify"), 50, 5) / 50
+            gms = timed(lambda i: sh_a.search(qa_dev, 5, "verify"), 50, 5) / 50
             qa_pin = torch.from_numpy(q_a).pin_memory()
-            hms = timed(lambda: sh_a.search_host(qa_pin, 5, "verify"), 50, 5) / 50
+            hms = timed(lambda i: sh_a.search_host(qa_pin, 5, "verify"), 50, 5) / 50
             t0 = time.perf_counter()
             for _ in range(3):
                 for r in range(q_a.shape[0]):          # one query at a time, as heavy_ranker.py:97-101 drives it
@@ -532,49 +719,45 @@ def run_ours(args):
 
     # ---- hybrid=True's extra work (BM25 leg + fusion), reported beside the dense headline ----
     hybrid = None
-    if rank == 0 and world == 1 and args.sweep:
+    if rank == 0 and world == 1 and args.sweep and headline:
         try:
-            hybrid = hybrid_leg_section(torch, ops, shard, q_dev, timed, with_cpu=not args.no_cpu)
+            hybrid = hybrid_leg_section(torch, ops, shard, q_dev, lambda fn, st, wm: timed(lambda i: fn(), st, wm),
+                                        with_cpu=not args.no_cpu)
         except Exception as exc:  # noqa: BLE001
             hybrid = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cq, per_step, reps = cpu_sample_qps(B, TOPK, args.cpu_seconds, args.cpu_rows)
+    if rank == 0 and world == 1 and not args.no_cpu and headline:
+        cq, per_step, reps = cpu_sample_qps(B, topk, args.cpu_seconds, args.cpu_rows)
         cpu = {"value": cq, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{args.cpu_rows} of {args.rows} rows x {DIM} fp32, B={B}, k={TOPK}, numpy/OpenBLAS sgemm + "
+               "sample": f"{args.cpu_rows} of {n_rows} rows x {dim} fp32, B={B}, k={topk}, numpy/OpenBLAS sgemm + "
                          f"argpartition (oracle.np_search_fast), {reps} reps of {per_step * 1e3:.1f} ms; QPS scaled by "
-                         f"rows ratio"}
-
-    # ---- opt-in kernels, in subprocesses, after everything above is measured (rank 0, N=1 only) ----
-    preview = None
-    if rank == 0 and world == 1 and args.sweep and args.preview:
-        try:
-            torch.cuda.synchronize()
-            preview = opt_in_preview()
-        except Exception as exc:  # noqa: BLE001
-            preview = {"error": f"{type(exc).__name__}: {exc}"}
+                         f"rows ratio (the --impl reference arm times FULL 10 M-row steps)"}
 
     if rank == 0:
-        merge_launches = 1 if world > 1 else 0
+        p2p = world > 1 and any(isinstance(b_, tuple) and len(b_) == 9 and b_[7] is not None for b_ in index._bufs.values())
+        xlaunch = 0 if world == 1 else 2          # push + flag-waiting merge, or all-gather (NCCL's kernel) + merge
         line = {
-            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"top-{TOPK} exact cosine search over {args.rows}x{DIM} bf16 docs, batch {B}, "
-                                   f"row-sharded over {world} GPU(s)", "rows": args.rows, "dim": DIM, "batch": B,
-                       "k": TOPK, "rows_per_gpu": hi - lo, "parallelism": f"row-shard x{world}",
+            "metric": cfg["metric"], "value": value, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+            "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": f"top-{topk} exact cosine search over {n_rows}x{dim} docs, batch {B}",
+                       "rows": n_rows, "dim": dim, "batch": B, "k": topk, "storage": f"{cfg['dtype']} rows in HBM",
+                       "rows_per_gpu": hi - lo, "parallelism": f"row-shard x{world}",
                        "exchange": ("none" if world == 1 else
-                                    ("nvlink peer-memory push + flag-waiting merge kernel"
-                                     if any(b[7] is not None for b in index._bufs.values())
+                                    ("nvlink peer-memory push + flag-waiting merge kernel" if p2p
                                      else "one NCCL all-gather + merge kernel")),
+                       "pipelining": ("steps issued back to back on one stream" if world == 1 else
+                                      "exchange + merge of step i on a side stream under the scan of step i+1 (2 slots)"),
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB per GPU streamed per step)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
-            "gpu_launches": K * (launches + merge_launches),
-            "recall_at_10": recall, "recall_at_10_batch256": recall_b256, "fast_vs_verify_max_rel_score_err": max_rel,
+            "gpu_launches": K * (launches + xlaunch - (1 if (world > 1 and not p2p) else 0)),
+            "one_step_at_a_time_ms": serial_ms,
+            "recall_at_k": recall, "recall_at_10_batch256": recall_b256, "fast_vs_verify_max_rel_score_err": max_rel,
+            "independent_check": independent, "sharded_equals_single": sharded_single,
             "sweep": sweep, "pool_k1": pool, "config_a_reference_scale": config_a, "hybrid_leg": hybrid,
-            "opt_in_preview": preview,
+            "tuning": shard.get_tuning().as_dict(),
             "lib": f"libvqa_b200.so v{vqa._native.lib().vqa_version()}",
         }
         print(json.dumps(line), flush=True)
@@ -589,13 +772,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--config", default="headline", choices=["headline", "D"],
+                    help="headline = BASELINE metric (10M x 768 bf16, top-10); D = BASELINE configs[3] shard per GPU")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--sweep", type=int, default=1)
-    ap.add_argument("--preview", type=int, default=1, help="time the opt-in kernels in subprocesses (N=1 only)")
+    ap.add_argument("--check", type=int, default=1, help="independent torch fp32 checker + sharded-vs-single check")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=500_000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-cap-seconds", type=float, default=150.0, help="--impl reference: wall-clock cap of the run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

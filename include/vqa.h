@@ -123,6 +123,15 @@ VQA_API int vqa_index_bind(vqa_index_t *h, const void *rows_dev, int64_t n_rows,
 VQA_API int vqa_index_destroy(vqa_index_t *h);
 
 /*
+ * Diagnostic: while `stamps_dev` is set (NULL switches it off), every CTA of the smem-resident tcgen05 scan
+ * kernel writes 32 uint64 stamps -- %globaltimer (ns) in slots 0..15, clock64 in 16..31 -- of: 0 entry,
+ * 1 first / 2 last TMA issue, 3 first MMA / 4 last commit, 5 queries staged, 6..12 tiles 0, 1, 3, 7, 15, 31, 63
+ * leaving the epilogue, 13 last tile, 14 exit.  The buffer must hold 256 bytes per SM.  This is how
+ * profiles/r2_timeline_*.json (where the per-launch fixed cost goes) were produced; no effect on results.
+ */
+VQA_API int vqa_debug_timeline(vqa_index_t *h, void *stamps_dev, size_t bytes);
+
+/*
  * Kernel-selection knobs of one index handle.  Every field has a measured default (vqa_tuning_default);
  * they exist for benchmarks and tests -- a drop-in user never touches them.  -1 / 0 = "auto" where noted.
  * Replaces: nothing in the reference (txtai exposes faiss' `nprobe`/`components` strings the same way,
@@ -142,13 +151,14 @@ typedef struct vqa_tuning {
     int32_t ts_split;      /* TS kernel: hi+lo rows (1) or storage-precision screen (0), -1 = auto                */
     int32_t ts_groups;     /* TS kernel: chunks of 128 queries per launch (cluster size), 1..4 (2)                */
     int32_t reduce_select; /* radix-select candidate reduce for k > 32 and for re-scoring reduces, 0|1 (1)        */
-    int32_t reduce_early;  /* early exit in the k <= 32 warp reduce over sorted internal lists, 0|1               */
+    int32_t reduce_early;  /* early exit in the k <= 32 warp reduce over sorted internal lists, 0|1 (1)           */
     int32_t pdl_chain;     /* 2nd+ scan launch of one search overlaps the previous reduce, 0|1                    */
     int32_t tma_l2promo;   /* CUtensorMapL2promotion of the document tensor map, 0..3 (3 = 256 B)                 */
     int32_t tma_hint;      /* L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last (1)         */
-    int32_t stream_max_b;  /* FAST: batches up to this size take the CUDA-core streaming kernel, 0..8 (2)         */
+    int32_t stream_max_b;  /* FAST: batches up to this size take the CUDA-core streaming kernel, 0..8 (2) ...     */
+    int32_t stream_min_mb; /* ... when the shard is at least this many MB (its fixed cost is ~80 us higher), (8000)*/
     int32_t pair;          /* FAST: tensor-bound batches take the cta_group::2 pair kernel, 0|1                   */
-    int32_t reserved[5];
+    int32_t reserved[4];
 } vqa_tuning_t;
 
 /* Library defaults (no environment). */

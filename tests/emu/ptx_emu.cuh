@@ -152,6 +152,8 @@ inline void tc_fence_after_sync() {}
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
+inline uint64_t globaltimer_ns() { return 0; }  // diagnostic stamps: no clock in the emulator
+inline uint64_t sm_clock() { return 0; }
 inline void prefetch_tmap(const void *) {}
 // copy one box into CTA `cta`'s shared memory at offset `dst` and complete its bytes on that CTA's mbarrier
 inline void emu_tma_box(int cta, uint32_t dst, const emu::EmuTmap *m, int32_t c0, int32_t c1, uint32_t bar_off) {

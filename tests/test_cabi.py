@@ -38,7 +38,7 @@ def test_tuning_knobs_are_validated_once_not_read_on_the_search_path(monkeypatch
         monkeypatch.delenv(v, raising=False)
     t = N.tuning_default()
     assert t.size == ctypes.sizeof(N.Tuning) and t.ts_extra == 6 and t.ts_qs == 1 and t.reduce_select == 1
-    assert t.ts_ks == -1 and t.stream_max_b == 2 and t.tma_l2promo == 3
+    assert t.ts_ks == -1 and t.stream_max_b == 2 and t.tma_l2promo == 3 and t.reduce_early == 1
     assert N.tuning_default(from_env=True).as_dict() == t.as_dict()
     monkeypatch.setenv("VQA_TS_QS", "0")
     monkeypatch.setenv("VQA_TS_EXTRA", "12")
@@ -210,10 +210,11 @@ def test_product_never_references_the_emulator():
 
 
 def test_measured_kernels_are_unchanged():
-    """The tensor-core kernels on the DEFAULT routing are instruction-for-instruction the ones measured on the
-    B200 in round 1 (profiles/r1_measured_kernel_sass.json): the opt-in variants added since (QS, radix select)
-    must not perturb them.  Compares SASS instruction streams of the current build; skipped when the toolchain
-    differs from the one that produced the fingerprints."""
+    """The tensor-core kernels are instruction-for-instruction the ones of the build that was last measured on the
+    B200 (profiles/r2_measured_kernel_sass.json, rewritten by `tools/sass_fingerprint.py --write` when a GPU session
+    measures a new build): a source edit after the last measurement that perturbs them fails here, so the numbers in
+    DESIGN.md always belong to the committed code.  Compares SASS instruction streams of the current build; skipped
+    when the toolchain differs from the one that produced the fingerprints."""
     import json
     import shutil
     import sys

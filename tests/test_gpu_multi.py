@@ -39,6 +39,37 @@ for exchange in ("nccl", "p2p"):
         rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / K for a, b in zip(i.cpu(), fi.cpu())])
         ok = ok and rec >= 0.999
     ok = ok and i[0, :3].tolist() == [0, N // 2, N - 1]
+    # pipelined searches (exchange + merge of batch i on a side stream under the scan of batch i+1, two slots in
+    # flight), device- and host-buffer forms: every step's result equals the synchronous answer for its queries
+    want = {}
+    qs = [qd, torch.roll(qd, 1, 0).contiguous(), torch.roll(qd, 2, 0).contiguous()]
+    for j, qq in enumerate(qs):
+        a, b_ = sh.search(qq, K)
+        want[j] = (a.clone(), b_.clone())
+    pend = [None, None]
+    for step in range(7):
+        slot = step % 2
+        if pend[slot] is not None:
+            ps, pi, ev, j = pend[slot]
+            ev.synchronize()
+            ok = ok and torch.equal(pi, want[j][1]) and torch.equal(ps, want[j][0])
+        pend[slot] = sh.search_pipelined(qs[step % 3], K, slot) + (step % 3,)
+    for p_ in pend:
+        p_[2].synchronize()
+        ok = ok and torch.equal(p_[1], want[p_[3]][1])
+    qh = [x.cpu().pin_memory() for x in qs]
+    pend = [None, None]
+    for step in range(6):
+        slot = step % 2
+        if pend[slot] is not None:
+            ps, pi, ev, j = pend[slot]
+            ev.synchronize()
+            ok = ok and torch.equal(pi, want[j][1].cpu()) and torch.equal(ps, want[j][0].cpu())
+        pend[slot] = sh.search_host_pipelined(qh[step % 3], K, slot) + (step % 3,)
+    for p_ in pend:
+        p_[2].synchronize()
+        ok = ok and torch.equal(p_[1], want[p_[3]][1].cpu())
+    torch.cuda.synchronize()
     if not ok:
         print("FAILED", exchange, storage, mode, rank, flush=True)
         break

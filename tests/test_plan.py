@@ -35,26 +35,27 @@ KNOB_ENV = ("VQA_TS_QS", "VQA_TS_KS", "VQA_REDUCE_SELECT", "VQA_TS_SPLIT", "VQA_
 
 
 def test_default_routing(monkeypatch):
-    """Round-2 defaults (flipped by the B200 timings in profiles/r2_*): B <= 2 on the CUDA-core streaming kernel,
-    up to 32 queries on the smem-resident tcgen05 kernel, beyond that the QS variant of the TMEM-resident-query
-    kernel with four accumulator stages at dim 768, and dim 1024 on it too."""
+    """Round-2 defaults (flipped by the B200 timings in profiles/r2_call1.log): B <= 2 on the CUDA-core streaming
+    kernel for shards of >= 8 GB, up to 32 queries on the smem-resident tcgen05 kernel, beyond that the QS variant of
+    the TMEM-resident-query kernel with three accumulator stages at dim 768, and dim 1024 on it too."""
     for v in KNOB_ENV:
         monkeypatch.delenv(v, raising=False)
     n = 10_000_000
     for b in (1, 2):                                       # north_star's small-batch regime: HBM-streaming warp dot products
         assert plan(n, 768, BF16, b, 10)["family"] == STREAM
+        assert plan(1_250_000, 768, BF16, b, 10)["family"] == TENSOR   # ... whose fixed cost loses on an 8-GPU shard
     for b in (3, 8, 32):                                   # headline: smem-resident tcgen05 kernel, hi/lo columns
         p = plan(n, 768, BF16, b, 10)
         assert p["family"] == TENSOR and p["split"] == 1 and p["smem"] <= SMEM
     for b in (33, 64, 128, 256, 1024):                     # large batches: queries in TMEM, screen + re-score of 32
         p = plan(n, 768, BF16, b, 10)
-        assert (p["family"], p["split"], p["qs"], p["ks"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 1, 4, 16, 32, 1)
-        assert p["tmem_query_cols"] == 256 and p["smem"] <= SMEM       # 8 blocks in TMEM -> 4 accumulator stages
+        assert (p["family"], p["split"], p["qs"], p["ks"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 1, 2, 16, 32, 1)
+        assert p["tmem_query_cols"] == 320 and p["smem"] <= SMEM       # 10 blocks in TMEM -> 3 accumulator stages
     p = plan(n, 768, BF16, 8, 100)                         # k > 32: TS with hi/lo rows and heaps, no re-scoring
     assert (p["family"], p["split"], p["qs"], p["kscan"], p["rescore"]) == (TS, 1, 1, 100, 0)
     assert plan(n, 768, BF16, 1, 100)["family"] == TS      # big k is never a streaming-kernel case
-    p = plan(12_500_000, 1024, F16, 64, 100)               # BASELINE configs[3]: one pass, 12 blocks in TMEM + 4 in smem
-    assert (p["family"], p["qs"], p["ks"], p["split"], p["rescore"]) == (TS, 1, 4, 0, 1)
+    p = plan(12_500_000, 1024, F16, 64, 100)               # BASELINE configs[3]: one pass, 10 blocks in TMEM + 6 in smem
+    assert (p["family"], p["qs"], p["ks"], p["split"], p["rescore"]) == (TS, 1, 6, 0, 1)
     assert plan(n, 1024, BF16, 64, 10, TS) is not None
     assert plan(n, 768, F32, 4, 10)["family"] == STREAM and plan(n, 776, BF16, 4, 10)["family"] == STREAM
     assert plan(n, 768, BF16, 4, 10, VERIFY)["family"] == STREAM
@@ -113,13 +114,13 @@ def test_every_plan_fits_shared_and_tensor_memory(monkeypatch, qs, select):
 
 def test_config_d_plan(monkeypatch):
     """BASELINE configs[3] (12.5 M x 1024 fp16 per GPU, B = 64, top-100) on the default routing:
-    one pass of the TMEM-resident-query kernel -- 12 query blocks in tensor memory, 4 in shared memory, heaps for
+    one pass of the TMEM-resident-query kernel -- 10 query blocks in tensor memory, 6 in shared memory, heaps for
     64 rows, 106 candidates per list, the 128 best re-scored exactly by the radix-select reduce."""
     monkeypatch.setenv("VQA_TS_QS", "1")
     monkeypatch.setenv("VQA_REDUCE_SELECT", "1")
     monkeypatch.delenv("VQA_TS_KS", raising=False)
     p = plan(12_500_000, 1024, F16, 64, 100)
-    assert (p["family"], p["qs"], p["ks"], p["split"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 1, 4, 0, 106, 128, 1)
-    assert p["passes"] == 1 and p["tmem_query_cols"] == 384 and p["stages"] >= 3 and p["smem"] <= SMEM
+    assert (p["family"], p["qs"], p["ks"], p["split"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 1, 6, 0, 106, 128, 1)
+    assert p["passes"] == 1 and p["tmem_query_cols"] == 320 and p["stages"] >= 3 and p["smem"] <= SMEM
     q = plan(12_500_000, 1024, BF16, 64, 100)              # bf16 rows: 8-bit queries would need ~28 spare ranks -> hi/lo rows
     assert (q["family"], q["qs"], q["split"], q["rescore"]) == (TS, 1, 1, 0) and q["smem"] <= SMEM

@@ -25,7 +25,7 @@ MODES = {"verify": MODE_VERIFY, "fp32": MODE_VERIFY, "fast": MODE_FAST, "stream"
 
 EXPORTS = [
     "vqa_version", "vqa_last_error", "vqa_device_count", "vqa_index_create", "vqa_index_bind",
-    "vqa_index_destroy", "vqa_workspace_bytes", "vqa_search", "vqa_search_host_staging_bytes", "vqa_search_host_async",
+    "vqa_index_destroy", "vqa_debug_timeline", "vqa_workspace_bytes", "vqa_search", "vqa_search_host_staging_bytes", "vqa_search_host_async",
     "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_exchange_push", "vqa_merge_topk_wait",
     "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
     "vqa_search_plan", "vqa_plan_describe", "vqa_plan_describe_tuned",
@@ -42,11 +42,11 @@ class Tuning(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "size", "ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "mma_tb", "ts_qs",
         "ts_ks", "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-        "stream_max_b", "pair")] + [("reserved", ctypes.c_int32 * 5)]
+        "stream_max_b", "stream_min_mb", "pair")] + [("reserved", ctypes.c_int32 * 4)]
 
     KNOBS = ("ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "mma_tb", "ts_qs", "ts_ks",
              "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-             "stream_max_b", "pair")
+             "stream_max_b", "stream_min_mb", "pair")
 
     def update(self, **knobs) -> "Tuning":
         for key, val in knobs.items():
@@ -89,6 +89,8 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_index_create.argtypes = [c.POINTER(vp), i64, i32, i32, i32, i64]
     L.vqa_index_bind.restype = c.c_int
     L.vqa_index_bind.argtypes = [vp, vp, i64, i64]
+    L.vqa_debug_timeline.restype = c.c_int
+    L.vqa_debug_timeline.argtypes = [vp, vp, sz]
     L.vqa_index_destroy.restype = c.c_int
     L.vqa_index_destroy.argtypes = [vp]
     L.vqa_workspace_bytes.restype = c.c_int

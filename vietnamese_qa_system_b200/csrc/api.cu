@@ -109,6 +109,8 @@ struct vqa_index {
     };
     mutable PlanSlot plan_cache[8];
     mutable unsigned plan_next = 0;
+    unsigned long long *timeline = nullptr;  // vqa_debug_timeline
+    size_t timeline_bytes = 0;
 };
 
 // sparse (BM25) term index: CSR postings borrowed from the caller
@@ -163,11 +165,12 @@ const KnobSpec kKnobs[] = {
     {"VQA_TS_SPLIT", &vqa_tuning_t::ts_split, -1, 1, -1},
     {"VQA_TS_GROUPS", &vqa_tuning_t::ts_groups, 1, 4, 2},
     {"VQA_REDUCE_SELECT", &vqa_tuning_t::reduce_select, 0, 1, 1},
-    {"VQA_REDUCE_EARLY", &vqa_tuning_t::reduce_early, 0, 1, 0},
+    {"VQA_REDUCE_EARLY", &vqa_tuning_t::reduce_early, 0, 1, 1},
     {"VQA_PDL_CHAIN", &vqa_tuning_t::pdl_chain, 0, 1, 0},
     {"VQA_TMA_L2PROMO", &vqa_tuning_t::tma_l2promo, 0, 3, 3},
     {"VQA_TMA_HINT", &vqa_tuning_t::tma_hint, 0, 2, 1},
     {"VQA_STREAM_MAX_B", &vqa_tuning_t::stream_max_b, 0, 8, 2},
+    {"VQA_STREAM_MIN_MB", &vqa_tuning_t::stream_min_mb, 0, 1 << 30, 8000},
     {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 0},
 };
 
@@ -267,13 +270,14 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     // re-score them exactly in the reduce.  Larger k: hi + lo rows (64 queries per CTA).
     const int kb = h->dim / vqa::kBlockK;
     // QS variant: ks of the kb query blocks in shared memory.  At most 12 fit tensor memory beside two accumulator
-    // stages; 8 leave FOUR stages (measured, profiles/r2_*: B = 128 at a 1.25 M-row shard 0.431 -> 0.366 ms), so
-    // auto = kb - 8 where shared memory has room for it, else the minimum that fits
+    // stages; 10 leave THREE.  Measured (profiles/r2_call1.log): at dim 768 ks = 2 beats 0 / 4 / 6 at every batch
+    // size on the 10 M-row index (B = 64: 2.28 vs 2.59 ms at ks = 4) and ties at the 1.25 M-row shard; at dim 1024
+    // ks = 6 ties 4 and 8 loses 40 % (the ring shrinks to 80 KB).  So auto = kb - 10.
     const int qs = tu.ts_qs != 0 ? 1 : 0;
     int ks = 0;
     if (qs) {
         const int ks_min = kb > 12 ? kb - 12 : 0;
-        ks = tu.ts_ks >= 0 ? tu.ts_ks : (kb > 8 && kb <= 12 ? kb - 8 : ks_min);
+        ks = tu.ts_ks >= 0 ? tu.ts_ks : (kb > 10 ? kb - 10 : 0);
         if (ks < ks_min) ks = ks_min;
         if (ks > kb) ks = kb;
     } else if (h->dim > 768) {
@@ -352,13 +356,17 @@ int make_plan_uncached(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
     if (mode == VQA_MODE_FAST) {
         // Measured on B200 (profiles/):
         //  * B <= 2 (stream_max_b): the CUDA-core streaming kernel (128-bit no-allocate loads, warp dot products)
-        //    reads the rows at the HBM roofline with the smallest fixed cost -- 2.18 vs 2.28 ms at 10 M x 768;
+        //    has the highest steady-state rate -- 2.20 vs 2.27 ms at 10 M x 768 (shards of >= stream_min_mb only);
         //  * up to 32 queries, k <= 32: the TMA-fed tcgen05 kernel with the queries resident in shared memory (hi/lo
         //    columns) -- CUDA cores cannot keep up with HBM beyond ~4 queries per streamed element;
         //  * beyond that, and k > 32: the TMEM-resident-query kernel serves 128 queries per CTA from one HBM pass
         //    (screen with storage-precision queries, exact re-scoring in the reduce; hi/lo rows + heaps for big k).
         //  fp32 rows (verify mode's native storage) and dims that are not multiples of 64: streaming kernel.
-        if (nq <= h->tune.stream_max_b && k <= 32) {
+        // (the streaming kernel's steady state is 7.33 TB/s against 6.8 for the N = 16 MMA tiles, but its fixed cost
+        // is ~80 us higher: it wins from ~5 M rows of 768 bf16 upwards -- stream_min_mb)
+        const long long shard_mb = (long long)h->n_rows * h->dim * elem_size(h->dtype) / 1000000;
+        const bool sixteen = h->dtype == VQA_BF16 || h->dtype == VQA_F16;
+        if (nq <= h->tune.stream_max_b && k <= 32 && (!sixteen || shard_mb >= h->tune.stream_min_mb)) {
             plan_stream(h, nq, pl);
             return VQA_OK;
         }
@@ -545,6 +553,15 @@ int vqa_index_bind(vqa_index_t *h, const void *rows_dev, int64_t n_rows, int64_t
     h->stride = row_stride_bytes;
     invalidate_plans(h);
     return build_tmaps(h);
+}
+
+int vqa_debug_timeline(vqa_index_t *h, void *stamps_dev, size_t bytes) {
+    if (!h) return fail(VQA_E_INVALID, "null index handle");
+    if (stamps_dev && (bytes < 256 || reinterpret_cast<uintptr_t>(stamps_dev) % 8 != 0))
+        return fail(VQA_E_INVALID, "timeline buffer must be 8-byte aligned and hold >= 256 bytes per CTA");
+    h->timeline = static_cast<unsigned long long *>(stamps_dev);
+    h->timeline_bytes = stamps_dev ? bytes : 0;
+    return VQA_OK;
 }
 
 int vqa_index_destroy(vqa_index_t *h) {
@@ -805,6 +822,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.slot_g = tb ? slot_g + (long long)l0 * 32 : nullptr;
             a.pdl = (l0 > 0 && h->tune.pdl_chain) ? 1 : 0;
             a.tma_hint = h->tune.tma_hint;
+            a.timeline = (h->timeline && h->timeline_bytes >= (size_t)a.grid * 32 * 8) ? h->timeline : nullptr;
             cudaError_t e = vqa::launch_mma(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
             vqa::Rescore rs;

@@ -50,6 +50,7 @@ struct MmaLaunch {
     unsigned long long *slot_g = nullptr;  // opt-in TB variants: [nq][32] tournament slots (see MmaParams), else nullptr
     int pdl = 0;  // opt-in: launch with programmatic stream serialization (2nd+ scan of one search, see mma_launch.cu)
     int tma_hint = 1;  // L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last
+    unsigned long long *timeline = nullptr;  // diagnostic per-CTA stamps (vqa_debug_timeline), normally nullptr
 };
 
 struct TsLaunch {

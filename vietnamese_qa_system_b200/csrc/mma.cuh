@@ -66,7 +66,19 @@ struct MmaParams {
     // so their minimum is a lower bound of the global k-th best -- close to the exact one, because the top-k
     // documents mostly sit in different lists -- long before any single list's own k-th best gets there.
     unsigned long long *slot_g;
+    // Diagnostic (vqa_debug_timeline): [gridDim.x][kTimelineSlots] per-CTA stamps -- %globaltimer in slots 0..15,
+    // clock64 in 16..31 -- of entry, first/last TMA issue, first MMA / last commit, queries staged, tiles
+    // 0, 1, 3, 7, 15, 31, 63 and the last one leaving the epilogue, and exit.  nullptr (always, in normal use): off.
+    unsigned long long *timeline;
 };
+
+constexpr int kTimelineSlots = 32;
+__device__ __forceinline__ void timeline_stamp(unsigned long long *tl, int slot) {
+    if (tl != nullptr && (threadIdx.x & 31) == 0) {
+        tl[(size_t)blockIdx.x * kTimelineSlots + slot] = ptx::globaltimer_ns();
+        tl[(size_t)blockIdx.x * kTimelineSlots + 16 + slot] = ptx::sm_clock();
+    }
+}
 
 constexpr int kSlotStride = 32;  // slots reserved per query (k <= 32 on the register-list path)
 
@@ -314,6 +326,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     uint32_t tmem_base = 0;
     const uint16_t cta_mask = (uint16_t)((1u << p.n_groups) - 1u);
     const int slice_rows = kTileRows / (p.multicast ? p.n_groups : 1);  // rows of each box this CTA fetches
+    if (warp == 0) timeline_stamp(p.timeline, 0);
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&tmap_docs);
         for (int s = 0; s < S; ++s) {
@@ -414,13 +427,16 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                     }
                 }
                 __syncwarp();
+                if (it == 0) timeline_stamp(p.timeline, 1);
             }
         }
+        timeline_stamp(p.timeline, 2);
     } else if (warp == 5) {
         uint32_t it = 0;
         uint32_t lt = 0;  // local tile counter
         const uint32_t q_base = ptx::smem_u32(q_smem);
         const uint32_t a_base = ptx::smem_u32(a_smem);
+        timeline_stamp(p.timeline, 3);
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
@@ -450,6 +466,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 __syncwarp();
             }
         }
+        timeline_stamp(p.timeline, 4);
     } else if (NQ <= 32 && p.k <= 32) {
         // epilogue warps 0..3 (TMEM lane quadrant = warp), per-warp top-k lists in REGISTERS
         constexpr int RQ = NQ <= 32 ? NQ : 1;  // (keeps the arrays small when this branch is dead)
@@ -462,6 +479,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             tau[q] = q < nq ? neg_inf() : __int_as_float(0x7f800000);
         }
         uint32_t lt = 0;
+        if (warp == 0) timeline_stamp(p.timeline, 5);
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
@@ -546,7 +564,10 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty + as);
+            if (p.timeline != nullptr && warp == 0 && ((lt + 1) & lt) == 0 && lt < 64)  // tiles 0, 1, 3, 7, 15, 31, 63
+                timeline_stamp(p.timeline, 6 + (31 - __clz((int)lt + 1)));
         }
+        if (warp == 0) timeline_stamp(p.timeline, 13);
         // Every MMA (hence every TMA write) of this CTA has retired once the last accumulator was
         // handed over: the document ring is free, park this warp's lists there for the CTA merge.
         float *ms = reinterpret_cast<float *>(a_smem);
@@ -637,6 +658,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             ci[idx] = L.i[b * L.kcap + e];
         }
     }
+    if (warp == 0) timeline_stamp(p.timeline, 14);
     if (warp == 4) {
         __syncwarp();
         ptx::tc_fence_after_sync();

@@ -78,6 +78,15 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
+// wall clock in ns, shared by all SMs (diagnostic stamps only)
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ uint64_t sm_clock() { return (uint64_t)clock64(); }  // this SM's cycle counter
+
 __device__ __forceinline__ void prefetch_tmap(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

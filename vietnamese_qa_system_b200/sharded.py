@@ -101,6 +101,8 @@ class ShardedFlat:
         self.exchange = exchange
         self._bufs = {}
         self._epoch = 0
+        self._side = None      # side stream of the pipelined search (exchange + merge of batch i under scan i+1)
+        self._last = {}        # (b, k, slot) -> event after which the slot's buffers may be reused
 
     @staticmethod
     def _layout(b: int, k: int):
@@ -108,8 +110,11 @@ class ShardedFlat:
         block = (ids_off + b * k * 8 + 15) // 16 * 16
         return ids_off, block
 
-    def _buffers(self, b: int, k: int):
-        key = (b, k)
+    def _buffers(self, b: int, k: int, slot: int = 0):
+        """Per (B, k, slot): the packed local result block, the gather buffer (or the peer-memory exchange), the
+        merged outputs and a PRIVATE scan workspace -- two slots never share scratch, so searches of different
+        slots may be in flight together (and searches issued from different host threads must use different slots)."""
+        key = (b, k, slot)
         buf = self._bufs.get(key)
         if buf is None:
             dev = self.shard.device
@@ -119,6 +124,7 @@ class ShardedFlat:
             i_view = local[ids_off:ids_off + b * k * 8].view(torch.int64).view(b, k)
             out_s = torch.empty((b, k), dtype=torch.float32, device=dev)
             out_i = torch.empty((b, k), dtype=torch.int64, device=dev)
+            ws = torch.empty(self.shard.workspace_bytes(b, k, self.mode), dtype=torch.uint8, device=dev)
             p2p = None
             if self.exchange in ("auto", "p2p") and k <= 32 and self.world <= 16:
                 try:
@@ -128,21 +134,101 @@ class ShardedFlat:
                         raise
                     p2p = None
             gathered = None if p2p is not None else torch.empty(block * self.world, dtype=torch.uint8, device=dev)
-            buf = (local, gathered, s_view, i_view, ids_off, out_s, out_i, p2p)
+            buf = (local, gathered, s_view, i_view, ids_off, out_s, out_i, p2p, ws)
             self._bufs[key] = buf
         return buf
 
+    def _exchange(self, buf, b: int, k: int):
+        local, gathered, _, _, ids_off, out_s, out_i, p2p, _ = buf
+        if p2p is not None:
+            return p2p.push_and_merge(local, b, k, ids_off, out_s, out_i)
+        dist.all_gather_into_tensor(gathered, local, group=self.group)
+        return self._ops.merge_topk_packed(gathered, self.world, b, k, ids_off, out_s, out_i)
+
     def search(self, queries: torch.Tensor, k: int, mode: Optional[str] = None):
-        """Returns (scores [B,k], ids [B,k]) -- identical on every rank.  The returned tensors are
-        reused by the next search with the same (B, k)."""
+        """Returns (scores [B,k], ids [B,k]) -- identical on every rank, valid in stream order on the current
+        stream.  The returned tensors are reused by the next search with the same (B, k)."""
         if mode is not None:
             self.mode = mode
         if self.world == 1:
             return self.shard.search(queries, k, self.mode)
         b = int(queries.shape[0]) if queries.dim() == 2 else 1
-        local, gathered, s_view, i_view, ids_off, out_s, out_i, p2p = self._buffers(b, k)
-        self.shard.search(queries, k, self.mode, s_view, i_view)
-        if p2p is not None:
-            return p2p.push_and_merge(local, b, k, ids_off, out_s, out_i)
-        dist.all_gather_into_tensor(gathered, local, group=self.group)
-        return self._ops.merge_topk_packed(gathered, self.world, b, k, ids_off, out_s, out_i)
+        buf = self._buffers(b, k)
+        self.shard.search(queries, k, self.mode, buf[2], buf[3], workspace=buf[8])
+        return self._exchange(buf, b, k)
+
+    def search_pipelined(self, queries: torch.Tensor, k: int, slot: int):
+        """One search whose exchange + merge run on a side stream, so that the NEXT call's scan (another ``slot``)
+        overlaps them: the scan of batch i+1 streams the shard while batch i's 384-byte-per-query candidates cross
+        NVLink and are merged.  Returns ``(scores, ids, event)``; the tensors hold the result once ``event`` has
+        completed (``event.synchronize()`` on the host, or ``stream.wait_event(event)``), and belong to ``slot``
+        until the next call with the same slot.  Alternate slots 0 / 1.  ``queries`` must stay untouched until the
+        scan has run (stream order on the current stream)."""
+        b = int(queries.shape[0]) if queries.dim() == 2 else 1
+        dev = self.shard.device
+        main = torch.cuda.current_stream(dev)
+        if self.world == 1:
+            ws = self._bufs.get(("ws1", b, k, slot))
+            if ws is None:
+                ws = (torch.empty(self.shard.workspace_bytes(b, k, self.mode), dtype=torch.uint8, device=dev),
+                      torch.empty((b, k), dtype=torch.float32, device=dev),
+                      torch.empty((b, k), dtype=torch.int64, device=dev))
+                self._bufs[("ws1", b, k, slot)] = ws
+            s, i = self.shard.search(queries, k, self.mode, ws[1], ws[2], workspace=ws[0])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            return s, i, ev
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        buf = self._buffers(b, k, slot)
+        prev = self._last.get((b, k, slot))
+        if prev is not None:
+            main.wait_event(prev)          # the slot's previous exchange has read `local` and written the outputs
+        self.shard.search(queries, k, self.mode, buf[2], buf[3], workspace=buf[8])
+        scanned = torch.cuda.Event()
+        scanned.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(scanned)
+            out_s, out_i = self._exchange(buf, b, k)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._last[(b, k, slot)] = done
+        return out_s, out_i, done
+
+    def search_host_pipelined(self, queries_host: torch.Tensor, k: int, slot: int):
+        """``search_pipelined`` with HOST buffers: pinned float32 ``[B, dim]`` queries in, pinned ``(scores, ids)`` out.
+        Enqueues the H2D copy of the queries, the scan, the exchange + merge and the D2H copy of the merged result and
+        returns ``(scores_host, ids_host, event)`` at once; the host tensors hold the result when ``event`` has
+        completed.  A serving loop keeps two slots in flight: it reads slot s's result (``event.synchronize()``)
+        just before re-issuing slot s, so the per-step host wake-up is off the critical path while every byte of
+        every step still crosses PCIe inside the loop.  ``queries_host`` must be pinned and stay untouched until
+        ``event`` has completed."""
+        if queries_host.is_cuda or queries_host.dtype != torch.float32 or not queries_host.is_contiguous():
+            raise ValueError("queries_host must be a contiguous float32 CPU tensor")
+        if not queries_host.is_pinned():
+            raise ValueError("queries_host must be pinned (page-locked) for an asynchronous copy")
+        if self.world == 1:
+            return self.shard.search_host_async(queries_host, k, self.mode, slot=slot)
+        b = int(queries_host.shape[0])
+        dev = self.shard.device
+        key = ("host", b, k, slot)
+        st = self._bufs.get(key)
+        if st is None:
+            st = (torch.empty((b, self.shard.dim), dtype=torch.float32, device=dev),
+                  torch.empty((b, k), dtype=torch.float32).pin_memory(),
+                  torch.empty((b, k), dtype=torch.int64).pin_memory())
+            self._bufs[key] = st
+        q_dev, hs, hi = st
+        main = torch.cuda.current_stream(dev)
+        prev = self._last.get((b, k, slot))
+        if prev is not None:
+            main.wait_event(prev)          # the slot's previous D2H copies are done (q_dev is re-written below)
+        q_dev.copy_(queries_host, non_blocking=True)
+        out_s, out_i, done = self.search_pipelined(q_dev, k, slot)
+        with torch.cuda.stream(self._side):
+            hs.copy_(out_s, non_blocking=True)
+            hi.copy_(out_i, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._last[(b, k, slot)] = done
+        return hs, hi, done
