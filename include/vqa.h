@@ -145,7 +145,6 @@ typedef struct vqa_tuning {
     int32_t mma_stages;    /* cap on ring stages, 0 = auto                                                        */
     int32_t mma_groups;    /* smem-resident kernel: query chunks side by side per launch, 1..4 (4)                */
     int32_t mma_multicast; /* those chunks as a cluster with TMA multicast, 0|1 (1)                               */
-    int32_t mma_tb;        /* tournament bound in the smem-resident kernel, 0|1                                   */
     int32_t ts_qs;         /* TMEM-resident-query kernel: QS variant (part of the query block in smem), 0|1 (1)   */
     int32_t ts_ks;         /* QS: 64-column query blocks kept in shared memory, -1 = auto, else 0..16             */
     int32_t ts_split;      /* TS kernel: hi+lo rows (1) or storage-precision screen (0), -1 = auto                */
@@ -158,6 +157,7 @@ typedef struct vqa_tuning {
     int32_t stream_max_b;  /* FAST: batches up to this size take the CUDA-core streaming kernel, 0..8 (2) ...     */
     int32_t stream_min_mb; /* ... when the shard is at least this many MB (its fixed cost is ~80 us higher), (8000)*/
     int32_t pair;          /* FAST: tensor-bound batches take the cta_group::2 pair kernel, 0|1                   */
+    int32_t dyn_tiles;     /* smem-resident kernel without clusters: CTAs take tiles from a shared counter, 0|1 (1)*/
     int32_t reserved[4];
 } vqa_tuning_t;
 

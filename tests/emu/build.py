@@ -83,6 +83,9 @@ def transform(name: str, src: str) -> str:
         src, d = re.subn(r"(static __device__ __noinline__ Entry reglist_(?:insert_one|merge32)\([^)]*\) \{\n)",
                          r"\1    if ((threadIdx.x & 31) == 0) ++emu_event_counter();\n", src)
         assert d == 2, d
+        src, d = re.subn(r"(uint32_t \(&ci\)\[NB\], bool cand_sorted\) \{\n)",
+                         r"\1    if ((threadIdx.x & 31) == 0) emu_event_counter() += NB;\n", src)
+        assert d == 1, d
     if name == "ts.cuh":
         src, a = re.subn(r'asm volatile\(\s*"tcgen05\.st\.sync\.aligned\.32x32b\.x16\.b32.*?: "memory"\);',
                          "ptx::model_tmem_st16(taddr, r);", src, flags=re.S)

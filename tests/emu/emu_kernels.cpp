@@ -219,8 +219,7 @@ int emu_reduce_u32(const float *cand_s, const uint32_t *cand_i, int n_lists, int
 // as api.cu does it.  rows: 16-bit storage [n_rows][dim]; ncol in {16, 32, 64, 128}; the batch is cut into chunks
 // of ncol / 2 queries handled side by side (n_groups = chunks).
 int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, const float *q, int n_queries, int k,
-                      long long first_id, int sm_count, int ncol, int stages, int kps, int multicast, int tb,
-                      unsigned long long *slots /* [n_queries][32], caller-initialised (zeros or garbage) */,
+                      long long first_id, int sm_count, int ncol, int stages, int kps, int multicast,
                       float *out_s, long long *out_i) {
     return guarded([&] {
         const int pass_nq = ncol / 2;
@@ -273,10 +272,15 @@ int emu_search_tensor(const void *rows, int bf16, long long n_rows, int dim, con
         a.cand_stride = cstride;
         a.tau_g = tau_g.data();
         a.epoch = 1;
-        a.slot_g = (tb && pass_nq <= 32 && k <= 32) ? slots : nullptr;  // api.cu's rule for the TB variants
+        // dynamic tile schedule (api.cu: launches without clusters) unless the test switches it off; the counter
+        // starts as garbage of another epoch, as a recycled workspace would hold
+        static unsigned long long tile_ctr = 0xdeadbeef00000007ull;
+        const char *dyn = std::getenv("VQA_DYN_TILES");
+        a.tile_ctr = (dyn == nullptr || std::atoi(dyn) != 0) ? &tile_ctr : nullptr;
         if (vqa::launch_mma(a, nullptr) != cudaSuccess) throw std::runtime_error("tensor scan launch failed");
+        if (a.tile_ctr != nullptr && g == 1 && tile_ctr != 0) throw std::runtime_error("tile counter not reset by the last CTA");
         if (vqa::launch_reduce_u32(cand_s.data(), cand_i.data(), cstride, k, grid, k, k, first_id, out_s, out_i,
-                                   n_queries, tau_g.data(), g, pass_nq, nullptr, emu_opts(), nullptr, a.slot_g) != cudaSuccess)
+                                   n_queries, tau_g.data(), g, pass_nq, nullptr, emu_opts(), nullptr) != cudaSuccess)
             throw std::runtime_error("reduce launch failed");
     });
 }

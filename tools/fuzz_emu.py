@@ -75,9 +75,8 @@ while time.time() < t_end:
             q = T._unit(rng, b, dim)
             out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
             if os.environ.get("FUZZ_VERBOSE"): print("mma", kind, dim, n, b, k, sm, ncol, stages, kps, mc, flush=True)
-            tb = int(rng.integers(2)); slots = np.zeros((b, 32), np.uint64)   # opt-in tournament bound (TB variants)
-            rc = L.emu_search_tensor(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, ncol, stages, kps, mc, tb, T.ptr(slots), T.ptr(out_s), T.ptr(out_i))
-            tag = ("mma", kind, dim, n, b, k, sm, ncol, stages, kps, mc, tb); tol = 1e-5
+            rc = L.emu_search_tensor(T.ptr(raw), int(kind == "bf16"), n, dim, T.ptr(q), b, k, 7, sm, ncol, stages, kps, mc, T.ptr(out_s), T.ptr(out_i))
+            tag = ("mma", kind, dim, n, b, k, sm, ncol, stages, kps, mc); tol = 1e-5
         else:
             split = int(rng.integers(2)); k = int(rng.choice([1, 5, 10, 26] + ([40, 100] if qs else []))) if not split else int(rng.choice([3, 20, 32, 50]))
             b = int(rng.integers(1, 200)); kps = int(rng.choice([d for d in (1, 2, 3, 4) if kb % d == 0])); stages = int(rng.integers(2, 6))

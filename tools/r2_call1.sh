@@ -19,7 +19,7 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o $O/cta2_probe too
 timeout 60 $O/cta2_probe 2>&1 | tail -n 14
 timeout 60 $O/cta2_probe --alloc-leader-only 2>&1 | tail -n 14
 
-group "headline kernel at the 8-GPU shard size (1.25 M rows): tournament bound, early-exit reduce" \
+group "headline kernel at the 8-GPU shard size (1.25 M rows): tournament bound (since removed), early-exit reduce" \
   ROWS=1250000 K=10 MODE=tensor BATCHES=1,2,8,16,32 ITERS=50 \
   "VARIANTS=-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1;VQA_MMA_TB=1,VQA_REDUCE_EARLY=1"
 group "streaming kernel vs tcgen05 for B = 1, 2, 4 at the shard size" \

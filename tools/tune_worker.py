@@ -1,5 +1,5 @@
 """One timing run; shape from the environment (ROWS, DIM, DTYPE, BATCHES, MODE, K), kernel variants as
-VARIANTS="-;VQA_MMA_TB=1;VQA_REDUCE_EARLY=1,VQA_MMA_TB=1": each is applied to the ONE generated index through
+VARIANTS="-;VQA_TS_KS=4;VQA_REDUCE_EARLY=0,VQA_TS_QS=0": each is applied to the ONE generated index through
 FlatShard.set_tuning (the library reads its environment only in vqa_index_create; "-" = the handle as created)."""
 import json
 import os

@@ -40,13 +40,13 @@ ABI_VERSION = 120  # VQA_VERSION this binding was written against (include/vqa.h
 class Tuning(ctypes.Structure):
     """vqa_tuning_t (include/vqa.h): the kernel-selection knobs stored in an index handle."""
     _fields_ = [(n, ctypes.c_int32) for n in (
-        "size", "ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "mma_tb", "ts_qs",
+        "size", "ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "ts_qs",
         "ts_ks", "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-        "stream_max_b", "stream_min_mb", "pair")] + [("reserved", ctypes.c_int32 * 4)]
+        "stream_max_b", "stream_min_mb", "pair", "dyn_tiles")] + [("reserved", ctypes.c_int32 * 4)]
 
-    KNOBS = ("ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "mma_tb", "ts_qs", "ts_ks",
+    KNOBS = ("ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "ts_qs", "ts_ks",
              "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-             "stream_max_b", "stream_min_mb", "pair")
+             "stream_max_b", "stream_min_mb", "pair", "dyn_tiles")
 
     def update(self, **knobs) -> "Tuning":
         for key, val in knobs.items():

@@ -159,7 +159,6 @@ const KnobSpec kKnobs[] = {
     {"VQA_MMA_STAGES", &vqa_tuning_t::mma_stages, 0, vqa::kMaxStages, 0},
     {"VQA_MMA_GROUPS", &vqa_tuning_t::mma_groups, 1, 4, 4},
     {"VQA_MMA_MULTICAST", &vqa_tuning_t::mma_multicast, 0, 1, 1},
-    {"VQA_MMA_TB", &vqa_tuning_t::mma_tb, 0, 1, 0},
     {"VQA_TS_QS", &vqa_tuning_t::ts_qs, 0, 1, 1},
     {"VQA_TS_KS", &vqa_tuning_t::ts_ks, -1, 16, -1},
     {"VQA_TS_SPLIT", &vqa_tuning_t::ts_split, -1, 1, -1},
@@ -172,6 +171,7 @@ const KnobSpec kKnobs[] = {
     {"VQA_STREAM_MAX_B", &vqa_tuning_t::stream_max_b, 0, 8, 2},
     {"VQA_STREAM_MIN_MB", &vqa_tuning_t::stream_min_mb, 0, 1 << 30, 8000},
     {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 0},
+    {"VQA_DYN_TILES", &vqa_tuning_t::dyn_tiles, 0, 1, 1},
 };
 
 void tuning_defaults(vqa_tuning_t *t) {
@@ -653,8 +653,8 @@ int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int3
     if (!bytes) return fail(VQA_E_INVALID, "bytes is null");
     (void)mode;
     // candidates: per CTA, per query, k entries of (float score, u32 row); + one shared-threshold slot per query
-    // (+ 32 tournament slots per query for the opt-in TB scan variants)
-    *bytes = cand_elems(h, n_queries, k) * 8 + (size_t)n_queries * 8 + 512 + (size_t)n_queries * 32 * 8 + 256;
+    // + 64 tile counters of the dynamic tile schedule (one per scan launch of a search) + alignment slack
+    *bytes = cand_elems(h, n_queries, k) * 8 + (size_t)n_queries * 8 + 64 * 8 + 768;
     return VQA_OK;
 }
 
@@ -685,8 +685,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     uint32_t *cand_i = reinterpret_cast<uint32_t *>(cand_s + cand_elems(h, n_queries, k));
     unsigned long long *tau_g = reinterpret_cast<unsigned long long *>(
         (reinterpret_cast<uintptr_t>(cand_i + cand_elems(h, n_queries, k)) + 255) & ~(uintptr_t)255);
-    unsigned long long *slot_g = reinterpret_cast<unsigned long long *>(
-        (reinterpret_cast<uintptr_t>(tau_g + n_queries) + 255) & ~(uintptr_t)255);  // [n_queries][32]
+    unsigned long long *tile_ctr = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(tau_g + n_queries) + 255) & ~(uintptr_t)255);  // [64], one per scan launch
     const long long cand_stride = (long long)n_queries * k;
     vqa::ReduceOpts ropts;
     ropts.select = h->tune.reduce_select;
@@ -739,6 +739,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.cand_stride = cstride;
             a.tau_g = tau_g + l0;
             a.epoch = epoch;
+            a.timeline = (h->timeline && h->timeline_bytes >= (size_t)a.grid * 32 * 8) ? h->timeline : nullptr;
             cudaError_t e = vqa::launch_ts(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "TS scan launch failed: %s", cudaGetErrorString(e));
             vqa::Rescore rs;
@@ -817,11 +818,9 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.cand_stride = cstride;
             a.tau_g = tau_g + l0;
             a.epoch = epoch;
-            // opt-in tournament bound: register-list path only (<= 32 queries per CTA, list length <= 32)
-            const bool tb = h->tune.mma_tb != 0 && pl.pass_nq <= 32 && kscan <= 32;
-            a.slot_g = tb ? slot_g + (long long)l0 * 32 : nullptr;
             a.pdl = (l0 > 0 && h->tune.pdl_chain) ? 1 : 0;
             a.tma_hint = h->tune.tma_hint;
+            a.tile_ctr = h->tune.dyn_tiles ? tile_ctr + (l0 / per_launch) % 64 : nullptr;
             a.timeline = (h->timeline && h->timeline_bytes >= (size_t)a.grid * 32 * 8) ? h->timeline : nullptr;
             cudaError_t e = vqa::launch_mma(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
@@ -836,7 +835,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, pl.ss_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
                                        (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
-                                       ropts, pl.ss_split ? nullptr : &rs, a.slot_g);
+                                       ropts, pl.ss_split ? nullptr : &rs);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;

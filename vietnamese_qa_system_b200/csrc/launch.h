@@ -47,10 +47,10 @@ struct MmaLaunch {
     long long cand_stride;
     unsigned long long *tau_g;  // [nq] shared thresholds for this pass (or nullptr)
     uint32_t epoch;
-    unsigned long long *slot_g = nullptr;  // opt-in TB variants: [nq][32] tournament slots (see MmaParams), else nullptr
     int pdl = 0;  // opt-in: launch with programmatic stream serialization (2nd+ scan of one search, see mma_launch.cu)
     int tma_hint = 1;  // L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last
     unsigned long long *timeline = nullptr;  // diagnostic per-CTA stamps (vqa_debug_timeline), normally nullptr
+    unsigned long long *tile_ctr = nullptr;  // dynamic tile schedule (launches without clusters), see MmaParams
 };
 
 struct TsLaunch {
@@ -77,6 +77,7 @@ struct TsLaunch {
     int pdl = 0;  // opt-in: launch with programmatic stream serialization (2nd+ scan of one search)
     int qs = 0;   // 1: the QS kernel variant (part of the query block in shared memory); opt-in, see ts.cuh
     int ks = 0;   // QS: 64-column blocks of the query block kept in shared memory
+    unsigned long long *timeline = nullptr;  // diagnostic per-CTA counters (vqa_debug_timeline), normally nullptr
 };
 
 cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st);
@@ -111,7 +112,7 @@ cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long 
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                               int list_mod, int queries_per_group, cudaStream_t st, const ReduceOpts &opts,
-                              const Rescore *rs = nullptr, unsigned long long *slot_reset = nullptr);
+                              const Rescore *rs = nullptr);
 struct WaitFlags {
     const unsigned long long *flags = nullptr;
     int n = 0;

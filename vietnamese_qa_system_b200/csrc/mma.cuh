@@ -61,11 +61,11 @@ struct MmaParams {
     // k-th best).  A document scoring below any list's k-th best cannot be in the global top-k.
     unsigned long long *tau_g;  // [nq] for this pass, or nullptr
     uint32_t epoch;
-    // TB variants ("tournament bound", opt-in): [nq][kSlotStride] slots, same encoding as tau_g.  List l of a
-    // query publishes its BEST score into slot l % k; the k slots then hold the scores of k distinct documents,
-    // so their minimum is a lower bound of the global k-th best -- close to the exact one, because the top-k
-    // documents mostly sit in different lists -- long before any single list's own k-th best gets there.
-    unsigned long long *slot_g;
+    // Dynamic tile schedule (launches without clusters): one 64-bit counter in the workspace, (epoch << 32) | next
+    // tile.  The producer warp of every CTA takes tiles from it instead of the static round-robin share, so an SM
+    // that streams slower than its neighbours (the per-CTA spread was 195..270 us of a 285 us launch at B = 1,
+    // profiles/r2_timeline_shard.json) simply takes fewer tiles and all CTAs finish together.  nullptr: static.
+    unsigned long long *tile_ctr;
     // Diagnostic (vqa_debug_timeline): [gridDim.x][kTimelineSlots] per-CTA stamps -- %globaltimer in slots 0..15,
     // clock64 in 16..31 -- of entry, first/last TMA issue, first MMA / last commit, queries staged, tiles
     // 0, 1, 3, 7, 15, 31, 63 and the last one leaving the epilogue, and exit.  nullptr (always, in normal use): off.
@@ -79,8 +79,6 @@ __device__ __forceinline__ void timeline_stamp(unsigned long long *tl, int slot)
         tl[(size_t)blockIdx.x * kTimelineSlots + 16 + slot] = ptx::sm_clock();
     }
 }
-
-constexpr int kSlotStride = 32;  // slots reserved per query (k <= 32 on the register-list path)
 
 // order-preserving float -> uint32 (larger float <=> larger uint), tagged with the search epoch
 __device__ __forceinline__ unsigned long long tau_encode(float f, uint32_t epoch) {
@@ -103,6 +101,45 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// ---- tile schedule -------------------------------------------------------------------------------
+constexpr int kTileRing = 32;  // published tile ids in flight per CTA (producer runs < 16 tiles ahead of the epilogue)
+
+// A CTA's FIRST tile: CAS on the epoch-tagged counter, so a stale or uninitialised word reads as "0 tiles taken".
+// Later tiles are plain atomicAdds issued one tile ahead (the counter already carries this launch's epoch by then),
+// so their ~1 us round trip hides behind the TMA issue loop.  Exactly gridDim.x grabs see a value >= n_tiles (every
+// CTA stops at its first); the one that sees the LAST of them zeroes the counter, so a CUDA-graph replay (same
+// epoch) starts clean.
+__device__ __forceinline__ uint32_t grab_first_tile(unsigned long long *ctr, uint32_t epoch) {
+    unsigned long long cur = ld_volatile_u64(ctr);
+    uint32_t t;
+    while (true) {
+        const bool fresh = (uint32_t)(cur >> 32) != epoch;
+        t = fresh ? 0u : (uint32_t)cur;
+        const unsigned long long nv = ((unsigned long long)epoch << 32) | (unsigned long long)(t + 1);
+        const unsigned long long seen = atomicCAS(ctr, cur, nv);
+        if (seen == cur) break;
+        cur = seen;
+    }
+    return t;
+}
+__device__ __forceinline__ int tile_from_ticket(unsigned long long *ctr, uint32_t t, int n_tiles) {
+    if (t == (uint32_t)n_tiles + gridDim.x - 1) *reinterpret_cast<volatile unsigned long long *>(ctr) = 0ull;
+    return t < (uint32_t)n_tiles ? (int)t : -1;
+}
+
+// tile `lt` of this CTA as seen by a consumer role (MMA issuer, epilogue): the static share, or what the producer
+// warp published (spin on shared memory; the producer is always ahead except at the very start)
+__device__ __forceinline__ int consumer_tile(const MmaParams &p, const volatile uint32_t *pub, const volatile int *tile_q,
+                                             uint32_t lt, int stream0, int n_streams) {
+    if (p.tile_ctr == nullptr) {
+        const long long t = stream0 + (long long)lt * n_streams;
+        return t < p.n_tiles ? (int)t : -1;
+    }
+    while (*pub <= lt) __nanosleep(20);
+    __threadfence_block();
+    return tile_q[lt % kTileRing];
 }
 
 template <int NCOL>
@@ -245,6 +282,48 @@ static __device__ __noinline__ Entry reglist_merge32(float ls, uint32_t li, floa
     return e;
 }
 
+// NB independent merges of 32 candidates (one per lane) into NB register lists, interleaved step by step.  One merge is
+// a chain of ~20 dependent shuffle+compare steps (~2000 cycles with a single warp per scheduler); while a kernel
+// warms up EVERY query of a tile needs one (nothing beats an empty list), and run one after the other they cost the
+// headline kernel ~40 us for its first tile and ~75 us over its first eight (profiles/r2_timeline_shard.json).
+// Interleaving NB = 8 chains keeps the shuffle pipe busy instead: same instructions, an eighth of the latency.
+// Lists ls/li are the epilogue's per-query arrays, `base` the first query of the batch (a constant after unrolling).
+template <int NB, int RQ>
+__device__ __forceinline__ void reglist_merge32_batch(float (&ls)[RQ], uint32_t (&li)[RQ], int base, float (&cs)[NB],
+                                                      uint32_t (&ci)[NB], bool cand_sorted) {
+    const int lane = threadIdx.x & 31;
+    if (!cand_sorted) {
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const bool keep = ((lane & stride) == 0) == ((lane & size) == 0 || size == 32);
+#pragma unroll
+                for (int b = 0; b < NB; ++b) bitonic_step(cs[b], ci[b], stride, keep);
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float rs = __shfl_sync(kFullMask, ls[base + b], 31 - lane);
+        const uint32_t ri = __shfl_sync(kFullMask, li[base + b], 31 - lane);
+        if (ranks_before<uint32_t>(rs, ri, cs[b], ci[b])) {
+            cs[b] = rs;
+            ci[b] = ri;
+        }
+    }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) bitonic_step(cs[b], ci[b], stride, (lane & stride) == 0);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        ls[base + b] = cs[b];
+        li[base + b] = ci[b];
+    }
+}
+
 // one 16-column group of this thread's document row.  SPLIT: score = acc_hi + acc_lo * lo_inv_scale
 // (column j = q_hi[j], column NQ + j = q_lo[j]); otherwise one column per query.
 template <int NCOL, bool SPLIT>
@@ -281,7 +360,7 @@ __device__ __forceinline__ void load_scores16(uint32_t taddr, int c0, float lo_i
 // SPLIT: hi + lo column per query (NCOL / 2 queries per CTA, scores good to fp32 rounding).
 // !SPLIT: one storage-precision column per query (NCOL queries per CTA): a SCREEN whose k + spare best
 // candidates are re-scored exactly by the reduce kernel (screen-then-rescore, k + spare <= 32).
-template <bool BF16, int NCOL, bool SPLIT, bool TB = false>
+template <bool BF16, int NCOL, bool SPLIT>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p) {
     constexpr int NQ = SPLIT ? NCOL / 2 : NCOL;  // queries per CTA
@@ -307,6 +386,9 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     uint64_t *tfull = bars + 2 * kMaxStages;     // [kMaxAccStages]
     uint64_t *tempty = tfull + kMaxAccStages;    // [kMaxAccStages]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kMaxAccStages);
+    volatile int *tile_q = reinterpret_cast<volatile int *>(reinterpret_cast<unsigned char *>(bars) + 512);  // [kTileRing]
+    volatile uint32_t *tile_pub = reinterpret_cast<volatile uint32_t *>(reinterpret_cast<unsigned char *>(bars) + 512 +
+                                                                         kTileRing * 4);
     ListView<uint32_t> L = list_carve<uint32_t>(reinterpret_cast<unsigned char *>(bars) + 1024, NQ, p.k);
 
     const int tid = threadIdx.x;
@@ -329,6 +411,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     if (warp == 0) timeline_stamp(p.timeline, 0);
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&tmap_docs);
+        *tile_pub = 0;
         for (int s = 0; s < S; ++s) {
             ptx::mbar_init(full + s, 1);
             ptx::mbar_init(empty + s, p.multicast ? p.n_groups : 1);  // every consumer CTA of the cluster
@@ -407,7 +490,23 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     // for UTMALDG / UTCHMMA); one elected lane issues the asynchronous instructions ----------
     if (warp == 4) {
         uint32_t it = 0;
-        for (int tile = stream0; tile < p.n_tiles; tile += n_streams) {
+        const bool dyn = p.tile_ctr != nullptr;
+        int tile = stream0 < p.n_tiles ? stream0 : -1;
+        if (dyn) {
+            tile = 0;
+            if (lane == 0) tile = tile_from_ticket(p.tile_ctr, grab_first_tile(p.tile_ctr, p.epoch), p.n_tiles);
+            tile = __shfl_sync(kFullMask, tile, 0);
+        }
+        for (uint32_t lt = 0;; ++lt) {
+            unsigned long long ticket = 0;
+            if (dyn && lane == 0) {
+                tile_q[lt % kTileRing] = tile;
+                __threadfence_block();
+                *tile_pub = lt + 1;
+                // ticket of tile lt + 1, taken now and looked at after this tile's loads are issued
+                if (tile >= 0) ticket = atomicAdd(p.tile_ctr, 1ull);
+            }
+            if (tile < 0) break;
             for (int kg = 0; kg < KG; ++kg, ++it) {
                 const int s = it % S;
                 const uint32_t ph = (it / S) & 1;
@@ -429,6 +528,13 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 __syncwarp();
                 if (it == 0) timeline_stamp(p.timeline, 1);
             }
+            if (dyn) {
+                if (lane == 0) tile = tile_from_ticket(p.tile_ctr, (uint32_t)ticket, p.n_tiles);
+                tile = __shfl_sync(kFullMask, tile, 0);
+            } else {
+                const long long t = stream0 + (long long)(lt + 1) * n_streams;
+                tile = t < p.n_tiles ? (int)t : -1;
+            }
         }
         timeline_stamp(p.timeline, 2);
     } else if (warp == 5) {
@@ -437,7 +543,8 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         const uint32_t q_base = ptx::smem_u32(q_smem);
         const uint32_t a_base = ptx::smem_u32(a_smem);
         timeline_stamp(p.timeline, 3);
-        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
+        for (;; ++lt) {
+            if (consumer_tile(p, tile_pub, tile_q, lt, stream0, n_streams) < 0) break;
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
             ptx::mbar_wait(tempty + as, aph ^ 1);
@@ -480,7 +587,9 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         }
         uint32_t lt = 0;
         if (warp == 0) timeline_stamp(p.timeline, 5);
-        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
+        for (;; ++lt) {
+            const int tile = consumer_tile(p, tile_pub, tile_q, lt, stream0, n_streams);
+            if (tile < 0) break;
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
             // pick up the other CTAs' thresholds (one coalesced load per warp, issued before the wait)
@@ -499,65 +608,59 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NCOL);
 #pragma unroll
             for (int c0 = 0; c0 < RQ; c0 += 16) {
+                constexpr int G = RQ < 16 ? RQ : 16;   // queries in this 16-column group
+                constexpr int NB = G < 8 ? G : 8;      // merges interleaved per batch
                 float v[16];
                 load_scores16<NCOL, SPLIT>(taddr, c0, p.lo_inv_scale, v);
                 bool any = false;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < RQ) any |= (v[j] >= tau[c0 + j]);
-                if (__ballot_sync(kFullMask, any && valid) == 0) continue;
+                for (int j = 0; j < G; ++j) any |= (v[j] >= tau[c0 + j]);
+                if (__ballot_sync(kFullMask, any && valid) == 0) continue;   // the common case once thresholds are up
+                unsigned m[G];
+                bool heavy = false;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (c0 + j < RQ) {
-                        constexpr int dummy = 0;
-                        (void)dummy;
-                        const int q = c0 + j;
-                        const bool pass = valid && v[j] >= tau[q];
-                        unsigned m = __ballot_sync(kFullMask, pass);
-                        if (m != 0) {
-                            float top_before = 0.f;
-                            if constexpr (TB) top_before = __shfl_sync(kFullMask, ls[q], 0);
-                            if (__popc(m) >= 4) {
-                                const Entry e = reglist_merge32(ls[q], li[q], pass ? v[j] : neg_inf(),
-                                                                pass ? base_row + lane : invalid_id<uint32_t>(), false);
-                                ls[q] = e.s;
-                                li[q] = e.i;
-                            } else {
-                                while (m) {
-                                    const int src = __ffs(m) - 1;
-                                    m &= m - 1;
-                                    const Entry e = reglist_insert_one(ls[q], li[q], __shfl_sync(kFullMask, v[j], src),
-                                                                       base_row + src);
-                                    ls[q] = e.s;
-                                    li[q] = e.i;
-                                }
-                            }
-                            const uint32_t last = __shfl_sync(kFullMask, li[q], p.k - 1);
-                            const float ts = __shfl_sync(kFullMask, ls[q], p.k - 1);
-                            if (last != invalid_id<uint32_t>() && ts > tau[q]) {
-                                tau[q] = ts;
-                                if (tau_g != nullptr && lane == 0) atomicMax(tau_g + q, tau_encode(ts, p.epoch));
-                            }
-                            if constexpr (TB) {
-                                // this list's best improved (rare: ~ln(n) times per list): publish it into the
-                                // list's slot, re-read the query's k slots and share their minimum as a threshold
-                                const float top_after = __shfl_sync(kFullMask, ls[q], 0);
-                                if (top_after > top_before && p.slot_g != nullptr && tau_g != nullptr) {
-                                    unsigned long long *sl = p.slot_g + (long long)(q0 + q) * kSlotStride;
-                                    const int my_slot = (stream0 * 4 + warp) % p.k;
-                                    if (lane == 0) atomicMax(sl + my_slot, tau_encode(top_after, p.epoch));
-                                    float b = __int_as_float(0x7f800000);
-                                    if (lane < p.k) b = tau_decode(ld_volatile_u64(sl + lane), p.epoch);
-                                    if (lane == my_slot) b = fmaxf(b, top_after);  // (lane 0's atomic may not be visible yet)
+                for (int j = 0; j < G; ++j) {
+                    m[j] = __ballot_sync(kFullMask, valid && v[j] >= tau[c0 + j]);
+                    heavy |= __popc(m[j]) >= 4;
+                }
+                if (heavy) {
+                    // warm-up tiles: many rows beat the (still low) thresholds -- merge all G queries of the group,
+                    // NB at a time (queries without a passing row merge 32 empty candidates: a no-op)
 #pragma unroll
-                                    for (int sh = 16; sh >= 1; sh >>= 1) b = fminf(b, __shfl_xor_sync(kFullMask, b, sh));
-                                    if (b > tau[q]) {
-                                        tau[q] = b;
-                                        if (lane == 0) atomicMax(tau_g + q, tau_encode(b, p.epoch));
-                                    }
-                                }
-                            }
+                    for (int h = 0; h < G / NB; ++h) {
+                        float cs[NB];
+                        uint32_t ci[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            const bool pass = (m[h * NB + b] >> lane) & 1u;
+                            cs[b] = pass ? v[h * NB + b] : neg_inf();
+                            ci[b] = pass ? base_row + lane : invalid_id<uint32_t>();
                         }
+                        reglist_merge32_batch<NB, RQ>(ls, li, c0 + h * NB, cs, ci, false);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        unsigned mm = m[j];
+                        while (mm) {
+                            const int src = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const Entry e = reglist_insert_one(ls[c0 + j], li[c0 + j], __shfl_sync(kFullMask, v[j], src),
+                                                               base_row + src);
+                            ls[c0 + j] = e.s;
+                            li[c0 + j] = e.i;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    if (m[j] == 0) continue;  // warp-uniform
+                    const int q = c0 + j;
+                    const uint32_t last = __shfl_sync(kFullMask, li[q], p.k - 1);
+                    const float ts = __shfl_sync(kFullMask, ls[q], p.k - 1);
+                    if (last != invalid_id<uint32_t>() && ts > tau[q]) {
+                        tau[q] = ts;
+                        if (tau_g != nullptr && lane == 0) atomicMax(tau_g + q, tau_encode(ts, p.epoch));
                     }
                 }
             }
@@ -580,7 +683,9 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
     } else {
         // epilogue warps 0..3: TMEM lane quadrant = warp; CTA-shared lists in shared memory (k > 32)
         uint32_t lt = 0;
-        for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
+        for (;; ++lt) {
+            const int tile = consumer_tile(p, tile_pub, tile_q, lt, stream0, n_streams);
+            if (tile < 0) break;
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
             ptx::mbar_wait(tfull + as, aph);
@@ -638,17 +743,35 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         // merge the four epilogue warps' lists per query (bitonic, in registers) and publish
         const float *ms = reinterpret_cast<const float *>(a_smem);
         const uint32_t *mi = reinterpret_cast<const uint32_t *>(a_smem + 4 * NQ * 32 * sizeof(float));
-        for (int q = warp; q < nq; q += kMmaThreads / 32) {
-            float s0 = ms[q * 32 + lane];
-            uint32_t i0 = mi[q * 32 + lane];
-            for (int w = 1; w < 4; ++w) {
-                const Entry e = reglist_merge32(s0, i0, ms[(w * NQ + q) * 32 + lane], mi[(w * NQ + q) * 32 + lane], true);
-                s0 = e.s;
-                i0 = e.i;
+        // every warp takes the queries q = warp, warp + 6, ... and merges them TOGETHER (interleaved chains, see
+        // reglist_merge32_batch): the four warps' lists arrive sorted, so each merge is 5 compare-exchange steps
+        constexpr int NW = kMmaThreads / 32;
+        constexpr int TQ = (NQ + NW - 1) / NW;
+        float s0[TQ];
+        uint32_t i0[TQ];
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+            const int q = warp + NW * t < NQ ? warp + NW * t : 0;
+            s0[t] = ms[q * 32 + lane];
+            i0[t] = mi[q * 32 + lane];
+        }
+        for (int w = 1; w < 4; ++w) {
+            float c_s[TQ];
+            uint32_t c_i[TQ];
+#pragma unroll
+            for (int t = 0; t < TQ; ++t) {
+                const int q = warp + NW * t < NQ ? warp + NW * t : 0;
+                c_s[t] = ms[(w * NQ + q) * 32 + lane];
+                c_i[t] = mi[(w * NQ + q) * 32 + lane];
             }
-            if (lane < p.k) {
-                cs[q * p.k + lane] = s0;
-                ci[q * p.k + lane] = i0;
+            reglist_merge32_batch<TQ, TQ>(s0, i0, 0, c_s, c_i, true);
+        }
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+            const int q = warp + NW * t;
+            if (q < nq && lane < p.k) {
+                cs[q * p.k + lane] = s0[t];
+                ci[q * p.k + lane] = i0[t];
             }
         }
     } else {

@@ -10,7 +10,7 @@ static unsigned long long tma_policy(int v) {
     return v == 0 ? 0x1000000000000000ull : (v == 2 ? 0x14F0000000000000ull : 0x12F0000000000000ull);
 }
 
-template <bool BF16, int NCOL, bool SPLIT, bool TB = false>
+template <bool BF16, int NCOL, bool SPLIT>
 static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     MmaParams p;
     p.q = a.q;
@@ -34,10 +34,10 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     // side-by-side chunks re-read each tile from L2: keep it there (normal policy) instead of evict-first
     p.tma_policy = a.n_groups > 1 ? 0x1000000000000000ull : tma_policy(a.tma_hint);
     p.multicast = a.multicast;
-    p.slot_g = TB ? a.slot_g : nullptr;
     p.timeline = a.timeline;
+    p.tile_ctr = (a.n_groups == 1 && !a.multicast) ? a.tile_ctr : nullptr;
     const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps, SPLIT ? 1 : 0);
-    auto kern = mma_topk_kernel<BF16, NCOL, SPLIT, TB>;
+    auto kern = mma_topk_kernel<BF16, NCOL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (!a.multicast && !a.pdl) {
@@ -122,17 +122,6 @@ int mma_max_active_clusters(bool bf16, int ncol, int split, int cluster, size_t 
 
 template <bool BF16>
 static cudaError_t launch_mma_t(const MmaLaunch &a, cudaStream_t st) {
-    // TB variants (tournament bound, opt-in): register-list path only (<= 32 queries per CTA, k <= 32)
-    if (a.slot_g != nullptr && a.tau_g != nullptr && a.k <= 32) {
-        if (!a.split) {
-            if (a.ncol == 16) return launch_mma_one<BF16, 16, false, true>(a, st);
-            if (a.ncol == 32) return launch_mma_one<BF16, 32, false, true>(a, st);
-        } else {
-            if (a.ncol == 16) return launch_mma_one<BF16, 16, true, true>(a, st);
-            if (a.ncol == 32) return launch_mma_one<BF16, 32, true, true>(a, st);
-            if (a.ncol == 64) return launch_mma_one<BF16, 64, true, true>(a, st);
-        }
-    }
     if (!a.split) {
         switch (a.ncol) {
             case 16: return launch_mma_one<BF16, 16, false>(a, st);

@@ -56,6 +56,11 @@ struct TsParams {
     int n_groups;
     int multicast;
     int ks;        // QS variants: the LAST ks 64-column blocks of the query block live in shared memory, not TMEM
+    // Diagnostic (vqa_debug_timeline), normally nullptr: per CTA 32 uint64 -- 0 entry / 15 exit (%globaltimer ns),
+    // SM-clock cycles: 1 producer waiting for a free ring stage, 2 MMA warp waiting for documents, 3 MMA warp waiting
+    // for a free accumulator stage, 4 MMA warp's whole loop, 5 epilogue warp 0 waiting for an accumulator, 6 its whole
+    // loop, 7 its list flushes (count), 8 tiles of this CTA, 9 producer's whole loop
+    unsigned long long *timeline;
 };
 
 constexpr int kTsQBlockBytes = kTsRows * kBlockK * 2;  // 16 KB: 128 query rows x one 64-column block, 128B-swizzled
@@ -153,6 +158,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     const uint32_t idesc = (1u << 4) | ((p.a_fp16 ? 0u : (DOC_BF16 ? 1u : 0u)) << 7) | ((DOC_BF16 ? 1u : 0u) << 10) |
                            ((uint32_t)(kTsDocs >> 3) << 17) | ((uint32_t)(kTsRows >> 4) << 24);
 
+    if (p.timeline != nullptr && tid == 0) p.timeline[(size_t)blockIdx.x * 32] = ptx::globaltimer_ns();
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&tmap_docs);
         for (int s = 0; s < S; ++s) {
@@ -181,11 +187,15 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         // ===== TMA producer =====
         named_bar_arrive(1, kMmaThreads);  // (does not wait for the query block: documents start streaming now)
         uint32_t it = 0;
+        const bool tl = p.timeline != nullptr;
+        unsigned long long w_empty = 0, t_loop = tl ? ptx::sm_clock() : 0;
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams) {
             for (int kg = 0; kg < KG; ++kg, ++it) {
                 const int s = it % S;
                 const uint32_t ph = (it / S) & 1;
+                const unsigned long long t_w = tl ? ptx::sm_clock() : 0;
                 ptx::mbar_wait(empty + s, ph ^ 1);
+                if (tl) w_empty += ptx::sm_clock() - t_w;
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(full + s, stage_bytes);
                     for (int j = 0; j < KPS; ++j) {
@@ -202,6 +212,10 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 __syncwarp();
             }
         }
+        if (tl && lane == 0) {
+            p.timeline[(size_t)blockIdx.x * 32 + 1] = w_empty;
+            p.timeline[(size_t)blockIdx.x * 32 + 9] = ptx::sm_clock() - t_loop;
+        }
     } else if (warp == 5) {
         // ===== MMA issuer: waits for the query block (named barrier 1), then D = Q * docs^T =====
         __syncwarp();
@@ -210,16 +224,22 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         uint32_t it = 0, lt = 0;
         const uint32_t ring = ptx::smem_u32(a_smem);
         const uint32_t qs_base = ptx::smem_u32(q_smem);
+        const bool tl = p.timeline != nullptr;
+        unsigned long long w_full = 0, w_tempty = 0, t_loop = tl ? ptx::sm_clock() : 0;
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
+            unsigned long long t_w = tl ? ptx::sm_clock() : 0;
             ptx::mbar_wait(tempty + as, aph ^ 1);
+            if (tl) w_tempty += ptx::sm_clock() - t_w;
             ptx::tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)(ACOLS + as * kTsDocs);
             for (int kg = 0; kg < KG; ++kg, ++it) {
                 const int s = it % S;
                 const uint32_t ph = (it / S) & 1;
+                t_w = tl ? ptx::sm_clock() : 0;
                 ptx::mbar_wait(full + s, ph);
+                if (tl) w_full += ptx::sm_clock() - t_w;
                 ptx::tc_fence_after_sync();
                 if (ptx::elect_one()) {
                     for (int j = 0; j < KPS; ++j) {
@@ -244,6 +264,13 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 }
                 __syncwarp();
             }
+        }
+        if (tl && lane == 0) {
+            unsigned long long *o = p.timeline + (size_t)blockIdx.x * 32;
+            o[2] = w_full;
+            o[3] = w_tempty;
+            o[4] = ptx::sm_clock() - t_loop;
+            o[8] = lt;
         }
     } else {
         // ===== warps 0-3: thread = query row =====
@@ -379,7 +406,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 lst_i[e * LR + lrow] = invalid_id<uint32_t>();
             }
         }
-        auto flush = [&]() {
+        auto flush = [&]() __attribute__((always_inline)) {
             if constexpr (KL > 0) {
                 const int wmax = __reduce_max_sync(kFullMask, cnt);
                 for (int b = 0; b < wmax; ++b) {
@@ -400,16 +427,18 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                     }
                 }
                 cnt = 0;
-                // threshold = score of rank k-1 (p.k <= KL), once that slot is filled
-                float ts = neg_inf();
-                uint32_t ti = invalid_id<uint32_t>();
+                // threshold = score of rank k-1 (p.k <= KL), once that slot is filled.  Written as reductions over
+                // the whole (sorted) list: `if (e == p.k - 1) ts = rs[e]` is turned into rs[p.k - 1] by the compiler,
+                // and ONE dynamic index sends both register arrays to local memory (128-byte stack frame, ~12 LDL +
+                // 12 STL per tile and warp -- r2_ts_b256.ncu-rep: 14.8 M local requests per launch)
+                float ts = __int_as_float(0x7f800000);
+                int filled = 0;
 #pragma unroll
-                for (int e = 0; e < KLR; ++e)
-                    if (e == p.k - 1) {
-                        ts = rs[e];
-                        ti = ri[e];
-                    }
-                if (ti != invalid_id<uint32_t>() && ts > tau) {
+                for (int e = 0; e < KLR; ++e) {
+                    ts = fminf(ts, e < p.k ? rs[e] : __int_as_float(0x7f800000));
+                    filled += (e < p.k && ri[e] != invalid_id<uint32_t>()) ? 1 : 0;
+                }
+                if (filled == p.k && ts > tau) {
                     tau = ts;
                     if (tg != nullptr) atomicMax(tg, tau_encode(ts, p.epoch));
                 }
@@ -463,12 +492,16 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         };
 
         uint32_t lt = 0;
+        const bool tl = p.timeline != nullptr && warp == 0;
+        unsigned long long w_tfull = 0, n_flush = 0, t_loop = tl ? ptx::sm_clock() : 0;
         for (int tile = stream0; tile < p.n_tiles; tile += n_streams, ++lt) {
             const int as = lt % AS;
             const uint32_t aph = (lt / AS) & 1;
             unsigned long long graw = 0;
             if (tg != nullptr) graw = ld_volatile_u64(tg);
+            const unsigned long long t_w = tl ? ptx::sm_clock() : 0;
             ptx::mbar_wait(tfull + as, aph);
+            if (tl) w_tfull += ptx::sm_clock() - t_w;
             ptx::tc_fence_after_sync();
             if (tg != nullptr) tau = fmaxf(tau, tau_decode(graw, p.epoch));
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ACOLS + as * kTsDocs);
@@ -533,7 +566,10 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                                     ++cnt;
                                 }
                             }
-                            if (__ballot_sync(kFullMask, cnt > CAP - 16) != 0) flush();
+                            if (__ballot_sync(kFullMask, cnt > CAP - 16) != 0) {
+                                flush();
+                                ++n_flush;
+                            }
                         }
                     }
                 }
@@ -579,6 +615,12 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             if (lane == 0) ptx::mbar_arrive(tempty + as);
             }  // classic epilogue (QS = false)
         }
+        if (tl && lane == 0) {
+            unsigned long long *o = p.timeline + (size_t)blockIdx.x * 32;
+            o[5] = w_tfull;
+            o[6] = ptx::sm_clock() - t_loop;
+            o[7] = n_flush;
+        }
         flush();
         // 3. publish this row's list
         if (live && !is_lo) {
@@ -602,6 +644,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
 
     ptx::tc_fence_before_sync();
     __syncthreads();
+    if (p.timeline != nullptr && tid == 0) p.timeline[(size_t)blockIdx.x * 32 + 15] = ptx::globaltimer_ns();
     if (warp == 4) {
         ptx::tc_fence_after_sync();
         ptx::tmem_dealloc(tmem_base, 512);

@@ -28,6 +28,7 @@ static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     p.n_groups = a.n_groups;
     p.multicast = a.multicast;
     p.ks = QS ? a.ks : 0;
+    p.timeline = a.timeline;
     const size_t smem = ts_smem_bytes_rt(a.k, a.stages * a.kps, a.split, p.ks, a.nq, QS ? 1 : 0);
     auto kern = ts_topk_kernel<BF16, KL, QS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
