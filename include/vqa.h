@@ -82,8 +82,10 @@ typedef enum vqa_mode {
     /* FAST, but force one kernel family (benchmarks / tests). */
     VQA_MODE_FAST_STREAM = 2,
     VQA_MODE_FAST_TENSOR = 3,
-    /* tcgen05 with the query block resident in tensor memory (large batches, dim <= 768) */
-    VQA_MODE_FAST_TS = 4
+    /* tcgen05 with the query block resident in tensor memory (large batches, dim <= 1024) */
+    VQA_MODE_FAST_TS = 4,
+    /* the same with CTA pairs: tcgen05.mma.cta_group::2, 256 queries per pair (tensor-bound regime, B > 128) */
+    VQA_MODE_FAST_PAIR = 5
 } vqa_mode;
 
 typedef struct vqa_index vqa_index_t; /* opaque */
@@ -158,7 +160,8 @@ typedef struct vqa_tuning {
     int32_t stream_min_mb; /* ... when the shard is at least this many MB (its fixed cost is ~80 us higher), (8000)*/
     int32_t pair;          /* FAST: tensor-bound batches take the cta_group::2 pair kernel, 0|1                   */
     int32_t dyn_tiles;     /* smem-resident kernel without clusters: CTAs take tiles from a shared counter, 0|1 (1)*/
-    int32_t reserved[4];
+    int32_t seed;          /* smem-resident kernel, register lists: warm-up bound from the first tiles' maxima, 0|1 (1) */
+    int32_t reserved[3];
 } vqa_tuning_t;
 
 /* Library defaults (no environment). */

@@ -535,11 +535,16 @@ def test_emulated_query_block_split_between_tmem_and_smem(emu2, monkeypatch, kin
     ("f16", 128, 900, 5, 1, 8, 16, 4, 2, 0),           # k = 1
     ("bf16", 128, 5000, 16, 10, 2, 32, 4, 2, 0),       # two CTAs, ~20 tiles each: warm-up merges, then single inserts
 ])
-def test_emulated_register_list_epilogue_batched_merges(emu2, kind, dim, n, b, k, sm, ncol, stages, kps, mc):
-    """The register-list epilogue of mma_topk_kernel merges the queries of a 16-column group in interleaved batches
-    of 8 while the thresholds are low (reglist_merge32_batch; warm-up cost 75 -> ~20 us on the B200) and falls back
-    to single inserts afterwards; the four warps' lists are merged per warp in one interleaved batch at teardown.
-    Ids must be the oracle's (three-way tie at the top: lower id first), scores within fp32 rounding."""
+@pytest.mark.parametrize("seed,dyn", [("1", "1"), ("0", "0"), ("1", "0")])
+def test_emulated_register_list_epilogue_seed_and_dynamic_tiles(emu2, monkeypatch, kind, dim, n, b, k, sm, ncol, stages, kps,
+                                                                mc, seed, dyn):
+    """The register-list epilogue of mma_topk_kernel with and without (a) the warm-up seed -- the first tile only
+    publishes per-query maxima into k slots whose minimum bounds the k-th best before any list exists (75 us of
+    warm-up merges on the B200 otherwise) -- and (b) the dynamic tile schedule (tickets of one counter instead of the
+    static round-robin share).  Neither may change the answer: the oracle's ids (three-way tie at the top: lower id
+    first), scores within fp32 rounding; slots and counter are left zeroed for the next launch."""
+    monkeypatch.setenv("VQA_SEED", seed)
+    monkeypatch.setenv("VQA_DYN_TILES", dyn)
     emu2.emu_search_tensor.argtypes = _MMA_ARGS
     rng = np.random.default_rng(dim + n + b + k)
     docs, q = _unit(rng, n, dim), _unit(rng, b, dim)
@@ -558,4 +563,4 @@ def test_emulated_register_list_epilogue_batched_merges(emu2, kind, dim, n, b, k
     assert np.abs(out_s - want_s).max() <= 1e-5
     assert out_i[0, :min(k, 3)].tolist() == [103, 100 + n // 2, 100 + n - 1][:min(k, 3)]
     assert np.all(np.diff(out_s, axis=1) <= 0)
-    assert events > 0                     # both update paths are instrumented (batched merges count NB each)
+    assert events > 0                     # list updates are instrumented

@@ -64,7 +64,8 @@ def test_radix_select_reduce_is_bit_identical_to_the_list_insertion_reduce(monke
     ("fp16", 5000, 832, 40, 5, 1, 0),        # 13 query blocks
     ("bf16", 20000, 768, 100, 10, 4, 0),     # dim 768, 4 accumulator stages
     ("bf16", 20000, 768, 256, 10, 6, 0),     # 5 accumulator stages, cluster of 2
-    ("fp16", 20000, 768, 130, 10, 12, 0),    # nothing in TMEM but accumulators
+    ("fp16", 20000, 768, 130, 10, 10, 0),    # two blocks in TMEM, ten in shared memory, cluster of 2
+    ("fp16", 20000, 768, 60, 10, 12, 0),     # nothing in TMEM but accumulators (fits for <= 64 query rows)
     ("bf16", 4000, 768, 32, 100, 2, 1),      # k = 100 at dim 768 with the QS variant (hi/lo heaps)
 ])
 def test_query_block_split_between_tmem_and_smem(monkeypatch, storage, n, d, b, k, ks, select):
@@ -194,3 +195,80 @@ def test_set_tuning_changes_the_plan_of_a_live_index_and_rejects_nonsense():
     with pytest.raises(ValueError):
         shard.set_tuning(ts_extra=-5)
     assert shard.get_tuning().ts_extra == 6                    # a refused tuning leaves the handle untouched
+
+
+@pytest.mark.parametrize("storage,n,d,b,k", [("bf16", 300000, 768, 32, 10), ("bf16", 200000, 768, 1, 10),
+                                             ("fp16", 150000, 384, 16, 32), ("bf16", 3000, 768, 8, 5),
+                                             ("bf16", 150000, 768, 100, 10), ("bf16", 100, 768, 32, 10)])
+def test_warmup_seed_and_dynamic_tiles_leave_results_unchanged(monkeypatch, storage, n, d, b, k):
+    """The headline kernel's warm-up seed (a bound from the first tiles' per-warp maxima) and its dynamic tile schedule
+    change WHEN candidates are seen, never which are kept: ids and score bits equal the run with both switched off,
+    three times in a row on one index (slots and tile counter are recycled), and pass the oracle bars."""
+    from vietnamese_qa_system_b200 import ops
+
+    rng = np.random.default_rng(n + b)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    monkeypatch.setenv("VQA_SEED", "0")
+    monkeypatch.setenv("VQA_DYN_TILES", "0")
+    s0, i0, stored = gpu_search(docs, q, k, "tensor", storage)
+    monkeypatch.delenv("VQA_SEED")
+    monkeypatch.delenv("VQA_DYN_TILES")
+    rows = torch.from_numpy(docs).to(DEV).to({"bf16": torch.bfloat16, "fp16": torch.float16}[storage])
+    shard = ops.FlatShard(rows)
+    t = shard.get_tuning()
+    assert t.seed == 1 and t.dyn_tiles == 1
+    qd = torch.from_numpy(q).to(DEV)
+    for _ in range(3):
+        s1, i1 = shard.search(qd, k, "tensor")
+        torch.cuda.synchronize()
+        assert np.array_equal(i0, i1.cpu().numpy()) and np.array_equal(s0.view(np.int32), s1.cpu().numpy().view(np.int32))
+    os_, oi = oracle.search(stored, q, k, oracle.CANONICAL, storage)
+    assert recall(i0, oi) >= 0.999 and i0[0, :2].tolist() == [3, n // 2]
+
+
+def test_warmup_seed_under_graph_replay_with_new_queries():
+    """A CUDA-graph replay reuses the captured epoch: the reduce must have cleared the seed slots and the tile counter,
+    or the maxima of the PREVIOUS queries would pass as bounds for the new ones."""
+    from vietnamese_qa_system_b200 import ops
+
+    rng = np.random.default_rng(5)
+    rows = torch.from_numpy(unit_rows(rng, 100000, 768)).to(DEV).to(torch.bfloat16)
+    shard = ops.FlatShard(rows)
+    ref = ops.FlatShard(rows)
+    ref.set_tuning(seed=0, dyn_tiles=0)
+    q = torch.from_numpy(unit_rows(rng, 32, 768)).to(DEV)
+    out_s = torch.empty((32, 10), dtype=torch.float32, device=DEV)
+    out_i = torch.empty((32, 10), dtype=torch.int64, device=DEV)
+    shard.search(q, 10, "tensor", out_s, out_i)             # warm-up outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        shard.search(q, 10, "tensor", out_s, out_i)
+    for rep in range(3):
+        q.copy_(torch.from_numpy(unit_rows(np.random.default_rng(rep), 32, 768)).to(DEV))
+        g.replay()
+        torch.cuda.synchronize()
+        ref_s, ref_i = ref.search(q, 10, "tensor")
+        torch.cuda.synchronize()
+        assert torch.equal(out_i, ref_i) and torch.equal(out_s, ref_s)
+
+
+@pytest.mark.parametrize("storage,n,d,b,k", [("bf16", 60000, 768, 256, 10), ("fp16", 50000, 768, 200, 10),
+                                             ("bf16", 30000, 768, 300, 5), ("bf16", 40000, 1024, 256, 10),
+                                             ("fp16", 9000, 384, 129, 26), ("bf16", 200, 768, 256, 10)])
+def test_cta_pair_kernel_matches_the_oracle(storage, n, d, b, k):
+    """ts_pair_topk_kernel (tcgen05.mma.cta_group::2: M = 256 queries across a CTA pair, N = 128 documents, each CTA
+    holding half of every tile; pair.cuh) + the re-scoring reduce: same bars as every fast mode, ids equal to the
+    TMEM-resident-query kernel's, planted duplicate lower id first; batches that leave a tail of <= 128 queries
+    finish on the TS kernel."""
+    rng = np.random.default_rng(n + b)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    q[b - 1] = docs[n - 1]
+    s, i = _check(docs, q, k, "pair", storage)
+    assert i[0, :2].tolist() == [3, n // 2] and i[b - 1, 0] == n - 1
+    s2, i2, _ = gpu_search(docs, q, k, "ts", storage)
+    assert recall(i, i2) >= 0.999 and np.abs(s - s2).max() <= 5e-7

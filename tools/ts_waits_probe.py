@@ -15,6 +15,7 @@ from vietnamese_qa_system_b200 import _native as N, ops  # noqa: E402
 
 n, d = int(os.environ.get("ROWS", "10000000")), int(os.environ.get("DIM", "768"))
 k = int(os.environ.get("K", "10"))
+MODE = os.environ.get("MODE", "ts")
 dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("DTYPE", "bf16")]
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(1)
@@ -31,17 +32,17 @@ out = {"rows": n, "dim": d, "k": k, "knobs": knobs}
 for b in [int(x) for x in os.environ.get("BATCHES", "128,256").split(",")]:
     q = ops.normalize_rows(torch.randn((b, d), generator=g, device=dev))
     for _ in range(3):
-        shard.search(q, k, "ts")
+        shard.search(q, k, MODE)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        shard.search(q, k, "ts")
+        shard.search(q, k, MODE)
     e1.record()
     torch.cuda.synchronize()
     N.check(N.lib().vqa_debug_timeline(shard._h, ctypes.c_void_p(stamps.data_ptr()), stamps.numel() * 8))
     stamps.zero_()
-    shard.search(q[:256] if b > 256 else q, k, "ts")        # one scan launch
+    shard.search(q[:256] if b > 256 else q, k, MODE)        # one scan launch
     torch.cuda.synchronize()
     N.check(N.lib().vqa_debug_timeline(shard._h, None, 0))
     t = stamps.cpu().numpy().astype(np.float64)

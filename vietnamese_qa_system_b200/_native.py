@@ -18,10 +18,10 @@ OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
 # vqa_dtype
 F32, BF16, F16, I64, I32, U8 = 0, 1, 2, 3, 4, 5
 # vqa_mode
-MODE_VERIFY, MODE_FAST, MODE_FAST_STREAM, MODE_FAST_TENSOR, MODE_FAST_TS = 0, 1, 2, 3, 4
+MODE_VERIFY, MODE_FAST, MODE_FAST_STREAM, MODE_FAST_TENSOR, MODE_FAST_TS, MODE_FAST_PAIR = 0, 1, 2, 3, 4, 5
 
 MODES = {"verify": MODE_VERIFY, "fp32": MODE_VERIFY, "fast": MODE_FAST, "stream": MODE_FAST_STREAM,
-         "tensor": MODE_FAST_TENSOR, "ts": MODE_FAST_TS}
+         "tensor": MODE_FAST_TENSOR, "ts": MODE_FAST_TS, "pair": MODE_FAST_PAIR}
 
 EXPORTS = [
     "vqa_version", "vqa_last_error", "vqa_device_count", "vqa_index_create", "vqa_index_bind",
@@ -42,11 +42,11 @@ class Tuning(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "size", "ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "ts_qs",
         "ts_ks", "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-        "stream_max_b", "stream_min_mb", "pair", "dyn_tiles")] + [("reserved", ctypes.c_int32 * 4)]
+        "stream_max_b", "stream_min_mb", "pair", "dyn_tiles", "seed")] + [("reserved", ctypes.c_int32 * 3)]
 
     KNOBS = ("ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "ts_qs", "ts_ks",
              "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-             "stream_max_b", "stream_min_mb", "pair", "dyn_tiles")
+             "stream_max_b", "stream_min_mb", "pair", "dyn_tiles", "seed")
 
     def update(self, **knobs) -> "Tuning":
         for key, val in knobs.items():

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libvqa_b200.so")
-SOURCES = ["api.cu", "misc_launch.cu", "scan_f32.cu", "scan_bf16.cu", "scan_f16.cu", "mma_launch.cu", "ts_launch.cu", "sparse_launch.cu"]
+SOURCES = ["api.cu", "misc_launch.cu", "scan_f32.cu", "scan_bf16.cu", "scan_f16.cu", "mma_launch.cu", "ts_launch.cu", "pair_launch.cu", "sparse_launch.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

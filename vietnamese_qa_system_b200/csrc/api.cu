@@ -172,6 +172,7 @@ const KnobSpec kKnobs[] = {
     {"VQA_STREAM_MIN_MB", &vqa_tuning_t::stream_min_mb, 0, 1 << 30, 8000},
     {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 0},
     {"VQA_DYN_TILES", &vqa_tuning_t::dyn_tiles, 0, 1, 1},
+    {"VQA_SEED", &vqa_tuning_t::seed, 0, 1, 1},
 };
 
 void tuning_defaults(vqa_tuning_t *t) {
@@ -318,6 +319,42 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     return true;
 }
 
+// CTA-pair kernel (pair.cuh): screen mode only; the tensor-memory part of the query block must leave two
+// 128-column accumulator stages, so at most 8 of its 64-column blocks stay there
+bool pair_eligible(const vqa_index *h, int k) {
+    return tensor_eligible(h) && h->dim <= 1024 && k + spare_ranks(h) <= 32;
+}
+
+bool plan_pair(const vqa_index *h, int nq, int k, Plan *pl) {
+    if (!pair_eligible(h, k)) return false;
+    const vqa_tuning_t &tu = h->tune;
+    const int kb = h->dim / vqa::kBlockK;
+    const int ks_min = kb > 8 ? kb - 8 : 0;
+    int ks = tu.ts_ks >= 0 ? tu.ts_ks : ks_min;
+    if (ks < ks_min) ks = ks_min;
+    if (ks > kb) ks = kb;
+    const size_t fixed = vqa::pair_smem_bytes(0, ks);
+    if (fixed >= (size_t)h->max_smem) return false;
+    const int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
+    int kps = tu.mma_kps > 0 ? tu.mma_kps : (kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
+    if (kps < 1 || kb % kps != 0) kps = 1;
+    while (kps > 1 && boxes / kps < 3) kps = (kps % 2 == 0) ? kps / 2 : 1;
+    int stages = boxes / kps;
+    if (stages > vqa::kMaxStages) stages = vqa::kMaxStages;
+    if (stages < 2) return false;
+    pl->family = VQA_MODE_FAST_PAIR;
+    pl->ts_split = 0;
+    pl->ts_qs = 1;
+    pl->ts_ks = ks;
+    pl->pass_nq = 256;
+    pl->stages = stages;
+    pl->kps = kps;
+    pl->passes = (nq + 255) / 256;
+    pl->groups = 1;
+    pl->grid = h->sm_count & ~1;
+    return true;
+}
+
 void plan_stream(const vqa_index *h, int nq, Plan *pl) {
     pl->family = VQA_MODE_FAST_STREAM;
     pl->pass_nq = nq >= 5 ? 8 : (nq >= 3 ? 4 : (nq == 2 ? 2 : 1));
@@ -353,6 +390,12 @@ int make_plan_uncached(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
                                            "(dim <= 768 with the QS variant switched off)");
         return VQA_OK;
     }
+    if (mode == VQA_MODE_FAST_PAIR) {
+        if (!plan_pair(h, nq, k, pl))
+            return fail(VQA_E_UNSUPPORTED, "CTA-pair path needs bf16/fp16 rows, dim %% 64 == 0, dim <= 1024 and "
+                                           "k + spare ranks <= 32 (dim=%d k=%d)", h->dim, k);
+        return VQA_OK;
+    }
     if (mode == VQA_MODE_FAST) {
         // Measured on B200 (profiles/):
         //  * B <= 2 (stream_max_b): the CUDA-core streaming kernel (128-bit no-allocate loads, warp dot products)
@@ -370,6 +413,8 @@ int make_plan_uncached(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
             plan_stream(h, nq, pl);
             return VQA_OK;
         }
+        //  * more than 128 queries (tune.pair): CTA pairs, cta_group::2 MMAs -- the tensor-bound regime.
+        if (h->tune.pair && nq > 128 && plan_pair(h, nq, k, pl)) return VQA_OK;
         if ((nq > 32 || k > 32) && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
         if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
@@ -578,7 +623,8 @@ int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t 
     if (rc) return rc;
     if (family) *family = pl.family;
     if (n_launches)
-        *n_launches = (pl.family == VQA_MODE_FAST_TENSOR || pl.family == VQA_MODE_FAST_TS)
+        *n_launches = (pl.family == VQA_MODE_FAST_TENSOR || pl.family == VQA_MODE_FAST_TS ||
+                       pl.family == VQA_MODE_FAST_PAIR)
                           ? 2 * ((pl.passes + pl.groups - 1) / pl.groups)
                           : 2;  // stream family: one scan launch (grid.y = passes) + one reduce
     return VQA_OK;
@@ -628,6 +674,16 @@ int vqa_plan_describe_tuned(int64_t n_rows, int32_t dim, int32_t dtype, int32_t 
         out[12] = pl.ts_split ? 0 : 1;
         out[13] = (dim / vqa::kBlockK - pl.ts_ks) * (vqa::kBlockK / 2);  // query block; the rest are accumulators
         *smem_bytes = vqa::ts_smem_bytes(kscan, pl.stages * pl.kps, pl.ts_split, pl.ts_ks, nq_launch, pl.ts_qs);
+    } else if (pl.family == VQA_MODE_FAST_PAIR) {
+        const int kscan = k + spare_ranks(&fake);
+        out[7] = 0;
+        out[8] = 1;
+        out[9] = pl.ts_ks;
+        out[10] = kscan;
+        out[11] = 32;
+        out[12] = 1;
+        out[13] = (dim / vqa::kBlockK - pl.ts_ks) * (vqa::kBlockK / 2);  // query block; the rest: 128-column accumulators
+        *smem_bytes = vqa::pair_smem_bytes(pl.stages * pl.kps, pl.ts_ks);
     } else if (pl.family == VQA_MODE_FAST_TENSOR) {
         const int kscan = pl.ss_split ? k : k + spare_ranks(&fake);
         out[7] = pl.ss_split;
@@ -653,8 +709,9 @@ int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int3
     if (!bytes) return fail(VQA_E_INVALID, "bytes is null");
     (void)mode;
     // candidates: per CTA, per query, k entries of (float score, u32 row); + one shared-threshold slot per query
-    // + 64 tile counters of the dynamic tile schedule (one per scan launch of a search) + alignment slack
-    *bytes = cand_elems(h, n_queries, k) * 8 + (size_t)n_queries * 8 + 64 * 8 + 768;
+    // + 64 tile counters of the dynamic tile schedule (one per scan launch of a search), 32 warm-up seed slots per
+    // query + alignment slack
+    *bytes = cand_elems(h, n_queries, k) * 8 + (size_t)n_queries * 8 + 64 * 8 + (size_t)n_queries * 32 * 8 + 1024;
     return VQA_OK;
 }
 
@@ -687,6 +744,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
         (reinterpret_cast<uintptr_t>(cand_i + cand_elems(h, n_queries, k)) + 255) & ~(uintptr_t)255);
     unsigned long long *tile_ctr = reinterpret_cast<unsigned long long *>(
         (reinterpret_cast<uintptr_t>(tau_g + n_queries) + 255) & ~(uintptr_t)255);  // [64], one per scan launch
+    unsigned long long *slot_g = tile_ctr + 64;  // [n_queries][32]
     const long long cand_stride = (long long)n_queries * k;
     vqa::ReduceOpts ropts;
     ropts.select = h->tune.reduce_select;
@@ -695,15 +753,17 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     static std::atomic<uint32_t> g_epoch{1};
     const uint32_t epoch = g_epoch.fetch_add(2, std::memory_order_relaxed);  // odd, unique, never 0 (0 = cleared slot)
 
-    if (pl.family == VQA_MODE_FAST_TS && h->n_rows > 0) {
+    // TMEM-resident-query kernel over the queries [qb, qe) of this search (the whole batch, or the tail a CTA-pair
+    // launch leaves over)
+    auto run_ts = [&](const Plan &pl, int qb, int qe) -> int {
         // list length inside the scan: with screen-then-rescore a few spare ranks absorb the reordering
         // that the queries' storage rounding can cause (score error ~5e-5 against rank gaps of ~7e-4)
         const int kscan = pl.ts_split ? k : k + spare_ranks(h);
         const long long cstride = (long long)n_queries * kscan;
         const int per_launch = pl.groups * pl.pass_nq;
         const long long tiles = (h->n_rows + 63) / 64;
-        for (int l0 = 0; l0 < n_queries; l0 += per_launch) {
-            const int nq = n_queries - l0 < per_launch ? n_queries - l0 : per_launch;
+        for (int l0 = qb; l0 < qe; l0 += per_launch) {
+            const int nq = qe - l0 < per_launch ? qe - l0 : per_launch;
             const int chunks = (nq + pl.pass_nq - 1) / pl.pass_nq;
             int g = 1, lg = 0;
             while (g < chunks) {
@@ -722,7 +782,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.a_fp16 = pl.ts_afp16;
             a.qs = pl.ts_qs;
             a.ks = pl.ts_ks;
-            a.pdl = (l0 > 0 && h->tune.pdl_chain) ? 1 : 0;
+            a.pdl = (l0 > qb && h->tune.pdl_chain) ? 1 : 0;
             a.stages = pl.stages;
             a.kps = pl.kps;
             a.grid = (int)streams * g;
@@ -755,6 +815,64 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
                                        out_scores_dev + (long long)l0 * k,
                                        (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
                                        ropts, pl.ts_split ? nullptr : &rs);
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+        }
+        return VQA_OK;
+    };
+    if (pl.family == VQA_MODE_FAST_TS && h->n_rows > 0) return run_ts(pl, 0, n_queries);
+
+    if (pl.family == VQA_MODE_FAST_PAIR && h->n_rows > 0) {
+        // CTA pairs (cta_group::2): launches of up to 256 queries; a tail of <= 128 queries goes to the TS kernel
+        // (one CTA per tile stream serves it from one HBM pass just as well)
+        const int kscan = k + spare_ranks(h);
+        const long long cstride = (long long)n_queries * kscan;
+        const long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
+        for (int l0 = 0; l0 < n_queries; l0 += 256) {
+            const int nq = n_queries - l0 < 256 ? n_queries - l0 : 256;
+            if (nq <= 128) {
+                Plan pts;
+                std::memset(&pts, 0, sizeof(pts));
+                if (!plan_ts(h, nq, k, &pts) || pts.ts_split)
+                    return fail(VQA_E_UNSUPPORTED, "no TMEM-resident-query plan for the tail of a CTA-pair search");
+                rc = run_ts(pts, l0, n_queries);
+                if (rc) return rc;
+                break;
+            }
+            long long pairs = h->sm_count / 2;
+            if (pairs > tiles) pairs = tiles;
+            if (pairs < 1) pairs = 1;
+            vqa::PairLaunch a;
+            a.tmap = &h->tmap[1];
+            a.bf16 = h->dtype == VQA_BF16;
+            a.stages = pl.stages;
+            a.kps = pl.kps;
+            a.grid = (int)pairs * 2;
+            a.q = queries_dev + (long long)l0 * q_stride;
+            a.q_stride = q_stride;
+            a.nq = nq;
+            a.k = kscan;
+            a.n_rows = h->n_rows;
+            a.dim = h->dim;
+            a.cand_s = cand_s + (long long)l0 * kscan;
+            a.cand_i = cand_i + (long long)l0 * kscan;
+            a.cand_stride = cstride;
+            a.tau_g = tau_g + l0;
+            a.epoch = epoch;
+            a.ks = pl.ts_ks;
+            a.timeline = (h->timeline && h->timeline_bytes >= (size_t)a.grid * 32 * 8) ? h->timeline : nullptr;
+            cudaError_t e = vqa::launch_pair(a, st);
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "CTA-pair scan launch failed: %s", cudaGetErrorString(e));
+            vqa::Rescore rs;
+            rs.rows = h->rows;
+            rs.stride = h->stride;
+            rs.dim = h->dim;
+            rs.bf16 = h->dtype == VQA_BF16;
+            rs.q = queries_dev + (long long)l0 * q_stride;
+            rs.q_stride = q_stride;
+            rs.k_final = k;
+            e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
+                                       kscan, 32, h->first_id, out_scores_dev + (long long)l0 * k,
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, 2, 128, st, ropts, &rs);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;
@@ -821,6 +939,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.pdl = (l0 > 0 && h->tune.pdl_chain) ? 1 : 0;
             a.tma_hint = h->tune.tma_hint;
             a.tile_ctr = h->tune.dyn_tiles ? tile_ctr + (l0 / per_launch) % 64 : nullptr;
+            a.slot_g = (h->tune.seed && pl.pass_nq <= 32 && kscan <= 32) ? slot_g + (long long)l0 * 32 : nullptr;
             a.timeline = (h->timeline && h->timeline_bytes >= (size_t)a.grid * 32 * 8) ? h->timeline : nullptr;
             cudaError_t e = vqa::launch_mma(a, st);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "tensor scan launch failed: %s", cudaGetErrorString(e));
@@ -835,7 +954,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, pl.ss_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
                                        (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
-                                       ropts, pl.ss_split ? nullptr : &rs);
+                                       ropts, pl.ss_split ? nullptr : &rs, a.slot_g);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;

@@ -51,6 +51,7 @@ struct MmaLaunch {
     int tma_hint = 1;  // L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last
     unsigned long long *timeline = nullptr;  // diagnostic per-CTA stamps (vqa_debug_timeline), normally nullptr
     unsigned long long *tile_ctr = nullptr;  // dynamic tile schedule (launches without clusters), see MmaParams
+    unsigned long long *slot_g = nullptr;    // warm-up seed slots [nq][32] (register-list path), see MmaParams
 };
 
 struct TsLaunch {
@@ -79,6 +80,30 @@ struct TsLaunch {
     int ks = 0;   // QS: 64-column blocks of the query block kept in shared memory
     unsigned long long *timeline = nullptr;  // diagnostic per-CTA counters (vqa_debug_timeline), normally nullptr
 };
+
+// CTA-pair kernel (pair.cuh): cta_group::2 MMAs, 256 queries per pair, screen mode only
+struct PairLaunch {
+    const CUtensorMap *tmap;  // box = 64 columns x 64 rows
+    bool bf16;
+    int stages;
+    int kps;
+    int grid;                 // 2 x pairs
+    const float *q;
+    long long q_stride;
+    int nq;                   // <= 256
+    int k;                    // list length inside the scan (<= 32)
+    long long n_rows;
+    int dim;
+    float *cand_s;
+    uint32_t *cand_i;
+    long long cand_stride;
+    unsigned long long *tau_g;
+    uint32_t epoch;
+    int ks;                   // 64-column query blocks kept in shared memory
+    unsigned long long *timeline = nullptr;
+};
+cudaError_t launch_pair(const PairLaunch &a, cudaStream_t st);
+size_t pair_smem_bytes(int boxes, int ks);
 
 cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st);
 size_t ts_smem_bytes(int k, int boxes, int split, int ks = 0, int nq = 1 << 30, int qs = 0);
@@ -112,7 +137,7 @@ cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long 
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                               int list_mod, int queries_per_group, cudaStream_t st, const ReduceOpts &opts,
-                              const Rescore *rs = nullptr);
+                              const Rescore *rs = nullptr, unsigned long long *slot_reset = nullptr);
 struct WaitFlags {
     const unsigned long long *flags = nullptr;
     int n = 0;

@@ -24,8 +24,10 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
                                    long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                                    float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                                    int list_mod, int queries_per_group, cudaStream_t st, const ReduceOpts &opts,
-                                   const Rescore *rs = nullptr, const WaitFlags *wf = nullptr) {
+                                   const Rescore *rs = nullptr, const WaitFlags *wf = nullptr,
+                                   unsigned long long *slot_reset = nullptr) {
     ReduceParams<IdT> p;
+    p.slot_reset = k_out <= 32 ? slot_reset : nullptr;
     // internal (u32 row id) lists only: the scans emit them sorted; the public merge API does not require it
     p.early_exit = (sizeof(IdT) == 4 && opts.early) ? 1 : 0;
     p.trigger_early = (sizeof(IdT) == 4 && opts.trigger_early) ? 1 : 0;
@@ -72,7 +74,7 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
         const long long n_cand = (long long)(n_lists / (list_mod > 1 ? list_mod : 1)) * k_in;
         const size_t smem = select_smem_bytes(n_cand);
         if (opts.select && wf == nullptr && smem <= kSelectSmemLimit &&
-            (k_out > 32 || rs != nullptr)) {
+            (k_out > 32 || (rs != nullptr && p.slot_reset == nullptr))) {
             cudaError_t e = cudaFuncSetAttribute(reduce_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             cfg.gridDim = dim3(n_queries);
@@ -98,9 +100,9 @@ cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long 
                               long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, unsigned long long *tau_g_reset,
                               int list_mod, int queries_per_group, cudaStream_t st, const ReduceOpts &opts,
-                              const Rescore *rs) {
+                              const Rescore *rs, unsigned long long *slot_reset) {
     return launch_reduce_t<uint32_t>(cand_s, cand_i, list_stride, list_stride, query_stride, n_lists, k_in, k_out, id_base, out_s,
-                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, opts, rs, nullptr);
+                                     out_i, n_queries, tau_g_reset, list_mod, queries_per_group, st, opts, rs, nullptr, slot_reset);
 }
 cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long long list_stride,
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out,

@@ -61,6 +61,15 @@ struct MmaParams {
     // k-th best).  A document scoring below any list's k-th best cannot be in the global top-k.
     unsigned long long *tau_g;  // [nq] for this pass, or nullptr
     uint32_t epoch;
+    // Warm-up seed (register-list path): [nq][kSlotStride] slots, same encoding as tau_g.  While a list is empty
+    // nothing can be rejected, so tile 0 used to cost one 32-wide bitonic merge per query and warp -- a ~2000-cycle
+    // dependent chain each, 40 us at B = 32, 75 us over the first eight tiles (profiles/r2_timeline_shard.json).
+    // Instead, for its FIRST tile a warp only publishes, per query, the best score among its 32 rows into slot
+    // (global warp % k) -- five shuffle steps -- and holds the accumulator stage; before its second tile it reads the
+    // query's k slots back.  They hold scores of k DISTINCT documents (lists are disjoint), so their minimum is a
+    // lower bound of the global k-th best, and it is already tight: every slot is the best of ~1900 rows.  Then
+    // tile 0 is filtered against that bound like any later tile (a handful of single inserts).  nullptr: off.
+    unsigned long long *slot_g;
     // Dynamic tile schedule (launches without clusters): one 64-bit counter in the workspace, (epoch << 32) | next
     // tile.  The producer warp of every CTA takes tiles from it instead of the static round-robin share, so an SM
     // that streams slower than its neighbours (the per-CTA spread was 195..270 us of a 285 us launch at B = 1,
@@ -72,6 +81,7 @@ struct MmaParams {
     unsigned long long *timeline;
 };
 
+constexpr int kSlotStride = 32;  // seed slots reserved per query (k <= 32 on the register-list path)
 constexpr int kTimelineSlots = 32;
 __device__ __forceinline__ void timeline_stamp(unsigned long long *tl, int slot) {
     if (tl != nullptr && (threadIdx.x & 31) == 0) {
@@ -106,27 +116,29 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 // ---- tile schedule -------------------------------------------------------------------------------
 constexpr int kTileRing = 32;  // published tile ids in flight per CTA (producer runs < 16 tiles ahead of the epilogue)
 
-// A CTA's FIRST tile: CAS on the epoch-tagged counter, so a stale or uninitialised word reads as "0 tiles taken".
-// Later tiles are plain atomicAdds issued one tile ahead (the counter already carries this launch's epoch by then),
-// so their ~1 us round trip hides behind the TMA issue loop.  Exactly gridDim.x grabs see a value >= n_tiles (every
-// CTA stops at its first); the one that sees the LAST of them zeroes the counter, so a CUDA-graph replay (same
-// epoch) starts clean.
-__device__ __forceinline__ uint32_t grab_first_tile(unsigned long long *ctr, uint32_t epoch) {
-    unsigned long long cur = ld_volatile_u64(ctr);
-    uint32_t t;
-    while (true) {
-        const bool fresh = (uint32_t)(cur >> 32) != epoch;
-        t = fresh ? 0u : (uint32_t)cur;
-        const unsigned long long nv = ((unsigned long long)epoch << 32) | (unsigned long long)(t + 1);
-        const unsigned long long seen = atomicCAS(ctr, cur, nv);
-        if (seen == cur) break;
-        cur = seen;
+// Every CTA's first tile is its static one (tile = CTA index, no atomic in front of the first TMA); later tiles are
+// tickets of one counter, (epoch << 32) | tickets taken, tile = gridDim.x + ticket.  Tickets are plain atomicAdds issued
+// one tile ahead, so their ~1 us round trip hides behind the TMA issue loop.  A counter left at zero by the previous
+// launch (or holding an older epoch) is brought to (epoch, 0) by an atomicMax every CTA issues first; a word that is
+// neither (a workspace that was never zeroed) is repaired through a CAS -- correct, but a one-off ~0.3 ms storm, which
+// is why vqa.h asks for a zeroed workspace.  Exactly gridDim.x tickets are >= the number of dynamic tiles (every CTA
+// stops at its first); whoever draws the LAST of them zeroes the counter for the next launch / graph replay.
+__device__ __forceinline__ int tile_from_ticket(unsigned long long *ctr, unsigned long long old, uint32_t epoch, int n_tiles) {
+    uint32_t t = (uint32_t)old;
+    if ((uint32_t)(old >> 32) != epoch) {  // garbage word: take a ticket through a CAS that also installs the epoch
+        unsigned long long cur = ld_volatile_u64(ctr);
+        while (true) {
+            const bool fresh = (uint32_t)(cur >> 32) != epoch;
+            t = fresh ? 0u : (uint32_t)cur;
+            const unsigned long long nv = ((unsigned long long)epoch << 32) | (unsigned long long)(t + 1);
+            const unsigned long long seen = atomicCAS(ctr, cur, nv);
+            if (seen == cur) break;
+            cur = seen;
+        }
     }
-    return t;
-}
-__device__ __forceinline__ int tile_from_ticket(unsigned long long *ctr, uint32_t t, int n_tiles) {
-    if (t == (uint32_t)n_tiles + gridDim.x - 1) *reinterpret_cast<volatile unsigned long long *>(ctr) = 0ull;
-    return t < (uint32_t)n_tiles ? (int)t : -1;
+    if (t == (uint32_t)n_tiles - 1u) *reinterpret_cast<volatile unsigned long long *>(ctr) = 0ull;
+    const long long tile = (long long)gridDim.x + t;
+    return tile < n_tiles ? (int)tile : -1;
 }
 
 // tile `lt` of this CTA as seen by a consumer role (MMA issuer, epilogue): the static share, or what the producer
@@ -492,11 +504,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         uint32_t it = 0;
         const bool dyn = p.tile_ctr != nullptr;
         int tile = stream0 < p.n_tiles ? stream0 : -1;
-        if (dyn) {
-            tile = 0;
-            if (lane == 0) tile = tile_from_ticket(p.tile_ctr, grab_first_tile(p.tile_ctr, p.epoch), p.n_tiles);
-            tile = __shfl_sync(kFullMask, tile, 0);
-        }
+        if (dyn && lane == 0) atomicMax(p.tile_ctr, (unsigned long long)p.epoch << 32);  // stale / zero -> (epoch, 0)
         for (uint32_t lt = 0;; ++lt) {
             unsigned long long ticket = 0;
             if (dyn && lane == 0) {
@@ -529,7 +537,7 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
                 if (it == 0) timeline_stamp(p.timeline, 1);
             }
             if (dyn) {
-                if (lane == 0) tile = tile_from_ticket(p.tile_ctr, (uint32_t)ticket, p.n_tiles);
+                if (lane == 0) tile = tile_from_ticket(p.tile_ctr, ticket, p.epoch, p.n_tiles);
                 tile = __shfl_sync(kFullMask, tile, 0);
             } else {
                 const long long t = stream0 + (long long)(lt + 1) * n_streams;
@@ -587,6 +595,65 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
         }
         uint32_t lt = 0;
         if (warp == 0) timeline_stamp(p.timeline, 5);
+        // one tile's scores against the lists: per 16-column group one compare per query and one ballot in the common
+        // case; a passing row is inserted with one ballot + shuffle, or by a 32-wide bitonic merge when >= 4 lanes pass
+        auto process = [&](int tile, int as) {
+            const long long row = (long long)tile * kTileRows + warp * 32 + lane;
+            const bool valid = row < p.n_rows;
+            const uint32_t base_row = (uint32_t)(tile * kTileRows + warp * 32);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NCOL);
+#pragma unroll
+            for (int c0 = 0; c0 < RQ; c0 += 16) {
+                float v[16];
+                load_scores16<NCOL, SPLIT>(taddr, c0, p.lo_inv_scale, v);
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < RQ) any |= (v[j] >= tau[c0 + j]);
+                if (__ballot_sync(kFullMask, any && valid) == 0) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (c0 + j < RQ) {
+                        const int q = c0 + j;
+                        const bool pass = valid && v[j] >= tau[q];
+                        unsigned m = __ballot_sync(kFullMask, pass);
+                        if (m != 0) {
+                            if (__popc(m) >= 4) {
+                                const Entry e = reglist_merge32(ls[q], li[q], pass ? v[j] : neg_inf(),
+                                                                pass ? base_row + lane : invalid_id<uint32_t>(), false);
+                                ls[q] = e.s;
+                                li[q] = e.i;
+                            } else {
+                                while (m) {
+                                    const int src = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const Entry e = reglist_insert_one(ls[q], li[q], __shfl_sync(kFullMask, v[j], src),
+                                                                       base_row + src);
+                                    ls[q] = e.s;
+                                    li[q] = e.i;
+                                }
+                            }
+                            const uint32_t last = __shfl_sync(kFullMask, li[q], p.k - 1);
+                            const float ts = __shfl_sync(kFullMask, ls[q], p.k - 1);
+                            if (last != invalid_id<uint32_t>() && ts > tau[q]) {
+                                tau[q] = ts;
+                                if (tau_g != nullptr && lane == 0) atomicMax(tau_g + q, tau_encode(ts, p.epoch));
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        auto release = [&](int as) {
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty + as);
+        };
+        // warm-up seed (see MmaParams::slot_g): the first tile publishes per-query maxima and keeps its stage
+        const bool seed = p.slot_g != nullptr && tau_g != nullptr;
+        unsigned long long *slots = seed ? p.slot_g + (long long)q0 * kSlotStride : nullptr;
+        const int my_slot = (stream0 * 4 + warp) % p.k;
+        int held_tile = -1;
         for (;; ++lt) {
             const int tile = consumer_tile(p, tile_pub, tile_q, lt, stream0, n_streams);
             if (tile < 0) break;
@@ -602,73 +669,54 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
 #pragma unroll
                 for (int q = 0; q < RQ; ++q) tau[q] = fmaxf(tau[q], __shfl_sync(kFullMask, tg, q));
             }
-            const long long row = (long long)tile * kTileRows + warp * 32 + lane;
-            const bool valid = row < p.n_rows;
-            const uint32_t base_row = (uint32_t)(tile * kTileRows + warp * 32);
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NCOL);
+            if (seed && lt == 0) {
+                const long long row = (long long)tile * kTileRows + warp * 32 + lane;
+                const bool valid = row < p.n_rows;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NCOL);
 #pragma unroll
-            for (int c0 = 0; c0 < RQ; c0 += 16) {
-                constexpr int G = RQ < 16 ? RQ : 16;   // queries in this 16-column group
-                constexpr int NB = G < 8 ? G : 8;      // merges interleaved per batch
-                float v[16];
-                load_scores16<NCOL, SPLIT>(taddr, c0, p.lo_inv_scale, v);
-                bool any = false;
+                for (int c0 = 0; c0 < RQ; c0 += 16) {
+                    float v[16];
+                    load_scores16<NCOL, SPLIT>(taddr, c0, p.lo_inv_scale, v);
+                    float mine = neg_inf();   // lane j ends up with the warp maximum of query c0 + j
 #pragma unroll
-                for (int j = 0; j < G; ++j) any |= (v[j] >= tau[c0 + j]);
-                if (__ballot_sync(kFullMask, any && valid) == 0) continue;   // the common case once thresholds are up
-                unsigned m[G];
-                bool heavy = false;
+                    for (int j = 0; j < 16; ++j) {
+                        float mx = valid ? v[j] : neg_inf();
 #pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    m[j] = __ballot_sync(kFullMask, valid && v[j] >= tau[c0 + j]);
-                    heavy |= __popc(m[j]) >= 4;
-                }
-                if (heavy) {
-                    // warm-up tiles: many rows beat the (still low) thresholds -- merge all G queries of the group,
-                    // NB at a time (queries without a passing row merge 32 empty candidates: a no-op)
-#pragma unroll
-                    for (int h = 0; h < G / NB; ++h) {
-                        float cs[NB];
-                        uint32_t ci[NB];
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) {
-                            const bool pass = (m[h * NB + b] >> lane) & 1u;
-                            cs[b] = pass ? v[h * NB + b] : neg_inf();
-                            ci[b] = pass ? base_row + lane : invalid_id<uint32_t>();
-                        }
-                        reglist_merge32_batch<NB, RQ>(ls, li, c0 + h * NB, cs, ci, false);
+                        for (int sh = 16; sh >= 1; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, sh));
+                        if (lane == j) mine = mx;
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < G; ++j) {
-                        unsigned mm = m[j];
-                        while (mm) {
-                            const int src = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const Entry e = reglist_insert_one(ls[c0 + j], li[c0 + j], __shfl_sync(kFullMask, v[j], src),
-                                                               base_row + src);
-                            ls[c0 + j] = e.s;
-                            li[c0 + j] = e.i;
-                        }
-                    }
+                    if (lane < 16 && c0 + lane < nq && mine > neg_inf())
+                        atomicMax(slots + (long long)(c0 + lane) * kSlotStride + my_slot, tau_encode(mine, p.epoch));
                 }
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    if (m[j] == 0) continue;  // warp-uniform
-                    const int q = c0 + j;
-                    const uint32_t last = __shfl_sync(kFullMask, li[q], p.k - 1);
-                    const float ts = __shfl_sync(kFullMask, ls[q], p.k - 1);
-                    if (last != invalid_id<uint32_t>() && ts > tau[q]) {
-                        tau[q] = ts;
-                        if (tau_g != nullptr && lane == 0) atomicMax(tau_g + q, tau_encode(ts, p.epoch));
-                    }
-                }
+                held_tile = tile;   // stage 0 is released after the bounds have been read (next tile, or the end)
+                continue;
             }
-            ptx::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty + as);
+            if (held_tile >= 0) {
+                // the k slots of each query hold the best scores of k disjoint sets of rows: their minimum is a lower
+                // bound of the global k-th best (an empty / stale slot decodes to -inf: no bound yet)
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) {
+                    float b = __int_as_float(0x7f800000);
+                    if (lane < p.k) b = q < nq ? tau_decode(ld_volatile_u64(slots + (long long)q * kSlotStride + lane), p.epoch) : b;
+#pragma unroll
+                    for (int sh = 16; sh >= 1; sh >>= 1) b = fminf(b, __shfl_xor_sync(kFullMask, b, sh));
+                    if (q < nq && b > tau[q]) {
+                        tau[q] = b;
+                        if (lane == 0) atomicMax(tau_g + q, tau_encode(b, p.epoch));
+                    }
+                }
+                process(held_tile, 0);
+                release(0);
+                held_tile = -1;
+            }
+            process(tile, as);
+            release(as);
             if (p.timeline != nullptr && warp == 0 && ((lt + 1) & lt) == 0 && lt < 64)  // tiles 0, 1, 3, 7, 15, 31, 63
                 timeline_stamp(p.timeline, 6 + (31 - __clz((int)lt + 1)));
+        }
+        if (held_tile >= 0) {  // a CTA with a single tile: no second tile came to trigger the deferred pass
+            process(held_tile, 0);
+            release(0);
         }
         if (warp == 0) timeline_stamp(p.timeline, 13);
         // Every MMA (hence every TMA write) of this CTA has retired once the last accumulator was

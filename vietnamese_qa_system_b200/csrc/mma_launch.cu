@@ -35,6 +35,7 @@ static cudaError_t launch_mma_one(const MmaLaunch &a, cudaStream_t st) {
     p.tma_policy = a.n_groups > 1 ? 0x1000000000000000ull : tma_policy(a.tma_hint);
     p.multicast = a.multicast;
     p.timeline = a.timeline;
+    p.slot_g = ((SPLIT ? NCOL / 2 : NCOL) <= 32 && a.k <= 32) ? a.slot_g : nullptr;  // register-list path only
     p.tile_ctr = (a.n_groups == 1 && !a.multicast) ? a.tile_ctr : nullptr;
     const size_t smem = mma_smem_bytes_rt(NCOL, a.dim, a.k, a.stages * a.kps, SPLIT ? 1 : 0);
     auto kern = mma_topk_kernel<BF16, NCOL, SPLIT>;

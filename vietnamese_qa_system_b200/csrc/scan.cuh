@@ -247,6 +247,8 @@ struct ReduceParams {
     float *out_s;     // [nq][k_out]
     long long *out_i;
     unsigned long long *tau_g_reset;  // [n_queries] shared-threshold slots to clear for the next search, or nullptr
+    unsigned long long *slot_reset;   // [n_queries][32] warm-up seed slots of the tcgen05 scan to clear (a graph replay
+                                      // reuses the epoch, so stale maxima of other queries would pass as bounds), or nullptr
     // Opt-in (VQA_REDUCE_EARLY=1), k_out <= 32 kernel: every candidate list is sorted best-first, and the lists are
     // visited entry-major, so once ceil(n_lists / 32) consecutive chunks -- a window that holds one entry of EVERY
     // list -- offered nothing that beats the running k-th best, no later entry of any list can: stop reading.
@@ -462,6 +464,7 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
         p.out_i[(long long)q * kf + lane] = ok ? (long long)li + p.id_base : -1LL;
     }
     if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;  // a graph replay reuses the epoch
+    if (p.slot_reset != nullptr) p.slot_reset[(long long)q * 32 + lane] = 0ull;
 }
 
 // k_out in (32, 128]: one CTA of 8 warps per query.  Phase 1: warp w folds the candidate lists
