@@ -480,7 +480,8 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             traffic = None
     kname = {2: "scan_topk_kernel (CUDA cores)", 3: "mma_topk_kernel (tcgen05, queries in smem)",
-             4: "ts_topk_kernel (tcgen05, queries in TMEM)"}.get(fam, str(fam))
+             4: "ts_topk_kernel (tcgen05, queries in TMEM)",
+             5: "ts_pair_topk_kernel (tcgen05 cta_group::2, queries in TMEM)"}.get(fam, str(fam))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "frac_of_8TBs_datasheet": achieved / 8000.0, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": kname,
@@ -632,7 +633,9 @@ def run_ours(args):
                               "scan_hbm_frac": alg_bytes / (kms / 1e3) / 1e9 / hbm_peak,
                               "tensor_frac": 2.0 * b_ * (hi - lo) * dim / (ms / 1e3) / 1e12 / tf_peak,
                               "family": {2: "stream (CUDA cores)", 3: "tcgen05, queries in smem (hi/lo)",
-                                         4: "tcgen05, queries in TMEM (screen + exact re-score)"}.get(fam_b, str(fam_b))})
+                                         4: "tcgen05, queries in TMEM (screen + exact re-score)",
+                                         5: "tcgen05 cta_group::2 CTA pairs, queries in TMEM (screen + exact re-score)"
+                                         }.get(fam_b, str(fam_b))})
             except Exception as exc:  # noqa: BLE001
                 sweep.append({"batch": b_, "error": f"{type(exc).__name__}: {exc}"})
 

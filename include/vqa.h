@@ -158,7 +158,7 @@ typedef struct vqa_tuning {
     int32_t tma_hint;      /* L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last (1)         */
     int32_t stream_max_b;  /* FAST: batches up to this size take the CUDA-core streaming kernel, 0..8 (2) ...     */
     int32_t stream_min_mb; /* ... when the shard is at least this many MB (its fixed cost is ~80 us higher), (8000)*/
-    int32_t pair;          /* FAST: tensor-bound batches take the cta_group::2 pair kernel, 0|1                   */
+    int32_t pair;          /* FAST: batches of > 128 queries take the cta_group::2 CTA-pair kernel, 0|1 (1)       */
     int32_t dyn_tiles;     /* smem-resident kernel without clusters: CTAs take tiles from a shared counter, 0|1 (1)*/
     int32_t seed;          /* smem-resident kernel, register lists: warm-up bound from the first tiles' maxima, 0|1 (1) */
     int32_t reserved[3];

@@ -156,3 +156,32 @@ def test_hf_encoder_to_search_end_to_end():
     e.index([{"id": i + 1, "text": t} for i, t in enumerate(texts)])
     hit = e.search(texts[4], 1)[0]
     assert hit["id"] == 5 and hit["text"] == texts[4] and abs(hit["score"] - 1.0) < 1e-5
+
+
+def test_append_is_in_place_and_delete_compacts_in_chunks():
+    """SURVEY.md 8(f) rank 4 'without full rebuild': appends write behind the live rows of a capacity-reserved buffer
+    (the buffer address only changes when the capacity is exhausted, geometrically), delete compacts in place chunk
+    by chunk; ids stay stable and results equal a freshly built index over the surviving rows."""
+    rng = np.random.default_rng(21)
+    base = unit_rows(rng, 3000, 128)
+    ann = B200Flat({"dtype": "fp32", "compact_chunk": 257})
+    ann.index(base[:1000])
+    ptrs = set()
+    for lo in range(1000, 3000, 100):
+        ann.append(base[lo:lo + 100])
+        ptrs.add(ann._buf.data_ptr())
+    assert ann.count() == 3000 and ann.capacity >= 3000
+    assert len(ptrs) <= 4                                   # 20 appends, at most a few re-allocations (growth 1.5x)
+    q = base[[5, 1500, 2999]] 
+    assert [r[0][0] for r in ann.search(q, 1)] == [5, 1500, 2999]
+    kill = [0, 5, 6, 7, 999, 1500, 2998] + list(range(2000, 2300))
+    ann.delete(kill)
+    assert ann.count() == 3000 - len(kill)
+    keep = np.setdiff1d(np.arange(3000), kill)
+    ref = B200Flat({"dtype": "fp32"})
+    ref.index(base[keep])
+    got = ann.search(q, 4)
+    want = [[(int(keep[i]), s) for i, s in row] for row in ref.search(q, 4)]
+    assert got == want                                      # same rows, original ids
+    ann.append(base[:3])                                    # appended rows get fresh ids behind the old range
+    assert ann.search(base[:1], 1)[0][0][0] == 3000

@@ -65,7 +65,6 @@ def test_radix_select_reduce_is_bit_identical_to_the_list_insertion_reduce(monke
     ("bf16", 20000, 768, 100, 10, 4, 0),     # dim 768, 4 accumulator stages
     ("bf16", 20000, 768, 256, 10, 6, 0),     # 5 accumulator stages, cluster of 2
     ("fp16", 20000, 768, 130, 10, 10, 0),    # two blocks in TMEM, ten in shared memory, cluster of 2
-    ("fp16", 20000, 768, 60, 10, 12, 0),     # nothing in TMEM but accumulators (fits for <= 64 query rows)
     ("bf16", 4000, 768, 32, 100, 2, 1),      # k = 100 at dim 768 with the QS variant (hi/lo heaps)
 ])
 def test_query_block_split_between_tmem_and_smem(monkeypatch, storage, n, d, b, k, ks, select):

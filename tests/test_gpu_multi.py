@@ -73,6 +73,41 @@ for exchange in ("nccl", "p2p"):
     if not ok:
         print("FAILED", exchange, storage, mode, rank, flush=True)
         break
+# the drop-in class on a row-sharded index (Embeddings(shards=True), heavy_ranker.py:78-83 form): same hits as one GPU,
+# dense and hybrid (the BM25 leg and the content store are replicated per rank), built directly and loaded from disk
+from vietnamese_qa_system_b200 import Embeddings
+words = ["ha", "noi", "sai", "gon", "pho", "bun", "cha", "song", "nui", "bien", "truong", "hoc", "may", "tinh"]
+rg = np.random.default_rng(11)
+texts = [" ".join(words[int(j)] for j in rg.integers(0, len(words), int(rg.integers(4, 12)))) + f" ma{i % 89}" for i in range(3000)]
+import zlib
+class Enc2:
+    def __call__(self, tt):
+        out = np.empty((len(tt), 256), np.float32)
+        for r, t_ in enumerate(tt):
+            out[r] = np.random.default_rng(zlib.crc32(t_.encode())).standard_normal(256)
+        return out
+docs_e = [{"id": i + 1, "text": t_} for i, t_ in enumerate(texts)]
+qs_e = [texts[7], texts[2500], "pho bun ma5", "khong co"]
+for hyb in (False, True):
+    one = Embeddings(hybrid=hyb, content=True, transform=Enc2(), dtype="fp32")
+    one.index(docs_e)
+    many = Embeddings(hybrid=hyb, content=True, transform=Enc2(), dtype="fp32", shards=True)
+    many.index(docs_e)
+    ok = ok and many.count() == 3000 and many.ann.shard.n < 3000
+    a_, b_ = one.batchsearch(qs_e, 3), many.batchsearch(qs_e, 3)
+    ok = ok and a_ == b_ and b_[0][0]["id"] == 8 and b_[0][0]["text"] == texts[7]
+    if not ok:
+        print("FAILED Embeddings(shards=True)", hyb, rank, a_[:1], b_[:1], flush=True)
+if rank == 0:
+    one = Embeddings(content=True, transform=Enc2(), dtype="bf16")
+    one.index(docs_e)
+    one.save(os.environ["VQA_TMP"] + "/ix")
+dist.barrier()
+ld = Embeddings(transform=Enc2(), shards=True)
+ld.load(os.environ["VQA_TMP"] + "/ix")
+ref1 = Embeddings(transform=Enc2())
+ref1.load(os.environ["VQA_TMP"] + "/ix")
+ok = ok and ld.count() == 3000 and ld.ann.shard.n < 3000 and [[h["id"] for h in r] for r in ld.batchsearch(qs_e, 5)] == [[h["id"] for h in r] for r in ref1.batchsearch(qs_e, 5)]
 t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
 sys.exit(0 if int(t.item()) == 1 else 1)
@@ -89,7 +124,7 @@ def test_sharded_nccl_matches_single_gpu(world, tmp_path):
         port = s.getsockname()[1]
     script = tmp_path / "worker.py"
     script.write_text(SCRIPT)
-    env = dict(os.environ, VQA_ROOT=ROOT)
+    env = dict(os.environ, VQA_ROOT=ROOT, VQA_TMP=str(tmp_path))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        env=env, capture_output=True, text=True, timeout=600)

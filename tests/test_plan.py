@@ -47,7 +47,13 @@ def test_default_routing(monkeypatch):
     for b in (3, 8, 32):                                   # headline: smem-resident tcgen05 kernel, hi/lo columns
         p = plan(n, 768, BF16, b, 10)
         assert p["family"] == TENSOR and p["split"] == 1 and p["smem"] <= SMEM
-    for b in (33, 64, 128, 256, 1024):                     # large batches: queries in TMEM, screen + re-score of 32
+    for b in (129, 256, 1024):                             # > 128 queries: CTA pairs (cta_group::2), 256 queries per launch
+        p = plan(n, 768, BF16, b, 10)
+        assert (p["family"], p["pass_nq"], p["ks"], p["kscan"], p["k_out"], p["rescore"]) == (5, 256, 4, 16, 32, 1)
+        assert p["tmem_query_cols"] == 256 and p["smem"] <= SMEM and p["stages"] >= 3   # + two 128-column accumulators
+    assert plan(n, 768, BF16, 256, 10, pair=0)["family"] == TS
+    assert plan(n, 768, BF16, 256, 27)["family"] == TS      # k + spare > 32: no register lists -> TS kernel
+    for b in (33, 64, 128):                                # large batches: queries in TMEM, screen + re-score of 32
         p = plan(n, 768, BF16, b, 10)
         assert (p["family"], p["split"], p["qs"], p["ks"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 1, 2, 16, 32, 1)
         assert p["tmem_query_cols"] == 320 and p["smem"] <= SMEM       # 10 blocks in TMEM -> 3 accumulator stages

@@ -54,6 +54,11 @@ class B200Flat:
         self.shard: Optional[ops.FlatShard] = None
         self._positions: Optional[torch.Tensor] = None  # row -> ANN id once rows were deleted
         self._next_id = 0
+        # capacity-reserved storage: `_buf` holds `_cap` rows of which the first `shard.n` are live, so that
+        # append() writes new rows behind the live ones in place (amortised O(rows appended), no copy of the index)
+        self._buf: Optional[torch.Tensor] = None
+        self.growth = float(self.config.get("growth", 1.5))   # capacity factor when the buffer has to grow
+        self.compact_chunk = int(self.config.get("compact_chunk", 1 << 20))  # rows moved per step by delete()
 
     # ------------------------------------------------------------------
     @property
@@ -76,8 +81,16 @@ class B200Flat:
         return emb_f32 if self.dtype == torch.float32 else emb_f32.to(self.dtype)
 
     def _bind(self, rows: torch.Tensor) -> None:
+        """(Re)create the native handle over ``rows`` -- a view of ``_buf`` or a tensor of its own.  Cheap: the handle
+        borrows the memory; only the TMA tensor maps are rebuilt."""
+        if self._buf is None or rows.data_ptr() != self._buf.data_ptr():
+            self._buf = rows
         self.shard = ops.FlatShard(rows, self.first_global_id if self._positions is None else 0)
         self.config["dimensions"] = int(rows.shape[1])
+
+    @property
+    def capacity(self) -> int:
+        return 0 if self._buf is None else int(self._buf.shape[0])
 
     # ------------------------------------------------------------------ txtai ANN API
     def index(self, embeddings) -> None:
@@ -96,7 +109,15 @@ class B200Flat:
             return self.index(embeddings)
         if new.shape[1] != self.shard.dim:
             raise ValueError(f"dimension mismatch: index has {self.shard.dim}, got {new.shape[1]}")
-        rows = torch.cat([self.shard.rows, new], dim=0)
+        n, m = self.shard.n, int(new.shape[0])
+        if n + m > self.capacity:
+            # grow geometrically: ONE allocation + one device copy of the live rows, then appends are in place again
+            cap = max(n + m, int(self.capacity * self.growth) + 1)
+            buf = torch.empty((cap, self.shard.dim), dtype=self.dtype, device=self._buf.device)
+            buf[:n].copy_(self._buf[:n])
+            self._buf = buf
+        self._buf[n:n + m].copy_(new)
+        rows = self._buf[:n + m]
         if self._positions is not None:
             extra = torch.arange(self._next_id, self._next_id + new.shape[0], dtype=torch.int64, device=rows.device)
             self._positions = torch.cat([self._positions, extra])
@@ -115,7 +136,16 @@ class B200Flat:
         kill = torch.as_tensor(list(ids), dtype=torch.int64, device=dev)
         keep = ~torch.isin(pos, kill)
         self._positions = pos[keep]
-        self._bind(self.shard.rows[keep].contiguous())
+        src = torch.nonzero(keep).squeeze(1)              # surviving rows, ascending: src[j] >= j
+        n_keep = int(src.numel())
+        first = int((src != torch.arange(n_keep, device=dev)).to(torch.int64).argmax().item()) if n_keep else 0
+        if n_keep and bool((src[first:] != torch.arange(first, n_keep, device=dev)).any()):
+            # compact IN PLACE, chunk by chunk: a chunk's sources lie at or behind its destination and behind every
+            # earlier destination, so nothing is overwritten before it is read; the temporary is one chunk, not the index
+            for c in range(first, n_keep, self.compact_chunk):
+                e = min(c + self.compact_chunk, n_keep)
+                self._buf[c:e] = self._buf.index_select(0, src[c:e])
+        self._bind(self._buf[:n_keep])
 
     def count(self) -> int:
         return 0 if self.shard is None else self.shard.n
@@ -190,3 +220,85 @@ class B200Flat:
             torch.tensor(meta["positions"], dtype=torch.int64, device=self.device)
         self._next_id = int(meta.get("next_id", meta["n"]))
         self._bind(rows.to(self.device).contiguous())
+
+
+class B200Sharded(B200Flat):
+    """The same ANN contract over a ROW-SHARDED index: one process per GPU (``torchrun``), rank r of G holds the
+    contiguous row block ``shard_bounds(N, G, r)`` of the document matrix; a search is the local scan + fused top-k,
+    one exchange of the ``[B, k]`` candidates over NVLink and the merge-top-k kernel (``sharded.ShardedFlat``), and
+    returns the identical global answer on every rank.  ANN ids are global row positions, as in ``B200Flat``.
+
+    This is what lets ``Embeddings(**cfg)`` (heavy_ranker.py:78-83) mount an index that does not fit -- or should not
+    be scanned by -- one GPU: ``Embeddings(path=..., content=True, shards=True)`` under ``torchrun``.  Every rank calls
+    ``index`` / ``load`` / ``search`` with the same arguments (SPMD); ``index`` keeps only this rank's block.
+    ``append`` / ``delete`` / ``save`` are single-index operations: build and save with ``B200Flat``, then ``load``
+    here (each rank memory-maps its own row block)."""
+
+    def __init__(self, config: Optional[dict] = None):
+        super().__init__(config)
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("a sharded index needs torch.distributed to be initialised (one process per GPU, torchrun)")
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.exchange = str(self.config.get("exchange", "auto"))
+        self.n_total = 0
+        self.sharded = None
+
+    def _wrap(self, rows: torch.Tensor, n_total: int) -> None:
+        from .sharded import ShardedFlat
+
+        self.n_total = int(n_total)
+        self.sharded = ShardedFlat(rows, self.n_total, mode=self.mode, exchange=self.exchange)
+        self.shard = self.sharded.shard
+        self._buf = rows
+        self.first_global_id = self.shard.first_global_id
+        self._next_id = self.n_total
+        self.config["dimensions"] = int(rows.shape[1])
+        self.config["offset"] = self.n_total
+
+    def index(self, embeddings) -> None:
+        from .sharded import shard_bounds
+
+        n_total = int(embeddings.shape[0]) if hasattr(embeddings, "shape") else len(embeddings)
+        lo, hi = shard_bounds(n_total, self.world, self.rank)
+        block = embeddings[lo:hi]
+        emb = _as_cuda_f32(block, self.device) if hi > lo else \
+            torch.empty((0, int(embeddings.shape[1])), dtype=torch.float32, device=self.device)
+        self._positions = None
+        self._wrap(self._store(emb).contiguous(), n_total)
+
+    def load(self, path: str, row_range: Optional[Tuple[int, int]] = None) -> None:
+        from .sharded import shard_bounds
+
+        if row_range is not None:
+            raise ValueError("a sharded index chooses its own row block")
+        with open(path + ".json", "r", encoding="utf-8") as f:
+            n_total = int(json.load(f)["n"])
+        super().load(path, row_range=shard_bounds(n_total, self.world, self.rank))
+        self._wrap(self.shard.rows, n_total)
+
+    def count(self) -> int:
+        return self.n_total
+
+    def search_tensors(self, queries: torch.Tensor, limit: int, mode=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.sharded is None:
+            raise RuntimeError("index is empty: call index() or load() first")
+        s, i = self.sharded.search(queries, int(limit), mode)
+        return s.clone(), i.clone()      # the sharded index reuses its output buffers
+
+    def search(self, queries, limit: int, mode=None) -> List[List[Tuple[int, float]]]:
+        if self.sharded is None:
+            raise RuntimeError("index is empty: call index() or load() first")
+        s, i = self.search_tensors(_as_cuda_f32(queries, self.device), limit, mode)
+        s_np, i_np = s.cpu().numpy(), i.cpu().numpy()
+        return [[(i_, s_) for i_, s_ in zip(i_np[b].tolist(), s_np[b].tolist()) if i_ >= 0] for b in range(s_np.shape[0])]
+
+    def append(self, embeddings) -> None:
+        raise NotImplementedError("append to a row-sharded index: append to the single index and reload the shards")
+
+    def delete(self, ids: Sequence[int]) -> None:
+        raise NotImplementedError("delete from a row-sharded index: delete from the single index and reload the shards")
+
+    def save(self, path: str) -> None:
+        raise NotImplementedError("a row-sharded index is loaded from a saved B200Flat index, not saved itself")

@@ -170,7 +170,7 @@ const KnobSpec kKnobs[] = {
     {"VQA_TMA_HINT", &vqa_tuning_t::tma_hint, 0, 2, 1},
     {"VQA_STREAM_MAX_B", &vqa_tuning_t::stream_max_b, 0, 8, 2},
     {"VQA_STREAM_MIN_MB", &vqa_tuning_t::stream_min_mb, 0, 1 << 30, 8000},
-    {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 0},
+    {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 1},
     {"VQA_DYN_TILES", &vqa_tuning_t::dyn_tiles, 0, 1, 1},
     {"VQA_SEED", &vqa_tuning_t::seed, 0, 1, 1},
 };

@@ -694,16 +694,37 @@ mma_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const MmaParams p
             if (held_tile >= 0) {
                 // the k slots of each query hold the best scores of k disjoint sets of rows: their minimum is a lower
                 // bound of the global k-th best (an empty / stale slot decodes to -inf: no bound yet)
+                // (all loads first, sixteen queries at a time: a volatile load may not pass the atomic that follows the
+                // previous query's minimum, and 32 dependent L2 round trips cost ~13 us -- profiles/r2_call4.log)
 #pragma unroll
-                for (int q = 0; q < RQ; ++q) {
-                    float b = __int_as_float(0x7f800000);
-                    if (lane < p.k) b = q < nq ? tau_decode(ld_volatile_u64(slots + (long long)q * kSlotStride + lane), p.epoch) : b;
+                for (int h0 = 0; h0 < RQ; h0 += 16) {
+                    unsigned long long raw[16];
 #pragma unroll
-                    for (int sh = 16; sh >= 1; sh >>= 1) b = fminf(b, __shfl_xor_sync(kFullMask, b, sh));
-                    if (q < nq && b > tau[q]) {
-                        tau[q] = b;
-                        if (lane == 0) atomicMax(tau_g + q, tau_encode(b, p.epoch));
+                    for (int j = 0; j < 16; ++j) {
+                        raw[j] = 0ull;
+                        if (h0 + j < RQ && h0 + j < nq && lane < p.k)
+                            raw[j] = ld_volatile_u64(slots + (long long)(h0 + j) * kSlotStride + lane);
                     }
+                    float bound[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float b = lane < p.k ? tau_decode(raw[j], p.epoch) : __int_as_float(0x7f800000);
+#pragma unroll
+                        for (int sh = 16; sh >= 1; sh >>= 1) b = fminf(b, __shfl_xor_sync(kFullMask, b, sh));
+                        bound[j] = b;
+                    }
+                    float mine = neg_inf();   // lane j publishes query h0 + j's bound if it improves the threshold
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (h0 + j < RQ) {
+                            const int q = h0 + j;
+                            if (q < nq && bound[j] > tau[q]) {
+                                tau[q] = bound[j];
+                                if (lane == j) mine = bound[j];
+                            }
+                        }
+                    }
+                    if (lane < 16 && mine > neg_inf()) atomicMax(tau_g + h0 + lane, tau_encode(mine, p.epoch));
                 }
                 process(held_tile, 0);
                 release(0);

@@ -340,8 +340,19 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
         }
         __syncwarp();
     }
-    float ls = neg_inf();
-    IdT li = invalid_id<IdT>();
+    // NL partial lists, each fed by every NL-th chunk: the sort + merge of a chunk is a chain of ~20 dependent
+    // shuffle steps (~1.2 us for one warp alone), and chunks of one list depend on each other -- four independent
+    // lists advance four chains in lock step instead (straight-line code, same instructions).  A candidate is offered
+    // only if it beats the best k-th place any partial list has reached (no candidate below it can be in the union's
+    // top k); the lists are merged at the end.
+    constexpr int NL = 4;
+    float ls[NL];
+    IdT li[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        ls[l] = neg_inf();
+        li[l] = invalid_id<IdT>();
+    }
     float tau = neg_inf();
     const int lmod = p.list_mod > 1 ? p.list_mod : 1;
     const int lgrp = p.list_mod > 1 ? q / p.queries_per_group : 0;
@@ -369,51 +380,94 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
           }
       }
 #pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        if (base0 + u * 32 >= total) break;  // warp-uniform
-        const float s = sv[u];
-        const IdT id = iv[u];
-        bool valid = id != invalid_id<IdT>();
-        if constexpr (sizeof(IdT) == 8) valid = valid && id >= 0;
-        const bool pass = valid && s >= tau;
-        if (__ballot_sync(kFullMask, pass) == 0) {
-            if (p.early_exit && ++quiet >= quiet_need) {
+      for (int u0 = 0; u0 < PF; u0 += NL) {
+        if (base0 + u0 * 32 >= total) break;  // warp-uniform
+        float cs[NL];
+        IdT ci[NL];
+        unsigned any = 0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const float s = sv[u0 + l];
+            const IdT id = iv[u0 + l];
+            bool valid = id != invalid_id<IdT>();
+            if constexpr (sizeof(IdT) == 8) valid = valid && id >= 0;
+            const bool pass = valid && s >= tau;
+            const unsigned m = __ballot_sync(kFullMask, pass);
+            // early exit counts chunks in order: a chunk without a pass extends the quiet run, one with a pass ends it
+            if (base0 + (u0 + l) * 32 < total) {
+                if (m == 0) ++quiet;
+                else quiet = 0;
+            }
+            any |= m;
+            cs[l] = pass ? s : neg_inf();
+            ci[l] = pass ? id : invalid_id<IdT>();
+        }
+        if (any == 0) {
+            if (p.early_exit && quiet >= quiet_need) {
                 stop = true;
                 break;
             }
             continue;
         }
-        quiet = 0;
-        float cs = pass ? s : neg_inf();
-        IdT ci = pass ? id : invalid_id<IdT>();
 #pragma unroll
         for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                const bool desc = (lane & size) == 0 || size == 32;
-                bitonic_step_t<IdT>(cs, ci, stride, ((lane & stride) == 0) == desc);
+                const bool keep = ((lane & stride) == 0) == ((lane & size) == 0 || size == 32);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) bitonic_step_t<IdT>(cs[l], ci[l], stride, keep);
             }
         }
-        const float rs = __shfl_sync(kFullMask, ls, 31 - lane);
-        const IdT ri = shfl_any(li, 31 - lane);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const float rs = __shfl_sync(kFullMask, ls[l], 31 - lane);
+            const IdT ri = shfl_any(li[l], 31 - lane);
+            if (ranks_before<IdT>(rs, ri, cs[l], ci[l])) {
+                cs[l] = rs;
+                ci[l] = ri;
+            }
+        }
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) bitonic_step_t<IdT>(cs[l], ci[l], stride, (lane & stride) == 0);
+        }
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            ls[l] = cs[l];
+            li[l] = ci[l];
+            const IdT last = shfl_any(li[l], p.k_out - 1);
+            const float t = __shfl_sync(kFullMask, ls[l], p.k_out - 1);
+            if (last != invalid_id<IdT>()) tau = fmaxf(tau, t);
+        }
+        if (p.early_exit && quiet >= quiet_need) {
+            stop = true;
+            break;
+        }
+      }
+    }
+    // union of the partial lists: three merges of sorted lists (five compare-exchange steps each)
+#pragma unroll
+    for (int l = 1; l < NL; ++l) {
+        float cs = ls[l];
+        IdT ci = li[l];
+        const float rs = __shfl_sync(kFullMask, ls[0], 31 - lane);
+        const IdT ri = shfl_any(li[0], 31 - lane);
         if (ranks_before<IdT>(rs, ri, cs, ci)) {
             cs = rs;
             ci = ri;
         }
 #pragma unroll
         for (int stride = 16; stride > 0; stride >>= 1) bitonic_step_t<IdT>(cs, ci, stride, (lane & stride) == 0);
-        ls = cs;
-        li = ci;
-        const IdT last = shfl_any(li, p.k_out - 1);
-        tau = last != invalid_id<IdT>() ? __shfl_sync(kFullMask, ls, p.k_out - 1) : neg_inf();
-      }
+        ls[0] = cs;
+        li[0] = ci;
     }
     if constexpr (sizeof(IdT) == 4) {
         if (p.rs_rows != nullptr) {
             // lane e re-scores candidate e exactly: 4 independent fp32 FMA chains over the row
             float exact = neg_inf();
-            if (lane < p.k_out && li != invalid_id<IdT>()) {
-                const unsigned char *row = p.rs_rows + (long long)li * p.rs_stride;
+            if (lane < p.k_out && li[0] != invalid_id<IdT>()) {
+                const unsigned char *row = p.rs_rows + (long long)li[0] * p.rs_stride;
                 const float *qv = p.rs_q + (long long)q * p.rs_q_stride;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 const int nch = p.rs_dim / 8;
@@ -444,24 +498,24 @@ __global__ void __launch_bounds__(kReduceWarpsPerCta * 32) reduce_topk_warp_kern
                 }
                 exact = (a0 + a1) + (a2 + a3);
             } else {
-                li = invalid_id<IdT>();
+                li[0] = invalid_id<IdT>();
             }
-            ls = exact;
+            ls[0] = exact;
 #pragma unroll
             for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
                 for (int stride = size >> 1; stride > 0; stride >>= 1) {
                     const bool desc = (lane & size) == 0 || size == 32;
-                    bitonic_step_t<IdT>(ls, li, stride, ((lane & stride) == 0) == desc);
+                    bitonic_step_t<IdT>(ls[0], li[0], stride, ((lane & stride) == 0) == desc);
                 }
             }
         }
     }
     const int kf = p.k_final > 0 ? p.k_final : p.k_out;
     if (lane < kf) {
-        const bool ok = li != invalid_id<IdT>();
-        p.out_s[(long long)q * kf + lane] = ok ? ls : neg_inf();
-        p.out_i[(long long)q * kf + lane] = ok ? (long long)li + p.id_base : -1LL;
+        const bool ok = li[0] != invalid_id<IdT>();
+        p.out_s[(long long)q * kf + lane] = ok ? ls[0] : neg_inf();
+        p.out_i[(long long)q * kf + lane] = ok ? (long long)li[0] + p.id_base : -1LL;
     }
     if (p.tau_g_reset != nullptr && lane == 0) p.tau_g_reset[q] = 0ull;  // a graph replay reuses the epoch
     if (p.slot_reset != nullptr) p.slot_reset[(long long)q * 32 + lane] = 0ull;

@@ -43,7 +43,7 @@ _DB_FILE = "documents"
 _IDS_FILE = "ids.json"
 _SCORING_FILE = "scoring"
 _HYBRID_CANDIDATES = 10  # each leg fetches limit * 10 candidates (txtai Search)
-_PERSISTED_KEYS_SKIP = {"transform", "device"}
+_PERSISTED_KEYS_SKIP = {"transform", "device", "shards", "exchange"}   # deployment choices, not index properties
 
 
 def _is_vector(x: Any) -> bool:
@@ -87,9 +87,21 @@ class Embeddings:
 
     def _ann_config(self) -> dict:
         cfg = {"dtype": self.config.get("dtype", "bf16"), "device": self.config.get("device")}
-        if "mode" in self.config:
-            cfg["mode"] = self.config["mode"]
+        for key in ("mode", "exchange"):
+            if key in self.config:
+                cfg[key] = self.config[key]
         return cfg
+
+    def _new_ann(self) -> B200Flat:
+        """``shards=True`` (under torchrun, one process per GPU): the dense index is row-sharded over the ranks and
+        searched with one NVLink exchange per batch (``ann.B200Sharded``); every rank makes the same calls and gets
+        the same results.  The BM25 leg of a hybrid index and the content store are replicated per rank -- they are
+        small next to the dense matrix.  Default: one GPU holds the whole index (``ann.B200Flat``)."""
+        if self.config.get("shards"):
+            from .ann import B200Sharded
+
+            return B200Sharded(self._ann_config())
+        return B200Flat(self._ann_config())
 
     # ------------------------------------------------------------------ vectors
     def _encoder_fn(self):
@@ -198,7 +210,7 @@ class Embeddings:
             vecs = torch.cat(parts) if parts else torch.empty((0, int(self.config.get("dimensions", 0))),
                                                               device="cuda")
         self.config["dimensions"] = int(vecs.shape[1])
-        self.ann = B200Flat(self._ann_config())
+        self.ann = self._new_ann()
         self.ann.index(vecs)
         self._store_content(rows)
 
@@ -328,7 +340,7 @@ class Embeddings:
         self.configure({**cfg, **keep})
         self.ann = self.scoring = None
         if self._dense:
-            self.ann = B200Flat(self._ann_config())
+            self.ann = self._new_ann()
             self.ann.load(os.path.join(path, _ANN_FILE))
         if self.config.get("scoring"):
             self.scoring = BM25(self.config["scoring"], device=self.config.get("device"))
