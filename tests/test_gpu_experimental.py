@@ -256,12 +256,14 @@ def test_warmup_seed_under_graph_replay_with_new_queries():
 
 @pytest.mark.parametrize("storage,n,d,b,k", [("bf16", 60000, 768, 256, 10), ("fp16", 50000, 768, 200, 10),
                                              ("bf16", 30000, 768, 300, 5), ("bf16", 40000, 1024, 256, 10),
-                                             ("fp16", 9000, 384, 129, 26), ("bf16", 200, 768, 256, 10)])
+                                             ("fp16", 9000, 384, 129, 26), ("bf16", 200, 768, 256, 10),
+                                             ("bf16", 50000, 768, 100, 10), ("fp16", 30000, 768, 64, 10),
+                                             ("bf16", 20000, 1024, 33, 16)])
 def test_cta_pair_kernel_matches_the_oracle(storage, n, d, b, k):
     """ts_pair_topk_kernel (tcgen05.mma.cta_group::2: M = 256 queries across a CTA pair, N = 128 documents, each CTA
     holding half of every tile; pair.cuh) + the re-scoring reduce: same bars as every fast mode, ids equal to the
-    TMEM-resident-query kernel's, planted duplicate lower id first; batches that leave a tail of <= 128 queries
-    finish on the TS kernel."""
+    TMEM-resident-query kernel's, planted duplicate lower id first; launches of <= 128 queries (small batches, the
+    tail of a large one) run the same 128-document tiles on single CTAs (PAIR = false)."""
     rng = np.random.default_rng(n + b)
     docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
     docs[n // 2] = docs[3]

@@ -173,6 +173,7 @@ const KnobSpec kKnobs[] = {
     {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 1},
     {"VQA_DYN_TILES", &vqa_tuning_t::dyn_tiles, 0, 1, 1},
     {"VQA_SEED", &vqa_tuning_t::seed, 0, 1, 1},
+    {"VQA_WIDE", &vqa_tuning_t::wide, 0, 1, 0},
 };
 
 void tuning_defaults(vqa_tuning_t *t) {
@@ -325,6 +326,27 @@ bool pair_eligible(const vqa_index *h, int k) {
     return tensor_eligible(h) && h->dim <= 1024 && k + spare_ranks(h) <= 32;
 }
 
+// ring geometry of the 128-document-tile kernel: `single` = one CTA fetches both 64-row halves of a tile (16 KB per
+// 64-column block), else each CTA of a pair fetches its own half (8 KB)
+bool pair_geometry(const vqa_index *h, int ks, bool single, int *stages, int *kps_out) {
+    const vqa_tuning_t &tu = h->tune;
+    const int kb = h->dim / vqa::kBlockK;
+    const size_t fixed = vqa::pair_smem_bytes(0, ks);
+    if (fixed >= (size_t)h->max_smem) return false;
+    const size_t unit = single ? vqa::kStageBytes : vqa::kStageBytes / 2;
+    const int slots = (int)(((size_t)h->max_smem - fixed) / unit);   // 64-column blocks of a tile that fit the ring
+    // measured (profiles/r2_call5.log, pairs at dim 768): 4 blocks per stage 3.41 ms, 3 or 6: 3.94, 2: 5.17, 1: 9.57
+    int kps = tu.mma_kps > 0 ? tu.mma_kps : (kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
+    if (kps < 1 || kb % kps != 0) kps = 1;
+    while (kps > 1 && slots / kps < 2) kps = (kps % 2 == 0) ? kps / 2 : 1;
+    int st = slots / kps;
+    if (st > vqa::kMaxStages) st = vqa::kMaxStages;
+    if (st < 2) return false;
+    *stages = st;
+    *kps_out = kps;
+    return true;
+}
+
 bool plan_pair(const vqa_index *h, int nq, int k, Plan *pl) {
     if (!pair_eligible(h, k)) return false;
     const vqa_tuning_t &tu = h->tune;
@@ -333,25 +355,19 @@ bool plan_pair(const vqa_index *h, int nq, int k, Plan *pl) {
     int ks = tu.ts_ks >= 0 ? tu.ts_ks : ks_min;
     if (ks < ks_min) ks = ks_min;
     if (ks > kb) ks = kb;
-    const size_t fixed = vqa::pair_smem_bytes(0, ks);
-    if (fixed >= (size_t)h->max_smem) return false;
-    const int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
-    int kps = tu.mma_kps > 0 ? tu.mma_kps : (kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
-    if (kps < 1 || kb % kps != 0) kps = 1;
-    while (kps > 1 && boxes / kps < 3) kps = (kps % 2 == 0) ? kps / 2 : 1;
-    int stages = boxes / kps;
-    if (stages > vqa::kMaxStages) stages = vqa::kMaxStages;
-    if (stages < 2) return false;
+    int stages = 0, kps = 0, s1 = 0, k1 = 0;
+    if (!pair_geometry(h, ks, nq <= 128, &stages, &kps)) return false;
+    if (nq > 128 && nq % 256 != 0 && nq % 256 <= 128 && !pair_geometry(h, ks, true, &s1, &k1)) return false;  // the tail launch
     pl->family = VQA_MODE_FAST_PAIR;
     pl->ts_split = 0;
     pl->ts_qs = 1;
     pl->ts_ks = ks;
-    pl->pass_nq = 256;
+    pl->pass_nq = nq <= 128 ? 128 : 256;
     pl->stages = stages;
     pl->kps = kps;
-    pl->passes = (nq + 255) / 256;
+    pl->passes = nq <= 128 ? 1 : (nq + 255) / 256;
     pl->groups = 1;
-    pl->grid = h->sm_count & ~1;
+    pl->grid = nq <= 128 ? h->sm_count : (h->sm_count & ~1);
     return true;
 }
 
@@ -414,7 +430,8 @@ int make_plan_uncached(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
             return VQA_OK;
         }
         //  * more than 128 queries (tune.pair): CTA pairs, cta_group::2 MMAs -- the tensor-bound regime.
-        if (h->tune.pair && nq > 128 && plan_pair(h, nq, k, pl)) return VQA_OK;
+        //    (tune.wide: the same 128-document tiles on single CTAs for 33..128 queries)
+        if (((h->tune.pair && nq > 128) || (h->tune.wide && nq > 32 && nq <= 128)) && plan_pair(h, nq, k, pl)) return VQA_OK;
         if ((nq > 32 || k > 32) && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
         if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
@@ -683,7 +700,7 @@ int vqa_plan_describe_tuned(int64_t n_rows, int32_t dim, int32_t dtype, int32_t 
         out[11] = 32;
         out[12] = 1;
         out[13] = (dim / vqa::kBlockK - pl.ts_ks) * (vqa::kBlockK / 2);  // query block; the rest: 128-column accumulators
-        *smem_bytes = vqa::pair_smem_bytes(pl.stages * pl.kps, pl.ts_ks);
+        *smem_bytes = vqa::pair_smem_bytes(pl.stages * pl.kps * (n_queries <= 128 ? 2 : 1), pl.ts_ks);
     } else if (pl.family == VQA_MODE_FAST_TENSOR) {
         const int kscan = pl.ss_split ? k : k + spare_ranks(&fake);
         out[7] = pl.ss_split;
@@ -822,31 +839,27 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     if (pl.family == VQA_MODE_FAST_TS && h->n_rows > 0) return run_ts(pl, 0, n_queries);
 
     if (pl.family == VQA_MODE_FAST_PAIR && h->n_rows > 0) {
-        // CTA pairs (cta_group::2): launches of up to 256 queries; a tail of <= 128 queries goes to the TS kernel
-        // (one CTA per tile stream serves it from one HBM pass just as well)
+        // 128-document tiles: launches of up to 256 queries on CTA pairs (cta_group::2); a launch of <= 128 queries
+        // (a small batch, or the tail of a large one) runs the same tiles on single CTAs
         const int kscan = k + spare_ranks(h);
         const long long cstride = (long long)n_queries * kscan;
         const long long tiles = (h->n_rows + vqa::kTileRows - 1) / vqa::kTileRows;
         for (int l0 = 0; l0 < n_queries; l0 += 256) {
             const int nq = n_queries - l0 < 256 ? n_queries - l0 : 256;
-            if (nq <= 128) {
-                Plan pts;
-                std::memset(&pts, 0, sizeof(pts));
-                if (!plan_ts(h, nq, k, &pts) || pts.ts_split)
-                    return fail(VQA_E_UNSUPPORTED, "no TMEM-resident-query plan for the tail of a CTA-pair search");
-                rc = run_ts(pts, l0, n_queries);
-                if (rc) return rc;
-                break;
-            }
-            long long pairs = h->sm_count / 2;
-            if (pairs > tiles) pairs = tiles;
-            if (pairs < 1) pairs = 1;
+            const bool single = nq <= 128;
+            int stages = pl.stages, kps = pl.kps;
+            if (single != (n_queries <= 128) && !pair_geometry(h, pl.ts_ks, single, &stages, &kps))
+                return fail(VQA_E_UNSUPPORTED, "no ring geometry for the tail launch of a CTA-pair search");
+            long long streams = single ? h->sm_count : h->sm_count / 2;
+            if (streams > tiles) streams = tiles;
+            if (streams < 1) streams = 1;
             vqa::PairLaunch a;
             a.tmap = &h->tmap[1];
             a.bf16 = h->dtype == VQA_BF16;
-            a.stages = pl.stages;
-            a.kps = pl.kps;
-            a.grid = (int)pairs * 2;
+            a.stages = stages;
+            a.kps = kps;
+            a.pair = single ? 0 : 1;
+            a.grid = (int)streams * (single ? 1 : 2);
             a.q = queries_dev + (long long)l0 * q_stride;
             a.q_stride = q_stride;
             a.nq = nq;
@@ -861,7 +874,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.ks = pl.ts_ks;
             a.timeline = (h->timeline && h->timeline_bytes >= (size_t)a.grid * 32 * 8) ? h->timeline : nullptr;
             cudaError_t e = vqa::launch_pair(a, st);
-            if (e != cudaSuccess) return fail(VQA_E_CUDA, "CTA-pair scan launch failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess) return fail(VQA_E_CUDA, "128-document-tile scan launch failed: %s", cudaGetErrorString(e));
             vqa::Rescore rs;
             rs.rows = h->rows;
             rs.stride = h->stride;
@@ -872,7 +885,8 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             rs.k_final = k;
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, 32, h->first_id, out_scores_dev + (long long)l0 * k,
-                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, 2, 128, st, ropts, &rs);
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, single ? 1 : 2, 128, st,
+                                       ropts, &rs);
             if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
         }
         return VQA_OK;

@@ -87,7 +87,8 @@ struct PairLaunch {
     bool bf16;
     int stages;
     int kps;
-    int grid;                 // 2 x pairs
+    int grid;                 // 2 x pairs (pair = 1) or CTAs (pair = 0)
+    // stages x kps = 64-column blocks of a TILE in the ring (8 KB per CTA each with pair = 1, 16 KB with pair = 0)
     const float *q;
     long long q_stride;
     int nq;                   // <= 256
@@ -100,6 +101,7 @@ struct PairLaunch {
     unsigned long long *tau_g;
     uint32_t epoch;
     int ks;                   // 64-column query blocks kept in shared memory
+    int pair = 1;             // 1: CTA pairs (grid = 2 x pairs, <= 256 queries); 0: one CTA per tile stream (<= 128 queries)
     unsigned long long *timeline = nullptr;
 };
 cudaError_t launch_pair(const PairLaunch &a, cudaStream_t st);

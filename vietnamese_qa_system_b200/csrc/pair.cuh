@@ -143,10 +143,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
 
 }  // namespace ptx2
 
-template <bool DOC_BF16, int KL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
+// PAIR = true: launched as clusters of 2 (cta_group::2, 256 queries per pair).  PAIR = false: the same 128-document
+// tiles on ONE CTA (cta_group::1, M = 128 queries, N = 128 documents: a 64-cycle instruction that reads its 4 KB of A
+// from tensor memory at the 64 B/cycle the TMEM read port gives -- ts.cuh's N = 64 tiles need that bandwidth twice
+// over, which is what holds B = 64..128 at ~58 cycles per 32-cycle MMA, profiles/r2_ts_waits_10m.json); the CTA
+// fetches both 64-row halves of a tile itself.
+template <bool DOC_BF16, int KL, bool PAIR>
+__global__ void __launch_bounds__(kMmaThreads, 1)
 ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairParams p) {
     static_assert(KL == 16 || KL == 32, "register lists only");
+    constexpr int HB = PAIR ? 1 : 2;   // 64-row document boxes this CTA fetches per 64-column block of a tile
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -154,7 +160,7 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
     const int S = p.n_stages;
     const int KPS = p.kps;
     const int KG = KB / KPS;
-    const uint32_t stage_bytes = (uint32_t)KPS * kTsBoxBytes;   // per CTA: KPS boxes of 64 documents x 64 columns
+    const uint32_t stage_bytes = (uint32_t)KPS * HB * kTsBoxBytes;  // per CTA: KPS x HB boxes of 64 documents x 64 columns
     const int KSB = p.ks;
     const int KT = KB - KSB;
     const int ACOLS = KT * (kBlockK / 2);
@@ -176,34 +182,40 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
-    const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader
-    const int pair0 = blockIdx.x >> 1;
-    const int n_pairs = gridDim.x >> 1;
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;   // 0 = leader
+    const int pair0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_pairs = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int q0 = (int)rank * kPairRows;
     const int nq = p.nq - q0 < kPairRows ? (p.nq - q0 > 0 ? p.nq - q0 : 0) : kPairRows;
-    // M = 256, N = 128, K-major A and B, fp32 accumulate
+    // M = 256 (pair) / 128, N = 128, K-major A and B, fp32 accumulate
     const uint32_t idesc = (1u << 4) | ((DOC_BF16 ? 1u : 0u) << 7) | ((DOC_BF16 ? 1u : 0u) << 10) |
-                           ((uint32_t)(kPairDocs >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                           ((uint32_t)(kPairDocs >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+    constexpr uint32_t NARR = PAIR ? 8u : 4u;   // epilogue warps that report to the MMA warp
 
     if (p.timeline != nullptr && tid == 0) p.timeline[(size_t)blockIdx.x * 32] = ptx::globaltimer_ns();
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&tmap_docs);
         for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(full + s, 2);
+            ptx::mbar_init(full + s, PAIR ? 2 : 1);
             ptx::mbar_init(empty + s, 1);
         }
         for (int a = 0; a < AS; ++a) {
             ptx::mbar_init(tfull + a, 1);
-            ptx::mbar_init(tempty + a, 8);
+            ptx::mbar_init(tempty + a, NARR);
         }
-        ptx::mbar_init(qready, 8);
+        ptx::mbar_init(qready, NARR);
         ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::cluster_sync_all();   // the peer signals these barriers: they must exist pair-wide first
+    if constexpr (PAIR) ptx::cluster_sync_all();   // the peer signals these barriers: they must exist pair-wide first
     if (warp == 4) {
-        ptx2::tmem_alloc2(tmem_slot, 512);
-        ptx2::tmem_relinquish2();
+        if constexpr (PAIR) {
+            ptx2::tmem_alloc2(tmem_slot, 512);
+            ptx2::tmem_relinquish2();
+        } else {
+            ptx::tmem_alloc(tmem_slot, 512);
+            ptx::tmem_relinquish();
+        }
         ptx::tc_fence_before_sync();
     }
     grid_launch_dependents();
@@ -225,12 +237,22 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
                 ptx::mbar_wait(empty + s, ph ^ 1);
                 if (tl) w_empty += ptx::sm_clock() - t_w;
                 if (ptx::elect_one()) {
-                    const uint32_t lead_full = ptx2::mapa_rank(ptx::smem_u32(full + s), 0);
-                    ptx2::mbar_arrive_expect_tx_cluster(lead_full, stage_bytes);
-                    for (int j = 0; j < KPS; ++j)
-                        ptx2::tma_load_2d_pair(a_smem + (size_t)s * stage_bytes + (size_t)j * kTsBoxBytes, &tmap_docs,
-                                               (kg * KPS + j) * kBlockK, tile * kPairDocs + (int)rank * (kPairDocs / 2),
-                                               lead_full, p.tma_policy);
+                    if constexpr (PAIR) {
+                        const uint32_t lead_full = ptx2::mapa_rank(ptx::smem_u32(full + s), 0);
+                        ptx2::mbar_arrive_expect_tx_cluster(lead_full, stage_bytes);
+                        for (int j = 0; j < KPS; ++j)
+                            ptx2::tma_load_2d_pair(a_smem + (size_t)s * stage_bytes + (size_t)j * kTsBoxBytes, &tmap_docs,
+                                                   (kg * KPS + j) * kBlockK, tile * kPairDocs + (int)rank * (kPairDocs / 2),
+                                                   lead_full, p.tma_policy);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(full + s, stage_bytes);
+                        for (int j = 0; j < KPS; ++j)
+#pragma unroll
+                            for (int hb = 0; hb < 2; ++hb)   // rows 0..63 and 64..127 of the tile, back to back: one 128-row B operand
+                                ptx::tma_load_2d(a_smem + (size_t)s * stage_bytes + (size_t)(j * 2 + hb) * kTsBoxBytes, &tmap_docs,
+                                                 (kg * KPS + j) * kBlockK, tile * kPairDocs + hb * (kPairDocs / 2), full + s,
+                                                 p.tma_policy);
+                    }
                 }
                 __syncwarp();
             }
@@ -242,7 +264,8 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
     } else if (warp == 5) {
         if (rank == 0) {
             // ===== MMA issuer (leader only): waits for both CTAs' query blocks, then D = Q * docs^T for the pair =====
-            ptx2::mbar_wait_cluster(qready, 0);
+            if constexpr (PAIR) ptx2::mbar_wait_cluster(qready, 0);
+            else ptx::mbar_wait(qready, 0);
             ptx::tc_fence_after_sync();
             uint32_t it = 0, lt = 0;
             const uint32_t ring = ptx::smem_u32(a_smem);
@@ -253,7 +276,8 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
                 const int as = lt % AS;
                 const uint32_t aph = (lt / AS) & 1;
                 unsigned long long t_w = tl ? ptx::sm_clock() : 0;
-                ptx2::mbar_wait_cluster(tempty + as, aph ^ 1);
+                if constexpr (PAIR) ptx2::mbar_wait_cluster(tempty + as, aph ^ 1);
+                else ptx::mbar_wait(tempty + as, aph ^ 1);
                 if (tl) w_tempty += ptx::sm_clock() - t_w;
                 ptx::tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ACOLS + as * kPairDocs);
@@ -261,28 +285,36 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     t_w = tl ? ptx::sm_clock() : 0;
-                    ptx2::mbar_wait_cluster(full + s, ph);
+                    if constexpr (PAIR) ptx2::mbar_wait_cluster(full + s, ph);
+                    else ptx::mbar_wait(full + s, ph);
                     if (tl) w_full += ptx::sm_clock() - t_w;
                     ptx::tc_fence_after_sync();
                     if (ptx::elect_one()) {
                         for (int j = 0; j < KPS; ++j) {
                             const int kb = kg * KPS + j;
-                            const uint64_t db0 = ptx::umma_desc_k_sw128(ring + (uint32_t)s * stage_bytes + (uint32_t)j * kTsBoxBytes);
+                            const uint64_t db0 = ptx::umma_desc_k_sw128(ring + (uint32_t)s * stage_bytes + (uint32_t)(j * HB) * kTsBoxBytes);
                             if (kb >= KT) {  // this block of the queries is in shared memory (both CTAs, same offset)
                                 const uint64_t da0 = ptx::umma_desc_k_sw128(qs_base + (uint32_t)(kb - KT) * kTsQBlockBytes);
 #pragma unroll
-                                for (int k4 = 0; k4 < kBlockK / 16; ++k4)
-                                    ptx2::umma2_ss(d_tmem, da0 + (uint64_t)(k4 * 2), db0 + (uint64_t)(k4 * 2), idesc,
-                                                   (kb | k4) != 0 ? 1u : 0u);
+                                for (int k4 = 0; k4 < kBlockK / 16; ++k4) {
+                                    if constexpr (PAIR) ptx2::umma2_ss(d_tmem, da0 + (uint64_t)(k4 * 2), db0 + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
+                                    else ptx::umma_f16(d_tmem, da0 + (uint64_t)(k4 * 2), db0 + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
+                                }
                                 continue;
                             }
 #pragma unroll
-                            for (int k4 = 0; k4 < kBlockK / 16; ++k4)
-                                ptx2::umma2_ts(d_tmem, tmem_base + (uint32_t)(kb * 32 + k4 * 8), db0 + (uint64_t)(k4 * 2), idesc,
-                                               (kb | k4) != 0 ? 1u : 0u);
+                            for (int k4 = 0; k4 < kBlockK / 16; ++k4) {
+                                if constexpr (PAIR) ptx2::umma2_ts(d_tmem, tmem_base + (uint32_t)(kb * 32 + k4 * 8), db0 + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
+                                else umma_f16_ts(d_tmem, tmem_base + (uint32_t)(kb * 32 + k4 * 8), db0 + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0 ? 1u : 0u);
+                            }
                         }
-                        ptx2::umma2_commit_mc(empty + s, (uint16_t)0x3);                    // stage free in both CTAs
-                        if (kg == KG - 1) ptx2::umma2_commit_mc(tfull + as, (uint16_t)0x3);  // accumulator ready in both
+                        if constexpr (PAIR) {
+                            ptx2::umma2_commit_mc(empty + s, (uint16_t)0x3);                    // stage free in both CTAs
+                            if (kg == KG - 1) ptx2::umma2_commit_mc(tfull + as, (uint16_t)0x3);  // accumulator ready in both
+                        } else {
+                            ptx::umma_commit(empty + s);
+                            if (kg == KG - 1) ptx::umma_commit(tfull + as);
+                        }
                     }
                     __syncwarp();
                 }
@@ -299,7 +331,7 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
         // ===== warps 0-3 (both CTAs): thread = query row =====
         const int row = warp * 32 + lane;            // TMEM lane = query row of this CTA
         const bool live = row < nq;
-        const uint32_t lead_qready = ptx2::mapa_rank(ptx::smem_u32(qready), 0);
+        const uint32_t lead_qready = PAIR ? ptx2::mapa_rank(ptx::smem_u32(qready), 0) : 0u;
         // 1. this row of the query block -> tensor memory (first KT blocks) and shared memory (last KSB blocks)
         {
             const float *src = p.q + (long long)(q0 + (live ? row : 0)) * p.q_stride;
@@ -351,7 +383,10 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
             ptx::fence_proxy_async_smem();
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx2::mbar_arrive_cluster(lead_qready);   // 4 warps x 2 CTAs -> the leader's MMA warp may start
+            if (lane == 0) {   // 4 warps (x 2 CTAs) -> the (leader's) MMA warp may start
+                if constexpr (PAIR) ptx2::mbar_arrive_cluster(lead_qready);
+                else ptx::mbar_arrive(qready);
+            }
         }
         // 2. private register list + threshold (ts.cuh, QS epilogue)
         float tau = live ? neg_inf() : __int_as_float(0x7f800000);
@@ -397,7 +432,7 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
             }
         };
 
-        const uint32_t lead_tempty0 = ptx2::mapa_rank(ptx::smem_u32(tempty), 0);
+        const uint32_t lead_tempty0 = PAIR ? ptx2::mapa_rank(ptx::smem_u32(tempty), 0) : 0u;
         uint32_t lt = 0;
         const bool tl = p.timeline != nullptr && warp == 0;
         unsigned long long w_tfull = 0, n_flush = 0, t_loop = tl ? ptx::sm_clock() : 0;
@@ -429,7 +464,10 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
                 if (half == 1) {  // all 128 scores of the row are in registers: the accumulator goes back to the MMA warp
                     ptx::tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) ptx2::mbar_arrive_cluster(lead_tempty0 + (uint32_t)as * 8u);
+                    if (lane == 0) {
+                        if constexpr (PAIR) ptx2::mbar_arrive_cluster(lead_tempty0 + (uint32_t)as * 8u);
+                        else ptx::mbar_arrive(tempty + as);
+                    }
                 }
                 const long long hdoc0 = doc0 + half * 64;
                 const int ndoc = p.n_rows - hdoc0 < 64 ? (p.n_rows - hdoc0 > 0 ? (int)(p.n_rows - hdoc0) : 0) : 64;
@@ -492,11 +530,12 @@ ts_pair_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const PairPar
 
     ptx::tc_fence_before_sync();
     __syncthreads();
-    ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared / tensor memory: nobody leaves early
+    if constexpr (PAIR) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared / tensor memory: nobody leaves early
     if (p.timeline != nullptr && tid == 0) p.timeline[(size_t)blockIdx.x * 32 + 15] = ptx::globaltimer_ns();
     if (warp == 4) {
         ptx::tc_fence_after_sync();
-        ptx2::tmem_dealloc2(tmem_base, 512);
+        if constexpr (PAIR) ptx2::tmem_dealloc2(tmem_base, 512);
+        else ptx::tmem_dealloc(tmem_base, 512);
     }
 }
 
