@@ -161,7 +161,7 @@ typedef struct vqa_tuning {
     int32_t pair;          /* FAST: batches of > 128 queries take the cta_group::2 CTA-pair kernel, 0|1 (1)       */
     int32_t dyn_tiles;     /* smem-resident kernel without clusters: CTAs take tiles from a shared counter, 0|1 (1)*/
     int32_t seed;          /* smem-resident kernel, register lists: warm-up bound from the first tiles' maxima, 0|1 (1) */
-    int32_t wide;          /* FAST: 33..128 queries on single-CTA 128-document tiles (pair.cuh, PAIR = false), 0|1 */
+    int32_t wide;          /* FAST: 33..128 queries (dim <= 768) on single-CTA 128-document tiles (pair.cuh), 0|1 (1) */
     int32_t reserved[2];
 } vqa_tuning_t;
 

@@ -161,7 +161,9 @@ def test_family_selection_and_launch_count():
     assert odd.plan(8, 10, "fast")[0] == 2                                            # dim % 64 != 0: streaming
     assert shard.plan(32, 10, "verify")[0] == 2
     assert shard.plan(32, 10, "fast")[1] == 2            # one scan launch + one reduce launch
-    assert shard.plan(128, 10, "fast") == (4, 2)         # > 32 queries: TMEM-resident-query kernel, one pass
+    assert shard.plan(128, 10, "fast") == (5, 2)         # 33..128 queries: 128-document tiles on single CTAs, one pass
+    assert shard.plan(256, 10, "fast") == (5, 2)         # > 128: CTA pairs (cta_group::2), one pass per 256 queries
+    assert shard.plan(300, 10, "fast") == (5, 4) and shard.plan(128, 10, "ts") == (4, 2)
     assert shard.plan(128, 100, "fast")[0] == 4          # k > 32: same kernel with hi/lo rows and heap lists
     assert shard.plan(8, 100, "fast")[0] == 4 and shard.plan(8, 32, "fast")[0] == 3
     wide = ops.FlatShard(torch.zeros((256, 1024), dtype=torch.float16, device=DEV))

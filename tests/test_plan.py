@@ -53,8 +53,12 @@ def test_default_routing(monkeypatch):
         assert p["tmem_query_cols"] == 256 and p["smem"] <= SMEM and p["stages"] >= 3   # + two 128-column accumulators
     assert plan(n, 768, BF16, 256, 10, pair=0)["family"] == TS
     assert plan(n, 768, BF16, 256, 27)["family"] == TS      # k + spare > 32: no register lists -> TS kernel
-    for b in (33, 64, 128):                                # large batches: queries in TMEM, screen + re-score of 32
+    for b in (33, 64, 128):                                # 33..128 queries: the same 128-document tiles on single CTAs
         p = plan(n, 768, BF16, b, 10)
+        assert (p["family"], p["pass_nq"], p["ks"], p["kscan"], p["rescore"]) == (5, 128, 4, 16, 1) and p["smem"] <= SMEM
+        assert plan(n, 1024, BF16, b, 10)["family"] == TS  # ... at dim <= 768 only
+    for b in (33, 64, 128):                                # knob off: TMEM-resident-query kernel, screen + re-score of 32
+        p = plan(n, 768, BF16, b, 10, wide=0)
         assert (p["family"], p["split"], p["qs"], p["ks"], p["kscan"], p["k_out"], p["rescore"]) == (TS, 0, 1, 2, 16, 32, 1)
         assert p["tmem_query_cols"] == 320 and p["smem"] <= SMEM       # 10 blocks in TMEM -> 3 accumulator stages
     p = plan(n, 768, BF16, 8, 100)                         # k > 32: TS with hi/lo rows and heaps, no re-scoring
@@ -70,7 +74,7 @@ def test_default_routing(monkeypatch):
 def test_round1_routing_is_still_reachable_through_the_knobs(monkeypatch):
     for v in KNOB_ENV:
         monkeypatch.delenv(v, raising=False)
-    r1 = dict(ts_qs=0, reduce_select=0, stream_max_b=0)
+    r1 = dict(ts_qs=0, reduce_select=0, stream_max_b=0, wide=0, pair=0)
     n = 10_000_000
     assert plan(n, 768, BF16, 1, 10, **r1)["family"] == TENSOR
     p = plan(n, 768, BF16, 128, 10, **r1)
@@ -79,6 +83,7 @@ def test_round1_routing_is_still_reachable_through_the_knobs(monkeypatch):
     assert plan(12_500_000, 1024, F16, 64, 100, **r1)["family"] == TENSOR     # dim 1024 does not fit TMEM without QS
     assert plan(n, 1024, BF16, 64, 10, TS, **r1) is None
     monkeypatch.setenv("VQA_TS_QS", "0")                   # the environment spelling is read by vqa_plan_describe too
+    monkeypatch.setenv("VQA_WIDE", "0")
     assert plan(n, 768, BF16, 128, 10)["qs"] == 0
 
 
@@ -111,11 +116,17 @@ def test_every_plan_fits_shared_and_tensor_memory(monkeypatch, qs, select):
                     assert p["tmem_query_cols"] <= 384                        # two accumulator stages
             if p["family"] == TENSOR:
                 assert p["stages"] >= 2 and p["ncol"] in (16, 32, 64, 128)
-    assert (TENSOR, 0, 1, 0) in seen
+            if p["family"] == 5:                                              # 128-document tiles (pairs / single CTAs)
+                kb = dim // 64
+                assert b > 32 and k + 6 <= 32 and dim <= 1024 and (b > 128 or dim <= 768)
+                assert p["stages"] >= 2 and kb % p["kps"] == 0 and 0 <= p["ks"] <= kb
+                assert p["tmem_query_cols"] + 2 * 128 <= 512                  # two 128-column accumulator stages
+                assert (p["kscan"], p["k_out"], p["rescore"]) == (k + 6, 32, 1)
+    assert (TENSOR, 0, 1, 0) in seen and (5, 1, 0, 1) in seen
     if qs:
         assert (TS, 1, 0, 1) in seen and (TS, 1, 1, 0) in seen
     else:
-        assert (TS, 0, 0, 1) in seen and (TS, 0, 1, 0) in seen
+        assert (TS, 0, 1, 0) in seen      # (screen-mode TS plans need the QS variant once 128-document tiles take dim <= 768)
 
 
 def test_config_d_plan(monkeypatch):

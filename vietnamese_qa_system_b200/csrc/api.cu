@@ -173,7 +173,7 @@ const KnobSpec kKnobs[] = {
     {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 1},
     {"VQA_DYN_TILES", &vqa_tuning_t::dyn_tiles, 0, 1, 1},
     {"VQA_SEED", &vqa_tuning_t::seed, 0, 1, 1},
-    {"VQA_WIDE", &vqa_tuning_t::wide, 0, 1, 0},
+    {"VQA_WIDE", &vqa_tuning_t::wide, 0, 1, 1},
 };
 
 void tuning_defaults(vqa_tuning_t *t) {
@@ -430,8 +430,12 @@ int make_plan_uncached(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
             return VQA_OK;
         }
         //  * more than 128 queries (tune.pair): CTA pairs, cta_group::2 MMAs -- the tensor-bound regime.
-        //    (tune.wide: the same 128-document tiles on single CTAs for 33..128 queries)
-        if (((h->tune.pair && nq > 128) || (h->tune.wide && nq > 32 && nq <= 128)) && plan_pair(h, nq, k, pl)) return VQA_OK;
+        //    tune.wide: the same 128-document tiles on single CTAs for 33..128 queries -- measured (profiles/r2_call7.log)
+        //    at dim 768: B = 64 / 128 2.31 / 2.46 -> 2.23 / 2.28 ms on 10 M rows, 0.341 / 0.361 -> 0.335 / 0.348 ms on
+        //    the 8-GPU shard; at dim 1024 (8 of 16 query blocks become shared-memory operands) it loses 2-5 %: dim <= 768
+        if (((h->tune.pair && nq > 128) || (h->tune.wide && nq > 32 && nq <= 128 && h->dim <= 768)) &&
+            plan_pair(h, nq, k, pl))
+            return VQA_OK;
         if ((nq > 32 || k > 32) && ts_eligible(h) && plan_ts(h, nq, k, pl)) return VQA_OK;
         if (tensor_eligible(h) && plan_tensor(h, nq, k, pl)) return VQA_OK;
         plan_stream(h, nq, pl);
