@@ -460,6 +460,40 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_per_step = total_ms / K
     value = B * K / (total_ms / 1e3)
+    # ---- e2e: host buffers through the public API, two steps in flight, all copies inside the timed region ------
+    hpend = [None, None]
+    e2e_sink = [0]
+
+    def e2e_step(i):
+        slot = i & 1
+        if hpend[slot] is not None:            # the result of step i-2 is read on the host before its slot is reused
+            hs, hi_, ev = hpend[slot]
+            ev.synchronize()
+            e2e_sink[0] += int(hi_[0, 0])
+        hpend[slot] = index.search_host_pipelined(q_host, topk, slot)
+
+    def e2e_drain():
+        for p_ in hpend:
+            if p_ is not None:
+                p_[2].synchronize()
+                e2e_sink[0] += int(p_[1][0, 0])
+
+    e2e_ms = timed(e2e_step, K, 3, e2e_drain)
+    shard = index.shard
+    if world == 1:
+        sync_ms = timed(lambda i: shard.search_host(q_host, topk, "fast"), K, 3) / K
+    else:
+        def sync_step(i):
+            _, _, ev = index.search_host_pipelined(q_host, topk, 0)
+            ev.synchronize()
+        sync_ms = timed(sync_step, K, 3) / K
+    e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
+           "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": 2,
+           "one_at_a_time_ms_per_step": sync_ms, "one_at_a_time_qps": B / sync_ms * 1e3,
+           "api": ("FlatShard.search_host_async -> vqa_search_host_async (C ABI, pinned host buffers)" if world == 1 else
+                   "ShardedFlat.search_host_pipelined (pinned host buffers; cudaMemcpyAsync H2D -> vqa_search -> "
+                   "exchange -> vqa_merge_topk -> D2H)")}
+
     # the same steps one at a time (scan -> exchange -> merge serialised on one stream): the latency of a single batch
     serial_ms = timed(lambda i: index.search(q_dev, topk), K, 3) / K
 
@@ -481,7 +515,8 @@ def run_ours(args):
             traffic = None
     kname = {2: "scan_topk_kernel (CUDA cores)", 3: "mma_topk_kernel (tcgen05, queries in smem)",
              4: "ts_topk_kernel (tcgen05, queries in TMEM)",
-             5: "ts_pair_topk_kernel (tcgen05 cta_group::2, queries in TMEM)"}.get(fam, str(fam))
+             5: "ts_pair_topk_kernel (tcgen05, 128-document tiles" + (", cta_group::2 CTA pairs)" if B > 128 else ", single CTAs)")
+             }.get(fam, str(fam))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "frac_of_8TBs_datasheet": achieved / 8000.0, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": kname,
@@ -491,39 +526,6 @@ def run_ours(args):
                 "note": "kernel_ms = CUDA-event time of vqa_search on this rank's shard (scan kernel + the per-query "
                         "candidate reduce, which PDL-overlaps the scan's tail); step_frac = the same bytes over the "
                         "whole step (exchange + merge included)"}
-
-    # ---- e2e: host buffers through the public API, two steps in flight, all copies inside the timed region ------
-    hpend = [None, None]
-    e2e_sink = [0]
-
-    def e2e_step(i):
-        slot = i & 1
-        if hpend[slot] is not None:            # the result of step i-2 is read on the host before its slot is reused
-            hs, hi_, ev = hpend[slot]
-            ev.synchronize()
-            e2e_sink[0] += int(hi_[0, 0])
-        hpend[slot] = index.search_host_pipelined(q_host, topk, slot)
-
-    def e2e_drain():
-        for p_ in hpend:
-            if p_ is not None:
-                p_[2].synchronize()
-                e2e_sink[0] += int(p_[1][0, 0])
-
-    e2e_ms = timed(e2e_step, K, 3, e2e_drain)
-    if world == 1:
-        sync_ms = timed(lambda i: shard.search_host(q_host, topk, "fast"), K, 3) / K
-    else:
-        def sync_step(i):
-            _, _, ev = index.search_host_pipelined(q_host, topk, 0)
-            ev.synchronize()
-        sync_ms = timed(sync_step, K, 3) / K
-    e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
-           "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": 2,
-           "one_at_a_time_ms_per_step": sync_ms, "one_at_a_time_qps": B / sync_ms * 1e3,
-           "api": ("FlatShard.search_host_async -> vqa_search_host_async (C ABI, pinned host buffers)" if world == 1 else
-                   "ShardedFlat.search_host_pipelined (pinned host buffers; cudaMemcpyAsync H2D -> vqa_search -> "
-                   "exchange -> vqa_merge_topk -> D2H)")}
 
     # ---- recall@k of the fast path against fp32-verify arithmetic on the same rows -----
     s_fast, i_fast = index.search(q_dev, topk, "fast")
@@ -634,7 +636,8 @@ def run_ours(args):
                               "tensor_frac": 2.0 * b_ * (hi - lo) * dim / (ms / 1e3) / 1e12 / tf_peak,
                               "family": {2: "stream (CUDA cores)", 3: "tcgen05, queries in smem (hi/lo)",
                                          4: "tcgen05, queries in TMEM (screen + exact re-score)",
-                                         5: "tcgen05 cta_group::2 CTA pairs, queries in TMEM (screen + exact re-score)"
+                                         5: ("tcgen05, 128-document tiles, queries in TMEM (screen + exact re-score): "
+                                             + ("cta_group::2 CTA pairs" if b_ > 128 else "single CTAs"))
                                          }.get(fam_b, str(fam_b))})
             except Exception as exc:  # noqa: BLE001
                 sweep.append({"batch": b_, "error": f"{type(exc).__name__}: {exc}"})

@@ -247,7 +247,7 @@ VQA_API int vqa_merge_topk_strided(const float *cand_scores_dev, const int64_t *
  * peer's flag (release, system scope); vqa_merge_topk_wait is vqa_merge_topk_strided whose kernel
  * first acquires all n_lists flags (>= epoch).  peer_*_ptrs are HOST arrays of `world` device
  * pointers (peer r's slot for this rank / peer r's flag for this rank); flags_dev is this rank's own
- * flag array, one per rank.  k_out <= 32.
+ * flag array, one per rank.
  */
 VQA_API int vqa_exchange_push(const void *local_block_dev, size_t block_bytes, void *const *peer_slot_ptrs,
                               uint64_t *const *peer_flag_ptrs, int32_t world, uint64_t epoch, int32_t device,

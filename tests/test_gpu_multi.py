@@ -73,6 +73,20 @@ for exchange in ("nccl", "p2p"):
     if not ok:
         print("FAILED", exchange, storage, mode, rank, flush=True)
         break
+# top-100 (BASELINE configs[3]'s k): the big-k merge kernel behind both exchanges, in order and pipelined
+for exchange in ("nccl", "p2p"):
+    full = ops.FlatShard(rows.to(torch.float16))
+    fs, fi = full.search(qd, 100, "verify")
+    sh = ShardedFlat(rows[lo:hi].to(torch.float16).contiguous(), N, mode="verify", exchange=exchange)
+    s, i = sh.search(qd, 100)
+    ok = ok and torch.equal(i, fi) and torch.equal(s, fs)
+    for slot in (0, 1, 0):
+        ps, pi, ev = sh.search_pipelined(qd, 100, slot)
+        ev.synchronize()
+        ok = ok and torch.equal(pi, fi) and torch.equal(ps, fs)
+    if not ok:
+        print("FAILED top-100", exchange, rank, flush=True)
+        break
 # the drop-in class on a row-sharded index (Embeddings(shards=True), heavy_ranker.py:78-83 form): same hits as one GPU,
 # dense and hybrid (the BM25 leg and the content store are replicated per rank), built directly and loaded from disk
 from vietnamese_qa_system_b200 import Embeddings

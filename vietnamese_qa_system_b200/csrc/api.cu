@@ -1127,7 +1127,7 @@ int vqa_merge_topk_wait(const float *cand_scores_dev, const int64_t *cand_ids_de
         return fail(VQA_E_INVALID, "null device pointer argument");
     if (n_lists < 1 || n_lists > 32 || n_queries < 1 || k_in < 1)
         return fail(VQA_E_INVALID, "n_lists must be in [1, 32]; n_queries, k_in >= 1");
-    if (k_out < 1 || k_out > 32) return fail(VQA_E_INVALID, "k_out must be in [1, 32] for the flag-waiting merge");
+    if (k_out < 1 || k_out > vqa::kMaxK) return fail(VQA_E_INVALID, "k_out must be in [1, %d]", vqa::kMaxK);
     if (list_stride_scores < (int64_t)n_queries * k_in || list_stride_ids < (int64_t)n_queries * k_in)
         return fail(VQA_E_INVALID, "list strides must be >= n_queries * k_in elements");
     if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");

@@ -537,6 +537,15 @@ __global__ void __launch_bounds__(kReduceBigWarps * 32) reduce_topk_kernel(const
     if (p.trigger_early) grid_launch_dependents();
     __syncthreads();
     grid_dependency_wait();
+    if (p.wait_flags != nullptr) {   // peer-memory exchange: every rank's block must have landed (acquire, system scope)
+        if (tid < p.wait_n) {
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u64(p.wait_flags + tid) < p.wait_epoch) {
+                if (++spins > (1ull << 31)) __trap();  // a peer died: fail the launch instead of hanging
+            }
+        }
+        __syncthreads();
+    }
     const int lmod = p.list_mod > 1 ? p.list_mod : 1;
     const int lgrp = p.list_mod > 1 ? q / p.queries_per_group : 0;
     const int n_eff = p.n_lists / lmod;

@@ -102,6 +102,7 @@ class ShardedFlat:
         self._bufs = {}
         self._epoch = 0
         self._side = None      # side stream of the pipelined search (exchange + merge of batch i under scan i+1)
+        self._copy = None      # copy stream of the host-buffer form (H2D of batch i+1 under scan i)
         self._last = {}        # (b, k, slot) -> event after which the slot's buffers may be reused
 
     @staticmethod
@@ -126,7 +127,7 @@ class ShardedFlat:
             out_i = torch.empty((b, k), dtype=torch.int64, device=dev)
             ws = torch.empty(self.shard.workspace_bytes(b, k, self.mode), dtype=torch.uint8, device=dev)
             p2p = None
-            if self.exchange in ("auto", "p2p") and k <= 32 and self.world <= 16:
+            if self.exchange in ("auto", "p2p") and self.world <= 16:
                 try:
                     p2p = self._ops.PeerExchange(block, self.rank, self.world, dev, self.group)
                 except Exception:  # noqa: BLE001 - symmetric memory unavailable on this build / topology
@@ -181,6 +182,16 @@ class ShardedFlat:
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
         buf = self._buffers(b, k, slot)
+        if buf[7] is None:
+            # NCCL exchange: its kernel cannot share an SM with the scan's 226 KB CTAs and spins until every rank has
+            # joined, so on a side stream it would sit on an SM the next scan needs (measured on 8 GPUs, config D:
+            # 6.64 ms pipelined vs 5.91 ms in order) -- keep the step in stream order
+            self.shard.search(queries, k, self.mode, buf[2], buf[3], workspace=buf[8])
+            out_s, out_i = self._exchange(buf, b, k)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._last[(b, k, slot)] = done
+            return out_s, out_i, done
         prev = self._last.get((b, k, slot))
         if prev is not None:
             main.wait_event(prev)          # the slot's previous exchange has read `local` and written the outputs
@@ -220,12 +231,21 @@ class ShardedFlat:
             self._bufs[key] = st
         q_dev, hs, hi = st
         main = torch.cuda.current_stream(dev)
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=dev)
         prev = self._last.get((b, k, slot))
-        if prev is not None:
-            main.wait_event(prev)          # the slot's previous D2H copies are done (q_dev is re-written below)
-        q_dev.copy_(queries_host, non_blocking=True)
+        with torch.cuda.stream(self._copy):
+            # the queries of step i+1 cross PCIe on a copy stream while the scan of step i runs; the scan only waits
+            # for the event (the slot's previous D2H copies are done before q_dev is re-written)
+            if prev is not None:
+                self._copy.wait_event(prev)
+            q_dev.copy_(queries_host, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._copy)
+        main.wait_event(copied)
         out_s, out_i, done = self.search_pipelined(q_dev, k, slot)
         with torch.cuda.stream(self._side):
+            self._side.wait_event(done)    # (the NCCL form finishes on the main stream)
             hs.copy_(out_s, non_blocking=True)
             hi.copy_(out_i, non_blocking=True)
             done = torch.cuda.Event()
