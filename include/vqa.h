@@ -162,7 +162,8 @@ typedef struct vqa_tuning {
     int32_t dyn_tiles;     /* smem-resident kernel without clusters: CTAs take tiles from a shared counter, 0|1 (1)*/
     int32_t seed;          /* smem-resident kernel, register lists: warm-up bound from the first tiles' maxima, 0|1 (1) */
     int32_t wide;          /* FAST: 33..128 queries (dim <= 768) on single-CTA 128-document tiles (pair.cuh), 0|1 (1) */
-    int32_t reserved[2];
+    int32_t ts_m64;        /* TS kernel, <= 64 queries, screen mode: M = 64 instructions, 0|1                       */
+    int32_t reserved[1];
 } vqa_tuning_t;
 
 /* Library defaults (no environment). */
@@ -303,7 +304,7 @@ VQA_API int vqa_search_plan(const vqa_index_t *h, int32_t n_queries, int32_t k, 
  * 2 passes, 3 side-by-side groups, 4 ring stages, 5 k-blocks per stage, 6 MMA N (tensor family),
  * 7 hi/lo split (tensor: ss_split, TS: ts_split), 8 QS variant, 9 query blocks in shared memory,
  * 10 list length inside the scan, 11 candidates kept by the reduce (k_out), 12 reduce re-scores (0/1),
- * 13 TMEM columns used, 14 reserved, 15 reserved; *smem_bytes = dynamic shared memory of the scan kernel. */
+ * 13 TMEM columns used, 14 M = 64 variant (0/1), 15 reserved; *smem_bytes = dynamic shared memory of the scan kernel. */
 VQA_API int vqa_plan_describe(int64_t n_rows, int32_t dim, int32_t dtype, int32_t n_queries, int32_t k,
                               int32_t mode, int32_t sm_count, int32_t max_smem, int32_t *out,
                               size_t *smem_bytes);

@@ -273,3 +273,24 @@ def test_cta_pair_kernel_matches_the_oracle(storage, n, d, b, k):
     assert i[0, :2].tolist() == [3, n // 2] and i[b - 1, 0] == n - 1
     s2, i2, _ = gpu_search(docs, q, k, "ts", storage)
     assert recall(i, i2) >= 0.999 and np.abs(s - s2).max() <= 5e-7
+
+
+@pytest.mark.parametrize("storage,n,d,b,k,ks", [("fp16", 30000, 1024, 64, 100, 6), ("bf16", 20000, 768, 40, 10, 2),
+                                                ("bf16", 5000, 768, 64, 26, 4), ("fp16", 9000, 512, 33, 5, 0),
+                                                ("fp16", 40000, 1024, 50, 100, 8)])
+def test_m64_variant_of_the_tmem_resident_query_kernel(monkeypatch, storage, n, d, b, k, ks):
+    """<= 64 queries in screen mode (BASELINE configs[3]: B = 64, top-100) with M = 64 instructions: the 64 query rows
+    sit in lanes 0..15 of each quarter of tensor memory, half the A bytes are read per MMA, shared-memory query blocks
+    are 8 KB.  Same oracle bars; ids equal to the M = 128 kernel's."""
+    monkeypatch.setenv("VQA_TS_KS", str(ks))
+    monkeypatch.setenv("VQA_TS_M64", "0")
+    rng = np.random.default_rng(n + b)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]
+    q[0] = docs[3]
+    q[b - 1] = docs[n - 1]
+    s0, i0, _ = gpu_search(docs, q, k, "ts", storage)
+    monkeypatch.setenv("VQA_TS_M64", "1")
+    s, i = _check(docs, q, k, "ts", storage)
+    assert i[0, :2].tolist() == [3, n // 2] and i[b - 1, 0] == n - 1
+    assert recall(i, i0) >= 0.999 and np.abs(s - s0).max() <= 5e-7

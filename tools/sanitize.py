@@ -17,13 +17,15 @@ def unit(n, d):
     return x / x.norm(dim=1, keepdim=True)
 
 
-docs, q = unit(3000, 768), unit(70, 768)
+docs, q = unit(3000, 768), unit(300, 768)
 for dt in (torch.float32, torch.bfloat16):
     shard = ops.FlatShard(docs.to(dev).to(dt))
-    modes = ["verify", "stream"] + ([] if dt == torch.float32 else ["tensor", "ts", "fast"])
+    modes = ["verify", "stream"] + ([] if dt == torch.float32 else ["tensor", "ts", "pair", "fast"])
     for mode in modes:
-        for b, k in ((1, 10), (9, 5), (40, 10), (70, 100)):
+        for b, k in ((1, 10), (9, 5), (32, 10), (40, 10), (70, 100), (130, 10), (300, 10)):
             if mode in ("verify", "stream") and b > 9:
+                continue
+            if mode == "pair" and k > 26:
                 continue
             s, i = shard.search(q[:b].to(dev), k, mode)
             torch.cuda.synchronize()

@@ -141,6 +141,7 @@ struct Plan {
     int ts_afp16;
     int ts_qs;    // TS family: the opt-in QS kernel variant (part of the query block in shared memory)
     int ts_ks;    // QS: 64-column blocks of the query block kept in shared memory
+    int ts_m64;   // QS, <= 64 queries, screen mode: M = 64 instructions
     int grid;
 };
 
@@ -174,6 +175,7 @@ const KnobSpec kKnobs[] = {
     {"VQA_DYN_TILES", &vqa_tuning_t::dyn_tiles, 0, 1, 1},
     {"VQA_SEED", &vqa_tuning_t::seed, 0, 1, 1},
     {"VQA_WIDE", &vqa_tuning_t::wide, 0, 1, 1},
+    {"VQA_TS_M64", &vqa_tuning_t::ts_m64, 0, 1, 0},
 };
 
 void tuning_defaults(vqa_tuning_t *t) {
@@ -293,7 +295,8 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     int split = tu.ts_split >= 0 ? tu.ts_split : ((k + spare <= 32 || (big_screen_ok && h->dtype == VQA_F16)) ? 0 : 1);
     if (!split && k + spare > 32 && !big_screen_ok) split = 1;
     const int kscan = split ? k : k + spare;
-    const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split, ks, nq, qs);
+    const int m64 = (qs && !split && nq <= 64 && tu.ts_m64) ? 1 : 0;
+    const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split, ks, nq, qs, m64);
     if (fixed >= (size_t)h->max_smem) return false;
     int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
     // 8 KB boxes: four column blocks per ring stage halve the per-byte handshakes (measured 2.74 -> 2.57 ms
@@ -310,7 +313,8 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     pl->ts_qs = qs;
     pl->ts_ks = ks;
     pl->ts_afp16 = 0;  // (fp16 queries against bf16 rows would halve the rounding, but the MMA rejects mixed operands)
-    pl->pass_nq = split ? 64 : 128;
+    pl->ts_m64 = m64;
+    pl->pass_nq = (split || m64) ? 64 : 128;
     pl->ncol = 0;
     pl->stages = stages;
     pl->kps = kps;
@@ -694,7 +698,8 @@ int vqa_plan_describe_tuned(int64_t n_rows, int32_t dim, int32_t dtype, int32_t 
         out[11] = pl.ts_split ? kscan : (kscan > 32 ? vqa::kMaxK : 32);
         out[12] = pl.ts_split ? 0 : 1;
         out[13] = (dim / vqa::kBlockK - pl.ts_ks) * (vqa::kBlockK / 2);  // query block; the rest are accumulators
-        *smem_bytes = vqa::ts_smem_bytes(kscan, pl.stages * pl.kps, pl.ts_split, pl.ts_ks, nq_launch, pl.ts_qs);
+        out[14] = pl.ts_m64;
+        *smem_bytes = vqa::ts_smem_bytes(kscan, pl.stages * pl.kps, pl.ts_split, pl.ts_ks, nq_launch, pl.ts_qs, pl.ts_m64);
     } else if (pl.family == VQA_MODE_FAST_PAIR) {
         const int kscan = k + spare_ranks(&fake);
         out[7] = 0;
@@ -803,6 +808,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             a.a_fp16 = pl.ts_afp16;
             a.qs = pl.ts_qs;
             a.ks = pl.ts_ks;
+            a.m64 = pl.ts_m64;
             a.pdl = (l0 > qb && h->tune.pdl_chain) ? 1 : 0;
             a.stages = pl.stages;
             a.kps = pl.kps;

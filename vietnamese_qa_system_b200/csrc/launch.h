@@ -78,6 +78,7 @@ struct TsLaunch {
     int pdl = 0;  // opt-in: launch with programmatic stream serialization (2nd+ scan of one search)
     int qs = 0;   // 1: the QS kernel variant (part of the query block in shared memory); opt-in, see ts.cuh
     int ks = 0;   // QS: 64-column blocks of the query block kept in shared memory
+    int m64 = 0;  // QS, <= 64 queries, no hi/lo rows: M = 64 instructions (half the tensor-memory A read per MMA)
     unsigned long long *timeline = nullptr;  // diagnostic per-CTA counters (vqa_debug_timeline), normally nullptr
 };
 
@@ -108,7 +109,7 @@ cudaError_t launch_pair(const PairLaunch &a, cudaStream_t st);
 size_t pair_smem_bytes(int boxes, int ks);
 
 cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st);
-size_t ts_smem_bytes(int k, int boxes, int split, int ks = 0, int nq = 1 << 30, int qs = 0);
+size_t ts_smem_bytes(int k, int boxes, int split, int ks = 0, int nq = 1 << 30, int qs = 0, int m64 = 0);
 cudaError_t launch_scan(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_f32(const ScanLaunch &a, cudaStream_t st);
 cudaError_t launch_scan_bf16(const ScanLaunch &a, cudaStream_t st);

@@ -78,11 +78,12 @@ inline int ts_list_rows(int k, int split, int nq, int qs) {
 // [lists: rows x k x 8 B, or the 32-deep candidate buffers (rows x 32 x 8 B) of the register-list variants]
 // shared-memory lists (k > 32) are kept for the live rows only: 64 with hi/lo rows, else 128; every
 // variant also has 32-deep candidate buffers for those rows
-inline size_t ts_smem_bytes_rt(int k, int boxes, int split, int ks = 0, int nq = 1 << 30, int qs = 0) {
+// m64: the M = 64 variant (<= 64 queries per CTA): a shared-memory query block is 64 rows = 8 KB
+inline size_t ts_smem_bytes_rt(int k, int boxes, int split, int ks = 0, int nq = 1 << 30, int qs = 0, int m64 = 0) {
     const int depth = ts_reg_list_len(k) > 0 ? 32 : k + 32;
     const int rows = ts_list_rows(k, split, nq, qs);
-    return 1024 + (size_t)ks * kTsQBlockBytes + (size_t)boxes * kTsBoxBytes + 1024 + (split ? 2 * 64 * kTsDocs * 4 : 0) +
-           (size_t)rows * depth * 8;
+    return 1024 + (size_t)ks * (m64 ? kTsQBlockBytes / 2 : kTsQBlockBytes) + (size_t)boxes * kTsBoxBytes + 1024 +
+           (split ? 2 * 64 * kTsDocs * 4 : 0) + (size_t)rows * depth * 8;
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -113,10 +114,16 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // shared-memory-A form of the MMA into the same accumulator; only the first dim/64 - ks blocks occupy TMEM.
 // That (a) fits dim 1024 (BASELINE configs[3]: 12 blocks = 384 columns in TMEM + 4 blocks = 64 KB in shared
 // memory, 2 accumulator stages) and (b) is a knob at dim 768: ks = 4 leaves 256 TMEM columns = 4 accumulator
-// stages instead of 2.  QS = false compiles exactly the kernel measured in round 1.
-template <bool DOC_BF16, int KL, bool QS = false>
+// stages instead of 2.  (Default since round 2; QS = false is round 1's kernel.)
+// M64 (QS variants, <= 64 queries per CTA, no hi/lo rows): M = 64 instructions.  The 64 query rows sit in lanes 0..15
+// of each of the four 32-lane quarters of tensor memory (row r <-> lane 32 * (r / 16) + r % 16, pinned on the hardware
+// by tools/m64_probe.cu), so each instruction reads half the A bytes from tensor memory -- the read port (64 B/cycle)
+// is what paces the M = 128 x N = 64 tiles -- and a shared-memory query block is 8 KB instead of 16.
+template <bool DOC_BF16, int KL, bool QS = false, bool M64 = false>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) {
+    static_assert(!M64 || QS, "M = 64 is a QS variant");
+    constexpr int QBLK = M64 ? kTsQBlockBytes / 2 : kTsQBlockBytes;   // bytes of one shared-memory query block
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -130,7 +137,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     const int ACOLS = QS ? KT * (kBlockK / 2) : p.dim / 2;  // TMEM columns of the query block
     const int AS = (QS && (512 - ACOLS) / kTsDocs > kMaxAccStages) ? kMaxAccStages : (512 - ACOLS) / kTsDocs;  // accumulator stages
     unsigned char *q_smem = smem;                   // QS: KSB blocks of 128 query rows x 128 bytes
-    unsigned char *a_smem = smem + (size_t)KSB * kTsQBlockBytes;  // document ring
+    unsigned char *a_smem = smem + (size_t)KSB * QBLK;  // document ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(a_smem + (size_t)S * stage_bytes);
     uint64_t *full = bars;
     uint64_t *empty = bars + kMaxStages;
@@ -156,7 +163,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     const uint16_t cta_mask = (uint16_t)((1u << p.n_groups) - 1u);
     const int slice_rows = kTsDocs / (p.multicast ? p.n_groups : 1);
     const uint32_t idesc = (1u << 4) | ((p.a_fp16 ? 0u : (DOC_BF16 ? 1u : 0u)) << 7) | ((DOC_BF16 ? 1u : 0u) << 10) |
-                           ((uint32_t)(kTsDocs >> 3) << 17) | ((uint32_t)(kTsRows >> 4) << 24);
+                           ((uint32_t)(kTsDocs >> 3) << 17) | ((uint32_t)((M64 ? 64 : kTsRows) >> 4) << 24);
 
     if (p.timeline != nullptr && tid == 0) p.timeline[(size_t)blockIdx.x * 32] = ptx::globaltimer_ns();
     if (warp == 4 && lane == 0) {
@@ -246,7 +253,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                         const int kb = kg * KPS + j;
                         const uint64_t db0 = ptx::umma_desc_k_sw128(ring + (uint32_t)s * stage_bytes + (uint32_t)j * kTsBoxBytes);
                         if (QS && kb >= KT) {  // this block of the queries is in shared memory
-                            const uint64_t da0 = ptx::umma_desc_k_sw128(qs_base + (uint32_t)(kb - KT) * kTsQBlockBytes);
+                            const uint64_t da0 = ptx::umma_desc_k_sw128(qs_base + (uint32_t)(kb - KT) * QBLK);
 #pragma unroll
                             for (int k4 = 0; k4 < kBlockK / 16; ++k4)  // +32 bytes along K = +2 in the address field
                                 ptx::umma_f16(d_tmem, da0 + (uint64_t)(k4 * 2), db0 + (uint64_t)(k4 * 2), idesc,
@@ -275,9 +282,9 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     } else {
         // ===== warps 0-3: thread = query row =====
         const int row = warp * 32 + lane;                       // TMEM lane
-        const int qrow = p.split ? (row & 63) : row;            // query of this row within the chunk
-        const bool is_lo = p.split && row >= 64;
-        const bool live = qrow < nq;
+        const int qrow = M64 ? warp * 16 + (lane & 15) : (p.split ? (row & 63) : row);   // query of this row within the chunk
+        const bool is_lo = !M64 && p.split && row >= 64;
+        const bool live = qrow < nq && (!M64 || lane < 16);     // (M = 64: lanes 16..31 of every quarter are not rows)
         // 1. write this row of the query block into TMEM (16-bit pairs, K ascending)
         {
             const float *src = p.q + (long long)(q0 + (live ? qrow : 0)) * p.q_stride;
@@ -348,8 +355,9 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             if constexpr (QS) {
                 // the remaining blocks of this row -> shared memory, K-major, 128-byte swizzle (16-byte chunk c of
                 // row r at r * 128 + ((c ^ (r & 7)) << 4)), same 16-bit values as the TMEM part
-                for (int kb = KT; kb < KB; ++kb) {
-                    unsigned char *tile = q_smem + (size_t)(kb - KT) * kTsQBlockBytes;
+                for (int kb = KT; kb < KB && (!M64 || lane < 16); ++kb) {
+                    unsigned char *tile = q_smem + (size_t)(kb - KT) * QBLK;
+                    const int row = M64 ? qrow : warp * 32 + lane;   // row of the K-major shared-memory tile
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -391,7 +399,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
         int cnt = 0;
         float worst_s = neg_inf();                  // KL == 0: the heap's root = the worst kept entry
         uint32_t worst_i = invalid_id<uint32_t>();
-        const int lrow = row & (LR - 1);            // this thread's list / buffer column
+        const int lrow = M64 ? qrow : (row & (LR - 1));   // this thread's list / buffer column
         float *buf_s = KL > 0 ? lst_s : reinterpret_cast<float *>(lst_i + (size_t)p.k * LR);   // [CAP][LR]
         uint32_t *buf_i = reinterpret_cast<uint32_t *>(buf_s + CAP * LR);
         if constexpr (KL > 0) {
@@ -400,7 +408,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 rs[e] = neg_inf();
                 ri[e] = invalid_id<uint32_t>();
             }
-        } else if (!is_lo && (!QS || row < LR)) {  // (QS with <= 64 queries: rows 64.. own no list column)
+        } else if (!is_lo && (!QS || row < LR) && (!M64 || lane < 16)) {  // (QS with <= 64 queries: rows 64.. own no list column)
             for (int e = 0; e < p.k; ++e) {
                 lst_s[e * LR + lrow] = neg_inf();
                 lst_i[e * LR + lrow] = invalid_id<uint32_t>();

@@ -4,13 +4,13 @@
 
 namespace vqa {
 
-template <bool BF16, int KL, bool QS>
+template <bool BF16, int KL, bool QS, bool M64 = false>
 static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     TsParams p;
     p.q = a.q;
     p.q_stride = a.q_stride;
     p.nq = a.nq;
-    p.per_cta = a.split ? 64 : 128;
+    p.per_cta = (a.split || M64) ? 64 : 128;
     p.split = a.split;
     p.a_fp16 = a.a_fp16;
     p.k = a.k;
@@ -29,8 +29,8 @@ static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     p.multicast = a.multicast;
     p.ks = QS ? a.ks : 0;
     p.timeline = a.timeline;
-    const size_t smem = ts_smem_bytes_rt(a.k, a.stages * a.kps, a.split, p.ks, a.nq, QS ? 1 : 0);
-    auto kern = ts_topk_kernel<BF16, KL, QS>;
+    const size_t smem = ts_smem_bytes_rt(a.k, a.stages * a.kps, a.split, p.ks, a.nq, QS ? 1 : 0, M64 ? 1 : 0);
+    auto kern = ts_topk_kernel<BF16, KL, QS, M64>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (!a.multicast && !a.pdl) {
@@ -64,12 +64,12 @@ static cudaError_t launch_ts_tk(const TsLaunch &a, cudaStream_t st) {
     return cudaLaunchKernelEx(&cfg, kern, *a.tmap, p);
 }
 
-template <bool BF16, bool QS>
+template <bool BF16, bool QS, bool M64 = false>
 static cudaError_t launch_ts_t(const TsLaunch &a, cudaStream_t st) {
     switch (ts_reg_list_len(a.k)) {
-        case 16: return launch_ts_tk<BF16, 16, QS>(a, st);
-        case 32: return launch_ts_tk<BF16, 32, QS>(a, st);
-        default: return launch_ts_tk<BF16, 0, QS>(a, st);
+        case 16: return launch_ts_tk<BF16, 16, QS, M64>(a, st);
+        case 32: return launch_ts_tk<BF16, 32, QS, M64>(a, st);
+        default: return launch_ts_tk<BF16, 0, QS, M64>(a, st);
     }
 }
 
@@ -78,14 +78,18 @@ cudaError_t launch_ts(const TsLaunch &a, cudaStream_t st) {
     if (a.qs) {
         // the TMEM part of the query block must leave at least one accumulator stage
         if (a.ks < 0 || a.ks > kb || (kb - a.ks) * (kBlockK / 2) + kTsDocs > 512) return cudaErrorInvalidValue;
+        if (a.m64) {   // M = 64 instructions: one chunk of <= 64 queries, no hi/lo rows, no cluster
+            if (a.split || a.nq > 64 || a.n_groups != 1) return cudaErrorInvalidValue;
+            return a.bf16 ? launch_ts_t<true, true, true>(a, st) : launch_ts_t<false, true, true>(a, st);
+        }
         return a.bf16 ? launch_ts_t<true, true>(a, st) : launch_ts_t<false, true>(a, st);
     }
     if (a.dim / 2 + kTsDocs > 512) return cudaErrorInvalidValue;
     return a.bf16 ? launch_ts_t<true, false>(a, st) : launch_ts_t<false, false>(a, st);
 }
 
-size_t ts_smem_bytes(int k, int boxes, int split, int ks, int nq, int qs) {
-    return ts_smem_bytes_rt(k, boxes, split, ks, nq, qs);
+size_t ts_smem_bytes(int k, int boxes, int split, int ks, int nq, int qs, int m64) {
+    return ts_smem_bytes_rt(k, boxes, split, ks, nq, qs, m64);
 }
 
 }  // namespace vqa
