@@ -79,6 +79,7 @@ int main(void) {
     CHECK_VQA(vqa_search_host_staging_bytes(index, b, k, VQA_MODE_VERIFY, &staging_bytes));
     void *staging = NULL;
     CHECK_CUDA(cudaMalloc(&staging, staging_bytes));
+    CHECK_CUDA(cudaMemset(staging, 0, staging_bytes)); /* zeroed once after allocation (include/vqa.h) */
     float scores[4 * 5];
     int64_t ids[4 * 5];
     CHECK_VQA(vqa_search_host(index, q, b, k, VQA_MODE_VERIFY, scores, ids, staging, staging_bytes, /*stream=*/NULL));

@@ -175,7 +175,10 @@ VQA_API int vqa_tuning_from_env(vqa_tuning_t *t);
 VQA_API int vqa_index_set_tuning(vqa_index_t *h, const vqa_tuning_t *t);
 VQA_API int vqa_index_get_tuning(const vqa_index_t *h, vqa_tuning_t *t);
 
-/* Bytes of device workspace vqa_search needs for a batch of `n_queries`, top `k`. */
+/* Bytes of device workspace vqa_search needs for a batch of `n_queries`, top `k`.
+ * Zero the workspace once after allocating it (cudaMemset); the library keeps it consistent from then on.  A
+ * workspace that was never zeroed still gives correct results -- stale words are recognised by their epoch tags --
+ * but its first search pays a one-off ~0.3 ms repair of the tile counter (a CAS that 148 CTAs contend for). */
 VQA_API int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int32_t mode,
                                 size_t *bytes);
 
@@ -199,7 +202,7 @@ VQA_API int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q
 /*
  * Same search with HOST buffers: H2D copy of the queries, search, D2H copy of
  * the results, stream-synchronised before returning.  `staging_dev` must hold
- * vqa_search_host_staging_bytes() bytes.  This is the call the reference-facing
+ * vqa_search_host_staging_bytes() bytes (it contains the search workspace: zero it once after allocation).  This is the call the reference-facing
  * plugin makes for numpy inputs (heavy_ranker.py:98-101 receives host lists).
  */
 VQA_API int vqa_search_host_staging_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k,

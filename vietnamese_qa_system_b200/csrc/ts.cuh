@@ -408,7 +408,8 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                 rs[e] = neg_inf();
                 ri[e] = invalid_id<uint32_t>();
             }
-        } else if (!is_lo && (!QS || row < LR) && (!M64 || lane < 16)) {  // (QS with <= 64 queries: rows 64.. own no list column)
+        } else if (M64 ? lane < 16 : (!is_lo && (!QS || row < LR))) {  // (QS with <= 64 queries: rows 64.. own no list column;
+                                                                         //  M = 64: the rows are lanes 0..15 of every quarter)
             for (int e = 0; e < p.k; ++e) {
                 lst_s[e * LR + lrow] = neg_inf();
                 lst_i[e * LR + lrow] = invalid_id<uint32_t>();

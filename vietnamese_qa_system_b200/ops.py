@@ -106,7 +106,7 @@ class FlatShard:
         if ws is None:
             need = ctypes.c_size_t()
             N.check(N.lib().vqa_workspace_bytes(self._h, n_queries, k, mode, ctypes.byref(need)))
-            ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            ws = torch.zeros(need.value, dtype=torch.uint8, device=self.device)   # zeroed once (include/vqa.h)
             self._ws[key] = ws
         return ws
 
@@ -155,7 +155,7 @@ class FlatShard:
         if st is None:
             need = ctypes.c_size_t()
             N.check(N.lib().vqa_search_host_staging_bytes(self._h, b, k, m, ctypes.byref(need)))
-            st = (torch.empty(need.value, dtype=torch.uint8, device=self.device),
+            st = (torch.zeros(need.value, dtype=torch.uint8, device=self.device),
                   torch.empty((b, k), dtype=torch.float32).pin_memory(),
                   torch.empty((b, k), dtype=torch.int64).pin_memory())
             self._ws[key] = st
@@ -183,7 +183,7 @@ class FlatShard:
         if st is None:
             need = ctypes.c_size_t()
             N.check(N.lib().vqa_search_host_staging_bytes(self._h, b, k, m, ctypes.byref(need)))
-            st = (torch.empty(need.value, dtype=torch.uint8, device=self.device),
+            st = (torch.zeros(need.value, dtype=torch.uint8, device=self.device),
                   torch.empty((b, k), dtype=torch.float32).pin_memory(),
                   torch.empty((b, k), dtype=torch.int64).pin_memory())
             self._ws[key] = st

@@ -125,7 +125,7 @@ class ShardedFlat:
             i_view = local[ids_off:ids_off + b * k * 8].view(torch.int64).view(b, k)
             out_s = torch.empty((b, k), dtype=torch.float32, device=dev)
             out_i = torch.empty((b, k), dtype=torch.int64, device=dev)
-            ws = torch.empty(self.shard.workspace_bytes(b, k, self.mode), dtype=torch.uint8, device=dev)
+            ws = torch.zeros(self.shard.workspace_bytes(b, k, self.mode), dtype=torch.uint8, device=dev)
             p2p = None
             if self.exchange in ("auto", "p2p") and self.world <= 16:
                 try:
@@ -171,7 +171,7 @@ class ShardedFlat:
         if self.world == 1:
             ws = self._bufs.get(("ws1", b, k, slot))
             if ws is None:
-                ws = (torch.empty(self.shard.workspace_bytes(b, k, self.mode), dtype=torch.uint8, device=dev),
+                ws = (torch.zeros(self.shard.workspace_bytes(b, k, self.mode), dtype=torch.uint8, device=dev),
                       torch.empty((b, k), dtype=torch.float32, device=dev),
                       torch.empty((b, k), dtype=torch.int64, device=dev))
                 self._bufs[("ws1", b, k, slot)] = ws
