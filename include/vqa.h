@@ -156,13 +156,13 @@ typedef struct vqa_tuning {
     int32_t pdl_chain;     /* 2nd+ scan launch of one search overlaps the previous reduce, 0|1                    */
     int32_t tma_l2promo;   /* CUtensorMapL2promotion of the document tensor map, 0..3 (3 = 256 B)                 */
     int32_t tma_hint;      /* L2 policy of the document stream: 0 normal, 1 evict-first, 2 evict-last (1)         */
-    int32_t stream_max_b;  /* FAST: batches up to this size take the CUDA-core streaming kernel, 0..8 (2) ...     */
+    int32_t stream_max_b;  /* FAST: batches up to this size take the CUDA-core streaming kernel, 0..8 (0) ...     */
     int32_t stream_min_mb; /* ... when the shard is at least this many MB (its fixed cost is ~80 us higher), (8000)*/
     int32_t pair;          /* FAST: batches of > 128 queries take the cta_group::2 CTA-pair kernel, 0|1 (1)       */
     int32_t dyn_tiles;     /* smem-resident kernel without clusters: CTAs take tiles from a shared counter, 0|1 (1)*/
     int32_t seed;          /* smem-resident kernel, register lists: warm-up bound from the first tiles' maxima, 0|1 (1) */
     int32_t wide;          /* FAST: 33..128 queries (dim <= 768) on single-CTA 128-document tiles (pair.cuh), 0|1 (1) */
-    int32_t ts_m64;        /* TS kernel, <= 64 queries, screen mode: M = 64 instructions, 0|1                       */
+    int32_t ts_m64;        /* TS kernel, <= 64 queries, screen mode: M = 64 instructions, 0|1 (1)                   */
     int32_t reserved[1];
 } vqa_tuning_t;
 

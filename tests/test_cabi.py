@@ -38,7 +38,7 @@ def test_tuning_knobs_are_validated_once_not_read_on_the_search_path(monkeypatch
         monkeypatch.delenv(v, raising=False)
     t = N.tuning_default()
     assert t.size == ctypes.sizeof(N.Tuning) and t.ts_extra == 6 and t.ts_qs == 1 and t.reduce_select == 1
-    assert t.ts_ks == -1 and t.stream_max_b == 2 and t.tma_l2promo == 3 and t.reduce_early == 1
+    assert t.ts_ks == -1 and t.stream_max_b == 0 and t.tma_l2promo == 3 and t.reduce_early == 1 and t.ts_m64 == 1
     assert N.tuning_default(from_env=True).as_dict() == t.as_dict()
     monkeypatch.setenv("VQA_TS_QS", "0")
     monkeypatch.setenv("VQA_TS_EXTRA", "12")

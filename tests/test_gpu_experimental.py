@@ -183,7 +183,7 @@ def test_set_tuning_changes_the_plan_of_a_live_index_and_rejects_nonsense():
     q = torch.from_numpy(unit_rows(rng, 1, 768)).to(DEV)
     shard = ops.FlatShard(rows)
     assert shard.plan(1, 10, "fast")[0] == 3                   # B = 1 on a small shard: tcgen05 kernel
-    shard.set_tuning(stream_min_mb=0)
+    shard.set_tuning(stream_max_b=2, stream_min_mb=0)
     assert shard.plan(1, 10, "fast")[0] == 2                   # streaming kernel (the plan cache was dropped)
     want = [t.clone() for t in shard.search(q, 10, "fast")]
     shard.set_tuning(stream_max_b=0)

@@ -41,10 +41,10 @@ def test_default_routing(monkeypatch):
     for v in KNOB_ENV:
         monkeypatch.delenv(v, raising=False)
     n = 10_000_000
-    for b in (1, 2):                                       # north_star's small-batch regime: HBM-streaming warp dot products
-        assert plan(n, 768, BF16, b, 10)["family"] == STREAM
-        assert plan(1_250_000, 768, BF16, b, 10)["family"] == TENSOR   # ... whose fixed cost loses on an 8-GPU shard
-    for b in (3, 8, 32):                                   # headline: smem-resident tcgen05 kernel, hi/lo columns
+    for b in (1, 2):                                       # the CUDA-core streaming kernel is a knob away (it lost to the
+        assert plan(n, 768, BF16, b, 10, stream_max_b=2)["family"] == STREAM         # seeded tcgen05 kernel at every size)
+        assert plan(1_250_000, 768, BF16, b, 10, stream_max_b=2)["family"] == TENSOR  # ... and never on small shards
+    for b in (1, 2, 3, 8, 32):                             # headline: smem-resident tcgen05 kernel, hi/lo columns
         p = plan(n, 768, BF16, b, 10)
         assert p["family"] == TENSOR and p["split"] == 1 and p["smem"] <= SMEM
     for b in (129, 256, 1024):                             # > 128 queries: CTA pairs (cta_group::2), 256 queries per launch
@@ -64,8 +64,9 @@ def test_default_routing(monkeypatch):
     p = plan(n, 768, BF16, 8, 100)                         # k > 32: TS with hi/lo rows and heaps, no re-scoring
     assert (p["family"], p["split"], p["qs"], p["kscan"], p["rescore"]) == (TS, 1, 1, 100, 0)
     assert plan(n, 768, BF16, 1, 100)["family"] == TS      # big k is never a streaming-kernel case
-    p = plan(12_500_000, 1024, F16, 64, 100)               # BASELINE configs[3]: one pass, 10 blocks in TMEM + 6 in smem
-    assert (p["family"], p["qs"], p["ks"], p["split"], p["rescore"]) == (TS, 1, 6, 0, 1)
+    p = plan(12_500_000, 1024, F16, 64, 100)               # BASELINE configs[3]: one pass, 10 blocks in TMEM + 6 in smem,
+    assert (p["family"], p["qs"], p["ks"], p["split"], p["rescore"]) == (TS, 1, 6, 0, 1)     # M = 64 instructions
+    assert p["pass_nq"] == 64 and p["smem"] <= SMEM
     assert plan(n, 1024, BF16, 64, 10, TS) is not None
     assert plan(n, 768, F32, 4, 10)["family"] == STREAM and plan(n, 776, BF16, 4, 10)["family"] == STREAM
     assert plan(n, 768, BF16, 4, 10, VERIFY)["family"] == STREAM

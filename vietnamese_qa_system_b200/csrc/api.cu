@@ -169,13 +169,13 @@ const KnobSpec kKnobs[] = {
     {"VQA_PDL_CHAIN", &vqa_tuning_t::pdl_chain, 0, 1, 0},
     {"VQA_TMA_L2PROMO", &vqa_tuning_t::tma_l2promo, 0, 3, 3},
     {"VQA_TMA_HINT", &vqa_tuning_t::tma_hint, 0, 2, 1},
-    {"VQA_STREAM_MAX_B", &vqa_tuning_t::stream_max_b, 0, 8, 2},
+    {"VQA_STREAM_MAX_B", &vqa_tuning_t::stream_max_b, 0, 8, 0},
     {"VQA_STREAM_MIN_MB", &vqa_tuning_t::stream_min_mb, 0, 1 << 30, 8000},
     {"VQA_PAIR", &vqa_tuning_t::pair, 0, 1, 1},
     {"VQA_DYN_TILES", &vqa_tuning_t::dyn_tiles, 0, 1, 1},
     {"VQA_SEED", &vqa_tuning_t::seed, 0, 1, 1},
     {"VQA_WIDE", &vqa_tuning_t::wide, 0, 1, 1},
-    {"VQA_TS_M64", &vqa_tuning_t::ts_m64, 0, 1, 0},
+    {"VQA_TS_M64", &vqa_tuning_t::ts_m64, 0, 1, 1},
 };
 
 void tuning_defaults(vqa_tuning_t *t) {
@@ -417,16 +417,14 @@ int make_plan_uncached(const vqa_index *h, int nq, int k, int mode, Plan *pl) {
         return VQA_OK;
     }
     if (mode == VQA_MODE_FAST) {
-        // Measured on B200 (profiles/):
-        //  * B <= 2 (stream_max_b): the CUDA-core streaming kernel (128-bit no-allocate loads, warp dot products)
-        //    has the highest steady-state rate -- 2.20 vs 2.27 ms at 10 M x 768 (shards of >= stream_min_mb only);
+        // Measured on B200 (profiles/r2_call*.log):
         //  * up to 32 queries, k <= 32: the TMA-fed tcgen05 kernel with the queries resident in shared memory (hi/lo
-        //    columns) -- CUDA cores cannot keep up with HBM beyond ~4 queries per streamed element;
+        //    columns) -- CUDA cores cannot keep up with HBM beyond ~4 queries per streamed element.  Since the warm-up
+        //    seed and the dynamic tile schedule it also wins at B = 1, 2 (10 M x 768: 2.07 ms against 2.19 ms for the
+        //    CUDA-core streaming kernel; 0.274 against 0.363 ms on the 8-GPU shard), so stream_max_b defaults to 0:
+        //    the streaming kernel serves verify mode, fp32 rows and dims that are not multiples of 64;
         //  * beyond that, and k > 32: the TMEM-resident-query kernel serves 128 queries per CTA from one HBM pass
         //    (screen with storage-precision queries, exact re-scoring in the reduce; hi/lo rows + heaps for big k).
-        //  fp32 rows (verify mode's native storage) and dims that are not multiples of 64: streaming kernel.
-        // (the streaming kernel's steady state is 7.33 TB/s against 6.8 for the N = 16 MMA tiles, but its fixed cost
-        // is ~80 us higher: it wins from ~5 M rows of 768 bf16 upwards -- stream_min_mb)
         const long long shard_mb = (long long)h->n_rows * h->dim * elem_size(h->dtype) / 1000000;
         const bool sixteen = h->dtype == VQA_BF16 || h->dtype == VQA_F16;
         if (nq <= h->tune.stream_max_b && k <= 32 && (!sixteen || shard_mb >= h->tune.stream_min_mb)) {
