@@ -200,6 +200,19 @@ VQA_API int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q
                        void *stream);
 
 /*
+ * The same search on TWO streams: the scan on `scan_stream`, the candidate reduce (the kernel that writes
+ * out_scores_dev / out_ids_dev) on `reduce_stream` behind an event the library records after the scan.  The scan
+ * stream is then free for the NEXT search's scan the moment this scan ends -- in a loop over independent batches
+ * the reduce (and whatever the caller orders behind it on `reduce_stream`: the cross-GPU exchange, the merge, the
+ * D2H copy) overlaps the next scan.  Consecutive searches in flight must use distinct workspaces and outputs.
+ * Replaces: nothing in the reference; it is how ShardedFlat.search_pipelined keeps the scans back to back.
+ */
+VQA_API int vqa_search_2s(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
+                          int32_t n_queries, int32_t k, int32_t mode, float *out_scores_dev,
+                          int64_t *out_ids_dev, void *workspace_dev, size_t workspace_bytes,
+                          void *scan_stream, void *reduce_stream);
+
+/*
  * Same search with HOST buffers: H2D copy of the queries, search, D2H copy of
  * the results, stream-synchronised before returning.  `staging_dev` must hold
  * vqa_search_host_staging_bytes() bytes (it contains the search workspace: zero it once after allocation).  This is the call the reference-facing

@@ -239,3 +239,42 @@ def test_cuda_graph_capture_of_search():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out_i, i_ref) and torch.equal(out_s, s_ref)
+
+
+@pytest.mark.parametrize("b,k,mode", [(32, 10, "fast"), (1, 10, "fast"), (100, 10, "fast"), (300, 10, "fast"), (9, 100, "fast"),
+                                      (5, 10, "verify")])
+def test_two_stream_search_keeps_scans_back_to_back(b, k, mode):
+    """vqa_search_2s: scan on the current stream, candidate reduce on a second stream behind the library's hand-over
+    event.  Six searches in flight over two workspace slots (the serving loop of ShardedFlat.search_pipelined): every
+    result equals the one-stream answer for its queries."""
+    rng = np.random.default_rng(b + k)
+    docs = unit_rows(rng, 60000, 768)
+    shard = ops.FlatShard(torch.from_numpy(docs).to(DEV).to(torch.bfloat16))
+    qs = [torch.from_numpy(unit_rows(rng, b, 768)).to(DEV) for _ in range(3)]
+    want = [tuple(t.clone() for t in shard.search(q, k, mode)) for q in qs]
+    side = torch.cuda.Stream(device=DEV)
+    main = torch.cuda.current_stream()
+    slots = [(torch.zeros(shard.workspace_bytes(b, k, mode), dtype=torch.uint8, device=DEV),
+              torch.empty((b, k), dtype=torch.float32, device=DEV), torch.empty((b, k), dtype=torch.int64, device=DEV))
+             for _ in range(2)]
+    done = [None, None]
+    got = []
+    for step in range(6):
+        sl = step % 2
+        ws, out_s, out_i = slots[sl]
+        if done[sl] is not None:
+            done[sl][0].synchronize()
+            got.append((done[sl][1], out_s.clone(), out_i.clone()))
+            main.wait_event(done[sl][0])
+        shard.search(qs[step % 3], k, mode, out_s, out_i, workspace=ws, reduce_stream=side)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        done[sl] = (ev, step % 3)
+    for sl in range(2):
+        done[sl][0].synchronize()
+        got.append((done[sl][1], slots[sl][1].clone(), slots[sl][2].clone()))
+    assert len(got) == 6
+    for j, s, i in got:
+        assert torch.equal(i, want[j][1]) and torch.equal(s, want[j][0])
+    with pytest.raises(ValueError):
+        shard.search(qs[0], k, mode, reduce_stream=main)         # the two streams must differ

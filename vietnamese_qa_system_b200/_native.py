@@ -25,7 +25,7 @@ MODES = {"verify": MODE_VERIFY, "fp32": MODE_VERIFY, "fast": MODE_FAST, "stream"
 
 EXPORTS = [
     "vqa_version", "vqa_last_error", "vqa_device_count", "vqa_index_create", "vqa_index_bind",
-    "vqa_index_destroy", "vqa_debug_timeline", "vqa_workspace_bytes", "vqa_search", "vqa_search_host_staging_bytes", "vqa_search_host_async",
+    "vqa_index_destroy", "vqa_debug_timeline", "vqa_workspace_bytes", "vqa_search", "vqa_search_2s", "vqa_search_host_staging_bytes", "vqa_search_host_async",
     "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_exchange_push", "vqa_merge_topk_wait",
     "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
     "vqa_search_plan", "vqa_plan_describe", "vqa_plan_describe_tuned",
@@ -97,6 +97,8 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_workspace_bytes.argtypes = [vp, i32, i32, i32, c.POINTER(sz)]
     L.vqa_search.restype = c.c_int
     L.vqa_search.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp, vp, sz, vp]
+    L.vqa_search_2s.restype = c.c_int
+    L.vqa_search_2s.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp, vp, sz, vp, vp]
     L.vqa_search_host_staging_bytes.restype = c.c_int
     L.vqa_search_host_staging_bytes.argtypes = [vp, i32, i32, i32, c.POINTER(sz)]
     L.vqa_search_host.restype = c.c_int

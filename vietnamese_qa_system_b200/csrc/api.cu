@@ -111,6 +111,12 @@ struct vqa_index {
     mutable unsigned plan_next = 0;
     unsigned long long *timeline = nullptr;  // vqa_debug_timeline
     size_t timeline_bytes = 0;
+    // vqa_search_2s: scan stream -> reduce stream hand-over.  A stream wait captures the event's record at enqueue
+    // time, so ONE event serves every call (guarded by `mu`); created on first use, destroyed with the handle.
+    mutable cudaEvent_t handoff = nullptr;
+    ~vqa_index() {
+        if (handoff) cudaEventDestroy(handoff);
+    }
 };
 
 // sparse (BM25) term index: CSR postings borrowed from the caller
@@ -739,9 +745,29 @@ int vqa_workspace_bytes(const vqa_index_t *h, int32_t n_queries, int32_t k, int3
     return VQA_OK;
 }
 
+static int search_impl(const vqa_index_t *h, const float *queries_dev, int64_t q_stride, int32_t n_queries, int32_t k,
+                       int32_t mode, float *out_scores_dev, int64_t *out_ids_dev, void *workspace_dev,
+                       size_t workspace_bytes, void *stream, void *reduce_stream);
+
 int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride, int32_t n_queries, int32_t k,
                int32_t mode, float *out_scores_dev, int64_t *out_ids_dev, void *workspace_dev,
                size_t workspace_bytes, void *stream) {
+    return search_impl(h, queries_dev, q_stride, n_queries, k, mode, out_scores_dev, out_ids_dev, workspace_dev,
+                       workspace_bytes, stream, nullptr);
+}
+
+int vqa_search_2s(const vqa_index_t *h, const float *queries_dev, int64_t q_stride, int32_t n_queries, int32_t k,
+                  int32_t mode, float *out_scores_dev, int64_t *out_ids_dev, void *workspace_dev,
+                  size_t workspace_bytes, void *scan_stream, void *reduce_stream) {
+    if (!reduce_stream || reduce_stream == scan_stream)
+        return fail(VQA_E_INVALID, "vqa_search_2s needs a reduce stream different from the scan stream");
+    return search_impl(h, queries_dev, q_stride, n_queries, k, mode, out_scores_dev, out_ids_dev, workspace_dev,
+                       workspace_bytes, scan_stream, reduce_stream);
+}
+
+static int search_impl(const vqa_index_t *h, const float *queries_dev, int64_t q_stride, int32_t n_queries, int32_t k,
+                       int32_t mode, float *out_scores_dev, int64_t *out_ids_dev, void *workspace_dev,
+                       size_t workspace_bytes, void *stream, void *reduce_stream) {
     int rc = check_search_args(h, n_queries, k);
     if (rc) return rc;
     if (!queries_dev || !out_scores_dev || !out_ids_dev || !workspace_dev)
@@ -760,6 +786,19 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     DeviceGuard guard(h->device);
     if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t rst = reinterpret_cast<cudaStream_t>(reduce_stream);
+    // Two-stream form: every candidate reduce is enqueued on `rst` behind an event recorded after its scan, so the
+    // scan stream is free for the NEXT search's scan the moment this one ends (the caller gives consecutive searches
+    // distinct workspaces and outputs).  Returns the stream the reduce must be launched on.
+    cudaError_t handoff_err = cudaSuccess;
+    auto reduce_on = [&]() -> cudaStream_t {
+        if (!rst) return st;
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (!h->handoff) handoff_err = cudaEventCreateWithFlags(&h->handoff, cudaEventDisableTiming);
+        if (handoff_err == cudaSuccess) handoff_err = cudaEventRecord(h->handoff, st);
+        if (handoff_err == cudaSuccess) handoff_err = cudaStreamWaitEvent(rst, h->handoff, 0);
+        return rst;
+    };
 
     uintptr_t ws = (reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~(uintptr_t)255;
     float *cand_s = reinterpret_cast<float *>(ws);
@@ -771,6 +810,7 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
     unsigned long long *slot_g = tile_ctr + 64;  // [n_queries][32]
     const long long cand_stride = (long long)n_queries * k;
     vqa::ReduceOpts ropts;
+    ropts.no_pdl = rst ? 1 : 0;   // (programmatic launch relaxes the order against the previous KERNEL of a stream only)
     ropts.select = h->tune.reduce_select;
     ropts.early = h->tune.reduce_early;
     ropts.trigger_early = h->tune.pdl_chain;
@@ -838,9 +878,10 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, pl.ts_split ? kscan : (kscan > 32 ? vqa::kMaxK : 32), h->first_id,
                                        out_scores_dev + (long long)l0 * k,
-                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, reduce_on(),
                                        ropts, pl.ts_split ? nullptr : &rs);
-            if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess || handoff_err != cudaSuccess)
+                return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e != cudaSuccess ? e : handoff_err));
         }
         return VQA_OK;
     };
@@ -893,9 +934,10 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             rs.k_final = k;
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, 32, h->first_id, out_scores_dev + (long long)l0 * k,
-                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, single ? 1 : 2, 128, st,
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, single ? 1 : 2, 128, reduce_on(),
                                        ropts, &rs);
-            if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess || handoff_err != cudaSuccess)
+                return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e != cudaSuccess ? e : handoff_err));
         }
         return VQA_OK;
     }
@@ -975,9 +1017,10 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
             rs.k_final = k;
             e = vqa::launch_reduce_u32(cand_s + (long long)l0 * kscan, cand_i + (long long)l0 * kscan, cstride, kscan, a.grid,
                                        kscan, pl.ss_split ? kscan : 32, h->first_id, out_scores_dev + (long long)l0 * k,
-                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, st,
+                                       (long long *)out_ids_dev + (long long)l0 * k, nq, tau_g + l0, g, pl.pass_nq, reduce_on(),
                                        ropts, pl.ss_split ? nullptr : &rs, a.slot_g);
-            if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess || handoff_err != cudaSuccess)
+                return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e != cudaSuccess ? e : handoff_err));
         }
         return VQA_OK;
     }
@@ -1018,8 +1061,9 @@ int vqa_search(const vqa_index_t *h, const float *queries_dev, int64_t q_stride,
         }
     }
     cudaError_t e = vqa::launch_reduce_u32(cand_s, cand_i, cand_stride, k, n_lists, k, k, h->first_id, out_scores_dev,
-                                           (long long *)out_ids_dev, n_queries, nullptr, 1, 1, st, ropts);
-    if (e != cudaSuccess) return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+                                           (long long *)out_ids_dev, n_queries, nullptr, 1, 1, reduce_on(), ropts);
+    if (e != cudaSuccess || handoff_err != cudaSuccess)
+                return fail(VQA_E_CUDA, "reduce launch failed: %s", cudaGetErrorString(e != cudaSuccess ? e : handoff_err));
     return VQA_OK;
 }
 

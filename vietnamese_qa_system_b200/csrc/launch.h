@@ -134,6 +134,7 @@ struct ReduceOpts {
     int select = 0;         // radix-select kernel for k_out > 32 and for re-scoring reduces
     int early = 0;          // early exit over sorted internal lists (k_out <= 32 warp kernel)
     int trigger_early = 0;  // release PDL dependents at once (the next scan of the same search does not read our output)
+    int no_pdl = 0;         // plain launch (the reduce runs on another stream than its scan, behind an event)
 };
 
 cudaError_t launch_reduce_u32(const float *cand_s, const uint32_t *cand_i, long long list_stride,

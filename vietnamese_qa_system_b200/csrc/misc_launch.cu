@@ -64,7 +64,7 @@ static cudaError_t launch_reduce_t(const float *cand_s, const IdT *cand_i, long 
     cudaLaunchConfig_t cfg = {};
     cfg.stream = st;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = opts.no_pdl ? 0 : 1;
     if constexpr (sizeof(IdT) == 4) {
         // radix-select reduce (scan.cuh; default on since the round-2 timings, vqa_tuning_t::reduce_select):
         // needs every candidate of a query in shared memory at once and no peer flags to wait for.

@@ -117,10 +117,12 @@ class FlatShard:
 
     # -- search ---------------------------------------------------------------
     def search(self, queries: torch.Tensor, k: int, mode="fast", out_scores: Optional[torch.Tensor] = None,
-               out_ids: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+               out_ids: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+               reduce_stream: Optional[torch.cuda.Stream] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """queries: float32 [B, dim] CUDA, L2-normalised.  Returns (scores f32 [B,k], ids i64 [B,k]).
-        ``workspace``: caller-owned uint8 scratch of ``workspace_bytes(B, k)`` (default: per-stream cache)."""
+        ``workspace``: caller-owned uint8 scratch of ``workspace_bytes(B, k)`` (default: per-stream cache).
+        ``reduce_stream``: ``vqa_search_2s`` -- the scan runs on the current stream, the candidate reduce on
+        ``reduce_stream`` (the outputs are valid in THAT stream's order); pass a workspace of your own."""
         _need_cuda(queries, "queries")
         if queries.dtype != torch.float32:
             raise ValueError(f"queries must be float32; got {queries.dtype}")
@@ -138,6 +140,12 @@ class FlatShard:
             out_ids = torch.empty((b, k), dtype=torch.int64, device=self.device)
         ws = workspace if workspace is not None else self.workspace(b, k, m)
         q_stride = queries.stride(0) if b > 1 else self.dim
+        if reduce_stream is not None:
+            N.check(N.lib().vqa_search_2s(self._h, ctypes.c_void_p(queries.data_ptr()), q_stride, b, k, m,
+                                          ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(out_ids.data_ptr()),
+                                          ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                          ctypes.c_void_p(_stream(self.device)), ctypes.c_void_p(reduce_stream.cuda_stream)))
+            return out_scores, out_ids
         N.check(N.lib().vqa_search(self._h, ctypes.c_void_p(queries.data_ptr()), q_stride, b, k, m,
                                    ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(out_ids.data_ptr()),
                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(_stream(self.device))))

@@ -175,9 +175,17 @@ class ShardedFlat:
                       torch.empty((b, k), dtype=torch.float32, device=dev),
                       torch.empty((b, k), dtype=torch.int64, device=dev))
                 self._bufs[("ws1", b, k, slot)] = ws
-            s, i = self.shard.search(queries, k, self.mode, ws[1], ws[2], workspace=ws[0])
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            prev = self._last.get((b, k, slot))
+            if prev is not None:
+                main.wait_event(prev)      # the slot's previous reduce has read its candidate lists
+            # scan on the current stream, candidate reduce on the side stream: the next call's scan follows this
+            # one back to back (vqa_search_2s)
+            s, i = self.shard.search(queries, k, self.mode, ws[1], ws[2], workspace=ws[0], reduce_stream=self._side)
             ev = torch.cuda.Event()
-            ev.record(main)
+            ev.record(self._side)
+            self._last[(b, k, slot)] = ev
             return s, i, ev
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
@@ -195,11 +203,10 @@ class ShardedFlat:
         prev = self._last.get((b, k, slot))
         if prev is not None:
             main.wait_event(prev)          # the slot's previous exchange has read `local` and written the outputs
-        self.shard.search(queries, k, self.mode, buf[2], buf[3], workspace=buf[8])
-        scanned = torch.cuda.Event()
-        scanned.record(main)
+        # scan on the current stream; candidate reduce, push and merge on the side stream (vqa_search_2s hands over
+        # with an event recorded right after the scan), so consecutive scans run back to back
+        self.shard.search(queries, k, self.mode, buf[2], buf[3], workspace=buf[8], reduce_stream=self._side)
         with torch.cuda.stream(self._side):
-            self._side.wait_event(scanned)
             out_s, out_i = self._exchange(buf, b, k)
             done = torch.cuda.Event()
             done.record(self._side)
