@@ -163,7 +163,8 @@ typedef struct vqa_tuning {
     int32_t seed;          /* smem-resident kernel, register lists: warm-up bound from the first tiles' maxima, 0|1 (1) */
     int32_t wide;          /* FAST: 33..128 queries (dim <= 768) on single-CTA 128-document tiles (pair.cuh), 0|1 (1) */
     int32_t ts_m64;        /* TS kernel, <= 64 queries, screen mode: M = 64 instructions, 0|1 (1)                   */
-    int32_t reserved[1];
+    int32_t smem_reserve_kb; /* shared memory per SM the TS / 128-document-tile scans leave free so that the re-scoring
+                                reduce of the previous batch can run NEXT to them in a pipelined loop, 0..64 (0)    */
 } vqa_tuning_t;
 
 /* Library defaults (no environment). */

@@ -42,11 +42,11 @@ class Tuning(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "size", "ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "ts_qs",
         "ts_ks", "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-        "stream_max_b", "stream_min_mb", "pair", "dyn_tiles", "seed", "wide", "ts_m64")] + [("reserved", ctypes.c_int32 * 1)]
+        "stream_max_b", "stream_min_mb", "pair", "dyn_tiles", "seed", "wide", "ts_m64", "smem_reserve_kb")]
 
     KNOBS = ("ts_extra", "ss_screen", "mma_kps", "mma_stages", "mma_groups", "mma_multicast", "ts_qs", "ts_ks",
              "ts_split", "ts_groups", "reduce_select", "reduce_early", "pdl_chain", "tma_l2promo", "tma_hint",
-             "stream_max_b", "stream_min_mb", "pair", "dyn_tiles", "seed", "wide", "ts_m64")
+             "stream_max_b", "stream_min_mb", "pair", "dyn_tiles", "seed", "wide", "ts_m64", "smem_reserve_kb")
 
     def update(self, **knobs) -> "Tuning":
         for key, val in knobs.items():

@@ -182,6 +182,7 @@ const KnobSpec kKnobs[] = {
     {"VQA_SEED", &vqa_tuning_t::seed, 0, 1, 1},
     {"VQA_WIDE", &vqa_tuning_t::wide, 0, 1, 1},
     {"VQA_TS_M64", &vqa_tuning_t::ts_m64, 0, 1, 1},
+    {"VQA_SMEM_RESERVE_KB", &vqa_tuning_t::smem_reserve_kb, 0, 64, 0},
 };
 
 void tuning_defaults(vqa_tuning_t *t) {
@@ -222,6 +223,13 @@ bool tensor_eligible(const vqa_index *h) {
 }
 
 int spare_ranks(const vqa_index *h) { return h->tune.ts_extra; }
+
+// shared memory a scan CTA may take: the device limit minus what the knob keeps free for a kernel that should run
+// NEXT to the scan on the same SM (the re-scoring reduce of the previous batch in a pipelined loop needs ~21 KB)
+size_t smem_budget(const vqa_index *h, bool big_reduce) {
+    const size_t keep = big_reduce ? (size_t)h->tune.smem_reserve_kb * 1024 : 0;
+    return (size_t)h->max_smem > keep ? (size_t)h->max_smem - keep : 0;
+}
 
 // pick the widest MMA N (<= what the batch needs) whose smem ring still has >= 4 boxes.
 // Screen mode (k + spare <= 32): one storage-precision column per query, up to 32 queries per CTA,
@@ -303,8 +311,9 @@ bool plan_ts(const vqa_index *h, int nq, int k, Plan *pl) {
     const int kscan = split ? k : k + spare;
     const int m64 = (qs && !split && nq <= 64 && tu.ts_m64) ? 1 : 0;
     const size_t fixed = vqa::ts_smem_bytes(kscan, 0, split, ks, nq, qs, m64);
-    if (fixed >= (size_t)h->max_smem) return false;
-    int boxes = (int)(((size_t)h->max_smem - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
+    const size_t budget = smem_budget(h, !split && kscan <= 32);   // (screen mode with register lists: select-kernel reduce)
+    if (fixed >= budget) return false;
+    int boxes = (int)((budget - fixed) / (vqa::kStageBytes / 2));  // 8 KB boxes
     // 8 KB boxes: four column blocks per ring stage halve the per-byte handshakes (measured 2.74 -> 2.57 ms
     // at B = 128, 5.17 -> 4.38 ms at B = 256 on 10M x 768)
     int kps = tu.mma_kps > 0 ? tu.mma_kps : (kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
@@ -342,9 +351,10 @@ bool pair_geometry(const vqa_index *h, int ks, bool single, int *stages, int *kp
     const vqa_tuning_t &tu = h->tune;
     const int kb = h->dim / vqa::kBlockK;
     const size_t fixed = vqa::pair_smem_bytes(0, ks);
-    if (fixed >= (size_t)h->max_smem) return false;
+    const size_t budget = smem_budget(h, true);
+    if (fixed >= budget) return false;
     const size_t unit = single ? vqa::kStageBytes : vqa::kStageBytes / 2;
-    const int slots = (int)(((size_t)h->max_smem - fixed) / unit);   // 64-column blocks of a tile that fit the ring
+    const int slots = (int)((budget - fixed) / unit);   // 64-column blocks of a tile that fit the ring
     // measured (profiles/r2_call5.log, pairs at dim 768): 4 blocks per stage 3.41 ms, 3 or 6: 3.94, 2: 5.17, 1: 9.57
     int kps = tu.mma_kps > 0 ? tu.mma_kps : (kb % 4 == 0 ? 4 : (kb % 3 == 0 ? 3 : (kb % 2 == 0 ? 2 : 1)));
     if (kps < 1 || kb % kps != 0) kps = 1;
