@@ -53,7 +53,7 @@ extern "C" {
 #define VQA_API __attribute__((visibility("default")))
 #endif
 
-#define VQA_VERSION 120 /* 111: + vqa_plan_describe, vqa_search_host_async; 120: + vqa_tuning_t (no getenv on the search path) */
+#define VQA_VERSION 121 /* 111: + vqa_plan_describe, vqa_search_host_async; 120: + vqa_tuning_t (no getenv on the search path); 121: + vqa_merge_segments (k <= 1024) */
 
 typedef enum vqa_status {
     VQA_OK = 0,
@@ -275,6 +275,26 @@ VQA_API int vqa_merge_topk_wait(const float *cand_scores_dev, const int64_t *can
                                 int32_t n_queries, int32_t k_in, int32_t k_out, float *out_scores_dev,
                                 int64_t *out_ids_dev, const uint64_t *flags_dev, uint64_t epoch,
                                 int32_t device, void *stream);
+
+/*
+ * Top k for k beyond one search call's limit (128 < k <= 1024; the hybrid search of txtai fetches 10 x limit
+ * dense candidates, heavy_ranker.py:98,100 with limit > 12).  The caller cuts the shard into row segments in
+ * ascending row order (one vqa_index handle per segment over a slice of the same rows), runs vqa_search on each
+ * for its own top k_seg, and this call sorts the n_segments x k_seg survivors of every query and writes the best
+ * k_out: score descending (-0 == +0), ties -> the lower position.
+ *   seg_scores_dev float32 / seg_ids_dev int64 [n_segments, n_queries, k_seg]   each list as vqa_search wrote it
+ *                 (unused slots -inf / -1); n_segments * k_seg <= 8192
+ *   saturated_dev int32 [n_segments]   out: non-zero when the segment's LAST kept candidate is inside some query's
+ *                 answer, i.e. the segment may hold more of that query's top k_out than k_seg.  The answer is exact
+ *                 when no segment with more than k_seg rows is saturated; otherwise the caller halves the saturated
+ *                 segments, searches the halves and merges again (vietnamese_qa_system_b200/ops.py does).
+ * vqa_merge_segments_limits reports the largest k_out and n_segments * k_seg.
+ * Replaces: nothing in the reference (faiss answers any k in one call); it is how this engine composes k > 128.
+ */
+VQA_API int vqa_merge_segments_limits(int32_t *max_k_out, int32_t *max_candidates);
+VQA_API int vqa_merge_segments(const float *seg_scores_dev, const int64_t *seg_ids_dev, int32_t n_segments,
+                               int32_t n_queries, int32_t k_seg, int32_t k_out, float *out_scores_dev,
+                               int64_t *out_ids_dev, int32_t *saturated_dev, int32_t device, void *stream);
 
 /*
  * Fused masked mean-pool (+ optional L2 normalise) over encoder hidden states:

@@ -364,6 +364,12 @@ inline T atomicMax(T *p, T v) {
     return o;
 }
 template <typename T>
+inline T atomicOr(T *p, T v) {
+    T o = *p;
+    *p = o | v;
+    return o;
+}
+template <typename T>
 inline T atomicCAS(T *p, T cmp, T v) {
     T o = *p;
     if (o == cmp) *p = v;

@@ -7,6 +7,7 @@
 #define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
 #define cudaFuncSetAttribute(...) cudaSuccess
 #define cudaGetLastError() cudaSuccess
+#define cudaMemsetAsync(p, v, n, st) (std::memset((p), (v), (n)), cudaSuccess)
 
 // cudaLaunchKernelEx (PDL launch of the reduce kernels, cluster launch of the tensor kernels): same grid / block,
 // the cluster dimension attribute is honoured, the others are ignored
@@ -152,6 +153,16 @@ int emu_merge_topk(const float *cand_s, const long long *cand_i, int n_lists, in
         const long long stride = (long long)n_queries * k_in;
         if (vqa::launch_reduce_i64(cand_s, cand_i, stride, stride, k_in, n_lists, k_in, k_out, 0, out_s, out_i,
                                    n_queries, nullptr) != cudaSuccess)
+            throw std::runtime_error("launch failed");
+    });
+}
+
+// vqa_merge_segments: [n_seg][n_queries][k_seg] sorted lists -> top k_out + the per-segment saturation flags
+int emu_merge_segments(const float *seg_s, const long long *seg_i, int n_seg, int n_queries, int k_seg, int k_out,
+                       float *out_s, long long *out_i, int *saturated) {
+    return guarded([&] {
+        if (vqa::launch_merge_segments(seg_s, seg_i, n_seg, n_queries, k_seg, k_out, out_s, out_i, saturated,
+                                       nullptr) != cudaSuccess)
             throw std::runtime_error("launch failed");
     });
 }

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported():
 
 def test_version_and_last_error():
     L = N.lib()
-    assert L.vqa_version() == 120 == N.ABI_VERSION
+    assert L.vqa_version() == 121 == N.ABI_VERSION
     assert isinstance(N.last_error(), str)
 
 

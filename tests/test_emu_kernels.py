@@ -564,3 +564,46 @@ def test_emulated_register_list_epilogue_seed_and_dynamic_tiles(emu2, monkeypatc
     assert out_i[0, :min(k, 3)].tolist() == [103, 100 + n // 2, 100 + n - 1][:min(k, 3)]
     assert np.all(np.diff(out_s, axis=1) <= 0)
     assert events > 0                     # list updates are instrumented
+
+
+def test_emulated_segment_merge_composes_a_wide_top_k(emu):
+    """vqa_merge_segments + the host-side segment logic of ops.FlatShard (k > 128, hybrid search with limit > 12):
+    per-segment top-128 lists (here from the oracle, as vqa_search writes them) -> the kernel's sorted top-k and
+    saturation flags -> saturated segments halved and merged again, until the answer equals the oracle's top-k
+    bit for bit.  The planted cluster makes the first pass inexact, so the flags are what makes the result right."""
+    from vietnamese_qa_system_b200.ops import K_SEGMENT, split_saturated, wide_segments
+    L = emu
+    L.emu_merge_segments.argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]
+    rng = np.random.default_rng(77)
+    n, d, b, k, ks = 2600, 32, 3, 300, K_SEGMENT
+    docs, q = _unit(rng, n, d), _unit(rng, b, d)
+    near = q[0] + 0.05 * rng.standard_normal((400, d)).astype(np.float32)
+    docs[1000:1400] = near / np.linalg.norm(near, axis=1, keepdims=True)     # 400 near-copies of query 0 in a row
+    docs[1003] = docs[1001]
+    docs[2500] = docs[1001]                                                   # exact ties -> lower id first
+    want_s, want_i = oracle.search(docs, q, k)
+    bounds, passes, first = wide_segments(n, k), 0, None
+    assert len(bounds) == 10 and bounds[0] == (0, 260) and bounds[-1][1] == n
+    while True:
+        seg_s = np.full((len(bounds), b, ks), -np.inf, np.float32)
+        seg_i = np.full((len(bounds), b, ks), -1, np.int64)
+        for s_, (lo, hi) in enumerate(bounds):
+            kk = min(ks, hi - lo)
+            seg_s[s_, :, :kk], seg_i[s_, :, :kk] = oracle.search(docs[lo:hi], q, kk, first_id=lo)
+        out_s, out_i = np.empty((b, k), np.float32), np.empty((b, k), np.int64)
+        sat = np.full(len(bounds), 7, np.int32)
+        ok(L, L.emu_merge_segments(ptr(seg_s), ptr(seg_i), len(bounds), b, ks, k, ptr(out_s), ptr(out_i), ptr(sat)))
+        passes += 1
+        first = out_i.copy() if first is None else first
+        bounds, changed = split_saturated(bounds, sat.tolist())
+        if not changed:
+            break
+    assert passes >= 2 and not np.array_equal(first, want_i)
+    assert np.array_equal(out_i, want_i) and np.array_equal(out_s, want_s)
+    # fewer candidates than k: the tail is empty; a single short segment; -0.0 ties with +0.0
+    seg_s = np.array([[[0.5, -0.0, -np.inf]], [[0.75, 0.0, -1.0]]], np.float32)
+    seg_i = np.array([[[4, 9, -1]], [[20, 21, 22]]], np.int64)
+    out_s, out_i, sat = np.empty((1, 7), np.float32), np.empty((1, 7), np.int64), np.zeros(2, np.int32)
+    ok(L, L.emu_merge_segments(ptr(seg_s), ptr(seg_i), 2, 1, 3, 7, ptr(out_s), ptr(out_i), ptr(sat)))
+    assert out_i.tolist() == [[20, 4, 9, 21, 22, -1, -1]] and np.signbit(out_s[0, 2]) and not np.signbit(out_s[0, 3])
+    assert np.all(np.isneginf(out_s[0, 5:])) and sat.tolist() == [0, 1]

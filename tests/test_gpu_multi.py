@@ -87,6 +87,16 @@ for exchange in ("nccl", "p2p"):
     if not ok:
         print("FAILED top-100", exchange, rank, flush=True)
         break
+# k > 128 (hybrid search with limit > 12): per-rank segment composition + all-gather + vqa_merge_segments
+full = ops.FlatShard(rows)
+sh = ShardedFlat(rows[lo:hi].contiguous(), N, mode="verify")
+for kk in (300, 1000):
+    fs, fi = full.search(qd, kk, "verify")
+    s, i = sh.search(qd, kk)
+    ok = ok and torch.equal(i, fi) and torch.equal(s, fs) and i[0, :3].tolist() == [0, N // 2, N - 1]
+    if not ok:
+        print("FAILED wide k", kk, rank, flush=True)
+        break
 # the drop-in class on a row-sharded index (Embeddings(shards=True), heavy_ranker.py:78-83 form): same hits as one GPU,
 # dense and hybrid (the BM25 leg and the content store are replicated per rank), built directly and loaded from disk
 from vietnamese_qa_system_b200 import Embeddings

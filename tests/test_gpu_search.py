@@ -184,7 +184,9 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         shard.search(q, 0)
     with pytest.raises(ValueError):
-        shard.search(q, 129)
+        shard.search(q, 1025)                      # 129..1024 are composed from segment searches (below)
+    with pytest.raises(ValueError):
+        shard.search(q, 200, workspace=torch.zeros(1 << 20, dtype=torch.uint8, device=DEV))
     with pytest.raises(ValueError):
         shard.search(torch.zeros((2, 384), device=DEV), 5)
     with pytest.raises(ValueError):
@@ -278,3 +280,49 @@ def test_two_stream_search_keeps_scans_back_to_back(b, k, mode):
         assert torch.equal(i, want[j][1]) and torch.equal(s, want[j][0])
     with pytest.raises(ValueError):
         shard.search(qs[0], k, mode, reduce_stream=main)         # the two streams must differ
+
+
+# ---- k > 128: segment searches + vqa_merge_segments -----------------------------------------
+@pytest.mark.parametrize("storage,mode", [("fp32", "verify"), ("bf16", "verify"), ("bf16", "fast"), ("fp16", "fast")])
+@pytest.mark.parametrize("n,b,k", [(6000, 3, 129), (20000, 5, 300), (50000, 2, 1000), (900, 4, 1000), (131, 1, 130)])
+def test_wide_k_is_composed_from_segment_searches(storage, mode, n, b, k):
+    """txtai's hybrid search asks the dense leg for 10 x limit candidates (heavy_ranker.py:98,100 with limit > 12
+    -> k > 128).  One vqa_search call answers k <= 128; ops.FlatShard cuts the shard into row segments, takes each
+    segment's best 128 and merges them (vqa_merge_segments), halving segments the merge reports as saturated.  A
+    planted run of 400 near-copies of query 0 puts most of its answer into one or two segments, so the second
+    pass is exercised; exact ties keep the lower id first.  verify mode: ids and score bits equal the oracle's."""
+    d = 256
+    rng = np.random.default_rng(n + k)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    if n >= 6000:
+        near = q[0] + 0.02 * rng.standard_normal((400, d)).astype(np.float32)
+        docs[n // 2:n // 2 + 400] = near / np.linalg.norm(near, axis=1, keepdims=True)
+        docs[n // 2 + 3] = docs[n // 2 + 1]
+        docs[n - 1] = docs[n // 2 + 1]
+    rows = torch.from_numpy(docs).to(DEV).to(TORCH_DT[storage])
+    shard = ops.FlatShard(rows, first_global_id=1000)
+    s, i = shard.search(torch.from_numpy(q).to(DEV), k, mode)
+    s2, i2 = shard.search(torch.from_numpy(q).to(DEV), k, mode)          # cached segments and buffers: same answer
+    s, i, s2, i2 = s.cpu().numpy(), i.cpu().numpy(), s2.cpu().numpy(), i2.cpu().numpy()
+    assert np.array_equal(i, i2) and np.array_equal(s.view(np.int32), s2.view(np.int32))
+    stored = rows.float().cpu().numpy()
+    ws, wi = oracle.search(stored, q, k, oracle.CANONICAL, storage, 1000)
+    if mode == "verify":
+        assert np.array_equal(i, wi), np.argwhere(i != wi)[:4]
+        assert np.array_equal(s.view(np.int32), ws.view(np.int32))
+    else:
+        assert recall(i, wi) >= 0.999
+        fin = np.isfinite(ws)
+        assert np.array_equal(np.isfinite(s), fin) and np.abs(np.sort(s[fin]) - np.sort(ws[fin])).max() <= 5e-3
+    assert np.all(i[:, min(k, n):] == -1) and np.all(np.diff(s[:, :min(k, n)], axis=1) <= 0)
+
+
+def test_merge_segments_c_abi_argument_errors():
+    z = torch.zeros((65, 2, 128), device=DEV)
+    zi = torch.zeros((65, 2, 128), dtype=torch.int64, device=DEV)
+    with pytest.raises(ValueError):
+        ops.merge_segments(z, zi, 200)                # 65 * 128 candidates > 8192
+    with pytest.raises(ValueError):
+        ops.merge_segments(z[:4].contiguous(), zi[:4].contiguous(), 1025)
+    with pytest.raises(ValueError):
+        ops.merge_segments(z[:4].contiguous(), zi[:4].contiguous().int(), 100)

@@ -185,7 +185,7 @@ def test_embeddings_hybrid_matches_oracle(tmp_path):
     e = Embeddings(hybrid=True, content=True, transform=enc, dtype="fp32")      # fp32 -> verify mode: exact dense leg
     e.index([{"id": i + 1, "text": t, "source": f"s{i}"} for i, t in enumerate(texts)])
     queries = [texts[10], "phở bún chả", "mã5 hà nội", "không-có-từ-nào", texts[700] + " sông núi"]
-    for limit, w in ((1, None), (3, None), (5, 0.7), (12, 0.2)):
+    for limit, w in ((1, None), (3, None), (5, 0.7), (12, 0.2), (13, None), (20, 0.3)):   # > 12: dense k > 128
         got = e.batchsearch(queries, limit, w) if w is not None else e.batchsearch(queries, limit)
         want = oracle_hybrid(e, texts, queries, limit, 0.5 if w is None else w)
         for g, wv in zip(got, want):
@@ -200,7 +200,7 @@ def test_embeddings_hybrid_matches_oracle(tmp_path):
     assert e2.config["hybrid"] is True and e2.scoring is not None
     assert e2.batchsearch(queries, 3) == e.batchsearch(queries, 3)
     with pytest.raises(NotImplementedError):
-        e.search(texts[0], 13)                                               # 130 dense candidates > 128
+        e.search(texts[0], 103)                                              # 1030 dense candidates > 1024
     with pytest.raises(ValueError):
         e.search(np.zeros(384, np.float32), 1)                               # the sparse leg needs text
 

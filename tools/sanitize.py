@@ -30,6 +30,11 @@ for dt in (torch.float32, torch.bfloat16):
             s, i = shard.search(q[:b].to(dev), k, mode)
             torch.cuda.synchronize()
             assert int((i >= 0).sum()) == b * min(k, 3000), (mode, b, k)
+shard = ops.FlatShard(docs.to(dev).to(torch.bfloat16))
+for mode in ("verify", "fast"):                                  # k > 128: segment searches + vqa_merge_segments
+    s, i = shard.search(q[:3].to(dev), 700, mode)
+    torch.cuda.synchronize()
+    assert int((i >= 0).sum()) == 3 * 700, mode
 h = torch.randn(5, 33, 768, generator=g).to(torch.bfloat16).to(dev)
 m = (torch.arange(33)[None, :] < torch.tensor([33, 1, 0, 17, 8])[:, None]).to(torch.int64).to(dev)
 out = ops.pool_normalize(h, m)

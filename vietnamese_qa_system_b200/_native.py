@@ -27,6 +27,7 @@ EXPORTS = [
     "vqa_version", "vqa_last_error", "vqa_device_count", "vqa_index_create", "vqa_index_bind",
     "vqa_index_destroy", "vqa_debug_timeline", "vqa_workspace_bytes", "vqa_search", "vqa_search_2s", "vqa_search_host_staging_bytes", "vqa_search_host_async",
     "vqa_search_host", "vqa_merge_topk", "vqa_merge_topk_strided", "vqa_exchange_push", "vqa_merge_topk_wait",
+    "vqa_merge_segments", "vqa_merge_segments_limits",
     "vqa_pool_normalize", "vqa_normalize_rows", "vqa_agree",
     "vqa_search_plan", "vqa_plan_describe", "vqa_plan_describe_tuned",
     "vqa_tuning_default", "vqa_tuning_from_env", "vqa_index_set_tuning", "vqa_index_get_tuning",
@@ -34,7 +35,7 @@ EXPORTS = [
     "vqa_sparse_workspace_bytes", "vqa_sparse_search", "vqa_hybrid_fuse", "vqa_hybrid_fuse_rrf", "vqa_agree_f64",
 ]
 
-ABI_VERSION = 120  # VQA_VERSION this binding was written against (include/vqa.h)
+ABI_VERSION = 121  # VQA_VERSION this binding was written against (include/vqa.h)
 
 
 class Tuning(ctypes.Structure):
@@ -113,6 +114,10 @@ def _bind(L: ctypes.CDLL) -> None:
     L.vqa_exchange_push.argtypes = [vp, sz, c.POINTER(vp), c.POINTER(vp), i32, c.c_uint64, i32, vp]
     L.vqa_merge_topk_wait.restype = c.c_int
     L.vqa_merge_topk_wait.argtypes = [vp, vp, i64, i64, i32, i32, i32, i32, vp, vp, vp, c.c_uint64, i32, vp]
+    L.vqa_merge_segments.restype = c.c_int
+    L.vqa_merge_segments.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
+    L.vqa_merge_segments_limits.restype = c.c_int
+    L.vqa_merge_segments_limits.argtypes = [c.POINTER(i32), c.POINTER(i32)]
     L.vqa_pool_normalize.restype = c.c_int
     L.vqa_pool_normalize.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]
     L.vqa_normalize_rows.restype = c.c_int

@@ -1210,6 +1210,34 @@ int vqa_merge_topk(const float *cand_scores_dev, const int64_t *cand_ids_dev, in
                                   n_lists, n_queries, k_in, k_out, out_scores_dev, out_ids_dev, device, stream);
 }
 
+int vqa_merge_segments_limits(int32_t *max_k_out, int32_t *max_candidates) {
+    if (max_k_out) *max_k_out = vqa::segmerge_max_k();
+    if (max_candidates) *max_candidates = vqa::segmerge_max_cand();
+    return VQA_OK;
+}
+
+int vqa_merge_segments(const float *seg_scores_dev, const int64_t *seg_ids_dev, int32_t n_segments, int32_t n_queries,
+                       int32_t k_seg, int32_t k_out, float *out_scores_dev, int64_t *out_ids_dev,
+                       int32_t *saturated_dev, int32_t device, void *stream) {
+    if (!seg_scores_dev || !seg_ids_dev || !out_scores_dev || !out_ids_dev || !saturated_dev)
+        return fail(VQA_E_INVALID, "null device pointer argument");
+    if (n_segments < 1 || n_queries < 1 || k_seg < 1)
+        return fail(VQA_E_INVALID, "n_segments, n_queries, k_seg must be >= 1");
+    if ((int64_t)n_segments * k_seg > vqa::segmerge_max_cand())
+        return fail(VQA_E_INVALID, "n_segments * k_seg must be <= %d (got %lld)", vqa::segmerge_max_cand(),
+                    (long long)n_segments * k_seg);
+    if (k_out < 1 || k_out > vqa::segmerge_max_k())
+        return fail(VQA_E_INVALID, "k_out must be in [1, %d] (got %d)", vqa::segmerge_max_k(), k_out);
+    if (vqa_device_count() == 0) return fail(VQA_E_CUDA, "no CUDA device available (no CPU fallback)");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(VQA_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaError_t e = vqa::launch_merge_segments(seg_scores_dev, (const long long *)seg_ids_dev, n_segments, n_queries,
+                                               k_seg, k_out, out_scores_dev, (long long *)out_ids_dev, saturated_dev,
+                                               reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(VQA_E_CUDA, "segment merge launch failed: %s", cudaGetErrorString(e));
+    return VQA_OK;
+}
+
 int vqa_pool_normalize(const void *hidden_dev, int32_t h_dtype, const void *mask_dev, int32_t m_dtype,
                        int32_t batch, int32_t seq, int32_t dim, int32_t normalize, float *out_dev, int32_t device,
                        void *stream) {

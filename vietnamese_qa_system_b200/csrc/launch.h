@@ -154,6 +154,11 @@ cudaError_t launch_reduce_i64(const float *cand_s, const long long *cand_i, long
                               long long list_stride_i, long long query_stride, int n_lists, int k_in, int k_out, long long id_base,
                               float *out_s, long long *out_i, int n_queries, cudaStream_t st,
                               const WaitFlags *wf = nullptr);
+// segment merge (scan.cuh): [n_seg][n_queries][k_seg] sorted lists -> top-k_out per query, k_out <= segmerge_max_k()
+int segmerge_max_k();
+int segmerge_max_cand();
+cudaError_t launch_merge_segments(const float *seg_s, const long long *seg_i, int n_seg, int n_queries, int k_seg,
+                                  int k_out, float *out_s, long long *out_i, int *saturated, cudaStream_t st);
 cudaError_t launch_pool(const void *hidden, int h_dtype, const void *mask, int m_dtype, int batch, int seq,
                         int dim, int normalize, float *out, cudaStream_t st);
 cudaError_t launch_normalize(const float *in, long long in_stride, long long n_rows, int dim, float *out,

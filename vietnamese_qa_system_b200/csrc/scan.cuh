@@ -828,4 +828,85 @@ static __global__ void __launch_bounds__(kSelThreads) reduce_select_kernel(const
 }
 
 
+// ---- segment merge: top-k for k beyond the per-list capacity (kMaxK) -----------------------------------------
+// A search for 128 < k <= kWideK is composed on the host (ops.FlatShard, vqa_merge_segments in include/vqa.h): the
+// shard is cut into row segments, each searched for its own top-k_seg with the kernels above, and this kernel
+// sorts the n_seg x k_seg survivors of one query (one CTA each) and writes the best k_out.  The answer is exact
+// unless a segment holds more than k_seg of the true top-k_out; that can only be the case when the segment's LAST
+// kept candidate is itself inside the answer, which is what `saturated[seg]` reports -- the host halves those
+// segments and merges again.  Order: score descending (-0 == +0), ties -> the lower position; segments are in
+// ascending row order and every list is sorted that way, so the candidate slot number is the tie-break.
+constexpr int kWideK = 1024;        // largest k_out
+constexpr int kSegMaxCand = 8192;   // n_seg * k_seg, padded to a power of two: 64 KB of keys
+constexpr int kSegThreads = 1024;
+
+struct SegMergeParams {
+    const float *seg_s;        // [n_seg][n_queries][k_seg]
+    const long long *seg_i;    // same shape; -1 = empty slot
+    int n_seg, n_queries, k_seg, k_out;
+    float *out_s;              // [n_queries][k_out]
+    long long *out_i;
+    int *saturated;            // [n_seg], OR over the queries; zeroed by the launcher
+};
+
+static __global__ void __launch_bounds__(kSegThreads) merge_segments_kernel(const SegMergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
+    const int tid = threadIdx.x, q = blockIdx.x;
+    const int n_cand = p.n_seg * p.k_seg;
+    int n_pad = 2;
+    while (n_pad < n_cand) n_pad <<= 1;
+    const size_t qbase = (size_t)q * p.k_seg, sstride = (size_t)p.n_queries * p.k_seg;
+    for (int c = tid; c < n_pad; c += kSegThreads) {
+        unsigned long long key = 0ull;  // empty slots sort last
+        if (c < n_cand) {
+            const int s = c / p.k_seg, j = c - s * p.k_seg;
+            const size_t at = (size_t)s * sstride + qbase + j;
+            if (p.seg_i[at] >= 0)
+                key = ((unsigned long long)ord_f32(p.seg_s[at] + 0.f) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)c);
+        }
+        keys[c] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (n_pad >> 1); t += kSegThreads) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                const bool desc = (lo & size) == 0;
+                if ((a < b) == desc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = tid; r < p.k_out; r += kSegThreads) {
+        const unsigned long long key = r < n_pad ? keys[r] : 0ull;
+        float s = neg_inf();
+        long long id = -1LL;
+        if (key != 0ull) {
+            const int c = (int)(0xffffffffu - (uint32_t)key);
+            const int sg = c / p.k_seg, j = c - sg * p.k_seg;
+            const size_t at = (size_t)sg * sstride + qbase + j;
+            s = p.seg_s[at];
+            id = p.seg_i[at];
+        }
+        p.out_s[(size_t)q * p.k_out + r] = s;
+        p.out_i[(size_t)q * p.k_out + r] = id;
+    }
+    const unsigned long long kth = p.k_out <= n_pad ? keys[p.k_out - 1] : 0ull;
+    for (int sg = tid; sg < p.n_seg; sg += kSegThreads) {
+        const size_t at = (size_t)sg * sstride + qbase + (p.k_seg - 1);
+        if (p.seg_i[at] >= 0) {
+            const int c = sg * p.k_seg + p.k_seg - 1;
+            const unsigned long long key =
+                ((unsigned long long)ord_f32(p.seg_s[at] + 0.f) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)c);
+            if (key >= kth) atomicOr(&p.saturated[sg], 1);
+        }
+    }
+}
+
+
 }  // namespace vqa

@@ -43,6 +43,7 @@ _DB_FILE = "documents"
 _IDS_FILE = "ids.json"
 _SCORING_FILE = "scoring"
 _HYBRID_CANDIDATES = 10  # each leg fetches limit * 10 candidates (txtai Search)
+_DENSE_K_MAX = 1024      # vqa_search answers k <= 128 per call; ops.FlatShard composes up to 1024 (vqa_merge_segments)
 _PERSISTED_KEYS_SKIP = {"transform", "device", "shards", "exchange"}   # deployment choices, not index properties
 
 
@@ -269,9 +270,10 @@ class Embeddings:
             return self.scoring.search_tensors(queries, k)
         cand = limit * _HYBRID_CANDIDATES
         kd = min(cand, self.count())
-        if kd > 128:
-            raise NotImplementedError(f"hybrid search fetches {_HYBRID_CANDIDATES} x limit dense candidates; "
-                                      f"limit <= 12 is supported (got {limit})")
+        if kd > _DENSE_K_MAX:
+            raise NotImplementedError(f"hybrid search fetches {_HYBRID_CANDIDATES} x limit dense candidates and the "
+                                      f"engine answers k <= {_DENSE_K_MAX}: limit <= "
+                                      f"{_DENSE_K_MAX // _HYBRID_CANDIDATES} is supported (got {limit})")
         if weights is None:
             weights = 0.5
         if isinstance(weights, (int, float)):

@@ -8,7 +8,7 @@ to the CPU.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -36,6 +36,36 @@ def mode_id(mode) -> int:
         return N.MODES[str(mode).lower()]
     except KeyError:
         raise ValueError(f"unknown search mode {mode!r}; expected one of {sorted(N.MODES)}") from None
+
+
+K_CALL_MAX = 128   # largest k of one vqa_search call (consts.h kMaxK)
+K_SEGMENT = 128    # candidates kept per row segment by the k > 128 composition
+
+
+def wide_segments(n_rows: int, k: int, k_seg: int = K_SEGMENT, max_candidates: int = 8192) -> List[Tuple[int, int]]:
+    """Row segments ``[(lo, hi), ...]`` (ascending, non-empty) for a top-k with ``k > 128`` (vqa_merge_segments,
+    include/vqa.h): about ``k / 32`` of them, so that a segment is expected to hold a quarter of the ``k_seg``
+    candidates it can report and a second pass is rare; never more than ``max_candidates / k_seg``."""
+    if n_rows <= 0:
+        return []
+    want = max(2, -(-int(k) // 32))
+    nseg = max(1, min(want, max_candidates // k_seg, n_rows))
+    cuts = [n_rows * i // nseg for i in range(nseg + 1)]
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
+def split_saturated(bounds: Sequence[Tuple[int, int]], saturated: Sequence[int], k_seg: int = K_SEGMENT):
+    """Second-pass segment list: every saturated segment with more than ``k_seg`` rows (it may hold more of the
+    answer than it could report) is cut in half.  Returns ``(new_bounds, changed)``."""
+    out, changed = [], False
+    for (a, b), flag in zip(bounds, saturated):
+        if flag and b - a > k_seg:
+            m = (a + b) // 2
+            out += [(a, m), (m, b)]
+            changed = True
+        else:
+            out.append((a, b))
+    return out, changed
 
 
 class FlatShard:
@@ -67,6 +97,8 @@ class FlatShard:
         stride_bytes = (rows.stride(0) if self.n > 1 else self.dim) * rows.element_size()
         N.check(L.vqa_index_bind(self._h, ctypes.c_void_p(rows.data_ptr() if self.n else 0), self.n, stride_bytes))
         self._ws = {}
+        self._segs: Dict[Tuple[int, int], "FlatShard"] = {}   # row segments of the k > 128 composition
+        self._wide = {}
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -89,6 +121,7 @@ class FlatShard:
         t.update(**knobs)
         N.check(N.lib().vqa_index_set_tuning(self._h, ctypes.byref(t)))
         self._ws.clear()
+        self._segs.clear()
         return t
 
     # -- planning / workspace -------------------------------------------------
@@ -138,6 +171,10 @@ class FlatShard:
             out_scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
         if out_ids is None:
             out_ids = torch.empty((b, k), dtype=torch.int64, device=self.device)
+        if k > K_CALL_MAX:
+            if workspace is not None or reduce_stream is not None:
+                raise ValueError(f"k > {K_CALL_MAX} is composed from segment searches: no workspace= / reduce_stream=")
+            return self._search_wide(queries, int(k), m, out_scores, out_ids)
         ws = workspace if workspace is not None else self.workspace(b, k, m)
         q_stride = queries.stride(0) if b > 1 else self.dim
         if reduce_stream is not None:
@@ -150,6 +187,74 @@ class FlatShard:
                                    ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(out_ids.data_ptr()),
                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(_stream(self.device))))
         return out_scores, out_ids
+
+    # -- k > 128: segment searches + vqa_merge_segments --------------------------
+    def _segment(self, lo: int, hi: int) -> "FlatShard":
+        seg = self._segs.get((lo, hi))
+        if seg is None:
+            seg = FlatShard(self.rows[lo:hi], self.first_global_id + lo)
+            N.check(N.lib().vqa_index_set_tuning(seg._h, ctypes.byref(self.get_tuning())))
+            self._segs[(lo, hi)] = seg
+        return seg
+
+    def _search_wide(self, queries: torch.Tensor, k: int, mode: int, out_scores: torch.Tensor, out_ids: torch.Tensor):
+        """Top-k for 128 < k <= 1024 (txtai's hybrid search asks each leg for 10 x limit candidates,
+        heavy_ranker.py:98,100 with limit > 12): the shard is cut into row segments (views of the same rows, one
+        native handle each), every segment reports its own best 128 through ``vqa_search`` and
+        ``vqa_merge_segments`` sorts the survivors.  The merge also reports which segments may hold more of the
+        answer than 128; those are halved and searched again -- the flags are read on the host, so unlike
+        ``k <= 128`` this call synchronises the stream at least once.  Same order as every other search: score
+        descending, ties -> the lower id."""
+        L = N.lib()
+        kmax, cmax = ctypes.c_int32(), ctypes.c_int32()
+        N.check(L.vqa_merge_segments_limits(ctypes.byref(kmax), ctypes.byref(cmax)))
+        if k > kmax.value:
+            raise ValueError(f"k must be in [1, {kmax.value}] (got {k})")
+        b = int(queries.shape[0])
+        dev, ks, cap = self.device, K_SEGMENT, cmax.value // K_SEGMENT
+        bounds = wide_segments(self.n, k, ks, cmax.value)
+        if not bounds:
+            out_scores.fill_(float("-inf"))
+            out_ids.fill_(-1)
+            return out_scores, out_ids
+        key = (b, _stream(dev))
+        st = self._wide.get(key)
+        if st is None:   # two candidate buffers (a second pass moves the kept segments' lists into their new slots)
+            st = [(torch.empty((cap, b, ks), dtype=torch.float32, device=dev),
+                   torch.empty((cap, b, ks), dtype=torch.int64, device=dev)) for _ in range(2)]
+            st.append(torch.empty(cap, dtype=torch.int32, device=dev))
+            self._wide = {key: st}
+        sat = st[2]
+        have: Dict[Tuple[int, int], int] = {}
+        cur = 0
+        while True:
+            S, I = st[cur]
+            pS, pI = st[cur ^ 1]
+            for slot, (lo, hi) in enumerate(bounds):
+                old = have.get((lo, hi))
+                if old is not None:
+                    S[slot].copy_(pS[old])
+                    I[slot].copy_(pI[old])
+                    continue
+                seg, kk = self._segment(lo, hi), min(ks, hi - lo)
+                if kk == ks:
+                    seg.search(queries, ks, mode, out_scores=S[slot], out_ids=I[slot])
+                else:            # fewer rows than list slots: the tail stays empty (-inf / -1)
+                    S[slot].fill_(float("-inf"))
+                    I[slot].fill_(-1)
+                    ts, ti = seg.search(queries, kk, mode)
+                    S[slot, :, :kk].copy_(ts)
+                    I[slot, :, :kk].copy_(ti)
+            merge_segments(S[:len(bounds)], I[:len(bounds)], k, out_scores, out_ids, sat)
+            flags = sat[:len(bounds)].tolist()          # device -> host: synchronises the stream
+            new_bounds, changed = split_saturated(bounds, flags, ks)
+            if not changed:
+                return out_scores, out_ids
+            if len(new_bounds) > cap:
+                raise RuntimeError(f"top-{k}: more than {cap} row segments would be needed (the answer is "
+                                   f"concentrated in a few row ranges); search with k <= {K_CALL_MAX} instead")
+            have = {seg_b: i for i, seg_b in enumerate(bounds) if seg_b in set(new_bounds)}
+            bounds, cur = new_bounds, cur ^ 1
 
     def search_host(self, queries_host: torch.Tensor, k: int, mode="fast"):
         """Host-buffer search through ``vqa_search_host``: pinned fp32 [B,dim] in,
@@ -222,6 +327,33 @@ def merge_topk(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int):
                                    lists, b, k_in, k, ctypes.c_void_p(out_s.data_ptr()),
                                    ctypes.c_void_p(out_i.data_ptr()), dev.index or 0, ctypes.c_void_p(_stream(dev))))
     return out_s, out_i
+
+
+def merge_segments(seg_scores: torch.Tensor, seg_ids: torch.Tensor, k: int, out_scores: Optional[torch.Tensor] = None,
+                   out_ids: Optional[torch.Tensor] = None, saturated: Optional[torch.Tensor] = None):
+    """``vqa_merge_segments``: seg_* [segments, B, k_seg] (float32 / int64, CUDA; lists sorted, segments in ascending
+    row order) -> ``(scores [B,k], ids [B,k], saturated int32 [segments])`` for ``k <= 1024``."""
+    _need_cuda(seg_scores, "seg_scores")
+    _need_cuda(seg_ids, "seg_ids")
+    if seg_scores.dtype != torch.float32 or seg_ids.dtype != torch.int64:
+        raise ValueError("seg_scores must be float32 and seg_ids int64")
+    if seg_scores.dim() != 3 or seg_scores.shape != seg_ids.shape:
+        raise ValueError("seg_scores / seg_ids must both be [segments, B, k_seg]")
+    if not (seg_scores.is_contiguous() and seg_ids.is_contiguous()):
+        raise ValueError("seg_scores / seg_ids must be contiguous")
+    nseg, b, ks = (int(x) for x in seg_scores.shape)
+    dev = seg_scores.device
+    if out_scores is None:
+        out_scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+    if out_ids is None:
+        out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    if saturated is None:
+        saturated = torch.empty(nseg, dtype=torch.int32, device=dev)
+    N.check(N.lib().vqa_merge_segments(ctypes.c_void_p(seg_scores.data_ptr()), ctypes.c_void_p(seg_ids.data_ptr()),
+                                       nseg, b, ks, int(k), ctypes.c_void_p(out_scores.data_ptr()),
+                                       ctypes.c_void_p(out_ids.data_ptr()), ctypes.c_void_p(saturated.data_ptr()),
+                                       dev.index or 0, ctypes.c_void_p(_stream(dev))))
+    return out_scores, out_ids, saturated
 
 
 def merge_topk_packed(gathered: torch.Tensor, n_lists: int, n_queries: int, k: int, ids_offset: int,

@@ -154,6 +154,17 @@ class ShardedFlat:
         if self.world == 1:
             return self.shard.search(queries, k, self.mode)
         b = int(queries.shape[0]) if queries.dim() == 2 else 1
+        if k > self._ops.K_CALL_MAX:
+            # k > 128 (hybrid search with limit > 12): every rank composes its shard's top k from row segments
+            # (ops.FlatShard._search_wide), the lists are all-gathered and merged by the same kernel -- ranks are
+            # row ranges in ascending order, exactly the segments of vqa_merge_segments
+            s, i = self.shard.search(queries, k, self.mode)
+            gs = torch.empty((self.world, b, k), dtype=torch.float32, device=s.device)
+            gi = torch.empty((self.world, b, k), dtype=torch.int64, device=s.device)
+            dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
+            out_s, out_i, _ = self._ops.merge_segments(gs, gi, k)
+            return out_s, out_i
         buf = self._buffers(b, k)
         self.shard.search(queries, k, self.mode, buf[2], buf[3], workspace=buf[8])
         return self._exchange(buf, b, k)
