@@ -131,7 +131,6 @@ int emu_pool_normalize(const void *hidden, int h_dtype, const void *mask, int m_
             throw std::runtime_error("launch failed");
     });
 }
-
 int emu_normalize_rows(const float *in, long long n_rows, int dim, float *out, void *cast_out, int cast_kind) {
     return guarded([&] {
         if (vqa::launch_normalize(in, dim, n_rows, dim, out, dim, cast_out, cast_kind, dim, nullptr) != cudaSuccess)

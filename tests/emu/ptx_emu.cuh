@@ -191,25 +191,8 @@ inline void tma_load_2d_multicast(void *smem_dst, const void *tmap, int32_t c0, 
         if (cta_mask & (1u << c)) emu_tma_box(c, emu::smem_off(smem_dst), emu_tmap(tmap), c0, c1, emu::smem_off(bar));
 }
 
-// 1-D bulk copy: plain bytes into this CTA's shared memory, completed on its mbarrier
-inline void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(gsrc) & 15u) || (emu::smem_off(smem_dst) & 15u))
-        throw std::runtime_error("emu: cp.async.bulk needs 16-byte aligned addresses and size");
-    std::memcpy(smem_dst, gsrc, bytes);
-    emu::MBar *b = reinterpret_cast<emu::MBar *>(bar);
-    b->tx -= (int32_t)bytes;
-    emu::mbar_check(b);
-}
-
 // ---- thread-block clusters ------------------------------------------------------------
 inline uint32_t cluster_ctarank() { return (uint32_t)emu::cur_cta(); }
-inline uint32_t cluster_nctarank() { return (uint32_t)emu::S().cluster; }
-inline float ld_dsmem_f32(const float *local, uint32_t rank) {
-    if ((int)rank >= emu::S().cluster) throw std::runtime_error("emu: distributed shared memory rank out of range");
-    float v;
-    std::memcpy(&v, emu::smem_base_of((int)rank) + emu::smem_off(local), 4);
-    return v;
-}
 inline void cluster_sync_all() { emu::cluster_barrier(); }
 
 // ---- tcgen05: TMEM allocation -----------------------------------------------

@@ -174,24 +174,36 @@ def _to_storage(x, kind):
                                       ("f32", 384), ("f32", 512), ("f32", 1024), ("f16", 1024), ("bf16", 64)])
 def test_emulated_k1_pool_normalize(emu, kind, dim):
     """K1 for every token-unroll the register budget picks (2 at 768 bf16, 3 at 384 bf16, 4 at 1024 bf16, ...),
-    right- and middle-masked sequences, an all-padding row and a single-token row."""
+    right- and middle-masked sequences, a long masked run inside the valid range, an all-padding row and a
+    single-token row, integer / byte / fractional float masks; non-finite values under masked tokens must not leak
+    (masked tokens are never loaded)."""
+    run = emu.emu_pool_normalize
     rng = np.random.default_rng(dim)
     b, s = 6, 70
-    raw, vals = _to_storage(rng.standard_normal((b, s, dim)).astype(np.float32), kind)
+    x = rng.standard_normal((b, s, dim)).astype(np.float32)
     lens = [70, 1, 0, 33, 17, 64]
     mask = (np.arange(s)[None, :] < np.array(lens)[:, None]).astype(np.int64)
     mask[3, 5:9] = 0                                                          # holes inside the valid range
+    mask[0, 16:48] = 0                                                        # a long masked run
+    x[0, 20] = np.inf                                                         # ... under the mask: never read / never used
+    x[3, 6] = np.nan
+    raw, vals = _to_storage(x, kind)
+    vals = np.where(mask[:, :, None] != 0, vals, 0)
     code = {"f32": 0, "bf16": 1, "f16": 2}[kind]
     for normalize in (1, 0):
         out = np.empty((b, dim), np.float32)
-        ok(emu, emu.emu_pool_normalize(ptr(raw), code, ptr(mask), 3, b, s, dim, normalize, ptr(out)))
+        ok(emu, run(ptr(raw), code, ptr(mask), 3, b, s, dim, normalize, ptr(out)))
         want = oracle.mean_pool(vals, mask, bool(normalize))
         assert np.abs(out - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
         assert np.all(out[2] == 0)                                            # all-padding row
     m8 = mask.astype(np.uint8)
     out8 = np.empty((b, dim), np.float32)
-    ok(emu, emu.emu_pool_normalize(ptr(raw), code, ptr(m8), 5, b, s, dim, 1, ptr(out8)))
+    ok(emu, run(ptr(raw), code, ptr(m8), 5, b, s, dim, 1, ptr(out8)))
     assert np.array_equal(out8, out) or np.abs(out8 - oracle.mean_pool(vals, mask, True)).max() < 1e-5
+    mf = mask.astype(np.float32) * 0.5                                        # fractional weights (F32 masks)
+    outf = np.empty((b, dim), np.float32)
+    ok(emu, run(ptr(raw), code, ptr(mf), 0, b, s, dim, 0, ptr(outf)))
+    assert np.abs(outf - oracle.mean_pool(vals, mask, False)).max() <= 1e-5 * max(1.0, np.abs(want).max())
 
 
 # ---- the fp32 verify kernel family (scan_topk_kernel + reduce) on the emulator ---------------------------

@@ -159,46 +159,9 @@ static cudaError_t launch_pool_warp(const void *hidden, const void *mask, int m_
     return cudaGetLastError();
 }
 
-// bulk-copy cluster kernel (pool.cuh): rows of whole 16-byte chunks, at most 384 of them, sequences up to 4096 tokens
-template <typename T>
-static bool pool_bulk_ok(const void *hidden, int seq, int dim) {
-    constexpr int E = Elem<T>::E;
-    if (dim < E || dim % E != 0 || dim / E > kPoolBulkThreads || seq < 1 || seq > kPoolBulkMaxSeq) return false;
-    if (reinterpret_cast<uintptr_t>(hidden) % 16 != 0) return false;
-    return pool_bulk_geom(seq, dim, (int)sizeof(T)).smem <= kSelectSmemLimit;
-}
-
-template <typename T>
-static cudaError_t launch_pool_bulk(const void *hidden, const void *mask, int m_dtype, int batch, int seq, int dim,
-                                    int normalize, float *out, cudaStream_t st) {
-    const PoolBulkGeom gm = pool_bulk_geom(seq, dim, (int)sizeof(T));
-    const int parts = gm.nblk >= 4 ? 2 : 1;          // CTAs per sequence (one cluster)
-    auto kern = pool_bulk_kernel<T>;
-    if (gm.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem);
-        if (e != cudaSuccess) return e;
-    }
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = parts;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)batch * parts);
-    cfg.blockDim = dim3(kPoolBulkThreads);
-    cfg.dynamicSmemBytes = gm.smem;
-    cfg.stream = st;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, static_cast<const unsigned char *>(hidden), mask, m_dtype, seq, dim,
-                              normalize, out);
-}
-
 template <typename T>
 static cudaError_t launch_pool_t(const void *hidden, const void *mask, int m_dtype, int batch, int seq, int dim,
                                  int normalize, float *out, cudaStream_t st) {
-    if (pool_bulk_ok<T>(hidden, seq, dim))
-        return launch_pool_bulk<T>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);
     // rows of up to 2 KB (16-bit) / 4 KB (fp32): warp-per-token fast path
     const int iters = (dim / Elem<T>::E + 31) / 32;
     if (iters <= 1) return launch_pool_warp<T, 1>(hidden, mask, m_dtype, batch, seq, dim, normalize, out, st);

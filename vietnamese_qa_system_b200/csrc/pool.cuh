@@ -9,7 +9,6 @@
 #pragma once
 
 #include "common.cuh"
-#include "ptx.cuh"
 
 namespace vqa {
 
@@ -237,178 +236,6 @@ pool_normalize_warp_kernel(const unsigned char *__restrict__ hidden, const void 
     } else {
         for (int d = tid; d < dim; d += kPoolFastThreads) orow[d] = pooled[d];
     }
-}
-
-// K1, bulk-copy form (the default for rows that are a whole number of 16-byte chunks): a CLUSTER of P CTAs per
-// sequence.  The sequence is cut into blocks of `tb` tokens (about 12 KB: tokens of one sequence are contiguous
-// in memory); block j belongs to CTA j % P of the cluster.  One thread streams the CTA's blocks that hold any
-// unmasked token into a shared-memory ring with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) --
-// bytes in flight are bounded by shared memory, not by registers -- and all threads add them up: thread
-// (chunk c, token lane g) owns the 16-byte chunk c of tokens g, g + G, ... of a block, fp32 accumulators.
-// Fully masked blocks are never loaded; masked tokens inside a loaded block are skipped, not multiplied.
-// The token lanes are combined through shared memory, the P partial sums through distributed shared memory by
-// CTA 0 of the cluster in rank order (a fixed order: the result does not depend on timing), which then divides,
-// normalises and writes the row.  With 512 short-lived CTAs of 384 threads (B = 256, P = 2) four CTAs fit an SM
-// and the whole grid is resident at once; a long sequence is shared by two SMs.
-constexpr int kPoolBulkThreads = 384;
-constexpr int kPoolBulkWarps = kPoolBulkThreads / 32;
-constexpr int kPoolBulkStages = 3;
-constexpr int kPoolBulkStageBytes = 12288;
-constexpr int kPoolBulkMaxSeq = 4096;
-
-struct PoolBulkGeom {
-    int nch, groups, tb, stage_bytes, nblk;
-    size_t smem;
-};
-// shared memory: [ring: stages x stage_bytes (lane partials alias it afterwards)] [psum: dim] [pooled: dim]
-// [mw: seq] [red: 32] [blist: nblk ints] [barriers: 2 x stages x 8 B]
-__host__ __device__ inline PoolBulkGeom pool_bulk_geom(int seq, int dim, int elem_bytes) {
-    PoolBulkGeom g;
-    const int e = 16 / elem_bytes, row_bytes = dim * elem_bytes;
-    g.nch = dim / e;
-    g.groups = kPoolBulkThreads / g.nch;
-    const int per = kPoolBulkStageBytes / (row_bytes * g.groups);
-    g.tb = g.groups * (per < 1 ? 1 : per);
-    g.stage_bytes = g.tb * row_bytes;
-    g.nblk = (seq + g.tb - 1) / g.tb;
-    size_t ring = (size_t)kPoolBulkStages * g.stage_bytes;
-    const size_t lanes = (size_t)g.groups * dim * sizeof(float);
-    if (ring < lanes) ring = lanes;
-    g.smem = ring + (size_t)(2 * dim + seq + 32 + g.nblk) * sizeof(float) + 2 * kPoolBulkStages * sizeof(uint64_t) + 16;
-    return g;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kPoolBulkThreads, 4)
-pool_bulk_kernel(const unsigned char *__restrict__ hidden, const void *__restrict__ mask, int mdt, int seq, int dim,
-                 int normalize, float *__restrict__ out) {
-    constexpr int E = Elem<T>::E;
-    extern __shared__ __align__(16) unsigned char smem[];
-    const PoolBulkGeom gm = pool_bulk_geom(seq, dim, (int)sizeof(T));
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t P = ptx::cluster_nctarank(), part = ptx::cluster_ctarank();
-    const int b = blockIdx.x / P;
-    size_t ring_bytes = (size_t)kPoolBulkStages * gm.stage_bytes;
-    if (ring_bytes < (size_t)gm.groups * dim * sizeof(float)) ring_bytes = (size_t)gm.groups * dim * sizeof(float);
-    unsigned char *ring = smem;
-    float *lanes = reinterpret_cast<float *>(smem);                  // [groups][dim], after the loop
-    float *psum = reinterpret_cast<float *>(smem + ring_bytes);      // [dim] this CTA's partial sum
-    float *pooled = psum + dim;                                      // [dim]
-    float *mw = pooled + dim;                                        // [seq] mask weights
-    float *red = mw + seq;                                           // [32]
-    int *blist = reinterpret_cast<int *>(red + 32);                  // [nblk] this CTA's blocks with a live token
-    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(blist + gm.nblk) + 7) & ~(uintptr_t)7);
-    uint64_t *empty = full + kPoolBulkStages;
-    int *nlive = reinterpret_cast<int *>(red + 31);                  // (red[31] is not used by block_sum: 12 warps)
-
-    const long long mbase = (long long)b * seq;
-    const unsigned char *hrow = hidden + (long long)b * seq * dim * sizeof(T);
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kPoolBulkStages; ++s) {
-            ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], kPoolBulkWarps);
-        }
-        ptx::fence_mbar_init();
-    }
-    float cnt = 0.f;
-    for (int s = tid; s < seq; s += kPoolBulkThreads) {
-        const float m = mask_at(mask, mdt, mbase + s);
-        mw[s] = m;
-        cnt += m;
-    }
-    cnt = block_sum(cnt, red);            // (also orders mw[] and the barrier init before what follows)
-    // warp 0: the list of this CTA's blocks that hold a live token, in ascending order
-    if (tid < 32) {
-        int n = 0;
-        for (int j0 = 0; j0 * (int)P + (int)part < gm.nblk; j0 += 32) {
-            const int j = (j0 + lane) * (int)P + (int)part;
-            bool live = false;
-            if (j < gm.nblk)
-                for (int t = 0; t < gm.tb && j * gm.tb + t < seq; ++t) live = live || mw[j * gm.tb + t] != 0.f;
-            const unsigned bal = __ballot_sync(kFullMask, live);
-            if (live) blist[n + __popc(bal & ((1u << lane) - 1u))] = j;
-            n += __popc(bal);
-        }
-        if (lane == 0) *nlive = n;
-    }
-    __syncthreads();
-    const int nb = *nlive;
-    const int row_bytes = dim * (int)sizeof(T);
-    auto issue = [&](int i) {             // thread 0: block blist[i] -> stage i % stages
-        const int st = i % kPoolBulkStages, j = blist[i];
-        const int rows = min(gm.tb, seq - j * gm.tb);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)row_bytes;
-        ptx::mbar_arrive_expect_tx(&full[st], bytes);
-        ptx::bulk_load_1d(ring + (size_t)st * gm.stage_bytes, hrow + (long long)j * gm.tb * row_bytes, bytes, &full[st]);
-    };
-    if (tid == 0)
-        for (int i = 0; i < nb && i < kPoolBulkStages; ++i) issue(i);
-
-    const int g = tid / gm.nch, c = tid - g * gm.nch;
-    const bool worker = g < gm.groups;
-    float acc[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = 0.f;
-    for (int i = 0; i < nb; ++i) {
-        const int st = i % kPoolBulkStages;
-        const uint32_t ph = (uint32_t)(i / kPoolBulkStages) & 1u;
-        ptx::mbar_wait(&full[st], ph);
-        if (worker) {
-            const int s0 = blist[i] * gm.tb;
-            const unsigned char *src = ring + (size_t)st * gm.stage_bytes + (size_t)c * 16;
-            for (int t = g; t < gm.tb; t += gm.groups) {
-                const int s = s0 + t;
-                if (s >= seq) break;
-                const float m = mw[s];
-                if (m != 0.f) {
-                    const uint4 w = *reinterpret_cast<const uint4 *>(src + (size_t)t * row_bytes);
-                    float x[E];
-                    Elem<T>::unpack(w, x);
-#pragma unroll
-                    for (int e = 0; e < E; ++e) acc[e] = fmaf(x[e], m, acc[e]);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[st]);
-        if (tid == 0 && i + kPoolBulkStages < nb) {
-            ptx::mbar_wait(&empty[st], ph);          // every warp has read block i: its stage can be refilled
-            issue(i + kPoolBulkStages);
-        }
-    }
-    __syncthreads();                                   // the ring is idle: the lane partials reuse it
-    if (worker) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) lanes[(size_t)g * dim + c * E + e] = acc[e];
-    }
-    __syncthreads();
-    for (int d = tid; d < dim; d += kPoolBulkThreads) {
-        float t = 0.f;
-        for (int gg = 0; gg < gm.groups; ++gg) t += lanes[(size_t)gg * dim + d];
-        psum[d] = t;
-    }
-    ptx::cluster_sync_all();                           // every CTA's psum[] is complete and visible cluster-wide
-    if (part == 0) {
-        const float den = fmaxf(cnt, 1e-9f);
-        float ss = 0.f;
-        for (int d = tid; d < dim; d += kPoolBulkThreads) {
-            float t = psum[d];
-            for (uint32_t r = 1; r < P; ++r) t += ptx::ld_dsmem_f32(&psum[d], r);
-            const float mean = t / den;
-            pooled[d] = mean;
-            ss += mean * mean;
-        }
-        ss = block_sum(ss, red);
-        float *orow = out + (long long)b * dim;
-        if (normalize) {
-            const float nrm = sqrtf(ss);
-            for (int d = tid; d < dim; d += kPoolBulkThreads) orow[d] = nrm > 0.f ? pooled[d] / nrm : 0.f;
-        } else {
-            for (int d = tid; d < dim; d += kPoolBulkThreads) orow[d] = pooled[d];
-        }
-    }
-    ptx::cluster_sync_all();                           // CTA 0 has read the peers' partial sums: they may exit
 }
 
 // Row-wise L2 normalise: one warp per row, float4 accesses.  Optional cast copy.

@@ -111,32 +111,11 @@ __device__ __forceinline__ void tma_load_2d_multicast(void *smem_dst, const void
         : "memory");
 }
 
-// 1-D bulk copy (the TMA unit without a tensor map): `bytes` contiguous bytes global -> this CTA's shared memory,
-// completed on the mbarrier; addresses and size are multiples of 16
-__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // ---- thread-block clusters ---------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-    return r;
-}
-// the float at the same shared-memory offset as `local` in CTA `rank` of this cluster (distributed shared memory)
-__device__ __forceinline__ float ld_dsmem_f32(const float *local, uint32_t rank) {
-    uint32_t remote;
-    float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-    return v;
 }
 // all threads of all CTAs in the cluster
 __device__ __forceinline__ void cluster_sync_all() {
