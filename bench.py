@@ -441,8 +441,12 @@ def run_ours(args):
     # ---- headline: inputs resident in HBM; N>1: exchange + merge of step i under the scan of step i+1 ----------
     pend = [None, None]
 
+    host_s = {"value": 0.0, "e2e": 0.0}     # host time spent enqueueing (is a loop host-bound?)
+
     def step(i):
+        t_ = time.perf_counter()
         pend[i & 1] = index.search_pipelined(q_dev, topk, i & 1)
+        host_s["value"] += time.perf_counter() - t_
 
     def drain():
         main = torch.cuda.current_stream()
@@ -456,8 +460,10 @@ def run_ours(args):
     drain()
     barrier()
     sampler.start()
+    host_s["value"] = 0.0
     total_ms = timed(step, K, 0, drain)
     clocks = sampler.stop()
+    host_enqueue_us = host_s["value"] / K * 1e6
     ms_per_step = total_ms / K
     value = B * K / (total_ms / 1e3)
     # ---- dominant kernel alone (local scan+select of this rank's shard), same stream; measured right after the
@@ -475,7 +481,9 @@ def run_ours(args):
             hs, hi_, ev = hpend[slot]
             ev.synchronize()
             e2e_sink[0] += int(hi_[0, 0])
+        t_ = time.perf_counter()
         hpend[slot] = index.search_host_pipelined(q_host, topk, slot)
+        host_s["e2e"] += time.perf_counter() - t_
 
     def e2e_drain():
         for p_ in hpend:
@@ -484,6 +492,7 @@ def run_ours(args):
                 e2e_sink[0] += int(p_[1][0, 0])
 
     e2e_ms = timed(e2e_step, K, 3, e2e_drain)
+    e2e_host_us = host_s["e2e"] / (K + 3) * 1e6
     shard = index.shard
     if world == 1:
         sync_ms = timed(lambda i: shard.search_host(q_host, topk, "fast"), K, 3) / K
@@ -493,7 +502,7 @@ def run_ours(args):
             ev.synchronize()
         sync_ms = timed(sync_step, K, 3) / K
     e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
-           "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": 2,
+           "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": 2, "host_enqueue_us_per_step": e2e_host_us,
            "one_at_a_time_ms_per_step": sync_ms, "one_at_a_time_qps": B / sync_ms * 1e3,
            "api": ("FlatShard.search_host_async -> vqa_search_host_async (C ABI, pinned host buffers)" if world == 1 else
                    "ShardedFlat.search_host_pipelined (pinned host buffers; cudaMemcpyAsync H2D -> vqa_search -> "
@@ -763,7 +772,7 @@ def run_ours(args):
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e9:.2f} GB per GPU streamed per step)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": K * (launches + xlaunch - (1 if (world > 1 and not p2p) else 0)),
-            "one_step_at_a_time_ms": serial_ms,
+            "one_step_at_a_time_ms": serial_ms, "host_enqueue_us_per_step": host_enqueue_us,
             "recall_at_k": recall, "recall_at_10_batch256": recall_b256, "fast_vs_verify_max_rel_score_err": max_rel,
             "independent_check": independent, "sharded_equals_single": sharded_single,
             "sweep": sweep, "pool_k1": pool, "config_a_reference_scale": config_a, "hybrid_leg": hybrid,

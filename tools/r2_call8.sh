@@ -18,7 +18,7 @@ try:
 except Exception as e:
     print(sys.argv[1], 'unreadable', e); sys.exit(0)
 print({k: d[k] for k in ('metric', 'n_gpus', 'value', 'ms_per_step', 'one_step_at_a_time_ms', 'recall_at_k')}, d['config']['exchange'])
-print('roofline', {k: d['roofline'][k] for k in ('frac', 'step_frac', 'kernel_ms', 'kernel')}, 'e2e', d['e2e']['value'], d['e2e']['one_at_a_time_ms_per_step'], d['clocks'])
+print('roofline', {k: d['roofline'][k] for k in ('frac', 'step_frac', 'kernel_ms', 'kernel')}, 'e2e', d['e2e']['value'], d['e2e']['one_at_a_time_ms_per_step'], 'host us per step', d.get('host_enqueue_us_per_step'), d['e2e'].get('host_enqueue_us_per_step'), d['clocks'])
 print('independent', d['independent_check']); print('sharded_equals_single', d['sharded_equals_single'])
 for r in d['sweep']: print(r['batch'], round(r['ms'], 4), round(r['scan_ms'], 4), round(r['hbm_frac'], 3), round(r['tensor_frac'], 3), r['family'][:34])
 PY
