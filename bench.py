@@ -471,13 +471,14 @@ def run_ours(args):
     shard = index.shard
     scan_ms = timed(lambda i: shard.search(q_dev, topk, "fast"), K, 3) / K
 
-    # ---- e2e: host buffers through the public API, two steps in flight, all copies inside the timed region ------
-    hpend = [None, None]
+    # ---- e2e: host buffers through the public API, --inflight steps in flight, all copies inside the timed region --
+    n_slots = max(2, int(args.inflight))
+    hpend = [None] * n_slots
     e2e_sink = [0]
 
     def e2e_step(i):
-        slot = i & 1
-        if hpend[slot] is not None:            # the result of step i-2 is read on the host before its slot is reused
+        slot = i % n_slots
+        if hpend[slot] is not None:            # the result of step i-n_slots is read on the host before its slot is reused
             hs, hi_, ev = hpend[slot]
             ev.synchronize()
             e2e_sink[0] += int(hi_[0, 0])
@@ -502,7 +503,7 @@ def run_ours(args):
             ev.synchronize()
         sync_ms = timed(sync_step, K, 3) / K
     e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
-           "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": 2, "host_enqueue_us_per_step": e2e_host_us,
+           "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": n_slots, "host_enqueue_us_per_step": e2e_host_us,
            "one_at_a_time_ms_per_step": sync_ms, "one_at_a_time_qps": B / sync_ms * 1e3,
            "api": ("FlatShard.search_host_async -> vqa_search_host_async (C ABI, pinned host buffers)" if world == 1 else
                    "ShardedFlat.search_host_pipelined (pinned host buffers; cudaMemcpyAsync H2D -> vqa_search -> "
@@ -798,6 +799,7 @@ def main():
     ap.add_argument("--sweep", type=int, default=1)
     ap.add_argument("--check", type=int, default=1, help="independent torch fp32 checker + sharded-vs-single check")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="host-buffer (e2e) loop: batches in flight (buffer slots)")
     ap.add_argument("--cpu-rows", type=int, default=500_000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-cap-seconds", type=float, default=150.0, help="--impl reference: wall-clock cap of the run")

@@ -102,6 +102,11 @@ def test_b200flat_ann_contract(tmp_path):
     os_, oi = oracle.search(docs, q, 4)
     assert [[i for i, _ in row] for row in out] == oi.tolist()
     assert [[s for _, s in row] for row in out] == [[float(x) for x in r] for r in os_]
+    # limit > 128 (any limit up to 1024, as faiss answers it): composed from row-segment searches, host queries included
+    wide = ann.search(q[:2], 300)
+    ws_, wi = oracle.search(docs, q[:2], 300)
+    assert [[i for i, _ in row] for row in wide] == wi.tolist()
+    assert [[s for _, s in row] for row in wide] == [[float(x) for x in r] for r in ws_]
     # append keeps ids stable and appended rows are searchable
     extra = unit_rows(rng, 10, 768)
     ann.append(extra)

@@ -120,6 +120,9 @@ for hyb in (False, True):
     ok = ok and many.count() == 3000 and many.ann.shard.n < 3000
     a_, b_ = one.batchsearch(qs_e, 3), many.batchsearch(qs_e, 3)
     ok = ok and a_ == b_ and b_[0][0]["id"] == 8 and b_[0][0]["text"] == texts[7]
+    if hyb:                                        # limit > 12: 150 candidates per leg, the dense leg composed from segments
+        a15, b15 = one.batchsearch(qs_e, 15), many.batchsearch(qs_e, 15)
+        ok = ok and a15 == b15 and len(b15[0]) == 15
     if not ok:
         print("FAILED Embeddings(shards=True)", hyb, rank, a_[:1], b_[:1], flush=True)
 if rank == 0:

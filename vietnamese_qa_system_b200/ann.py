@@ -165,7 +165,8 @@ class B200Flat:
         ties -> lower id; fewer than ``limit`` entries when the index is smaller."""
         if self.shard is None:
             raise RuntimeError("index is empty: call index() or load() first")
-        use_host_call = (not isinstance(queries, torch.Tensor) or not queries.is_cuda) and self._positions is None
+        use_host_call = (not isinstance(queries, torch.Tensor) or not queries.is_cuda) and self._positions is None \
+            and int(limit) <= ops.K_CALL_MAX      # (k > 128 is composed on the device side: ops.FlatShard._search_wide)
         if use_host_call:
             q = queries if isinstance(queries, torch.Tensor) else \
                 torch.from_numpy(np.ascontiguousarray(np.asarray(queries, dtype=np.float32)))
