@@ -143,7 +143,8 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
     uint64_t *empty = bars + kMaxStages;
     uint64_t *tfull = bars + 2 * kMaxStages;
     uint64_t *tempty = tfull + kMaxAccStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + kMaxAccStages);
+    uint64_t *qready = tempty + kMaxAccStages;   // the query block is in place (one arrival per epilogue warp)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qready + 1);
     float *xchg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 1024);  // [2][64 docs][64 rows]
     unsigned char *lists = reinterpret_cast<unsigned char *>(xchg) + (p.split ? 2 * 64 * kTsDocs * 4 : 0);
     // per-thread sorted lists (KL == 0) and candidate buffers, entry-major so that a warp's accesses are
@@ -176,6 +177,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             ptx::mbar_init(tfull + a, 1);
             ptx::mbar_init(tempty + a, 4);
         }
+        ptx::mbar_init(qready, 4);
         ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -192,7 +194,7 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
 
     if (warp == 4) {
         // ===== TMA producer =====
-        named_bar_arrive(1, kMmaThreads);  // (does not wait for the query block: documents start streaming now)
+        // (does not wait for the query block: documents start streaming now)
         uint32_t it = 0;
         const bool tl = p.timeline != nullptr;
         unsigned long long w_empty = 0, t_loop = tl ? ptx::sm_clock() : 0;
@@ -224,9 +226,10 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             p.timeline[(size_t)blockIdx.x * 32 + 9] = ptx::sm_clock() - t_loop;
         }
     } else if (warp == 5) {
-        // ===== MMA issuer: waits for the query block (named barrier 1), then D = Q * docs^T =====
-        __syncwarp();
-        named_bar_sync(1, kMmaThreads);
+        // ===== MMA issuer: waits for the query block (mbarrier `qready`: the four epilogue warps arrive once their rows
+        // are in tensor / shared memory), then D = Q * docs^T.  (Until round 2 this was a named bar.sync reached from two
+        // code locations -- legal, but compute-sanitizer's synccheck reports it as block-level divergence.)
+        ptx::mbar_wait(qready, 0);
         ptx::tc_fence_after_sync();
         uint32_t it = 0, lt = 0;
         const uint32_t ring = ptx::smem_u32(a_smem);
@@ -355,7 +358,11 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
             if constexpr (QS) {
                 // the remaining blocks of this row -> shared memory, K-major, 128-byte swizzle (16-byte chunk c of
                 // row r at r * 128 + ((c ^ (r & 7)) << 4)), same 16-bit values as the TMEM part
-                for (int kb = KT; kb < KB && (!M64 || lane < 16); ++kb) {
+                // (M = 64: lanes 16..31 own no row; they walk the loop with the stores switched off, so that the warp
+                //  reaches the block-wide barrier below converged -- a divergent loop exit here made synccheck report
+                //  the bar.sync as executed by a split warp)
+                const bool owns_row = !M64 || lane < 16;
+                for (int kb = KT; kb < KB; ++kb) {
                     unsigned char *tile = q_smem + (size_t)(kb - KT) * QBLK;
                     const int row = M64 ? qrow : warp * 32 + lane;   // row of the K-major shared-memory tile
 #pragma unroll
@@ -376,14 +383,14 @@ ts_topk_kernel(const __grid_constant__ CUtensorMap tmap_docs, const TsParams p) 
                         uint4 w;
                         if (DOC_BF16 && !p.a_fp16) w = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
                         else w = make_uint4(pack_f16x2(x[0], x[1]), pack_f16x2(x[2], x[3]), pack_f16x2(x[4], x[5]), pack_f16x2(x[6], x[7]));
-                        *reinterpret_cast<uint4 *>(tile + row * 128 + ((c ^ (row & 7)) << 4)) = w;
+                        if (owns_row) *reinterpret_cast<uint4 *>(tile + row * 128 + ((c ^ (row & 7)) << 4)) = w;
                     }
                 }
                 ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
             }
             ptx::tc_fence_before_sync();
             __syncwarp();
-            named_bar_sync(1, kMmaThreads);  // with the MMA warp
+            if (lane == 0) ptx::mbar_arrive(qready);   // -> the MMA warp; the epilogue warps do not wait for each other
         }
         // 2. private list + threshold
         float tau = (live && !is_lo) ? neg_inf() : __int_as_float(0x7f800000);
