@@ -595,7 +595,7 @@ def test_emulated_segment_merge_composes_a_wide_top_k(emu):
     docs[2500] = docs[1001]                                                   # exact ties -> lower id first
     want_s, want_i = oracle.search(docs, q, k)
     bounds, passes, first = wide_segments(n, k), 0, None
-    assert len(bounds) == 10 and bounds[0] == (0, 260) and bounds[-1][1] == n
+    assert len(bounds) == 5 and bounds[0] == (0, 520) and bounds[-1][1] == n
     while True:
         seg_s = np.full((len(bounds), b, ks), -np.inf, np.float32)
         seg_i = np.full((len(bounds), b, ks), -1, np.int64)

@@ -199,14 +199,14 @@ def test_heavy_ranker_build_and_load_orchestration(tmp_path):
 
 def test_wide_k_segment_plan():
     """Host logic of the k > 128 composition (ops.FlatShard._search_wide): segments tile the shard in ascending
-    order, about k / 32 of them and never more than the merge kernel holds; only saturated segments that are
+    order, about k / 64 of them and never more than the merge kernel holds; only saturated segments that are
     larger than their candidate list are split."""
     from vietnamese_qa_system_b200.ops import K_SEGMENT, split_saturated, wide_segments
     for n, k in ((10_000_000, 1000), (1_250_000, 129), (131, 130), (50, 1024), (1, 500), (70_000, 1024)):
         b = wide_segments(n, k)
         assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
         assert all(hi > lo for lo, hi in b) and len(b) * K_SEGMENT <= 8192
-        assert len(b) == min(max(2, -(-k // 32)), n, 64)
+        assert len(b) == min(max(2, -(-k // 64)), n, 64)
     assert wide_segments(0, 300) == []
     b, changed = split_saturated([(0, 300), (300, 400), (400, 1000)], [1, 1, 0])
     assert changed and b == [(0, 150), (150, 300), (300, 400), (400, 1000)]     # 100 rows <= 128: nothing more there

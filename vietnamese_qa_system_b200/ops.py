@@ -44,11 +44,12 @@ K_SEGMENT = 128    # candidates kept per row segment by the k > 128 composition
 
 def wide_segments(n_rows: int, k: int, k_seg: int = K_SEGMENT, max_candidates: int = 8192) -> List[Tuple[int, int]]:
     """Row segments ``[(lo, hi), ...]`` (ascending, non-empty) for a top-k with ``k > 128`` (vqa_merge_segments,
-    include/vqa.h): about ``k / 32`` of them, so that a segment is expected to hold a quarter of the ``k_seg``
-    candidates it can report and a second pass is rare; never more than ``max_candidates / k_seg``."""
+    include/vqa.h): about ``k / 64`` of them, so that a segment is expected to hold half of the ``k_seg`` candidates
+    it can report (on unclustered data the 128th is then ~8 standard deviations away and a second pass is rare; every
+    segment search has a fixed cost, so fewer is faster); never more than ``max_candidates / k_seg``."""
     if n_rows <= 0:
         return []
-    want = max(2, -(-int(k) // 32))
+    want = max(2, -(-int(k) // 64))
     nseg = max(1, min(want, max_candidates // k_seg, n_rows))
     cuts = [n_rows * i // nseg for i in range(nseg + 1)]
     return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
@@ -253,7 +254,8 @@ class FlatShard:
             if len(new_bounds) > cap:
                 raise RuntimeError(f"top-{k}: more than {cap} row segments would be needed (the answer is "
                                    f"concentrated in a few row ranges); search with k <= {K_CALL_MAX} instead")
-            have = {seg_b: i for i, seg_b in enumerate(bounds) if seg_b in set(new_bounds)}
+            kept = set(new_bounds)
+            have = {seg_b: i for i, seg_b in enumerate(bounds) if seg_b in kept}
             bounds, cur = new_bounds, cur ^ 1
 
     def search_host(self, queries_host: torch.Tensor, k: int, mode="fast"):

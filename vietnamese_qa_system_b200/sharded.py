@@ -228,7 +228,8 @@ class ShardedFlat:
         """``search_pipelined`` with HOST buffers: pinned float32 ``[B, dim]`` queries in, pinned ``(scores, ids)`` out.
         Enqueues the H2D copy of the queries, the scan, the exchange + merge and the D2H copy of the merged result and
         returns ``(scores_host, ids_host, event)`` at once; the host tensors hold the result when ``event`` has
-        completed.  A serving loop keeps two slots in flight: it reads slot s's result (``event.synchronize()``)
+        completed.  A serving loop keeps two or three slots in flight (three measured best at 0.29 ms steps, bench.py
+        ``--inflight``): it reads slot s's result (``event.synchronize()``)
         just before re-issuing slot s, so the per-step host wake-up is off the critical path while every byte of
         every step still crosses PCIe inside the loop.  ``queries_host`` must be pinned and stay untouched until
         ``event`` has completed."""
