@@ -59,5 +59,10 @@ for b in [int(x) for x in os.environ.get("BATCHES", "128,256").split(",")]:
         "producer_wait_free_stage_share": round(med(t[:, 1]) / max(prod_loop, 1.0), 3),
         "epilogue_wait_accumulator_share": round(med(t[:, 5]) / epi_loop, 3),
         "epilogue_busy_cycles_per_tile": round((epi_loop - med(t[:, 5])) / tiles),
-        "epilogue_flushes_per_cta": med(t[:, 7])}
+        "epilogue_flushes_per_cta": med(t[:, 7]),
+        # where the rest of a launch goes: per-CTA life time (globaltimer) against its role loops (SM cycles)
+        "cta_us_min_med_max": [round(float(x) / 1e3, 1) for x in np.percentile((t[live, 15] - t[live, 0]), [0, 50, 100])],
+        "cta_start_spread_us": round(float(t[live, 0].max() - t[live, 0].min()) / 1e3, 1),
+        "cta_end_spread_us": round(float(t[live, 15].max() - t[live, 15].min()) / 1e3, 1),
+        "loop_cycles_mma_epilogue_producer": [round(mma_loop), round(epi_loop), round(prod_loop)]}
 print(json.dumps(out))
