@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import json
 import os
+import warnings
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -211,7 +212,9 @@ class B200Flat:
         lo, hi = (0, meta["n"]) if row_range is None else row_range
         if row_range is not None and meta.get("positions") is not None:
             raise NotImplementedError("sharded load of an index with deleted rows")
-        block = torch.from_numpy(np.ascontiguousarray(raw[lo:hi]))
+        with warnings.catch_warnings():      # the memory map is read-only and the tensor is only read (uploaded below)
+            warnings.simplefilter("ignore", UserWarning)
+            block = torch.from_numpy(np.ascontiguousarray(raw[lo:hi]))
         if self.dtype == torch.float32:
             rows = block.view(torch.float32).reshape(hi - lo, meta["dim"])
         else:
