@@ -494,6 +494,25 @@ def run_ours(args):
 
     e2e_ms = timed(e2e_step, K, 3, e2e_drain)
     e2e_host_us = host_s["e2e"] / (K + 3) * 1e6
+    e2e_2s_ms = None
+    if world == 1:
+        # the same loop through the two-stream form (copy stream + vqa_search_2s + D2H behind the reduce), reported beside
+        hp2 = [None] * n_slots
+
+        def e2e2_step(i):
+            slot = i % n_slots
+            if hp2[slot] is not None:
+                hp2[slot][2].synchronize()
+                e2e_sink[0] += int(hp2[slot][1][0, 0])
+            hp2[slot] = index.search_host_pipelined(q_host, topk, slot, two_stream=True)
+
+        def e2e2_drain():
+            for p_ in hp2:
+                if p_ is not None:
+                    p_[2].synchronize()
+                    e2e_sink[0] += int(p_[1][0, 0])
+
+        e2e_2s_ms = timed(e2e2_step, K, 3, e2e2_drain) / K
     shard = index.shard
     if world == 1:
         sync_ms = timed(lambda i: shard.search_host(q_host, topk, "fast"), K, 3) / K
@@ -504,6 +523,7 @@ def run_ours(args):
         sync_ms = timed(sync_step, K, 3) / K
     e2e = {"value": B * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,
            "d2h_bytes_per_step": B * topk * 12, "ms_per_step": e2e_ms / K, "in_flight": n_slots, "host_enqueue_us_per_step": e2e_host_us,
+           "two_stream_form_ms_per_step": e2e_2s_ms,
            "one_at_a_time_ms_per_step": sync_ms, "one_at_a_time_qps": B / sync_ms * 1e3,
            "api": ("FlatShard.search_host_async -> vqa_search_host_async (C ABI, pinned host buffers)" if world == 1 else
                    "ShardedFlat.search_host_pipelined (pinned host buffers; cudaMemcpyAsync H2D -> vqa_search -> "

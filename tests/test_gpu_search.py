@@ -326,3 +326,27 @@ def test_merge_segments_c_abi_argument_errors():
         ops.merge_segments(z[:4].contiguous(), zi[:4].contiguous(), 1025)
     with pytest.raises(ValueError):
         ops.merge_segments(z[:4].contiguous(), zi[:4].contiguous().int(), 100)
+
+
+def test_host_buffer_loop_two_stream_form_on_one_gpu():
+    """ShardedFlat.search_host_pipelined(two_stream=True) without a process group: the H2D copy on a copy stream, the
+    scan on the current stream, reduce + D2H on the side stream -- same answers as the synchronous host call, with
+    three slots in flight."""
+    from vietnamese_qa_system_b200.sharded import ShardedFlat
+    rng = np.random.default_rng(9)
+    docs = unit_rows(rng, 40000, 768)
+    rows = torch.from_numpy(docs).to(DEV).to(torch.bfloat16)
+    sh = ShardedFlat(rows, 40000, mode="fast")
+    qs = [torch.from_numpy(unit_rows(rng, 32, 768)).pin_memory() for _ in range(4)]
+    want = [tuple(t.clone() for t in sh.shard.search_host(q, 10, "fast")) for q in qs]
+    pend = [None] * 3
+    for step in range(11):
+        slot = step % 3
+        if pend[slot] is not None:
+            hs, hi, ev, j = pend[slot]
+            ev.synchronize()
+            assert torch.equal(hi, want[j][1]) and torch.equal(hs, want[j][0])
+        pend[slot] = sh.search_host_pipelined(qs[step % 4], 10, slot, two_stream=True) + (step % 4,)
+    for hs, hi, ev, j in pend:
+        ev.synchronize()
+        assert torch.equal(hi, want[j][1]) and torch.equal(hs, want[j][0])

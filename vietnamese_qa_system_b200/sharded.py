@@ -224,7 +224,7 @@ class ShardedFlat:
         self._last[(b, k, slot)] = done
         return out_s, out_i, done
 
-    def search_host_pipelined(self, queries_host: torch.Tensor, k: int, slot: int):
+    def search_host_pipelined(self, queries_host: torch.Tensor, k: int, slot: int, two_stream: Optional[bool] = None):
         """``search_pipelined`` with HOST buffers: pinned float32 ``[B, dim]`` queries in, pinned ``(scores, ids)`` out.
         Enqueues the H2D copy of the queries, the scan, the exchange + merge and the D2H copy of the merged result and
         returns ``(scores_host, ids_host, event)`` at once; the host tensors hold the result when ``event`` has
@@ -237,7 +237,9 @@ class ShardedFlat:
             raise ValueError("queries_host must be a contiguous float32 CPU tensor")
         if not queries_host.is_pinned():
             raise ValueError("queries_host must be pinned (page-locked) for an asynchronous copy")
-        if self.world == 1:
+        if not (self.world > 1 if two_stream is None else two_stream):
+            # one GPU, one call: vqa_search_host_async (H2D, scan, reduce, D2H in stream order on the current stream).
+            # two_stream=True takes the path below on one GPU as well: copy stream + vqa_search_2s + D2H behind the reduce
             return self.shard.search_host_async(queries_host, k, self.mode, slot=slot)
         b = int(queries_host.shape[0])
         dev = self.shard.device
