@@ -546,7 +546,9 @@ def run_ours(args):
                 traffic, traffic_src = ent["bytes"], ent["source"]
         except Exception:  # noqa: BLE001
             traffic = None
-    kname = {2: "scan_topk_kernel (CUDA cores)", 3: "mma_topk_kernel (tcgen05, queries in smem)",
+    screen_mode = fam == 3 and shard.describe(B, topk, "fast")["split"] == 0
+    kname = {2: "scan_topk_kernel (CUDA cores)",
+             3: "mma_topk_kernel (tcgen05, queries in smem" + (", screen mode + exact re-score in the reduce)" if screen_mode else ", hi/lo columns)"),
              4: "ts_topk_kernel (tcgen05, queries in TMEM)",
              5: "ts_pair_topk_kernel (tcgen05, 128-document tiles" + (", cta_group::2 CTA pairs)" if B > 128 else ", single CTAs)")
              }.get(fam, str(fam))
@@ -663,11 +665,14 @@ def run_ours(args):
                 ms = timed(sstep, n_it, 3, sdrain) / n_it
                 kms = timed(lambda i: shard.search(qd, topk, "fast"), n_it, 2) / n_it
                 fam_b, _ = shard.plan(b_, topk, "fast")
+                screen_b = fam_b == 3 and shard.describe(b_, topk, "fast")["split"] == 0
                 sweep.append({"batch": b_, "ms": ms, "qps": b_ / ms * 1e3, "scan_ms": kms,
                               "hbm_frac": alg_bytes / (ms / 1e3) / 1e9 / hbm_peak,
                               "scan_hbm_frac": alg_bytes / (kms / 1e3) / 1e9 / hbm_peak,
                               "tensor_frac": 2.0 * b_ * (hi - lo) * dim / (ms / 1e3) / 1e12 / tf_peak,
-                              "family": {2: "stream (CUDA cores)", 3: "tcgen05, queries in smem (hi/lo)",
+                              "family": {2: "stream (CUDA cores)",
+                                         3: ("tcgen05, queries in smem (screen + exact re-score)" if screen_b
+                                             else "tcgen05, queries in smem (hi/lo)"),
                                          4: "tcgen05, queries in TMEM (screen + exact re-score)",
                                          5: ("tcgen05, 128-document tiles, queries in TMEM (screen + exact re-score): "
                                              + ("cta_group::2 CTA pairs" if b_ > 128 else "single CTAs"))

@@ -142,7 +142,8 @@ VQA_API int vqa_debug_timeline(vqa_index_t *h, void *stamps_dev, size_t bytes);
 typedef struct vqa_tuning {
     int32_t size;          /* sizeof(vqa_tuning_t) as the caller compiled it (ABI growth check)                  */
     int32_t ts_extra;      /* spare candidate ranks kept by the screen-then-rescore scans, 0..96 (6)              */
-    int32_t ss_screen;     /* smem-resident tcgen05 kernel: screen mode instead of hi/lo columns, 0|1 (0)         */
+    int32_t ss_screen;     /* smem-resident tcgen05 kernel: screen mode instead of hi/lo columns, 0|1, -1 auto =
+                              only for scans of >= 12 GB with more than 16 queries (-1)                             */
     int32_t mma_kps;       /* 64-column blocks per TMA ring stage, 0 = auto, else 1..16                           */
     int32_t mma_stages;    /* cap on ring stages, 0 = auto                                                        */
     int32_t mma_groups;    /* smem-resident kernel: query chunks side by side per launch, 1..4 (4)                */

@@ -294,3 +294,24 @@ def test_m64_variant_of_the_tmem_resident_query_kernel(monkeypatch, storage, n, 
     s, i = _check(docs, q, k, "ts", storage)
     assert i[0, :2].tolist() == [3, n // 2] and i[b - 1, 0] == n - 1
     assert recall(i, i0) >= 0.999 and np.abs(s - s0).max() <= 5e-7
+
+
+@pytest.mark.parametrize("storage", ["bf16", "fp16"])
+@pytest.mark.parametrize("n,d,b,k", [(30000, 768, 32, 10), (9000, 768, 17, 5), (20000, 384, 8, 26), (4000, 1024, 32, 1),
+                                     (150, 768, 3, 10)])
+def test_screen_mode_of_the_smem_resident_kernel(monkeypatch, storage, n, d, b, k):
+    """ss_screen (planner default for scans of >= 12 GB with more than 16 queries -- BASELINE's 10 M x 768 index on ONE
+    GPU at B = 32; forced here on small indexes): mma_topk_kernel with one storage-precision column per query (half the
+    tensor work of the hi/lo form), k + 6 candidates per list, exact fp32 re-scoring in the reduce.  Against the oracle
+    (recall, exact scores) and against the hi/lo form of the same kernel."""
+    rng = np.random.default_rng(n + d + k)
+    docs, q = unit_rows(rng, n, d), unit_rows(rng, b, d)
+    docs[n // 2] = docs[3]                                    # a tie, decided by the lower id
+    q[0] = docs[3]
+    monkeypatch.setenv("VQA_SS_SCREEN", "1")
+    s1, i1 = _check(docs, q, k, "tensor", storage)
+    monkeypatch.setenv("VQA_SS_SCREEN", "0")
+    s0, i0 = _check(docs, q, k, "tensor", storage)
+    assert recall(i1, i0) >= 0.999
+    if k >= 2 and n > 2000:
+        assert i1[0, :2].tolist() == [3, n // 2]

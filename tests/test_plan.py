@@ -44,9 +44,16 @@ def test_default_routing(monkeypatch):
     for b in (1, 2):                                       # the CUDA-core streaming kernel is a knob away (it lost to the
         assert plan(n, 768, BF16, b, 10, stream_max_b=2)["family"] == STREAM         # seeded tcgen05 kernel at every size)
         assert plan(1_250_000, 768, BF16, b, 10, stream_max_b=2)["family"] == TENSOR  # ... and never on small shards
-    for b in (1, 2, 3, 8, 32):                             # headline: smem-resident tcgen05 kernel, hi/lo columns
+    for b in (1, 2, 3, 8, 16):                             # headline kernel: smem-resident tcgen05, hi/lo columns
         p = plan(n, 768, BF16, b, 10)
         assert p["family"] == TENSOR and p["split"] == 1 and p["smem"] <= SMEM
+    for b in (17, 32):                                     # ... and for more than 16 queries over a scan of >= 12 GB screen
+        p = plan(n, 768, BF16, b, 10)                      # mode (half the tensor work, exact re-score of k + 6): ss_screen = -1
+        assert (p["family"], p["split"], p["kscan"], p["rescore"]) == (TENSOR, 0, 16, 1) and p["smem"] <= SMEM
+        for rows, knobs in ((n, {"ss_screen": 0}), (5_000_000, {}), (1_250_000, {})):
+            p = plan(rows, 768, BF16, b, 10, **knobs)      # forced off / the 2- and 8-GPU shards: hi/lo columns
+            assert (p["family"], p["split"], p["rescore"]) == (TENSOR, 1, 0)
+    assert plan(1_250_000, 768, BF16, 32, 10, ss_screen=1)["split"] == 0
     for b in (129, 256, 1024):                             # > 128 queries: CTA pairs (cta_group::2), 256 queries per launch
         p = plan(n, 768, BF16, b, 10)
         assert (p["family"], p["pass_nq"], p["ks"], p["kscan"], p["k_out"], p["rescore"]) == (5, 256, 4, 16, 32, 1)

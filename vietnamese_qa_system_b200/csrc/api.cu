@@ -161,7 +161,7 @@ struct KnobSpec {
 // kernel and the radix-select / re-scoring reduce on, batches of <= 2 on the CUDA-core streaming kernel
 const KnobSpec kKnobs[] = {
     {"VQA_TS_EXTRA", &vqa_tuning_t::ts_extra, 0, 96, 6},
-    {"VQA_SS_SCREEN", &vqa_tuning_t::ss_screen, 0, 1, 0},
+    {"VQA_SS_SCREEN", &vqa_tuning_t::ss_screen, -1, 1, -1},
     {"VQA_MMA_KPS", &vqa_tuning_t::mma_kps, 0, 16, 0},
     {"VQA_MMA_STAGES", &vqa_tuning_t::mma_stages, 0, vqa::kMaxStages, 0},
     {"VQA_MMA_GROUPS", &vqa_tuning_t::mma_groups, 1, 4, 4},
@@ -237,9 +237,14 @@ size_t smem_budget(const vqa_index *h, bool big_reduce) {
 bool plan_tensor(const vqa_index *h, int nq, int k, Plan *pl) {
     const vqa_tuning_t &tu = h->tune;
     // Measured (profiles/r1_tune_screen.log): for <= 32 queries per CTA the hi/lo kernel already runs at
-    // the HBM roofline and the re-scoring stage's cold row reads cost ~35 us per search, so screen mode is
-    // opt-in here (ss_screen); it pays off in the TMEM-resident-query kernel, 128 queries per CTA.
-    const bool screen = tu.ss_screen != 0 && k + spare_ranks(h) <= 32;
+    // the HBM roofline and the re-scoring stage costs ~60 us per search, so screen mode is off for short scans.
+    // A LONG scan with more than 16 queries is another matter: sustained, the hi/lo kernel's tensor work runs the
+    // GPU into its power cap (1.5 GHz), and halving it buys more than the re-scoring costs -- A/B/A at 10 M x 768,
+    // B = 32: 2.124 / 2.129 ms against 2.066 ms (profiles/r2_call35.log).  ss_screen = -1 (default) therefore
+    // screens when one scan streams >= 12 GB (break-even: 60 us against ~3 % of the scan) and nq > 16.
+    const long long scan_bytes = (long long)h->n_rows * h->dim * elem_size(h->dtype);
+    const bool want_screen = tu.ss_screen < 0 ? (nq > 16 && scan_bytes >= 12000000000LL) : tu.ss_screen != 0;
+    const bool screen = want_screen && k + spare_ranks(h) <= 32;
     const int kk = screen ? k + spare_ranks(h) : k;
     const int cands[4] = {128, 64, 32, 16};
     const int first = screen ? 2 : 0;  // screen mode keeps its lists in registers: <= 32 queries per CTA

@@ -131,6 +131,24 @@ class FlatShard:
         N.check(N.lib().vqa_search_plan(self._h, n_queries, k, mode_id(mode), ctypes.byref(fam), ctypes.byref(nl)))
         return fam.value, nl.value
 
+    def describe(self, n_queries: int, k: int, mode="fast") -> dict:
+        """The planner's choice for this shard's shape and tuning (``vqa_plan_describe_tuned``): kernel family, queries
+        per CTA, ring geometry, and for the tcgen05 families whether the scan screens (``split == 0``: storage-precision
+        queries, ``kscan`` candidates kept, exact re-scoring in the reduce) or carries hi/lo query columns."""
+        props = torch.cuda.get_device_properties(self.device)
+        out = (ctypes.c_int32 * 16)()
+        smem = ctypes.c_size_t()
+        t = self.get_tuning()
+        N.check(N.lib().vqa_plan_describe_tuned(self.n, self.dim, _TORCH_TO_VQA[self.rows.dtype], n_queries, k,
+                                                mode_id(mode), props.multi_processor_count,
+                                                int(getattr(props, "shared_memory_per_block_optin", 232448)),
+                                                ctypes.byref(t), out, ctypes.byref(smem)))
+        keys = ("family", "pass_nq", "passes", "groups", "stages", "kps", "ncol", "split", "qs", "ks", "kscan", "k_out",
+                "rescore", "tmem_query_cols", "m64")
+        d = dict(zip(keys, list(out)))
+        d["smem"] = int(smem.value)
+        return d
+
     def workspace(self, n_queries: int, k: int, mode: int) -> torch.Tensor:
         """Scratch (candidate lists, thresholds) of one search, cached per (B, k, CUDA stream): searches issued
         on different streams run concurrently and must not share candidate buffers (include/vqa.h, threading).
