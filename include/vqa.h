@@ -76,8 +76,9 @@ typedef enum vqa_mode {
     /* fp32 arithmetic in the canonical FMA / butterfly order:
      * ids bit-identical to the CPU oracle, works for fp32 / bf16 / fp16 rows. */
     VQA_MODE_VERIFY = 0,
-    /* free summation order; engine picks the HBM-streaming CUDA-core kernel
-     * (small batches) or the tcgen05/TMEM tensor-core kernel (large batches). */
+    /* free summation order; the engine picks the kernel family by row type, batch and k: for 16-bit rows with
+     * dim % 64 == 0 one of the tcgen05 kernels (queries in shared memory up to 32, in tensor memory beyond, CTA pairs
+     * beyond 128), otherwise the HBM-streaming CUDA-core kernel (vqa_search_plan). */
     VQA_MODE_FAST = 1,
     /* FAST, but force one kernel family (benchmarks / tests). */
     VQA_MODE_FAST_STREAM = 2,
